@@ -1,0 +1,670 @@
+// The drop-in C ABI (include/chowdsp_fft.h, include/chowdsp_fft_b200.h): plan objects, the process-wide
+// device twiddle cache, the pointer-kind policy and the host-staging pipeline.  Replaces the reference's
+// dispatcher layer (/root/reference/chowdsp_fft.cpp:63-78, 232-452) and plan construction
+// (/root/reference/simd/chowdsp_fft_impl_common.hpp:162-228).  Never throws across the ABI, has no CPU
+// compute path: without a CUDA device plan creation fails and says so.
+#include <cmath>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <new>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/chowdsp_fft_b200.h"
+#include "dispatch.h"
+
+#define CFB_API __attribute__ ((visibility ("default")))
+
+namespace
+{
+using namespace cfb;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+thread_local char t_error[512] = "";
+
+int fail (int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start (ap, fmt);
+    vsnprintf (t_error, sizeof (t_error), fmt, ap);
+    va_end (ap);
+    if (getenv ("CHOWDSP_FFT_B200_QUIET") == nullptr)
+        fprintf (stderr, "chowdsp_fft_b200: %s\n", t_error);
+    return code;
+}
+int fail_cuda (cudaError_t e, const char* what)
+{
+    return fail (chowdsp::fft::FFT_B200_ECUDA, "%s: %s", what, cudaGetErrorString (e));
+}
+#define CFB_CUDA(call)                           \
+    do                                           \
+    {                                            \
+        const cudaError_t e__ = (call);          \
+        if (e__ != cudaSuccess)                  \
+            return fail_cuda (e__, #call);       \
+    } while (0)
+
+bool device_available()
+{
+    static const bool ok = []
+    {
+        int n = 0;
+        const cudaError_t e = cudaGetDeviceCount (&n);
+        if (e != cudaSuccess)
+            (void) cudaGetLastError(); // clear the sticky "no device" state
+        return e == cudaSuccess && n > 0;
+    }();
+    return ok;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device twiddle cache: one immutable table set per (device, complex length, needs-real-split);
+// owned by the process, shared by every plan (so pre-allocated handles never leak device memory).
+// ------------------------------------------------------------------------------------------------
+struct Tables
+{
+    float2* tw = nullptr;  // stage twiddles
+    float2* rtw = nullptr; // real split twiddles (real plans only)
+};
+
+std::mutex g_tables_mutex;
+std::map<uint64_t, Tables> g_tables;
+
+int get_tables (int device, int logM, bool real, Tables& out)
+{
+    const uint64_t key = ((uint64_t) device << 32) | ((uint64_t) logM << 1) | (real ? 1u : 0u);
+    std::lock_guard<std::mutex> lock (g_tables_mutex);
+    auto it = g_tables.find (key);
+    if (it != g_tables.end())
+    {
+        out = it->second;
+        return 0;
+    }
+    Tables t;
+    const int len = stage_twiddle_len (logM);
+    if (len < 0)
+        return fail (chowdsp::fft::FFT_B200_EINVAL, "no kernel for complex length 2^%d", logM);
+    std::vector<float2> host ((size_t) len + 1);
+    fill_stage_twiddles_rt (logM, host.data());
+    CFB_CUDA (cudaMalloc (&t.tw, sizeof (float2) * ((size_t) len + 1)));
+    CFB_CUDA (cudaMemcpy (t.tw, host.data(), sizeof (float2) * ((size_t) len + 1), cudaMemcpyHostToDevice));
+    if (real)
+    {
+        const int M = 1 << logM;
+        std::vector<float2> hr ((size_t) M / 2 + 1);
+        fill_real_twiddles (hr.data(), M);
+        CFB_CUDA (cudaMalloc (&t.rtw, sizeof (float2) * hr.size()));
+        CFB_CUDA (cudaMemcpy (t.rtw, hr.data(), sizeof (float2) * hr.size(), cudaMemcpyHostToDevice));
+    }
+    g_tables[key] = t;
+    out = t;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+constexpr uint64_t kMagic = 0x4346423230304642ull; // "CFB200FB"
+constexpr int kMaxDevices = 16;
+
+struct Plan
+{
+    uint64_t magic;
+    int N;
+    int is_complex;
+    int logM; // complex length handled by the kernel: log2 N (complex) or log2 N - 1 (real)
+    int logW; // unordered layout: 3 = 8-lane, 2 = 4-lane
+    int owns_memory;
+    int home_device;
+    Tables tables[kMaxDevices]; // filled lazily per device (guarded by g_tables_mutex through get_tables)
+    bool have[kMaxDevices];
+};
+
+int ilog2i (int v)
+{
+    int l = 0;
+    while ((1 << l) < v)
+        ++l;
+    return l;
+}
+
+// reference size rules: common.hpp:168-177 (+ AVX-then-SSE fallback, chowdsp_fft.cpp:262-273);
+// powers of two only (north star), one CTA-resident transform (<= 2^14 complex points).
+int choose_width (int N, bool is_complex, bool use_avx)
+{
+    if (N <= 0 || (N & (N - 1)) != 0)
+        return 0;
+    for (int W = use_avx ? 8 : 4; W >= 4; W /= 2)
+        if (N % (is_complex ? W * W : 2 * W * W) == 0)
+            return W;
+    return 0;
+}
+
+Plan* as_plan (void* setup)
+{
+    auto* p = static_cast<Plan*> (setup);
+    if (p == nullptr || (reinterpret_cast<uintptr_t> (p) & 7) != 0 || p->magic != kMagic)
+    {
+        fail (chowdsp::fft::FFT_B200_EINVAL, "invalid FFT setup handle %p", setup);
+        return nullptr;
+    }
+    return p;
+}
+
+int plan_tables (Plan* p, Tables& t)
+{
+    int dev = 0;
+    CFB_CUDA (cudaGetDevice (&dev));
+    if (dev < 0 || dev >= kMaxDevices)
+        return fail (chowdsp::fft::FFT_B200_EINVAL, "device index %d out of range", dev);
+    if (! p->have[dev])
+    {
+        Tables nt;
+        const int rc = get_tables (dev, p->logM, ! p->is_complex, nt);
+        if (rc != 0)
+            return rc;
+        std::lock_guard<std::mutex> lock (g_tables_mutex);
+        p->tables[dev] = nt;
+        p->have[dev] = true;
+    }
+    t = p->tables[dev];
+    return 0;
+}
+
+size_t reference_bytes (int N, bool is_complex) // sse:67-72 / avx:73-78: 2*Ncvec*W*4 + sizeof(FFT_Setup)
+{
+    return (size_t) N * (is_complex ? 8 : 4) + 96;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pointer classification and staging
+// ------------------------------------------------------------------------------------------------
+enum class Mem
+{
+    Device,  // device or managed: kernels use it directly
+    Pinned,  // page-locked host memory mapped into the device address space
+    Pageable // ordinary host memory
+};
+
+struct PtrInfo
+{
+    Mem kind;
+    const void* dev; // pointer a kernel may dereference (Device / Pinned)
+};
+
+PtrInfo classify (const void* p)
+{
+    cudaPointerAttributes a {};
+    if (cudaPointerGetAttributes (&a, p) != cudaSuccess)
+    {
+        (void) cudaGetLastError();
+        return { Mem::Pageable, nullptr };
+    }
+    switch (a.type)
+    {
+        case cudaMemoryTypeDevice:
+        case cudaMemoryTypeManaged: return { Mem::Device, a.devicePointer ? a.devicePointer : p };
+        case cudaMemoryTypeHost: return { a.devicePointer ? Mem::Pinned : Mem::Pageable, a.devicePointer };
+        default: return { Mem::Pageable, nullptr };
+    }
+}
+
+// per-thread staging: two lanes so H2D of chunk c+1, the kernel of chunk c and D2H of chunk c-1 overlap
+struct Staging
+{
+    cudaStream_t stream[2] = { nullptr, nullptr };
+    float* buf[2][3] = { { nullptr, nullptr, nullptr }, { nullptr, nullptr, nullptr } };
+    size_t cap[2][3] = { { 0, 0, 0 }, { 0, 0, 0 } };
+    int device = -1;
+
+    int ensure (int lane, int slot, size_t bytes)
+    {
+        int dev = 0;
+        CFB_CUDA (cudaGetDevice (&dev));
+        if (device != dev)
+        {
+            release();
+            device = dev;
+        }
+        if (stream[lane] == nullptr)
+            CFB_CUDA (cudaStreamCreateWithFlags (&stream[lane], cudaStreamNonBlocking));
+        if (cap[lane][slot] < bytes)
+        {
+            if (buf[lane][slot] != nullptr)
+            {
+                CFB_CUDA (cudaStreamSynchronize (stream[lane]));
+                CFB_CUDA (cudaFree (buf[lane][slot]));
+                buf[lane][slot] = nullptr;
+                cap[lane][slot] = 0;
+            }
+            const size_t want = bytes < (1u << 20) ? (1u << 20) : bytes;
+            CFB_CUDA (cudaMalloc (&buf[lane][slot], want));
+            cap[lane][slot] = want;
+        }
+        return 0;
+    }
+    void release()
+    {
+        for (int l = 0; l < 2; ++l)
+        {
+            for (int s = 0; s < 3; ++s)
+            {
+                if (buf[l][s] != nullptr)
+                    cudaFree (buf[l][s]);
+                buf[l][s] = nullptr;
+                cap[l][s] = 0;
+            }
+            if (stream[l] != nullptr)
+                cudaStreamDestroy (stream[l]);
+            stream[l] = nullptr;
+        }
+    }
+    ~Staging() { /* process teardown: the driver reclaims; avoid CUDA calls during static destruction */ }
+};
+thread_local Staging t_staging;
+
+constexpr size_t kZeroCopyBytes = 256 * 1024;     // pinned buffers up to this size are used in place
+constexpr size_t kChunkBytes = 32ull * 1024 * 1024; // host staging granularity per lane
+
+int kind_of (const Plan* p, int direction)
+{
+    if (p->is_complex)
+        return direction == chowdsp::fft::FFT_FORWARD ? C2C_FWD : C2C_BWD;
+    return direction == chowdsp::fft::FFT_FORWARD ? R2C : C2R;
+}
+
+int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inner, long long in_outer, long long in_inner, long long out_outer, long long out_inner, int direction, bool ordered, cudaStream_t stream)
+{
+    Tables t;
+    const int rc = plan_tables (p, t);
+    if (rc != 0)
+        return rc;
+    FftArgs a {};
+    a.in = in;
+    a.out = out;
+    a.in_inner = in_inner;
+    a.in_outer = in_outer;
+    a.out_inner = out_inner;
+    a.out_outer = out_outer;
+    a.inner = inner;
+    a.batch = outer * inner;
+    a.logW = p->logW;
+    a.tw = t.tw;
+    a.rtw = t.rtw;
+    const cudaError_t e = launch_fft (p->logM, kind_of (p, direction), ! ordered, a, stream);
+    if (e != cudaSuccess)
+        return fail_cuda (e, "fft kernel launch");
+    return 0;
+}
+
+// Host-resident batch: chunked H2D -> kernel -> D2H on two alternating lanes.
+int staged_transform (Plan* p, const float* in, float* out, int batch, long long in_stride, long long out_stride, int direction, bool ordered)
+{
+    const long long nfl = p->is_complex ? 2LL * p->N : p->N;
+    if (batch > 1 && (in_stride < nfl || out_stride < nfl))
+        return fail (chowdsp::fft::FFT_B200_EINVAL, "host-memory batches need non-overlapping strides >= %lld floats", nfl);
+    // rows are copied with their stride (2-D copy) and packed densely on the device
+    const size_t row_bytes = (size_t) nfl * sizeof (float);
+    int per_chunk = (int) (kChunkBytes / row_bytes);
+    if (per_chunk < 1)
+        per_chunk = 1;
+    int lane = 0;
+    for (int b0 = 0; b0 < batch; b0 += per_chunk, lane ^= 1)
+    {
+        const int nb = batch - b0 < per_chunk ? batch - b0 : per_chunk;
+        Staging& s = t_staging;
+        int rc = s.ensure (lane, 0, row_bytes * (size_t) nb);
+        if (rc == 0)
+            rc = s.ensure (lane, 1, row_bytes * (size_t) nb);
+        if (rc != 0)
+            return rc;
+        cudaStream_t st = s.stream[lane];
+        CFB_CUDA (cudaMemcpy2DAsync (s.buf[lane][0], row_bytes, in + (long long) b0 * in_stride, (size_t) (batch > 1 ? in_stride : nfl) * sizeof (float), row_bytes, (size_t) nb, cudaMemcpyHostToDevice, st));
+        rc = enqueue_transform (p, s.buf[lane][0], s.buf[lane][1], 1, nb, 0, nfl, 0, nfl, direction, ordered, st);
+        if (rc != 0)
+            return rc;
+        CFB_CUDA (cudaMemcpy2DAsync (out + (long long) b0 * out_stride, (size_t) (batch > 1 ? out_stride : nfl) * sizeof (float), s.buf[lane][1], row_bytes, row_bytes, (size_t) nb, cudaMemcpyDeviceToHost, st));
+    }
+    for (int l = 0; l < 2; ++l)
+        if (t_staging.stream[l] != nullptr)
+            CFB_CUDA (cudaStreamSynchronize (t_staging.stream[l]));
+    return 0;
+}
+
+// shared front end of fft_transform / fft_transform_unordered / fft_transform_batched
+int transform_any (void* setup, const float* in, float* out, int batch, long long in_stride, long long out_stride, int direction, bool ordered, cudaStream_t stream, bool force_sync)
+{
+    Plan* p = as_plan (setup);
+    if (p == nullptr)
+        return chowdsp::fft::FFT_B200_EINVAL;
+    if (in == nullptr || out == nullptr || batch < 0)
+        return fail (chowdsp::fft::FFT_B200_EINVAL, "null buffer or negative batch");
+    if (batch == 0)
+        return 0;
+    const long long nfl = p->is_complex ? 2LL * p->N : p->N;
+    const PtrInfo pi = classify (in), po = classify (out);
+    const bool in_dev = pi.kind == Mem::Device, out_dev = po.kind == Mem::Device;
+    if (in_dev != out_dev)
+        return fail (chowdsp::fft::FFT_B200_EINVAL, "input and output must both be device memory or both be host memory");
+    if (in_dev)
+    {
+        const int rc = enqueue_transform (p, static_cast<const float*> (pi.dev), static_cast<float*> (const_cast<void*> (po.dev)), 1, batch, 0, in_stride, 0, out_stride, direction, ordered, stream);
+        if (rc != 0)
+            return rc;
+        if (force_sync)
+            CFB_CUDA (cudaStreamSynchronize (stream));
+        return 0;
+    }
+    // host memory
+    const size_t span_in = (size_t) ((batch - 1) * in_stride + nfl) * sizeof (float);
+    const size_t span_out = (size_t) ((batch - 1) * out_stride + nfl) * sizeof (float);
+    if (pi.kind == Mem::Pinned && po.kind == Mem::Pinned && span_in <= kZeroCopyBytes && span_out <= kZeroCopyBytes)
+    {
+        // zero-copy: the kernel reads / writes the mapped host buffers over PCIe, one launch, one sync
+        cudaStream_t st = cudaStreamPerThread;
+        const int rc = enqueue_transform (p, static_cast<const float*> (pi.dev), static_cast<float*> (const_cast<void*> (po.dev)), 1, batch, 0, in_stride, 0, out_stride, direction, ordered, st);
+        if (rc != 0)
+            return rc;
+        CFB_CUDA (cudaStreamSynchronize (st));
+        return 0;
+    }
+    return staged_transform (p, in, out, batch, in_stride, out_stride, direction, ordered);
+}
+
+// elementwise front end (convolve / accumulate): operands a, b (read) and ab (read-modify-write)
+int elementwise_any (Plan* p, bool convolve, const float* a, const float* b, float* ab, int batch, long long a_stride, long long b_stride, long long ab_stride, long long nfl, float scaling, cudaStream_t stream, bool force_sync)
+{
+    if (a == nullptr || b == nullptr || ab == nullptr || batch < 0)
+        return fail (chowdsp::fft::FFT_B200_EINVAL, "null buffer or negative batch");
+    if (batch == 0 || nfl == 0)
+        return 0;
+    const PtrInfo ia = classify (a), ib = classify (b), iab = classify (ab);
+    const bool all_dev = ia.kind == Mem::Device && ib.kind == Mem::Device && iab.kind == Mem::Device;
+    const bool any_dev = ia.kind == Mem::Device || ib.kind == Mem::Device || iab.kind == Mem::Device;
+    if (any_dev && ! all_dev)
+        return fail (chowdsp::fft::FFT_B200_EINVAL, "operands must all be device memory or all be host memory");
+    auto run = [&] (const float* da, const float* db, float* dab, long long sa, long long sb, long long sab, cudaStream_t st) -> int
+    {
+        const cudaError_t e = convolve
+                                  ? launch_convolve (da, db, dab, sa, sb, sab, (int) nfl, batch, p->logW, ! p->is_complex, scaling, st)
+                                  : launch_accumulate (da, db, dab, nfl, st);
+        return e == cudaSuccess ? 0 : fail_cuda (e, "elementwise kernel launch");
+    };
+    if (all_dev)
+    {
+        const int rc = run (static_cast<const float*> (ia.dev), static_cast<const float*> (ib.dev), static_cast<float*> (const_cast<void*> (iab.dev)), a_stride, b_stride, ab_stride, stream);
+        if (rc != 0)
+            return rc;
+        if (force_sync)
+            CFB_CUDA (cudaStreamSynchronize (stream));
+        return 0;
+    }
+    const size_t bytes_a = (size_t) ((batch - 1) * a_stride + nfl) * sizeof (float);
+    const size_t bytes_b = (size_t) ((batch - 1) * b_stride + nfl) * sizeof (float);
+    const size_t bytes_ab = (size_t) ((batch - 1) * ab_stride + nfl) * sizeof (float);
+    const bool all_pinned = ia.kind == Mem::Pinned && ib.kind == Mem::Pinned && iab.kind == Mem::Pinned;
+    if (all_pinned && bytes_a <= kZeroCopyBytes && bytes_b <= kZeroCopyBytes && bytes_ab <= kZeroCopyBytes)
+    {
+        cudaStream_t st = cudaStreamPerThread;
+        const int rc = run (static_cast<const float*> (ia.dev), static_cast<const float*> (ib.dev), static_cast<float*> (const_cast<void*> (iab.dev)), a_stride, b_stride, ab_stride, st);
+        if (rc != 0)
+            return rc;
+        CFB_CUDA (cudaStreamSynchronize (st));
+        return 0;
+    }
+    // staged: whole operands through lane 0 (aliasing between host operands is preserved by copying
+    // each one separately and writing only ab back)
+    Staging& s = t_staging;
+    int rc = s.ensure (0, 0, bytes_a);
+    if (rc == 0)
+        rc = s.ensure (0, 1, bytes_b);
+    if (rc == 0)
+        rc = s.ensure (0, 2, bytes_ab);
+    if (rc != 0)
+        return rc;
+    cudaStream_t st = s.stream[0];
+    CFB_CUDA (cudaMemcpyAsync (s.buf[0][0], a, bytes_a, cudaMemcpyHostToDevice, st));
+    CFB_CUDA (cudaMemcpyAsync (s.buf[0][1], b, bytes_b, cudaMemcpyHostToDevice, st));
+    CFB_CUDA (cudaMemcpyAsync (s.buf[0][2], ab, bytes_ab, cudaMemcpyHostToDevice, st));
+    rc = run (s.buf[0][0], s.buf[0][1], s.buf[0][2], a_stride, b_stride, ab_stride, st);
+    if (rc != 0)
+        return rc;
+    CFB_CUDA (cudaMemcpyAsync (ab, s.buf[0][2], bytes_ab, cudaMemcpyDeviceToHost, st));
+    CFB_CUDA (cudaStreamSynchronize (st));
+    return 0;
+}
+
+// registry of aligned_malloc blocks: pinned (cudaHostAlloc) vs plain (posix_memalign)
+std::mutex g_alloc_mutex;
+std::unordered_map<void*, bool> g_allocs; // ptr -> is_pinned
+} // namespace
+
+// ------------------------------------------------------------------------------------------------
+// exported C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C"
+{
+namespace chowdsp::fft
+{
+CFB_API size_t fft_bytes_required (int N, fft_transform_t transform, bool)
+{
+    const size_t ref = reference_bytes (N > 0 ? N : 0, transform == FFT_COMPLEX);
+    return ref > sizeof (Plan) + 64 ? ref : sizeof (Plan) + 64;
+}
+
+CFB_API void* fft_new_setup_preallocated (int N, fft_transform_t transform, void* data, bool use_avx_if_available)
+{
+    if (data == nullptr)
+    {
+        fail (FFT_B200_EINVAL, "fft_new_setup_preallocated: null data block");
+        return nullptr;
+    }
+    const bool is_complex = transform == FFT_COMPLEX;
+    const int W = choose_width (N, is_complex, use_avx_if_available);
+    const int logM = W == 0 ? -1 : ilog2i (N) - (is_complex ? 0 : 1);
+    if (W == 0 || logM < kMinLogM || logM > kMaxLogM)
+    {
+        fail (FFT_B200_EINVAL, "unsupported FFT size N=%d (%s): need a power of two, %s", N, is_complex ? "complex" : "real", is_complex ? "16 <= N <= 16384" : "32 <= N <= 32768");
+        return nullptr;
+    }
+    if (! device_available())
+    {
+        fail (FFT_B200_ENODEVICE, "no usable CUDA device: chowdsp_fft_b200 has no CPU fallback");
+        return nullptr;
+    }
+    auto* p = reinterpret_cast<Plan*> ((reinterpret_cast<uintptr_t> (data) + 7) & ~static_cast<uintptr_t> (7));
+    std::memset (p, 0, sizeof (Plan));
+    p->N = N;
+    p->is_complex = is_complex ? 1 : 0;
+    p->logM = logM;
+    p->logW = W == 8 ? 3 : 2;
+    p->owns_memory = 0;
+    p->magic = kMagic;
+    if (cudaGetDevice (&p->home_device) != cudaSuccess)
+    {
+        fail (FFT_B200_ECUDA, "cudaGetDevice failed");
+        return nullptr;
+    }
+    Tables t;
+    if (plan_tables (p, t) != 0)
+    {
+        p->magic = 0;
+        return nullptr;
+    }
+    return p;
+}
+
+CFB_API void* fft_new_setup (int N, fft_transform_t transform, bool use_avx_if_available)
+{
+    void* block = std::malloc (sizeof (Plan) + 64);
+    if (block == nullptr)
+        return nullptr;
+    void* p = fft_new_setup_preallocated (N, transform, block, use_avx_if_available);
+    if (p == nullptr)
+    {
+        std::free (block);
+        return nullptr;
+    }
+    auto* plan = static_cast<Plan*> (p);
+    plan->owns_memory = 1;
+    // remember the malloc'd base right behind the plan (the block has 64 spare bytes)
+    std::memcpy (reinterpret_cast<char*> (plan) + sizeof (Plan), &block, sizeof (void*));
+    return p;
+}
+
+CFB_API void fft_destroy_setup (void* setup)
+{
+    if (setup == nullptr)
+        return;
+    Plan* p = as_plan (setup);
+    if (p == nullptr)
+        return;
+    p->magic = 0;
+    if (p->owns_memory)
+    {
+        void* block = nullptr;
+        std::memcpy (&block, reinterpret_cast<char*> (p) + sizeof (Plan), sizeof (void*));
+        std::free (block);
+    }
+}
+
+CFB_API int fft_simd_width_bytes (void* setup)
+{
+    Plan* p = as_plan (setup);
+    return p == nullptr ? 0 : (p->logW == 3 ? 32 : 16);
+}
+
+CFB_API void fft_transform (void* setup, const float* input, float* output, float*, fft_direction_t direction)
+{
+    const Plan* p = static_cast<const Plan*> (setup);
+    const long long nfl = (p != nullptr && p->magic == kMagic) ? (p->is_complex ? 2LL * p->N : p->N) : 0;
+    (void) transform_any (setup, input, output, 1, nfl, nfl, direction, true, cudaStreamPerThread, true);
+}
+
+CFB_API void fft_transform_unordered (void* setup, const float* input, float* output, float*, fft_direction_t direction)
+{
+    const Plan* p = static_cast<const Plan*> (setup);
+    const long long nfl = (p != nullptr && p->magic == kMagic) ? (p->is_complex ? 2LL * p->N : p->N) : 0;
+    (void) transform_any (setup, input, output, 1, nfl, nfl, direction, false, cudaStreamPerThread, true);
+}
+
+CFB_API void fft_convolve_unordered (void* setup, const float* a, const float* b, float* ab, float scaling)
+{
+    Plan* p = as_plan (setup);
+    if (p == nullptr)
+        return;
+    const long long nfl = p->is_complex ? 2LL * p->N : p->N;
+    (void) elementwise_any (p, true, a, b, ab, 1, nfl, nfl, nfl, nfl, scaling, cudaStreamPerThread, true);
+}
+
+CFB_API void fft_accumulate (void* setup, const float* a, const float* b, float* ab, int N)
+{
+    Plan* p = as_plan (setup);
+    if (p == nullptr)
+        return;
+    if (N < 0 || N % 8 != 0)
+    {
+        fail (FFT_B200_EINVAL, "fft_accumulate: N=%d must be a non-negative multiple of 8", N);
+        return;
+    }
+    (void) elementwise_any (p, false, a, b, ab, 1, N, N, N, N, 0.f, cudaStreamPerThread, true);
+}
+
+CFB_API void* aligned_malloc (size_t nb_bytes)
+{
+    void* p = nullptr;
+    bool pinned = false;
+    if (device_available())
+    {
+        if (cudaHostAlloc (&p, nb_bytes > 0 ? nb_bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped) == cudaSuccess)
+            pinned = true;
+        else
+        {
+            (void) cudaGetLastError();
+            p = nullptr;
+        }
+    }
+    if (p == nullptr && posix_memalign (&p, 64, nb_bytes > 0 ? nb_bytes : 1) != 0)
+        return nullptr;
+    std::lock_guard<std::mutex> lock (g_alloc_mutex);
+    g_allocs[p] = pinned;
+    return p;
+}
+
+CFB_API void aligned_free (void* p)
+{
+    if (p == nullptr)
+        return;
+    bool pinned = false, known = false;
+    {
+        std::lock_guard<std::mutex> lock (g_alloc_mutex);
+        auto it = g_allocs.find (p);
+        if (it != g_allocs.end())
+        {
+            pinned = it->second;
+            known = true;
+            g_allocs.erase (it);
+        }
+    }
+    if (! known)
+    {
+        fail (FFT_B200_EINVAL, "aligned_free: %p was not returned by aligned_malloc", p);
+        return;
+    }
+    if (pinned)
+        cudaFreeHost (p);
+    else
+        std::free (p);
+}
+
+// ---- extensions (chowdsp_fft_b200.h) -----------------------------------------------------------
+CFB_API int fft_transform_batched (void* setup, const float* input, float* output, int batch, long long in_stride, long long out_stride, fft_direction_t direction, int ordered, void* stream)
+{
+    return transform_any (setup, input, output, batch, in_stride, out_stride, direction, ordered != 0, static_cast<cudaStream_t> (stream), false);
+}
+
+CFB_API int fft_transform_strided (void* setup, const float* input, float* output, int outer, int inner, long long in_outer, long long in_inner, long long out_outer, long long out_inner, fft_direction_t direction, int ordered, void* stream)
+{
+    Plan* p = as_plan (setup);
+    if (p == nullptr)
+        return FFT_B200_EINVAL;
+    if (input == nullptr || output == nullptr || outer < 0 || inner < 0 || (long long) outer * inner > 0x7fffffffLL)
+        return fail (FFT_B200_EINVAL, "fft_transform_strided: bad arguments");
+    if (outer == 0 || inner == 0)
+        return 0;
+    if (classify (input).kind != Mem::Device || classify (output).kind != Mem::Device)
+        return fail (FFT_B200_EINVAL, "fft_transform_strided needs device pointers");
+    return enqueue_transform (p, input, output, outer, inner, in_outer, in_inner, out_outer, out_inner, direction, ordered != 0, static_cast<cudaStream_t> (stream));
+}
+
+CFB_API int fft_convolve_unordered_batched (void* setup, const float* a, const float* b, float* ab, int batch, long long a_stride, long long b_stride, long long ab_stride, float scaling, void* stream)
+{
+    Plan* p = as_plan (setup);
+    if (p == nullptr)
+        return FFT_B200_EINVAL;
+    const long long nfl = p->is_complex ? 2LL * p->N : p->N;
+    return elementwise_any (p, true, a, b, ab, batch, a_stride, b_stride, ab_stride, nfl, scaling, static_cast<cudaStream_t> (stream), false);
+}
+
+CFB_API int fft_accumulate_batched (void* setup, const float* a, const float* b, float* ab, long long n, void* stream)
+{
+    Plan* p = as_plan (setup);
+    if (p == nullptr)
+        return FFT_B200_EINVAL;
+    if (n < 0 || n % 8 != 0)
+        return fail (FFT_B200_EINVAL, "fft_accumulate_batched: n must be a non-negative multiple of 8");
+    return elementwise_any (p, false, a, b, ab, 1, n, n, n, n, 0.f, static_cast<cudaStream_t> (stream), false);
+}
+
+CFB_API const char* fft_b200_last_error (void) { return t_error; }
+CFB_API unsigned long long fft_b200_launch_count (void) { return cfb::launch_count(); }
+CFB_API int fft_b200_device_available (void) { return device_available() ? 1 : 0; }
+} // namespace chowdsp::fft
+}

@@ -1,0 +1,79 @@
+// Runtime size dispatch + the elementwise (unordered-domain) kernels.
+#include <atomic>
+
+#include "dispatch.h"
+#include "elementwise_kernels.cuh"
+
+namespace cfb
+{
+namespace
+{
+std::atomic<unsigned long long> g_launches { 0 };
+}
+unsigned long long launch_count() { return g_launches.load (std::memory_order_relaxed); }
+void count_launch() { g_launches.fetch_add (1, std::memory_order_relaxed); }
+
+#define CFB_FOR_SIZES(X) X (4) X (5) X (6) X (7) X (8) X (9) X (10) X (11) X (12) X (13) X (14)
+
+cudaError_t launch_fft (int logM, int kind, bool unordered, const FftArgs& args, cudaStream_t stream)
+{
+    switch (logM)
+    {
+#define X(n) \
+    case n: return launch_fft_##n (kind, unordered, args, stream);
+        CFB_FOR_SIZES (X)
+#undef X
+        default: return cudaErrorInvalidValue;
+    }
+}
+int stage_twiddle_len (int logM)
+{
+    switch (logM)
+    {
+#define X(n) \
+    case n: return stage_twiddle_len_##n();
+        CFB_FOR_SIZES (X)
+#undef X
+        default: return -1;
+    }
+}
+void fill_stage_twiddles_rt (int logM, float2* tw)
+{
+    switch (logM)
+    {
+#define X(n) \
+    case n: fill_stage_twiddles_##n (tw); return;
+        CFB_FOR_SIZES (X)
+#undef X
+        default: return;
+    }
+}
+
+static int elementwise_grid (long long items, int threads)
+{
+    // enough CTAs to fill 148 SMs x 8 resident CTAs, grid-stride beyond that
+    const long long want = (items + threads - 1) / threads;
+    const long long cap = 148LL * 8 * 4;
+    return (int) (want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+cudaError_t launch_convolve (const float* a, const float* b, float* ab, long long a_stride, long long b_stride, long long ab_stride, int nfloats, int batch, int logW, bool is_real, float scaling, cudaStream_t stream)
+{
+    if (batch <= 0)
+        return cudaSuccess;
+    const ConvArgs p { a, b, ab, a_stride, b_stride, ab_stride, nfloats, batch, logW, is_real ? 1 : 0, scaling };
+    const long long items = (long long) (nfloats >> 3) * batch;
+    convolve_kernel<<<elementwise_grid (items, 256), 256, 0, stream>>> (p);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_accumulate (const float* a, const float* b, float* ab, long long n, cudaStream_t stream)
+{
+    if (n <= 0)
+        return cudaSuccess;
+    accumulate_kernel<<<elementwise_grid (n / 4, 256), 256, 0, stream>>> (a, b, ab, n / 4);
+    count_launch();
+    return cudaGetLastError();
+}
+} // namespace cfb

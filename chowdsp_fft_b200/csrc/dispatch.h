@@ -1,0 +1,43 @@
+// Host-side launch interface between the plan / C-ABI layer and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "fft_kernels.cuh"
+
+namespace cfb
+{
+constexpr int kMinLogM = 4;  // 16 complex points per CTA-resident transform
+constexpr int kMaxLogM = 14; // 16384 complex points: the largest single-kernel transform
+constexpr int kRadix = 16;   // complex points per thread
+
+// One launch of the single-kernel transform (complex length 2^logM per transform).
+cudaError_t launch_fft (int logM, int kind, bool unordered, const FftArgs& args, cudaStream_t stream);
+// number of float2 entries of the stage twiddle table for 2^logM, and the fill routine (fp64 -> fp32)
+int stage_twiddle_len (int logM);
+void fill_stage_twiddles_rt (int logM, float2* tw);
+
+cudaError_t launch_convolve (const float* a, const float* b, float* ab, long long a_stride, long long b_stride, long long ab_stride, int nfloats, int batch, int logW, bool is_real, float scaling, cudaStream_t stream);
+cudaError_t launch_accumulate (const float* a, const float* b, float* ab, long long n, cudaStream_t stream);
+
+// every kernel launch made by this library bumps this counter (bench.py reports it as gpu_launches)
+unsigned long long launch_count();
+void count_launch();
+
+// per-size entry points, one translation unit each (fft_inst.cu compiled with -DCFB_LOGM=n)
+#define CFB_DECL_INST(n)                                                                       \
+    cudaError_t launch_fft_##n (int kind, bool unordered, const FftArgs& args, cudaStream_t stream); \
+    int stage_twiddle_len_##n();                                                               \
+    void fill_stage_twiddles_##n (float2* tw);
+CFB_DECL_INST (4)
+CFB_DECL_INST (5)
+CFB_DECL_INST (6)
+CFB_DECL_INST (7)
+CFB_DECL_INST (8)
+CFB_DECL_INST (9)
+CFB_DECL_INST (10)
+CFB_DECL_INST (11)
+CFB_DECL_INST (12)
+CFB_DECL_INST (13)
+CFB_DECL_INST (14)
+#undef CFB_DECL_INST
+} // namespace cfb

@@ -1,0 +1,63 @@
+/*
+ * B200 extensions to the chowdsp_fft C API: batched, stream-ordered entry points with no analogue in
+ * the reference (one reference call = one transform on the calling thread,
+ * /root/reference/chowdsp_fft.cpp:318-432).  Semantics of every batched call: bit-for-bit what a loop
+ * of `batch` single calls of the matching chowdsp_fft.h function would produce.
+ *
+ * Plain C ABI: pointers, sizes and an opaque `void* stream` (a cudaStream_t; NULL = the legacy default
+ * stream).  All functions return 0 on success or a negative FFT_B200_E* code; fft_b200_last_error()
+ * gives the text for the calling thread's last failure.
+ *
+ * Pointer policy: when every data pointer is device (or managed) memory the call only enqueues work on
+ * `stream` and returns.  When the data pointers are host memory the call stages chunks through the
+ * device on internal streams (H2D, transform, D2H overlapped) and returns after the result is in the
+ * host buffer.  Mixing host and device data pointers in one call is rejected.
+ */
+#pragma once
+#include "chowdsp_fft.h"
+
+#ifdef __cplusplus
+extern "C"
+{
+namespace chowdsp::fft
+{
+#endif
+
+enum
+{
+    FFT_B200_OK = 0,
+    FFT_B200_EINVAL = -1,   /* bad handle / argument */
+    FFT_B200_ECUDA = -2,    /* CUDA runtime error, see fft_b200_last_error() */
+    FFT_B200_ENODEVICE = -3 /* no usable CUDA device: there is no CPU fallback */
+};
+
+/* `batch` transforms; transform b reads input + b*in_stride and writes output + b*out_stride (strides in
+   floats).  ordered != 0 behaves like fft_transform, 0 like fft_transform_unordered.
+   Replaces a loop over reference chowdsp_fft.h:138 / :145. */
+int fft_transform_batched (void* setup, const float* input, float* output, int batch, long long in_stride, long long out_stride, fft_direction_t direction, int ordered, void* stream);
+
+/* Two-level batch: transform (o, i), o < outer, i < inner, reads input + o*in_outer + i*in_inner and
+   writes output + o*out_outer + i*out_inner.  Input windows may overlap (STFT frame gather:
+   in_inner = hop, in_outer = channel stride); outputs must not.  Device pointers only. */
+int fft_transform_strided (void* setup, const float* input, float* output, int outer, int inner, long long in_outer, long long in_inner, long long out_outer, long long out_inner, fft_direction_t direction, int ordered, void* stream);
+
+/* batch x (ab += a*b*scaling) on unordered spectra; a stride of 0 shares that operand across the
+   batch (e.g. one impulse response for all channels).  Replaces a loop over reference chowdsp_fft.h:154. */
+int fft_convolve_unordered_batched (void* setup, const float* dft_a, const float* dft_b, float* dft_ab, int batch, long long a_stride, long long b_stride, long long ab_stride, float scaling, void* stream);
+
+/* ab[i] = a[i] + b[i] for n floats (n % 8 == 0), stream-ordered.  Reference chowdsp_fft.h:160. */
+int fft_accumulate_batched (void* setup, const float* a, const float* b, float* ab, long long n, void* stream);
+
+/* Text of the calling thread's most recent failure ("" if none). */
+const char* fft_b200_last_error (void);
+
+/* Number of CUDA kernels this library has launched in this process (all threads). */
+unsigned long long fft_b200_launch_count (void);
+
+/* 1 if a CUDA device is usable from this process, else 0. */
+int fft_b200_device_available (void);
+
+#ifdef __cplusplus
+}
+} // namespace chowdsp::fft
+#endif

@@ -1,0 +1,151 @@
+// TEST INFRASTRUCTURE ONLY -- host shim that lets chowdsp_fft_b200/csrc/*.cuh compile with plain g++.
+//
+// There is no GPU in the build container, so index maps, twiddle tables, layouts and shared-memory
+// bank behaviour of the CUDA kernels are pre-validated here: every CUDA thread of a block becomes one
+// OS thread, __syncthreads() is a std::barrier, dynamic shared memory is a heap block.  The kernels'
+// source is compiled UNCHANGED (-DCHOWDSP_EMU).  This is a checker for the kernel source, not a CPU
+// implementation of the product: nothing under chowdsp_fft_b200/ builds, links or loads it, and the
+// shipped library has no CPU path.
+#pragma once
+#include <algorithm>
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <thread>
+#include <vector>
+
+struct float2 { float x, y; };
+struct alignas (16) float4 { float x, y, z, w; };
+static inline float2 make_float2 (float x, float y) { return float2 { x, y }; }
+static inline float4 make_float4 (float x, float y, float z, float w) { return float4 { x, y, z, w }; }
+struct dim3
+{
+    unsigned x = 1, y = 1, z = 1;
+    dim3 (unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x (x_), y (y_), z (z_) {}
+};
+typedef void* cudaStream_t;
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+
+namespace emu
+{
+struct SmemOp { uint32_t off; uint8_t bytes; uint8_t is_store; };
+struct ThreadCtx
+{
+    dim3 tIdx, bIdx, bDim, gDim;
+    std::barrier<>* bar = nullptr;
+    char* smem = nullptr;
+    std::vector<SmemOp>* log = nullptr; // per-thread smem op sequence (bank-conflict analysis)
+};
+inline thread_local ThreadCtx ctx;
+
+struct ConflictStats
+{
+    long ops = 0;           // warp-level shared-memory instructions
+    long wavefronts = 0;    // modelled wavefronts
+    long ideal = 0;         // wavefronts with zero conflicts
+    int worst = 0;          // worst wavefronts/ideal ratio seen (x100)
+};
+inline ConflictStats g_stats;
+inline bool g_log_smem = false;
+
+// wavefront model: an access of 32 lanes costs max over the 32 banks of the number of DISTINCT 4-byte
+// words requested in that bank (same-word requests broadcast).
+inline void analyse_block (std::vector<std::vector<SmemOp>>& logs)
+{
+    const size_t nthreads = logs.size();
+    for (size_t w0 = 0; w0 < nthreads; w0 += 32)
+    {
+        const size_t w1 = std::min (nthreads, w0 + 32);
+        const size_t nops = logs[w0].size();
+        for (size_t t = w0; t < w1; ++t)
+            if (logs[t].size() != nops)
+            {
+                std::fprintf (stderr, "emu: divergent smem op count inside a warp (%zu vs %zu)\n", logs[t].size(), nops);
+                std::abort();
+            }
+        for (size_t i = 0; i < nops; ++i)
+        {
+            std::vector<uint32_t> words[32];
+            int bytes = 0;
+            for (size_t t = w0; t < w1; ++t)
+            {
+                const SmemOp& op = logs[t][i];
+                if (op.bytes == 0)
+                    continue; // predicated off
+                bytes = std::max<int> (bytes, op.bytes);
+                for (uint32_t b = 0; b < op.bytes; b += 4)
+                {
+                    const uint32_t word = (op.off + b) / 4;
+                    auto& v = words[word % 32];
+                    if (std::find (v.begin(), v.end(), word) == v.end())
+                        v.push_back (word);
+                }
+            }
+            if (bytes == 0)
+                continue;
+            int wf = 0;
+            size_t total_words = 0;
+            for (auto& v : words)
+            {
+                wf = std::max<int> (wf, (int) v.size());
+                total_words += v.size();
+            }
+            const int ideal = std::max<int> (1, (int) ((total_words + 31) / 32));
+            g_stats.ops++;
+            g_stats.wavefronts += wf;
+            g_stats.ideal += ideal;
+            g_stats.worst = std::max (g_stats.worst, wf * 100 / ideal);
+        }
+    }
+}
+
+template <typename Kernel, typename... Args>
+void launch (Kernel kernel, dim3 grid, dim3 block, size_t smem_bytes, Args... args)
+{
+    const unsigned nthreads = block.x * block.y * block.z;
+    for (unsigned bx = 0; bx < grid.x; ++bx)
+    {
+        std::vector<char> smem (smem_bytes + 64);
+        std::barrier<> bar ((std::ptrdiff_t) nthreads);
+        std::vector<std::vector<SmemOp>> logs (nthreads);
+        std::vector<std::thread> pool;
+        pool.reserve (nthreads);
+        for (unsigned t = 0; t < nthreads; ++t)
+            pool.emplace_back ([&, t]
+                               {
+                                   ctx.tIdx = dim3 (t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+                                   ctx.bIdx = dim3 (bx, 0, 0);
+                                   ctx.bDim = block;
+                                   ctx.gDim = grid;
+                                   ctx.bar = &bar;
+                                   ctx.smem = smem.data();
+                                   ctx.log = g_log_smem ? &logs[t] : nullptr;
+                                   kernel (args...);
+                               });
+        for (auto& th : pool)
+            th.join();
+        if (g_log_smem)
+            analyse_block (logs);
+    }
+}
+} // namespace emu
+
+#define threadIdx (emu::ctx.tIdx)
+#define blockIdx (emu::ctx.bIdx)
+#define blockDim (emu::ctx.bDim)
+#define gridDim (emu::ctx.gDim)
+static inline void __syncthreads() { emu::ctx.bar->arrive_and_wait(); }
+template <typename T>
+static inline T __ldg (const T* p) { return *p; }
+static inline float __fmaf_rn (float a, float b, float c) { return std::fmaf (a, b, c); }

@@ -1,0 +1,101 @@
+// TEST INFRASTRUCTURE ONLY -- runs the CUDA kernel source on the host through cuda_emu.h so that the
+// index maps, twiddle tables, layouts and bank-conflict behaviour can be checked without a GPU
+// (tests/test_emu_kernels.py, `-m "not gpu"`).  Not part of the product; never loaded by the package.
+#define CHOWDSP_EMU 1
+#include "fft_kernels.cuh"
+#include "elementwise_kernels.cuh"
+
+using namespace cfb;
+
+namespace
+{
+template <int LOGM, int KIND, bool UNORD>
+int run_one (FftArgs a)
+{
+    constexpr int R = 16;
+    using G = Geo<LOGM, R>;
+    using L = Launch<LOGM, R>;
+    std::vector<float2> tw ((size_t) G::TW_LEN + 1), rtw ((size_t) G::M / 2 + 1);
+    fill_stage_twiddles<LOGM, R> (tw.data());
+    fill_real_twiddles (rtw.data(), G::M);
+    a.tw = tw.data();
+    a.rtw = rtw.data();
+    const unsigned grid = (unsigned) ((a.batch + L::PER_CTA - 1) / L::PER_CTA);
+    emu::launch (fft_kernel<LOGM, R, KIND, UNORD>, dim3 (grid), dim3 (L::THREADS), (size_t) L::SMEM_BYTES, a);
+    return 0;
+}
+
+template <int LOGM>
+int run_logm (int kind, int unord, const FftArgs& a)
+{
+    switch (kind * 2 + (unord ? 1 : 0))
+    {
+        case 0: return run_one<LOGM, C2C_FWD, false> (a);
+        case 1: return run_one<LOGM, C2C_FWD, true> (a);
+        case 2: return run_one<LOGM, C2C_BWD, false> (a);
+        case 3: return run_one<LOGM, C2C_BWD, true> (a);
+        case 4: return run_one<LOGM, R2C, false> (a);
+        case 5: return run_one<LOGM, R2C, true> (a);
+        case 6: return run_one<LOGM, C2R, false> (a);
+        case 7: return run_one<LOGM, C2R, true> (a);
+    }
+    return -1;
+}
+} // namespace
+
+extern "C"
+{
+// logM = log2 of the COMPLEX length run by the CTA (N for C2C, N/2 for real transforms)
+int emu_fft (int logM, int kind, int unord, int logW, const float* in, float* out, int batch, int inner, long long in_inner, long long in_outer, long long out_inner, long long out_outer, int log_conflicts, long* stats /* ops, wavefronts, ideal, worst_x100 */)
+{
+    FftArgs a {};
+    a.in = in;
+    a.out = out;
+    a.in_inner = in_inner;
+    a.in_outer = in_outer;
+    a.out_inner = out_inner;
+    a.out_outer = out_outer;
+    a.inner = inner;
+    a.batch = batch;
+    a.logW = logW;
+    emu::g_log_smem = log_conflicts != 0;
+    emu::g_stats = {};
+    int rc = -1;
+    switch (logM)
+    {
+        case 4: rc = run_logm<4> (kind, unord, a); break;
+        case 5: rc = run_logm<5> (kind, unord, a); break;
+        case 6: rc = run_logm<6> (kind, unord, a); break;
+        case 7: rc = run_logm<7> (kind, unord, a); break;
+        case 8: rc = run_logm<8> (kind, unord, a); break;
+        case 9: rc = run_logm<9> (kind, unord, a); break;
+        case 10: rc = run_logm<10> (kind, unord, a); break;
+        case 11: rc = run_logm<11> (kind, unord, a); break;
+        case 12: rc = run_logm<12> (kind, unord, a); break;
+        case 13: rc = run_logm<13> (kind, unord, a); break;
+        case 14: rc = run_logm<14> (kind, unord, a); break;
+        default: break;
+    }
+    if (stats)
+    {
+        stats[0] = emu::g_stats.ops;
+        stats[1] = emu::g_stats.wavefronts;
+        stats[2] = emu::g_stats.ideal;
+        stats[3] = emu::g_stats.worst;
+    }
+    return rc;
+}
+
+int emu_convolve (const float* a, const float* b, float* ab, long long a_stride, long long b_stride, long long ab_stride, int nfloats, int batch, int logW, int is_real, float scaling)
+{
+    ConvArgs p { a, b, ab, a_stride, b_stride, ab_stride, nfloats, batch, logW, is_real, scaling };
+    emu::launch (convolve_kernel, dim3 (2), dim3 (64), 0, p);
+    return 0;
+}
+
+int emu_accumulate (const float* a, const float* b, float* ab, long long n)
+{
+    emu::launch (accumulate_kernel, dim3 (2), dim3 (64), 0, a, b, ab, n / 4);
+    return 0;
+}
+}
