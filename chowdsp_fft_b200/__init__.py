@@ -1,0 +1,13 @@
+"""chowdsp_fft_b200 -- B200-native (sm_100a) engine behind the chowdsp_fft C API.
+
+The product is the C-ABI shared library ``chowdsp_fft_b200/lib/libchowdsp_fft_b200.so`` (headers in
+``include/``); this package is the thin host-side mirror of the reference's interface used by the
+tests and the benchmark.  No CPU fallback exists.
+"""
+from .api import (FFT_BACKWARD, FFT_COMPLEX, FFT_FORWARD, FFT_REAL, FFTError, aligned_array, aligned_free,
+                  aligned_malloc, device_available, fft_accumulate, fft_accumulate_batched, fft_bytes_required,
+                  fft_convolve_unordered, fft_convolve_unordered_batched, fft_destroy_setup, fft_new_setup,
+                  fft_new_setup_preallocated, fft_simd_width_bytes, fft_transform, fft_transform_batched,
+                  fft_transform_strided, fft_transform_unordered, launch_count)
+
+__all__ = [n for n in dir() if not n.startswith("_")]

@@ -1,0 +1,154 @@
+"""Host-side mirror of the reference's C API (chowdsp_fft.h:64-163) over libchowdsp_fft_b200.so.
+
+Same function names, argument order and meaning as the reference; buffers may be numpy fp32 arrays
+(host memory), torch CUDA tensors (device memory) or raw integer addresses.  Errors that the C API can
+only signal with NULL / a sticky message are raised here as exceptions.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import lib
+
+FFT_FORWARD, FFT_BACKWARD = 0, 1   # chowdsp_fft.h:64-68
+FFT_REAL, FFT_COMPLEX = 0, 1       # chowdsp_fft.h:71-75
+
+
+class FFTError(RuntimeError):
+    pass
+
+
+def _last_error() -> str:
+    return lib().fft_b200_last_error().decode(errors="replace")
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise FFTError(_last_error() or f"chowdsp_fft_b200 error {rc}")
+
+
+def _addr(buf) -> int:
+    """Address of a numpy array, torch tensor or raw int pointer (fp32, contiguous)."""
+    if buf is None:
+        return 0
+    if isinstance(buf, int):
+        return buf
+    if isinstance(buf, np.ndarray):
+        if buf.dtype != np.float32 or not buf.flags["C_CONTIGUOUS"]:
+            raise TypeError("numpy buffers must be C-contiguous float32")
+        return buf.ctypes.data
+    if hasattr(buf, "data_ptr"):  # torch.Tensor without importing torch here
+        if str(buf.dtype) != "torch.float32" or not buf.is_contiguous():
+            raise TypeError("torch buffers must be contiguous float32")
+        return buf.data_ptr()
+    raise TypeError(f"unsupported buffer type {type(buf)!r}")
+
+
+def _stream(stream) -> int:
+    if stream is None:
+        return 0
+    if isinstance(stream, int):
+        return stream
+    return int(stream.cuda_stream)  # torch.cuda.Stream
+
+
+def device_available() -> bool:
+    return bool(lib().fft_b200_device_available())
+
+
+def launch_count() -> int:
+    return int(lib().fft_b200_launch_count())
+
+
+def fft_bytes_required(N: int, transform: int, use_avx_if_available: bool = True) -> int:
+    return int(lib().fft_bytes_required(N, transform, use_avx_if_available))
+
+
+def fft_new_setup(N: int, transform: int, use_avx_if_available: bool = True) -> int:
+    s = lib().fft_new_setup(N, transform, use_avx_if_available)
+    if not s:
+        raise FFTError(_last_error() or f"fft_new_setup({N}) failed")
+    return s
+
+
+def fft_new_setup_preallocated(N: int, transform: int, data, use_avx_if_available: bool = True) -> int:
+    s = lib().fft_new_setup_preallocated(N, transform, _addr(data), use_avx_if_available)
+    if not s:
+        raise FFTError(_last_error() or f"fft_new_setup_preallocated({N}) failed")
+    return s
+
+
+def fft_destroy_setup(setup: int) -> None:
+    lib().fft_destroy_setup(setup)
+
+
+def fft_simd_width_bytes(setup: int) -> int:
+    return int(lib().fft_simd_width_bytes(setup))
+
+
+def _void_call(fn, *args) -> None:
+    """The reference-shaped functions return void; surface the sticky error text as an exception."""
+    lib().fft_b200_clear_error()
+    fn(*args)
+    err = _last_error()
+    if err:
+        raise FFTError(err)
+
+
+def fft_transform(setup: int, input, output, work, direction: int) -> None:
+    _void_call(lib().fft_transform, setup, _addr(input), _addr(output), _addr(work), direction)
+
+
+def fft_transform_unordered(setup: int, input, output, work, direction: int) -> None:
+    _void_call(lib().fft_transform_unordered, setup, _addr(input), _addr(output), _addr(work), direction)
+
+
+def fft_convolve_unordered(setup: int, dft_a, dft_b, dft_ab, scaling: float) -> None:
+    _void_call(lib().fft_convolve_unordered, setup, _addr(dft_a), _addr(dft_b), _addr(dft_ab), scaling)
+
+
+def fft_accumulate(setup: int, a, b, ab, N: int) -> None:
+    _void_call(lib().fft_accumulate, setup, _addr(a), _addr(b), _addr(ab), N)
+
+
+def aligned_malloc(nb_bytes: int) -> int:
+    p = lib().aligned_malloc(nb_bytes)
+    if not p:
+        raise MemoryError(f"aligned_malloc({nb_bytes})")
+    return p
+
+
+def aligned_free(p: int) -> None:
+    lib().aligned_free(p)
+
+
+def aligned_array(nfloats: int) -> np.ndarray:
+    """fp32 numpy view of an aligned_malloc block (pinned + device-mapped when a GPU is present).
+    Free with aligned_free(arr.ctypes.data) once no view is alive."""
+    p = aligned_malloc(max(1, nfloats) * 4)
+    return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(nfloats,))
+
+
+# ---- batched / stream-ordered extensions (chowdsp_fft_b200.h) --------------------------------------
+def fft_transform_batched(setup: int, input, output, batch: int, in_stride: int, out_stride: int,
+                          direction: int, ordered: bool = True, stream=None) -> None:
+    _check(lib().fft_transform_batched(setup, _addr(input), _addr(output), batch, in_stride, out_stride,
+                                       direction, int(ordered), _stream(stream)))
+
+
+def fft_transform_strided(setup: int, input, output, outer: int, inner: int, in_outer: int, in_inner: int,
+                          out_outer: int, out_inner: int, direction: int, ordered: bool = True, stream=None) -> None:
+    _check(lib().fft_transform_strided(setup, _addr(input), _addr(output), outer, inner, in_outer, in_inner,
+                                       out_outer, out_inner, direction, int(ordered), _stream(stream)))
+
+
+def fft_convolve_unordered_batched(setup: int, dft_a, dft_b, dft_ab, batch: int, a_stride: int, b_stride: int,
+                                   ab_stride: int, scaling: float, stream=None) -> None:
+    _check(lib().fft_convolve_unordered_batched(setup, _addr(dft_a), _addr(dft_b), _addr(dft_ab), batch,
+                                                a_stride, b_stride, ab_stride, scaling, _stream(stream)))
+
+
+def fft_accumulate_batched(setup: int, a, b, ab, n: int, stream=None) -> None:
+    _check(lib().fft_accumulate_batched(setup, _addr(a), _addr(b), _addr(ab), n, _stream(stream)))

@@ -664,6 +664,7 @@ CFB_API int fft_accumulate_batched (void* setup, const float* a, const float* b,
 }
 
 CFB_API const char* fft_b200_last_error (void) { return t_error; }
+CFB_API void fft_b200_clear_error (void) { t_error[0] = 0; }
 CFB_API unsigned long long fft_b200_launch_count (void) { return cfb::launch_count(); }
 CFB_API int fft_b200_device_available (void) { return device_available() ? 1 : 0; }
 } // namespace chowdsp::fft

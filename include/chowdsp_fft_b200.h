@@ -48,8 +48,10 @@ int fft_convolve_unordered_batched (void* setup, const float* dft_a, const float
 /* ab[i] = a[i] + b[i] for n floats (n % 8 == 0), stream-ordered.  Reference chowdsp_fft.h:160. */
 int fft_accumulate_batched (void* setup, const float* a, const float* b, float* ab, long long n, void* stream);
 
-/* Text of the calling thread's most recent failure ("" if none). */
+/* Text of the calling thread's most recent failure ("" if none), and a way to reset it (the
+   reference-shaped functions return void, so callers that want to detect failures clear, call, read). */
 const char* fft_b200_last_error (void);
+void fft_b200_clear_error (void);
 
 /* Number of CUDA kernels this library has launched in this process (all threads). */
 unsigned long long fft_b200_launch_count (void);

@@ -1,0 +1,128 @@
+"""CPU pre-validation of the CUDA kernel SOURCE (chowdsp_fft_b200/csrc/*.cuh) through the host shim in
+tests/emu: index maps, twiddle tables, layouts, batching and shared-memory bank behaviour, checked
+against the oracle.  This exercises the kernel source, not the product library; the GPU parity tests
+(tests/test_gpu_parity.py, -m gpu) are the ones that go through the C ABI."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+fp = C.POINTER(C.c_float)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    from tests.emu.build_emu import build
+
+    L = C.CDLL(build())
+    L.emu_fft.argtypes = [C.c_int] * 4 + [fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 4 + [C.c_int, C.POINTER(C.c_long)]
+    L.emu_convolve.argtypes = [fp, fp, fp] + [C.c_longlong] * 3 + [C.c_int] * 4 + [C.c_float]
+    L.emu_accumulate.argtypes = [fp, fp, fp, C.c_longlong]
+    return L
+
+
+def run_fft(L, x, N, is_c, W, backward, ordered, batch, inner=None, strides=None, out_floats=None, log=False):
+    logM = int(np.log2(N)) - (0 if is_c else 1)
+    kind = (1 if backward else 0) if is_c else (3 if backward else 2)
+    nfl = 2 * N if is_c else N
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.zeros(out_floats if out_floats is not None else batch * nfl, np.float32)
+    st = (C.c_long * 4)()
+    inner = batch if inner is None else inner
+    ii, io, oi, oo = strides if strides is not None else (nfl, 0, nfl, 0)
+    rc = L.emu_fft(logM, kind, 0 if ordered else 1, {8: 3, 4: 2}[W], x.ctypes.data_as(fp), out.ctypes.data_as(fp),
+                   batch, inner, ii, io, oi, oo, int(log), st)
+    assert rc == 0
+    return out, list(st)
+
+
+SIZES = [(16, True), (32, True), (64, True), (256, True), (512, True), (1024, True), (4096, True), (8192, True),
+         (16384, True), (32, False), (64, False), (128, False), (1024, False), (2048, False), (8192, False), (32768, False)]
+
+
+@pytest.mark.parametrize("N,is_c", SIZES)
+@pytest.mark.parametrize("avx", [True, False])
+def test_emulated_kernels_match_oracle(emu, oracle_mod, N, is_c, avx):
+    o = oracle_mod
+    W = o.simd_width(N, is_c, avx)
+    if W == 0 or (avx and W != 8):
+        pytest.skip("layout not available at this size")
+    nfl = 2 * N if is_c else N
+    batch = 3 if N <= 2048 else 1  # 3 exercises the ragged last CTA for small N (several transforms per CTA)
+    rng = np.random.default_rng(N + W)
+    x = rng.uniform(-1, 1, (batch, nfl)).astype(np.float32)
+    tol = o.parity_tol(N)  # north star: rel L2 <= 1e-6 log2 N
+    for ordered in (True, False):
+        f, st = run_fft(emu, x, N, is_c, W, False, ordered, batch, log=True)
+        ref = o.np_transform(x, N, is_c, W, False, ordered)
+        assert o.rel_l2(f, ref) < min(tol, 4e-7)
+        b, st2 = run_fft(emu, ref, N, is_c, W, True, ordered, batch, log=True)
+        assert o.rel_l2(b, o.np_transform(ref, N, is_c, W, True, ordered)) < min(tol, 4e-7)
+        for s in (st, st2):
+            if s[0]:
+                # shared-memory exchanges: <= 7% extra wavefronts overall (the mirrored reads of the real
+                # split step collide on one slot per 16), nothing worse than 2x on any single access
+                assert s[1] <= 1.07 * s[2], s
+                assert s[3] <= 200, s
+
+
+def test_emulated_impulse_and_tone_positions(emu, oracle_mod):
+    """Unit impulses and single-bin tones expose index / sign / layout errors exactly."""
+    o = oracle_mod
+    N, W = 256, 8
+    for is_c in (True, False):
+        nfl = 2 * N if is_c else N
+        x = np.zeros((2, nfl), np.float32)
+        x[0, 0] = 1.0
+        x[1, 2 if is_c else 1] = 1.0  # impulse at n = 1
+        for ordered in (True, False):
+            f, _ = run_fft(emu, x, N, is_c, W, False, ordered, 2)
+            assert np.allclose(f.reshape(2, nfl), o.np_transform(x, N, is_c, W, False, ordered), atol=2e-6)
+        n = np.arange(N)
+        k0 = 37
+        tone = np.cos(2 * np.pi * k0 * n / N).astype(np.float32)
+        xt = np.zeros(nfl, np.float32)
+        if is_c:
+            xt[0::2] = tone
+        else:
+            xt[:] = tone
+        f, _ = run_fft(emu, xt, N, is_c, W, False, True, 1)
+        spec = f[0::2] + 1j * f[1::2]
+        peak = np.argsort(-np.abs(spec))[:2 if is_c else 1]
+        assert set(peak.tolist()) == ({k0, N - k0} if is_c else {k0})
+
+
+def test_emulated_two_level_batch_is_an_stft_gather(emu, oracle_mod):
+    """outer x inner addressing = overlapping frame gather (hop < N) for the STFT path."""
+    o = oracle_mod
+    N, W, hop, channels, frames = 128, 8, 32, 2, 5
+    ch_stride = 400
+    rng = np.random.default_rng(5)
+    sig = rng.uniform(-1, 1, channels * ch_stride).astype(np.float32)
+    out, _ = run_fft(emu, sig, N, False, W, False, True, channels * frames, inner=frames,
+                     strides=(hop, ch_stride, N, frames * N), out_floats=channels * frames * N)
+    out = out.reshape(channels, frames, N)
+    for c in range(channels):
+        for f in range(frames):
+            want = o.np_transform(sig[c * ch_stride + f * hop: c * ch_stride + f * hop + N], N, False, W, False, True)
+            assert o.rel_l2(out[c, f], want) < 4e-7
+
+
+@pytest.mark.parametrize("is_c,W", [(False, 8), (False, 4), (True, 8), (True, 4)])
+def test_emulated_convolve_and_accumulate(emu, oracle_mod, is_c, W):
+    o = oracle_mod
+    N = 256
+    nfl = 2 * N if is_c else N
+    rng = np.random.default_rng(11)
+    batch = 3
+    a = rng.uniform(-1, 1, (batch, nfl)).astype(np.float32)
+    b = rng.uniform(-1, 1, nfl).astype(np.float32)  # shared operand (stride 0)
+    ab = rng.uniform(-1, 1, (batch, nfl)).astype(np.float32)
+    want = o.np_convolve(a, b[None, :], ab, N, is_c, W, 0.5 / N)
+    got = ab.copy()
+    emu.emu_convolve(a.ctypes.data_as(fp), b.ctypes.data_as(fp), got.ctypes.data_as(fp), nfl, 0, nfl, nfl, batch,
+                     {8: 3, 4: 2}[W], 0 if is_c else 1, 0.5 / N)
+    assert o.rel_l2(got, want) < 2e-7
+    s = np.empty_like(a)
+    emu.emu_accumulate(a.ctypes.data_as(fp), ab.ctypes.data_as(fp), s.ctypes.data_as(fp), a.size)
+    assert np.array_equal(s, a + ab)

@@ -1,0 +1,387 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libchowdsp_fft_b200.so via the ctypes
+mirror), against the oracle on identical inputs.
+
+Tolerances (north star): ordered and unordered outputs within relative L2 error 1e-6 * log2(N) of the
+reference; unordered outputs compared slot for slot in the reference's own layout.  The elementwise
+kernels (convolve / accumulate) are compared at 1e-6 relative L2 / bit-exact.
+The restated reference tests (test/test.cpp:47-62,103-118,131-232) use the reference's own absolute
+margin 2e-7 * n_floats (test/test.cpp:11).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def cf():
+    import chowdsp_fft_b200 as m
+
+    assert m.device_available(), "GPU tests need a CUDA device; there is no CPU fallback"
+    return m
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x, np.float32)).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def all_cases(o):
+    cases = []
+    for is_c in (True, False):
+        for lg in range(4, 16):
+            N = 1 << lg
+            for avx in (True, False):
+                W = o.simd_width(N, is_c, avx)
+                if W == 0 or (avx and W != 8):
+                    continue
+                if (is_c and N > 16384) or (not is_c and N > 32768):
+                    continue
+                cases.append((N, is_c, avx, W))
+    return cases
+
+
+def gpu_transform(cf, x, N, is_c, avx, backward, ordered, inplace=False):
+    """x: [batch, nfl] numpy -> numpy, through fft_transform_batched on device buffers."""
+    nfl = 2 * N if is_c else N
+    batch = x.shape[0]
+    s = cf.fft_new_setup(N, cf.FFT_COMPLEX if is_c else cf.FFT_REAL, avx)
+    try:
+        din = dev(x)
+        dout = din if inplace else torch.full_like(din, float("nan"))
+        cf.fft_transform_batched(s, din, dout, batch, nfl, nfl, cf.FFT_BACKWARD if backward else cf.FFT_FORWARD, ordered)
+        torch.cuda.synchronize()
+        return host(dout)
+    finally:
+        cf.fft_destroy_setup(s)
+
+
+# --------------------------------------------------------------------------------------------------
+def test_every_size_kind_layout_matches_oracle(cf, oracle_mod, ref_lib):
+    o = oracle_mod
+    rng = np.random.default_rng(42)
+    worst = 0.0
+    for N, is_c, avx, W in all_cases(o):
+        nfl = 2 * N if is_c else N
+        batch = 5 if N <= 4096 else 2  # odd batch: ragged last CTA when several transforms share one
+        x = rng.uniform(-1, 1, (batch, nfl)).astype(np.float32)
+        tol = o.parity_tol(N)
+        for ordered in (True, False):
+            want_f = o.np_transform(x, N, is_c, W, False, ordered)
+            got_f = gpu_transform(cf, x, N, is_c, avx, False, ordered)
+            e = o.rel_l2(got_f, want_f)
+            assert e < tol, (N, is_c, W, ordered, "forward", e)
+            got_b = gpu_transform(cf, want_f, N, is_c, avx, True, ordered)
+            want_b = o.np_transform(want_f, N, is_c, W, True, ordered)
+            e2 = o.rel_l2(got_b, want_b)
+            assert e2 < tol, (N, is_c, W, ordered, "backward", e2)
+            worst = max(worst, e, e2)
+            # in place (input and output may alias, chowdsp_fft.h:136)
+            assert np.array_equal(gpu_transform(cf, x, N, is_c, avx, False, ordered, inplace=True), got_f)
+            if ref_lib is not None:
+                ref_f, _ = ref_lib.transform(x, N, is_c, False, ordered, avx)
+                assert o.rel_l2(got_f, ref_f) < tol, (N, is_c, W, ordered, "vs live reference")
+                ref_b, _ = ref_lib.transform(ref_f, N, is_c, True, ordered, avx)
+                assert o.rel_l2(gpu_transform(cf, ref_f, N, is_c, avx, True, ordered), ref_b) < tol
+    assert worst < 5e-7  # we are in fact ~1.5e-7 from float64 truth, tighter than the reference itself
+
+
+def test_golden_vectors(cf, oracle_mod, golden):
+    o = oracle_mod
+    n = 0
+    for N in (32, 64, 128, 256, 1024, 4096):
+        for is_c in (False, True):
+            for W in (4, 8):
+                t = f"{'c' if is_c else 'r'}{N}w{W}"
+                if t + "_x" not in golden.files:
+                    continue
+                avx = W == 8
+                tol = o.parity_tol(N)
+                x = golden[t + "_x"]
+                assert o.rel_l2(gpu_transform(cf, x, N, is_c, avx, False, True), golden[t + "_fwd_ordered"]) < tol
+                assert o.rel_l2(gpu_transform(cf, x, N, is_c, avx, False, False), golden[t + "_fwd_unordered"]) < tol
+                assert o.rel_l2(gpu_transform(cf, golden[t + "_fwd_ordered"], N, is_c, avx, True, True), golden[t + "_bwd_ordered"]) < tol
+                assert o.rel_l2(gpu_transform(cf, golden[t + "_fwd_unordered"], N, is_c, avx, True, False), golden[t + "_bwd_unordered"]) < tol
+                # convolve on the reference's own unordered spectra
+                s = cf.fft_new_setup(N, cf.FFT_COMPLEX if is_c else cf.FFT_REAL, avx)
+                fu = golden[t + "_fwd_unordered"]
+                a, b, ab = dev(fu[0]), dev(fu[1]), dev(golden[t + "_conv_acc_in"])
+                cf.fft_convolve_unordered(s, a, b, ab, 0.5 / N)
+                assert o.rel_l2(host(ab), golden[t + "_conv_out"]) < 1e-6
+                cf.fft_destroy_setup(s)
+                n += 1
+    assert n >= 18
+
+
+def test_impulses_and_tones(cf, oracle_mod):
+    o = oracle_mod
+    for N, is_c, avx in ((1024, True, True), (1024, False, True), (64, True, False), (64, False, False)):
+        W = o.simd_width(N, is_c, avx)
+        nfl = 2 * N if is_c else N
+        x = np.zeros((3, nfl), np.float32)
+        x[0, 0] = 1.0
+        x[1, 2 if is_c else 1] = 1.0
+        k0 = 5
+        n = np.arange(N)
+        if is_c:
+            x[2, 0::2] = np.cos(2 * np.pi * k0 * n / N)
+            x[2, 1::2] = np.sin(2 * np.pi * k0 * n / N)
+        else:
+            x[2] = np.cos(2 * np.pi * k0 * n / N)
+        for ordered in (True, False):
+            got = gpu_transform(cf, x, N, is_c, avx, False, ordered)
+            want = o.np_transform(x, N, is_c, W, False, ordered)
+            assert np.allclose(got, want, atol=3e-6 * N ** 0.5)
+        spec = gpu_transform(cf, x, N, is_c, avx, False, True)[2]
+        mag = np.hypot(spec[0::2], spec[1::2])
+        mag[0] = abs(spec[0]) if not is_c else mag[0]
+        assert int(np.argmax(mag)) == k0
+
+
+def test_batched_equals_loop_of_single_calls(cf, oracle_mod):
+    """fft_transform_batched == a loop of fft_transform / fft_transform_unordered, bit for bit."""
+    rng = np.random.default_rng(1)
+    for N, is_c in ((4096, True), (2048, False), (64, True)):
+        nfl = 2 * N if is_c else N
+        s = cf.fft_new_setup(N, cf.FFT_COMPLEX if is_c else cf.FFT_REAL)
+        x = dev(rng.uniform(-1, 1, (7, nfl)))
+        for ordered in (True, False):
+            yb = torch.empty_like(x)
+            cf.fft_transform_batched(s, x, yb, 7, nfl, nfl, cf.FFT_FORWARD, ordered)
+            ys = torch.empty_like(x)
+            for i in range(7):
+                (cf.fft_transform if ordered else cf.fft_transform_unordered)(s, x[i], ys[i], None, cf.FFT_FORWARD)
+            torch.cuda.synchronize()
+            assert torch.equal(yb, ys)
+        cf.fft_destroy_setup(s)
+
+
+def test_strided_batches_and_stft_gather(cf, oracle_mod):
+    o = oracle_mod
+    N, hop, channels, frames = 2048, 512, 3, 9
+    ch_stride = (frames - 1) * hop + N + 64
+    rng = np.random.default_rng(9)
+    sig = rng.uniform(-1, 1, (channels, ch_stride)).astype(np.float32)
+    s = cf.fft_new_setup(N, cf.FFT_REAL)
+    d = dev(sig)
+    out = torch.zeros(channels, frames, N, device="cuda")
+    cf.fft_transform_strided(s, d, out, channels, frames, ch_stride, hop, frames * N, N, cf.FFT_FORWARD, True)
+    torch.cuda.synchronize()
+    got = host(out)
+    for c in range(channels):
+        fr = np.stack([sig[c, f * hop:f * hop + N] for f in range(frames)])
+        assert o.rel_l2(got[c], o.np_transform(fr, N, False, 8, False, True)) < o.parity_tol(N)
+    # padded strides in a plain batch
+    x = rng.uniform(-1, 1, (4, N + 32)).astype(np.float32)
+    dx = dev(x)
+    dy = torch.zeros(4, N + 64, device="cuda")
+    cf.fft_transform_batched(s, dx, dy, 4, N + 32, N + 64, cf.FFT_FORWARD, False)
+    torch.cuda.synchronize()
+    assert o.rel_l2(host(dy)[:, :N], o.np_transform(x[:, :N], N, False, 8, False, False)) < o.parity_tol(N)
+    assert float(dy[:, N:].abs().max()) == 0.0  # nothing written past each transform
+    cf.fft_destroy_setup(s)
+
+
+def test_convolve_and_accumulate(cf, oracle_mod, ref_lib):
+    o = oracle_mod
+    rng = np.random.default_rng(5)
+    for N, is_c, avx in ((8192, False, True), (4096, True, True), (64, False, False), (32, True, False), (256, False, False)):
+        W = o.simd_width(N, is_c, avx)
+        nfl = 2 * N if is_c else N
+        s = cf.fft_new_setup(N, cf.FFT_COMPLEX if is_c else cf.FFT_REAL, avx)
+        a = rng.uniform(-1, 1, (6, nfl)).astype(np.float32)
+        b = rng.uniform(-1, 1, (6, nfl)).astype(np.float32)
+        ab = rng.uniform(-1, 1, (6, nfl)).astype(np.float32)  # pre-loaded accumulator: it must ACCUMULATE
+        want = o.np_convolve(a, b, ab, N, is_c, W, 0.5 / N)
+        da, db, dab = dev(a), dev(b), dev(ab)
+        cf.fft_convolve_unordered_batched(s, da, db, dab, 6, nfl, nfl, nfl, 0.5 / N)
+        torch.cuda.synchronize()
+        assert o.rel_l2(host(dab), want) < 1e-6
+        if ref_lib is not None:
+            assert o.rel_l2(host(dab), ref_lib.convolve(a, b, ab, N, is_c, 0.5 / N, avx)) < 1e-6
+        # shared operand (stride 0) and the single-call form; aliasing ab == a is allowed (chowdsp_fft.h:153)
+        dab2 = dev(ab)
+        cf.fft_convolve_unordered_batched(s, da, db, dab2, 6, nfl, 0, nfl, 0.25)
+        torch.cuda.synchronize()
+        assert o.rel_l2(host(dab2), o.np_convolve(a, b[0][None], ab, N, is_c, W, 0.25)) < 1e-6
+        alias = dev(a[0])
+        cf.fft_convolve_unordered(s, alias, db[0], alias, 1.0)
+        assert o.rel_l2(host(alias), o.np_convolve(a[0], b[0], a[0], N, is_c, W, 1.0)) < 1e-6
+        # accumulate: plain sum, exact
+        dsum = torch.empty_like(da[0])
+        cf.fft_accumulate(s, da[0], db[0], dsum, nfl)
+        assert np.array_equal(host(dsum), a[0] + b[0])
+        cf.fft_destroy_setup(s)
+
+
+def test_reference_test_suite_restated(cf, oracle_mod):
+    """test/test.cpp:234-304 restated: sizes 2^5..2^15 (single-kernel range), {complex, real} x
+    {malloc'd, pre-allocated} x {SSE-layout, AVX-layout}; in-place ordered fwd / bwd / scale; the
+    unordered fwd -> convolve -> bwd (+ accumulate) chain.  Truth = oracle (float64), reference margin."""
+    o = oracle_mod
+    for is_c in (True, False):
+        for lg in range(5, 15 if is_c else 16):
+            N = 1 << lg
+            nfl = 2 * N if is_c else N
+            margin = 2.0e-7 * nfl
+            for avx in (False, True):
+                for prealloc in (False, True):
+                    W = o.simd_width(N, is_c, avx)
+                    tr = cf.FFT_COMPLEX if is_c else cf.FFT_REAL
+                    if prealloc:
+                        nbytes = cf.fft_bytes_required(N, tr, avx)
+                        block = cf.aligned_malloc(nbytes)
+                        s = cf.fft_new_setup_preallocated(N, tr, block, avx)
+                    else:
+                        s = cf.fft_new_setup(N, tr, avx)
+                    assert cf.fft_simd_width_bytes(s) == 4 * W
+                    if not avx:
+                        assert cf.fft_simd_width_bytes(s) == 16  # test.cpp:44-45
+                    sig = o.ref_signal(N, is_c, 100.0)
+                    data = cf.aligned_array(nfl)
+                    work = cf.aligned_array(nfl)
+                    data[:] = sig
+                    cf.fft_transform(s, data, data, work, cf.FFT_FORWARD)
+                    want = o.np_transform(sig, N, is_c, W, False, True)
+                    assert np.max(np.abs(data - want)) <= margin
+                    cf.fft_transform(s, data, data, work, cf.FFT_BACKWARD)
+                    assert np.max(np.abs(data / N - sig)) <= margin
+                    if not prealloc and lg <= 12:
+                        sig2 = o.ref_signal(N, is_c, 200.0)
+                        s1, s2, out = cf.aligned_array(nfl), cf.aligned_array(nfl), cf.aligned_array(nfl)
+                        s1[:], s2[:], out[:] = sig, sig2, 0.0
+                        cf.fft_transform_unordered(s, s1, s1, work, cf.FFT_FORWARD)
+                        cf.fft_transform_unordered(s, s2, s2, work, cf.FFT_FORWARD)
+                        cf.fft_convolve_unordered(s, s1, s2, out, 1.0 / N)
+                        cf.fft_transform_unordered(s, out, out, work, cf.FFT_BACKWARD)
+                        f1 = o.np_transform(sig, N, is_c, W, False, False)
+                        f2 = o.np_transform(sig2, N, is_c, W, False, False)
+                        want = o.np_transform(o.np_convolve(f1, f2, np.zeros(nfl, np.float32), N, is_c, W, 1.0 / N), N, is_c, W, True, False)
+                        if not is_c:
+                            cf.fft_accumulate(s, out, s1, out, N)  # test.cpp:218
+                            want = want + f1
+                        assert np.max(np.abs(out - want)) <= margin * max(1.0, float(np.max(np.abs(want))))
+                        for arr in (s1, s2, out):
+                            cf.aligned_free(arr.ctypes.data)
+                    cf.aligned_free(data.ctypes.data)
+                    cf.aligned_free(work.ctypes.data)
+                    if prealloc:
+                        cf.aligned_free(block)  # no fft_destroy_setup for pre-allocated plans (chowdsp_fft.h:98-113)
+                    else:
+                        cf.fft_destroy_setup(s)
+
+
+def test_host_pointer_paths(cf, oracle_mod):
+    """pageable numpy memory, pinned aligned_malloc memory (zero-copy when small, staged when large)."""
+    o = oracle_mod
+    rng = np.random.default_rng(3)
+    N = 4096
+    s = cf.fft_new_setup(N, cf.FFT_COMPLEX)
+    # pageable, single call, out of place and in place
+    x = rng.uniform(-1, 1, 2 * N).astype(np.float32)
+    y = np.zeros_like(x)
+    cf.fft_transform(s, x, y, None, cf.FFT_FORWARD)
+    want = o.np_transform(x, N, True, 8, False, True)
+    assert o.rel_l2(y, want) < o.parity_tol(N)
+    xi = x.copy()
+    cf.fft_transform(s, xi, xi, None, cf.FFT_FORWARD)
+    assert np.array_equal(xi, y)
+    # pinned batch large enough to take the chunked staging pipeline (3 chunks of 32 MiB)
+    batch = 3 * 1024 + 17
+    hin, hout = cf.aligned_array(batch * 2 * N), cf.aligned_array(batch * 2 * N)
+    hin[:] = rng.uniform(-1, 1, hin.size).astype(np.float32)
+    cf.fft_transform_batched(s, hin, hout, batch, 2 * N, 2 * N, cf.FFT_FORWARD, True)
+    d = dev(hin.reshape(batch, 2 * N))
+    dout = torch.empty_like(d)
+    cf.fft_transform_batched(s, d, dout, batch, 2 * N, 2 * N, cf.FFT_FORWARD, True)
+    torch.cuda.synchronize()
+    assert np.array_equal(hout.reshape(batch, 2 * N), host(dout))
+    sel = [0, 1, batch // 2, batch - 1]
+    assert o.rel_l2(hout.reshape(batch, 2 * N)[sel], o.np_transform(hin.reshape(batch, 2 * N)[sel], N, True, 8, False, True)) < o.parity_tol(N)
+    cf.aligned_free(hin.ctypes.data)
+    cf.aligned_free(hout.ctypes.data)
+    # mixing host and device data pointers is rejected, loudly
+    with pytest.raises(cf.FFTError):
+        cf.fft_transform_batched(s, x, dout, 1, 2 * N, 2 * N, cf.FFT_FORWARD, True)
+    cf.fft_destroy_setup(s)
+
+
+def test_setup_errors(cf):
+    os.environ["CHOWDSP_FFT_B200_QUIET"] = "1"
+    for N, tr in ((8, cf.FFT_COMPLEX), (16, cf.FFT_REAL), (96, cf.FFT_COMPLEX), (100, cf.FFT_REAL), (0, cf.FFT_REAL),
+                  (-4, cf.FFT_COMPLEX), (1 << 15, cf.FFT_COMPLEX), (1 << 16, cf.FFT_REAL)):
+        with pytest.raises(cf.FFTError):
+            cf.fft_new_setup(N, tr)
+    with pytest.raises(cf.FFTError):
+        cf.fft_transform_batched(12345678, None, None, 1, 1, 1, 0, True)
+
+
+# --------------------------------------------------------------------------------------------------
+# BASELINE.json full sizes: size-independent properties + sampled oracle comparison
+# --------------------------------------------------------------------------------------------------
+def test_config2_full_size_properties(cf, oracle_mod):
+    """batched C2C N=4096 x 65536 (BASELINE config 2), ordered and unordered."""
+    o = oracle_mod
+    N, batch = 4096, 65536
+    nfl = 2 * N
+    s = cf.fft_new_setup(N, cf.FFT_COMPLEX)
+    g = torch.Generator(device="cuda").manual_seed(42)
+    x = torch.rand(batch, nfl, device="cuda", generator=g) * 2 - 1
+    y = torch.empty_like(x)
+    for ordered in (True, False):
+        cf.fft_transform_batched(s, x, y, batch, nfl, nfl, cf.FFT_FORWARD, ordered)
+        # Parseval per transform: sum |X|^2 = N sum |x|^2 (layout independent)
+        ex = (x.double() ** 2).sum(dim=1)
+        ey = (y.double() ** 2).sum(dim=1)
+        assert float(((ey - N * ex).abs() / (N * ex)).max()) < 1e-5
+        # sampled transforms against the oracle, slot for slot
+        sel = torch.tensor([0, 1, 255, 256, 32767, 65534, 65535] + list(range(1000, 1249)), device="cuda")
+        want = o.np_transform(host(x[sel]), N, True, 8, False, ordered)
+        assert o.rel_l2(host(y[sel]), want) < o.parity_tol(N)
+        # round trip BACKWARD(FORWARD(x)) = N x
+        z = torch.empty_like(x)
+        cf.fft_transform_batched(s, y, z, batch, nfl, nfl, cf.FFT_BACKWARD, ordered)
+        err = (z / N - x).double().norm() / x.double().norm()
+        assert float(err) < o.parity_tol(N)
+        del z
+    # linearity on a slice: F(a x1 + b x2) = a F(x1) + b F(x2)
+    x1, x2 = x[:4096], x[4096:8192]
+    comb = (0.75 * x1 - 1.25 * x2).contiguous()
+    yc = torch.empty_like(comb)
+    cf.fft_transform_batched(s, comb, yc, 4096, nfl, nfl, cf.FFT_FORWARD, True)
+    cf.fft_transform_batched(s, x, y, 8192, nfl, nfl, cf.FFT_FORWARD, True)
+    lin = 0.75 * y[:4096] - 1.25 * y[4096:8192]
+    assert float((yc - lin).double().norm() / lin.double().norm()) < 1e-6
+    cf.fft_destroy_setup(s)
+
+
+def test_config3_stft_shape(cf, oracle_mod):
+    """R2C N=2048 hop 512 (BASELINE config 3) on 32 channels x 48000 samples; every frame vs oracle for
+    two channels, Parseval-style energy for all."""
+    o = oracle_mod
+    N, hop, channels, samples = 2048, 512, 32, 48000
+    frames = (samples - N) // hop + 1
+    s = cf.fft_new_setup(N, cf.FFT_REAL)
+    g = torch.Generator(device="cuda").manual_seed(42)
+    sig = torch.rand(channels, samples, device="cuda", generator=g) * 2 - 1
+    out = torch.empty(channels, frames, N, device="cuda")
+    cf.fft_transform_strided(s, sig, out, channels, frames, samples, hop, frames * N, N, cf.FFT_FORWARD, True)
+    torch.cuda.synchronize()
+    hs = host(sig)
+    for c in (0, channels - 1):
+        fr = np.stack([hs[c, f * hop:f * hop + N] for f in range(frames)])
+        assert o.rel_l2(host(out[c]), o.np_transform(fr, N, False, 8, False, True)) < o.parity_tol(N)
+    # inverse of every frame returns the frame (x N)
+    back = torch.empty_like(out)
+    cf.fft_transform_batched(s, out, back, channels * frames, N, N, cf.FFT_BACKWARD, True)
+    fr_all = sig.unfold(1, N, hop)
+    assert float((back / N - fr_all).double().norm() / fr_all.double().norm()) < o.parity_tol(N)
+    cf.fft_destroy_setup(s)

@@ -1,0 +1,145 @@
+"""Pins the oracle (oracle/oracle_fft.c and the numpy restatement in oracle/oracle.py) against the
+reference: the committed golden vectors (reference outputs, tests/gen_golden.py) and, when
+oracle/_ref/libchowdsp_fft_ref.so is present, the live reference.  CPU only."""
+import numpy as np
+import pytest
+
+GOLDEN_CASES = [(N, is_c, W) for N in (32, 64, 128, 256, 1024, 4096) for is_c in (False, True) for W in (4, 8)]
+TIGHT = 6e-7  # oracle (float64 inside) vs reference (fp32 FFTPACK passes): both ~2e-7 from truth
+
+
+def _tag(N, is_c, W):
+    return f"{'c' if is_c else 'r'}{N}w{W}"
+
+
+def _have(golden, N, is_c, W):
+    return _tag(N, is_c, W) + "_x" in golden.files
+
+
+@pytest.mark.parametrize("N,is_c,W", GOLDEN_CASES)
+def test_unordered_map_is_the_reference_permutation(oracle_mod, golden, N, is_c, W):
+    o = oracle_mod
+    if not _have(golden, N, is_c, W):
+        pytest.skip("size/width not supported by the reference")
+    t = _tag(N, is_c, W)
+    pm_np = o.np_unordered_map(N, is_c, W)
+    pm_c = o.load_c().unordered_map(N, is_c, W)
+    assert np.array_equal(pm_np, pm_c)
+    assert sorted(pm_np.tolist()) == list(range(2 * N if is_c else N))
+    # zreorder is a pure permutation: the reference's unordered output is bit-for-bit its ordered
+    # output pushed through the map
+    assert np.array_equal(golden[t + "_fwd_unordered"], golden[t + "_fwd_ordered"][:, pm_np])
+
+
+@pytest.mark.parametrize("N,is_c,W", GOLDEN_CASES)
+@pytest.mark.parametrize("impl", ["c", "numpy"])
+def test_transforms_match_golden(oracle_mod, golden, N, is_c, W, impl):
+    o = oracle_mod
+    if not _have(golden, N, is_c, W):
+        pytest.skip("size/width not supported by the reference")
+    t = _tag(N, is_c, W)
+    c = o.load_c()
+
+    def run(x, backward, ordered):
+        if impl == "numpy":
+            return o.np_transform(x, N, is_c, W, backward, ordered)
+        return np.stack([c.transform(row, N, is_c, W, backward, ordered) for row in x])
+
+    x = golden[t + "_x"]
+    assert o.rel_l2(run(x, False, True), golden[t + "_fwd_ordered"]) < TIGHT
+    assert o.rel_l2(run(x, False, False), golden[t + "_fwd_unordered"]) < TIGHT
+    assert o.rel_l2(run(golden[t + "_fwd_ordered"], True, True), golden[t + "_bwd_ordered"]) < TIGHT
+    assert o.rel_l2(run(golden[t + "_fwd_unordered"], True, False), golden[t + "_bwd_unordered"]) < TIGHT
+    # unscaled round trip: BACKWARD(FORWARD(x)) = N x  (chowdsp_fft.h:128-129)
+    assert o.rel_l2(golden[t + "_bwd_unordered"] / N, x) < 1e-6
+
+
+@pytest.mark.parametrize("N,is_c,W", GOLDEN_CASES)
+def test_convolve_matches_golden(oracle_mod, golden, N, is_c, W):
+    o = oracle_mod
+    if not _have(golden, N, is_c, W):
+        pytest.skip("size/width not supported by the reference")
+    t = _tag(N, is_c, W)
+    fu = golden[t + "_fwd_unordered"]
+    acc = golden[t + "_conv_acc_in"]
+    want = golden[t + "_conv_out"]
+    assert o.rel_l2(o.np_convolve(fu[0], fu[1], acc, N, is_c, W, 0.5 / N), want) < TIGHT
+    assert o.rel_l2(o.load_c().convolve(fu[0], fu[1], acc, N, is_c, W, 0.5 / N), want) < TIGHT
+    # the real DC/Nyquist slots are REAL products, not a complex one (avx:1974-1978)
+    if not is_c:
+        a, b = fu[0].astype(np.float64), fu[1].astype(np.float64)
+        assert abs(want[0] - (acc[0] + a[0] * b[0] * 0.5 / N)) <= 1e-6 * max(1.0, abs(want[0]))
+        assert abs(want[W] - (acc[W] + a[W] * b[W] * 0.5 / N)) <= 1e-6 * max(1.0, abs(want[W]))
+
+
+def test_size_rules(oracle_mod):
+    o = oracle_mod
+    c = o.load_c()
+    for is_c in (False, True):
+        for avx in (False, True):
+            for N in list(range(1, 70)) + [96, 100, 128, 192, 256, 1000, 1024, 4096, 1 << 20]:
+                assert o.simd_width(N, is_c, avx) == c.simd_width(N, is_c, avx)
+    assert o.simd_width(32, False, True) == 4 and o.simd_width(128, False, True) == 8
+    assert o.simd_width(16, True, True) == 4 and o.simd_width(64, True, True) == 8
+    assert o.simd_width(16, False, True) == 0 and o.simd_width(8, True, False) == 0
+    assert o.simd_width(96, True, True) == 0  # non powers of two are out of scope (north star)
+
+
+def test_accumulate(oracle_mod):
+    o = oracle_mod
+    rng = np.random.default_rng(3)
+    a, b = rng.standard_normal(256).astype(np.float32), rng.standard_normal(256).astype(np.float32)
+    assert np.array_equal(o.np_accumulate(a, b), a + b)
+    assert np.array_equal(o.load_c().accumulate(a, b), a + b)
+
+
+# ---- live reference (present in the build container and shipped to the GPU box) ----------------------
+@pytest.mark.parametrize("is_c", [False, True])
+@pytest.mark.parametrize("avx", [False, True])
+def test_against_live_reference(oracle_mod, ref_lib, is_c, avx):
+    o = oracle_mod
+    if ref_lib is None:
+        pytest.skip("oracle/_ref/libchowdsp_fft_ref.so not built")
+    rng = np.random.default_rng(42)
+    for lg in range(4, 17):
+        N = 1 << lg
+        W = o.simd_width(N, is_c, avx)
+        s = ref_lib.new_setup(N, is_c, avx)
+        if W == 0:
+            assert s is None
+            continue
+        assert s is not None and ref_lib.width(s) == W
+        nfl = 2 * N if is_c else N
+        x = rng.uniform(-1, 1, nfl).astype(np.float32)
+        fo, _ = ref_lib.transform(x, N, is_c, False, True, avx)
+        fu, _ = ref_lib.transform(x, N, is_c, False, False, avx)
+        assert np.array_equal(fu, fo[o.np_unordered_map(N, is_c, W)])
+        assert o.rel_l2(o.np_transform(x, N, is_c, W, False, True), fo) < TIGHT
+        assert o.rel_l2(o.load_c().transform(x, N, is_c, W, False, False), fu) < TIGHT
+        bu, _ = ref_lib.transform(fu, N, is_c, True, False, avx)
+        assert o.rel_l2(o.np_transform(fu, N, is_c, W, True, False), bu) < TIGHT
+        acc = rng.uniform(-1, 1, nfl).astype(np.float32)
+        cv = ref_lib.convolve(fu, fo[o.np_unordered_map(N, is_c, W)], acc, N, is_c, 0.25 / N, avx)
+        assert o.rel_l2(o.np_convolve(fu, fu, acc, N, is_c, W, 0.25 / N), cv) < TIGHT
+
+
+def test_reference_partitioned_convolution_is_a_linear_convolution(oracle_mod, ref_lib):
+    """Sanity of the config-4 driver (oracle/ref_driver.cpp): overlap-save output == direct convolution."""
+    o = oracle_mod
+    if ref_lib is None:
+        pytest.skip("oracle/_ref/libchowdsp_fft_ref.so not built")
+    N, P, channels, blocks = 256, 4, 2, 6
+    B = N // 2
+    rng = np.random.default_rng(7)
+    x = rng.uniform(-1, 1, (channels, blocks * B)).astype(np.float32)
+    ir = rng.uniform(-1, 1, (channels, P * B)).astype(np.float32)
+    h = np.zeros((channels, P, N), np.float32)
+    for c in range(channels):
+        for p in range(P):
+            seg = np.zeros(N, np.float32)
+            seg[:B] = ir[c, p * B:(p + 1) * B]
+            h[c, p] = ref_lib.transform(seg, N, False, False, False)[0]
+    y, _, _ = ref_lib.partitioned_convolve(x, h, N, P)
+    for c in range(channels):
+        want = np.convolve(x[c].astype(np.float64), ir[c].astype(np.float64))[:blocks * B]
+        assert o.rel_l2(y[c], want) < 1e-5
