@@ -14,16 +14,17 @@ cudaError_t launch_one (const FftArgs& a, cudaStream_t stream)
 {
     using L = Launch<CFB_LOGM, kRadix>;
     auto kernel = fft_kernel<CFB_LOGM, kRadix, KIND, UNORD>;
-    if (L::SMEM_BYTES > 48 * 1024)
+    constexpr int smem_bytes = UNORD ? L::SMEM_BYTES_UNORD : L::SMEM_BYTES;
+    if (smem_bytes > 48 * 1024)
     {
-        const cudaError_t e = cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_BYTES);
+        const cudaError_t e = cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e != cudaSuccess)
             return e;
     }
     if (a.batch <= 0)
         return cudaSuccess;
     const unsigned grid = (unsigned) (((long long) a.batch + L::PER_CTA - 1) / L::PER_CTA);
-    kernel<<<grid, L::THREADS, L::SMEM_BYTES, stream>>> (a);
+    kernel<<<grid, L::THREADS, smem_bytes, stream>>> (a);
     count_launch();
     return cudaGetLastError();
 }

@@ -74,6 +74,7 @@ struct Geo
     static constexpr int S = (LOGM + LOGR - 1) / LOGR;   // stages
     static constexpr int RLAST = 1 << (LOGM - (S - 1) * LOGR);
     static constexpr int SMEM_F2 = M + (M >> 4);         // padded float2 slots per transform
+    static constexpr int SMEM_F2_UNORD = M + (M >> 3);   // staging image of the unordered layout (W=4 pad is the larger one)
     static_assert (M >= R, "transform smaller than the per-thread radix");
     static FFT_CX int radix (int s) { return s == S - 1 ? RLAST : R; }
     static FFT_CX int ns (int s) { return ipow (R, s); } // product of the radices before stage s
@@ -116,15 +117,53 @@ FFT_HD void smem_skip() // keeps the per-warp op sequences aligned when a lane i
 // ---------------------------------------------------------------------------------------------
 // complex arithmetic.  DIR = -1 forward (e^{-i..}), +1 backward.
 // ---------------------------------------------------------------------------------------------
-FFT_HD float2 cadd (float2 a, float2 b) { return make_float2 (a.x + b.x, a.y + b.y); }
-FFT_HD float2 csub (float2 a, float2 b) { return make_float2 (a.x - b.x, a.y - b.y); }
+// Blackwell packed fp32x2 math (SASS FADD2 / FMUL2 / FFMA2): one instruction per COMPLEX add, two per
+// complex multiply.  The operand modifiers of those instructions (half swap, per-half negate, scalar
+// broadcast) absorb the (y, x) / (-y, x) shuffles written below, so multiplying by +-i is free.
+#ifdef CHOWDSP_EMU
+FFT_HD float2 f2_add (float2 a, float2 b) { return make_float2 (a.x + b.x, a.y + b.y); }
+FFT_HD float2 f2_sub (float2 a, float2 b) { return make_float2 (a.x - b.x, a.y - b.y); }
+FFT_HD float2 f2_mul (float2 a, float2 b) { return make_float2 (a.x * b.x, a.y * b.y); }
+FFT_HD float2 f2_fma (float2 a, float2 b, float2 c) { return make_float2 (std::fmaf (a.x, b.x, c.x), std::fmaf (a.y, b.y, c.y)); }
+#else
+FFT_HD unsigned long long f2_bits (float2 v) { return *reinterpret_cast<unsigned long long*> (&v); }
+FFT_HD float2 f2_from (unsigned long long b) { return *reinterpret_cast<float2*> (&b); }
+FFT_HD float2 f2_add (float2 a, float2 b)
+{
+    unsigned long long r;
+    asm ("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits (a)), "l"(f2_bits (b)));
+    return f2_from (r);
+}
+FFT_HD float2 f2_sub (float2 a, float2 b)
+{
+    unsigned long long r;
+    asm ("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits (a)), "l"(f2_bits (b)));
+    return f2_from (r);
+}
+FFT_HD float2 f2_mul (float2 a, float2 b)
+{
+    unsigned long long r;
+    asm ("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits (a)), "l"(f2_bits (b)));
+    return f2_from (r);
+}
+FFT_HD float2 f2_fma (float2 a, float2 b, float2 c)
+{
+    unsigned long long r;
+    asm ("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_bits (a)), "l"(f2_bits (b)), "l"(f2_bits (c)));
+    return f2_from (r);
+}
+#endif
+
+FFT_HD float2 cadd (float2 a, float2 b) { return f2_add (a, b); }
+FFT_HD float2 csub (float2 a, float2 b) { return f2_sub (a, b); }
 // a * w (DIR < 0) or a * conj(w) (DIR > 0); tables always hold the forward twiddle
 template <int DIR>
 FFT_HD float2 cmul_dir (float2 a, float2 w)
 {
+    const float2 t = f2_mul (a, make_float2 (w.x, w.x));
     if (DIR < 0)
-        return make_float2 (a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
-    return make_float2 (a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y);
+        return f2_fma (make_float2 (a.y, a.x), make_float2 (-w.y, w.y), t); // (ax wx - ay wy, ay wx + ax wy)
+    return f2_fma (make_float2 (a.y, a.x), make_float2 (w.y, -w.y), t);     // (ax wx + ay wy, ay wx - ax wy)
 }
 // a * (-i) forward, a * (+i) backward
 template <int DIR>
@@ -268,27 +307,6 @@ FFT_HD int unordered_pos_real (int bin, int logW)
     return ((((b << logW) + r) * 2) << logW) + lane;
 }
 
-template <bool REAL_LAYOUT, int LOGM, bool UNORD>
-FFT_HD float2 load_bin (const float* base, int bin, int logW)
-{
-    if constexpr (! UNORD)
-        return __ldg (reinterpret_cast<const float2*> (base) + bin);
-    const int p = REAL_LAYOUT ? unordered_pos_real<LOGM> (bin, logW) : unordered_pos_complex<LOGM> (bin, logW);
-    return make_float2 (__ldg (base + p), __ldg (base + p + (1 << logW)));
-}
-template <bool REAL_LAYOUT, int LOGM, bool UNORD>
-FFT_HD void store_bin (float* base, int bin, int logW, float2 v)
-{
-    if constexpr (! UNORD)
-    {
-        reinterpret_cast<float2*> (base)[bin] = v;
-        return;
-    }
-    const int p = REAL_LAYOUT ? unordered_pos_real<LOGM> (bin, logW) : unordered_pos_complex<LOGM> (bin, logW);
-    base[p] = v.x;
-    base[p + (1 << logW)] = v.y;
-}
-
 // ---------------------------------------------------------------------------------------------
 // one Stockham stage on the thread's R registers.  On entry v[m] = x_s[j + m T] (x_s = stage input in
 // natural order); on exit of the last stage v[m] = X[j + m T].
@@ -366,6 +384,85 @@ struct Stages
 };
 
 // ---------------------------------------------------------------------------------------------
+// unordered I/O goes through a shared-memory staging image of the spectrum IN THE UNORDERED LAYOUT, so
+// that global memory only ever sees linear 128-bit accesses; the permutation is paid on-chip.
+// Staging pad: one W-float gap per 2 W^2 floats keeps both the scattered 4-byte accesses (runs of W
+// lanes at stride 2 W^2) and the linear 16-byte accesses conflict free.
+// ---------------------------------------------------------------------------------------------
+FFT_HD int upad (int p, int logW) { return p + ((p >> (2 * logW + 1)) << logW); }
+
+FFT_HD float lds1 (const float* p)
+{
+#ifdef CHOWDSP_EMU
+    if (emu::ctx.log)
+        emu::ctx.log->push_back ({ (uint32_t) ((const char*) p - emu::ctx.smem), 4, 0 });
+#endif
+    return *p;
+}
+FFT_HD void sts1 (float* p, float v)
+{
+#ifdef CHOWDSP_EMU
+    if (emu::ctx.log)
+        emu::ctx.log->push_back ({ (uint32_t) ((const char*) p - emu::ctx.smem), 4, 1 });
+#endif
+    *p = v;
+}
+FFT_HD float4 lds4 (const float* p)
+{
+#ifdef CHOWDSP_EMU
+    if (emu::ctx.log)
+        emu::ctx.log->push_back ({ (uint32_t) ((const char*) p - emu::ctx.smem), 16, 0 });
+#endif
+    return *reinterpret_cast<const float4*> (p);
+}
+FFT_HD void sts4 (float* p, float4 v)
+{
+#ifdef CHOWDSP_EMU
+    if (emu::ctx.log)
+        emu::ctx.log->push_back ({ (uint32_t) ((const char*) p - emu::ctx.smem), 16, 1 });
+#endif
+    *reinterpret_cast<float4*> (p) = v;
+}
+
+template <bool REAL_LAYOUT, int LOGM>
+FFT_HD float2 staged_load_bin (const float* sf, int bin, int logW)
+{
+    const int p = REAL_LAYOUT ? unordered_pos_real<LOGM> (bin, logW) : unordered_pos_complex<LOGM> (bin, logW);
+    return make_float2 (lds1 (sf + upad (p, logW)), lds1 (sf + upad (p + (1 << logW), logW)));
+}
+template <bool REAL_LAYOUT, int LOGM>
+FFT_HD void staged_store_bin (float* sf, int bin, int logW, float2 v)
+{
+    const int p = REAL_LAYOUT ? unordered_pos_real<LOGM> (bin, logW) : unordered_pos_complex<LOGM> (bin, logW);
+    sts1 (sf + upad (p, logW), v.x);
+    sts1 (sf + upad (p + (1 << logW), logW), v.y);
+}
+// linear 128-bit copies between global memory and the staging image (2M floats = T * R/2 float4)
+template <class G>
+FFT_HD void staging_fill (float* sf, const float* __restrict__ in, int j, int logW, bool active)
+{
+#pragma unroll
+    for (int i = 0; i < G::R / 2; ++i)
+    {
+        const int q = j + i * G::T;
+        const float4 val = active ? __ldg (reinterpret_cast<const float4*> (in) + q) : make_float4 (0.f, 0.f, 0.f, 0.f);
+        sts4 (sf + upad (4 * q, logW), val);
+    }
+}
+template <class G>
+FFT_HD void staging_drain (const float* sf, float* __restrict__ out, int j, int logW, bool active)
+{
+#pragma unroll
+    for (int i = 0; i < G::R / 2; ++i)
+    {
+        const int q = j + i * G::T;
+        const float4 val = lds4 (sf + upad (4 * q, logW));
+        if (active)
+            reinterpret_cast<float4*> (out)[q] = val;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // the kernel.  blockDim.x = T * (transforms per CTA); dynamic smem = transforms per CTA * SMEM_F2 * 8.
 // ---------------------------------------------------------------------------------------------
 template <int LOGM, int R, int KIND, bool UNORD>
@@ -374,6 +471,7 @@ FFT_HD void fft_body (const FftArgs& a)
     using G = Geo<LOGM, R>;
     constexpr int DIR = (KIND == C2C_FWD || KIND == R2C) ? -1 : +1;
     constexpr int M = G::M, T = G::T;
+    constexpr int SMEM_F2 = UNORD ? G::SMEM_F2_UNORD : G::SMEM_F2;
     FFT_DYN_SMEM (float2, smem);
 
     const int tid = (int) threadIdx.x;
@@ -382,13 +480,17 @@ FFT_HD void fft_body (const FftArgs& a)
     const int per_cta = (int) blockDim.x / T;
     const long long x = (long long) blockIdx.x * per_cta + lt;
     const bool active = x < a.batch;
-    float2* s = smem + lt * G::SMEM_F2;
+    float2* s = smem + lt * SMEM_F2;
+    float* sf = reinterpret_cast<float*> (s); // the same buffer seen as the unordered staging image
+    const int logW = a.logW;
+    const float2 zero2 = make_float2 (0.f, 0.f);
 
     const long long xo = active ? x / a.inner : 0, xi = active ? x - xo * a.inner : 0;
     const float* __restrict__ in = a.in + xo * a.in_outer + xi * a.in_inner;
     float* __restrict__ out = a.out + xo * a.out_outer + xi * a.out_inner;
 
     float2 v[R];
+    bool smem_was_read = false; // a barrier is needed before the exchange buffer is overwritten
 
     // ---- prologue: v[m] = stage-0 input element j + m T -------------------------------------------
     if constexpr (KIND == C2C_FWD || KIND == R2C)
@@ -396,31 +498,65 @@ FFT_HD void fft_body (const FftArgs& a)
         // interleaved complex, or real samples read as (x[2n], x[2n+1]) pairs
 #pragma unroll
         for (int m = 0; m < R; ++m)
-            v[m] = active ? __ldg (reinterpret_cast<const float2*> (in) + j + m * T) : make_float2 (0.f, 0.f);
+            v[m] = active ? __ldg (reinterpret_cast<const float2*> (in) + j + m * T) : zero2;
     }
     else if constexpr (KIND == C2C_BWD)
     {
+        if constexpr (UNORD)
+        {
+            staging_fill<G> (sf, in, j, logW, active);
+            __syncthreads();
 #pragma unroll
-        for (int m = 0; m < R; ++m)
-            v[m] = active ? load_bin<false, LOGM, UNORD> (in, j + m * T, a.logW) : make_float2 (0.f, 0.f);
+            for (int m = 0; m < R; ++m)
+                v[m] = staged_load_bin<false, LOGM> (sf, j + m * T, logW);
+            smem_was_read = true;
+        }
+        else
+        {
+#pragma unroll
+            for (int m = 0; m < R; ++m)
+                v[m] = active ? __ldg (reinterpret_cast<const float2*> (in) + j + m * T) : zero2;
+        }
     }
     else // C2R: merge step  Z'[k] = (X[k] + X*[M-k]) + i conj(w_k) (X[k] - X*[M-k]),  w_k = e^{-2 pi i k / 2M}
     {
+        // fetch this thread's bin pairs (k, M-k), k = j + m T < M/2, into v[2m], v[2m+1];
+        // thread 0's first pair is (bin 0 = (DC, Nyquist), bin M/2) instead
+        if constexpr (UNORD)
+        {
+            staging_fill<G> (sf, in, j, logW, active);
+            __syncthreads();
+        }
 #pragma unroll
         for (int m = 0; m < R / 2; ++m)
         {
-            const int k = j + m * T; // k < M/2
-            if (m == 0 && j == 0)
+            const int k = j + m * T;
+            const int ka = k, kb = (m == 0 && j == 0) ? M / 2 : M - k;
+            if constexpr (UNORD)
             {
-                const float2 x0 = active ? load_bin<true, LOGM, UNORD> (in, 0, a.logW) : make_float2 (0.f, 0.f);     // (DC, Nyquist)
-                const float2 xh = active ? load_bin<true, LOGM, UNORD> (in, M / 2, a.logW) : make_float2 (0.f, 0.f);
-                sts2 (s + pad (0), make_float2 (x0.x + x0.y, x0.x - x0.y));
-                sts2 (s + pad (M / 2), make_float2 (2.f * xh.x, -2.f * xh.y));
+                v[2 * m] = staged_load_bin<true, LOGM> (sf, ka, logW);
+                v[2 * m + 1] = staged_load_bin<true, LOGM> (sf, kb, logW);
             }
             else
             {
-                const float2 xa = active ? load_bin<true, LOGM, UNORD> (in, k, a.logW) : make_float2 (0.f, 0.f);
-                const float2 xb = active ? load_bin<true, LOGM, UNORD> (in, M - k, a.logW) : make_float2 (0.f, 0.f);
+                v[2 * m] = active ? __ldg (reinterpret_cast<const float2*> (in) + ka) : zero2;
+                v[2 * m + 1] = active ? __ldg (reinterpret_cast<const float2*> (in) + kb) : zero2;
+            }
+        }
+        if constexpr (UNORD)
+            __syncthreads(); // staging image fully consumed before the natural-order image overwrites it
+#pragma unroll
+        for (int m = 0; m < R / 2; ++m)
+        {
+            const int k = j + m * T;
+            const float2 xa = v[2 * m], xb = v[2 * m + 1];
+            if (m == 0 && j == 0)
+            {
+                sts2 (s + pad (0), make_float2 (xa.x + xa.y, xa.x - xa.y));
+                sts2 (s + pad (M / 2), make_float2 (2.f * xb.x, -2.f * xb.y));
+            }
+            else
+            {
                 const float2 w = __ldg (a.rtw + k);
                 const float2 e = make_float2 (xa.x + xb.x, xa.y - xb.y);
                 const float2 d = make_float2 (xa.x - xb.x, xa.y + xb.y);
@@ -431,10 +567,13 @@ FFT_HD void fft_body (const FftArgs& a)
         }
         __syncthreads();
         gather_natural<G> (v, j, s);
+        smem_was_read = true;
     }
 
     // ---- the stages -----------------------------------------------------------------------------
-    Stages<G, DIR, 0>::run (v, j, s, a.tw, KIND == C2R);
+    Stages<G, DIR, 0>::run (v, j, s, a.tw, smem_was_read);
+    if (G::S > 1)
+        smem_was_read = true;
 
     // ---- epilogue -------------------------------------------------------------------------------
     if constexpr (KIND == C2C_BWD || KIND == C2R)
@@ -448,16 +587,26 @@ FFT_HD void fft_body (const FftArgs& a)
     }
     else if constexpr (KIND == C2C_FWD)
     {
-        if (active)
+        if constexpr (UNORD)
+        {
+            if (smem_was_read)
+                __syncthreads();
+#pragma unroll
+            for (int m = 0; m < R; ++m)
+                staged_store_bin<false, LOGM> (sf, j + m * T, logW, v[m]);
+            __syncthreads();
+            staging_drain<G> (sf, out, j, logW, active);
+        }
+        else if (active)
         {
 #pragma unroll
             for (int m = 0; m < R; ++m)
-                store_bin<false, LOGM, UNORD> (out, j + m * T, a.logW, v[m]);
+                reinterpret_cast<float2*> (out)[j + m * T] = v[m];
         }
     }
     else // R2C: split step  X[k] = E - i w_k D,  X[M-k] = conj(E + i w_k D),  E,D = (Z[k] +- Z*[M-k]) / 2
     {
-        if (G::S > 1)
+        if (smem_was_read)
             __syncthreads();
         scatter_natural<G> (v, j, s);
         __syncthreads();
@@ -465,30 +614,48 @@ FFT_HD void fft_body (const FftArgs& a)
         for (int m = 0; m < R / 2; ++m)
         {
             const int k = j + m * T;
+            v[2 * m] = lds2 (s + pad (k));
+            v[2 * m + 1] = lds2 (s + pad ((m == 0 && j == 0) ? M / 2 : M - k));
+        }
+        if constexpr (UNORD)
+            __syncthreads(); // natural-order image fully consumed before the staging image overwrites it
+#pragma unroll
+        for (int m = 0; m < R / 2; ++m)
+        {
+            const int k = j + m * T;
+            const float2 za = v[2 * m], zb = v[2 * m + 1];
+            float2 xa, xb;
+            int ka = k, kb = M - k;
             if (m == 0 && j == 0)
             {
-                const float2 z0 = lds2 (s + pad (0));
-                const float2 zh = lds2 (s + pad (M / 2));
-                if (active)
-                {
-                    store_bin<true, LOGM, UNORD> (out, 0, a.logW, make_float2 (z0.x + z0.y, z0.x - z0.y)); // (DC, Nyquist)
-                    store_bin<true, LOGM, UNORD> (out, M / 2, a.logW, make_float2 (zh.x, -zh.y));
-                }
+                xa = make_float2 (za.x + za.y, za.x - za.y); // (DC, Nyquist)
+                xb = make_float2 (zb.x, -zb.y);              // X[M/2] = conj Z[M/2]
+                kb = M / 2;
             }
             else
             {
-                const float2 za = lds2 (s + pad (k));
-                const float2 zb = lds2 (s + pad (M - k));
                 const float2 w = __ldg (a.rtw + k);
                 const float2 e = make_float2 (0.5f * (za.x + zb.x), 0.5f * (za.y - zb.y));
                 const float2 d = make_float2 (0.5f * (za.x - zb.x), 0.5f * (za.y + zb.y));
                 const float2 wd = cmul_dir<-1> (d, w);
-                if (active)
-                {
-                    store_bin<true, LOGM, UNORD> (out, k, a.logW, make_float2 (e.x + wd.y, e.y - wd.x));
-                    store_bin<true, LOGM, UNORD> (out, M - k, a.logW, make_float2 (e.x - wd.y, -e.y - wd.x));
-                }
+                xa = make_float2 (e.x + wd.y, e.y - wd.x);
+                xb = make_float2 (e.x - wd.y, -e.y - wd.x);
             }
+            if constexpr (UNORD)
+            {
+                staged_store_bin<true, LOGM> (sf, ka, logW, xa);
+                staged_store_bin<true, LOGM> (sf, kb, logW, xb);
+            }
+            else if (active)
+            {
+                reinterpret_cast<float2*> (out)[ka] = xa;
+                reinterpret_cast<float2*> (out)[kb] = xb;
+            }
+        }
+        if constexpr (UNORD)
+        {
+            __syncthreads();
+            staging_drain<G> (sf, out, j, logW, active);
         }
     }
 }
@@ -501,6 +668,7 @@ struct Launch
     static constexpr int THREADS = G::T >= 256 ? G::T : 256;
     static constexpr int PER_CTA = THREADS / G::T;
     static constexpr int SMEM_BYTES = PER_CTA * G::SMEM_F2 * 8;
+    static constexpr int SMEM_BYTES_UNORD = PER_CTA * G::SMEM_F2_UNORD * 8;
     static constexpr int MIN_BLOCKS = THREADS <= 256 ? 4 : (THREADS <= 512 ? 2 : 1);
 };
 

@@ -21,7 +21,7 @@ int run_one (FftArgs a)
     a.tw = tw.data();
     a.rtw = rtw.data();
     const unsigned grid = (unsigned) ((a.batch + L::PER_CTA - 1) / L::PER_CTA);
-    emu::launch (fft_kernel<LOGM, R, KIND, UNORD>, dim3 (grid), dim3 (L::THREADS), (size_t) L::SMEM_BYTES, a);
+    emu::launch (fft_kernel<LOGM, R, KIND, UNORD>, dim3 (grid), dim3 (L::THREADS), (size_t) (UNORD ? L::SMEM_BYTES_UNORD : L::SMEM_BYTES), a);
     return 0;
 }
 

@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""Device-resident throughput sweep over sizes / kinds / layouts (CUDA-event timed, buffers > L2).
+Prints one line per case: algorithmic GB/s and fraction of the measured HBM peak.  GPU only."""
+import argparse
+import json
+import math
+import os
+import sys
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import chowdsp_fft_b200 as cf  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--bytes", type=float, default=1.0, help="GiB per buffer")
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--sizes", default="")
+    ap.add_argument("--json", default="")
+    args = ap.parse_args()
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        peak = 6650.0
+    total_floats = int(args.bytes * 2**30 / 4)
+    x = torch.rand(total_floats, device="cuda") * 2 - 1
+    y = torch.empty_like(x)
+    stream = torch.cuda.current_stream()
+    rows = []
+    sizes = [int(s) for s in args.sizes.split(",")] if args.sizes else [1 << l for l in range(5, 16)]
+    for is_c in (True, False):
+        for N in sizes:
+            nfl = 2 * N if is_c else N
+            try:
+                s = cf.fft_new_setup(N, cf.FFT_COMPLEX if is_c else cf.FFT_REAL, True)
+            except cf.FFTError:
+                continue
+            batch = total_floats // nfl
+            for direction in (cf.FFT_FORWARD, cf.FFT_BACKWARD):
+                for ordered in (True, False):
+                    def step():
+                        cf.fft_transform_batched(s, x, y, batch, nfl, nfl, direction, ordered, stream)
+                    for _ in range(3):
+                        step()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    torch.cuda.synchronize()
+                    e0.record(stream)
+                    for _ in range(args.steps):
+                        step()
+                    e1.record(stream)
+                    torch.cuda.synchronize()
+                    ms = e0.elapsed_time(e1) / args.steps
+                    gbs = batch * nfl * 8 / (ms * 1e-3) / 1e9
+                    gfl = batch * (5.0 if is_c else 2.5) * N * math.log2(N) / (ms * 1e-3) / 1e9
+                    row = dict(kind=("C2C" if is_c else ("R2C" if direction == 0 else "C2R")), N=N,
+                               dir="fwd" if direction == 0 else "bwd", layout="ordered" if ordered else "unordered",
+                               batch=batch, ms=ms, gbs=gbs, frac=gbs / peak, gflops=gfl)
+                    rows.append(row)
+                    print(f"{row['kind']:4s} N={N:6d} {row['dir']} {row['layout']:9s} batch={batch:8d} {ms:8.4f} ms {gbs:8.1f} GB/s  frac={gbs/peak:5.3f}  {gfl/1e3:6.2f} TFLOP/s", flush=True)
+            cf.fft_destroy_setup(s)
+    if args.json:
+        json.dump({"peak_gbs": peak, "rows": rows}, open(args.json, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
