@@ -295,10 +295,9 @@ int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inne
     a.out_outer = out_outer;
     a.inner = inner;
     a.batch = outer * inner;
-    a.logW = p->logW;
     a.tw = t.tw;
     a.rtw = t.rtw;
-    const cudaError_t e = launch_fft (p->logM, kind_of (p, direction), ! ordered, a, stream);
+    const cudaError_t e = launch_fft (p->logM, kind_of (p, direction), ordered ? 0 : p->logW, a, stream);
     if (e != cudaSuccess)
         return fail_cuda (e, "fft kernel launch");
     return 0;

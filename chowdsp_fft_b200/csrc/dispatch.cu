@@ -15,12 +15,12 @@ void count_launch() { g_launches.fetch_add (1, std::memory_order_relaxed); }
 
 #define CFB_FOR_SIZES(X) X (4) X (5) X (6) X (7) X (8) X (9) X (10) X (11) X (12) X (13) X (14)
 
-cudaError_t launch_fft (int logM, int kind, bool unordered, const FftArgs& args, cudaStream_t stream)
+cudaError_t launch_fft (int logM, int kind, int logW, const FftArgs& args, cudaStream_t stream)
 {
     switch (logM)
     {
 #define X(n) \
-    case n: return launch_fft_##n (kind, unordered, args, stream);
+    case n: return launch_fft_##n (kind, logW, args, stream);
         CFB_FOR_SIZES (X)
 #undef X
         default: return cudaErrorInvalidValue;

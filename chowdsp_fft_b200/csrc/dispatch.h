@@ -11,7 +11,8 @@ constexpr int kMaxLogM = 14; // 16384 complex points: the largest single-kernel 
 constexpr int kRadix = 16;   // complex points per thread
 
 // One launch of the single-kernel transform (complex length 2^logM per transform).
-cudaError_t launch_fft (int logM, int kind, bool unordered, const FftArgs& args, cudaStream_t stream);
+// logW: 0 = ordered output/input, 2 / 3 = the reference's 4- / 8-lane unordered layout
+cudaError_t launch_fft (int logM, int kind, int logW, const FftArgs& args, cudaStream_t stream);
 // number of float2 entries of the stage twiddle table for 2^logM, and the fill routine (fp64 -> fp32)
 int stage_twiddle_len (int logM);
 void fill_stage_twiddles_rt (int logM, float2* tw);
@@ -25,7 +26,7 @@ void count_launch();
 
 // per-size entry points, one translation unit each (fft_inst.cu compiled with -DCFB_LOGM=n)
 #define CFB_DECL_INST(n)                                                                       \
-    cudaError_t launch_fft_##n (int kind, bool unordered, const FftArgs& args, cudaStream_t stream); \
+    cudaError_t launch_fft_##n (int kind, int logW, const FftArgs& args, cudaStream_t stream);      \
     int stage_twiddle_len_##n();                                                               \
     void fill_stage_twiddles_##n (float2* tw);
 CFB_DECL_INST (4)

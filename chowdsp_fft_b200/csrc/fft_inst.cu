@@ -9,12 +9,12 @@ namespace cfb
 {
 namespace
 {
-template <int KIND, bool UNORD>
+template <int KIND, int LOGW>
 cudaError_t launch_one (const FftArgs& a, cudaStream_t stream)
 {
     using L = Launch<CFB_LOGM, kRadix>;
-    auto kernel = fft_kernel<CFB_LOGM, kRadix, KIND, UNORD>;
-    constexpr int smem_bytes = UNORD ? L::SMEM_BYTES_UNORD : L::SMEM_BYTES;
+    auto kernel = fft_kernel<CFB_LOGM, kRadix, KIND, LOGW>;
+    constexpr int smem_bytes = LOGW != 0 ? L::SMEM_BYTES_UNORD : L::SMEM_BYTES;
     if (smem_bytes > 48 * 1024)
     {
         const cudaError_t e = cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
@@ -33,18 +33,26 @@ cudaError_t launch_one (const FftArgs& a, cudaStream_t stream)
 #define CFB_CAT2(a, b) a##b
 #define CFB_CAT(a, b) CFB_CAT2 (a, b)
 
-cudaError_t CFB_CAT (launch_fft_, CFB_LOGM) (int kind, bool unordered, const FftArgs& a, cudaStream_t stream)
+// logW: 0 = ordered, 2 = 4-lane unordered layout, 3 = 8-lane unordered layout.  The 8-lane layout needs
+// N % 64 == 0 (complex) / N % 128 == 0 (real), i.e. complex length >= 64 here.
+cudaError_t CFB_CAT (launch_fft_, CFB_LOGM) (int kind, int logW, const FftArgs& a, cudaStream_t stream)
 {
-    switch (kind * 2 + (unordered ? 1 : 0))
+    switch (kind * 4 + logW)
     {
-        case 0: return launch_one<C2C_FWD, false> (a, stream);
-        case 1: return launch_one<C2C_FWD, true> (a, stream);
-        case 2: return launch_one<C2C_BWD, false> (a, stream);
-        case 3: return launch_one<C2C_BWD, true> (a, stream);
-        case 4: return launch_one<R2C, false> (a, stream);
-        case 5: return launch_one<R2C, true> (a, stream);
-        case 6: return launch_one<C2R, false> (a, stream);
-        case 7: return launch_one<C2R, true> (a, stream);
+        case 0: return launch_one<C2C_FWD, 0> (a, stream);
+        case 2: return launch_one<C2C_FWD, 2> (a, stream);
+        case 4: return launch_one<C2C_BWD, 0> (a, stream);
+        case 6: return launch_one<C2C_BWD, 2> (a, stream);
+        case 8: return launch_one<R2C, 0> (a, stream);
+        case 10: return launch_one<R2C, 2> (a, stream);
+        case 12: return launch_one<C2R, 0> (a, stream);
+        case 14: return launch_one<C2R, 2> (a, stream);
+#if CFB_LOGM >= 6
+        case 3: return launch_one<C2C_FWD, 3> (a, stream);
+        case 7: return launch_one<C2C_BWD, 3> (a, stream);
+        case 11: return launch_one<R2C, 3> (a, stream);
+        case 15: return launch_one<C2R, 3> (a, stream);
+#endif
         default: return cudaErrorInvalidValue;
     }
 }

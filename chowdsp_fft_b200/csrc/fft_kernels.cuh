@@ -52,9 +52,8 @@ struct FftArgs
     long long in_inner, in_outer, out_inner, out_outer;
     int inner;
     int batch;           // total transforms
-    int logW;            // unordered layout: 3 = W8 (AVX handle), 2 = W4 (SSE handle)
     const float2* tw;    // stage twiddles, see twiddle_table_len()
-    const float2* rtw;   // real split twiddles exp(-2 pi i k / N), k < N/4 (R2C / C2R only)
+    const float2* rtw;   // real split twiddles exp(-2 pi i k / N) / 2, k < N/4 (R2C / C2R only)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -332,7 +331,9 @@ FFT_HD void stage_compute (float2 (&v)[G::R], int j, const float2* __restrict__ 
         RegFft<r, DIR, SUB>::run (&v[u]);
 }
 
-// scatter the stage's outputs to shared memory in the order the next stage reads them
+// Shared-memory addressing.  pad() is additive whenever one operand is a multiple of 16, so every
+// access below is written as (one per-thread base computed once) + (a compile-time padded offset):
+// the offset folds into the LDS/STS immediate and costs no integer instructions.
 template <class G, int STAGE>
 FFT_HD void stage_scatter (const float2 (&v)[G::R], int j, float2* s)
 {
@@ -343,25 +344,72 @@ FFT_HD void stage_scatter (const float2 (&v)[G::R], int j, float2* s)
         const int jv = j + u * G::T;
         const int k = jv & (Ns - 1);
         const int base = (jv - k) * r + k;
+        if constexpr (Ns % 16 == 0)
+        {
+            float2* sb = s + pad (base);
 #pragma unroll
-        for (int q = 0; q < r; ++q)
-            sts2 (s + pad (base + q * Ns), v[u + q * SUB]);
+            for (int q = 0; q < r; ++q)
+                sts2 (sb + pad (q * Ns), v[u + q * SUB]);
+        }
+        else if constexpr (Ns == 1 && r == 16)
+        {
+            float2* sb = s + 17 * jv; // pad (16 jv + q) = 17 jv + q
+#pragma unroll
+            for (int q = 0; q < r; ++q)
+                sts2 (sb + q, v[u + q * SUB]);
+        }
+        else
+        {
+#pragma unroll
+            for (int q = 0; q < r; ++q)
+                sts2 (s + pad (base + q * Ns), v[u + q * SUB]);
+        }
     }
 }
 
-template <class G>
+// pointer to natural-order element (j + m T) of the exchange buffer, m in [M0, M1)
+template <class G, int M0, int M1>
 FFT_HD void gather_natural (float2 (&v)[G::R], int j, const float2* s)
 {
+    if constexpr (G::T % 16 == 0)
+    {
+        const float2* sb = s + pad (j);
 #pragma unroll
-    for (int m = 0; m < G::R; ++m)
-        v[m] = lds2 (s + pad (j + m * G::T));
+        for (int m = M0; m < M1; ++m)
+            v[m] = lds2 (sb + pad (m * G::T));
+    }
+    else
+    {
+#pragma unroll
+        for (int m = M0; m < M1; ++m)
+            v[m] = lds2 (s + pad (j + m * G::T));
+    }
 }
-template <class G>
+template <class G, int M0, int M1>
 FFT_HD void scatter_natural (const float2 (&v)[G::R], int j, float2* s)
 {
+    if constexpr (G::T % 16 == 0)
+    {
+        float2* sb = s + pad (j);
 #pragma unroll
-    for (int m = 0; m < G::R; ++m)
-        sts2 (s + pad (j + m * G::T), v[m]);
+        for (int m = M0; m < M1; ++m)
+            sts2 (sb + pad (m * G::T), v[m]);
+    }
+    else
+    {
+#pragma unroll
+        for (int m = M0; m < M1; ++m)
+            sts2 (s + pad (j + m * G::T), v[m]);
+    }
+}
+// natural-order slot of the mirror element M - (j + m T), m < R/2 (the caller handles j == 0 && m == 0)
+template <class G>
+FFT_HD int mirror_slot (int j, int m)
+{
+    if constexpr (G::T % 16 == 0)
+        return pad (G::T - j) + pad (G::M - m * G::T - G::T); // (M - mT - T) + (T - j), first term % 16 == 0
+    else
+        return pad (G::M - j - m * G::T);
 }
 
 template <class G, int DIR, int STAGE>
@@ -377,7 +425,7 @@ struct Stages
                 __syncthreads(); // every thread has finished reading the previous exchange
             stage_scatter<G, STAGE> (v, j, s);
             __syncthreads();
-            gather_natural<G> (v, j, s);
+            gather_natural<G, 0, G::R> (v, j, s);
             Stages<G, DIR, STAGE + 1>::run (v, j, s, tw, true);
         }
     }
@@ -424,18 +472,72 @@ FFT_HD void sts4 (float* p, float4 v)
     *reinterpret_cast<float4*> (p) = v;
 }
 
-template <bool REAL_LAYOUT, int LOGM>
-FFT_HD float2 staged_load_bin (const float* sf, int bin, int logW)
+// Padded staging position (float index) of the bins a thread touches, as base(j) + constexpr(m).
+//   complex layout: bin j + m T            -> cplx (m)
+//   real layout:    bin k = j + m T, m<R/2 -> real_lo (m);   bin M - k -> real_hi (m)
+// Derivation: with L = M / W bins per lane row and L / T = R / W =: LT rows-per-... ratio, bin j + m T sits
+// in row r = m / LT at in-row index j + (m % LT) T; a row-local index i maps to block b = i / W, lane
+// i % W, padded position b (2 W^2 + W) + r 2 W + lane.  Odd rows of the real layout are reversed
+// (i -> (Q - i) mod Q), which turns j into -j; the wrap (i == 0) only ever hits thread j == 0 and is
+// patched with a select.  Falls back to the generic index computation when T < W.
+template <class G, int LOGW>
+struct UPos
 {
-    const int p = REAL_LAYOUT ? unordered_pos_real<LOGM> (bin, logW) : unordered_pos_complex<LOGM> (bin, logW);
-    return make_float2 (lds1 (sf + upad (p, logW)), lds1 (sf + upad (p + (1 << logW), logW)));
-}
-template <bool REAL_LAYOUT, int LOGM>
-FFT_HD void staged_store_bin (float* sf, int bin, int logW, float2 v)
+    static constexpr int W = 1 << LOGW, PW = 2 * W * W + W, T = G::T, M = G::M, R = G::R;
+    static constexpr int Q = M / W;                       // bins per lane row
+    static constexpr int LOGQ = G::LOGM - LOGW;
+    static constexpr bool FAST = (T >= W) && (R >= W);
+    static constexpr int LT = FAST ? R / W : 1;           // T-sized chunks per lane row
+    int j, ub_pos, ub_neg;
+    FFT_HD explicit UPos (int j_) : j (j_)
+    {
+        ub_pos = (j_ >> LOGW) * PW + (j_ & (W - 1));
+        ub_neg = ((-j_) >> LOGW) * PW + ((-j_) & (W - 1));
+    }
+    static FFT_HD int generic_complex (int bin) { return upad (unordered_pos_complex<G::LOGM> (bin, LOGW), LOGW); }
+    static FFT_HD int generic_real (int bin) { return upad (unordered_pos_real<G::LOGM> (bin, LOGW), LOGW); }
+
+    FFT_HD int cplx (int m) const
+    {
+        if constexpr (! FAST)
+            return generic_complex (j + m * T);
+        else
+            return ub_pos + (m % LT) * (T / W) * PW + (m / LT) * 2 * W;
+    }
+    FFT_HD int real_lo (int m) const
+    {
+        if constexpr (! FAST)
+            return generic_real (j + m * T);
+        else
+        {
+            const int r = m / LT, mp = m % LT;
+            if ((r & 1) == 0)
+                return ub_pos + mp * (T / W) * PW + r * 2 * W;
+            const int fast = ub_neg + ((Q - mp * T) / W) * PW + r * 2 * W;
+            return (mp == 0 && j == 0) ? r * 2 * W : fast;
+        }
+    }
+    FFT_HD int real_hi (int m) const // bin M - (j + m T); not valid for (j == 0 && m == 0)
+    {
+        if constexpr (! FAST)
+            return generic_real (M - j - m * T);
+        else
+        {
+            const int c = M - m * T;
+            const int rr = (c - T) >> LOGQ, e = (c - T) & (Q - 1);
+            const int fast = (rr & 1) == 0 ? ub_neg + ((T + e) / W) * PW + rr * 2 * W
+                                           : ub_pos + ((Q - e - T) / W) * PW + rr * 2 * W;
+            return (c % Q == 0 && j == 0) ? (c >> LOGQ) * 2 * W : fast;
+        }
+    }
+};
+template <int LOGW>
+FFT_CX int W_HALF_ROW() { return (1 << LOGW) * (1 << LOGW); } // padded staging position of real bin M/2 (row W/2, index 0)
+FFT_HD float2 staged_load (const float* sf, int upos, int W) { return make_float2 (lds1 (sf + upos), lds1 (sf + upos + W)); }
+FFT_HD void staged_store (float* sf, int upos, int W, float2 v)
 {
-    const int p = REAL_LAYOUT ? unordered_pos_real<LOGM> (bin, logW) : unordered_pos_complex<LOGM> (bin, logW);
-    sts1 (sf + upad (p, logW), v.x);
-    sts1 (sf + upad (p + (1 << logW), logW), v.y);
+    sts1 (sf + upos, v.x);
+    sts1 (sf + upos + W, v.y);
 }
 // linear 128-bit copies between global memory and the staging image (2M floats = T * R/2 float4)
 template <class G>
@@ -445,7 +547,7 @@ FFT_HD void staging_fill (float* sf, const float* __restrict__ in, int j, int lo
     for (int i = 0; i < G::R / 2; ++i)
     {
         const int q = j + i * G::T;
-        const float4 val = active ? __ldg (reinterpret_cast<const float4*> (in) + q) : make_float4 (0.f, 0.f, 0.f, 0.f);
+        const float4 val = __ldg (reinterpret_cast<const float4*> (in) + q);
         sts4 (sf + upad (4 * q, logW), val);
     }
 }
@@ -465,11 +567,12 @@ FFT_HD void staging_drain (const float* sf, float* __restrict__ out, int j, int 
 // ---------------------------------------------------------------------------------------------
 // the kernel.  blockDim.x = T * (transforms per CTA); dynamic smem = transforms per CTA * SMEM_F2 * 8.
 // ---------------------------------------------------------------------------------------------
-template <int LOGM, int R, int KIND, bool UNORD>
+template <int LOGM, int R, int KIND, int LOGW>
 FFT_HD void fft_body (const FftArgs& a)
 {
     using G = Geo<LOGM, R>;
     constexpr int DIR = (KIND == C2C_FWD || KIND == R2C) ? -1 : +1;
+    constexpr bool UNORD = LOGW != 0; // 0 = ordered; 2 / 3 = the reference's 4- / 8-lane unordered layout
     constexpr int M = G::M, T = G::T;
     constexpr int SMEM_F2 = UNORD ? G::SMEM_F2_UNORD : G::SMEM_F2;
     FFT_DYN_SMEM (float2, smem);
@@ -482,91 +585,95 @@ FFT_HD void fft_body (const FftArgs& a)
     const bool active = x < a.batch;
     float2* s = smem + lt * SMEM_F2;
     float* sf = reinterpret_cast<float*> (s); // the same buffer seen as the unordered staging image
-    const int logW = a.logW;
-    const float2 zero2 = make_float2 (0.f, 0.f);
+    constexpr int logW = LOGW;
 
-    const long long xo = active ? x / a.inner : 0, xi = active ? x - xo * a.inner : 0;
-    const float* __restrict__ in = a.in + xo * a.in_outer + xi * a.in_inner;
-    float* __restrict__ out = a.out + xo * a.out_outer + xi * a.out_inner;
+    // CTAs past the end of the batch re-read the last transform (loads stay unpredicated) and skip stores
+    const unsigned xc = active ? (unsigned) x : (unsigned) a.batch - 1u;
+    unsigned xo = 0, xi = xc;
+    if (a.inner < a.batch) // two-level batch (STFT gather); plain batches skip the division
+    {
+        xo = xc / (unsigned) a.inner;
+        xi = xc - xo * (unsigned) a.inner;
+    }
+    const float* __restrict__ in = a.in + (long long) xo * a.in_outer + (long long) xi * a.in_inner;
+    float* __restrict__ out = a.out + (long long) xo * a.out_outer + (long long) xi * a.out_inner;
 
     float2 v[R];
     bool smem_was_read = false; // a barrier is needed before the exchange buffer is overwritten
+    constexpr int WL = UNORD ? (1 << LOGW) : 1;
+    const UPos<G, UNORD ? LOGW : 2> up (j);
 
     // ---- prologue: v[m] = stage-0 input element j + m T -------------------------------------------
-    if constexpr (KIND == C2C_FWD || KIND == R2C)
+    if constexpr (KIND == C2C_FWD || KIND == R2C || (KIND == C2C_BWD && ! UNORD))
     {
-        // interleaved complex, or real samples read as (x[2n], x[2n+1]) pairs
+        // interleaved complex (natural order), or real samples read as (x[2n], x[2n+1]) pairs
+        const float2* __restrict__ in2 = reinterpret_cast<const float2*> (in) + j;
 #pragma unroll
         for (int m = 0; m < R; ++m)
-            v[m] = active ? __ldg (reinterpret_cast<const float2*> (in) + j + m * T) : zero2;
+            v[m] = __ldg (in2 + m * T);
     }
     else if constexpr (KIND == C2C_BWD)
     {
-        if constexpr (UNORD)
-        {
-            staging_fill<G> (sf, in, j, logW, active);
-            __syncthreads();
+        staging_fill<G> (sf, in, j, logW, active);
+        __syncthreads();
 #pragma unroll
-            for (int m = 0; m < R; ++m)
-                v[m] = staged_load_bin<false, LOGM> (sf, j + m * T, logW);
-            smem_was_read = true;
-        }
-        else
-        {
-#pragma unroll
-            for (int m = 0; m < R; ++m)
-                v[m] = active ? __ldg (reinterpret_cast<const float2*> (in) + j + m * T) : zero2;
-        }
+        for (int m = 0; m < R; ++m)
+            v[m] = staged_load (sf, up.cplx (m), WL);
+        smem_was_read = true;
     }
     else // C2R: merge step  Z'[k] = (X[k] + X*[M-k]) + i conj(w_k) (X[k] - X*[M-k]),  w_k = e^{-2 pi i k / 2M}
     {
-        // fetch this thread's bin pairs (k, M-k), k = j + m T < M/2, into v[2m], v[2m+1];
-        // thread 0's first pair is (bin 0 = (DC, Nyquist), bin M/2) instead
+        // This thread owns the pairs (k, M-k), k = j + m T < M/2 (thread 0's first pair is (0, M/2)).
+        // Z'[k] is its own stage-0 register m; Z'[M-k] belongs to thread T-j and travels through smem.
+        float2 xb[R / 2];
         if constexpr (UNORD)
         {
             staging_fill<G> (sf, in, j, logW, active);
             __syncthreads();
-        }
 #pragma unroll
-        for (int m = 0; m < R / 2; ++m)
-        {
-            const int k = j + m * T;
-            const int ka = k, kb = (m == 0 && j == 0) ? M / 2 : M - k;
-            if constexpr (UNORD)
+            for (int m = 0; m < R / 2; ++m)
             {
-                v[2 * m] = staged_load_bin<true, LOGM> (sf, ka, logW);
-                v[2 * m + 1] = staged_load_bin<true, LOGM> (sf, kb, logW);
+                v[m] = staged_load (sf, up.real_lo (m), WL);
+                xb[m] = staged_load (sf, (m == 0 && j == 0) ? W_HALF_ROW<LOGW>() : up.real_hi (m), WL);
             }
-            else
-            {
-                v[2 * m] = active ? __ldg (reinterpret_cast<const float2*> (in) + ka) : zero2;
-                v[2 * m + 1] = active ? __ldg (reinterpret_cast<const float2*> (in) + kb) : zero2;
-            }
-        }
-        if constexpr (UNORD)
             __syncthreads(); // staging image fully consumed before the natural-order image overwrites it
+        }
+        else
+        {
+            const float2* __restrict__ lo = reinterpret_cast<const float2*> (in) + j;
+            const float2* __restrict__ hi = reinterpret_cast<const float2*> (in) + (M - T) - j;
+#pragma unroll
+            for (int m = 0; m < R / 2; ++m)
+            {
+                const float2* ph = (m == 0 && j == 0) ? reinterpret_cast<const float2*> (in) + M / 2 : hi - m * T + T;
+                v[m] = __ldg (lo + m * T);
+                xb[m] = __ldg (ph);
+            }
+        }
+        const float2* __restrict__ rt = a.rtw + j;
 #pragma unroll
         for (int m = 0; m < R / 2; ++m)
         {
-            const int k = j + m * T;
-            const float2 xa = v[2 * m], xb = v[2 * m + 1];
+            const float2 xa = v[m], xm = xb[m];
+            const float2 wh = __ldg (rt + m * T);                          // w_k / 2
+            const float2 cm = make_float2 (xm.x, -xm.y);                   // conj X[M-k]
+            const float2 e = f2_add (xa, cm), d = f2_sub (xa, cm);
+            const float2 wd = cmul_dir<+1> (d, wh);                        // conj(w_k) d / 2
+            const float2 two = make_float2 (2.f, 2.f);
+            float2 zk = f2_fma (make_float2 (-wd.y, wd.x), two, e);                      // e + i conj(w) d
+            float2 zm = f2_fma (make_float2 (wd.y, wd.x), two, make_float2 (e.x, -e.y)); // conj(e - i conj(w) d)
+            int slot = mirror_slot<G> (j, m);
             if (m == 0 && j == 0)
             {
-                sts2 (s + pad (0), make_float2 (xa.x + xa.y, xa.x - xa.y));
-                sts2 (s + pad (M / 2), make_float2 (2.f * xb.x, -2.f * xb.y));
+                zk = make_float2 (xa.x + xa.y, xa.x - xa.y);   // Z'[0] from (DC, Nyquist)
+                zm = make_float2 (2.f * xm.x, -2.f * xm.y);    // Z'[M/2] = 2 conj X[M/2]
+                slot = pad (M / 2);
             }
-            else
-            {
-                const float2 w = __ldg (a.rtw + k);
-                const float2 e = make_float2 (xa.x + xb.x, xa.y - xb.y);
-                const float2 d = make_float2 (xa.x - xb.x, xa.y + xb.y);
-                const float2 wd = cmul_dir<+1> (d, w); // conj(w) * d
-                sts2 (s + pad (k), make_float2 (e.x - wd.y, e.y + wd.x));
-                sts2 (s + pad (M - k), make_float2 (e.x + wd.y, wd.x - e.y));
-            }
+            v[m] = zk;
+            sts2 (s + slot, zm);
         }
         __syncthreads();
-        gather_natural<G> (v, j, s);
+        gather_natural<G, R / 2, R> (v, j, s);
         smem_was_read = true;
     }
 
@@ -576,80 +683,69 @@ FFT_HD void fft_body (const FftArgs& a)
         smem_was_read = true;
 
     // ---- epilogue -------------------------------------------------------------------------------
-    if constexpr (KIND == C2C_BWD || KIND == C2R)
+    if constexpr (KIND == C2C_BWD || KIND == C2R || (KIND == C2C_FWD && ! UNORD))
     {
         if (active)
         {
+            float2* __restrict__ out2 = reinterpret_cast<float2*> (out) + j;
 #pragma unroll
             for (int m = 0; m < R; ++m)
-                reinterpret_cast<float2*> (out)[j + m * T] = v[m];
+                out2[m * T] = v[m];
         }
     }
     else if constexpr (KIND == C2C_FWD)
     {
-        if constexpr (UNORD)
-        {
-            if (smem_was_read)
-                __syncthreads();
-#pragma unroll
-            for (int m = 0; m < R; ++m)
-                staged_store_bin<false, LOGM> (sf, j + m * T, logW, v[m]);
+        if (smem_was_read)
             __syncthreads();
-            staging_drain<G> (sf, out, j, logW, active);
-        }
-        else if (active)
-        {
 #pragma unroll
-            for (int m = 0; m < R; ++m)
-                reinterpret_cast<float2*> (out)[j + m * T] = v[m];
-        }
+        for (int m = 0; m < R; ++m)
+            staged_store (sf, up.cplx (m), WL, v[m]);
+        __syncthreads();
+        staging_drain<G> (sf, out, j, logW, active);
     }
     else // R2C: split step  X[k] = E - i w_k D,  X[M-k] = conj(E + i w_k D),  E,D = (Z[k] +- Z*[M-k]) / 2
     {
+        // Z[k], k = j + m T < M/2, is this thread's register m; Z[M-k] is register R-1-m of thread T-j:
+        // only the upper half of the spectrum goes through shared memory.
         if (smem_was_read)
             __syncthreads();
-        scatter_natural<G> (v, j, s);
+        scatter_natural<G, R / 2, R> (v, j, s);
         __syncthreads();
+        float2 zb[R / 2];
 #pragma unroll
         for (int m = 0; m < R / 2; ++m)
-        {
-            const int k = j + m * T;
-            v[2 * m] = lds2 (s + pad (k));
-            v[2 * m + 1] = lds2 (s + pad ((m == 0 && j == 0) ? M / 2 : M - k));
-        }
+            zb[m] = lds2 (s + ((m == 0 && j == 0) ? pad (M / 2) : mirror_slot<G> (j, m)));
         if constexpr (UNORD)
             __syncthreads(); // natural-order image fully consumed before the staging image overwrites it
+        const float2* __restrict__ rt = a.rtw + j;
+        float2* __restrict__ lo = reinterpret_cast<float2*> (out) + j;
+        float2* __restrict__ hi = reinterpret_cast<float2*> (out) + (M - T) - j;
 #pragma unroll
         for (int m = 0; m < R / 2; ++m)
         {
-            const int k = j + m * T;
-            const float2 za = v[2 * m], zb = v[2 * m + 1];
-            float2 xa, xb;
-            int ka = k, kb = M - k;
-            if (m == 0 && j == 0)
+            const float2 za = v[m], zm = zb[m];
+            const float2 wh = __ldg (rt + m * T);                          // w_k / 2
+            const float2 cm = make_float2 (zm.x, -zm.y);                   // conj Z[M-k]
+            const float2 e = f2_add (za, cm), d = f2_sub (za, cm);         // 2E, 2D
+            const float2 wd = cmul_dir<-1> (d, wh);                        // w_k D
+            float2 xa = f2_fma (e, make_float2 (0.5f, 0.5f), make_float2 (wd.y, -wd.x));    // E - i w D
+            float2 xm = f2_fma (e, make_float2 (0.5f, -0.5f), make_float2 (-wd.y, -wd.x));  // conj(E + i w D)
+            const bool special = (m == 0 && j == 0);
+            if (special)
             {
                 xa = make_float2 (za.x + za.y, za.x - za.y); // (DC, Nyquist)
-                xb = make_float2 (zb.x, -zb.y);              // X[M/2] = conj Z[M/2]
-                kb = M / 2;
-            }
-            else
-            {
-                const float2 w = __ldg (a.rtw + k);
-                const float2 e = make_float2 (0.5f * (za.x + zb.x), 0.5f * (za.y - zb.y));
-                const float2 d = make_float2 (0.5f * (za.x - zb.x), 0.5f * (za.y + zb.y));
-                const float2 wd = cmul_dir<-1> (d, w);
-                xa = make_float2 (e.x + wd.y, e.y - wd.x);
-                xb = make_float2 (e.x - wd.y, -e.y - wd.x);
+                xm = make_float2 (zm.x, -zm.y);              // X[M/2] = conj Z[M/2]
             }
             if constexpr (UNORD)
             {
-                staged_store_bin<true, LOGM> (sf, ka, logW, xa);
-                staged_store_bin<true, LOGM> (sf, kb, logW, xb);
+                staged_store (sf, up.real_lo (m), WL, xa);
+                staged_store (sf, special ? W_HALF_ROW<LOGW>() : up.real_hi (m), WL, xm);
             }
             else if (active)
             {
-                reinterpret_cast<float2*> (out)[ka] = xa;
-                reinterpret_cast<float2*> (out)[kb] = xb;
+                lo[m * T] = xa;
+                float2* ph = special ? reinterpret_cast<float2*> (out) + M / 2 : hi - m * T + T;
+                *ph = xm;
             }
         }
         if constexpr (UNORD)
@@ -672,10 +768,10 @@ struct Launch
     static constexpr int MIN_BLOCKS = THREADS <= 256 ? 4 : (THREADS <= 512 ? 2 : 1);
 };
 
-template <int LOGM, int R, int KIND, bool UNORD>
+template <int LOGM, int R, int KIND, int LOGW>
 __global__ void __launch_bounds__ (Launch<LOGM, R>::THREADS, Launch<LOGM, R>::MIN_BLOCKS) fft_kernel (const FftArgs a)
 {
-    fft_body<LOGM, R, KIND, UNORD> (a);
+    fft_body<LOGM, R, KIND, LOGW> (a);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -699,12 +795,12 @@ inline void fill_stage_twiddles (float2* tw) // Geo<LOGM,R>::TW_LEN entries
             }
     }
 }
-inline void fill_real_twiddles (float2* rtw, int M) // M/2 entries: exp(-2 pi i k / 2M)
+inline void fill_real_twiddles (float2* rtw, int M) // M/2 entries: exp(-2 pi i k / 2M) / 2 (the split step's 1/2 folded in, exact)
 {
     for (int k = 0; k < M / 2; ++k)
     {
         const long double ang = -2.0L * 3.141592653589793238462643383279502884L * (long double) k / (long double) (2LL * M);
-        rtw[k] = make_float2 ((float) cosl (ang), (float) sinl (ang));
+        rtw[k] = make_float2 (0.5f * (float) cosl (ang), 0.5f * (float) sinl (ang));
     }
 }
 } // namespace cfb

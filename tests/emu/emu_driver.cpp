@@ -9,7 +9,7 @@ using namespace cfb;
 
 namespace
 {
-template <int LOGM, int KIND, bool UNORD>
+template <int LOGM, int KIND, int LOGW>
 int run_one (FftArgs a)
 {
     constexpr int R = 16;
@@ -21,23 +21,33 @@ int run_one (FftArgs a)
     a.tw = tw.data();
     a.rtw = rtw.data();
     const unsigned grid = (unsigned) ((a.batch + L::PER_CTA - 1) / L::PER_CTA);
-    emu::launch (fft_kernel<LOGM, R, KIND, UNORD>, dim3 (grid), dim3 (L::THREADS), (size_t) (UNORD ? L::SMEM_BYTES_UNORD : L::SMEM_BYTES), a);
+    emu::launch (fft_kernel<LOGM, R, KIND, LOGW>, dim3 (grid), dim3 (L::THREADS), (size_t) (LOGW != 0 ? L::SMEM_BYTES_UNORD : L::SMEM_BYTES), a);
     return 0;
 }
 
 template <int LOGM>
-int run_logm (int kind, int unord, const FftArgs& a)
+int run_logm (int kind, int logW, const FftArgs& a)
 {
-    switch (kind * 2 + (unord ? 1 : 0))
+    switch (kind * 4 + logW)
     {
-        case 0: return run_one<LOGM, C2C_FWD, false> (a);
-        case 1: return run_one<LOGM, C2C_FWD, true> (a);
-        case 2: return run_one<LOGM, C2C_BWD, false> (a);
-        case 3: return run_one<LOGM, C2C_BWD, true> (a);
-        case 4: return run_one<LOGM, R2C, false> (a);
-        case 5: return run_one<LOGM, R2C, true> (a);
-        case 6: return run_one<LOGM, C2R, false> (a);
-        case 7: return run_one<LOGM, C2R, true> (a);
+        case 0: return run_one<LOGM, C2C_FWD, 0> (a);
+        case 2: return run_one<LOGM, C2C_FWD, 2> (a);
+        case 4: return run_one<LOGM, C2C_BWD, 0> (a);
+        case 6: return run_one<LOGM, C2C_BWD, 2> (a);
+        case 8: return run_one<LOGM, R2C, 0> (a);
+        case 10: return run_one<LOGM, R2C, 2> (a);
+        case 12: return run_one<LOGM, C2R, 0> (a);
+        case 14: return run_one<LOGM, C2R, 2> (a);
+    }
+    if constexpr (LOGM >= 6)
+    {
+        switch (kind * 4 + logW)
+        {
+            case 3: return run_one<LOGM, C2C_FWD, 3> (a);
+            case 7: return run_one<LOGM, C2C_BWD, 3> (a);
+            case 11: return run_one<LOGM, R2C, 3> (a);
+            case 15: return run_one<LOGM, C2R, 3> (a);
+        }
     }
     return -1;
 }
@@ -57,23 +67,22 @@ int emu_fft (int logM, int kind, int unord, int logW, const float* in, float* ou
     a.out_outer = out_outer;
     a.inner = inner;
     a.batch = batch;
-    a.logW = logW;
     emu::g_log_smem = log_conflicts != 0;
     emu::g_stats = {};
     int rc = -1;
     switch (logM)
     {
-        case 4: rc = run_logm<4> (kind, unord, a); break;
-        case 5: rc = run_logm<5> (kind, unord, a); break;
-        case 6: rc = run_logm<6> (kind, unord, a); break;
-        case 7: rc = run_logm<7> (kind, unord, a); break;
-        case 8: rc = run_logm<8> (kind, unord, a); break;
-        case 9: rc = run_logm<9> (kind, unord, a); break;
-        case 10: rc = run_logm<10> (kind, unord, a); break;
-        case 11: rc = run_logm<11> (kind, unord, a); break;
-        case 12: rc = run_logm<12> (kind, unord, a); break;
-        case 13: rc = run_logm<13> (kind, unord, a); break;
-        case 14: rc = run_logm<14> (kind, unord, a); break;
+        case 4: rc = run_logm<4> (kind, unord ? logW : 0, a); break;
+        case 5: rc = run_logm<5> (kind, unord ? logW : 0, a); break;
+        case 6: rc = run_logm<6> (kind, unord ? logW : 0, a); break;
+        case 7: rc = run_logm<7> (kind, unord ? logW : 0, a); break;
+        case 8: rc = run_logm<8> (kind, unord ? logW : 0, a); break;
+        case 9: rc = run_logm<9> (kind, unord ? logW : 0, a); break;
+        case 10: rc = run_logm<10> (kind, unord ? logW : 0, a); break;
+        case 11: rc = run_logm<11> (kind, unord ? logW : 0, a); break;
+        case 12: rc = run_logm<12> (kind, unord ? logW : 0, a); break;
+        case 13: rc = run_logm<13> (kind, unord ? logW : 0, a); break;
+        case 14: rc = run_logm<14> (kind, unord ? logW : 0, a); break;
         default: break;
     }
     if (stats)

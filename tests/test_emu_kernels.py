@@ -62,9 +62,9 @@ def test_emulated_kernels_match_oracle(emu, oracle_mod, N, is_c, avx):
             if s[0]:
                 M = N if is_c else N // 2
                 if M >= 512:
-                    # shared-memory exchanges: <= 7% extra wavefronts overall (the mirrored reads of the
+                    # shared-memory exchanges: <= 10% extra wavefronts overall (the mirrored reads of the
                     # real split step collide on one slot per 16), nothing worse than 2x on one access
-                    assert s[1] <= 1.07 * s[2], s
+                    assert s[1] <= 1.10 * s[2], s
                     assert s[3] <= 200, s
                 else:
                     # several small transforms share a warp; their staging images alias in the banks
