@@ -77,9 +77,15 @@ struct Geo
     static_assert (M >= R, "transform smaller than the per-thread radix");
     static FFT_CX int radix (int s) { return s == S - 1 ? RLAST : R; }
     static FFT_CX int ns (int s) { return ipow (R, s); } // product of the radices before stage s
-    // float2 offset of stage s's twiddle table (stage 0 has none): [(t-1) * Ns + k], t = 1..r-1
-    static FFT_CX int tw_off (int s) { return s <= 1 ? 0 : tw_off (s - 1) + (radix (s - 1) - 1) * ns (s - 1); }
-    static constexpr int TW_LEN = S == 1 ? 0 : tw_off (S - 1) + (RLAST - 1) * ns (S - 1);
+    // Stage twiddle tables (stage 0 has none), all holding forward twiddles exp(-2 pi i k q / (Ns r)):
+    //   radix-16 stage : 6 rows q in {1, 2, 3, 4, 8, 12} x Ns entries; the other nine powers are one
+    //                    product of two rows each (w^q = w^(q%4) w^(q-q%4)), computed in registers
+    //   last stage r<16: (r-1) rows q = 1..r-1 x T entries (k = j only); the R/r butterflies of a thread
+    //                    differ by the constant factors W16^(u q), applied with immediates
+    static_assert (R_ == 16, "the twiddle scheme below assumes 16 points per thread");
+    static FFT_CX int tw_rows (int s) { return radix (s) == 16 ? 6 * ns (s) : (radix (s) - 1) * T; }
+    static FFT_CX int tw_off (int s) { return s <= 1 ? 0 : tw_off (s - 1) + tw_rows (s - 1); }
+    static constexpr int TW_LEN = S == 1 ? 0 : tw_off (S - 1) + tw_rows (S - 1);
 };
 
 // one padding slot per 16 float2: stride-2^a accesses (a <= 4) and unit-stride accesses are both
@@ -89,6 +95,29 @@ FFT_CX int pad (int i) { return i + (i >> 4); }
 // ---------------------------------------------------------------------------------------------
 // memory helpers (shared-memory ones are instrumented in the emulator)
 // ---------------------------------------------------------------------------------------------
+// streaming global loads: read-only path, no L1 allocation (the inputs are touched once; the twiddle
+// tables are what should stay in L1)
+FFT_HD float2 ldg_stream (const float2* p)
+{
+#ifdef CHOWDSP_EMU
+    return *p;
+#else
+    float2 r;
+    asm volatile ("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+#endif
+}
+FFT_HD float4 ldg_stream (const float4* p)
+{
+#ifdef CHOWDSP_EMU
+    return *p;
+#else
+    float4 r;
+    asm volatile ("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+#endif
+}
+
 FFT_HD float2 lds2 (const float2* p)
 {
 #ifdef CHOWDSP_EMU
@@ -190,6 +219,31 @@ FFT_HD float2 mul_w16 (float2 a)
     constexpr float sabs = (n == 1 || n == 7 || n == 9 || n == 15) ? S1 : (n == 2 || n == 6 || n == 10 || n == 14) ? H : C1;
     constexpr float s = n < 8 ? sabs : -sabs;
     return cmul_dir<DIR> (a, make_float2 (c, -s));
+}
+
+// a * W16^(DIR * num): num is a loop constant after unrolling, so the switch folds away
+template <int DIR>
+FFT_HD float2 mul_w16_rt (float2 a, int num)
+{
+    switch (num & 15)
+    {
+        case 0: return a;
+        case 1: return mul_w16<DIR, 1> (a);
+        case 2: return mul_w16<DIR, 2> (a);
+        case 3: return mul_w16<DIR, 3> (a);
+        case 4: return mul_w16<DIR, 4> (a);
+        case 5: return mul_w16<DIR, 5> (a);
+        case 6: return mul_w16<DIR, 6> (a);
+        case 7: return mul_w16<DIR, 7> (a);
+        case 8: return mul_w16<DIR, 8> (a);
+        case 9: return mul_w16<DIR, 9> (a);
+        case 10: return mul_w16<DIR, 10> (a);
+        case 11: return mul_w16<DIR, 11> (a);
+        case 12: return mul_w16<DIR, 12> (a);
+        case 13: return mul_w16<DIR, 13> (a);
+        case 14: return mul_w16<DIR, 14> (a);
+        default: return mul_w16<DIR, 15> (a);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -314,16 +368,45 @@ template <class G, int DIR, int STAGE>
 FFT_HD void stage_compute (float2 (&v)[G::R], int j, const float2* __restrict__ tw)
 {
     constexpr int r = G::radix (STAGE), Ns = G::ns (STAGE), SUB = G::R / r;
-    if constexpr (STAGE > 0)
+    if constexpr (STAGE > 0 && r == 16)
     {
-        const float2* __restrict__ t = tw + G::tw_off (STAGE);
+        const float2* __restrict__ t = tw + G::tw_off (STAGE) + (j & (Ns - 1));
+        const float2 w1 = __ldg (t), w2 = __ldg (t + Ns), w3 = __ldg (t + 2 * Ns);
+        const float2 w4 = __ldg (t + 3 * Ns), w8 = __ldg (t + 4 * Ns), w12 = __ldg (t + 5 * Ns);
+        v[1] = cmul_dir<DIR> (v[1], w1);
+        v[2] = cmul_dir<DIR> (v[2], w2);
+        v[3] = cmul_dir<DIR> (v[3], w3);
+        v[4] = cmul_dir<DIR> (v[4], w4);
+        v[5] = cmul_dir<DIR> (v[5], cmul_dir<-1> (w1, w4));
+        v[6] = cmul_dir<DIR> (v[6], cmul_dir<-1> (w2, w4));
+        v[7] = cmul_dir<DIR> (v[7], cmul_dir<-1> (w3, w4));
+        v[8] = cmul_dir<DIR> (v[8], w8);
+        v[9] = cmul_dir<DIR> (v[9], cmul_dir<-1> (w1, w8));
+        v[10] = cmul_dir<DIR> (v[10], cmul_dir<-1> (w2, w8));
+        v[11] = cmul_dir<DIR> (v[11], cmul_dir<-1> (w3, w8));
+        v[12] = cmul_dir<DIR> (v[12], w12);
+        v[13] = cmul_dir<DIR> (v[13], cmul_dir<-1> (w1, w12));
+        v[14] = cmul_dir<DIR> (v[14], cmul_dir<-1> (w2, w12));
+        v[15] = cmul_dir<DIR> (v[15], cmul_dir<-1> (w3, w12));
+    }
+    else if constexpr (STAGE > 0)
+    {
+        // last stage, radix r < 16: butterfly u of this thread has k = j + u T, and
+        // W^(k q) = W^(j q) W16^(u q)  because T = M / 16
+        const float2* __restrict__ t = tw + G::tw_off (STAGE) + j;
+        float2 w[r];
+#pragma unroll
+        for (int q = 1; q < r; ++q)
+            w[q] = __ldg (t + (q - 1) * G::T);
 #pragma unroll
         for (int u = 0; u < SUB; ++u)
         {
-            const int k = (j + u * G::T) & (Ns - 1);
 #pragma unroll
             for (int q = 1; q < r; ++q)
-                v[u + q * SUB] = cmul_dir<DIR> (v[u + q * SUB], __ldg (t + (q - 1) * Ns + k));
+            {
+                float2 x = cmul_dir<DIR> (v[u + q * SUB], w[q]);
+                v[u + q * SUB] = mul_w16_rt<DIR> (x, u * q);
+            }
         }
     }
 #pragma unroll
@@ -547,7 +630,7 @@ FFT_HD void staging_fill (float* sf, const float* __restrict__ in, int j, int lo
     for (int i = 0; i < G::R / 2; ++i)
     {
         const int q = j + i * G::T;
-        const float4 val = __ldg (reinterpret_cast<const float4*> (in) + q);
+        const float4 val = ldg_stream (reinterpret_cast<const float4*> (in) + q);
         sts4 (sf + upad (4 * q, logW), val);
     }
 }
@@ -610,7 +693,7 @@ FFT_HD void fft_body (const FftArgs& a)
         const float2* __restrict__ in2 = reinterpret_cast<const float2*> (in) + j;
 #pragma unroll
         for (int m = 0; m < R; ++m)
-            v[m] = __ldg (in2 + m * T);
+            v[m] = ldg_stream (in2 + m * T);
     }
     else if constexpr (KIND == C2C_BWD)
     {
@@ -646,8 +729,8 @@ FFT_HD void fft_body (const FftArgs& a)
             for (int m = 0; m < R / 2; ++m)
             {
                 const float2* ph = (m == 0 && j == 0) ? reinterpret_cast<const float2*> (in) + M / 2 : hi - m * T + T;
-                v[m] = __ldg (lo + m * T);
-                xb[m] = __ldg (ph);
+                v[m] = ldg_stream (lo + m * T);
+                xb[m] = ldg_stream (ph);
             }
         }
         const float2* __restrict__ rt = a.rtw + j;
@@ -778,21 +861,34 @@ __global__ void __launch_bounds__ (Launch<LOGM, R>::THREADS, Launch<LOGM, R>::MI
 // host side: twiddle tables (fp64 -> fp32), shared by the plan and the emulator tests
 // ---------------------------------------------------------------------------------------------
 template <int LOGM, int R>
-inline void fill_stage_twiddles (float2* tw) // Geo<LOGM,R>::TW_LEN entries
+inline void fill_stage_twiddles (float2* tw) // Geo<LOGM,R>::TW_LEN entries, layout described in Geo
 {
     using G = Geo<LOGM, R>;
+    const long double two_pi = 2.0L * 3.141592653589793238462643383279502884L;
     for (int s = 1; s < G::S; ++s)
     {
         const int r = G::radix (s), Ns = G::ns (s);
         float2* t = tw + G::tw_off (s);
-        for (int q = 1; q < r; ++q)
-            for (int k = 0; k < Ns; ++k)
-            {
-                // exp(-2 pi i k q / (Ns r)) with the angle reduced exactly in integers first
-                const long long num = ((long long) k * q) % ((long long) Ns * r);
-                const long double ang = -2.0L * 3.141592653589793238462643383279502884L * (long double) num / (long double) ((long long) Ns * r);
-                t[(q - 1) * Ns + k] = make_float2 ((float) cosl (ang), (float) sinl (ang));
-            }
+        const long long period = (long long) Ns * r;
+        if (r == 16)
+        {
+            const int rows[6] = { 1, 2, 3, 4, 8, 12 };
+            for (int i = 0; i < 6; ++i)
+                for (int k = 0; k < Ns; ++k)
+                {
+                    const long double ang = -two_pi * (long double) (((long long) k * rows[i]) % period) / (long double) period;
+                    t[i * Ns + k] = make_float2 ((float) cosl (ang), (float) sinl (ang));
+                }
+        }
+        else
+        {
+            for (int q = 1; q < r; ++q)
+                for (int k = 0; k < G::T; ++k)
+                {
+                    const long double ang = -two_pi * (long double) (((long long) k * q) % period) / (long double) period;
+                    t[(q - 1) * G::T + k] = make_float2 ((float) cosl (ang), (float) sinl (ang));
+                }
+        }
     }
 }
 inline void fill_real_twiddles (float2* rtw, int M) // M/2 entries: exp(-2 pi i k / 2M) / 2 (the split step's 1/2 folded in, exact)
