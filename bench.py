@@ -1,18 +1,20 @@
 #!/usr/bin/env python
-"""Benchmark of the chowdsp_fft hot path on B200.
+"""Benchmark of the chowdsp_fft hot path on B200 (DESIGN.md "Measurement").
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
 
 A "step" is one pass of the hot path over one batch of synthetic input.  Default workload =
 BASELINE.json configs[1]: batched complex C2C N=4096 x 65536 transforms fp32, ordered, 1 GPU
-(4 GiB algorithmic bytes per step, working set far larger than the 126 MB L2, so no L2 flush is
-needed between iterations).  Prints ONE JSON line on rank 0.
+(4 GiB algorithmic bytes per step; inputs + outputs are far larger than the 126 MB L2, so no L2 flush
+is needed between iterations).  Prints ONE JSON line on rank 0.
 
   value        whole-job throughput, inputs resident in HBM, CUDA-event timed on the launch stream
-  e2e          same metric through the C-ABI with HOST (pinned) buffers: H2D + transform + D2H timed
+  e2e          same metric through the C ABI with HOST (pinned) buffers: H2D + transform + D2H timed
   roofline     algorithmic bytes / launch duration vs the measured HBM peak (MEASURED_PEAKS.json)
   cpu_baseline the reference's own AVX build (oracle/_ref) one thread per host core, bounded sample
 --impl reference runs ONLY that CPU arm (rank 0), as the driver's comparison line.
+
+Other workloads (--workload): the remaining BASELINE configs and size variants, same JSON shape.
 """
 from __future__ import annotations
 
@@ -30,36 +32,24 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
-
-# name -> (N, is_complex, batch per GPU, ordered, description)
-WORKLOADS = {
-    "c2c4096": dict(N=4096, is_complex=True, batch=65536, ordered=True,
-                    desc="batched C2C N=4096 x 65536 fp32, ordered, forward (BASELINE configs[1])"),
-    "c2c4096_unordered": dict(N=4096, is_complex=True, batch=65536, ordered=False,
-                              desc="batched C2C N=4096 x 65536 fp32, unordered (reference W=8 layout), forward"),
-    "c2c1024": dict(N=1024, is_complex=True, batch=262144, ordered=True, desc="batched C2C N=1024 x 262144"),
-    "c2c16384": dict(N=16384, is_complex=True, batch=16384, ordered=True, desc="batched C2C N=16384 x 16384"),
-    "r2c2048": dict(N=2048, is_complex=False, batch=524288, ordered=True, desc="batched R2C N=2048 x 524288"),
-    "r2c8192": dict(N=8192, is_complex=False, batch=131072, ordered=False, desc="batched R2C N=8192 x 131072 unordered"),
-}
-
-
-def algorithmic_bytes(N: int, is_complex: bool) -> int:
-    """C2C 16 N bytes per transform (8N in + 8N out); R2C/C2R 8 N bytes."""
-    return 16 * N if is_complex else 8 * N
-
-
-def flops(N: int, is_complex: bool) -> float:
-    return (5.0 if is_complex else 2.5) * N * math.log2(N)
+METRIC = "batched fp32 FFT throughput, algorithmic bytes (in+out) per second"
 
 
 def hbm_peak():
-    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
-        with open(path) as f:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def host_cores():
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    return n
 
 
 class ClockSampler:
@@ -116,41 +106,278 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def cpu_reference_arm(wl, seconds_target: float, steps: int = 1, warmup: int = 0):
-    """Times the unmodified reference (oracle/_ref) with one thread per host core on a bounded sample
-    of the workload.  Returns (GB/s, cores, sample description, ms per step, SIMD width)."""
-    from oracle import oracle as o
+# ======================================================================================================
+# workloads
+# ======================================================================================================
+class BatchedFFT:
+    """`batch` independent transforms of size N per GPU (weak scaling: every rank runs the same batch)."""
 
-    ref = o.load_ref()
-    if ref is None:
-        raise RuntimeError("oracle/_ref/libchowdsp_fft_ref.so is missing (build it with make -C oracle)")
-    N, is_c, ordered = wl["N"], wl["is_complex"], wl["ordered"]
-    nfl = 2 * N if is_c else N
-    cores = ref.hardware_threads()
-    try:
-        cores = min(cores, len(os.sched_getaffinity(0)))
-    except Exception:
-        pass
-    # working set: enough transforms that every core streams from its own slice (>= 256 per core)
-    sample = min(wl["batch"], max(cores * 256, 2048))
-    rng = np.random.default_rng(42)
-    xin = o.aligned_copy(rng.uniform(-1, 1, sample * nfl).astype(np.float32))
-    out = o.aligned_empty(sample * nfl)
-    t1 = ref.transform_timed(xin, out, N, is_c, False, ordered, sample, nfl, nfl, cores)  # also warms up
-    reps = max(1, int(seconds_target / max(t1, 1e-6) / max(1, steps + warmup)))
-    times = []
-    for it in range(warmup + steps):
+    scaling = "weak"
+
+    def __init__(self, name, N, is_complex, batch, ordered, desc):
+        self.name, self.N, self.is_complex, self.batch, self.ordered, self.desc = name, N, is_complex, batch, ordered, desc
+        self.nfl = 2 * N if is_complex else N
+        # SURVEY.md §8(d): C2C 16 N bytes per transform (8N in + 8N out); R2C 8 N bytes
+        self.bytes_step = batch * (16 * N if is_complex else 8 * N)
+        self.flops_step = batch * (5.0 if is_complex else 2.5) * N * math.log2(N)
+        logm = int(math.log2(N)) - (0 if is_complex else 1)
+        self.kernel = "cfb::fft_kernel<%d,16,%s,%d>" % (logm, "C2C_FWD" if is_complex else "R2C", 0 if ordered else 3)
+
+    def config(self):
+        return {"workload": self.desc, "N": self.N, "transform": "C2C" if self.is_complex else "R2C",
+                "batch_per_gpu": self.batch, "ordered": self.ordered,
+                "l2_policy": "inputs+outputs (%.1f GiB per GPU) far exceed the 126 MB L2; no flush needed" % (2 * self.batch * self.nfl * 4 / 2**30),
+                "sharding": "independent transforms split by batch across GPUs, no collectives"}
+
+    def setup(self, cf, torch, rank, world):
+        self.cf, self.torch = cf, torch
+        self.plan = cf.fft_new_setup(self.N, cf.FFT_COMPLEX if self.is_complex else cf.FFT_REAL, True)
+        gen = torch.Generator(device="cuda").manual_seed(42 + rank)
+        self.x = torch.rand(self.batch, self.nfl, device="cuda", generator=gen) * 2 - 1
+        self.y = torch.empty_like(self.x)
+
+    def step(self, stream):
+        self.cf.fft_transform_batched(self.plan, self.x, self.y, self.batch, self.nfl, self.nfl, self.cf.FFT_FORWARD, self.ordered, stream)
+
+    def parity(self):
+        from oracle import oracle as o
+
+        sel = self.torch.arange(0, self.batch, max(1, self.batch // 64), device="cuda")[:64]
+        want = o.np_transform(self.x[sel].cpu().numpy(), self.N, self.is_complex, 8, False, self.ordered)
+        return {"rel_l2_vs_oracle": o.rel_l2(self.y[sel].cpu().numpy(), want), "tolerance": o.parity_tol(self.N), "transforms": int(sel.numel())}
+
+    def e2e(self, steps, barrier, reduce_max):
+        """HOST pinned buffers through the C ABI: H2D + kernel + D2H inside the timed region."""
+        cf, torch = self.cf, self.torch
+        hin, hout = cf.aligned_array(self.batch * self.nfl), cf.aligned_array(self.batch * self.nfl)
+        hin.reshape(self.batch, self.nfl)[:] = self.x.cpu().numpy()
+        call = lambda: cf.fft_transform_batched(self.plan, hin, hout, self.batch, self.nfl, self.nfl, cf.FFT_FORWARD, self.ordered)
+        call()  # warm-up (allocates the staging buffers)
+        barrier()
         t0 = time.perf_counter()
-        for _ in range(reps):
-            ref.transform_timed(xin, out, N, is_c, False, ordered, sample, nfl, nfl, cores)
-        dt = time.perf_counter() - t0
-        if it >= warmup:
-            times.append(dt)
-    per_step = float(np.mean(times))
-    gbs = sample * reps * algorithmic_bytes(N, is_c) / per_step / 1e9
-    width = o.simd_width(N, is_c, True) * 4
-    desc = f"{sample} transforms x {reps} passes per step, {cores} threads (one per core, pinned), reference AVX build W={width}B"
-    return gbs, cores, desc, per_step * 1e3, width
+        for _ in range(steps):
+            call()
+        torch.cuda.synchronize()
+        dt = reduce_max((time.perf_counter() - t0) / steps)
+        ok = bool(np.array_equal(hout.reshape(self.batch, self.nfl)[:4], self.y[:4].cpu().numpy()))
+        cf.aligned_free(hin.ctypes.data)
+        cf.aligned_free(hout.ctypes.data)
+        return {"seconds": dt, "h2d_bytes_per_step": self.batch * self.nfl * 4, "d2h_bytes_per_step": self.batch * self.nfl * 4,
+                "matches_device_path": ok,
+                "path": "fft_transform_batched(host pinned in/out): 32 MiB chunks, H2D/kernel/D2H overlapped on two streams"}
+
+    def cpu(self, seconds_target, steps=1, warmup=0):
+        """The unmodified reference, one thread per core over a bounded sample of the batch."""
+        from oracle import oracle as o
+
+        ref = o.load_ref()
+        if ref is None:
+            raise RuntimeError("oracle/_ref/libchowdsp_fft_ref.so is missing (build it with make -C oracle)")
+        cores = min(ref.hardware_threads(), host_cores())
+        sample = min(self.batch, max(cores * 256, 2048))
+        rng = np.random.default_rng(42)
+        xin = o.aligned_copy(rng.uniform(-1, 1, sample * self.nfl).astype(np.float32))
+        out = o.aligned_empty(sample * self.nfl)
+        run = lambda: ref.transform_timed(xin, out, self.N, self.is_complex, False, self.ordered, sample, self.nfl, self.nfl, cores)
+        t1 = run()
+        reps = max(1, int(seconds_target / max(t1, 1e-6) / max(1, steps + warmup)))
+        times = []
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                run()
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+        per_step = float(np.mean(times))
+        gbs = sample * reps * (self.bytes_step / self.batch) / per_step / 1e9
+        desc = f"{sample} transforms x {reps} passes per step, {cores} threads (one per core, pinned), reference AVX build W=32B"
+        return gbs, cores, desc, per_step * 1e3
+
+
+class STFT(BatchedFFT):
+    """BASELINE configs[2]: R2C N=2048 hop 512 over 1024 channels x 10 s @ 48 kHz, channels sharded over GPUs."""
+
+    scaling = "strong"
+
+    def __init__(self):
+        self.name, self.N, self.hop, self.channels_total, self.samples = "stft", 2048, 512, 1024, 480000
+        self.is_complex, self.ordered, self.nfl = False, True, 2048
+        self.frames = (self.samples - self.N) // self.hop + 1  # 934
+        self.desc = "multichannel STFT: R2C N=2048 hop 512, 1024 channels x 480000 samples (BASELINE configs[2])"
+        self.kernel = "cfb::fft_kernel<10,16,R2C,0>"
+
+    def config(self):
+        return {"workload": self.desc, "N": self.N, "hop": self.hop, "channels": self.channels_total, "frames_per_channel": self.frames,
+                "transform": "R2C", "ordered": True, "window": "rectangular (the reference has none)",
+                "bytes": "unique input + packed output (frames overlap 4x; re-reads hit L2)",
+                "l2_policy": "9.8 GB per step across the job, far larger than L2",
+                "sharding": "channels split contiguously across GPUs, no collectives"}
+
+    def setup(self, cf, torch, rank, world):
+        from chowdsp_fft_b200.sharding import shard_range
+
+        self.cf, self.torch = cf, torch
+        _, self.channels = shard_range(self.channels_total, rank, world)
+        self.batch = self.channels * self.frames
+        self.bytes_step = self.channels * self.samples * 4 + self.batch * self.N * 4
+        self.flops_step = self.batch * 2.5 * self.N * math.log2(self.N)
+        self.plan = cf.fft_new_setup(self.N, cf.FFT_REAL, True)
+        gen = torch.Generator(device="cuda").manual_seed(42 + rank)
+        self.x = torch.rand(self.channels, self.samples, device="cuda", generator=gen) * 2 - 1
+        self.y = torch.empty(self.channels, self.frames, self.N, device="cuda")
+
+    def step(self, stream):
+        self.cf.fft_transform_strided(self.plan, self.x, self.y, self.channels, self.frames, self.samples, self.hop,
+                                      self.frames * self.N, self.N, self.cf.FFT_FORWARD, True, stream)
+
+    def parity(self):
+        from oracle import oracle as o
+
+        c = self.channels - 1
+        sig = self.x[c].cpu().numpy()
+        fr = np.stack([sig[f * self.hop:f * self.hop + self.N] for f in range(0, self.frames, 37)])
+        got = self.y[c, ::37].cpu().numpy()
+        return {"rel_l2_vs_oracle": o.rel_l2(got, o.np_transform(fr, self.N, False, 8, False, True)), "tolerance": o.parity_tol(self.N), "transforms": len(fr)}
+
+    def e2e(self, steps, barrier, reduce_max):
+        return None  # the strided (frame-gather) entry point takes device pointers only
+
+    def cpu(self, seconds_target, steps=1, warmup=0):
+        from oracle import oracle as o
+
+        ref = o.load_ref()
+        cores = min(ref.hardware_threads(), host_cores())
+        rng = np.random.default_rng(42)
+        # one channel per call: 934 overlapping frames split across the cores (out of place, frames overlap)
+        xin = o.aligned_copy(rng.uniform(-1, 1, self.samples).astype(np.float32))
+        out = o.aligned_empty(self.frames * self.N)
+        run = lambda: ref.transform_timed(xin, out, self.N, False, False, True, self.frames, self.hop, self.N, cores)
+        t1 = run()
+        reps = max(1, int(seconds_target / max(t1, 1e-6) / max(1, steps + warmup)))
+        times = []
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                run()
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+        per_step = float(np.mean(times))
+        bytes_ch = self.samples * 4 + self.frames * self.N * 4
+        gbs = reps * bytes_ch / per_step / 1e9
+        return gbs, cores, f"{reps} channels x 934 frames per step, {cores} threads, reference AVX build", per_step * 1e3
+
+
+class Reverb(BatchedFFT):
+    """BASELINE configs[3]: partitioned convolution, 2^16-tap IR, N=8192 blocks, 4096 channels; one step =
+    one block (4096 new samples) for every channel through the fused kernel."""
+
+    scaling = "strong"
+
+    def __init__(self):
+        self.name, self.N, self.P, self.channels_total = "reverb", 8192, 16, 4096
+        self.B = self.N // 2
+        self.is_complex, self.ordered = False, False
+        self.desc = "partitioned convolution reverb: 2^16-tap per-channel IR, N=8192, 16 partitions, 4096 channels (BASELINE configs[3])"
+        self.kernel = "cfb::pconv_kernel<12,3>"
+        # SURVEY.md §8(d): window in 16384 (new samples only) + FDL write 32768 + 16 x (FDL + H read) + out 16384
+        self.bytes_per_channel_block = 16384 + 32768 + 16 * 32768 + 16 * 32768 + 16384
+        self.flops_per_channel_block = 2 * 2.5 * 8192 * 13 + 16 * 4096 * 8
+
+    def config(self):
+        return {"workload": self.desc, "N": self.N, "partitions": self.P, "channels": self.channels_total, "block": self.B,
+                "ir": "per-channel, pre-transformed, unordered layout (2 GiB)", "fused": "R2C -> 16 x MAC -> C2R -> overlap-save discard in one kernel",
+                "bytes": "1 114 112 B per channel-block (SURVEY.md §8d); the X_t spectrum is reused from registers, so actual traffic is 32 KiB lower",
+                "l2_policy": "4.6 GB per step, far larger than L2", "sharding": "channels split contiguously across GPUs, no collectives"}
+
+    def setup(self, cf, torch, rank, world):
+        from chowdsp_fft_b200.sharding import shard_range
+
+        self.cf, self.torch = cf, torch
+        _, self.channels = shard_range(self.channels_total, rank, world)
+        self.batch = self.channels
+        self.bytes_step = self.channels * self.bytes_per_channel_block
+        self.flops_step = self.channels * self.flops_per_channel_block
+        self.plan = cf.fft_new_setup(self.N, cf.FFT_REAL, True)
+        gen = torch.Generator(device="cuda").manual_seed(42 + rank)
+        self.blocks = 64
+        self.sig = torch.rand(self.channels, (self.blocks + 1) * self.B, device="cuda", generator=gen) * 2 - 1
+        self.sig[:, :self.B] = 0  # the block before the first one
+        ir_t = (torch.rand(self.channels * self.P, self.N, device="cuda", generator=gen) * 2 - 1) * 1e-3
+        ir_t[:, self.B:] = 0
+        self.h = torch.empty_like(ir_t)
+        cf.fft_transform_batched(self.plan, ir_t, self.h, self.channels * self.P, self.N, self.N, cf.FFT_FORWARD, False)
+        del ir_t
+        self.fdl = torch.zeros(self.channels, self.P, self.N, device="cuda")
+        self.out = torch.empty(self.channels, self.blocks * self.B, device="cuda")
+        self.t = 0
+        for _ in range(self.P):  # fill the delay line so that every timed step sums all 16 partitions
+            self.step(None)
+
+    def step(self, stream):
+        t = self.t
+        tb = t % self.blocks
+        win = self.sig[:, tb * self.B:]
+        out = self.out[:, tb * self.B:]
+        self.cf.fft_partitioned_convolve_step(self.plan, win.data_ptr(), self.sig.shape[1], self.h, self.P * self.N, self.fdl, self.P * self.N,
+                                              out.data_ptr(), self.out.shape[1], self.channels, self.P, t, 1.0 / self.N, stream)
+        self.t += 1
+
+    def parity(self):
+        """Last timed block of two channels against the oracle's composition of the same reference calls."""
+        from oracle import oracle as o
+
+        t = self.t - 1
+        tb = t % self.blocks
+        got, want = [], []
+        for c in (0, self.channels - 1):
+            fdl = self.fdl[c].cpu().numpy()
+            h = self.h[c * self.P:(c + 1) * self.P].cpu().numpy()
+            acc = np.zeros(self.N, np.float32)
+            for p in range(self.P):
+                acc = o.np_convolve(fdl[(t - p) % self.P], h[p], acc, self.N, False, 8, 1.0 / self.N)
+            want.append(o.np_transform(acc, self.N, False, 8, True, False)[self.B:])
+            got.append(self.out[c, tb * self.B:(tb + 1) * self.B].cpu().numpy())
+        return {"rel_l2_vs_oracle": o.rel_l2(np.stack(got), np.stack(want)), "tolerance": 1e-5, "transforms": 2}
+
+    def e2e(self, steps, barrier, reduce_max):
+        return None  # streaming state (delay line, IR) lives on the device by design
+
+    def cpu(self, seconds_target, steps=1, warmup=0):
+        from oracle import oracle as o
+
+        ref = o.load_ref()
+        cores = min(ref.hardware_threads(), host_cores())
+        channels, blocks = cores * 2, 48
+        rng = np.random.default_rng(42)
+        x = rng.uniform(-1, 1, (channels, blocks * self.B)).astype(np.float32)
+        h = (rng.uniform(-1, 1, (channels, self.P, self.N)) * 1e-3).astype(np.float32)
+        _, _, t1 = ref.partitioned_convolve(x, h, self.N, self.P, nthreads=cores)
+        reps = max(1, int(seconds_target / max(t1, 1e-6) / max(1, steps + warmup)))
+        times = []
+        for it in range(warmup + steps):
+            secs = 0.0
+            for _ in range(reps):
+                secs += ref.partitioned_convolve(x, h, self.N, self.P, nthreads=cores)[2]
+            if it >= warmup:
+                times.append(secs)
+        per_step = float(np.mean(times))
+        parts = sum(min(t + 1, self.P) for t in range(blocks))
+        bytes_total = reps * channels * (blocks * (16384 + 32768 + 16384) + parts * 65536)
+        gbs = bytes_total / per_step / 1e9
+        return gbs, cores, f"{reps} x ({channels} channels x {blocks} blocks, {parts / blocks:.1f} partitions summed per block on average), {cores} threads, reference AVX build", per_step * 1e3
+
+
+WORKLOADS = {
+    "c2c4096": lambda: BatchedFFT("c2c4096", 4096, True, 65536, True, "batched C2C N=4096 x 65536 fp32, ordered, forward (BASELINE configs[1])"),
+    "c2c4096_unordered": lambda: BatchedFFT("c2c4096_unordered", 4096, True, 65536, False, "batched C2C N=4096 x 65536 fp32, unordered (reference W=8 layout), forward (BASELINE configs[1])"),
+    "c2c1024": lambda: BatchedFFT("c2c1024", 1024, True, 262144, True, "batched C2C N=1024 x 262144 fp32, ordered, forward"),
+    "c2c8192": lambda: BatchedFFT("c2c8192", 8192, True, 32768, True, "batched C2C N=8192 x 32768 fp32, ordered, forward"),
+    "c2c16384": lambda: BatchedFFT("c2c16384", 16384, True, 16384, True, "batched C2C N=16384 x 16384 fp32, ordered, forward"),
+    "r2c2048": lambda: BatchedFFT("r2c2048", 2048, False, 524288, True, "batched R2C N=2048 x 524288 fp32, ordered, forward"),
+    "r2c8192": lambda: BatchedFFT("r2c8192", 8192, False, 131072, False, "batched R2C N=8192 x 131072 fp32, unordered, forward"),
+    "stft": STFT,
+    "reverb": Reverb,
+}
 
 
 def main():
@@ -163,27 +390,21 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    wl = WORKLOADS[args.workload]
-    N, is_c, batch, ordered = wl["N"], wl["is_complex"], wl["batch"], wl["ordered"]
-    nfl = 2 * N if is_c else N
+    wl = WORKLOADS[args.workload]()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    metric = "batched fp32 FFT throughput, algorithmic bytes (in+out) per second"
-    config = {"workload": wl["desc"], "N": N, "transform": "C2C" if is_c else "R2C", "batch_per_gpu": batch,
-              "ordered": ordered, "l2_policy": "inputs+outputs (%.1f GiB per GPU) far exceed the 126 MB L2; no flush needed" % (2 * batch * nfl * 4 / 2**30 / (1 if is_c else 1)),
-              "sharding": "independent transforms split by batch across GPUs, no collectives"}
 
     # ---------------------------------------------------------------- reference arm (CPU, rank 0 only)
     if args.impl == "reference":
         if rank != 0:
             return
-        gbs, cores, desc, ms, width = cpu_reference_arm(wl, seconds_target=20.0, steps=max(1, args.steps), warmup=args.warmup)
-        line = {"impl": "reference", "metric": metric, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
+        gbs, cores, desc, ms = wl.cpu(seconds_target=20.0, steps=max(1, args.steps), warmup=args.warmup)
+        flops_per_byte = (5.0 * wl.N * math.log2(wl.N)) / (16 * wl.N) if wl.is_complex else None
+        line = {"impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "gflops": gbs / algorithmic_bytes(N, is_c) * flops(N, is_c),
+                "scaling": wl.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wl.config(),
+                "gflops": gbs * flops_per_byte if flops_per_byte else None,
                 "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "reference", "sample": desc},
                 "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -191,6 +412,7 @@ def main():
         return
 
     # ---------------------------------------------------------------- our arm
+    args.warmup = max(args.warmup, 3)
     import torch
     import torch.distributed as dist
 
@@ -207,76 +429,55 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    setup = cf.fft_new_setup(N, cf.FFT_COMPLEX if is_c else cf.FFT_REAL, True)
-    gen = torch.Generator(device="cuda").manual_seed(42 + rank)
-    x = torch.rand(batch, nfl, device="cuda", generator=gen) * 2 - 1
-    y = torch.empty_like(x)
+    def reduce(v, op):
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    reduce_max = lambda v: reduce(v, dist.ReduceOp.MAX)
+    reduce_sum = lambda v: reduce(v, dist.ReduceOp.SUM)
+
+    wl.setup(cf, torch, rank, world)
     stream = torch.cuda.current_stream()
-
-    def step():
-        cf.fft_transform_batched(setup, x, y, batch, nfl, nfl, cf.FFT_FORWARD, ordered, stream)
-
     for _ in range(args.warmup):
-        step()
+        wl.step(stream)
     barrier()
     launches0 = cf.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
         ev0.record(stream)
         for _ in range(args.steps):
-            step()
+            wl.step(stream)
         ev1.record(stream)
         barrier()
     launches = cf.launch_count() - launches0
-    ms_total = ev0.elapsed_time(ev1)
-    t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
-    bytes_step = batch * algorithmic_bytes(N, is_c)
-    value = world * bytes_step / (ms_step * 1e-3) / 1e9
-    per_gpu = bytes_step / (ms_total / args.steps * 1e-3) / 1e9  # this rank's kernel: 1 launch per step
+    ms_local = ev0.elapsed_time(ev1) / args.steps
+    ms_step = reduce_max(ms_local)
+    bytes_job = reduce_sum(float(wl.bytes_step))
+    flops_job = reduce_sum(float(wl.flops_step))
+    value = bytes_job / (ms_step * 1e-3) / 1e9
+    per_gpu = wl.bytes_step / (ms_local * 1e-3) / 1e9  # this rank's kernel: one launch per step
     peak, peak_src = hbm_peak()
 
-    # quick parity gate beside the timing: 64 transforms of the timed output vs the oracle (rank 0)
     parity = None
     if rank == 0:
         try:
-            from oracle import oracle as o
-
-            sel = torch.arange(0, batch, max(1, batch // 64), device="cuda")[:64]
-            want = o.np_transform(x[sel].cpu().numpy(), N, is_c, 8, False, ordered)
-            parity = {"rel_l2_vs_oracle": o.rel_l2(y[sel].cpu().numpy(), want), "tolerance": o.parity_tol(N), "transforms": int(sel.numel())}
-        except Exception as e:  # the bench number stands on its own; tests/ are the parity gate
+            parity = wl.parity()  # quick gate beside the timing; tests/ hold the real parity suite
+        except Exception as e:
             parity = {"error": repr(e)}
 
-    # ---- e2e: HOST pinned buffers through the C ABI, H2D + kernel + D2H inside the timed region --------
     e2e = None
     if not args.no_e2e:
-        del y
-        hin, hout = cf.aligned_array(batch * nfl), cf.aligned_array(batch * nfl)
-        hin.reshape(batch, nfl)[:] = x.cpu().numpy()
-        k_e2e = max(2, min(5, args.steps))
-        cf.fft_transform_batched(setup, hin, hout, batch, nfl, nfl, cf.FFT_FORWARD, ordered)  # warm-up (staging buffers)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(k_e2e):
-            cf.fft_transform_batched(setup, hin, hout, batch, nfl, nfl, cf.FFT_FORWARD, ordered)
-        torch.cuda.synchronize()
-        dt = torch.tensor([(time.perf_counter() - t0) / k_e2e], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * bytes_step / float(dt.item()) / 1e9, "unit": "GB/s",
-               "h2d_bytes_per_step": batch * nfl * 4, "d2h_bytes_per_step": batch * nfl * 4,
-               "ms_per_step": float(dt.item()) * 1e3, "steps": k_e2e,
-               "path": "fft_transform_batched(host pinned in/out): 32 MiB chunks, H2D/kernel/D2H overlapped on two streams"}
-        cf.aligned_free(hin.ctypes.data)
-        cf.aligned_free(hout.ctypes.data)
+        r = wl.e2e(max(2, min(5, args.steps)), barrier, reduce_max)
+        if r is not None:
+            secs = r.pop("seconds")
+            e2e = {"value": bytes_job / secs / 1e9, "unit": "GB/s", "ms_per_step": secs * 1e3, **r}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
-            gbs, cores, desc, _, _ = cpu_reference_arm(wl, seconds_target=12.0)
+            gbs, cores, desc, _ = wl.cpu(seconds_target=12.0)
             cpu = {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "reference", "sample": desc}
         except Exception as e:
             cpu = {"value": None, "unit": "GB/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e!r}"}
@@ -289,18 +490,16 @@ def main():
         pass
 
     if rank == 0:
-        line = {"metric": metric, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "gflops": value / algorithmic_bytes(N, is_c) * flops(N, is_c),
+        line = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": wl.scaling,
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wl.config(),
+                "gflops": flops_job / (ms_step * 1e-3) / 1e9,
                 "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peak, "unit": "GB/s", "frac": per_gpu / peak,
                              "traffic": traffic, "peak_source": peak_src, "frac_of_nominal_8TBs": per_gpu / 8000.0,
-                             "kernel": "cfb::fft_kernel<%d,16,%s,%s>" % (int(math.log2(N)) - (0 if is_c else 1), "C2C_FWD" if is_c else "R2C", "false" if ordered else "true"),
-                             "algorithmic_bytes_per_launch": bytes_step},
+                             "kernel": wl.kernel, "algorithmic_bytes_per_launch": wl.bytes_step},
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(),
                 "parity": parity}
         print(json.dumps(line))
-    cf.fft_destroy_setup(setup)
     if world > 1:
         dist.destroy_process_group()
 

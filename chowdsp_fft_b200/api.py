@@ -152,3 +152,12 @@ def fft_convolve_unordered_batched(setup: int, dft_a, dft_b, dft_ab, batch: int,
 
 def fft_accumulate_batched(setup: int, a, b, ab, n: int, stream=None) -> None:
     _check(lib().fft_accumulate_batched(setup, _addr(a), _addr(b), _addr(ab), n, _stream(stream)))
+
+
+def fft_partitioned_convolve_step(setup: int, windows, window_stride: int, ir, ir_channel_stride: int, fdl,
+                                  fdl_channel_stride: int, output, output_stride: int, channels: int,
+                                  partitions: int, block_index: int, scaling: float, stream=None) -> None:
+    """One fused block step of partitioned overlap-save convolution (see chowdsp_fft_b200.h)."""
+    _check(lib().fft_partitioned_convolve_step(setup, _addr(windows), window_stride, _addr(ir), ir_channel_stride,
+                                               _addr(fdl), fdl_channel_stride, _addr(output), output_stride,
+                                               channels, partitions, block_index, scaling, _stream(stream)))

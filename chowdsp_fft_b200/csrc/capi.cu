@@ -652,6 +652,42 @@ CFB_API int fft_convolve_unordered_batched (void* setup, const float* a, const f
     return elementwise_any (p, true, a, b, ab, batch, a_stride, b_stride, ab_stride, nfl, scaling, static_cast<cudaStream_t> (stream), false);
 }
 
+CFB_API int fft_partitioned_convolve_step (void* setup, const float* windows, long long window_stride, const float* ir, long long ir_channel_stride, float* fdl, long long fdl_channel_stride, float* output, long long output_stride, int channels, int partitions, int block_index, float scaling, void* stream)
+{
+    Plan* p = as_plan (setup);
+    if (p == nullptr)
+        return FFT_B200_EINVAL;
+    if (p->is_complex)
+        return fail (FFT_B200_EINVAL, "fft_partitioned_convolve_step needs a REAL plan");
+    if (windows == nullptr || ir == nullptr || fdl == nullptr || output == nullptr || channels < 0 || partitions < 1 || block_index < 0)
+        return fail (FFT_B200_EINVAL, "fft_partitioned_convolve_step: bad arguments");
+    if (channels == 0)
+        return 0;
+    if (classify (windows).kind != Mem::Device || classify (ir).kind != Mem::Device || classify (fdl).kind != Mem::Device || classify (output).kind != Mem::Device)
+        return fail (FFT_B200_EINVAL, "fft_partitioned_convolve_step needs device pointers");
+    Tables t;
+    const int rc = plan_tables (p, t);
+    if (rc != 0)
+        return rc;
+    PConvArgs a {};
+    a.in = windows;
+    a.in_stride = window_stride;
+    a.ir = ir;
+    a.ir_ch_stride = ir_channel_stride;
+    a.fdl = fdl;
+    a.fdl_ch_stride = fdl_channel_stride;
+    a.out = output;
+    a.out_stride = output_stride;
+    a.channels = channels;
+    a.P = partitions;
+    a.t = block_index;
+    a.scaling = scaling;
+    a.tw = t.tw;
+    a.rtw = t.rtw;
+    const cudaError_t e = launch_pconv (p->logM, p->logW, a, static_cast<cudaStream_t> (stream));
+    return e == cudaSuccess ? 0 : fail_cuda (e, "partitioned convolution kernel launch");
+}
+
 CFB_API int fft_accumulate_batched (void* setup, const float* a, const float* b, float* ab, long long n, void* stream)
 {
     Plan* p = as_plan (setup);

@@ -26,6 +26,17 @@ cudaError_t launch_fft (int logM, int kind, int logW, const FftArgs& args, cudaS
         default: return cudaErrorInvalidValue;
     }
 }
+cudaError_t launch_pconv (int logM, int logW, const PConvArgs& args, cudaStream_t stream)
+{
+    switch (logM)
+    {
+#define X(n) \
+    case n: return launch_pconv_##n (logW, args, stream);
+        CFB_FOR_SIZES (X)
+#undef X
+        default: return cudaErrorInvalidValue;
+    }
+}
 int stage_twiddle_len (int logM)
 {
     switch (logM)

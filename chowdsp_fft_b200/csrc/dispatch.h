@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include "fft_kernels.cuh"
+#include "pconv_kernel.cuh"
 
 namespace cfb
 {
@@ -17,6 +18,9 @@ cudaError_t launch_fft (int logM, int kind, int logW, const FftArgs& args, cudaS
 int stage_twiddle_len (int logM);
 void fill_stage_twiddles_rt (int logM, float2* tw);
 
+// fused partitioned-convolution block step for a REAL plan of 2^(logM+1) samples (one CTA per channel)
+cudaError_t launch_pconv (int logM, int logW, const PConvArgs& args, cudaStream_t stream);
+
 cudaError_t launch_convolve (const float* a, const float* b, float* ab, long long a_stride, long long b_stride, long long ab_stride, int nfloats, int batch, int logW, bool is_real, float scaling, cudaStream_t stream);
 cudaError_t launch_accumulate (const float* a, const float* b, float* ab, long long n, cudaStream_t stream);
 
@@ -27,6 +31,7 @@ void count_launch();
 // per-size entry points, one translation unit each (fft_inst.cu compiled with -DCFB_LOGM=n)
 #define CFB_DECL_INST(n)                                                                       \
     cudaError_t launch_fft_##n (int kind, int logW, const FftArgs& args, cudaStream_t stream);      \
+    cudaError_t launch_pconv_##n (int logW, const PConvArgs& args, cudaStream_t stream);           \
     int stage_twiddle_len_##n();                                                               \
     void fill_stage_twiddles_##n (float2* tw);
 CFB_DECL_INST (4)

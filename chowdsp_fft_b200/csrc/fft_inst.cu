@@ -57,6 +57,39 @@ cudaError_t CFB_CAT (launch_fft_, CFB_LOGM) (int kind, int logW, const FftArgs& 
     }
 }
 
+namespace
+{
+template <int LOGW>
+cudaError_t launch_pconv_one (const PConvArgs& a, cudaStream_t stream)
+{
+    using G = Geo<CFB_LOGM, kRadix>;
+    auto kernel = pconv_kernel<CFB_LOGM, LOGW>;
+    constexpr int smem_bytes = G::SMEM_F2_UNORD * 8;
+    if (smem_bytes > 48 * 1024)
+    {
+        const cudaError_t e = cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e != cudaSuccess)
+            return e;
+    }
+    if (a.channels <= 0)
+        return cudaSuccess;
+    kernel<<<(unsigned) a.channels, G::T, smem_bytes, stream>>> (a);
+    count_launch();
+    return cudaGetLastError();
+}
+} // namespace
+
+cudaError_t CFB_CAT (launch_pconv_, CFB_LOGM) (int logW, const PConvArgs& a, cudaStream_t stream)
+{
+    if (logW == 2)
+        return launch_pconv_one<2> (a, stream);
+#if CFB_LOGM >= 6
+    if (logW == 3)
+        return launch_pconv_one<3> (a, stream);
+#endif
+    return cudaErrorInvalidValue;
+}
+
 int CFB_CAT (stage_twiddle_len_, CFB_LOGM)() { return Geo<CFB_LOGM, kRadix>::TW_LEN; }
 void CFB_CAT (fill_stage_twiddles_, CFB_LOGM) (float2* tw) { fill_stage_twiddles<CFB_LOGM, kRadix> (tw); }
 } // namespace cfb

@@ -648,38 +648,20 @@ FFT_HD void staging_drain (const float* sf, float* __restrict__ out, int j, int 
 }
 
 // ---------------------------------------------------------------------------------------------
-// the kernel.  blockDim.x = T * (transforms per CTA); dynamic smem = transforms per CTA * SMEM_F2 * 8.
-// ---------------------------------------------------------------------------------------------
-template <int LOGM, int R, int KIND, int LOGW>
-FFT_HD void fft_body (const FftArgs& a)
+// One transform on the calling thread group (T threads, j = thread index inside the transform).
+//   IN_STAGED  (unordered inputs only): the staging image is already in `s` and synchronised
+//   OUT_STAGED (unordered outputs only): leave the staging image in `s` (synchronised), do not drain it
+//   HALF_OUT   (C2R only): store only the second half of the output samples (overlap-save discard)
+template <int LOGM, int R, int KIND, int LOGW, bool IN_STAGED, bool OUT_STAGED, bool HALF_OUT>
+FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, bool active, int j, float2* s, const float2* __restrict__ tw_, const float2* __restrict__ rtw_)
 {
     using G = Geo<LOGM, R>;
     constexpr int DIR = (KIND == C2C_FWD || KIND == R2C) ? -1 : +1;
     constexpr bool UNORD = LOGW != 0; // 0 = ordered; 2 / 3 = the reference's 4- / 8-lane unordered layout
     constexpr int M = G::M, T = G::T;
-    constexpr int SMEM_F2 = UNORD ? G::SMEM_F2_UNORD : G::SMEM_F2;
-    FFT_DYN_SMEM (float2, smem);
-
-    const int tid = (int) threadIdx.x;
-    const int j = tid & (T - 1);
-    const int lt = tid / T;
-    const int per_cta = (int) blockDim.x / T;
-    const long long x = (long long) blockIdx.x * per_cta + lt;
-    const bool active = x < a.batch;
-    float2* s = smem + lt * SMEM_F2;
     float* sf = reinterpret_cast<float*> (s); // the same buffer seen as the unordered staging image
     constexpr int logW = LOGW;
-
-    // CTAs past the end of the batch re-read the last transform (loads stay unpredicated) and skip stores
-    const unsigned xc = active ? (unsigned) x : (unsigned) a.batch - 1u;
-    unsigned xo = 0, xi = xc;
-    if (a.inner < a.batch) // two-level batch (STFT gather); plain batches skip the division
-    {
-        xo = xc / (unsigned) a.inner;
-        xi = xc - xo * (unsigned) a.inner;
-    }
-    const float* __restrict__ in = a.in + (long long) xo * a.in_outer + (long long) xi * a.in_inner;
-    float* __restrict__ out = a.out + (long long) xo * a.out_outer + (long long) xi * a.out_inner;
+    struct { const float2* tw; const float2* rtw; } a { tw_, rtw_ };
 
     float2 v[R];
     bool smem_was_read = false; // a barrier is needed before the exchange buffer is overwritten
@@ -697,8 +679,11 @@ FFT_HD void fft_body (const FftArgs& a)
     }
     else if constexpr (KIND == C2C_BWD)
     {
-        staging_fill<G> (sf, in, j, logW, active);
-        __syncthreads();
+        if constexpr (! IN_STAGED)
+        {
+            staging_fill<G> (sf, in, j, logW, active);
+            __syncthreads();
+        }
 #pragma unroll
         for (int m = 0; m < R; ++m)
             v[m] = staged_load (sf, up.cplx (m), WL);
@@ -711,8 +696,11 @@ FFT_HD void fft_body (const FftArgs& a)
         float2 xb[R / 2];
         if constexpr (UNORD)
         {
-            staging_fill<G> (sf, in, j, logW, active);
-            __syncthreads();
+            if constexpr (! IN_STAGED)
+            {
+                staging_fill<G> (sf, in, j, logW, active);
+                __syncthreads();
+            }
 #pragma unroll
             for (int m = 0; m < R / 2; ++m)
             {
@@ -772,7 +760,7 @@ FFT_HD void fft_body (const FftArgs& a)
         {
             float2* __restrict__ out2 = reinterpret_cast<float2*> (out) + j;
 #pragma unroll
-            for (int m = 0; m < R; ++m)
+            for (int m = (HALF_OUT ? R / 2 : 0); m < R; ++m)
                 out2[m * T] = v[m];
         }
     }
@@ -784,7 +772,8 @@ FFT_HD void fft_body (const FftArgs& a)
         for (int m = 0; m < R; ++m)
             staged_store (sf, up.cplx (m), WL, v[m]);
         __syncthreads();
-        staging_drain<G> (sf, out, j, logW, active);
+        if constexpr (! OUT_STAGED)
+            staging_drain<G> (sf, out, j, logW, active);
     }
     else // R2C: split step  X[k] = E - i w_k D,  X[M-k] = conj(E + i w_k D),  E,D = (Z[k] +- Z*[M-k]) / 2
     {
@@ -834,9 +823,42 @@ FFT_HD void fft_body (const FftArgs& a)
         if constexpr (UNORD)
         {
             __syncthreads();
-            staging_drain<G> (sf, out, j, logW, active);
+            if constexpr (! OUT_STAGED)
+                staging_drain<G> (sf, out, j, logW, active);
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the batched transform kernel.  blockDim.x = T * (transforms per CTA); dynamic smem = transforms per
+// CTA * SMEM_F2 * 8 bytes.
+// ---------------------------------------------------------------------------------------------
+template <int LOGM, int R, int KIND, int LOGW>
+FFT_HD void fft_body (const FftArgs& a)
+{
+    using G = Geo<LOGM, R>;
+    constexpr int T = G::T;
+    constexpr int SMEM_F2 = LOGW != 0 ? G::SMEM_F2_UNORD : G::SMEM_F2;
+    FFT_DYN_SMEM (float2, smem);
+
+    const int tid = (int) threadIdx.x;
+    const int j = tid & (T - 1);
+    const int lt = tid / T;
+    const int per_cta = (int) blockDim.x / T;
+    const long long x = (long long) blockIdx.x * per_cta + lt;
+    const bool active = x < a.batch;
+
+    // CTAs past the end of the batch re-read the last transform (loads stay unpredicated) and skip stores
+    const unsigned xc = active ? (unsigned) x : (unsigned) a.batch - 1u;
+    unsigned xo = 0, xi = xc;
+    if (a.inner < a.batch) // two-level batch (STFT gather); plain batches skip the division
+    {
+        xo = xc / (unsigned) a.inner;
+        xi = xc - xo * (unsigned) a.inner;
+    }
+    const float* in = a.in + (long long) xo * a.in_outer + (long long) xi * a.in_inner;
+    float* out = a.out + (long long) xo * a.out_outer + (long long) xi * a.out_inner;
+    fft_core<LOGM, R, KIND, LOGW, false, false, false> (in, out, active, j, smem + lt * SMEM_F2, a.tw, a.rtw);
 }
 
 // threads per CTA / occupancy targets

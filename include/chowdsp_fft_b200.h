@@ -45,6 +45,20 @@ int fft_transform_strided (void* setup, const float* input, float* output, int o
    batch (e.g. one impulse response for all channels).  Replaces a loop over reference chowdsp_fft.h:154. */
 int fft_convolve_unordered_batched (void* setup, const float* dft_a, const float* dft_b, float* dft_ab, int batch, long long a_stride, long long b_stride, long long ab_stride, float scaling, void* stream);
 
+/* One block step of a uniform partitioned overlap-save convolution ("convolution reverb") for `channels`
+   independent channels, fused into a single kernel.  setup must be a REAL plan of size N; B = N/2 new
+   samples per block; every spectrum is in the plan's unordered layout.  Per channel c:
+     X        = fft_transform_unordered (FORWARD) of the N samples at windows + c*window_stride
+                (previous block followed by the new block)
+     fdl slot = fdl + c*fdl_channel_stride + (block_index % partitions)*N   <- X   (frequency-delay line)
+     Y        = sum over p = 0 .. min(block_index, partitions-1) of
+                  fdl[c][(block_index - p) % partitions] * ir[c][p] * scaling      (fft_convolve_unordered)
+                with ir[c][p] at ir + c*ir_channel_stride + p*N  (ir_channel_stride = 0: one IR for all)
+     output + c*output_stride  <- last B samples of fft_transform_unordered (BACKWARD) of Y
+   i.e. exactly the reference sequence chowdsp_fft.h:145 ; partitions x :154 ; :145 per channel and block
+   (test/test.cpp:214-218 shows the pattern), in one launch.  Device pointers only; stream-ordered. */
+int fft_partitioned_convolve_step (void* setup, const float* windows, long long window_stride, const float* ir, long long ir_channel_stride, float* fdl, long long fdl_channel_stride, float* output, long long output_stride, int channels, int partitions, int block_index, float scaling, void* stream);
+
 /* ab[i] = a[i] + b[i] for n floats (n % 8 == 0), stream-ordered.  Reference chowdsp_fft.h:160. */
 int fft_accumulate_batched (void* setup, const float* a, const float* b, float* ab, long long n, void* stream);
 

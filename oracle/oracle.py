@@ -335,3 +335,26 @@ def load_c() -> COracle:
     if not os.path.exists(ORACLE_SO):
         build()
     return COracle()
+
+
+def np_partitioned_convolve(x, h, N: int, P: int, W: int, scaling: float | None = None):
+    """Uniform partitioned overlap-save convolution restated on top of np_transform / np_convolve, block
+    by block, exactly the call sequence of oracle/ref_driver.cpp::ref_partitioned_convolve (itself the
+    reference API sequence chowdsp_fft.h:145 ; P x :154 ; :145).  x [channels, blocks*N/2] samples,
+    h [channels, P, N] unordered spectra.  Returns (y [channels, blocks*N/2], fdl [channels, P, N])."""
+    x = np.asarray(x, np.float32)
+    channels, total = x.shape
+    B = N // 2
+    blocks = total // B
+    scaling = 1.0 / N if scaling is None else scaling
+    fdl = np.zeros((channels, P, N), np.float32)
+    y = np.zeros((channels, blocks * B), np.float32)
+    xpad = np.concatenate([np.zeros((channels, B), np.float32), x], axis=1)
+    for t in range(blocks):
+        win = xpad[:, t * B:t * B + N]
+        fdl[:, t % P] = np_transform(win, N, False, W, False, False)
+        acc = np.zeros((channels, N), np.float32)
+        for p in range(min(t + 1, P)):
+            acc = np_convolve(fdl[:, (t - p) % P], h[:, p], acc, N, False, W, scaling)
+        y[:, t * B:(t + 1) * B] = np_transform(acc, N, False, W, True, False)[:, B:]
+    return y, fdl

@@ -4,6 +4,7 @@
 #define CHOWDSP_EMU 1
 #include "fft_kernels.cuh"
 #include "elementwise_kernels.cuh"
+#include "pconv_kernel.cuh"
 
 using namespace cfb;
 
@@ -93,6 +94,30 @@ int emu_fft (int logM, int kind, int unord, int logW, const float* in, float* ou
         stats[3] = emu::g_stats.worst;
     }
     return rc;
+}
+
+// fused partitioned-convolution step, real size N = 2^(logM+1)
+int emu_pconv (int logM, int logW, const float* in, long long in_stride, const float* ir, long long ir_ch_stride, float* fdl, long long fdl_ch_stride, float* out, long long out_stride, int channels, int P, int t, float scaling)
+{
+    auto run = [&] (auto logm_c, auto logw_c) -> int
+    {
+        constexpr int LOGM = decltype (logm_c)::value, LOGW = decltype (logw_c)::value;
+        using G = Geo<LOGM, 16>;
+        std::vector<float2> tw ((size_t) G::TW_LEN + 1), rtw ((size_t) G::M / 2 + 1);
+        fill_stage_twiddles<LOGM, 16> (tw.data());
+        fill_real_twiddles (rtw.data(), G::M);
+        PConvArgs a { in, in_stride, ir, ir_ch_stride, fdl, fdl_ch_stride, out, out_stride, channels, P, t, scaling, tw.data(), rtw.data() };
+        emu::g_log_smem = false;
+        emu::launch (pconv_kernel<LOGM, LOGW>, dim3 ((unsigned) channels), dim3 (G::T), (size_t) G::SMEM_F2_UNORD * 8, a);
+        return 0;
+    };
+    using std::integral_constant;
+    if (logM == 7 && logW == 3) return run (integral_constant<int, 7> {}, integral_constant<int, 3> {});
+    if (logM == 7 && logW == 2) return run (integral_constant<int, 7> {}, integral_constant<int, 2> {});
+    if (logM == 4 && logW == 2) return run (integral_constant<int, 4> {}, integral_constant<int, 2> {});
+    if (logM == 10 && logW == 3) return run (integral_constant<int, 10> {}, integral_constant<int, 3> {});
+    if (logM == 12 && logW == 3) return run (integral_constant<int, 12> {}, integral_constant<int, 3> {});
+    return -1;
 }
 
 int emu_convolve (const float* a, const float* b, float* ab, long long a_stride, long long b_stride, long long ab_stride, int nfloats, int batch, int logW, int is_real, float scaling)

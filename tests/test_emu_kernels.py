@@ -131,3 +131,42 @@ def test_emulated_convolve_and_accumulate(emu, oracle_mod, is_c, W):
     s = np.empty_like(a)
     emu.emu_accumulate(a.ctypes.data_as(fp), ab.ctypes.data_as(fp), s.ctypes.data_as(fp), a.size)
     assert np.array_equal(s, a + ab)
+
+
+@pytest.mark.parametrize("N,W", [(256, 8), (256, 4), (32, 4), (2048, 8)])
+def test_emulated_fused_partitioned_convolution(emu, oracle_mod, ref_lib, N, W):
+    """pconv_kernel (forward -> P x MAC -> inverse, overlap-save) against the oracle's block-by-block
+    composition and, when present, the reference API sequence itself."""
+    o = oracle_mod
+    emu.emu_pconv.argtypes = [C.c_int, C.c_int, fp, C.c_longlong, fp, C.c_longlong, fp, C.c_longlong, fp, C.c_longlong,
+                              C.c_int, C.c_int, C.c_int, C.c_float]
+    P, channels, blocks = 3, 2, 5
+    B = N // 2
+    rng = np.random.default_rng(N + W)
+    x = rng.uniform(-1, 1, (channels, blocks * B)).astype(np.float32)
+    ir = (rng.uniform(-1, 1, (channels, P * B)) * 0.1).astype(np.float32)
+    h = np.zeros((channels, P, N), np.float32)
+    for c in range(channels):
+        for p in range(P):
+            seg = np.zeros(N, np.float32)
+            seg[:B] = ir[c, p * B:(p + 1) * B]
+            h[c, p] = o.np_transform(seg, N, False, W, False, False)
+    want_y, want_fdl = o.np_partitioned_convolve(x, h, N, P, W)
+    xpad = np.ascontiguousarray(np.concatenate([np.zeros((channels, B), np.float32), x], axis=1))
+    fdl = np.zeros((channels, P, N), np.float32)
+    y = np.zeros((channels, blocks * B), np.float32)
+    logM = int(np.log2(N)) - 1
+    for t in range(blocks):
+        win = xpad[:, t * B:]
+        out = y[:, t * B:]
+        rc = emu.emu_pconv(logM, {8: 3, 4: 2}[W], win.ctypes.data_as(fp), xpad.shape[1], h.ctypes.data_as(fp), P * N,
+                           fdl.ctypes.data_as(fp), P * N, out.ctypes.data_as(fp), y.shape[1], channels, P, t, 1.0 / N)
+        assert rc == 0
+    assert o.rel_l2(fdl, want_fdl) < o.parity_tol(N)
+    assert o.rel_l2(y, want_y) < 2e-6
+    for c in range(channels):  # and it IS the linear convolution
+        direct = np.convolve(x[c].astype(np.float64), ir[c].astype(np.float64))[:blocks * B]
+        assert o.rel_l2(y[c], direct) < 5e-6
+    if ref_lib is not None and W == o.simd_width(N, False, True):
+        ref_y, ref_fdl, _ = ref_lib.partitioned_convolve(x, h, N, P)
+        assert o.rel_l2(y, ref_y) < 2e-6

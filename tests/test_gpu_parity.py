@@ -385,3 +385,102 @@ def test_config3_stft_shape(cf, oracle_mod):
     fr_all = sig.unfold(1, N, hop)
     assert float((back / N - fr_all).double().norm() / fr_all.double().norm()) < o.parity_tol(N)
     cf.fft_destroy_setup(s)
+
+
+def _ir_spectra(o, ir, N, P, W):
+    channels = ir.shape[0]
+    B = N // 2
+    h = np.zeros((channels, P, N), np.float32)
+    for p in range(P):
+        seg = np.zeros((channels, N), np.float32)
+        seg[:, :B] = ir[:, p * B:(p + 1) * B]
+        h[:, p] = o.np_transform(seg, N, False, W, False, False)
+    return h
+
+
+@pytest.mark.parametrize("N,avx,P", [(8192, True, 16), (256, False, 3), (1024, True, 4)])
+def test_fused_partitioned_convolution(cf, oracle_mod, ref_lib, N, avx, P):
+    """fft_partitioned_convolve_step (one fused kernel per block) == the reference call sequence
+    forward -> P x fft_convolve_unordered -> backward per channel and block (oracle composition and, when
+    present, the live reference), == the same sequence through our own unfused entry points, and == the
+    direct linear convolution."""
+    o = oracle_mod
+    W = o.simd_width(N, False, avx)
+    channels, blocks, B = 5, P + 4, N // 2
+    rng = np.random.default_rng(N)
+    x = rng.uniform(-1, 1, (channels, blocks * B)).astype(np.float32)
+    ir = (rng.uniform(-1, 1, (channels, P * B)) / np.sqrt(P * B)).astype(np.float32)
+    h = _ir_spectra(o, ir, N, P, W)
+    s = cf.fft_new_setup(N, cf.FFT_REAL, avx)
+    xpad = dev(np.concatenate([np.zeros((channels, B), np.float32), x], axis=1))
+    dh, fdl = dev(h), torch.zeros(channels, P, N, device="cuda")
+    y = torch.zeros(channels, blocks * B, device="cuda")
+    # unfused sequence through the batched entry points, kept in lock step
+    fdl_u, y_u = torch.zeros_like(fdl), torch.zeros_like(y)
+    spec, acc, back = (torch.zeros(channels, N, device="cuda") for _ in range(3))
+    for t in range(blocks):
+        cf.fft_partitioned_convolve_step(s, xpad[:, t * B:].data_ptr(), xpad.shape[1], dh, P * N, fdl, P * N,
+                                         y[:, t * B:].data_ptr(), y.shape[1], channels, P, t, 1.0 / N)
+        cf.fft_transform_strided(s, xpad[:, t * B:].data_ptr(), spec, channels, 1, xpad.shape[1], 0, N, 0, cf.FFT_FORWARD, False)
+        fdl_u[:, t % P] = spec
+        acc.zero_()
+        for p in range(min(t + 1, P)):
+            cf.fft_convolve_unordered_batched(s, fdl_u[:, (t - p) % P].contiguous(), dh[:, p].contiguous(), acc, channels, N, N, N, 1.0 / N)
+        cf.fft_transform_batched(s, acc, back, channels, N, N, cf.FFT_BACKWARD, False)
+        y_u[:, t * B:(t + 1) * B] = back[:, B:]
+    torch.cuda.synchronize()
+    assert torch.equal(fdl, fdl_u)  # same forward kernel code path -> identical spectra
+    assert o.rel_l2(host(y), host(y_u)) < 1e-6
+    want_y, want_fdl = o.np_partitioned_convolve(x, h, N, P, W)
+    assert o.rel_l2(host(fdl), want_fdl) < o.parity_tol(N)
+    assert o.rel_l2(host(y), want_y) < 3e-6
+    for c in range(channels):
+        direct = np.convolve(x[c].astype(np.float64), ir[c].astype(np.float64))[:blocks * B]
+        assert o.rel_l2(host(y[c]), direct) < 1e-5
+    if ref_lib is not None and avx:
+        ref_y, ref_fdl, _ = ref_lib.partitioned_convolve(x, h, N, P)
+        assert o.rel_l2(host(y), ref_y) < 3e-6
+        assert o.rel_l2(host(fdl), ref_fdl) < o.parity_tol(N)
+    cf.fft_destroy_setup(s)
+
+
+def test_config4_full_size_properties(cf, oracle_mod):
+    """Partitioned reverb at BASELINE config 4 scale (N=8192, 16 partitions, 4096 channels): linearity in
+    the input, an impulse input reproduces the IR, and sampled channels match the oracle."""
+    o = oracle_mod
+    N, P, channels, B = 8192, 16, 4096, 4096
+    blocks = P + 2
+    s = cf.fft_new_setup(N, cf.FFT_REAL)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    ir = (torch.rand(channels, P * B, device="cuda", generator=g) * 2 - 1) * 1e-3
+    seg = torch.zeros(channels * P, N, device="cuda")
+    seg[:, :B] = ir.reshape(channels * P, B)
+    h = torch.empty_like(seg)
+    cf.fft_transform_batched(s, seg, h, channels * P, N, N, cf.FFT_FORWARD, False)
+    del seg
+
+    def run(sig):
+        xpad = torch.cat([torch.zeros(channels, B, device="cuda"), sig], dim=1).contiguous()
+        fdl = torch.zeros(channels, P, N, device="cuda")
+        y = torch.zeros(channels, blocks * B, device="cuda")
+        for t in range(blocks):
+            cf.fft_partitioned_convolve_step(s, xpad[:, t * B:].data_ptr(), xpad.shape[1], h, P * N, fdl, P * N,
+                                             y[:, t * B:].data_ptr(), y.shape[1], channels, P, t, 1.0 / N)
+        torch.cuda.synchronize()
+        return y
+
+    g = torch.Generator(device="cuda").manual_seed(42)
+    x1 = torch.rand(channels, blocks * B, device="cuda", generator=g) * 2 - 1
+    x2 = torch.rand(channels, blocks * B, device="cuda", generator=g) * 2 - 1
+    y1, y2, y12 = run(x1), run(x2), run(0.5 * x1 - 2.0 * x2)
+    lin = 0.5 * y1 - 2.0 * y2
+    assert float((y12 - lin).double().norm() / lin.double().norm()) < 2e-6
+    imp = torch.zeros(channels, blocks * B, device="cuda")
+    imp[:, 0] = 1.0
+    yi = run(imp)
+    assert float((yi[:, :P * B] - ir).double().norm() / ir.double().norm()) < 2e-6
+    assert float(yi[:, P * B:].abs().max()) < 1e-7
+    for c in (0, 2047, 4095):
+        direct = np.convolve(host(x1[c]).astype(np.float64), host(ir[c]).astype(np.float64))[:blocks * B]
+        assert o.rel_l2(host(y1[c]), direct) < 1e-5
+    cf.fft_destroy_setup(s)
