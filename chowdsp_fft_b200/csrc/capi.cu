@@ -17,6 +17,7 @@
 
 #include "../../include/chowdsp_fft_b200.h"
 #include "dispatch.h"
+#include "large_plan.h"
 
 #define CFB_API __attribute__ ((visibility ("default")))
 
@@ -108,6 +109,39 @@ int get_tables (int device, int logM, bool real, Tables& out)
     return 0;
 }
 
+// two-level tables W_(2^n)^e = lo[e & mask] * hi[e >> lobits] for the multi-pass (large) transforms
+struct BigTables
+{
+    float2* lo = nullptr;
+    float2* hi = nullptr;
+    int lobits = 0;
+};
+std::map<uint64_t, BigTables> g_big_tables;
+
+int get_big_tables (int device, int n, BigTables& out)
+{
+    const uint64_t key = ((uint64_t) device << 32) | (uint64_t) n;
+    std::lock_guard<std::mutex> lock (g_tables_mutex);
+    auto it = g_big_tables.find (key);
+    if (it != g_big_tables.end())
+    {
+        out = it->second;
+        return 0;
+    }
+    BigTables t;
+    t.lobits = big_twiddle_lobits (n);
+    const size_t nlo = (size_t) 1 << t.lobits, nhi = (size_t) 1 << (n - t.lobits);
+    std::vector<float2> lo (nlo), hi (nhi);
+    fill_big_twiddles (lo.data(), hi.data(), n, t.lobits);
+    CFB_CUDA (cudaMalloc (&t.lo, sizeof (float2) * nlo));
+    CFB_CUDA (cudaMalloc (&t.hi, sizeof (float2) * nhi));
+    CFB_CUDA (cudaMemcpy (t.lo, lo.data(), sizeof (float2) * nlo, cudaMemcpyHostToDevice));
+    CFB_CUDA (cudaMemcpy (t.hi, hi.data(), sizeof (float2) * nhi, cudaMemcpyHostToDevice));
+    g_big_tables[key] = t;
+    out = t;
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------------
@@ -164,6 +198,11 @@ int plan_tables (Plan* p, Tables& t)
     CFB_CUDA (cudaGetDevice (&dev));
     if (dev < 0 || dev >= kMaxDevices)
         return fail (chowdsp::fft::FFT_B200_EINVAL, "device index %d out of range", dev);
+    if (p->logM > kMaxLogM)
+    {
+        t = Tables {};
+        return 0; // multi-pass plan: tables are fetched per pass (enqueue_large)
+    }
     if (! p->have[dev])
     {
         Tables nt;
@@ -280,8 +319,117 @@ int kind_of (const Plan* p, int direction)
     return direction == chowdsp::fft::FFT_FORWARD ? R2C : C2R;
 }
 
+// One transform larger than a CTA: 2 or 3 tile passes (+ a split/merge or reorder pass) through
+// stream-ordered scratch.  The reference uses the caller's `work` buffer for the same purpose
+// (simd/chowdsp_fft_impl_avx.cpp:1861-1863); here `work` may stay NULL.
+int enqueue_large (Plan* p, const float* in, float* out, int direction, bool ordered, cudaStream_t stream)
+{
+    int dev = 0;
+    CFB_CUDA (cudaGetDevice (&dev));
+    const int n = p->logM;
+    const bool fwd = direction == chowdsp::fft::FFT_FORWARD;
+    const int dir = fwd ? -1 : +1;
+    const LargeFactors f = choose_factors (n);
+    TilePass pass[3];
+    const int np = build_tile_passes (n, f, pass, p->is_complex ? 1u : 2u);
+    BigTables bt;
+    int rc = get_big_tables (dev, p->is_complex ? n : n + 1, bt);
+    if (rc != 0)
+        return rc;
+    for (int i = 0; i < np; ++i)
+    {
+        Tables st;
+        rc = get_tables (dev, pass[i].logL, false, st);
+        if (rc != 0)
+            return rc;
+        pass[i].args.tw = st.tw;
+        pass[i].args.tw_lo = bt.lo;
+        pass[i].args.tw_hi = bt.hi;
+        pass[i].args.tw_lobits = bt.lobits;
+    }
+    const size_t bytes = sizeof (float2) << n;
+    const bool need_s2 = fwd && (! p->is_complex || ! ordered);
+    float2 *s1 = nullptr, *s2 = nullptr;
+    CFB_CUDA (cudaMallocAsync (&s1, bytes, stream));
+    if (need_s2)
+        CFB_CUDA (cudaMallocAsync (&s2, bytes, stream));
+    auto run_passes = [&] (const float2* src, float2* dst) -> int
+    {
+        for (int i = 0; i < np; ++i)
+        {
+            pass[i].args.in = i == 0 ? src : s1;
+            pass[i].args.out = i == np - 1 ? dst : s1;
+            const cudaError_t e = launch_tile (pass[i].logL, dir, pass[i].load_j_fast, pass[i].args, stream);
+            if (e != cudaSuccess)
+                return fail_cuda (e, "tile pass launch");
+        }
+        return 0;
+    };
+    RealPassArgs ra {};
+    ra.logM = n;
+    ra.logW = ordered ? 0 : p->logW;
+    ra.tw_lobits = bt.lobits;
+    ra.tw_mult = 1;
+    ra.tw_lo = bt.lo;
+    ra.tw_hi = bt.hi;
+    cudaError_t e = cudaSuccess;
+    if (p->is_complex)
+    {
+        if (fwd)
+        {
+            rc = run_passes (reinterpret_cast<const float2*> (in), ordered ? reinterpret_cast<float2*> (out) : s2);
+            if (rc == 0 && ! ordered)
+                e = launch_complex_reorder (reinterpret_cast<const float*> (s2), out, n, p->logW, true, stream);
+        }
+        else
+        {
+            const float2* src = reinterpret_cast<const float2*> (in);
+            if (! ordered)
+            {
+                e = launch_complex_reorder (in, reinterpret_cast<float*> (s1), n, p->logW, false, stream);
+                src = s1;
+            }
+            if (e == cudaSuccess)
+                rc = run_passes (src, reinterpret_cast<float2*> (out));
+        }
+    }
+    else if (fwd)
+    {
+        rc = run_passes (reinterpret_cast<const float2*> (in), s2);
+        ra.in = reinterpret_cast<const float*> (s2);
+        ra.out = out;
+        if (rc == 0)
+            e = launch_real_pass (-1, ra, stream);
+    }
+    else
+    {
+        ra.in = in;
+        ra.out = reinterpret_cast<float*> (s1);
+        e = launch_real_pass (+1, ra, stream);
+        if (e == cudaSuccess)
+            rc = run_passes (s1, reinterpret_cast<float2*> (out));
+    }
+    CFB_CUDA (cudaFreeAsync (s1, stream));
+    if (s2 != nullptr)
+        CFB_CUDA (cudaFreeAsync (s2, stream));
+    if (e != cudaSuccess)
+        return fail_cuda (e, "large transform pass launch");
+    return rc;
+}
+
 int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inner, long long in_outer, long long in_inner, long long out_outer, long long out_inner, int direction, bool ordered, cudaStream_t stream)
 {
+    if (p->logM > kMaxLogM)
+    {
+        for (int o = 0; o < outer; ++o)
+            for (int i = 0; i < inner; ++i)
+            {
+                const int rc = enqueue_large (p, in + o * in_outer + i * in_inner, out + o * out_outer + i * out_inner, direction, ordered, stream);
+                if (rc != 0)
+                    return rc;
+            }
+        return 0;
+    }
     Tables t;
     const int rc = plan_tables (p, t);
     if (rc != 0)
@@ -468,9 +616,9 @@ CFB_API void* fft_new_setup_preallocated (int N, fft_transform_t transform, void
     const bool is_complex = transform == FFT_COMPLEX;
     const int W = choose_width (N, is_complex, use_avx_if_available);
     const int logM = W == 0 ? -1 : ilog2i (N) - (is_complex ? 0 : 1);
-    if (W == 0 || logM < kMinLogM || logM > kMaxLogM)
+    if (W == 0 || logM < kMinLogM || logM > kMaxLargeLog - (is_complex ? 0 : 1))
     {
-        fail (FFT_B200_EINVAL, "unsupported FFT size N=%d (%s): need a power of two, %s", N, is_complex ? "complex" : "real", is_complex ? "16 <= N <= 16384" : "32 <= N <= 32768");
+        fail (FFT_B200_EINVAL, "unsupported FFT size N=%d (%s): need a power of two, %s", N, is_complex ? "complex" : "real", is_complex ? "16 <= N <= 2^28" : "32 <= N <= 2^28");
         return nullptr;
     }
     if (! device_available())
@@ -659,6 +807,8 @@ CFB_API int fft_partitioned_convolve_step (void* setup, const float* windows, lo
         return FFT_B200_EINVAL;
     if (p->is_complex)
         return fail (FFT_B200_EINVAL, "fft_partitioned_convolve_step needs a REAL plan");
+    if (p->logM > kMaxLogM)
+        return fail (FFT_B200_EINVAL, "fft_partitioned_convolve_step: block size N=%d is larger than the single-kernel limit 32768", p->N);
     if (windows == nullptr || ir == nullptr || fdl == nullptr || output == nullptr || channels < 0 || partitions < 1 || block_index < 0)
         return fail (FFT_B200_EINVAL, "fft_partitioned_convolve_step: bad arguments");
     if (channels == 0)

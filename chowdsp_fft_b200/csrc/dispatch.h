@@ -4,6 +4,7 @@
 
 #include "fft_kernels.cuh"
 #include "pconv_kernel.cuh"
+#include "large_kernels.cuh"
 
 namespace cfb
 {
@@ -20,6 +21,11 @@ void fill_stage_twiddles_rt (int logM, float2* tw);
 
 // fused partitioned-convolution block step for a REAL plan of 2^(logM+1) samples (one CTA per channel)
 cudaError_t launch_pconv (int logM, int logW, const PConvArgs& args, cudaStream_t stream);
+
+// multi-pass (large transform) kernels, large_inst.cu
+cudaError_t launch_tile (int logL, int dir, bool load_j_fast, const TileArgs& args, cudaStream_t stream);
+cudaError_t launch_real_pass (int dir, const RealPassArgs& args, cudaStream_t stream);
+cudaError_t launch_complex_reorder (const float* in, float* out, int logN, int logW, bool to_unordered, cudaStream_t stream);
 
 cudaError_t launch_convolve (const float* a, const float* b, float* ab, long long a_stride, long long b_stride, long long ab_stride, int nfloats, int batch, int logW, bool is_real, float scaling, cudaStream_t stream);
 cudaError_t launch_accumulate (const float* a, const float* b, float* ab, long long n, cudaStream_t stream);

@@ -1,0 +1,69 @@
+// Instantiations and launchers of the multi-pass (large transform) kernels.
+#include "dispatch.h"
+#include "large_plan.h"
+
+namespace cfb
+{
+namespace
+{
+template <int LOGL, int DIR, bool JFAST>
+cudaError_t launch_tile_one (const TileArgs& a, cudaStream_t stream)
+{
+    using TL = TileLaunch<LOGL, kTileC>;
+    auto kernel = tile_fft_kernel<LOGL, kTileC, DIR, JFAST>;
+    if (TL::SMEM_BYTES > 48 * 1024)
+    {
+        const cudaError_t e = cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TL::SMEM_BYTES);
+        if (e != cudaSuccess)
+            return e;
+    }
+    kernel<<<(unsigned) a.ntiles, TL::THREADS, TL::SMEM_BYTES, stream>>> (a);
+    count_launch();
+    return cudaGetLastError();
+}
+template <int LOGL>
+cudaError_t launch_tile_l (int dir, bool jfast, const TileArgs& a, cudaStream_t stream)
+{
+    if (dir < 0)
+        return jfast ? launch_tile_one<LOGL, -1, true> (a, stream) : launch_tile_one<LOGL, -1, false> (a, stream);
+    return jfast ? launch_tile_one<LOGL, +1, true> (a, stream) : launch_tile_one<LOGL, +1, false> (a, stream);
+}
+} // namespace
+
+cudaError_t launch_tile (int logL, int dir, bool load_j_fast, const TileArgs& a, cudaStream_t stream)
+{
+    switch (logL)
+    {
+        case 6: return launch_tile_l<6> (dir, load_j_fast, a, stream);
+        case 7: return launch_tile_l<7> (dir, load_j_fast, a, stream);
+        case 8: return launch_tile_l<8> (dir, load_j_fast, a, stream);
+        case 9: return launch_tile_l<9> (dir, load_j_fast, a, stream);
+        case 10: return launch_tile_l<10> (dir, load_j_fast, a, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_real_pass (int dir, const RealPassArgs& a, cudaStream_t stream)
+{
+    const long long pairs = 1LL << (a.logM - 1);
+    const unsigned grid = (unsigned) ((pairs + 255) / 256);
+    if (dir < 0)
+        real_pass_kernel<-1><<<grid, 256, 0, stream>>> (a);
+    else
+        real_pass_kernel<+1><<<grid, 256, 0, stream>>> (a);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_complex_reorder (const float* in, float* out, int logN, int logW, bool to_unordered, cudaStream_t stream)
+{
+    const long long bins = 1LL << logN;
+    const unsigned grid = (unsigned) ((bins + 255) / 256);
+    if (to_unordered)
+        complex_reorder_kernel<true><<<grid, 256, 0, stream>>> (in, out, logN, logW);
+    else
+        complex_reorder_kernel<false><<<grid, 256, 0, stream>>> (in, out, logN, logW);
+    count_launch();
+    return cudaGetLastError();
+}
+} // namespace cfb

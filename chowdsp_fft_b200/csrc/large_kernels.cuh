@@ -1,0 +1,276 @@
+// Large transforms (more points than one CTA can hold): multi-pass "four-step" FFT built from TILE kernels.
+//
+// The reference runs any size with the same FFTPACK passes over the whole buffer
+// (/root/reference/simd/chowdsp_fft_impl_avx.cpp:430-490, cfftf1_ps) using the caller's `work` array as the
+// ping-pong buffer (:1861-1863).  Here N = L1 * L2 * L3 (each factor <= 1024) is done in two or three
+// passes, each of which reads and writes the array exactly once with full-sector accesses:
+//
+//   pass A  length-L1 FFTs down the columns of the [L1][N/L1] view (stride N/L1), times W_N^(k1*s), in place
+//   pass B  (three-pass plans) for every row k1: length-L2 column FFTs of its [L2][L3] view, times
+//           W_(L2 L3)^(k2*n3), in place
+//   pass C  length-L3 FFTs of contiguous rows, written transposed:  X[k1 + L1*(k2 + L2*k3)]
+//
+// A tile kernel owns C (= 8) transforms that are ADJACENT IN MEMORY across the transform index, so the
+// strided side of every pass still moves C*8 = 64 contiguous bytes per element row.  The butterflies,
+// twiddle scheme and exchange code are the ones of the single-kernel transform (fft_kernels.cuh).
+#pragma once
+#include "fft_kernels.cuh"
+
+// extra float2 slots between the exchange regions of adjacent transforms of a tile: 2 makes every
+// exchange of the tile kernels bank-conflict free (measured with the emulator for all pass lengths)
+#ifndef CFB_TILE_PAD
+#define CFB_TILE_PAD 2
+#endif
+
+namespace cfb
+{
+struct TileArgs
+{
+    const float2* in;
+    float2* out;
+    // tile g = blockIdx.x:  base = (g / gdiv) * g_hi + (g % gdiv) * g_lo ;  element idx of transform lt sits at
+    // base + lt * tstride + idx * estride   (all in float2 units)
+    long long in_g_hi, in_g_lo, in_tstride, in_estride;
+    long long out_g_hi, out_g_lo, out_tstride, out_estride;
+    int gdiv;
+    int ntiles;
+    // four-step twiddle after the transform: out[k] *= W_N^(k * c * tw_mult), c = (g % gdiv) * C + lt,
+    // W_N^e = tw_lo[e & mask] * tw_hi[e >> tw_lobits]   (tw_mult == 0: none)
+    unsigned tw_mult;
+    int tw_lobits;
+    const float2* tw_lo;
+    const float2* tw_hi;
+    const float2* tw; // stage twiddles of the length-L transform
+};
+
+template <int DIR>
+FFT_HD float2 big_twiddle (const TileArgs& a, unsigned e)
+{
+    const float2 lo = __ldg (a.tw_lo + (e & ((1u << a.tw_lobits) - 1u)));
+    const float2 hi = __ldg (a.tw_hi + (e >> a.tw_lobits));
+    return cmul_dir<-1> (lo, hi); // forward twiddle; the caller conjugates for DIR > 0
+}
+
+// LOAD_J_FAST: the transforms are contiguous rows (pass C), so the LOAD uses the thread map of the batched
+// kernel (consecutive threads = consecutive elements of one row) and the map switches to "consecutive
+// threads = adjacent transforms" at the first exchange, which is what makes the transposed store coalesced.
+template <int LOGL, int C, int DIR, bool LOAD_J_FAST>
+FFT_HD void tile_body (const TileArgs& a)
+{
+    constexpr int R = 16;
+    using G = Geo<LOGL, R>;
+    constexpr int T = G::T;
+    constexpr int RS = G::SMEM_F2 + CFB_TILE_PAD; // region stride chosen so that adjacent transforms land in different banks
+    static_assert (! LOAD_J_FAST || G::S >= 2, "the thread-map switch needs at least one exchange");
+    FFT_DYN_SMEM (float2, smem);
+    const int tid = (int) threadIdx.x;
+    const int g = (int) blockIdx.x;
+    if (g >= a.ntiles)
+        return;
+    const int ghi = g / a.gdiv, glo = g - ghi * a.gdiv;
+    const float2* __restrict__ in = a.in + ghi * a.in_g_hi + glo * a.in_g_lo;
+    float2* __restrict__ out = a.out + ghi * a.out_g_hi + glo * a.out_g_lo;
+
+    const int ltB = tid % C, jB = tid / C; // adjacent threads = adjacent transforms
+    const int ltA = tid / T, jA = tid % T; // adjacent threads = adjacent elements
+    float2 v[R];
+    float2* sB = smem + ltB * RS;
+
+    if constexpr (LOAD_J_FAST)
+    {
+        const float2* __restrict__ p = in + ltA * a.in_tstride + jA * a.in_estride;
+#pragma unroll
+        for (int m = 0; m < R; ++m)
+            v[m] = ldg_stream (p + (long long) (m * T) * a.in_estride);
+        float2* sA = smem + ltA * RS;
+        stage_compute<G, DIR, 0> (v, jA, a.tw);
+        stage_scatter<G, 0> (v, jA, sA);
+        __syncthreads();
+        gather_natural<G, 0, R> (v, jB, sB);
+        Stages<G, DIR, 1>::run (v, jB, sB, a.tw, true);
+    }
+    else
+    {
+        const float2* __restrict__ p = in + ltB * a.in_tstride + jB * a.in_estride;
+#pragma unroll
+        for (int m = 0; m < R; ++m)
+            v[m] = ldg_stream (p + (long long) (m * T) * a.in_estride);
+        Stages<G, DIR, 0>::run (v, jB, sB, a.tw, false);
+    }
+
+    // v[m] = X[jB + m T] of transform ltB
+    if (a.tw_mult != 0)
+    {
+        const unsigned c = (unsigned) (glo * C + ltB);
+        const unsigned e0 = (unsigned) jB * c * a.tw_mult, de = (unsigned) T * c * a.tw_mult; // e(m) = e0 + m de < N
+        // exact table values for m = 0..3 and for the strides 4, 8, 12; the rest is one product each
+        float2 w[4], d[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+            w[i] = big_twiddle<DIR> (a, e0 + i * de);
+            d[i] = i == 0 ? make_float2 (1.f, 0.f) : big_twiddle<DIR> (a, 4 * i * de);
+        }
+#pragma unroll
+        for (int m = 0; m < R; ++m)
+        {
+            const float2 wm = (m < 4) ? w[m] : cmul_dir<-1> (w[m & 3], d[m >> 2]);
+            v[m] = cmul_dir<DIR> (v[m], wm);
+        }
+    }
+    float2* __restrict__ q = out + ltB * a.out_tstride + jB * a.out_estride;
+#pragma unroll
+    for (int m = 0; m < R; ++m)
+        q[(long long) (m * T) * a.out_estride] = v[m];
+}
+
+template <int LOGL, int C>
+struct TileLaunch
+{
+    using G = Geo<LOGL, 16>;
+    static constexpr int THREADS = G::T * C;
+    static constexpr int SMEM_BYTES = C * (G::SMEM_F2 + CFB_TILE_PAD) * 8;
+    static constexpr int MIN_BLOCKS = THREADS <= 256 ? 4 : (THREADS <= 512 ? 2 : 1);
+};
+
+template <int LOGL, int C, int DIR, bool LOAD_J_FAST>
+__global__ void __launch_bounds__ (TileLaunch<LOGL, C>::THREADS, TileLaunch<LOGL, C>::MIN_BLOCKS) tile_fft_kernel (const TileArgs a)
+{
+    tile_body<LOGL, C, DIR, LOAD_J_FAST> (a);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Real transforms of 2M samples on top of an M-point complex transform (M too large for one CTA):
+// the split (forward) / merge (backward) step as its own streaming pass.  One thread per pair (k, M-k).
+//   forward : z = M-point FFT of the packed samples (ordered, natural) -> X in the pffft packing or the
+//             unordered real layout
+//   backward: X -> z' for the M-point inverse FFT
+// Same formulas as the fused step in fft_core; w_k = exp(-2 pi i k / 2M) from the two-level tables.
+// ---------------------------------------------------------------------------------------------
+struct RealPassArgs
+{
+    const float* in;
+    float* out;
+    int logM;
+    int logW;   // 0: ordered pffft packing, 2 / 3: unordered real layout
+    int tw_lobits;
+    unsigned tw_mult; // W_2M^k = W_N^(k * tw_mult) in the plan's big tables
+    const float2* tw_lo;
+    const float2* tw_hi;
+};
+
+FFT_HD int real_bin_pos_rt (int bin, int logM, int logW) // float offset of the re part (im is W floats later, or +1 ordered)
+{
+    const int logQ = logM - logW, Q = 1 << logQ;
+    const int r = bin >> logQ, mr = bin & (Q - 1);
+    const int m = (r & 1) ? ((Q - mr) & (Q - 1)) : mr;
+    const int b = m >> logW, lane = m & ((1 << logW) - 1);
+    return ((((b << logW) + r) * 2) << logW) + lane;
+}
+FFT_HD float2 real_load_bin (const float* p, int bin, int logM, int logW)
+{
+    if (logW == 0)
+        return reinterpret_cast<const float2*> (p)[bin];
+    const int pos = real_bin_pos_rt (bin, logM, logW);
+    return make_float2 (p[pos], p[pos + (1 << logW)]);
+}
+FFT_HD void real_store_bin (float* p, int bin, int logM, int logW, float2 v)
+{
+    if (logW == 0)
+    {
+        reinterpret_cast<float2*> (p)[bin] = v;
+        return;
+    }
+    const int pos = real_bin_pos_rt (bin, logM, logW);
+    p[pos] = v.x;
+    p[pos + (1 << logW)] = v.y;
+}
+
+template <int DIR>
+__global__ void __launch_bounds__ (256) real_pass_kernel (const RealPassArgs a)
+{
+    const int M = 1 << a.logM;
+    const int k = (int) (blockIdx.x * blockDim.x + threadIdx.x); // pair index, k <= M/2 - 1 ; k == 0 also does M/2
+    if (k >= M / 2)
+        return;
+    const unsigned e = (unsigned) k * a.tw_mult;
+    const float2 lo = __ldg (a.tw_lo + (e & ((1u << a.tw_lobits) - 1u))), hi = __ldg (a.tw_hi + (e >> a.tw_lobits));
+    const float2 w = cmul_dir<-1> (lo, hi);
+    if (DIR < 0)
+    {
+        // in: natural-order complex z (float2 array); out: half spectrum
+        const float2* z = reinterpret_cast<const float2*> (a.in);
+        if (k == 0)
+        {
+            const float2 z0 = z[0], zh = z[M / 2];
+            real_store_bin (a.out, 0, a.logM, a.logW, make_float2 (z0.x + z0.y, z0.x - z0.y));
+            real_store_bin (a.out, M / 2, a.logM, a.logW, make_float2 (zh.x, -zh.y));
+            return;
+        }
+        const float2 za = z[k], zm = z[M - k];
+        const float2 ee = make_float2 (0.5f * (za.x + zm.x), 0.5f * (za.y - zm.y));
+        const float2 dd = make_float2 (0.5f * (za.x - zm.x), 0.5f * (za.y + zm.y));
+        const float2 wd = cmul_dir<-1> (dd, w);
+        real_store_bin (a.out, k, a.logM, a.logW, make_float2 (ee.x + wd.y, ee.y - wd.x));
+        real_store_bin (a.out, M - k, a.logM, a.logW, make_float2 (ee.x - wd.y, -ee.y - wd.x));
+    }
+    else
+    {
+        float2* z = reinterpret_cast<float2*> (a.out);
+        if (k == 0)
+        {
+            const float2 x0 = real_load_bin (a.in, 0, a.logM, a.logW), xh = real_load_bin (a.in, M / 2, a.logM, a.logW);
+            z[0] = make_float2 (x0.x + x0.y, x0.x - x0.y);
+            z[M / 2] = make_float2 (2.f * xh.x, -2.f * xh.y);
+            return;
+        }
+        const float2 xa = real_load_bin (a.in, k, a.logM, a.logW), xm = real_load_bin (a.in, M - k, a.logM, a.logW);
+        const float2 ee = make_float2 (xa.x + xm.x, xa.y - xm.y);
+        const float2 dd = make_float2 (xa.x - xm.x, xa.y + xm.y);
+        const float2 wd = cmul_dir<+1> (dd, w);
+        z[k] = make_float2 (ee.x - wd.y, ee.y + wd.x);
+        z[M - k] = make_float2 (ee.x + wd.y, wd.x - ee.y);
+    }
+}
+
+// Complex ordered <-> unordered permutation for large N (the single-kernel sizes fuse it; here it is one
+// streaming pass: 64-byte chunk of 8 (or 32-byte chunk of 4) bins per thread group).
+//   TO_UNORDERED : in = interleaved natural order, out = unordered layout ; else the inverse.
+template <bool TO_UNORDERED>
+__global__ void __launch_bounds__ (256) complex_reorder_kernel (const float* in, float* out, int logN, int logW)
+{
+    const long long bin = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (bin >= (1LL << logN))
+        return;
+    const int logL = logN - logW;
+    const int r = (int) (bin >> logL);
+    const int rem = (int) (bin & ((1LL << logL) - 1));
+    const int b = rem >> logW, lane = rem & ((1 << logW) - 1);
+    const long long pos = ((((long long) (b << logW) + r) * 2) << logW) + lane;
+    if (TO_UNORDERED)
+    {
+        const float2 v = reinterpret_cast<const float2*> (in)[bin];
+        out[pos] = v.x;
+        out[pos + (1 << logW)] = v.y;
+    }
+    else
+        reinterpret_cast<float2*> (out)[bin] = make_float2 (in[pos], in[pos + (1 << logW)]);
+}
+
+// host: two-level table for W_N^e, e < N = 2^logN:  lo[e & mask] = W_N^(e & mask), hi[e >> lobits] = W_N^((e >> lobits) << lobits)
+inline void fill_big_twiddles (float2* lo, float2* hi, int logN, int lobits)
+{
+    const long double two_pi = 2.0L * 3.141592653589793238462643383279502884L;
+    const long long N = 1LL << logN;
+    for (long long e = 0; e < (1LL << lobits); ++e)
+    {
+        const long double ang = -two_pi * (long double) e / (long double) N;
+        lo[e] = make_float2 ((float) cosl (ang), (float) sinl (ang));
+    }
+    for (long long h = 0; h < (N >> lobits); ++h)
+    {
+        const long double ang = -two_pi * (long double) (h << lobits) / (long double) N;
+        hi[h] = make_float2 ((float) cosl (ang), (float) sinl (ang));
+    }
+}
+} // namespace cfb

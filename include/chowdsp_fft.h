@@ -55,8 +55,9 @@ typedef enum
    process-wide plan cache. */
 size_t fft_bytes_required (int N, fft_transform_t transform, bool use_avx_if_available CHOWDSP_FFT_DEFAULT_TRUE);
 
-/* reference chowdsp_fft.h:92.  Plan for power-of-two N: real 32 <= N <= 32768 (N % 32 == 0), complex
-   16 <= N <= 16384 (N % 16 == 0).  The handle is immutable and may be shared between threads.
+/* reference chowdsp_fft.h:92.  Plan for power-of-two N: real 32 <= N <= 2^28, complex 16 <= N <= 2^28.
+   Up to 32768 real / 16384 complex points a transform is ONE kernel; larger sizes run as a two- or
+   three-pass four-step transform.  The handle is immutable and may be shared between threads.
    use_avx_if_available selects which of the reference's two "unordered" layouts the plan speaks:
    true  -> the 8-lane (AVX) layout when N % 128 == 0 (real) / N % 64 == 0 (complex), else 4-lane;
    false -> always the 4-lane (SSE/NEON) layout.  Returns NULL for an unsupported N or without a GPU. */

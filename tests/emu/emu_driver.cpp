@@ -5,6 +5,7 @@
 #include "fft_kernels.cuh"
 #include "elementwise_kernels.cuh"
 #include "pconv_kernel.cuh"
+#include "large_plan.h"
 
 using namespace cfb;
 
@@ -51,6 +52,40 @@ int run_logm (int kind, int logW, const FftArgs& a)
         }
     }
     return -1;
+}
+} // namespace
+
+namespace
+{
+// multi-pass complex transform of 2^n points through the tile kernels (factors forced by the caller so that
+// small sizes can exercise the two- and three-pass plans); in/out interleaved complex, natural order
+template <int LOGL, int DIR>
+void emu_tile_launch (const TilePass& p)
+{
+    using TL = TileLaunch<LOGL, kTileC>;
+    if (p.load_j_fast)
+        emu::launch (tile_fft_kernel<LOGL, kTileC, DIR, true>, dim3 ((unsigned) p.args.ntiles), dim3 (TL::THREADS), (size_t) TL::SMEM_BYTES, p.args);
+    else
+        emu::launch (tile_fft_kernel<LOGL, kTileC, DIR, false>, dim3 ((unsigned) p.args.ntiles), dim3 (TL::THREADS), (size_t) TL::SMEM_BYTES, p.args);
+}
+template <int DIR>
+int emu_tile_dispatch (const TilePass& p)
+{
+    switch (p.logL)
+    {
+        case 6: emu_tile_launch<6, DIR> (p); return 0;
+        case 7: emu_tile_launch<7, DIR> (p); return 0;
+        case 8: emu_tile_launch<8, DIR> (p); return 0;
+        case 9: emu_tile_launch<9, DIR> (p); return 0;
+        case 10: emu_tile_launch<10, DIR> (p); return 0;
+    }
+    return -1;
+}
+template <int LOGL>
+void fill_tw_for (std::vector<float2>& tw)
+{
+    tw.assign ((size_t) Geo<LOGL, 16>::TW_LEN + 1, float2 { 0, 0 });
+    fill_stage_twiddles<LOGL, 16> (tw.data());
 }
 } // namespace
 
@@ -118,6 +153,52 @@ int emu_pconv (int logM, int logW, const float* in, long long in_stride, const f
     if (logM == 10 && logW == 3) return run (integral_constant<int, 10> {}, integral_constant<int, 3> {});
     if (logM == 12 && logW == 3) return run (integral_constant<int, 12> {}, integral_constant<int, 3> {});
     return -1;
+}
+
+int emu_large_c2c (int n, int l1, int l2, int l3, int backward, const float* in, float* out, int log_conflicts, long* stats)
+{
+    LargeFactors f;
+    f.l1 = l1; f.l2 = l2; f.l3 = l3;
+    if (l1 + l2 + l3 != n)
+        return -2;
+    TilePass p[3];
+    const int np = build_tile_passes (n, f, p);
+    const int lobits = big_twiddle_lobits (n);
+    std::vector<float2> lo ((size_t) 1 << lobits), hi ((size_t) 1 << (n - lobits));
+    fill_big_twiddles (lo.data(), hi.data(), n, lobits);
+    std::vector<float2> tmp ((size_t) 1 << n);
+    std::vector<float2> tw[3];
+    emu::g_log_smem = log_conflicts != 0;
+    emu::g_stats = {};
+    for (int i = 0; i < np; ++i)
+    {
+        switch (p[i].logL)
+        {
+            case 6: fill_tw_for<6> (tw[i]); break;
+            case 7: fill_tw_for<7> (tw[i]); break;
+            case 8: fill_tw_for<8> (tw[i]); break;
+            case 9: fill_tw_for<9> (tw[i]); break;
+            case 10: fill_tw_for<10> (tw[i]); break;
+            default: return -3;
+        }
+        p[i].args.tw = tw[i].data();
+        p[i].args.tw_lo = lo.data();
+        p[i].args.tw_hi = hi.data();
+        p[i].args.tw_lobits = lobits;
+        p[i].args.in = i == 0 ? reinterpret_cast<const float2*> (in) : tmp.data();
+        p[i].args.out = i == np - 1 ? reinterpret_cast<float2*> (out) : tmp.data();
+        const int rc = backward ? emu_tile_dispatch<+1> (p[i]) : emu_tile_dispatch<-1> (p[i]);
+        if (rc != 0)
+            return rc;
+    }
+    if (stats)
+    {
+        stats[0] = emu::g_stats.ops;
+        stats[1] = emu::g_stats.wavefronts;
+        stats[2] = emu::g_stats.ideal;
+        stats[3] = emu::g_stats.worst;
+    }
+    return 0;
 }
 
 int emu_convolve (const float* a, const float* b, float* ab, long long a_stride, long long b_stride, long long ab_stride, int nfloats, int batch, int logW, int is_real, float scaling)

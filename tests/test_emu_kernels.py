@@ -170,3 +170,23 @@ def test_emulated_fused_partitioned_convolution(emu, oracle_mod, ref_lib, N, W):
     if ref_lib is not None and W == o.simd_width(N, False, True):
         ref_y, ref_fdl, _ = ref_lib.partitioned_convolve(x, h, N, P)
         assert o.rel_l2(y, ref_y) < 2e-6
+
+
+@pytest.mark.parametrize("n,l1,l2,l3", [(12, 6, 0, 6), (13, 6, 0, 7), (15, 7, 0, 8), (18, 6, 6, 6)])
+def test_emulated_multi_pass_transform(emu, n, l1, l2, l3):
+    """Tile kernels + pass planning of the large-transform path (two- and three-pass four-step), with the
+    factorisation forced so that small sizes exercise it; bank-conflict free exchanges."""
+    emu.emu_large_c2c.argtypes = [C.c_int] * 5 + [fp, fp, C.c_int, C.POINTER(C.c_long)]
+    N = 1 << n
+    rng = np.random.default_rng(n)
+    x = rng.uniform(-1, 1, 2 * N).astype(np.float32)
+    z = x[0::2].astype(np.float64) + 1j * x[1::2]
+    for backward in ((0, 1) if n <= 13 else (0,)):
+        out = np.zeros_like(x)
+        st = (C.c_long * 4)()
+        assert emu.emu_large_c2c(n, l1, l2, l3, backward, x.ctypes.data_as(fp), out.ctypes.data_as(fp), int(n <= 15), st) == 0
+        ref = np.fft.ifft(z) * N if backward else np.fft.fft(z)
+        got = out[0::2] + 1j * out[1::2]
+        assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 4e-7
+        if n <= 15:
+            assert st[1] <= 1.15 * st[2] and st[3] <= 150, list(st)  # (nearly) conflict free

@@ -225,10 +225,11 @@ def test_convolve_and_accumulate(cf, oracle_mod, ref_lib):
 def test_reference_test_suite_restated(cf, oracle_mod):
     """test/test.cpp:234-304 restated: sizes 2^5..2^15 (single-kernel range), {complex, real} x
     {malloc'd, pre-allocated} x {SSE-layout, AVX-layout}; in-place ordered fwd / bwd / scale; the
-    unordered fwd -> convolve -> bwd (+ accumulate) chain.  Truth = oracle (float64), reference margin."""
+    unordered fwd -> convolve -> bwd (+ accumulate) chain.  Truth = oracle (float64), reference margin.
+    Sizes above 2^14 complex / 2^15 real run through the multi-pass path."""
     o = oracle_mod
     for is_c in (True, False):
-        for lg in range(5, 15 if is_c else 16):
+        for lg in range(5, 20):
             N = 1 << lg
             nfl = 2 * N if is_c else N
             margin = 2.0e-7 * nfl
@@ -254,7 +255,7 @@ def test_reference_test_suite_restated(cf, oracle_mod):
                     assert np.max(np.abs(data - want)) <= margin
                     cf.fft_transform(s, data, data, work, cf.FFT_BACKWARD)
                     assert np.max(np.abs(data / N - sig)) <= margin
-                    if not prealloc and lg <= 12:
+                    if not prealloc and (lg <= 12 or lg in (16, 19)):
                         sig2 = o.ref_signal(N, is_c, 200.0)
                         s1, s2, out = cf.aligned_array(nfl), cf.aligned_array(nfl), cf.aligned_array(nfl)
                         s1[:], s2[:], out[:] = sig, sig2, 0.0
@@ -317,7 +318,7 @@ def test_host_pointer_paths(cf, oracle_mod):
 def test_setup_errors(cf):
     os.environ["CHOWDSP_FFT_B200_QUIET"] = "1"
     for N, tr in ((8, cf.FFT_COMPLEX), (16, cf.FFT_REAL), (96, cf.FFT_COMPLEX), (100, cf.FFT_REAL), (0, cf.FFT_REAL),
-                  (-4, cf.FFT_COMPLEX), (1 << 15, cf.FFT_COMPLEX), (1 << 16, cf.FFT_REAL)):
+                  (-4, cf.FFT_COMPLEX), (1 << 29, cf.FFT_COMPLEX), (1 << 29, cf.FFT_REAL)):
         with pytest.raises(cf.FFTError):
             cf.fft_new_setup(N, tr)
     with pytest.raises(cf.FFTError):
@@ -483,4 +484,52 @@ def test_config4_full_size_properties(cf, oracle_mod):
     for c in (0, 2047, 4095):
         direct = np.convolve(host(x1[c]).astype(np.float64), host(ir[c]).astype(np.float64))[:blocks * B]
         assert o.rel_l2(host(y1[c]), direct) < 1e-5
+    cf.fft_destroy_setup(s)
+
+
+@pytest.mark.parametrize("is_c", [True, False])
+def test_large_transforms_multi_pass(cf, oracle_mod, ref_lib, is_c):
+    """Sizes beyond one CTA (two- and three-pass four-step, large_kernels.cuh): ordered and unordered,
+    forward and backward, in place and out of place, against the oracle and the live reference."""
+    o = oracle_mod
+    rng = np.random.default_rng(17)
+    sizes = [15, 16, 17, 19, 20, 21, 22] if is_c else [16, 17, 18, 20, 21, 22, 23]
+    for lg in sizes:
+        N = 1 << lg
+        nfl = 2 * N if is_c else N
+        tol = o.parity_tol(N)
+        x = rng.uniform(-1, 1, (2, nfl)).astype(np.float32)
+        for avx in ((True, False) if lg <= 17 else (True,)):
+            W = o.simd_width(N, is_c, avx)
+            for ordered in (True, False):
+                want_f = o.np_transform(x, N, is_c, W, False, ordered)
+                got_f = gpu_transform(cf, x, N, is_c, avx, False, ordered)
+                assert o.rel_l2(got_f, want_f) < tol, (N, is_c, W, ordered, "forward")
+                got_b = gpu_transform(cf, want_f, N, is_c, avx, True, ordered)
+                assert o.rel_l2(got_b, o.np_transform(want_f, N, is_c, W, True, ordered)) < tol, (N, is_c, W, ordered, "backward")
+                if lg <= 17:
+                    assert np.array_equal(gpu_transform(cf, x, N, is_c, avx, False, ordered, inplace=True), got_f)
+                if ref_lib is not None and lg <= 19 and avx:
+                    ref_f, _ = ref_lib.transform(x[:1], N, is_c, False, ordered, avx)
+                    assert o.rel_l2(got_f[:1], ref_f) < tol
+
+
+def test_config5_single_gpu_point(cf, oracle_mod):
+    """N = 2^26 complex on one GPU (the G=1 point of BASELINE config 5 at a size the oracle finishes in
+    seconds): round trip, Parseval, and a sampled-bin comparison against float64."""
+    o = oracle_mod
+    lg = 26
+    N = 1 << lg
+    s = cf.fft_new_setup(N, cf.FFT_COMPLEX)
+    g = torch.Generator(device="cuda").manual_seed(42)
+    x = torch.rand(2 * N, device="cuda", generator=g) * 2 - 1
+    y = torch.empty_like(x)
+    cf.fft_transform_batched(s, x, y, 1, 2 * N, 2 * N, cf.FFT_FORWARD, True)
+    ex, ey = float((x.double() ** 2).sum()), float((y.double() ** 2).sum())
+    assert abs(ey - N * ex) / (N * ex) < 1e-6
+    want = o.np_transform(host(x), N, True, 8, False, True)
+    assert o.rel_l2(host(y), want) < o.parity_tol(N)
+    z = torch.empty_like(x)
+    cf.fft_transform_batched(s, y, z, 1, 2 * N, 2 * N, cf.FFT_BACKWARD, True)
+    assert float((z / N - x).double().norm() / x.double().norm()) < o.parity_tol(N)
     cf.fft_destroy_setup(s)
