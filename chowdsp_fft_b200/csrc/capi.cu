@@ -319,10 +319,10 @@ int kind_of (const Plan* p, int direction)
     return direction == chowdsp::fft::FFT_FORWARD ? R2C : C2R;
 }
 
-// One transform larger than a CTA: 2 or 3 tile passes (+ a split/merge or reorder pass) through
+// `batch` transforms larger than a CTA: 2 or 3 tile passes (+ a split/merge or reorder pass) through
 // stream-ordered scratch.  The reference uses the caller's `work` buffer for the same purpose
-// (simd/chowdsp_fft_impl_avx.cpp:1861-1863); here `work` may stay NULL.
-int enqueue_large (Plan* p, const float* in, float* out, int direction, bool ordered, cudaStream_t stream)
+// (simd/chowdsp_fft_impl_avx.cpp:1861-1863); here `work` may stay NULL.  Strides in floats.
+int enqueue_large (Plan* p, const float* in, float* out, int batch, long long in_stride, long long out_stride, int direction, bool ordered, cudaStream_t stream)
 {
     int dev = 0;
     CFB_CUDA (cudaGetDevice (&dev));
@@ -347,67 +347,98 @@ int enqueue_large (Plan* p, const float* in, float* out, int direction, bool ord
         pass[i].args.tw_hi = bt.hi;
         pass[i].args.tw_lobits = bt.lobits;
     }
+    {   // keep freed scratch cached in the stream-ordered pool instead of returning it to the OS at every sync
+        static thread_local int pool_ready_for = -1;
+        if (pool_ready_for != dev)
+        {
+            cudaMemPool_t pool = nullptr;
+            if (cudaDeviceGetDefaultMemPool (&pool, dev) == cudaSuccess)
+            {
+                unsigned long long keep = ~0ull;
+                (void) cudaMemPoolSetAttribute (pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            (void) cudaGetLastError();
+            pool_ready_for = dev;
+        }
+    }
+    const long long npts = 1LL << n;              // float2 per transform
     const size_t bytes = sizeof (float2) << n;
+    // scratch is allocated per chunk of the batch (<= 512 MiB per buffer)
+    int chunk = (int) ((512ull << 20) / bytes);
+    chunk = chunk < 1 ? 1 : (chunk > batch ? batch : chunk);
     const bool need_s2 = fwd && (! p->is_complex || ! ordered);
     float2 *s1 = nullptr, *s2 = nullptr;
-    CFB_CUDA (cudaMallocAsync (&s1, bytes, stream));
+    CFB_CUDA (cudaMallocAsync (&s1, bytes * (size_t) chunk, stream));
     if (need_s2)
-        CFB_CUDA (cudaMallocAsync (&s2, bytes, stream));
-    auto run_passes = [&] (const float2* src, float2* dst) -> int
-    {
-        for (int i = 0; i < np; ++i)
-        {
-            pass[i].args.in = i == 0 ? src : s1;
-            pass[i].args.out = i == np - 1 ? dst : s1;
-            const cudaError_t e = launch_tile (pass[i].logL, dir, pass[i].load_j_fast, pass[i].args, stream);
-            if (e != cudaSuccess)
-                return fail_cuda (e, "tile pass launch");
-        }
-        return 0;
-    };
-    RealPassArgs ra {};
-    ra.logM = n;
-    ra.logW = ordered ? 0 : p->logW;
-    ra.tw_lobits = bt.lobits;
-    ra.tw_mult = 1;
-    ra.tw_lo = bt.lo;
-    ra.tw_hi = bt.hi;
+        CFB_CUDA (cudaMallocAsync (&s2, bytes * (size_t) chunk, stream));
     cudaError_t e = cudaSuccess;
-    if (p->is_complex)
+    for (int b0 = 0; b0 < batch && rc == 0 && e == cudaSuccess; b0 += chunk)
     {
-        if (fwd)
+        const int nb = batch - b0 < chunk ? batch - b0 : chunk;
+        const float* cin = in + (long long) b0 * in_stride;
+        float* cout = out + (long long) b0 * out_stride;
+        // src / dst strides in float2; the scratch is dense
+        auto run_passes = [&] (const float2* src, long long src_bs, float2* dst, long long dst_bs) -> int
         {
-            rc = run_passes (reinterpret_cast<const float2*> (in), ordered ? reinterpret_cast<float2*> (out) : s2);
-            if (rc == 0 && ! ordered)
-                e = launch_complex_reorder (reinterpret_cast<const float*> (s2), out, n, p->logW, true, stream);
+            for (int i = 0; i < np; ++i)
+            {
+                pass[i].args.in = i == 0 ? src : s1;
+                pass[i].args.in_bstride = i == 0 ? src_bs : npts;
+                pass[i].args.out = i == np - 1 ? dst : s1;
+                pass[i].args.out_bstride = i == np - 1 ? dst_bs : npts;
+                pass[i].args.batch = nb;
+                const cudaError_t le = launch_tile (pass[i].logL, dir, pass[i].load_j_fast, pass[i].args, stream);
+                if (le != cudaSuccess)
+                    return fail_cuda (le, "tile pass launch");
+            }
+            return 0;
+        };
+        RealPassArgs ra {};
+        ra.logM = n;
+        ra.logW = ordered ? 0 : p->logW;
+        ra.tw_lobits = bt.lobits;
+        ra.tw_mult = 1;
+        ra.tw_lo = bt.lo;
+        ra.tw_hi = bt.hi;
+        if (p->is_complex)
+        {
+            if (fwd && ordered)
+                rc = run_passes (reinterpret_cast<const float2*> (cin), in_stride / 2, reinterpret_cast<float2*> (cout), out_stride / 2);
+            else if (fwd)
+            {
+                rc = run_passes (reinterpret_cast<const float2*> (cin), in_stride / 2, s2, npts);
+                if (rc == 0)
+                    e = launch_complex_reorder (reinterpret_cast<const float*> (s2), cout, 2 * npts, out_stride, nb, n, p->logW, true, stream);
+            }
+            else if (ordered)
+                rc = run_passes (reinterpret_cast<const float2*> (cin), in_stride / 2, reinterpret_cast<float2*> (cout), out_stride / 2);
+            else
+            {
+                e = launch_complex_reorder (cin, reinterpret_cast<float*> (s1), in_stride, 2 * npts, nb, n, p->logW, false, stream);
+                if (e == cudaSuccess)
+                    rc = run_passes (s1, npts, reinterpret_cast<float2*> (cout), out_stride / 2);
+            }
+        }
+        else if (fwd)
+        {
+            rc = run_passes (reinterpret_cast<const float2*> (cin), in_stride / 2, s2, npts);
+            ra.in = reinterpret_cast<const float*> (s2);
+            ra.in_bstride = 2 * npts;
+            ra.out = cout;
+            ra.out_bstride = out_stride;
+            if (rc == 0)
+                e = launch_real_pass (-1, ra, nb, stream);
         }
         else
         {
-            const float2* src = reinterpret_cast<const float2*> (in);
-            if (! ordered)
-            {
-                e = launch_complex_reorder (in, reinterpret_cast<float*> (s1), n, p->logW, false, stream);
-                src = s1;
-            }
+            ra.in = cin;
+            ra.in_bstride = in_stride;
+            ra.out = reinterpret_cast<float*> (s1);
+            ra.out_bstride = 2 * npts;
+            e = launch_real_pass (+1, ra, nb, stream);
             if (e == cudaSuccess)
-                rc = run_passes (src, reinterpret_cast<float2*> (out));
+                rc = run_passes (s1, npts, reinterpret_cast<float2*> (cout), out_stride / 2);
         }
-    }
-    else if (fwd)
-    {
-        rc = run_passes (reinterpret_cast<const float2*> (in), s2);
-        ra.in = reinterpret_cast<const float*> (s2);
-        ra.out = out;
-        if (rc == 0)
-            e = launch_real_pass (-1, ra, stream);
-    }
-    else
-    {
-        ra.in = in;
-        ra.out = reinterpret_cast<float*> (s1);
-        e = launch_real_pass (+1, ra, stream);
-        if (e == cudaSuccess)
-            rc = run_passes (s1, reinterpret_cast<float2*> (out));
     }
     CFB_CUDA (cudaFreeAsync (s1, stream));
     if (s2 != nullptr)
@@ -421,13 +452,14 @@ int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inne
 {
     if (p->logM > kMaxLogM)
     {
+        if ((in_inner & 1) != 0 || (out_inner & 1) != 0 || (in_outer & 1) != 0 || (out_outer & 1) != 0)
+            return fail (chowdsp::fft::FFT_B200_EINVAL, "large transforms need even strides (8-byte aligned transforms)");
         for (int o = 0; o < outer; ++o)
-            for (int i = 0; i < inner; ++i)
-            {
-                const int rc = enqueue_large (p, in + o * in_outer + i * in_inner, out + o * out_outer + i * out_inner, direction, ordered, stream);
-                if (rc != 0)
-                    return rc;
-            }
+        {
+            const int rc = enqueue_large (p, in + o * in_outer, out + o * out_outer, inner, in_inner, out_inner, direction, ordered, stream);
+            if (rc != 0)
+                return rc;
+        }
         return 0;
     }
     Tables t;

@@ -17,7 +17,7 @@ cudaError_t launch_tile_one (const TileArgs& a, cudaStream_t stream)
         if (e != cudaSuccess)
             return e;
     }
-    kernel<<<(unsigned) a.ntiles, TL::THREADS, TL::SMEM_BYTES, stream>>> (a);
+    kernel<<<(unsigned) a.ntiles * (unsigned) a.batch, TL::THREADS, TL::SMEM_BYTES, stream>>> (a);
     count_launch();
     return cudaGetLastError();
 }
@@ -43,10 +43,10 @@ cudaError_t launch_tile (int logL, int dir, bool load_j_fast, const TileArgs& a,
     }
 }
 
-cudaError_t launch_real_pass (int dir, const RealPassArgs& a, cudaStream_t stream)
+cudaError_t launch_real_pass (int dir, const RealPassArgs& a, int batch, cudaStream_t stream)
 {
     const long long pairs = 1LL << (a.logM - 1);
-    const unsigned grid = (unsigned) ((pairs + 255) / 256);
+    const dim3 grid ((unsigned) ((pairs + 255) / 256), (unsigned) batch);
     if (dir < 0)
         real_pass_kernel<-1><<<grid, 256, 0, stream>>> (a);
     else
@@ -55,14 +55,14 @@ cudaError_t launch_real_pass (int dir, const RealPassArgs& a, cudaStream_t strea
     return cudaGetLastError();
 }
 
-cudaError_t launch_complex_reorder (const float* in, float* out, int logN, int logW, bool to_unordered, cudaStream_t stream)
+cudaError_t launch_complex_reorder (const float* in, float* out, long long in_bstride, long long out_bstride, int batch, int logN, int logW, bool to_unordered, cudaStream_t stream)
 {
     const long long bins = 1LL << logN;
-    const unsigned grid = (unsigned) ((bins + 255) / 256);
+    const dim3 grid ((unsigned) ((bins + 255) / 256), (unsigned) batch);
     if (to_unordered)
-        complex_reorder_kernel<true><<<grid, 256, 0, stream>>> (in, out, logN, logW);
+        complex_reorder_kernel<true><<<grid, 256, 0, stream>>> (in, out, in_bstride, out_bstride, logN, logW);
     else
-        complex_reorder_kernel<false><<<grid, 256, 0, stream>>> (in, out, logN, logW);
+        complex_reorder_kernel<false><<<grid, 256, 0, stream>>> (in, out, in_bstride, out_bstride, logN, logW);
     count_launch();
     return cudaGetLastError();
 }

@@ -33,7 +33,9 @@ struct TileArgs
     long long in_g_hi, in_g_lo, in_tstride, in_estride;
     long long out_g_hi, out_g_lo, out_tstride, out_estride;
     int gdiv;
-    int ntiles;
+    int ntiles;          // tiles of ONE transform
+    int batch;           // transforms in this launch: grid = batch * ntiles
+    long long in_bstride, out_bstride; // float2 between consecutive transforms of the batch
     // four-step twiddle after the transform: out[k] *= W_N^(k * c * tw_mult), c = (g % gdiv) * C + lt,
     // W_N^e = tw_lo[e & mask] * tw_hi[e >> tw_lobits]   (tw_mult == 0: none)
     unsigned tw_mult;
@@ -64,12 +66,13 @@ FFT_HD void tile_body (const TileArgs& a)
     static_assert (! LOAD_J_FAST || G::S >= 2, "the thread-map switch needs at least one exchange");
     FFT_DYN_SMEM (float2, smem);
     const int tid = (int) threadIdx.x;
-    const int g = (int) blockIdx.x;
-    if (g >= a.ntiles)
+    const int bx = (int) blockIdx.x / a.ntiles;
+    const int g = (int) blockIdx.x - bx * a.ntiles;
+    if (bx >= a.batch)
         return;
     const int ghi = g / a.gdiv, glo = g - ghi * a.gdiv;
-    const float2* __restrict__ in = a.in + ghi * a.in_g_hi + glo * a.in_g_lo;
-    float2* __restrict__ out = a.out + ghi * a.out_g_hi + glo * a.out_g_lo;
+    const float2* __restrict__ in = a.in + bx * a.in_bstride + ghi * a.in_g_hi + glo * a.in_g_lo;
+    float2* __restrict__ out = a.out + bx * a.out_bstride + ghi * a.out_g_hi + glo * a.out_g_lo;
 
     const int ltB = tid % C, jB = tid / C; // adjacent threads = adjacent transforms
     const int ltA = tid / T, jA = tid % T; // adjacent threads = adjacent elements
@@ -151,6 +154,7 @@ struct RealPassArgs
 {
     const float* in;
     float* out;
+    long long in_bstride, out_bstride; // floats between consecutive transforms (blockIdx.y)
     int logM;
     int logW;   // 0: ordered pffft packing, 2 / 3: unordered real layout
     int tw_lobits;
@@ -193,38 +197,40 @@ __global__ void __launch_bounds__ (256) real_pass_kernel (const RealPassArgs a)
     const int k = (int) (blockIdx.x * blockDim.x + threadIdx.x); // pair index, k <= M/2 - 1 ; k == 0 also does M/2
     if (k >= M / 2)
         return;
+    const float* a_in = a.in + (long long) blockIdx.y * a.in_bstride;
+    float* a_out = a.out + (long long) blockIdx.y * a.out_bstride;
     const unsigned e = (unsigned) k * a.tw_mult;
     const float2 lo = __ldg (a.tw_lo + (e & ((1u << a.tw_lobits) - 1u))), hi = __ldg (a.tw_hi + (e >> a.tw_lobits));
     const float2 w = cmul_dir<-1> (lo, hi);
     if (DIR < 0)
     {
         // in: natural-order complex z (float2 array); out: half spectrum
-        const float2* z = reinterpret_cast<const float2*> (a.in);
+        const float2* z = reinterpret_cast<const float2*> (a_in);
         if (k == 0)
         {
             const float2 z0 = z[0], zh = z[M / 2];
-            real_store_bin (a.out, 0, a.logM, a.logW, make_float2 (z0.x + z0.y, z0.x - z0.y));
-            real_store_bin (a.out, M / 2, a.logM, a.logW, make_float2 (zh.x, -zh.y));
+            real_store_bin (a_out, 0, a.logM, a.logW, make_float2 (z0.x + z0.y, z0.x - z0.y));
+            real_store_bin (a_out, M / 2, a.logM, a.logW, make_float2 (zh.x, -zh.y));
             return;
         }
         const float2 za = z[k], zm = z[M - k];
         const float2 ee = make_float2 (0.5f * (za.x + zm.x), 0.5f * (za.y - zm.y));
         const float2 dd = make_float2 (0.5f * (za.x - zm.x), 0.5f * (za.y + zm.y));
         const float2 wd = cmul_dir<-1> (dd, w);
-        real_store_bin (a.out, k, a.logM, a.logW, make_float2 (ee.x + wd.y, ee.y - wd.x));
-        real_store_bin (a.out, M - k, a.logM, a.logW, make_float2 (ee.x - wd.y, -ee.y - wd.x));
+        real_store_bin (a_out, k, a.logM, a.logW, make_float2 (ee.x + wd.y, ee.y - wd.x));
+        real_store_bin (a_out, M - k, a.logM, a.logW, make_float2 (ee.x - wd.y, -ee.y - wd.x));
     }
     else
     {
-        float2* z = reinterpret_cast<float2*> (a.out);
+        float2* z = reinterpret_cast<float2*> (a_out);
         if (k == 0)
         {
-            const float2 x0 = real_load_bin (a.in, 0, a.logM, a.logW), xh = real_load_bin (a.in, M / 2, a.logM, a.logW);
+            const float2 x0 = real_load_bin (a_in, 0, a.logM, a.logW), xh = real_load_bin (a_in, M / 2, a.logM, a.logW);
             z[0] = make_float2 (x0.x + x0.y, x0.x - x0.y);
             z[M / 2] = make_float2 (2.f * xh.x, -2.f * xh.y);
             return;
         }
-        const float2 xa = real_load_bin (a.in, k, a.logM, a.logW), xm = real_load_bin (a.in, M - k, a.logM, a.logW);
+        const float2 xa = real_load_bin (a_in, k, a.logM, a.logW), xm = real_load_bin (a_in, M - k, a.logM, a.logW);
         const float2 ee = make_float2 (xa.x + xm.x, xa.y - xm.y);
         const float2 dd = make_float2 (xa.x - xm.x, xa.y + xm.y);
         const float2 wd = cmul_dir<+1> (dd, w);
@@ -237,8 +243,10 @@ __global__ void __launch_bounds__ (256) real_pass_kernel (const RealPassArgs a)
 // streaming pass: 64-byte chunk of 8 (or 32-byte chunk of 4) bins per thread group).
 //   TO_UNORDERED : in = interleaved natural order, out = unordered layout ; else the inverse.
 template <bool TO_UNORDERED>
-__global__ void __launch_bounds__ (256) complex_reorder_kernel (const float* in, float* out, int logN, int logW)
+__global__ void __launch_bounds__ (256) complex_reorder_kernel (const float* in, float* out, long long in_bstride, long long out_bstride, int logN, int logW)
 {
+    in += (long long) blockIdx.y * in_bstride;
+    out += (long long) blockIdx.y * out_bstride;
     const long long bin = (long long) blockIdx.x * blockDim.x + threadIdx.x;
     if (bin >= (1LL << logN))
         return;

@@ -60,6 +60,7 @@ inline int build_tile_passes (int n, const LargeFactors& f, TilePass (&p)[3], un
         a.args.in_tstride = a.args.out_tstride = 1;
         a.args.in_estride = a.args.out_estride = S1;
         a.args.tw_mult = tw_scale;
+        a.args.batch = 1;
     }
     if (f.l2 != 0)
     {   // pass B: for every row k1, columns of its [L2][L3] view
@@ -74,6 +75,7 @@ inline int build_tile_passes (int n, const LargeFactors& f, TilePass (&p)[3], un
         b.args.in_tstride = b.args.out_tstride = 1;
         b.args.in_estride = b.args.out_estride = L3;
         b.args.tw_mult = (unsigned) L1 * tw_scale;
+        b.args.batch = 1;
     }
     {   // pass C: contiguous rows (k1, k2), written transposed to k1 + L1 (k2 + L2 k3)
         TilePass& c = p[np++];
@@ -91,6 +93,7 @@ inline int build_tile_passes (int n, const LargeFactors& f, TilePass (&p)[3], un
         c.args.out_tstride = 1;
         c.args.out_estride = L1 * L2;
         c.args.tw_mult = 0;
+        c.args.batch = 1;
     }
     return np;
 }
