@@ -367,6 +367,87 @@ class Reverb(BatchedFFT):
         return gbs, cores, f"{reps} x ({channels} channels x {blocks} blocks, {parts / blocks:.1f} partitions summed per block on average), {cores} threads, reference AVX build", per_step * 1e3
 
 
+class Huge(BatchedFFT):
+    """BASELINE configs[4]: ONE complex FFT of N = 2^28 points.  1 GPU: three-pass four-step on the device.
+    G > 1 GPUs: distributed four-step, local tile passes + one NCCL all-to-all over NVLink (transposed-out
+    contract; the natural-order variant costs a second all-to-all and is reported separately)."""
+
+    scaling = "strong"
+
+    def __init__(self, n=28):
+        self.name, self.n, self.N = "huge", n, 1 << n
+        self.is_complex, self.ordered, self.nfl = True, True, 2 << n
+        self.desc = f"single complex FFT N=2^{n} fp32 (BASELINE configs[4]): 3-pass four-step; distributed over G GPUs with an NCCL all-to-all"
+        self.kernel = "cfb::tile_fft_kernel<9|10,8,-1,*> x3 (+ ncclAllToAll for G>1)"
+
+    def config(self):
+        return {"workload": self.desc, "N": self.N, "transform": "C2C", "ordered": "natural order on 1 GPU; transposed-out per rank for G>1",
+                "passes": 3, "bytes": "algorithmic 16 N = 4 GiB per transform; each of the 3 passes re-reads and re-writes the array (12 GiB of HBM traffic in total)",
+                "l2_policy": "2 GiB arrays, far larger than L2", "sharding": "column blocks -> all-to-all -> row blocks"}
+
+    def setup(self, cf, torch, rank, world):
+        self.cf, self.torch, self.rank, self.world = cf, torch, rank, world
+        self.batch = 1
+        self.bytes_step = 16 * self.N // world
+        self.flops_step = 5.0 * self.N * math.log2(self.N) / world
+        gen = torch.Generator(device="cuda").manual_seed(42 + rank)
+        if world == 1:
+            self.plan = cf.fft_new_setup(self.N, cf.FFT_COMPLEX, True)
+            self.x = torch.rand(2 * self.N, device="cuda", generator=gen) * 2 - 1
+            self.y = torch.empty_like(self.x)
+        else:
+            from chowdsp_fft_b200.distributed import DistributedFFT
+
+            self.d = DistributedFFT(self.n, rank, world)
+            self.x = torch.rand(self.d.local_floats, device="cuda", generator=gen) * 2 - 1
+            self.y = torch.empty(self.d.S1 * self.d.rows * 2, device="cuda")
+
+    def step(self, stream):
+        if self.world == 1:
+            self.cf.fft_transform_batched(self.plan, self.x, self.y, 1, 2 * self.N, 2 * self.N, self.cf.FFT_FORWARD, True, stream)
+        else:
+            self.d.forward(self.x, self.y, stream=stream)
+
+    def parity(self):
+        if self.world != 1:
+            return {"note": "distributed parity is covered by tests/test_gpu_distributed.py"}
+        y = self.y.view(-1, 2)
+        x = self.x.view(-1, 2).double()
+        # 64 sampled bins against a direct float64 DFT sum (the full-size oracle comparison is in tests/)
+        torch = self.torch
+        ks = torch.arange(0, self.N, self.N // 64, device="cuda")[:64] + 3
+        n = torch.arange(self.N, device="cuda", dtype=torch.float64)
+        err, ref = 0.0, 0.0
+        for k in ks.tolist():
+            ang = -2.0 * math.pi * ((n * k) % self.N) / self.N
+            re = float((x[:, 0] * torch.cos(ang) - x[:, 1] * torch.sin(ang)).sum())
+            im = float((x[:, 0] * torch.sin(ang) + x[:, 1] * torch.cos(ang)).sum())
+            err += (float(y[k, 0]) - re) ** 2 + (float(y[k, 1]) - im) ** 2
+            ref += re * re + im * im
+        return {"rel_l2_vs_float64_dft": math.sqrt(err / ref), "tolerance": 1e-6 * self.n, "bins": int(ks.numel())}
+
+    def e2e(self, steps, barrier, reduce_max):
+        if self.world != 1:
+            return None
+        return BatchedFFT.e2e(self, steps, barrier, reduce_max)
+
+    def cpu(self, seconds_target, steps=1, warmup=0):
+        """The reference cannot thread one transform: 1 core by construction; bounded to 2^24."""
+        from oracle import oracle as o
+
+        ref = o.load_ref()
+        n = 24
+        N = 1 << n
+        rng = np.random.default_rng(42)
+        xin = o.aligned_copy(rng.uniform(-1, 1, 2 * N).astype(np.float32))
+        out = o.aligned_empty(2 * N)
+        times = []
+        for it in range(warmup + steps):
+            times.append(ref.transform_timed(xin, out, N, True, False, True, 1, 2 * N, 2 * N, 1))
+        per = float(np.mean(times[warmup:] or times))
+        return 16 * N / per / 1e9, 1, f"one C2C N=2^{n} transform (plan setup excluded), 1 thread: the reference is single-threaded per transform", per * 1e3
+
+
 WORKLOADS = {
     "c2c4096": lambda: BatchedFFT("c2c4096", 4096, True, 65536, True, "batched C2C N=4096 x 65536 fp32, ordered, forward (BASELINE configs[1])"),
     "c2c4096_unordered": lambda: BatchedFFT("c2c4096_unordered", 4096, True, 65536, False, "batched C2C N=4096 x 65536 fp32, unordered (reference W=8 layout), forward (BASELINE configs[1])"),
@@ -377,6 +458,7 @@ WORKLOADS = {
     "r2c8192": lambda: BatchedFFT("r2c8192", 8192, False, 131072, False, "batched R2C N=8192 x 131072 fp32, unordered, forward"),
     "stft": STFT,
     "reverb": Reverb,
+    "huge": Huge,
 }
 
 

@@ -161,3 +161,15 @@ def fft_partitioned_convolve_step(setup: int, windows, window_stride: int, ir, i
     _check(lib().fft_partitioned_convolve_step(setup, _addr(windows), window_stride, _addr(ir), ir_channel_stride,
                                                _addr(fdl), fdl_channel_stride, _addr(output), output_stride,
                                                channels, partitions, block_index, scaling, _stream(stream)))
+
+
+def fft_large_factors(setup: int) -> tuple[int, int, int]:
+    """(l1, l2, l3): log2 of the pass lengths of a multi-pass plan."""
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    _check(lib().fft_large_factors(setup, C.byref(a), C.byref(b), C.byref(c)))
+    return a.value, b.value, c.value
+
+
+def fft_dist_phase(setup: int, phase: int, rank: int, world: int, input, output, direction: int = FFT_FORWARD, stream=None) -> None:
+    """One local phase of the distributed four-step transform (see chowdsp_fft_b200.h)."""
+    _check(lib().fft_dist_phase(setup, phase, rank, world, _addr(input), _addr(output), direction, _stream(stream)))

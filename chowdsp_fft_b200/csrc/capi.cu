@@ -870,6 +870,56 @@ CFB_API int fft_partitioned_convolve_step (void* setup, const float* windows, lo
     return e == cudaSuccess ? 0 : fail_cuda (e, "partitioned convolution kernel launch");
 }
 
+CFB_API int fft_large_factors (void* setup, int* l1, int* l2, int* l3)
+{
+    Plan* p = as_plan (setup);
+    if (p == nullptr)
+        return FFT_B200_EINVAL;
+    if (p->logM <= kMaxLogM)
+        return fail (FFT_B200_EINVAL, "fft_large_factors: N=%d is a single-kernel plan", p->N);
+    const LargeFactors f = choose_factors (p->logM);
+    if (l1 != nullptr)
+        *l1 = f.l1;
+    if (l2 != nullptr)
+        *l2 = f.l2;
+    if (l3 != nullptr)
+        *l3 = f.l3;
+    return 0;
+}
+
+CFB_API int fft_dist_phase (void* setup, int phase, int rank, int world, const float* in, float* out, fft_direction_t direction, void* stream)
+{
+    Plan* p = as_plan (setup);
+    if (p == nullptr)
+        return FFT_B200_EINVAL;
+    if (! p->is_complex || p->logM <= kMaxLogM)
+        return fail (FFT_B200_EINVAL, "fft_dist_phase needs a complex multi-pass plan");
+    if (in == nullptr || out == nullptr || phase < 0 || phase > 2 || rank < 0 || rank >= world)
+        return fail (FFT_B200_EINVAL, "fft_dist_phase: bad arguments");
+    const LargeFactors f = choose_factors (p->logM);
+    TilePass tp;
+    if (! build_dist_phase (p->logM, f, phase, rank, world, tp))
+        return fail (FFT_B200_EINVAL, "fft_dist_phase: N=2^%d cannot be split over %d ranks (needs a three-pass plan, power-of-two world, L1/world >= 8)", p->logM, world);
+    int dev = 0;
+    CFB_CUDA (cudaGetDevice (&dev));
+    BigTables bt;
+    int rc = get_big_tables (dev, p->logM, bt);
+    if (rc != 0)
+        return rc;
+    Tables st;
+    rc = get_tables (dev, tp.logL, false, st);
+    if (rc != 0)
+        return rc;
+    tp.args.tw = st.tw;
+    tp.args.tw_lo = bt.lo;
+    tp.args.tw_hi = bt.hi;
+    tp.args.tw_lobits = bt.lobits;
+    tp.args.in = reinterpret_cast<const float2*> (in);
+    tp.args.out = reinterpret_cast<float2*> (out);
+    const cudaError_t e = launch_tile (tp.logL, direction == FFT_FORWARD ? -1 : +1, tp.load_j_fast, tp.args, static_cast<cudaStream_t> (stream));
+    return e == cudaSuccess ? 0 : fail_cuda (e, "distributed phase launch");
+}
+
 CFB_API int fft_accumulate_batched (void* setup, const float* a, const float* b, float* ab, long long n, void* stream)
 {
     Plan* p = as_plan (setup);

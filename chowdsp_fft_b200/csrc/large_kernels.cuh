@@ -36,6 +36,11 @@ struct TileArgs
     int ntiles;          // tiles of ONE transform
     int batch;           // transforms in this launch: grid = batch * ntiles
     long long in_bstride, out_bstride; // float2 between consecutive transforms of the batch
+    // optional two-level element stride on the input side (distributed exchange layout): element idx sits at
+    // (idx >> in_split_log) * in_chunk_stride + (idx & mask) * in_estride ; in_split_log = 31 disables it
+    int in_split_log;
+    long long in_chunk_stride;
+    unsigned tw_c_base;  // added to the twiddle column index (this rank's first global column)
     // four-step twiddle after the transform: out[k] *= W_N^(k * c * tw_mult), c = (g % gdiv) * C + lt,
     // W_N^e = tw_lo[e & mask] * tw_hi[e >> tw_lobits]   (tw_mult == 0: none)
     unsigned tw_mult;
@@ -94,17 +99,31 @@ FFT_HD void tile_body (const TileArgs& a)
     }
     else
     {
-        const float2* __restrict__ p = in + ltB * a.in_tstride + jB * a.in_estride;
+        const float2* __restrict__ p = in + ltB * a.in_tstride;
+        if (a.in_split_log >= 31)
+        {
+            p += jB * a.in_estride;
 #pragma unroll
-        for (int m = 0; m < R; ++m)
-            v[m] = ldg_stream (p + (long long) (m * T) * a.in_estride);
+            for (int m = 0; m < R; ++m)
+                v[m] = ldg_stream (p + (long long) (m * T) * a.in_estride);
+        }
+        else
+        {
+            const int mask = (1 << a.in_split_log) - 1;
+#pragma unroll
+            for (int m = 0; m < R; ++m)
+            {
+                const int idx = jB + m * T;
+                v[m] = ldg_stream (p + (long long) (idx >> a.in_split_log) * a.in_chunk_stride + (long long) (idx & mask) * a.in_estride);
+            }
+        }
         Stages<G, DIR, 0>::run (v, jB, sB, a.tw, false);
     }
 
     // v[m] = X[jB + m T] of transform ltB
     if (a.tw_mult != 0)
     {
-        const unsigned c = (unsigned) (glo * C + ltB);
+        const unsigned c = a.tw_c_base + (unsigned) (glo * C + ltB);
         const unsigned e0 = (unsigned) jB * c * a.tw_mult, de = (unsigned) T * c * a.tw_mult; // e(m) = e0 + m de < N
         // exact table values for m = 0..3 and for the strides 4, 8, 12; the rest is one product each
         float2 w[4], d[4];

@@ -61,6 +61,7 @@ inline int build_tile_passes (int n, const LargeFactors& f, TilePass (&p)[3], un
         a.args.in_estride = a.args.out_estride = S1;
         a.args.tw_mult = tw_scale;
         a.args.batch = 1;
+        a.args.in_split_log = 31;
     }
     if (f.l2 != 0)
     {   // pass B: for every row k1, columns of its [L2][L3] view
@@ -76,6 +77,7 @@ inline int build_tile_passes (int n, const LargeFactors& f, TilePass (&p)[3], un
         b.args.in_estride = b.args.out_estride = L3;
         b.args.tw_mult = (unsigned) L1 * tw_scale;
         b.args.batch = 1;
+        b.args.in_split_log = 31;
     }
     {   // pass C: contiguous rows (k1, k2), written transposed to k1 + L1 (k2 + L2 k3)
         TilePass& c = p[np++];
@@ -94,8 +96,82 @@ inline int build_tile_passes (int n, const LargeFactors& f, TilePass (&p)[3], un
         c.args.out_estride = L1 * L2;
         c.args.tw_mult = 0;
         c.args.batch = 1;
+        c.args.in_split_log = 31;
     }
     return np;
+}
+
+// Distributed four-step over `world` ranks (three-pass plans only).  Data contracts, N = L1 L2 L3, S1 = L2 L3:
+//   phase 0 input  : rank r holds the column block  A_r[n1][c] = x[n1 S1 + r S1/world + c]   ([L1][S1/world])
+//   phase 0        : pass A on the local columns, in place layout ([k1][c]); rows k1 of block h are the
+//                    contiguous chunk sent to rank h by the all-to-all
+//   phase 1 input  : exchange layout [world][L1/world][S1/world] (chunk g = columns of rank g)
+//   phase 1        : pass B, reading the exchange layout, writing natural rows [L1/world][S1]
+//   phase 2        : pass C, writing "transposed-out": out[q][k1_local] = X[(r L1/world + k1_local) + L1 q]
+inline bool build_dist_phase (int n, const LargeFactors& f, int phase, int rank, int world, TilePass& p)
+{
+    if (f.l2 == 0 || world < 1 || (world & (world - 1)) != 0)
+        return false;
+    const long long N = 1LL << n, L1 = 1LL << f.l1, L2 = 1LL << f.l2, L3 = 1LL << f.l3, S1 = L2 * L3;
+    if (L1 / world < kTileC || L2 / world < 1 || S1 / world < kTileC)
+        return false;
+    int wl = 0;
+    while ((1 << wl) < world)
+        ++wl;
+    p = {};
+    p.args.batch = 1;
+    p.args.in_split_log = 31;
+    (void) N;
+    if (phase == 0)
+    {
+        const long long cols = S1 / world;
+        p.logL = f.l1;
+        p.load_j_fast = false;
+        p.args.gdiv = (int) (cols / kTileC);
+        p.args.ntiles = (int) (cols / kTileC);
+        p.args.in_g_lo = p.args.out_g_lo = kTileC;
+        p.args.in_tstride = p.args.out_tstride = 1;
+        p.args.in_estride = p.args.out_estride = cols;
+        p.args.tw_mult = 1;
+        p.args.tw_c_base = (unsigned) (rank * cols);
+    }
+    else if (phase == 1)
+    {
+        const long long rows = L1 / world, cols = S1 / world;
+        p.logL = f.l2;
+        p.load_j_fast = false;
+        p.args.gdiv = (int) (L3 / kTileC);
+        p.args.ntiles = (int) (rows * L3 / kTileC);
+        p.args.in_g_hi = cols;             // row k1_local inside every chunk
+        p.args.in_g_lo = kTileC;
+        p.args.in_tstride = 1;
+        p.args.in_estride = L3;
+        p.args.in_split_log = f.l2 - wl;   // n2 values per chunk
+        p.args.in_chunk_stride = rows * cols;
+        p.args.out_g_hi = S1;
+        p.args.out_g_lo = kTileC;
+        p.args.out_tstride = 1;
+        p.args.out_estride = L3;
+        p.args.tw_mult = (unsigned) L1;
+    }
+    else
+    {
+        const long long rows = L1 / world;
+        p.logL = f.l3;
+        p.load_j_fast = true;
+        p.args.gdiv = (int) (rows / kTileC);
+        p.args.ntiles = (int) (rows * L2 / kTileC);
+        p.args.in_g_hi = L3;
+        p.args.in_g_lo = kTileC * S1;
+        p.args.in_tstride = S1;
+        p.args.in_estride = 1;
+        p.args.out_g_hi = rows;
+        p.args.out_g_lo = kTileC;
+        p.args.out_tstride = 1;
+        p.args.out_estride = rows * L2;
+        p.args.tw_mult = 0;
+    }
+    return true;
 }
 
 inline int big_twiddle_lobits (int n) { return n < 28 ? (n + 1) / 2 : 14; }

@@ -59,6 +59,23 @@ int fft_convolve_unordered_batched (void* setup, const float* dft_a, const float
    (test/test.cpp:214-218 shows the pattern), in one launch.  Device pointers only; stream-ordered. */
 int fft_partitioned_convolve_step (void* setup, const float* windows, long long window_stride, const float* ir, long long ir_channel_stride, float* fdl, long long fdl_channel_stride, float* output, long long output_stride, int channels, int partitions, int block_index, float scaling, void* stream);
 
+/* Distributed four-step transform of ONE complex transform of N = 2^n >= 2^21 points over `world` GPUs
+   (one process per GPU): the three LOCAL phases; the exchange between phase 0 and phase 1 is an
+   all-to-all of equal contiguous chunks (NCCL, or peer stores, see fft_dist_phase0_peer).
+   With N = L1*L2*L3 (fft_large_factors) and S1 = L2*L3, in complex elements:
+     phase 0  in : this rank's column block  A[n1][c] = x[n1*S1 + rank*S1/world + c]   ([L1][S1/world])
+              out: same shape; row block h (rows h*L1/world ...) is the contiguous chunk for rank h
+     phase 1  in : exchange layout [world][L1/world][S1/world] (chunk g came from rank g)
+              out: natural rows [L1/world][S1]
+     phase 2  in : phase 1's output ; out: "transposed-out" [S1][L1/world],
+              out[q][k] = X[(rank*L1/world + k) + L1*q]   (direction FFT_FORWARD; BACKWARD is the conjugate)
+   world must be a power of two with L1/world >= 8.  Device pointers, stream-ordered. */
+int fft_dist_phase (void* setup, int phase, int rank, int world, const float* in, float* out, fft_direction_t direction, void* stream);
+
+/* log2 of the pass lengths of a multi-pass plan (l2 = 0 for two-pass plans); returns FFT_B200_EINVAL for
+   single-kernel plans. */
+int fft_large_factors (void* setup, int* l1, int* l2, int* l3);
+
 /* ab[i] = a[i] + b[i] for n floats (n % 8 == 0), stream-ordered.  Reference chowdsp_fft.h:160. */
 int fft_accumulate_batched (void* setup, const float* a, const float* b, float* ab, long long n, void* stream);
 

@@ -201,6 +201,36 @@ int emu_large_c2c (int n, int l1, int l2, int l3, int backward, const float* in,
     return 0;
 }
 
+// one local phase of the distributed four-step (large_plan.h: build_dist_phase); forward only
+int emu_dist_phase (int n, int l1, int l2, int l3, int phase, int rank, int world, const float* in, float* out)
+{
+    LargeFactors f;
+    f.l1 = l1; f.l2 = l2; f.l3 = l3;
+    TilePass p;
+    if (! build_dist_phase (n, f, phase, rank, world, p))
+        return -2;
+    const int lobits = big_twiddle_lobits (n);
+    std::vector<float2> lo ((size_t) 1 << lobits), hi ((size_t) 1 << (n - lobits)), tw;
+    fill_big_twiddles (lo.data(), hi.data(), n, lobits);
+    switch (p.logL)
+    {
+        case 6: fill_tw_for<6> (tw); break;
+        case 7: fill_tw_for<7> (tw); break;
+        case 8: fill_tw_for<8> (tw); break;
+        case 9: fill_tw_for<9> (tw); break;
+        case 10: fill_tw_for<10> (tw); break;
+        default: return -3;
+    }
+    p.args.tw = tw.data();
+    p.args.tw_lo = lo.data();
+    p.args.tw_hi = hi.data();
+    p.args.tw_lobits = lobits;
+    p.args.in = reinterpret_cast<const float2*> (in);
+    p.args.out = reinterpret_cast<float2*> (out);
+    emu::g_log_smem = false;
+    return emu_tile_dispatch<-1> (p);
+}
+
 int emu_convolve (const float* a, const float* b, float* ab, long long a_stride, long long b_stride, long long ab_stride, int nfloats, int batch, int logW, int is_real, float scaling)
 {
     ConvArgs p { a, b, ab, a_stride, b_stride, ab_stride, nfloats, batch, logW, is_real, scaling };
