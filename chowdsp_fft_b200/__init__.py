@@ -8,7 +8,7 @@ from .api import (FFT_BACKWARD, FFT_COMPLEX, FFT_FORWARD, FFT_REAL, FFTError, al
                   aligned_malloc, device_available, fft_accumulate, fft_accumulate_batched, fft_bytes_required,
                   fft_convolve_unordered, fft_convolve_unordered_batched, fft_destroy_setup, fft_dist_phase,
                   fft_large_factors, fft_new_setup,
-                  fft_new_setup_preallocated, fft_partitioned_convolve_step, fft_simd_width_bytes, fft_transform, fft_transform_batched,
+                  fft_new_setup_preallocated, fft_partitioned_convolve_step, fft_simd_width_bytes, fft_stft_forward, fft_transform, fft_transform_batched,
                   fft_transform_strided, fft_transform_unordered, launch_count)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

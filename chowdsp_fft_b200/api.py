@@ -144,6 +144,14 @@ def fft_transform_strided(setup: int, input, output, outer: int, inner: int, in_
                                        out_outer, out_inner, direction, int(ordered), _stream(stream)))
 
 
+def fft_stft_forward(setup: int, signal, spectra, channels: int, frames: int, channel_stride: int, hop: int,
+                     out_channel_stride: int, out_frame_stride: int, window=None, ordered: bool = True, stream=None) -> None:
+    """Short-time Fourier analysis (frame gather + optional window + R2C in one kernel, see chowdsp_fft_b200.h)."""
+    _check(lib().fft_stft_forward(setup, _addr(signal), _addr(spectra), channels, frames, channel_stride, hop,
+                                  out_channel_stride, out_frame_stride, _addr(window) if window is not None else None,
+                                  int(ordered), _stream(stream)))
+
+
 def fft_convolve_unordered_batched(setup: int, dft_a, dft_b, dft_ab, batch: int, a_stride: int, b_stride: int,
                                    ab_stride: int, scaling: float, stream=None) -> None:
     _check(lib().fft_convolve_unordered_batched(setup, _addr(dft_a), _addr(dft_b), _addr(dft_ab), batch,

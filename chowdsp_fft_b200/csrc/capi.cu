@@ -448,8 +448,10 @@ int enqueue_large (Plan* p, const float* in, float* out, int batch, long long in
     return rc;
 }
 
-int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inner, long long in_outer, long long in_inner, long long out_outer, long long out_inner, int direction, bool ordered, cudaStream_t stream)
+int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inner, long long in_outer, long long in_inner, long long out_outer, long long out_inner, int direction, bool ordered, cudaStream_t stream, const float* window = nullptr)
 {
+    if (window != nullptr && (p->logM > kMaxLogM || p->is_complex || direction != chowdsp::fft::FFT_FORWARD || in_inner <= 0 || in_inner > p->N))
+        return fail (chowdsp::fft::FFT_B200_EINVAL, "windowed transforms need a REAL single-kernel plan, FFT_FORWARD and 0 < hop <= N");
     if (p->logM > kMaxLogM)
     {
         if ((in_inner & 1) != 0 || (out_inner & 1) != 0 || (in_outer & 1) != 0 || (out_outer & 1) != 0)
@@ -477,6 +479,20 @@ int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inne
     a.batch = outer * inner;
     a.tw = t.tw;
     a.rtw = t.rtw;
+    // overlapping real frames (STFT analysis): one CTA gathers the union of its frames once
+    const bool fwd_real = ! p->is_complex && direction == chowdsp::fft::FFT_FORWARD;
+    if (fwd_real && in_inner > 0 && in_inner <= p->N && (in_inner & 1) == 0 && (in_outer & 1) == 0
+        && (window != nullptr || (in_inner < p->N && inner > 1 && transforms_per_cta (p->logM) > 1)))
+    {
+        a.window = window;
+        a.vec4 = ((reinterpret_cast<uintptr_t> (in) & 15) == 0 && (in_inner & 3) == 0 && (in_outer & 3) == 0) ? 1 : 0;
+        const cudaError_t es = launch_stft (p->logM, ordered ? 0 : p->logW, a, stream);
+        if (es != cudaSuccess)
+            return fail_cuda (es, "stft kernel launch");
+        return 0;
+    }
+    if (window != nullptr)
+        return fail (chowdsp::fft::FFT_B200_EINVAL, "windowed transforms need even hop and channel strides");
     const cudaError_t e = launch_fft (p->logM, kind_of (p, direction), ordered ? 0 : p->logW, a, stream);
     if (e != cudaSuccess)
         return fail_cuda (e, "fft kernel launch");
@@ -821,6 +837,22 @@ CFB_API int fft_transform_strided (void* setup, const float* input, float* outpu
     if (classify (input).kind != Mem::Device || classify (output).kind != Mem::Device)
         return fail (FFT_B200_EINVAL, "fft_transform_strided needs device pointers");
     return enqueue_transform (p, input, output, outer, inner, in_outer, in_inner, out_outer, out_inner, direction, ordered != 0, static_cast<cudaStream_t> (stream));
+}
+
+CFB_API int fft_stft_forward (void* setup, const float* signal, float* spectra, int channels, int frames, long long channel_stride, long long hop, long long out_channel_stride, long long out_frame_stride, const float* window, int ordered, void* stream)
+{
+    Plan* p = as_plan (setup);
+    if (p == nullptr)
+        return FFT_B200_EINVAL;
+    if (p->is_complex)
+        return fail (FFT_B200_EINVAL, "fft_stft_forward needs a REAL plan");
+    if (signal == nullptr || spectra == nullptr || channels < 0 || frames < 0 || hop <= 0 || (long long) channels * frames > 0x7fffffffLL)
+        return fail (FFT_B200_EINVAL, "fft_stft_forward: bad arguments");
+    if (channels == 0 || frames == 0)
+        return 0;
+    if (classify (signal).kind != Mem::Device || classify (spectra).kind != Mem::Device || (window != nullptr && classify (window).kind != Mem::Device))
+        return fail (FFT_B200_EINVAL, "fft_stft_forward needs device pointers");
+    return enqueue_transform (p, signal, spectra, channels, frames, channel_stride, hop, out_channel_stride, out_frame_stride, FFT_FORWARD, ordered != 0, static_cast<cudaStream_t> (stream), window);
 }
 
 CFB_API int fft_convolve_unordered_batched (void* setup, const float* a, const float* b, float* ab, int batch, long long a_stride, long long b_stride, long long ab_stride, float scaling, void* stream)

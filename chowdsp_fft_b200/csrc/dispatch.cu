@@ -37,6 +37,28 @@ cudaError_t launch_pconv (int logM, int logW, const PConvArgs& args, cudaStream_
         default: return cudaErrorInvalidValue;
     }
 }
+cudaError_t launch_stft (int logM, int logW, const FftArgs& args, cudaStream_t stream)
+{
+    switch (logM)
+    {
+#define X(n) \
+    case n: return launch_stft_##n (logW, args, stream);
+        CFB_FOR_SIZES (X)
+#undef X
+        default: return cudaErrorInvalidValue;
+    }
+}
+int transforms_per_cta (int logM)
+{
+    switch (logM)
+    {
+#define X(n) \
+    case n: return transforms_per_cta_##n();
+        CFB_FOR_SIZES (X)
+#undef X
+        default: return 1;
+    }
+}
 int stage_twiddle_len (int logM)
 {
     switch (logM)

@@ -15,6 +15,10 @@ constexpr int kRadix = 16;   // complex points per thread
 // One launch of the single-kernel transform (complex length 2^logM per transform).
 // logW: 0 = ordered output/input, 2 / 3 = the reference's 4- / 8-lane unordered layout
 cudaError_t launch_fft (int logM, int kind, int logW, const FftArgs& args, cudaStream_t stream);
+// frame-gather R2C (STFT analysis): transform (o, i) reads in + o in_outer + i in_inner with 0 < in_inner <= N,
+// optional window; one CTA gathers the union of its frames once (stft_kernel)
+cudaError_t launch_stft (int logM, int logW, const FftArgs& args, cudaStream_t stream);
+int transforms_per_cta (int logM);
 // number of float2 entries of the stage twiddle table for 2^logM, and the fill routine (fp64 -> fp32)
 int stage_twiddle_len (int logM);
 void fill_stage_twiddles_rt (int logM, float2* tw);
@@ -38,6 +42,8 @@ void count_launch();
 #define CFB_DECL_INST(n)                                                                       \
     cudaError_t launch_fft_##n (int kind, int logW, const FftArgs& args, cudaStream_t stream);      \
     cudaError_t launch_pconv_##n (int logW, const PConvArgs& args, cudaStream_t stream);           \
+    cudaError_t launch_stft_##n (int logW, FftArgs args, cudaStream_t stream);                     \
+    int transforms_per_cta_##n();                                                              \
     int stage_twiddle_len_##n();                                                               \
     void fill_stage_twiddles_##n (float2* tw);
 CFB_DECL_INST (4)

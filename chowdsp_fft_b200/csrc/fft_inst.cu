@@ -90,6 +90,46 @@ cudaError_t CFB_CAT (launch_pconv_, CFB_LOGM) (int logW, const PConvArgs& a, cud
     return cudaErrorInvalidValue;
 }
 
+namespace
+{
+template <int LOGW>
+cudaError_t launch_stft_one (const FftArgs& a, cudaStream_t stream)
+{
+    using L = Launch<CFB_LOGM, kRadix>;
+    auto kernel = stft_kernel<CFB_LOGM, kRadix, LOGW>;
+    constexpr int smem_bytes = LOGW != 0 ? L::SMEM_BYTES_UNORD : L::SMEM_BYTES;
+    static_assert (smem_bytes >= L::PER_CTA * (8 << CFB_LOGM), "the union image must fit in the exchange buffers");
+    if (smem_bytes > 48 * 1024)
+    {
+        const cudaError_t e = cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e != cudaSuccess)
+            return e;
+    }
+    if (a.batch <= 0)
+        return cudaSuccess;
+    const long long outer = a.batch / a.inner;
+    kernel<<<(unsigned) (outer * a.groups), L::THREADS, smem_bytes, stream>>> (a);
+    count_launch();
+    return cudaGetLastError();
+}
+} // namespace
+
+// frame-gather R2C (STFT analysis); fills in a.groups
+cudaError_t CFB_CAT (launch_stft_, CFB_LOGM) (int logW, FftArgs a, cudaStream_t stream)
+{
+    a.groups = (a.inner + Launch<CFB_LOGM, kRadix>::PER_CTA - 1) / Launch<CFB_LOGM, kRadix>::PER_CTA;
+    switch (logW)
+    {
+        case 0: return launch_stft_one<0> (a, stream);
+        case 2: return launch_stft_one<2> (a, stream);
+#if CFB_LOGM >= 6
+        case 3: return launch_stft_one<3> (a, stream);
+#endif
+        default: return cudaErrorInvalidValue;
+    }
+}
+int CFB_CAT (transforms_per_cta_, CFB_LOGM)() { return Launch<CFB_LOGM, kRadix>::PER_CTA; }
+
 int CFB_CAT (stage_twiddle_len_, CFB_LOGM)() { return Geo<CFB_LOGM, kRadix>::TW_LEN; }
 void CFB_CAT (fill_stage_twiddles_, CFB_LOGM) (float2* tw) { fill_stage_twiddles<CFB_LOGM, kRadix> (tw); }
 } // namespace cfb

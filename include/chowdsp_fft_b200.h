@@ -41,6 +41,14 @@ int fft_transform_batched (void* setup, const float* input, float* output, int b
    in_inner = hop, in_outer = channel stride); outputs must not.  Device pointers only. */
 int fft_transform_strided (void* setup, const float* input, float* output, int outer, int inner, long long in_outer, long long in_inner, long long out_outer, long long out_inner, fft_direction_t direction, int ordered, void* stream);
 
+/* Short-time Fourier analysis of `channels` real signals: frame f of channel c is the N samples at
+   signal + c*channel_stride + f*hop (0 < hop, frames may overlap), multiplied by window[0..N) when window
+   is non-NULL (NULL = rectangular, which is what a loop over reference chowdsp_fft.h:138 computes), and its
+   forward real transform is written to spectra + c*out_channel_stride + f*out_frame_stride (N floats,
+   ordered pffft packing or the unordered layout).  One kernel: a CTA gathers the union of its consecutive
+   frames from HBM/L2 once.  Device pointers only; hop and channel_stride even; window needs hop <= N. */
+int fft_stft_forward (void* setup, const float* signal, float* spectra, int channels, int frames, long long channel_stride, long long hop, long long out_channel_stride, long long out_frame_stride, const float* window, int ordered, void* stream);
+
 /* batch x (ab += a*b*scaling) on unordered spectra; a stride of 0 shares that operand across the
    batch (e.g. one impulse response for all channels).  Replaces a loop over reference chowdsp_fft.h:154. */
 int fft_convolve_unordered_batched (void* setup, const float* dft_a, const float* dft_b, float* dft_ab, int batch, long long a_stride, long long b_stride, long long ab_stride, float scaling, void* stream);

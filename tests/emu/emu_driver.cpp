@@ -131,6 +131,46 @@ int emu_fft (int logM, int kind, int unord, int logW, const float* in, float* ou
     return rc;
 }
 
+// frame-gather R2C (stft_kernel): `outer` channels x `inner` frames, hop = in_inner, optional window
+int emu_stft (int logM, int unord, int logW, const float* in, float* out, int outer, int inner, long long in_outer, long long in_inner, long long out_outer, long long out_inner, const float* window, int vec4, int log_conflicts, long* stats)
+{
+    auto run = [&] (auto logm_c, auto logw_c) -> int
+    {
+        constexpr int LOGM = decltype (logm_c)::value, LOGW = decltype (logw_c)::value;
+        using G = Geo<LOGM, 16>;
+        using L = Launch<LOGM, 16>;
+        std::vector<float2> tw ((size_t) G::TW_LEN + 1), rtw ((size_t) G::M / 2 + 1);
+        fill_stage_twiddles<LOGM, 16> (tw.data());
+        fill_real_twiddles (rtw.data(), G::M);
+        FftArgs a {};
+        a.in = in; a.out = out;
+        a.in_inner = in_inner; a.in_outer = in_outer; a.out_inner = out_inner; a.out_outer = out_outer;
+        a.inner = inner; a.batch = outer * inner;
+        a.tw = tw.data(); a.rtw = rtw.data();
+        a.window = window; a.vec4 = vec4;
+        a.groups = (inner + L::PER_CTA - 1) / L::PER_CTA;
+        emu::launch (stft_kernel<LOGM, 16, LOGW>, dim3 ((unsigned) (outer * a.groups)), dim3 (L::THREADS), (size_t) (LOGW != 0 ? L::SMEM_BYTES_UNORD : L::SMEM_BYTES), a);
+        return 0;
+    };
+    using std::integral_constant;
+    emu::g_log_smem = log_conflicts != 0;
+    emu::g_stats = {};
+    int rc = -1;
+    const int lw = unord ? logW : 0;
+#define CFB_EMU_STFT(M, W) if (logM == M && lw == W) rc = run (integral_constant<int, M> {}, integral_constant<int, W> {});
+    CFB_EMU_STFT (4, 0) CFB_EMU_STFT (4, 2) CFB_EMU_STFT (6, 0) CFB_EMU_STFT (6, 3) CFB_EMU_STFT (8, 0) CFB_EMU_STFT (8, 3)
+    CFB_EMU_STFT (10, 0) CFB_EMU_STFT (10, 3) CFB_EMU_STFT (10, 2) CFB_EMU_STFT (12, 0)
+#undef CFB_EMU_STFT
+    if (stats)
+    {
+        stats[0] = emu::g_stats.ops;
+        stats[1] = emu::g_stats.wavefronts;
+        stats[2] = emu::g_stats.ideal;
+        stats[3] = emu::g_stats.worst;
+    }
+    return rc;
+}
+
 // fused partitioned-convolution step, real size N = 2^(logM+1)
 int emu_pconv (int logM, int logW, const float* in, long long in_stride, const float* ir, long long ir_ch_stride, float* fdl, long long fdl_ch_stride, float* out, long long out_stride, int channels, int P, int t, float scaling)
 {

@@ -18,6 +18,7 @@ def emu():
     L.emu_fft.argtypes = [C.c_int] * 4 + [fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 4 + [C.c_int, C.POINTER(C.c_long)]
     L.emu_convolve.argtypes = [fp, fp, fp] + [C.c_longlong] * 3 + [C.c_int] * 4 + [C.c_float]
     L.emu_accumulate.argtypes = [fp, fp, fp, C.c_longlong]
+    L.emu_stft.argtypes = [C.c_int] * 3 + [fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 4 + [fp, C.c_int, C.c_int, C.POINTER(C.c_long)]
     return L
 
 
@@ -190,3 +191,29 @@ def test_emulated_multi_pass_transform(emu, n, l1, l2, l3):
         assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 4e-7
         if n <= 15:
             assert st[1] <= 1.15 * st[2] and st[3] <= 150, list(st)  # (nearly) conflict free
+
+
+@pytest.mark.parametrize("N,hop,frames,ordered,W", [(2048, 512, 7, True, 8), (2048, 512, 4, False, 8), (2048, 2048, 5, True, 8),
+                                                    (512, 96, 19, True, 8), (512, 130, 9, False, 8), (128, 32, 18, False, 8),
+                                                    (32, 8, 21, True, 4), (32, 6, 40, False, 4), (8192, 1024, 3, True, 8)])
+@pytest.mark.parametrize("windowed", [False, True])
+def test_emulated_stft_gather(emu, oracle_mod, N, hop, frames, ordered, W, windowed):
+    """Frame-gather kernel (union of the CTA's frames staged once in shared memory, optional window) ==
+    a loop of single out-of-place transforms over the overlapping frames (the ragged last group included)."""
+    o = oracle_mod
+    channels = 2
+    samples = (frames - 1) * hop + N + 6
+    rng = np.random.default_rng(N + hop)
+    sig = rng.uniform(-1, 1, (channels, samples)).astype(np.float32)
+    win = (0.5 - 0.5 * np.cos(2 * np.pi * (np.arange(N) + 0.5) / N)).astype(np.float32)
+    out = np.zeros((channels, frames, N), np.float32)
+    st = (C.c_long * 4)()
+    vec4 = int(hop % 4 == 0 and samples % 4 == 0)
+    rc = emu.emu_stft(int(np.log2(N)) - 1, 0 if ordered else 1, {8: 3, 4: 2}[W], sig.ctypes.data_as(fp), out.ctypes.data_as(fp),
+                      channels, frames, samples, hop, frames * N, N, win.ctypes.data_as(fp) if windowed else None, vec4, 1, st)
+    assert rc == 0
+    fr = np.stack([[sig[c, f * hop:f * hop + N] for f in range(frames)] for c in range(channels)])
+    if windowed:
+        fr = fr * win
+    want = o.np_transform(fr.reshape(-1, N).astype(np.float32), N, False, W, False, ordered).reshape(out.shape)
+    assert o.rel_l2(out, want) < min(o.parity_tol(N), 4e-7)

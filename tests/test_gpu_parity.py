@@ -190,6 +190,35 @@ def test_strided_batches_and_stft_gather(cf, oracle_mod):
     cf.fft_destroy_setup(s)
 
 
+@pytest.mark.parametrize("N,hop,frames", [(2048, 512, 37), (2048, 2048, 5), (512, 96, 19), (512, 130, 9), (128, 32, 18),
+                                          (32, 6, 41), (8192, 1024, 6), (32768, 4096, 3), (1024, 256, 1)])
+def test_stft_forward_window_and_layouts(cf, oracle_mod, N, hop, frames):
+    """fft_stft_forward == a loop of single transforms over the (windowed) overlapping frames: ordered and
+    unordered, ragged last CTA group, hops that are not multiples of 4 floats (no 128-bit gather)."""
+    o = oracle_mod
+    channels = 3
+    samples = (frames - 1) * hop + N + 6
+    rng = np.random.default_rng(N + hop)
+    sig = rng.uniform(-1, 1, (channels, samples)).astype(np.float32)
+    win = (0.5 - 0.5 * np.cos(2 * np.pi * (np.arange(N) + 0.5) / N)).astype(np.float32)
+    W = o.simd_width(N, False, True)
+    s = cf.fft_new_setup(N, cf.FFT_REAL)
+    d, dw = dev(sig), dev(win)
+    fr = np.stack([[sig[c, f * hop:f * hop + N] for f in range(frames)] for c in range(channels)]).reshape(-1, N)
+    for ordered in (True, False):
+        for w in (None, dw):
+            out = torch.full((channels, frames, N), float("nan"), device="cuda")
+            n0 = cf.launch_count()
+            cf.fft_stft_forward(s, d, out, channels, frames, samples, hop, frames * N, N, w, ordered)
+            torch.cuda.synchronize()
+            assert cf.launch_count() - n0 == 1
+            want = o.np_transform((fr * win if w is not None else fr).astype(np.float32), N, False, W, False, ordered)
+            assert o.rel_l2(host(out).reshape(-1, N), want) < o.parity_tol(N), (ordered, w is not None)
+    with pytest.raises(cf.FFTError):
+        cf.fft_stft_forward(s, d, out, channels, frames, samples, N + 2, frames * N, N, dw, True)  # window with hop > N
+    cf.fft_destroy_setup(s)
+
+
 def test_convolve_and_accumulate(cf, oracle_mod, ref_lib):
     o = oracle_mod
     rng = np.random.default_rng(5)
