@@ -448,6 +448,111 @@ class Huge(BatchedFFT):
         return 16 * N / per / 1e9, 1, f"one C2C N=2^{n} transform (plan setup excluded), 1 thread: the reference is single-threaded per transform", per * 1e3
 
 
+class Single1024(BatchedFFT):
+    """BASELINE configs[0]: ONE real FFT N=1024, forward + inverse round trip through the drop-in calls (the
+    reference's own bench loop, bench/bench.cpp:82-110).  A latency case: the line's value is still GB/s, the
+    numbers that matter are in config.latency_us (sync call, stream-ordered, CUDA-graph replay)."""
+
+    scaling = "weak"
+
+    def __init__(self):
+        BatchedFFT.__init__(self, "single1024", 1024, False, 1, True, "single real FFT N=1024 forward+inverse round trip fp32 (BASELINE configs[0])")
+        self.bytes_step = 2 * 8 * self.N
+        self.flops_step = 2 * 2.5 * self.N * math.log2(self.N)
+        self.kernel = "cfb::fft_kernel<9,16,R2C,0> + cfb::fft_kernel<9,16,C2R,0>"
+        self.latency = {}
+
+    def config(self):
+        c = BatchedFFT.config(self)
+        c["l2_policy"] = "latency case: 4 KiB buffers, cache-resident by construction (as in the reference's bench loop)"
+        c["latency_us"] = self.latency
+        return c
+
+    def setup(self, cf, torch, rank, world):
+        self.cf, self.torch = cf, torch
+        self.plan = cf.fft_new_setup(self.N, cf.FFT_REAL, True)
+        i = torch.arange(self.N, device="cuda", dtype=torch.float32)
+        self.x = torch.sin(3.14 * (100.0 / 48000.0) * i).reshape(1, self.N)  # bench/bench.cpp:82-85
+        self.y = torch.empty_like(self.x)
+        self.z = torch.empty_like(self.x)
+        self.step(None)
+        torch.cuda.synchronize()
+        # (1) the drop-in calls: synchronous on return, like the reference's
+        t0 = time.perf_counter()
+        for _ in range(200):
+            cf.fft_transform(self.plan, self.x, self.y, None, cf.FFT_FORWARD)
+            cf.fft_transform(self.plan, self.y, self.z, None, cf.FFT_BACKWARD)
+        self.latency["drop_in_sync_calls"] = (time.perf_counter() - t0) / 200 * 1e6
+        # (2) CUDA-graph replay of 100 round trips
+        side = torch.cuda.Stream()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side):
+                for _ in range(100):
+                    self.step(side)
+            g.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(side)
+            for _ in range(10):
+                g.replay()
+            e1.record(side)
+            torch.cuda.synchronize()
+        self.latency["cuda_graph_replay"] = e0.elapsed_time(e1) / 1000 * 1e3
+        self.graph = g
+
+    def step(self, stream):
+        cf = self.cf
+        cf.fft_transform_batched(self.plan, self.x, self.y, 1, self.N, self.N, cf.FFT_FORWARD, True, stream)
+        cf.fft_transform_batched(self.plan, self.y, self.z, 1, self.N, self.N, cf.FFT_BACKWARD, True, stream)
+
+    def parity(self):
+        from oracle import oracle as o
+
+        x = self.x.cpu().numpy()
+        f = o.np_transform(x, self.N, False, 8, False, True)
+        return {"rel_l2_vs_oracle": max(o.rel_l2(self.y.cpu().numpy(), f), o.rel_l2(self.z.cpu().numpy() / self.N, x)),
+                "tolerance": o.parity_tol(self.N), "transforms": 2}
+
+    def e2e(self, steps, barrier, reduce_max):
+        cf = self.cf
+        hin, hmid, hout = cf.aligned_array(self.N), cf.aligned_array(self.N), cf.aligned_array(self.N)
+        hin[:] = self.x.cpu().numpy()[0]
+        n = 200
+        def call():
+            cf.fft_transform(self.plan, hin, hmid, None, cf.FFT_FORWARD)
+            cf.fft_transform(self.plan, hmid, hout, None, cf.FFT_BACKWARD)
+        call()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            call()
+        dt = (time.perf_counter() - t0) / n
+        self.latency["drop_in_host_buffers"] = dt * 1e6
+        ok = bool(np.allclose(hout / self.N, hin, atol=1e-5))
+        for h in (hin, hmid, hout):
+            cf.aligned_free(h.ctypes.data)
+        return {"seconds": dt, "h2d_bytes_per_step": 2 * 4 * self.N, "d2h_bytes_per_step": 2 * 4 * self.N, "matches_device_path": ok,
+                "path": "fft_transform x2 on aligned_malloc (pinned, device-mapped) host buffers: zero-copy kernel, one sync per call"}
+
+    def cpu(self, seconds_target, steps=1, warmup=0):
+        from oracle import oracle as o
+
+        ref = o.load_ref()
+        xin = o.aligned_copy(np.sin(3.14 * (100.0 / 48000.0) * np.arange(self.N)).astype(np.float32))
+        out, back = o.aligned_empty(self.N), o.aligned_empty(self.N)
+        reps = 20000
+        times = []
+        for it in range(warmup + max(1, steps)):
+            t = 0.0
+            for _ in range(4):
+                t += ref.transform_timed(xin, out, self.N, False, False, True, reps, 0, 0, 1)
+                t += ref.transform_timed(out, back, self.N, False, True, True, reps, 0, 0, 1)
+            times.append(t / 4)
+        per = float(np.mean(times[warmup:] or times)) / reps  # one forward + one backward
+        self.latency["reference_cpu_1_thread"] = per * 1e6
+        return self.bytes_step / per / 1e9, 1, f"{reps} forward + {reps} backward transforms of the same 4 KiB buffer per step, 1 thread (reference bench loop)", per * reps * 1e3
+
+
 WORKLOADS = {
     "c2c4096": lambda: BatchedFFT("c2c4096", 4096, True, 65536, True, "batched C2C N=4096 x 65536 fp32, ordered, forward (BASELINE configs[1])"),
     "c2c4096_unordered": lambda: BatchedFFT("c2c4096_unordered", 4096, True, 65536, False, "batched C2C N=4096 x 65536 fp32, unordered (reference W=8 layout), forward (BASELINE configs[1])"),
@@ -456,6 +561,7 @@ WORKLOADS = {
     "c2c16384": lambda: BatchedFFT("c2c16384", 16384, True, 16384, True, "batched C2C N=16384 x 16384 fp32, ordered, forward"),
     "r2c2048": lambda: BatchedFFT("r2c2048", 2048, False, 524288, True, "batched R2C N=2048 x 524288 fp32, ordered, forward"),
     "r2c8192": lambda: BatchedFFT("r2c8192", 8192, False, 131072, False, "batched R2C N=8192 x 131072 fp32, unordered, forward"),
+    "single1024": Single1024,
     "stft": STFT,
     "reverb": Reverb,
     "huge": Huge,
@@ -471,6 +577,7 @@ def main():
     ap.add_argument("--workload", default="c2c4096", choices=sorted(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--tune", action="append", default=[], metavar="KEY=VALUE", help="fft_b200_set_tuning hook (sweeps only)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]()
     rank = int(os.environ.get("RANK", "0"))
@@ -520,6 +627,9 @@ def main():
     reduce_max = lambda v: reduce(v, dist.ReduceOp.MAX)
     reduce_sum = lambda v: reduce(v, dist.ReduceOp.SUM)
 
+    for kv in args.tune:
+        k, v = kv.split("=")
+        cf.set_tuning(k, int(v, 0))
     wl.setup(cf, torch, rank, world)
     stream = torch.cuda.current_stream()
     for _ in range(args.warmup):
@@ -581,6 +691,8 @@ def main():
                              "kernel": wl.kernel, "algorithmic_bytes_per_launch": wl.bytes_step},
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(),
                 "parity": parity}
+        if args.tune:
+            line["config"]["tuning"] = args.tune
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -59,6 +59,7 @@ def lib() -> C.CDLL:
         "fft_partitioned_convolve_step": (i, [vp, vp, ll, vp, ll, vp, ll, vp, ll, i, i, i, f, vp]),
         "fft_dist_phase": (i, [vp, i, i, i, vp, vp, i, vp]),
         "fft_large_factors": (i, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "fft_b200_set_tuning": (i, [C.c_char_p, i]),
         "fft_b200_last_error": (C.c_char_p, []),
         "fft_b200_clear_error": (None, []),
         "fft_b200_launch_count": (C.c_ulonglong, []),
@@ -76,6 +77,6 @@ EXPORTED = (
     "fft_bytes_required", "fft_new_setup", "fft_new_setup_preallocated", "fft_destroy_setup",
     "fft_simd_width_bytes", "fft_transform", "fft_transform_unordered", "fft_convolve_unordered",
     "fft_accumulate", "aligned_malloc", "aligned_free", "fft_transform_batched", "fft_transform_strided", "fft_stft_forward",
-    "fft_convolve_unordered_batched", "fft_accumulate_batched", "fft_partitioned_convolve_step", "fft_dist_phase", "fft_large_factors", "fft_b200_last_error", "fft_b200_clear_error",
+    "fft_convolve_unordered_batched", "fft_accumulate_batched", "fft_partitioned_convolve_step", "fft_dist_phase", "fft_large_factors", "fft_b200_set_tuning", "fft_b200_last_error", "fft_b200_clear_error",
     "fft_b200_launch_count", "fft_b200_device_available",
 )

@@ -171,6 +171,11 @@ def fft_partitioned_convolve_step(setup: int, windows, window_stride: int, ir, i
                                                channels, partitions, block_index, scaling, _stream(stream)))
 
 
+def set_tuning(key: str, value: int) -> None:
+    """Benchmark/sweep hook (fft_b200_set_tuning)."""
+    _check(lib().fft_b200_set_tuning(key.encode(), int(value)))
+
+
 def fft_large_factors(setup: int) -> tuple[int, int, int]:
     """(l1, l2, l3): log2 of the pass lengths of a multi-pass plan."""
     a, b, c = C.c_int(), C.c_int(), C.c_int()

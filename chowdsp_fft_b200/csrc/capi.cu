@@ -78,9 +78,9 @@ struct Tables
 std::mutex g_tables_mutex;
 std::map<uint64_t, Tables> g_tables;
 
-int get_tables (int device, int logM, bool real, Tables& out)
+int get_tables (int device, int logM, bool real, Tables& out, int radix = 16)
 {
-    const uint64_t key = ((uint64_t) device << 32) | ((uint64_t) logM << 1) | (real ? 1u : 0u);
+    const uint64_t key = ((uint64_t) device << 32) | ((uint64_t) (radix == 32 ? 1 : 0) << 16) | ((uint64_t) logM << 1) | (real ? 1u : 0u);
     std::lock_guard<std::mutex> lock (g_tables_mutex);
     auto it = g_tables.find (key);
     if (it != g_tables.end())
@@ -89,11 +89,11 @@ int get_tables (int device, int logM, bool real, Tables& out)
         return 0;
     }
     Tables t;
-    const int len = stage_twiddle_len (logM);
+    const int len = stage_twiddle_len (logM, radix);
     if (len < 0)
         return fail (chowdsp::fft::FFT_B200_EINVAL, "no kernel for complex length 2^%d", logM);
     std::vector<float2> host ((size_t) len + 1);
-    fill_stage_twiddles_rt (logM, host.data());
+    fill_stage_twiddles_rt (logM, radix, host.data());
     CFB_CUDA (cudaMalloc (&t.tw, sizeof (float2) * ((size_t) len + 1)));
     CFB_CUDA (cudaMemcpy (t.tw, host.data(), sizeof (float2) * ((size_t) len + 1), cudaMemcpyHostToDevice));
     if (real)
@@ -157,8 +157,8 @@ struct Plan
     int logW; // unordered layout: 3 = 8-lane, 2 = 4-lane
     int owns_memory;
     int home_device;
-    Tables tables[kMaxDevices]; // filled lazily per device (guarded by g_tables_mutex through get_tables)
-    bool have[kMaxDevices];
+    Tables tables[2][kMaxDevices]; // [radix 16 | 32], filled lazily per device (guarded by g_tables_mutex through get_tables)
+    bool have[2][kMaxDevices];
 };
 
 int ilog2i (int v)
@@ -192,7 +192,12 @@ Plan* as_plan (void* setup)
     return p;
 }
 
-int plan_tables (Plan* p, Tables& t)
+// Points per thread of the single-kernel transform for complex length 2^logM: 32 where that geometry exists and
+// is enabled (tuning hook "radix32_mask", bit logM), else 16.
+unsigned g_radix32_mask = 0;
+int radix_for (int logM) { return (has_radix32 (logM) && ((g_radix32_mask >> logM) & 1u) != 0) ? 32 : 16; }
+
+int plan_tables (Plan* p, Tables& t, int radix = 16)
 {
     int dev = 0;
     CFB_CUDA (cudaGetDevice (&dev));
@@ -203,17 +208,18 @@ int plan_tables (Plan* p, Tables& t)
         t = Tables {};
         return 0; // multi-pass plan: tables are fetched per pass (enqueue_large)
     }
-    if (! p->have[dev])
+    const int ri = radix == 32 ? 1 : 0;
+    if (! p->have[ri][dev])
     {
         Tables nt;
-        const int rc = get_tables (dev, p->logM, ! p->is_complex, nt);
+        const int rc = get_tables (dev, p->logM, ! p->is_complex, nt, radix);
         if (rc != 0)
             return rc;
         std::lock_guard<std::mutex> lock (g_tables_mutex);
-        p->tables[dev] = nt;
-        p->have[dev] = true;
+        p->tables[ri][dev] = nt;
+        p->have[ri][dev] = true;
     }
-    t = p->tables[dev];
+    t = p->tables[ri][dev];
     return 0;
 }
 
@@ -309,6 +315,8 @@ struct Staging
 };
 thread_local Staging t_staging;
 
+bool g_stft_union = false; // tuning hook "stft_union"
+
 constexpr size_t kZeroCopyBytes = 256 * 1024;     // pinned buffers up to this size are used in place
 constexpr size_t kChunkBytes = 32ull * 1024 * 1024; // host staging granularity per lane
 
@@ -387,7 +395,7 @@ int enqueue_large (Plan* p, const float* in, float* out, int batch, long long in
                 pass[i].args.out = i == np - 1 ? dst : s1;
                 pass[i].args.out_bstride = i == np - 1 ? dst_bs : npts;
                 pass[i].args.batch = nb;
-                const cudaError_t le = launch_tile (pass[i].logL, dir, pass[i].load_j_fast, pass[i].args, stream);
+                const cudaError_t le = launch_tile (pass[i].logL, pass[i].C, dir, pass[i].load_j_fast, pass[i].args, stream);
                 if (le != cudaSuccess)
                     return fail_cuda (le, "tile pass launch");
             }
@@ -450,8 +458,8 @@ int enqueue_large (Plan* p, const float* in, float* out, int batch, long long in
 
 int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inner, long long in_outer, long long in_inner, long long out_outer, long long out_inner, int direction, bool ordered, cudaStream_t stream, const float* window = nullptr)
 {
-    if (window != nullptr && (p->logM > kMaxLogM || p->is_complex || direction != chowdsp::fft::FFT_FORWARD || in_inner <= 0 || in_inner > p->N))
-        return fail (chowdsp::fft::FFT_B200_EINVAL, "windowed transforms need a REAL single-kernel plan, FFT_FORWARD and 0 < hop <= N");
+    if (window != nullptr && (p->logM > kMaxLogM || p->is_complex || direction != chowdsp::fft::FFT_FORWARD))
+        return fail (chowdsp::fft::FFT_B200_EINVAL, "windowed transforms need a REAL single-kernel plan and FFT_FORWARD");
     if (p->logM > kMaxLogM)
     {
         if ((in_inner & 1) != 0 || (out_inner & 1) != 0 || (in_outer & 1) != 0 || (out_outer & 1) != 0)
@@ -465,7 +473,8 @@ int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inne
         return 0;
     }
     Tables t;
-    const int rc = plan_tables (p, t);
+    const int radix = radix_for (p->logM);
+    const int rc = plan_tables (p, t, radix);
     if (rc != 0)
         return rc;
     FftArgs a {};
@@ -479,21 +488,24 @@ int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inne
     a.batch = outer * inner;
     a.tw = t.tw;
     a.rtw = t.rtw;
-    // overlapping real frames (STFT analysis): one CTA gathers the union of its frames once
+    // windowed real frames (STFT analysis) go through the frame-gather kernel; plain overlapping frames only when
+    // the union-staging variant is selected (it is slower on B200, see stft_kernel)
     const bool fwd_real = ! p->is_complex && direction == chowdsp::fft::FFT_FORWARD;
-    if (fwd_real && in_inner > 0 && in_inner <= p->N && (in_inner & 1) == 0 && (in_outer & 1) == 0
-        && (window != nullptr || (in_inner < p->N && inner > 1 && transforms_per_cta (p->logM) > 1)))
+    const bool union_ok = in_inner > 0 && in_inner <= p->N;
+    if (fwd_real && (in_inner & 1) == 0 && (in_outer & 1) == 0
+        && (window != nullptr || (g_stft_union && union_ok && in_inner < p->N && inner > 1 && transforms_per_cta (p->logM, radix) > 1)))
     {
         a.window = window;
+        a.union_gather = (g_stft_union && union_ok) ? 1 : 0;
         a.vec4 = ((reinterpret_cast<uintptr_t> (in) & 15) == 0 && (in_inner & 3) == 0 && (in_outer & 3) == 0) ? 1 : 0;
-        const cudaError_t es = launch_stft (p->logM, ordered ? 0 : p->logW, a, stream);
+        const cudaError_t es = launch_stft (p->logM, ordered ? 0 : p->logW, radix, a, stream);
         if (es != cudaSuccess)
             return fail_cuda (es, "stft kernel launch");
         return 0;
     }
     if (window != nullptr)
         return fail (chowdsp::fft::FFT_B200_EINVAL, "windowed transforms need even hop and channel strides");
-    const cudaError_t e = launch_fft (p->logM, kind_of (p, direction), ordered ? 0 : p->logW, a, stream);
+    const cudaError_t e = launch_fft (p->logM, kind_of (p, direction), ordered ? 0 : p->logW, radix, a, stream);
     if (e != cudaSuccess)
         return fail_cuda (e, "fft kernel launch");
     return 0;
@@ -948,7 +960,7 @@ CFB_API int fft_dist_phase (void* setup, int phase, int rank, int world, const f
     tp.args.tw_lobits = bt.lobits;
     tp.args.in = reinterpret_cast<const float2*> (in);
     tp.args.out = reinterpret_cast<float2*> (out);
-    const cudaError_t e = launch_tile (tp.logL, direction == FFT_FORWARD ? -1 : +1, tp.load_j_fast, tp.args, static_cast<cudaStream_t> (stream));
+    const cudaError_t e = launch_tile (tp.logL, tp.C, direction == FFT_FORWARD ? -1 : +1, tp.load_j_fast, tp.args, static_cast<cudaStream_t> (stream));
     return e == cudaSuccess ? 0 : fail_cuda (e, "distributed phase launch");
 }
 
@@ -960,6 +972,31 @@ CFB_API int fft_accumulate_batched (void* setup, const float* a, const float* b,
     if (n < 0 || n % 8 != 0)
         return fail (FFT_B200_EINVAL, "fft_accumulate_batched: n must be a non-negative multiple of 8");
     return elementwise_any (p, false, a, b, ab, 1, n, n, n, n, 0.f, static_cast<cudaStream_t> (stream), false);
+}
+
+CFB_API int fft_b200_set_tuning (const char* key, int value)
+{
+    if (key != nullptr && std::strcmp (key, "tile_c") == 0 && (value == 0 || value == 8 || value == 16))
+    {
+        tile_c_override() = value;
+        return 0;
+    }
+    if (key != nullptr && std::strcmp (key, "tile_c_jfast") == 0 && (value == 0 || value == 8 || value == 16))
+    {
+        tile_c_jfast_override() = value;
+        return 0;
+    }
+    if (key != nullptr && std::strcmp (key, "radix32_mask") == 0)
+    {
+        g_radix32_mask = (unsigned) value;
+        return 0;
+    }
+    if (key != nullptr && std::strcmp (key, "stft_union") == 0)
+    {
+        g_stft_union = value != 0;
+        return 0;
+    }
+    return fail (FFT_B200_EINVAL, "fft_b200_set_tuning: unknown key or value");
 }
 
 CFB_API const char* fft_b200_last_error (void) { return t_error; }

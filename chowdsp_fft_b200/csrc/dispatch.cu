@@ -15,12 +15,12 @@ void count_launch() { g_launches.fetch_add (1, std::memory_order_relaxed); }
 
 #define CFB_FOR_SIZES(X) X (4) X (5) X (6) X (7) X (8) X (9) X (10) X (11) X (12) X (13) X (14)
 
-cudaError_t launch_fft (int logM, int kind, int logW, const FftArgs& args, cudaStream_t stream)
+cudaError_t launch_fft (int logM, int kind, int logW, int radix, const FftArgs& args, cudaStream_t stream)
 {
     switch (logM)
     {
 #define X(n) \
-    case n: return launch_fft_##n (kind, logW, args, stream);
+    case n: return launch_fft_##n (kind, logW, radix, args, stream);
         CFB_FOR_SIZES (X)
 #undef X
         default: return cudaErrorInvalidValue;
@@ -37,45 +37,56 @@ cudaError_t launch_pconv (int logM, int logW, const PConvArgs& args, cudaStream_
         default: return cudaErrorInvalidValue;
     }
 }
-cudaError_t launch_stft (int logM, int logW, const FftArgs& args, cudaStream_t stream)
+bool has_radix32 (int logM)
 {
     switch (logM)
     {
 #define X(n) \
-    case n: return launch_stft_##n (logW, args, stream);
+    case n: return has_radix32_##n() != 0;
+        CFB_FOR_SIZES (X)
+#undef X
+        default: return false;
+    }
+}
+cudaError_t launch_stft (int logM, int logW, int radix, const FftArgs& args, cudaStream_t stream)
+{
+    switch (logM)
+    {
+#define X(n) \
+    case n: return launch_stft_##n (logW, radix, args, stream);
         CFB_FOR_SIZES (X)
 #undef X
         default: return cudaErrorInvalidValue;
     }
 }
-int transforms_per_cta (int logM)
+int transforms_per_cta (int logM, int radix)
 {
     switch (logM)
     {
 #define X(n) \
-    case n: return transforms_per_cta_##n();
+    case n: return transforms_per_cta_##n (radix);
         CFB_FOR_SIZES (X)
 #undef X
         default: return 1;
     }
 }
-int stage_twiddle_len (int logM)
+int stage_twiddle_len (int logM, int radix)
 {
     switch (logM)
     {
 #define X(n) \
-    case n: return stage_twiddle_len_##n();
+    case n: return stage_twiddle_len_##n (radix);
         CFB_FOR_SIZES (X)
 #undef X
         default: return -1;
     }
 }
-void fill_stage_twiddles_rt (int logM, float2* tw)
+void fill_stage_twiddles_rt (int logM, int radix, float2* tw)
 {
     switch (logM)
     {
 #define X(n) \
-    case n: fill_stage_twiddles_##n (tw); return;
+    case n: fill_stage_twiddles_##n (radix, tw); return;
         CFB_FOR_SIZES (X)
 #undef X
         default: return;

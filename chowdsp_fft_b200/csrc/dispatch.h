@@ -10,24 +10,26 @@ namespace cfb
 {
 constexpr int kMinLogM = 4;  // 16 complex points per CTA-resident transform
 constexpr int kMaxLogM = 14; // 16384 complex points: the largest single-kernel transform
-constexpr int kRadix = 16;   // complex points per thread
+// complex points per thread: 16 everywhere, plus 32 for the sizes where it saves a shared-memory exchange
+// (2^9, 2^10, 2^13, 2^14; has_radix32)
 
 // One launch of the single-kernel transform (complex length 2^logM per transform).
 // logW: 0 = ordered output/input, 2 / 3 = the reference's 4- / 8-lane unordered layout
-cudaError_t launch_fft (int logM, int kind, int logW, const FftArgs& args, cudaStream_t stream);
+cudaError_t launch_fft (int logM, int kind, int logW, int radix, const FftArgs& args, cudaStream_t stream);
+bool has_radix32 (int logM);
 // frame-gather R2C (STFT analysis): transform (o, i) reads in + o in_outer + i in_inner with 0 < in_inner <= N,
 // optional window; one CTA gathers the union of its frames once (stft_kernel)
-cudaError_t launch_stft (int logM, int logW, const FftArgs& args, cudaStream_t stream);
-int transforms_per_cta (int logM);
+cudaError_t launch_stft (int logM, int logW, int radix, const FftArgs& args, cudaStream_t stream);
+int transforms_per_cta (int logM, int radix);
 // number of float2 entries of the stage twiddle table for 2^logM, and the fill routine (fp64 -> fp32)
-int stage_twiddle_len (int logM);
-void fill_stage_twiddles_rt (int logM, float2* tw);
+int stage_twiddle_len (int logM, int radix);
+void fill_stage_twiddles_rt (int logM, int radix, float2* tw);
 
 // fused partitioned-convolution block step for a REAL plan of 2^(logM+1) samples (one CTA per channel)
 cudaError_t launch_pconv (int logM, int logW, const PConvArgs& args, cudaStream_t stream);
 
 // multi-pass (large transform) kernels, large_inst.cu
-cudaError_t launch_tile (int logL, int dir, bool load_j_fast, const TileArgs& args, cudaStream_t stream);
+cudaError_t launch_tile (int logL, int C, int dir, bool load_j_fast, const TileArgs& args, cudaStream_t stream);
 cudaError_t launch_real_pass (int dir, const RealPassArgs& args, int batch, cudaStream_t stream);
 cudaError_t launch_complex_reorder (const float* in, float* out, long long in_bstride, long long out_bstride, int batch, int logN, int logW, bool to_unordered, cudaStream_t stream);
 
@@ -40,12 +42,13 @@ void count_launch();
 
 // per-size entry points, one translation unit each (fft_inst.cu compiled with -DCFB_LOGM=n)
 #define CFB_DECL_INST(n)                                                                       \
-    cudaError_t launch_fft_##n (int kind, int logW, const FftArgs& args, cudaStream_t stream);      \
+    cudaError_t launch_fft_##n (int kind, int logW, int radix, const FftArgs& args, cudaStream_t stream); \
     cudaError_t launch_pconv_##n (int logW, const PConvArgs& args, cudaStream_t stream);           \
-    cudaError_t launch_stft_##n (int logW, FftArgs args, cudaStream_t stream);                     \
-    int transforms_per_cta_##n();                                                              \
-    int stage_twiddle_len_##n();                                                               \
-    void fill_stage_twiddles_##n (float2* tw);
+    cudaError_t launch_stft_##n (int logW, int radix, FftArgs args, cudaStream_t stream);          \
+    int transforms_per_cta_##n (int radix);                                                    \
+    int has_radix32_##n();                                                                     \
+    int stage_twiddle_len_##n (int radix);                                                     \
+    void fill_stage_twiddles_##n (int radix, float2* tw);
 CFB_DECL_INST (4)
 CFB_DECL_INST (5)
 CFB_DECL_INST (6)

@@ -5,15 +5,22 @@
 #endif
 #include "dispatch.h"
 
+// sizes that also get the 32-points-per-thread geometry (one shared-memory exchange fewer than with 16)
+#if CFB_LOGM == 9 || CFB_LOGM == 10 || CFB_LOGM == 13 || CFB_LOGM == 14
+#define CFB_HAS_R32 1
+#else
+#define CFB_HAS_R32 0
+#endif
+
 namespace cfb
 {
 namespace
 {
-template <int KIND, int LOGW>
+template <int R, int KIND, int LOGW>
 cudaError_t launch_one (const FftArgs& a, cudaStream_t stream)
 {
-    using L = Launch<CFB_LOGM, kRadix>;
-    auto kernel = fft_kernel<CFB_LOGM, kRadix, KIND, LOGW>;
+    using L = Launch<CFB_LOGM, R>;
+    auto kernel = fft_kernel<CFB_LOGM, R, KIND, LOGW>;
     constexpr int smem_bytes = LOGW != 0 ? L::SMEM_BYTES_UNORD : L::SMEM_BYTES;
     if (smem_bytes > 48 * 1024)
     {
@@ -35,26 +42,39 @@ cudaError_t launch_one (const FftArgs& a, cudaStream_t stream)
 
 // logW: 0 = ordered, 2 = 4-lane unordered layout, 3 = 8-lane unordered layout.  The 8-lane layout needs
 // N % 64 == 0 (complex) / N % 128 == 0 (real), i.e. complex length >= 64 here.
-cudaError_t CFB_CAT (launch_fft_, CFB_LOGM) (int kind, int logW, const FftArgs& a, cudaStream_t stream)
+namespace
+{
+template <int R>
+cudaError_t launch_fft_r (int kind, int logW, const FftArgs& a, cudaStream_t stream)
 {
     switch (kind * 4 + logW)
     {
-        case 0: return launch_one<C2C_FWD, 0> (a, stream);
-        case 2: return launch_one<C2C_FWD, 2> (a, stream);
-        case 4: return launch_one<C2C_BWD, 0> (a, stream);
-        case 6: return launch_one<C2C_BWD, 2> (a, stream);
-        case 8: return launch_one<R2C, 0> (a, stream);
-        case 10: return launch_one<R2C, 2> (a, stream);
-        case 12: return launch_one<C2R, 0> (a, stream);
-        case 14: return launch_one<C2R, 2> (a, stream);
+        case 0: return launch_one<R, C2C_FWD, 0> (a, stream);
+        case 2: return launch_one<R, C2C_FWD, 2> (a, stream);
+        case 4: return launch_one<R, C2C_BWD, 0> (a, stream);
+        case 6: return launch_one<R, C2C_BWD, 2> (a, stream);
+        case 8: return launch_one<R, R2C, 0> (a, stream);
+        case 10: return launch_one<R, R2C, 2> (a, stream);
+        case 12: return launch_one<R, C2R, 0> (a, stream);
+        case 14: return launch_one<R, C2R, 2> (a, stream);
 #if CFB_LOGM >= 6
-        case 3: return launch_one<C2C_FWD, 3> (a, stream);
-        case 7: return launch_one<C2C_BWD, 3> (a, stream);
-        case 11: return launch_one<R2C, 3> (a, stream);
-        case 15: return launch_one<C2R, 3> (a, stream);
+        case 3: return launch_one<R, C2C_FWD, 3> (a, stream);
+        case 7: return launch_one<R, C2C_BWD, 3> (a, stream);
+        case 11: return launch_one<R, R2C, 3> (a, stream);
+        case 15: return launch_one<R, C2R, 3> (a, stream);
 #endif
         default: return cudaErrorInvalidValue;
     }
+}
+} // namespace
+
+cudaError_t CFB_CAT (launch_fft_, CFB_LOGM) (int kind, int logW, int radix, const FftArgs& a, cudaStream_t stream)
+{
+#if CFB_HAS_R32
+    if (radix == 32)
+        return launch_fft_r<32> (kind, logW, a, stream);
+#endif
+    return radix == 16 ? launch_fft_r<16> (kind, logW, a, stream) : cudaErrorInvalidValue;
 }
 
 namespace
@@ -62,7 +82,7 @@ namespace
 template <int LOGW>
 cudaError_t launch_pconv_one (const PConvArgs& a, cudaStream_t stream)
 {
-    using G = Geo<CFB_LOGM, kRadix>;
+    using G = Geo<CFB_LOGM, 16>;
     auto kernel = pconv_kernel<CFB_LOGM, LOGW>;
     constexpr int smem_bytes = G::SMEM_F2_UNORD * 8;
     if (smem_bytes > 48 * 1024)
@@ -92,11 +112,11 @@ cudaError_t CFB_CAT (launch_pconv_, CFB_LOGM) (int logW, const PConvArgs& a, cud
 
 namespace
 {
-template <int LOGW>
+template <int R, int LOGW, bool UNION>
 cudaError_t launch_stft_one (const FftArgs& a, cudaStream_t stream)
 {
-    using L = Launch<CFB_LOGM, kRadix>;
-    auto kernel = stft_kernel<CFB_LOGM, kRadix, LOGW>;
+    using L = Launch<CFB_LOGM, R>;
+    auto kernel = stft_kernel<CFB_LOGM, R, LOGW, UNION>;
     constexpr int smem_bytes = LOGW != 0 ? L::SMEM_BYTES_UNORD : L::SMEM_BYTES;
     static_assert (smem_bytes >= L::PER_CTA * (8 << CFB_LOGM), "the union image must fit in the exchange buffers");
     if (smem_bytes > 48 * 1024)
@@ -112,24 +132,60 @@ cudaError_t launch_stft_one (const FftArgs& a, cudaStream_t stream)
     count_launch();
     return cudaGetLastError();
 }
-} // namespace
-
-// frame-gather R2C (STFT analysis); fills in a.groups
-cudaError_t CFB_CAT (launch_stft_, CFB_LOGM) (int logW, FftArgs a, cudaStream_t stream)
+template <int R>
+cudaError_t launch_stft_r (int logW, FftArgs a, cudaStream_t stream)
 {
-    a.groups = (a.inner + Launch<CFB_LOGM, kRadix>::PER_CTA - 1) / Launch<CFB_LOGM, kRadix>::PER_CTA;
-    switch (logW)
+    a.groups = (a.inner + Launch<CFB_LOGM, R>::PER_CTA - 1) / Launch<CFB_LOGM, R>::PER_CTA;
+    switch (logW * 2 + (a.union_gather ? 1 : 0))
     {
-        case 0: return launch_stft_one<0> (a, stream);
-        case 2: return launch_stft_one<2> (a, stream);
+        case 0: return launch_stft_one<R, 0, false> (a, stream);
+        case 1: return launch_stft_one<R, 0, true> (a, stream);
+        case 4: return launch_stft_one<R, 2, false> (a, stream);
+        case 5: return launch_stft_one<R, 2, true> (a, stream);
 #if CFB_LOGM >= 6
-        case 3: return launch_stft_one<3> (a, stream);
+        case 6: return launch_stft_one<R, 3, false> (a, stream);
+        case 7: return launch_stft_one<R, 3, true> (a, stream);
 #endif
         default: return cudaErrorInvalidValue;
     }
 }
-int CFB_CAT (transforms_per_cta_, CFB_LOGM)() { return Launch<CFB_LOGM, kRadix>::PER_CTA; }
+} // namespace
 
-int CFB_CAT (stage_twiddle_len_, CFB_LOGM)() { return Geo<CFB_LOGM, kRadix>::TW_LEN; }
-void CFB_CAT (fill_stage_twiddles_, CFB_LOGM) (float2* tw) { fill_stage_twiddles<CFB_LOGM, kRadix> (tw); }
+// frame-gather R2C (STFT analysis); fills in a.groups
+cudaError_t CFB_CAT (launch_stft_, CFB_LOGM) (int logW, int radix, FftArgs a, cudaStream_t stream)
+{
+#if CFB_HAS_R32
+    if (radix == 32)
+        return launch_stft_r<32> (logW, a, stream);
+#endif
+    return radix == 16 ? launch_stft_r<16> (logW, a, stream) : cudaErrorInvalidValue;
+}
+int CFB_CAT (has_radix32_, CFB_LOGM)() { return CFB_HAS_R32; }
+int CFB_CAT (transforms_per_cta_, CFB_LOGM) (int radix)
+{
+#if CFB_HAS_R32
+    if (radix == 32)
+        return Launch<CFB_LOGM, 32>::PER_CTA;
+#endif
+    return Launch<CFB_LOGM, 16>::PER_CTA;
+}
+int CFB_CAT (stage_twiddle_len_, CFB_LOGM) (int radix)
+{
+#if CFB_HAS_R32
+    if (radix == 32)
+        return Geo<CFB_LOGM, 32>::TW_LEN;
+#endif
+    return Geo<CFB_LOGM, 16>::TW_LEN;
+}
+void CFB_CAT (fill_stage_twiddles_, CFB_LOGM) (int radix, float2* tw)
+{
+#if CFB_HAS_R32
+    if (radix == 32)
+    {
+        fill_stage_twiddles<CFB_LOGM, 32> (tw);
+        return;
+    }
+#endif
+    fill_stage_twiddles<CFB_LOGM, 16> (tw);
+}
 } // namespace cfb

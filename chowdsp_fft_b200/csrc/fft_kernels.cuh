@@ -59,6 +59,7 @@ struct FftArgs
     const float* window;
     int groups;
     int vec4;
+    int union_gather;    // stage the union of a CTA's frames through shared memory (see stft_kernel)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -77,25 +78,27 @@ struct Geo
     static constexpr int T = M / R;                      // threads per transform
     static constexpr int S = (LOGM + LOGR - 1) / LOGR;   // stages
     static constexpr int RLAST = 1 << (LOGM - (S - 1) * LOGR);
-    static constexpr int SMEM_F2 = M + (M >> 4);         // padded float2 slots per transform
+    static constexpr int SMEM_F2 = M + (M >> LOGR);      // padded float2 slots per transform (one pad slot per R)
     static constexpr int SMEM_F2_UNORD = M + (M >> 3);   // staging image of the unordered layout (W=4 pad is the larger one)
     static_assert (M >= R, "transform smaller than the per-thread radix");
     static FFT_CX int radix (int s) { return s == S - 1 ? RLAST : R; }
     static FFT_CX int ns (int s) { return ipow (R, s); } // product of the radices before stage s
     // Stage twiddle tables (stage 0 has none), all holding forward twiddles exp(-2 pi i k q / (Ns r)):
-    //   radix-16 stage : 6 rows q in {1, 2, 3, 4, 8, 12} x Ns entries; the other nine powers are one
-    //                    product of two rows each (w^q = w^(q%4) w^(q-q%4)), computed in registers
-    //   last stage r<16: (r-1) rows q = 1..r-1 x T entries (k = j only); the R/r butterflies of a thread
-    //                    differ by the constant factors W16^(u q), applied with immediates
-    static_assert (R_ == 16, "the twiddle scheme below assumes 16 points per thread");
-    static FFT_CX int tw_rows (int s) { return radix (s) == 16 ? 6 * ns (s) : (radix (s) - 1) * T; }
+    //   full-radix stage (r = R): rows q in {1, 2, 3} and {4, 8, .., R-4} x Ns entries (6 rows for R = 16, 10
+    //                    for R = 32); every other power is one product of two rows (w^q = w^(q%4) w^(q-q%4)),
+    //                    computed in registers
+    //   last stage r < R: (r-1) rows q = 1..r-1 x T entries (k = j only); the R/r butterflies of a thread
+    //                    differ by the constant factors W_R^(u q), applied with immediates
+    static_assert (R_ == 16 || R_ == 32, "the twiddle scheme below assumes 16 or 32 points per thread");
+    static constexpr int FULL_ROWS = 3 + (R_ / 4 - 1);
+    static FFT_CX int tw_rows (int s) { return radix (s) == R ? FULL_ROWS * ns (s) : (radix (s) - 1) * T; }
+    // one padding slot per R float2: stride-2^a accesses (2^a <= R) and unit-stride accesses are both conflict
+    // free, pad (a + b) = pad (a) + pad (b) whenever R | b, so every offset used below folds into an immediate
+    static FFT_CX int pad (int i) { return i + (i >> LOGR); }
     static FFT_CX int tw_off (int s) { return s <= 1 ? 0 : tw_off (s - 1) + tw_rows (s - 1); }
     static constexpr int TW_LEN = S == 1 ? 0 : tw_off (S - 1) + tw_rows (S - 1);
 };
 
-// one padding slot per 16 float2: stride-2^a accesses (a <= 4) and unit-stride accesses are both
-// conflict free, and every offset used below folds into an immediate.
-FFT_CX int pad (int i) { return i + (i >> 4); }
 
 // ---------------------------------------------------------------------------------------------
 // memory helpers (shared-memory ones are instrumented in the emulator)
@@ -204,50 +207,53 @@ FFT_HD float2 mul_mi (float2 a)
 {
     return DIR < 0 ? make_float2 (a.y, -a.x) : make_float2 (-a.y, a.x);
 }
-// a * exp(DIR * 2 pi i * NUM / 16) with compile-time constants
-template <int DIR, int NUM>
-FFT_HD float2 mul_w16 (float2 a)
+// cos (2 pi n / 32), sin (2 pi n / 32) as compile-time constants
+FFT_CX float cos32 (int n)
 {
-    constexpr float C1 = 0.923879532511286756f, S1 = 0.382683432365089772f, H = 0.707106781186547524f;
-    constexpr int n = NUM & 15;
+    n &= 31;
+    if (n > 16)
+        n = 32 - n;
+    const bool neg = n > 8;
+    if (neg)
+        n = 16 - n;
+    const float c = n == 0 ? 1.f : n == 1 ? 0.980785280403230449f : n == 2 ? 0.923879532511286756f : n == 3 ? 0.831469612302545237f
+                  : n == 4 ? 0.707106781186547524f : n == 5 ? 0.555570233019602225f : n == 6 ? 0.382683432365089772f
+                  : n == 7 ? 0.195090322016128268f : 0.f;
+    return neg ? -c : c;
+}
+FFT_CX float sin32 (int n) { return cos32 (n + 24); }
+
+// a * exp(DIR * 2 pi i * NUM / 32) with compile-time constants
+template <int DIR, int NUM>
+FFT_HD float2 mul_w32 (float2 a)
+{
+    constexpr int n = NUM & 31;
     if (n == 0)
         return a;
-    if (n == 4)
-        return mul_mi<DIR> (a);
     if (n == 8)
+        return mul_mi<DIR> (a);
+    if (n == 16)
         return make_float2 (-a.x, -a.y);
-    if (n == 12)
+    if (n == 24)
         return mul_mi<-DIR> (a);
-    // forward twiddle c - i s  with  c = cos(2 pi n/16), s = sin(2 pi n/16)
-    constexpr float c = (n == 1 || n == 15) ? C1 : (n == 2 || n == 14) ? H : (n == 3 || n == 13) ? S1
-                      : (n == 5 || n == 11) ? -S1 : (n == 6 || n == 10) ? -H : -C1;
-    constexpr float sabs = (n == 1 || n == 7 || n == 9 || n == 15) ? S1 : (n == 2 || n == 6 || n == 10 || n == 14) ? H : C1;
-    constexpr float s = n < 8 ? sabs : -sabs;
-    return cmul_dir<DIR> (a, make_float2 (c, -s));
+    return cmul_dir<DIR> (a, make_float2 (cos32 (n), -sin32 (n))); // forward twiddle c - i s
 }
+template <int DIR, int NUM>
+FFT_HD float2 mul_w16 (float2 a) { return mul_w32<DIR, 2 * NUM> (a); }
 
-// a * W16^(DIR * num): num is a loop constant after unrolling, so the switch folds away
+// a * W32^(DIR * num): num is a loop constant after unrolling, so the switch folds away
 template <int DIR>
-FFT_HD float2 mul_w16_rt (float2 a, int num)
+FFT_HD float2 mul_w32_rt (float2 a, int num)
 {
-    switch (num & 15)
+    switch (num & 31)
     {
-        case 0: return a;
-        case 1: return mul_w16<DIR, 1> (a);
-        case 2: return mul_w16<DIR, 2> (a);
-        case 3: return mul_w16<DIR, 3> (a);
-        case 4: return mul_w16<DIR, 4> (a);
-        case 5: return mul_w16<DIR, 5> (a);
-        case 6: return mul_w16<DIR, 6> (a);
-        case 7: return mul_w16<DIR, 7> (a);
-        case 8: return mul_w16<DIR, 8> (a);
-        case 9: return mul_w16<DIR, 9> (a);
-        case 10: return mul_w16<DIR, 10> (a);
-        case 11: return mul_w16<DIR, 11> (a);
-        case 12: return mul_w16<DIR, 12> (a);
-        case 13: return mul_w16<DIR, 13> (a);
-        case 14: return mul_w16<DIR, 14> (a);
-        default: return mul_w16<DIR, 15> (a);
+#define CFB_W32_CASE(n) case n: return mul_w32<DIR, n> (a);
+        CFB_W32_CASE (0) CFB_W32_CASE (1) CFB_W32_CASE (2) CFB_W32_CASE (3) CFB_W32_CASE (4) CFB_W32_CASE (5) CFB_W32_CASE (6) CFB_W32_CASE (7)
+        CFB_W32_CASE (8) CFB_W32_CASE (9) CFB_W32_CASE (10) CFB_W32_CASE (11) CFB_W32_CASE (12) CFB_W32_CASE (13) CFB_W32_CASE (14) CFB_W32_CASE (15)
+        CFB_W32_CASE (16) CFB_W32_CASE (17) CFB_W32_CASE (18) CFB_W32_CASE (19) CFB_W32_CASE (20) CFB_W32_CASE (21) CFB_W32_CASE (22) CFB_W32_CASE (23)
+        CFB_W32_CASE (24) CFB_W32_CASE (25) CFB_W32_CASE (26) CFB_W32_CASE (27) CFB_W32_CASE (28) CFB_W32_CASE (29) CFB_W32_CASE (30)
+#undef CFB_W32_CASE
+        default: return mul_w32<DIR, 31> (a);
     }
 }
 
@@ -342,6 +348,31 @@ struct RegFft<16, DIR, ST>
     }
 };
 
+template <int DIR, int ST>
+struct RegFft<32, DIR, ST>
+{
+    // 32 = 2 x 16:  X[k] = E[k] + W32^k O[k],  X[k + 16] = E[k] - W32^k O[k]
+    static FFT_HD void run (float2* v)
+    {
+        float2 e[16], o[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+        {
+            e[k] = v[(2 * k) * ST];
+            o[k] = v[(2 * k + 1) * ST];
+        }
+        RegFft<16, DIR, 1>::run (e);
+        RegFft<16, DIR, 1>::run (o);
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+        {
+            const float2 t = mul_w32_rt<DIR> (o[k], k);
+            v[k * ST] = cadd (e[k], t);
+            v[(k + 16) * ST] = csub (e[k], t);
+        }
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
 // position of a bin inside the reference's unordered layouts (pffft_zreorder,
 // /root/reference/simd/chowdsp_fft_impl_avx.cpp:1780-1839).  Returns the float offset of the real
@@ -373,7 +404,7 @@ template <class G, int DIR, int STAGE>
 FFT_HD void stage_compute (float2 (&v)[G::R], int j, const float2* __restrict__ tw)
 {
     constexpr int r = G::radix (STAGE), Ns = G::ns (STAGE), SUB = G::R / r;
-    if constexpr (STAGE > 0 && r == 16)
+    if constexpr (STAGE > 0 && r == G::R && G::R == 16)
     {
         const float2* __restrict__ t = tw + G::tw_off (STAGE) + (j & (Ns - 1));
         const float2 w1 = __ldg (t), w2 = __ldg (t + Ns), w3 = __ldg (t + 2 * Ns);
@@ -394,23 +425,38 @@ FFT_HD void stage_compute (float2 (&v)[G::R], int j, const float2* __restrict__ 
         v[14] = cmul_dir<DIR> (v[14], cmul_dir<-1> (w2, w12));
         v[15] = cmul_dir<DIR> (v[15], cmul_dir<-1> (w3, w12));
     }
+    else if constexpr (STAGE > 0 && r == G::R)
+    {
+        // R = 32: rows w^1, w^2, w^3 and w^4, w^8, .., w^28
+        const float2* __restrict__ t = tw + G::tw_off (STAGE) + (j & (Ns - 1));
+        const float2 w1 = __ldg (t), w2 = __ldg (t + Ns), w3 = __ldg (t + 2 * Ns);
+        v[1] = cmul_dir<DIR> (v[1], w1);
+        v[2] = cmul_dir<DIR> (v[2], w2);
+        v[3] = cmul_dir<DIR> (v[3], w3);
+#pragma unroll
+        for (int a4 = 1; a4 < G::R / 4; ++a4)
+        {
+            const float2 wa = __ldg (t + (2 + a4) * Ns);
+            v[4 * a4] = cmul_dir<DIR> (v[4 * a4], wa);
+            v[4 * a4 + 1] = cmul_dir<DIR> (v[4 * a4 + 1], cmul_dir<-1> (w1, wa));
+            v[4 * a4 + 2] = cmul_dir<DIR> (v[4 * a4 + 2], cmul_dir<-1> (w2, wa));
+            v[4 * a4 + 3] = cmul_dir<DIR> (v[4 * a4 + 3], cmul_dir<-1> (w3, wa));
+        }
+    }
     else if constexpr (STAGE > 0)
     {
-        // last stage, radix r < 16: butterfly u of this thread has k = j + u T, and
-        // W^(k q) = W^(j q) W16^(u q)  because T = M / 16
+        // last stage, radix r < R: butterfly u of this thread has k = j + u T, and
+        // W^(k q) = W^(j q) W_R^(u q)  because T = M / R
         const float2* __restrict__ t = tw + G::tw_off (STAGE) + j;
-        float2 w[r];
 #pragma unroll
         for (int q = 1; q < r; ++q)
-            w[q] = __ldg (t + (q - 1) * G::T);
-#pragma unroll
-        for (int u = 0; u < SUB; ++u)
         {
+            const float2 wq = __ldg (t + (q - 1) * G::T);
 #pragma unroll
-            for (int q = 1; q < r; ++q)
+            for (int u = 0; u < SUB; ++u)
             {
-                float2 x = cmul_dir<DIR> (v[u + q * SUB], w[q]);
-                v[u + q * SUB] = mul_w16_rt<DIR> (x, u * q);
+                const float2 x = cmul_dir<DIR> (v[u + q * SUB], wq);
+                v[u + q * SUB] = mul_w32_rt<DIR> (x, u * q * (32 / G::R));
             }
         }
     }
@@ -432,16 +478,16 @@ FFT_HD void stage_scatter (const float2 (&v)[G::R], int j, float2* s)
         const int jv = j + u * G::T;
         const int k = jv & (Ns - 1);
         const int base = (jv - k) * r + k;
-        if constexpr (Ns % 16 == 0)
+        if constexpr (Ns % G::R == 0)
         {
-            float2* sb = s + pad (base);
+            float2* sb = s + G::pad (base);
 #pragma unroll
             for (int q = 0; q < r; ++q)
-                sts2 (sb + pad (q * Ns), v[u + q * SUB]);
+                sts2 (sb + G::pad (q * Ns), v[u + q * SUB]);
         }
-        else if constexpr (Ns == 1 && r == 16)
+        else if constexpr (Ns == 1 && r == G::R)
         {
-            float2* sb = s + 17 * jv; // pad (16 jv + q) = 17 jv + q
+            float2* sb = s + (G::R + 1) * jv; // pad (R jv + q) = (R + 1) jv + q
 #pragma unroll
             for (int q = 0; q < r; ++q)
                 sts2 (sb + q, v[u + q * SUB]);
@@ -450,7 +496,7 @@ FFT_HD void stage_scatter (const float2 (&v)[G::R], int j, float2* s)
         {
 #pragma unroll
             for (int q = 0; q < r; ++q)
-                sts2 (s + pad (base + q * Ns), v[u + q * SUB]);
+                sts2 (s + G::pad (base + q * Ns), v[u + q * SUB]);
         }
     }
 }
@@ -459,45 +505,45 @@ FFT_HD void stage_scatter (const float2 (&v)[G::R], int j, float2* s)
 template <class G, int M0, int M1>
 FFT_HD void gather_natural (float2 (&v)[G::R], int j, const float2* s)
 {
-    if constexpr (G::T % 16 == 0)
+    if constexpr (G::T % G::R == 0)
     {
-        const float2* sb = s + pad (j);
+        const float2* sb = s + G::pad (j);
 #pragma unroll
         for (int m = M0; m < M1; ++m)
-            v[m] = lds2 (sb + pad (m * G::T));
+            v[m] = lds2 (sb + G::pad (m * G::T));
     }
     else
     {
 #pragma unroll
         for (int m = M0; m < M1; ++m)
-            v[m] = lds2 (s + pad (j + m * G::T));
+            v[m] = lds2 (s + G::pad (j + m * G::T));
     }
 }
 template <class G, int M0, int M1>
 FFT_HD void scatter_natural (const float2 (&v)[G::R], int j, float2* s)
 {
-    if constexpr (G::T % 16 == 0)
+    if constexpr (G::T % G::R == 0)
     {
-        float2* sb = s + pad (j);
+        float2* sb = s + G::pad (j);
 #pragma unroll
         for (int m = M0; m < M1; ++m)
-            sts2 (sb + pad (m * G::T), v[m]);
+            sts2 (sb + G::pad (m * G::T), v[m]);
     }
     else
     {
 #pragma unroll
         for (int m = M0; m < M1; ++m)
-            sts2 (s + pad (j + m * G::T), v[m]);
+            sts2 (s + G::pad (j + m * G::T), v[m]);
     }
 }
 // natural-order slot of the mirror element M - (j + m T), m < R/2 (the caller handles j == 0 && m == 0)
 template <class G>
 FFT_HD int mirror_slot (int j, int m)
 {
-    if constexpr (G::T % 16 == 0)
-        return pad (G::T - j) + pad (G::M - m * G::T - G::T); // (M - mT - T) + (T - j), first term % 16 == 0
+    if constexpr (G::T % G::R == 0)
+        return G::pad (G::T - j) + G::pad (G::M - m * G::T - G::T); // (M - mT - T) + (T - j), first term % R == 0
     else
-        return pad (G::M - j - m * G::T);
+        return G::pad (G::M - j - m * G::T);
 }
 
 template <class G, int DIR, int STAGE>
@@ -701,6 +747,13 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
 #pragma unroll
             for (int m = 0; m < R; ++m)
                 v[m] = ldg_stream (in2 + m * T);
+            if (win != nullptr) // constant-folded away in the plain batched kernel
+            {
+                const float2* __restrict__ wj = win + j;
+#pragma unroll
+                for (int m = 0; m < R; ++m)
+                    v[m] = f2_mul (v[m], __ldg (wj + m * T));
+            }
         }
     }
     else if constexpr (KIND == C2C_BWD)
@@ -764,7 +817,7 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
             {
                 zk = make_float2 (xa.x + xa.y, xa.x - xa.y);   // Z'[0] from (DC, Nyquist)
                 zm = make_float2 (2.f * xm.x, -2.f * xm.y);    // Z'[M/2] = 2 conj X[M/2]
-                slot = pad (M / 2);
+                slot = G::pad (M / 2);
             }
             v[m] = zk;
             sts2 (s + slot, zm);
@@ -812,7 +865,7 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
         float2 zb[R / 2];
 #pragma unroll
         for (int m = 0; m < R / 2; ++m)
-            zb[m] = lds2 (s + ((m == 0 && j == 0) ? pad (M / 2) : mirror_slot<G> (j, m)));
+            zb[m] = lds2 (s + ((m == 0 && j == 0) ? G::pad (M / 2) : mirror_slot<G> (j, m)));
         if constexpr (UNORD)
             __syncthreads(); // natural-order image fully consumed before the staging image overwrites it
         const float2* __restrict__ rt = a.rtw + j;
@@ -896,7 +949,8 @@ struct Launch
     static constexpr int PER_CTA = THREADS / G::T;
     static constexpr int SMEM_BYTES = PER_CTA * G::SMEM_F2 * 8;
     static constexpr int SMEM_BYTES_UNORD = PER_CTA * G::SMEM_F2_UNORD * 8;
-    static constexpr int MIN_BLOCKS = THREADS <= 256 ? 4 : (THREADS <= 512 ? 2 : 1);
+    // R = 16 kernels fit 64 registers per thread (1024 resident threads per SM), R = 32 kernels need 128 (512)
+    static constexpr int MIN_BLOCKS = (R == 16 ? 1024 : 512) / THREADS < 1 ? 1 : (R == 16 ? 1024 : 512) / THREADS;
 };
 
 template <int LOGM, int R, int KIND, int LOGW>
@@ -906,14 +960,19 @@ __global__ void __launch_bounds__ (Launch<LOGM, R>::THREADS, Launch<LOGM, R>::MI
 }
 
 // ---------------------------------------------------------------------------------------------
-// Frame-gather (STFT analysis) kernel: R2C of OVERLAPPING windows of one signal.  A CTA owns PER_CTA
-// consecutive frames of one channel, copies the UNION of their samples ((PER_CTA-1) hop + N floats instead
-// of PER_CTA N) into shared memory once with linear 128-bit loads, and every transform takes its stage-0
-// registers from there (times the analysis window, if any).  With hop = N/4 and four frames per CTA the
-// L2->SM input traffic drops 2.3x relative to gathering every frame separately.
-// Grid = outer * groups, groups = ceil (inner / PER_CTA).  Needs 0 < in_inner <= N and in_inner even.
+// Frame-gather (STFT analysis) kernel: R2C of OVERLAPPING windows of one signal, times an optional analysis
+// window.  A CTA owns PER_CTA consecutive frames of one channel.  Grid = outer * groups, groups =
+// ceil (inner / PER_CTA).
+//   UNION = false: every transform loads its own frame straight into registers (re-reads of the overlap are
+//                  L2 hits) -- the faster variant on B200: the kernel is bound by the L1/shared-memory pipe,
+//                  not by L2->SM bytes (ncu: l1tex 84 %, DRAM 47 %), and staging costs extra wavefronts.
+//   UNION = true : the union of the CTA's frames ((PER_CTA-1) hop + N floats instead of PER_CTA N) is copied
+//                  into shared memory once with linear 128-bit loads and every transform takes its stage-0
+//                  registers from there; 2.3x fewer L2->SM bytes at hop = N/4 (kept selectable for parts where
+//                  that is the bound).  Needs 0 < in_inner <= N.
+// in_inner and in_outer must be even (8-byte aligned frames).
 // ---------------------------------------------------------------------------------------------
-template <int LOGM, int R, int LOGW>
+template <int LOGM, int R, int LOGW, bool UNION>
 FFT_HD void stft_body (const FftArgs& a)
 {
     using G = Geo<LOGM, R>;
@@ -933,6 +992,13 @@ FFT_HD void stft_body (const FftArgs& a)
     const int ltc = active ? lt : nact - 1; // idle transforms of the last group redo its last frame and skip the store
 
     const float* __restrict__ base = a.in + (long long) o * a.in_outer + (long long) f0 * a.in_inner;
+    float* out = a.out + (long long) o * a.out_outer + (long long) (f0 + ltc) * a.out_inner;
+    if constexpr (! UNION)
+    {
+        fft_core<LOGM, R, R2C, LOGW, false, false, false, false> (base + (long long) ltc * a.in_inner, out, active, j, smem + lt * SMEM_F2, a.tw, a.rtw,
+                                                                  nullptr, reinterpret_cast<const float2*> (a.window));
+        return;
+    }
     const int span = (nact - 1) * (int) a.in_inner + NFL; // floats, <= per_cta * NFL
     float* su = reinterpret_cast<float*> (smem);
     if (a.vec4)
@@ -956,15 +1022,14 @@ FFT_HD void stft_body (const FftArgs& a)
         }
     }
     __syncthreads();
-    float* out = a.out + (long long) o * a.out_outer + (long long) (f0 + ltc) * a.out_inner;
     fft_core<LOGM, R, R2C, LOGW, false, false, false, true> (nullptr, out, active, j, smem + lt * SMEM_F2, a.tw, a.rtw,
                                                              smem + ltc * (int) (a.in_inner / 2), reinterpret_cast<const float2*> (a.window));
 }
 
-template <int LOGM, int R, int LOGW>
+template <int LOGM, int R, int LOGW, bool UNION>
 __global__ void __launch_bounds__ (Launch<LOGM, R>::THREADS, Launch<LOGM, R>::MIN_BLOCKS) stft_kernel (const FftArgs a)
 {
-    stft_body<LOGM, R, LOGW> (a);
+    stft_body<LOGM, R, LOGW, UNION> (a);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -980,10 +1045,10 @@ inline void fill_stage_twiddles (float2* tw) // Geo<LOGM,R>::TW_LEN entries, lay
         const int r = G::radix (s), Ns = G::ns (s);
         float2* t = tw + G::tw_off (s);
         const long long period = (long long) Ns * r;
-        if (r == 16)
+        if (r == R)
         {
-            const int rows[6] = { 1, 2, 3, 4, 8, 12 };
-            for (int i = 0; i < 6; ++i)
+            const int rows[10] = { 1, 2, 3, 4, 8, 12, 16, 20, 24, 28 };
+            for (int i = 0; i < G::FULL_ROWS; ++i)
                 for (int k = 0; k < Ns; ++k)
                 {
                     const long double ang = -two_pi * (long double) (((long long) k * rows[i]) % period) / (long double) period;

@@ -6,11 +6,11 @@ namespace cfb
 {
 namespace
 {
-template <int LOGL, int DIR, bool JFAST>
+template <int LOGL, int C, int DIR, bool JFAST>
 cudaError_t launch_tile_one (const TileArgs& a, cudaStream_t stream)
 {
-    using TL = TileLaunch<LOGL, kTileC>;
-    auto kernel = tile_fft_kernel<LOGL, kTileC, DIR, JFAST>;
+    using TL = TileLaunch<LOGL, C>;
+    auto kernel = tile_fft_kernel<LOGL, C, DIR, JFAST>;
     if (TL::SMEM_BYTES > 48 * 1024)
     {
         const cudaError_t e = cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TL::SMEM_BYTES);
@@ -21,24 +21,34 @@ cudaError_t launch_tile_one (const TileArgs& a, cudaStream_t stream)
     count_launch();
     return cudaGetLastError();
 }
-template <int LOGL>
-cudaError_t launch_tile_l (int dir, bool jfast, const TileArgs& a, cudaStream_t stream)
+template <int LOGL, int C>
+cudaError_t launch_tile_lc (int dir, bool jfast, const TileArgs& a, cudaStream_t stream)
 {
     if (dir < 0)
-        return jfast ? launch_tile_one<LOGL, -1, true> (a, stream) : launch_tile_one<LOGL, -1, false> (a, stream);
-    return jfast ? launch_tile_one<LOGL, +1, true> (a, stream) : launch_tile_one<LOGL, +1, false> (a, stream);
+        return jfast ? launch_tile_one<LOGL, C, -1, true> (a, stream) : launch_tile_one<LOGL, C, -1, false> (a, stream);
+    return jfast ? launch_tile_one<LOGL, C, +1, true> (a, stream) : launch_tile_one<LOGL, C, +1, false> (a, stream);
+}
+template <int LOGL>
+cudaError_t launch_tile_l (int C, int dir, bool jfast, const TileArgs& a, cudaStream_t stream)
+{
+    if (C == 8)
+        return launch_tile_lc<LOGL, 8> (dir, jfast, a, stream);
+    if constexpr (LOGL <= 9)
+        if (C == 16)
+            return launch_tile_lc<LOGL, 16> (dir, jfast, a, stream);
+    return cudaErrorInvalidValue;
 }
 } // namespace
 
-cudaError_t launch_tile (int logL, int dir, bool load_j_fast, const TileArgs& a, cudaStream_t stream)
+cudaError_t launch_tile (int logL, int C, int dir, bool load_j_fast, const TileArgs& a, cudaStream_t stream)
 {
     switch (logL)
     {
-        case 6: return launch_tile_l<6> (dir, load_j_fast, a, stream);
-        case 7: return launch_tile_l<7> (dir, load_j_fast, a, stream);
-        case 8: return launch_tile_l<8> (dir, load_j_fast, a, stream);
-        case 9: return launch_tile_l<9> (dir, load_j_fast, a, stream);
-        case 10: return launch_tile_l<10> (dir, load_j_fast, a, stream);
+        case 6: return launch_tile_l<6> (C, dir, load_j_fast, a, stream);
+        case 7: return launch_tile_l<7> (C, dir, load_j_fast, a, stream);
+        case 8: return launch_tile_l<8> (C, dir, load_j_fast, a, stream);
+        case 9: return launch_tile_l<9> (C, dir, load_j_fast, a, stream);
+        case 10: return launch_tile_l<10> (C, dir, load_j_fast, a, stream);
         default: return cudaErrorInvalidValue;
     }
 }

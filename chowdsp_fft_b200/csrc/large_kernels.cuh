@@ -16,14 +16,20 @@
 #pragma once
 #include "fft_kernels.cuh"
 
-// extra float2 slots between the exchange regions of adjacent transforms of a tile: 2 makes every
-// exchange of the tile kernels bank-conflict free (measured with the emulator for all pass lengths)
-#ifndef CFB_TILE_PAD
-#define CFB_TILE_PAD 2
-#endif
 
 namespace cfb
 {
+// float2 slots between the exchange regions of adjacent transforms of a tile.  Adjacent threads of a warp own
+// adjacent transforms, so the region stride must spread the C transforms over all 32 banks: stride mod 16
+// float2 slots = an odd multiple of 16 / C (checked with the emulator's bank model for every pass length).
+FFT_CX int tile_region_stride (int smem_f2, int C)
+{
+    int rs = smem_f2;
+    while ((rs % 16) % (2 * (16 / C)) != 16 / C)
+        ++rs;
+    return rs;
+}
+
 struct TileArgs
 {
     const float2* in;
@@ -67,7 +73,7 @@ FFT_HD void tile_body (const TileArgs& a)
     constexpr int R = 16;
     using G = Geo<LOGL, R>;
     constexpr int T = G::T;
-    constexpr int RS = G::SMEM_F2 + CFB_TILE_PAD; // region stride chosen so that adjacent transforms land in different banks
+    constexpr int RS = tile_region_stride (G::SMEM_F2, C);
     static_assert (! LOAD_J_FAST || G::S >= 2, "the thread-map switch needs at least one exchange");
     FFT_DYN_SMEM (float2, smem);
     const int tid = (int) threadIdx.x;
@@ -83,6 +89,21 @@ FFT_HD void tile_body (const TileArgs& a)
     const int ltA = tid / T, jA = tid % T; // adjacent threads = adjacent elements
     float2 v[R];
     float2* sB = smem + ltB * RS;
+    float2* sTw = smem + C * RS;           // A[m][lt] = W_N^(mu m T c(lt)), see the twiddle step below
+    const unsigned cT = a.tw_c_base + (unsigned) (glo * C + ltB); // this thread's column in the twiddle index
+    if (a.tw_mult != 0)
+    {
+        for (int i = tid; i - tid < R * C; i += T * C) // i = m C + lt
+        {
+            if (i < R * C)
+            {
+                const unsigned c = a.tw_c_base + (unsigned) (glo * C + i % C);
+                sts2 (sTw + i, big_twiddle<DIR> (a, (unsigned) (i / C) * (unsigned) T * c * a.tw_mult));
+            }
+            else
+                smem_skip();
+        }
+    } // visibility: every pass has at least one exchange barrier before the twiddle step
 
     if constexpr (LOAD_J_FAST)
     {
@@ -120,23 +141,17 @@ FFT_HD void tile_body (const TileArgs& a)
         Stages<G, DIR, 0>::run (v, jB, sB, a.tw, false);
     }
 
-    // v[m] = X[jB + m T] of transform ltB
+    // v[m] = X[jB + m T] of transform ltB.  Four-step twiddle W_N^(mu k c), k = jB + m T, c = c0 + ltB:
+    //   W^(mu k c) = W^(mu jB c) * W^(mu m T c) = B (own register, one table lookup per thread)
+    //                                            * A[m][ltB] (16 C values per CTA, looked up once, kept in smem)
+    // so a thread makes 2 (+2 for the first 16 C threads) scattered table loads instead of one pair per element.
     if (a.tw_mult != 0)
     {
-        const unsigned c = a.tw_c_base + (unsigned) (glo * C + ltB);
-        const unsigned e0 = (unsigned) jB * c * a.tw_mult, de = (unsigned) T * c * a.tw_mult; // e(m) = e0 + m de < N
-        // exact table values for m = 0..3 and for the strides 4, 8, 12; the rest is one product each
-        float2 w[4], d[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-        {
-            w[i] = big_twiddle<DIR> (a, e0 + i * de);
-            d[i] = i == 0 ? make_float2 (1.f, 0.f) : big_twiddle<DIR> (a, 4 * i * de);
-        }
+        const float2 bw = big_twiddle<DIR> (a, (unsigned) jB * cT * a.tw_mult);
 #pragma unroll
         for (int m = 0; m < R; ++m)
         {
-            const float2 wm = (m < 4) ? w[m] : cmul_dir<-1> (w[m & 3], d[m >> 2]);
+            const float2 wm = m == 0 ? bw : cmul_dir<-1> (bw, lds2 (sTw + m * C + ltB));
             v[m] = cmul_dir<DIR> (v[m], wm);
         }
     }
@@ -151,7 +166,7 @@ struct TileLaunch
 {
     using G = Geo<LOGL, 16>;
     static constexpr int THREADS = G::T * C;
-    static constexpr int SMEM_BYTES = C * (G::SMEM_F2 + CFB_TILE_PAD) * 8;
+    static constexpr int SMEM_BYTES = (C * tile_region_stride (G::SMEM_F2, C) + 16 * C) * 8; // exchange regions + twiddle rows A[16][C]
     static constexpr int MIN_BLOCKS = THREADS <= 256 ? 4 : (THREADS <= 512 ? 2 : 1);
 };
 

@@ -5,7 +5,18 @@
 
 namespace cfb
 {
-constexpr int kTileC = 8;        // adjacent transforms per tile: 64 contiguous bytes on the strided side
+// adjacent transforms per tile = contiguous complex elements on the strided side of a pass: 16 (one full 128-byte
+// line per element row) whenever the CTA stays at <= 512 threads, 8 (64 bytes) for 1024-point passes
+constexpr int kTileCMax = 16;
+inline int& tile_c_override() { static int v = 0; return v; }       // tuning hooks (0 = policy below)
+inline int& tile_c_jfast_override() { static int v = 0; return v; } // ... for the contiguous-row (last) pass only
+inline int tile_c (int logL, bool jfast = false)
+{
+    const int ov = (jfast && tile_c_jfast_override() != 0) ? tile_c_jfast_override() : tile_c_override();
+    if (ov != 0)
+        return (ov == 16 && logL > 9) ? 8 : ov;
+    return logL <= 9 ? 16 : 8;
+}
 constexpr int kMinTileLog = 6;   // tile transforms are 64 .. 1024 points
 constexpr int kMaxTileLog = 10;
 constexpr int kMaxLargeLog = 28; // 2^28 complex points (2 GiB) is the largest single transform
@@ -36,6 +47,7 @@ inline LargeFactors choose_factors (int n)
 
 struct TilePass
 {
+    int C;             // transforms per tile (8 or 16)
     int logL;          // transform length of this pass
     bool load_j_fast;  // contiguous-row pass (the last one)
     TileArgs args;     // in / out / twiddle pointers are filled in by the caller
@@ -51,6 +63,8 @@ inline int build_tile_passes (int n, const LargeFactors& f, TilePass (&p)[3], un
         TilePass& a = p[np++];
         a = {};
         a.logL = f.l1;
+        a.C = tile_c (f.l1);
+        const int kTileC = a.C;
         a.load_j_fast = false;
         const long long S1 = N / L1;
         a.args.gdiv = (int) (S1 / kTileC);
@@ -68,6 +82,8 @@ inline int build_tile_passes (int n, const LargeFactors& f, TilePass (&p)[3], un
         TilePass& b = p[np++];
         b = {};
         b.logL = f.l2;
+        b.C = tile_c (f.l2);
+        const int kTileC = b.C;
         b.load_j_fast = false;
         b.args.gdiv = (int) (L3 / kTileC);
         b.args.ntiles = (int) (L1 * L3 / kTileC);
@@ -83,6 +99,8 @@ inline int build_tile_passes (int n, const LargeFactors& f, TilePass (&p)[3], un
         TilePass& c = p[np++];
         c = {};
         c.logL = f.l3;
+        c.C = tile_c (f.l3, true);
+        const int kTileC = c.C;
         c.load_j_fast = true;
         c.args.gdiv = (int) (L1 / kTileC);
         c.args.ntiles = (int) (L1 * L2 / kTileC);
@@ -113,12 +131,14 @@ inline bool build_dist_phase (int n, const LargeFactors& f, int phase, int rank,
     if (f.l2 == 0 || world < 1 || (world & (world - 1)) != 0)
         return false;
     const long long N = 1LL << n, L1 = 1LL << f.l1, L2 = 1LL << f.l2, L3 = 1LL << f.l3, S1 = L2 * L3;
-    if (L1 / world < kTileC || L2 / world < 1 || S1 / world < kTileC)
+    const int kTileC = tile_c (phase == 0 ? f.l1 : (phase == 1 ? f.l2 : f.l3), phase == 2);
+    if (L1 / world < kTileCMax || L2 / world < 1 || S1 / world < kTileCMax)
         return false;
     int wl = 0;
     while ((1 << wl) < world)
         ++wl;
     p = {};
+    p.C = kTileC;
     p.args.batch = 1;
     p.args.in_split_log = 31;
     (void) N;

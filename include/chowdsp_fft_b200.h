@@ -45,8 +45,8 @@ int fft_transform_strided (void* setup, const float* input, float* output, int o
    signal + c*channel_stride + f*hop (0 < hop, frames may overlap), multiplied by window[0..N) when window
    is non-NULL (NULL = rectangular, which is what a loop over reference chowdsp_fft.h:138 computes), and its
    forward real transform is written to spectra + c*out_channel_stride + f*out_frame_stride (N floats,
-   ordered pffft packing or the unordered layout).  One kernel: a CTA gathers the union of its consecutive
-   frames from HBM/L2 once.  Device pointers only; hop and channel_stride even; window needs hop <= N. */
+   ordered pffft packing or the unordered layout).  One kernel, the window multiply is fused into the load.
+   Device pointers only; hop and channel_stride must be even. */
 int fft_stft_forward (void* setup, const float* signal, float* spectra, int channels, int frames, long long channel_stride, long long hop, long long out_channel_stride, long long out_frame_stride, const float* window, int ordered, void* stream);
 
 /* batch x (ab += a*b*scaling) on unordered spectra; a stride of 0 shares that operand across the
@@ -91,6 +91,12 @@ int fft_accumulate_batched (void* setup, const float* a, const float* b, float* 
    reference-shaped functions return void, so callers that want to detect failures clear, call, read). */
 const char* fft_b200_last_error (void);
 void fft_b200_clear_error (void);
+
+/* Tuning hook for benchmarks/sweeps (not needed in normal use): key "tile_c" = transforms per tile of the
+   multi-pass kernels (8, 16, or 0 for the built-in policy); "radix32_mask" bit n = use the 32-points-per-thread kernel for complex length 2^n (n in 9, 10, 13, 14);
+   "stft_union" = 1 stages the union of a CTA's
+   overlapping frames through shared memory (fewer L2 reads, more shared-memory traffic). */
+int fft_b200_set_tuning (const char* key, int value);
 
 /* Number of CUDA kernels this library has launched in this process (all threads). */
 unsigned long long fft_b200_launch_count (void);

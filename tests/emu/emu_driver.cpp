@@ -11,10 +11,11 @@ using namespace cfb;
 
 namespace
 {
-template <int LOGM, int KIND, int LOGW>
-int run_one (FftArgs a)
+int g_emu_radix = 16; // emu_set_radix: 32 selects the 32-points-per-thread geometry where it is instantiated
+
+template <int LOGM, int KIND, int LOGW, int R>
+int run_one_r (FftArgs a)
 {
-    constexpr int R = 16;
     using G = Geo<LOGM, R>;
     using L = Launch<LOGM, R>;
     std::vector<float2> tw ((size_t) G::TW_LEN + 1), rtw ((size_t) G::M / 2 + 1);
@@ -25,6 +26,14 @@ int run_one (FftArgs a)
     const unsigned grid = (unsigned) ((a.batch + L::PER_CTA - 1) / L::PER_CTA);
     emu::launch (fft_kernel<LOGM, R, KIND, LOGW>, dim3 (grid), dim3 (L::THREADS), (size_t) (LOGW != 0 ? L::SMEM_BYTES_UNORD : L::SMEM_BYTES), a);
     return 0;
+}
+template <int LOGM, int KIND, int LOGW>
+int run_one (FftArgs a)
+{
+    if constexpr (LOGM == 9 || LOGM == 10 || LOGM == 13 || LOGM == 14)
+        if (g_emu_radix == 32)
+            return run_one_r<LOGM, KIND, LOGW, 32> (a);
+    return g_emu_radix == 16 ? run_one_r<LOGM, KIND, LOGW, 16> (a) : -1;
 }
 
 template <int LOGM>
@@ -59,14 +68,25 @@ namespace
 {
 // multi-pass complex transform of 2^n points through the tile kernels (factors forced by the caller so that
 // small sizes can exercise the two- and three-pass plans); in/out interleaved complex, natural order
+template <int LOGL, int C, int DIR>
+void emu_tile_launch_c (const TilePass& p)
+{
+    using TL = TileLaunch<LOGL, C>;
+    if (p.load_j_fast)
+        emu::launch (tile_fft_kernel<LOGL, C, DIR, true>, dim3 ((unsigned) p.args.ntiles), dim3 (TL::THREADS), (size_t) TL::SMEM_BYTES, p.args);
+    else
+        emu::launch (tile_fft_kernel<LOGL, C, DIR, false>, dim3 ((unsigned) p.args.ntiles), dim3 (TL::THREADS), (size_t) TL::SMEM_BYTES, p.args);
+}
 template <int LOGL, int DIR>
 void emu_tile_launch (const TilePass& p)
 {
-    using TL = TileLaunch<LOGL, kTileC>;
-    if (p.load_j_fast)
-        emu::launch (tile_fft_kernel<LOGL, kTileC, DIR, true>, dim3 ((unsigned) p.args.ntiles), dim3 (TL::THREADS), (size_t) TL::SMEM_BYTES, p.args);
+    if (p.C == 16)
+    {
+        if constexpr (LOGL <= 9)
+            emu_tile_launch_c<LOGL, 16, DIR> (p);
+    }
     else
-        emu::launch (tile_fft_kernel<LOGL, kTileC, DIR, false>, dim3 ((unsigned) p.args.ntiles), dim3 (TL::THREADS), (size_t) TL::SMEM_BYTES, p.args);
+        emu_tile_launch_c<LOGL, 8, DIR> (p);
 }
 template <int DIR>
 int emu_tile_dispatch (const TilePass& p)
@@ -132,7 +152,7 @@ int emu_fft (int logM, int kind, int unord, int logW, const float* in, float* ou
 }
 
 // frame-gather R2C (stft_kernel): `outer` channels x `inner` frames, hop = in_inner, optional window
-int emu_stft (int logM, int unord, int logW, const float* in, float* out, int outer, int inner, long long in_outer, long long in_inner, long long out_outer, long long out_inner, const float* window, int vec4, int log_conflicts, long* stats)
+int emu_stft (int logM, int unord, int logW, const float* in, float* out, int outer, int inner, long long in_outer, long long in_inner, long long out_outer, long long out_inner, const float* window, int vec4, int union_gather, int log_conflicts, long* stats)
 {
     auto run = [&] (auto logm_c, auto logw_c) -> int
     {
@@ -149,7 +169,11 @@ int emu_stft (int logM, int unord, int logW, const float* in, float* out, int ou
         a.tw = tw.data(); a.rtw = rtw.data();
         a.window = window; a.vec4 = vec4;
         a.groups = (inner + L::PER_CTA - 1) / L::PER_CTA;
-        emu::launch (stft_kernel<LOGM, 16, LOGW>, dim3 ((unsigned) (outer * a.groups)), dim3 (L::THREADS), (size_t) (LOGW != 0 ? L::SMEM_BYTES_UNORD : L::SMEM_BYTES), a);
+        a.union_gather = union_gather;
+        if (union_gather)
+            emu::launch (stft_kernel<LOGM, 16, LOGW, true>, dim3 ((unsigned) (outer * a.groups)), dim3 (L::THREADS), (size_t) (LOGW != 0 ? L::SMEM_BYTES_UNORD : L::SMEM_BYTES), a);
+        else
+            emu::launch (stft_kernel<LOGM, 16, LOGW, false>, dim3 ((unsigned) (outer * a.groups)), dim3 (L::THREADS), (size_t) (LOGW != 0 ? L::SMEM_BYTES_UNORD : L::SMEM_BYTES), a);
         return 0;
     };
     using std::integral_constant;
@@ -194,6 +218,9 @@ int emu_pconv (int logM, int logW, const float* in, long long in_stride, const f
     if (logM == 12 && logW == 3) return run (integral_constant<int, 12> {}, integral_constant<int, 3> {});
     return -1;
 }
+
+void emu_set_tile_c (int c) { tile_c_override() = c; }
+void emu_set_radix (int r) { g_emu_radix = r; }
 
 int emu_large_c2c (int n, int l1, int l2, int l3, int backward, const float* in, float* out, int log_conflicts, long* stats)
 {

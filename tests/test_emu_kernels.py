@@ -18,7 +18,7 @@ def emu():
     L.emu_fft.argtypes = [C.c_int] * 4 + [fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 4 + [C.c_int, C.POINTER(C.c_long)]
     L.emu_convolve.argtypes = [fp, fp, fp] + [C.c_longlong] * 3 + [C.c_int] * 4 + [C.c_float]
     L.emu_accumulate.argtypes = [fp, fp, fp, C.c_longlong]
-    L.emu_stft.argtypes = [C.c_int] * 3 + [fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 4 + [fp, C.c_int, C.c_int, C.POINTER(C.c_long)]
+    L.emu_stft.argtypes = [C.c_int] * 3 + [fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 4 + [fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_long)]
     return L
 
 
@@ -70,6 +70,32 @@ def test_emulated_kernels_match_oracle(emu, oracle_mod, N, is_c, avx):
                 else:
                     # several small transforms share a warp; their staging images alias in the banks
                     assert s[1] <= 2.6 * s[2] and s[3] <= 400, s
+
+
+@pytest.mark.parametrize("N,is_c", [(512, True), (1024, True), (8192, True), (16384, True), (1024, False), (2048, False), (16384, False), (32768, False)])
+def test_emulated_radix32_geometry(emu, oracle_mod, N, is_c):
+    """The 32-points-per-thread geometry (one exchange fewer for M = 512, 1024, 8192, 16384): same results,
+    conflict-free exchanges."""
+    o = oracle_mod
+    W = 8
+    nfl = 2 * N if is_c else N
+    batch = 3 if N <= 2048 else 1
+    rng = np.random.default_rng(N + 32)
+    x = rng.uniform(-1, 1, (batch, nfl)).astype(np.float32)
+    emu.emu_set_radix(32)
+    try:
+        for ordered in (True, False):
+            f, st = run_fft(emu, x, N, is_c, W, False, ordered, batch, log=True)
+            ref = o.np_transform(x, N, is_c, W, False, ordered)
+            assert o.rel_l2(f, ref) < 4e-7
+            b, st2 = run_fft(emu, ref, N, is_c, W, True, ordered, batch, log=True)
+            assert o.rel_l2(b, o.np_transform(ref, N, is_c, W, True, ordered)) < 4e-7
+            for s in (st, st2):
+                M = N if is_c else N // 2
+                if M >= 1024:
+                    assert s[1] <= 1.10 * s[2] and s[3] <= 200, s
+    finally:
+        emu.emu_set_radix(16)
 
 
 def test_emulated_impulse_and_tone_positions(emu, oracle_mod):
@@ -173,11 +199,13 @@ def test_emulated_fused_partitioned_convolution(emu, oracle_mod, ref_lib, N, W):
         assert o.rel_l2(y, ref_y) < 2e-6
 
 
-@pytest.mark.parametrize("n,l1,l2,l3", [(12, 6, 0, 6), (13, 6, 0, 7), (15, 7, 0, 8), (18, 6, 6, 6)])
-def test_emulated_multi_pass_transform(emu, n, l1, l2, l3):
+@pytest.mark.parametrize("tile_c", [8, 16])
+@pytest.mark.parametrize("n,l1,l2,l3", [(12, 6, 0, 6), (13, 6, 0, 7), (15, 7, 0, 8), (18, 6, 6, 6), (15, 9, 0, 6), (15, 6, 0, 9), (16, 10, 0, 6), (16, 6, 0, 10)])
+def test_emulated_multi_pass_transform(emu, n, l1, l2, l3, tile_c):
     """Tile kernels + pass planning of the large-transform path (two- and three-pass four-step), with the
-    factorisation forced so that small sizes exercise it; bank-conflict free exchanges."""
+    factorisation forced so that small sizes exercise it; both tile widths; bank-conflict free exchanges."""
     emu.emu_large_c2c.argtypes = [C.c_int] * 5 + [fp, fp, C.c_int, C.POINTER(C.c_long)]
+    emu.emu_set_tile_c(tile_c)
     N = 1 << n
     rng = np.random.default_rng(n)
     x = rng.uniform(-1, 1, 2 * N).astype(np.float32)
@@ -185,19 +213,19 @@ def test_emulated_multi_pass_transform(emu, n, l1, l2, l3):
     for backward in ((0, 1) if n <= 13 else (0,)):
         out = np.zeros_like(x)
         st = (C.c_long * 4)()
-        assert emu.emu_large_c2c(n, l1, l2, l3, backward, x.ctypes.data_as(fp), out.ctypes.data_as(fp), int(n <= 15), st) == 0
+        assert emu.emu_large_c2c(n, l1, l2, l3, backward, x.ctypes.data_as(fp), out.ctypes.data_as(fp), int(n <= 16), st) == 0
         ref = np.fft.ifft(z) * N if backward else np.fft.fft(z)
         got = out[0::2] + 1j * out[1::2]
         assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 4e-7
-        if n <= 15:
+        if n <= 16:
             assert st[1] <= 1.15 * st[2] and st[3] <= 150, list(st)  # (nearly) conflict free
 
 
 @pytest.mark.parametrize("N,hop,frames,ordered,W", [(2048, 512, 7, True, 8), (2048, 512, 4, False, 8), (2048, 2048, 5, True, 8),
                                                     (512, 96, 19, True, 8), (512, 130, 9, False, 8), (128, 32, 18, False, 8),
                                                     (32, 8, 21, True, 4), (32, 6, 40, False, 4), (8192, 1024, 3, True, 8)])
-@pytest.mark.parametrize("windowed", [False, True])
-def test_emulated_stft_gather(emu, oracle_mod, N, hop, frames, ordered, W, windowed):
+@pytest.mark.parametrize("windowed,union", [(False, True), (True, True), (True, False)])
+def test_emulated_stft_gather(emu, oracle_mod, N, hop, frames, ordered, W, windowed, union):
     """Frame-gather kernel (union of the CTA's frames staged once in shared memory, optional window) ==
     a loop of single out-of-place transforms over the overlapping frames (the ragged last group included)."""
     o = oracle_mod
@@ -210,7 +238,7 @@ def test_emulated_stft_gather(emu, oracle_mod, N, hop, frames, ordered, W, windo
     st = (C.c_long * 4)()
     vec4 = int(hop % 4 == 0 and samples % 4 == 0)
     rc = emu.emu_stft(int(np.log2(N)) - 1, 0 if ordered else 1, {8: 3, 4: 2}[W], sig.ctypes.data_as(fp), out.ctypes.data_as(fp),
-                      channels, frames, samples, hop, frames * N, N, win.ctypes.data_as(fp) if windowed else None, vec4, 1, st)
+                      channels, frames, samples, hop, frames * N, N, win.ctypes.data_as(fp) if windowed else None, vec4, int(union), 1, st)
     assert rc == 0
     fr = np.stack([[sig[c, f * hop:f * hop + N] for f in range(frames)] for c in range(channels)])
     if windowed:

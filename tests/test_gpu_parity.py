@@ -164,6 +164,25 @@ def test_batched_equals_loop_of_single_calls(cf, oracle_mod):
         cf.fft_destroy_setup(s)
 
 
+@pytest.mark.parametrize("N,is_c", [(512, True), (1024, True), (8192, True), (16384, True), (1024, False), (2048, False), (16384, False), (32768, False)])
+def test_radix32_geometry(cf, oracle_mod, N, is_c):
+    """The 32-points-per-thread kernels (complex lengths 2^9, 2^10, 2^13, 2^14): every kind and layout vs the oracle."""
+    o = oracle_mod
+    nfl = 2 * N if is_c else N
+    rng = np.random.default_rng(N)
+    x = rng.uniform(-1, 1, (5, nfl)).astype(np.float32)
+    cf.set_tuning("radix32_mask", 0x7FFF)
+    try:
+        for ordered in (True, False):
+            f = gpu_transform(cf, x, N, is_c, True, False, ordered)
+            ref = o.np_transform(x, N, is_c, 8, False, ordered)
+            assert o.rel_l2(f, ref) < o.parity_tol(N)
+            b = gpu_transform(cf, ref, N, is_c, True, True, ordered, inplace=True)
+            assert o.rel_l2(b, o.np_transform(ref, N, is_c, 8, True, ordered)) < o.parity_tol(N)
+    finally:
+        cf.set_tuning("radix32_mask", 0)
+
+
 def test_strided_batches_and_stft_gather(cf, oracle_mod):
     o = oracle_mod
     N, hop, channels, frames = 2048, 512, 3, 9
@@ -214,8 +233,16 @@ def test_stft_forward_window_and_layouts(cf, oracle_mod, N, hop, frames):
             assert cf.launch_count() - n0 == 1
             want = o.np_transform((fr * win if w is not None else fr).astype(np.float32), N, False, W, False, ordered)
             assert o.rel_l2(host(out).reshape(-1, N), want) < o.parity_tol(N), (ordered, w is not None)
-    with pytest.raises(cf.FFTError):
-        cf.fft_stft_forward(s, d, out, channels, frames, samples, N + 2, frames * N, N, dw, True)  # window with hop > N
+    cf.set_tuning("stft_union", 1)  # the union-staging variant: same results
+    try:
+        for w in (None, dw):
+            out = torch.full((channels, frames, N), float("nan"), device="cuda")
+            cf.fft_stft_forward(s, d, out, channels, frames, samples, hop, frames * N, N, w, True)
+            torch.cuda.synchronize()
+            want = o.np_transform((fr * win if w is not None else fr).astype(np.float32), N, False, W, False, True)
+            assert o.rel_l2(host(out).reshape(-1, N), want) < o.parity_tol(N)
+    finally:
+        cf.set_tuning("stft_union", 0)
     cf.fft_destroy_setup(s)
 
 

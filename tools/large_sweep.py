@@ -5,7 +5,15 @@ sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")
 import torch
 import chowdsp_fft_b200 as cf
 
-sizes = [int(a) for a in sys.argv[1:]] or [15, 16, 18, 20, 22, 24, 26, 28]
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+for a in sys.argv[1:]:
+    if a.startswith("--tile-c-jfast="):
+        cf.set_tuning("tile_c_jfast", int(a.split("=")[1]))
+        print("tile_c_jfast override:", a.split("=")[1])
+    elif a.startswith("--tile-c="):
+        cf.set_tuning("tile_c", int(a.split("=")[1]))
+        print("tile_c override:", a.split("=")[1])
+sizes = [int(a) for a in args] or [15, 16, 18, 20, 22, 24, 26, 28]
 st = torch.cuda.current_stream()
 for is_c in (True, False):
     for lg in sizes:

@@ -20,18 +20,23 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--sizes", default="")
     ap.add_argument("--json", default="")
+    ap.add_argument("--radix32-mask", type=int, default=-1)
+    ap.add_argument("--kinds", default="c,r")
     args = ap.parse_args()
     try:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         peak = 6650.0
+    if args.radix32_mask >= 0:
+        cf.set_tuning("radix32_mask", args.radix32_mask)
+        print("radix32_mask:", args.radix32_mask)
     total_floats = int(args.bytes * 2**30 / 4)
     x = torch.rand(total_floats, device="cuda") * 2 - 1
     y = torch.empty_like(x)
     stream = torch.cuda.current_stream()
     rows = []
     sizes = [int(s) for s in args.sizes.split(",")] if args.sizes else [1 << l for l in range(5, 16)]
-    for is_c in (True, False):
+    for is_c in [k == "c" for k in args.kinds.split(",")]:
         for N in sizes:
             nfl = 2 * N if is_c else N
             try:
