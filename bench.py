@@ -398,7 +398,7 @@ class Huge(BatchedFFT):
         else:
             from chowdsp_fft_b200.distributed import DistributedFFT
 
-            self.d = DistributedFFT(self.n, rank, world)
+            self.d = DistributedFFT(self.n, rank, world, exchange=os.environ.get("CFB_DIST_EXCHANGE", "peer"))
             self.x = torch.rand(self.d.local_floats, device="cuda", generator=gen) * 2 - 1
             self.y = torch.empty(self.d.S1 * self.d.rows * 2, device="cuda")
 

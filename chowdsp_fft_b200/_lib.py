@@ -58,6 +58,12 @@ def lib() -> C.CDLL:
         "fft_accumulate_batched": (i, [vp, vp, vp, vp, ll, vp]),
         "fft_partitioned_convolve_step": (i, [vp, vp, ll, vp, ll, vp, ll, vp, ll, i, i, i, f, vp]),
         "fft_dist_phase": (i, [vp, i, i, i, vp, vp, i, vp]),
+        "fft_dist_phase0_peer": (i, [vp, i, i, vp, C.POINTER(vp), i, vp]),
+        "fft_dist_alloc": (vp, [C.c_size_t]),
+        "fft_dist_free": (None, [vp]),
+        "fft_dist_ipc_export": (i, [vp, vp]),
+        "fft_dist_ipc_open": (vp, [vp]),
+        "fft_dist_ipc_close": (None, [vp]),
         "fft_large_factors": (i, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "fft_b200_set_tuning": (i, [C.c_char_p, i]),
         "fft_b200_last_error": (C.c_char_p, []),
@@ -77,6 +83,6 @@ EXPORTED = (
     "fft_bytes_required", "fft_new_setup", "fft_new_setup_preallocated", "fft_destroy_setup",
     "fft_simd_width_bytes", "fft_transform", "fft_transform_unordered", "fft_convolve_unordered",
     "fft_accumulate", "aligned_malloc", "aligned_free", "fft_transform_batched", "fft_transform_strided", "fft_stft_forward",
-    "fft_convolve_unordered_batched", "fft_accumulate_batched", "fft_partitioned_convolve_step", "fft_dist_phase", "fft_large_factors", "fft_b200_set_tuning", "fft_b200_last_error", "fft_b200_clear_error",
+    "fft_convolve_unordered_batched", "fft_accumulate_batched", "fft_partitioned_convolve_step", "fft_dist_phase", "fft_dist_phase0_peer", "fft_dist_alloc", "fft_dist_free", "fft_dist_ipc_export", "fft_dist_ipc_open", "fft_dist_ipc_close", "fft_large_factors", "fft_b200_set_tuning", "fft_b200_last_error", "fft_b200_clear_error",
     "fft_b200_launch_count", "fft_b200_device_available",
 )

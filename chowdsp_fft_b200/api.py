@@ -186,3 +186,37 @@ def fft_large_factors(setup: int) -> tuple[int, int, int]:
 def fft_dist_phase(setup: int, phase: int, rank: int, world: int, input, output, direction: int = FFT_FORWARD, stream=None) -> None:
     """One local phase of the distributed four-step transform (see chowdsp_fft_b200.h)."""
     _check(lib().fft_dist_phase(setup, phase, rank, world, _addr(input), _addr(output), direction, _stream(stream)))
+
+
+def fft_dist_phase0_peer(setup: int, rank: int, world: int, input, peer_recv: list[int], direction: int = FFT_FORWARD, stream=None) -> None:
+    """Phase 0 fused with the exchange: row blocks are stored straight into the owners' buffers (peer memory)."""
+    arr = (C.c_void_p * world)(*peer_recv)
+    _check(lib().fft_dist_phase0_peer(setup, rank, world, _addr(input), arr, direction, _stream(stream)))
+
+
+def fft_dist_alloc(nbytes: int) -> int:
+    p = lib().fft_dist_alloc(nbytes)
+    if not p:
+        raise FFTError(_last_error() or "fft_dist_alloc failed")
+    return p
+
+
+def fft_dist_free(p: int) -> None:
+    lib().fft_dist_free(p)
+
+
+def fft_dist_ipc_export(p: int) -> bytes:
+    buf = C.create_string_buffer(64)
+    _check(lib().fft_dist_ipc_export(p, buf))
+    return buf.raw
+
+
+def fft_dist_ipc_open(handle: bytes) -> int:
+    p = lib().fft_dist_ipc_open(C.create_string_buffer(handle, 64))
+    if not p:
+        raise FFTError(_last_error() or "fft_dist_ipc_open failed")
+    return p
+
+
+def fft_dist_ipc_close(p: int) -> None:
+    lib().fft_dist_ipc_close(p)

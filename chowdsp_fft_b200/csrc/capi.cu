@@ -193,9 +193,13 @@ Plan* as_plan (void* setup)
 }
 
 // Points per thread of the single-kernel transform for complex length 2^logM: 32 where that geometry exists and
-// is enabled (tuning hook "radix32_mask", bit logM), else 16.
-unsigned g_radix32_mask = 0;
-int radix_for (int logM) { return (has_radix32 (logM) && ((g_radix32_mask >> logM) & 1u) != 0) ? 32 : 16; }
+// pays off, else 16.  Measured on B200 (profiles/r01_radix32_sweep.txt): one exchange fewer is worth +15..25 % at
+// 2^13, +5..9 % at 2^14, +2..9 % for the real kinds at 2^10 (STFT config +5 %), and costs 0..5 % at 2^9 and for
+// complex 2^10 (fewer resident warps).  Tuning hook "radix32_mask": bit n = complex length 2^n for the complex
+// kinds, bit 16+n for the real kinds; -1 restores this default.
+constexpr unsigned kRadix32Default = (1u << 13) | (1u << 14) | (1u << (16 + 10)) | (1u << (16 + 13)) | (1u << (16 + 14));
+unsigned g_radix32_mask = kRadix32Default;
+int radix_for (int logM, bool is_complex) { return (has_radix32 (logM) && ((g_radix32_mask >> (logM + (is_complex ? 0 : 16))) & 1u) != 0) ? 32 : 16; }
 
 int plan_tables (Plan* p, Tables& t, int radix = 16)
 {
@@ -316,6 +320,7 @@ struct Staging
 thread_local Staging t_staging;
 
 bool g_stft_union = false; // tuning hook "stft_union"
+int g_pf_ahead = 0;        // tuning hook "pf_ahead": L2 prefetch distance of the single-kernel transforms, in CTAs
 
 constexpr size_t kZeroCopyBytes = 256 * 1024;     // pinned buffers up to this size are used in place
 constexpr size_t kChunkBytes = 32ull * 1024 * 1024; // host staging granularity per lane
@@ -473,7 +478,7 @@ int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inne
         return 0;
     }
     Tables t;
-    const int radix = radix_for (p->logM);
+    const int radix = radix_for (p->logM, p->is_complex != 0);
     const int rc = plan_tables (p, t, radix);
     if (rc != 0)
         return rc;
@@ -488,6 +493,7 @@ int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inne
     a.batch = outer * inner;
     a.tw = t.tw;
     a.rtw = t.rtw;
+    a.pf_ahead = g_pf_ahead;
     // windowed real frames (STFT analysis) go through the frame-gather kernel; plain overlapping frames only when
     // the union-staging variant is selected (it is slower on B200, see stft_kernel)
     const bool fwd_real = ! p->is_complex && direction == chowdsp::fft::FFT_FORWARD;
@@ -964,6 +970,96 @@ CFB_API int fft_dist_phase (void* setup, int phase, int rank, int world, const f
     return e == cudaSuccess ? 0 : fail_cuda (e, "distributed phase launch");
 }
 
+CFB_API int fft_dist_phase0_peer (void* setup, int rank, int world, const float* in, float* const* peer_recv, fft_direction_t direction, void* stream)
+{
+    Plan* p = as_plan (setup);
+    if (p == nullptr)
+        return FFT_B200_EINVAL;
+    if (! p->is_complex || p->logM <= kMaxLogM)
+        return fail (FFT_B200_EINVAL, "fft_dist_phase0_peer needs a complex multi-pass plan");
+    if (in == nullptr || peer_recv == nullptr || world < 1 || world > 8 || rank < 0 || rank >= world)
+        return fail (FFT_B200_EINVAL, "fft_dist_phase0_peer: bad arguments (world <= 8)");
+    const LargeFactors f = choose_factors (p->logM);
+    TilePass tp;
+    if (! build_dist_phase (p->logM, f, 0, rank, world, tp))
+        return fail (FFT_B200_EINVAL, "fft_dist_phase0_peer: N=2^%d cannot be split over %d ranks", p->logM, world);
+    int dev = 0;
+    CFB_CUDA (cudaGetDevice (&dev));
+    BigTables bt;
+    int rc = get_big_tables (dev, p->logM, bt);
+    if (rc != 0)
+        return rc;
+    Tables st;
+    rc = get_tables (dev, tp.logL, false, st);
+    if (rc != 0)
+        return rc;
+    int wl = 0;
+    while ((1 << wl) < world)
+        ++wl;
+    tp.args.tw = st.tw;
+    tp.args.tw_lo = bt.lo;
+    tp.args.tw_hi = bt.hi;
+    tp.args.tw_lobits = bt.lobits;
+    tp.args.in = reinterpret_cast<const float2*> (in);
+    tp.args.out = nullptr;
+    tp.args.peer_row_log = f.l1 - wl;
+    for (int h = 0; h < world; ++h)
+    {
+        if (peer_recv[h] == nullptr)
+            return fail (FFT_B200_EINVAL, "fft_dist_phase0_peer: null receive buffer for rank %d", h);
+        tp.args.peer_out[h] = reinterpret_cast<float2*> (peer_recv[h]);
+    }
+    const cudaError_t e = launch_tile (tp.logL, tp.C, direction == FFT_FORWARD ? -1 : +1, tp.load_j_fast, tp.args, static_cast<cudaStream_t> (stream));
+    return e == cudaSuccess ? 0 : fail_cuda (e, "distributed phase 0 (peer stores) launch");
+}
+
+// Peer-memory plumbing for the fused exchange: plain cudaMalloc blocks (IPC handles need whole allocations)
+CFB_API void* fft_dist_alloc (size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaMalloc (&p, bytes > 0 ? bytes : 1) != cudaSuccess)
+    {
+        fail_cuda (cudaGetLastError(), "fft_dist_alloc");
+        return nullptr;
+    }
+    return p;
+}
+CFB_API void fft_dist_free (void* p)
+{
+    if (p != nullptr)
+        (void) cudaFree (p);
+}
+CFB_API int fft_dist_ipc_export (void* p, void* handle64)
+{
+    static_assert (sizeof (cudaIpcMemHandle_t) == 64, "IPC handles are exchanged as 64 opaque bytes");
+    if (p == nullptr || handle64 == nullptr)
+        return fail (FFT_B200_EINVAL, "fft_dist_ipc_export: null argument");
+    cudaIpcMemHandle_t h;
+    CFB_CUDA (cudaIpcGetMemHandle (&h, p));
+    std::memcpy (handle64, &h, 64);
+    return 0;
+}
+CFB_API void* fft_dist_ipc_open (const void* handle64)
+{
+    if (handle64 == nullptr)
+        return nullptr;
+    cudaIpcMemHandle_t h;
+    std::memcpy (&h, handle64, 64);
+    void* p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle (&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess)
+    {
+        fail_cuda (e, "cudaIpcOpenMemHandle");
+        return nullptr;
+    }
+    return p;
+}
+CFB_API void fft_dist_ipc_close (void* p)
+{
+    if (p != nullptr)
+        (void) cudaIpcCloseMemHandle (p);
+}
+
 CFB_API int fft_accumulate_batched (void* setup, const float* a, const float* b, float* ab, long long n, void* stream)
 {
     Plan* p = as_plan (setup);
@@ -988,7 +1084,12 @@ CFB_API int fft_b200_set_tuning (const char* key, int value)
     }
     if (key != nullptr && std::strcmp (key, "radix32_mask") == 0)
     {
-        g_radix32_mask = (unsigned) value;
+        g_radix32_mask = value == -1 ? kRadix32Default : (unsigned) value;
+        return 0;
+    }
+    if (key != nullptr && std::strcmp (key, "pf_ahead") == 0 && value >= 0)
+    {
+        g_pf_ahead = value;
         return 0;
     }
     if (key != nullptr && std::strcmp (key, "stft_union") == 0)

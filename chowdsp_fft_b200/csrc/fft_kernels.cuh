@@ -60,6 +60,9 @@ struct FftArgs
     int groups;
     int vec4;
     int union_gather;    // stage the union of a CTA's frames through shared memory (see stft_kernel)
+    // L2 prefetch distance in CTAs (0 = off): a CTA asks L2 for the input of CTA blockIdx.x + pf_ahead, about one
+    // wave of resident CTAs ahead, so that the loads of a later CTA on this SM find their lines in L2
+    int pf_ahead;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -123,6 +126,20 @@ FFT_HD float4 ldg_stream (const float4* p)
     float4 r;
     asm volatile ("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
+#endif
+}
+
+// ask L2 for the 128-byte lines of one transform's input (M complex = M/16 lines, R/16 per thread)
+template <class G>
+FFT_HD void prefetch_transform_l2 (const float* p, int j)
+{
+#ifndef CHOWDSP_EMU
+#pragma unroll
+    for (int i = 0; i < (G::R >= 16 ? G::R / 16 : 1); ++i)
+        asm volatile ("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*> (p) + (size_t) (j + i * G::T) * 128));
+#else
+    (void) p;
+    (void) j;
 #endif
 }
 
@@ -937,6 +954,20 @@ FFT_HD void fft_body (const FftArgs& a)
     }
     const float* in = a.in + (long long) xo * a.in_outer + (long long) xi * a.in_inner;
     float* out = a.out + (long long) xo * a.out_outer + (long long) xi * a.out_inner;
+    if (a.pf_ahead > 0)
+    {
+        const long long xn = x + (long long) a.pf_ahead * per_cta;
+        if (xn < a.batch)
+        {
+            unsigned no = 0, ni = (unsigned) xn;
+            if (a.inner < a.batch)
+            {
+                no = ni / (unsigned) a.inner;
+                ni -= no * (unsigned) a.inner;
+            }
+            prefetch_transform_l2<G> (a.in + (long long) no * a.in_outer + (long long) ni * a.in_inner, j);
+        }
+    }
     fft_core<LOGM, R, KIND, LOGW, false, false, false> (in, out, active, j, smem + lt * SMEM_F2, a.tw, a.rtw);
 }
 
@@ -993,6 +1024,14 @@ FFT_HD void stft_body (const FftArgs& a)
 
     const float* __restrict__ base = a.in + (long long) o * a.in_outer + (long long) f0 * a.in_inner;
     float* out = a.out + (long long) o * a.out_outer + (long long) (f0 + ltc) * a.out_inner;
+    if (a.pf_ahead > 0)
+    {
+        const long long bn = (long long) blockIdx.x + a.pf_ahead;
+        const long long on = bn / a.groups;
+        const long long fn = (bn - on * a.groups) * per_cta + lt;
+        if (on * a.inner < a.batch && fn < a.inner)
+            prefetch_transform_l2<G> (a.in + on * a.in_outer + fn * a.in_inner, j);
+    }
     if constexpr (! UNION)
     {
         fft_core<LOGM, R, R2C, LOGW, false, false, false, false> (base + (long long) ltc * a.in_inner, out, active, j, smem + lt * SMEM_F2, a.tw, a.rtw,

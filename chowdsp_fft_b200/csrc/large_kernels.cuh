@@ -54,6 +54,13 @@ struct TileArgs
     const float2* tw_lo;
     const float2* tw_hi;
     const float2* tw; // stage twiddles of the length-L transform
+    // Fused exchange of the distributed four-step (phase 0): output row k = element index of the transform goes to
+    // rank h = k >> peer_row_log, whose receive buffer is mapped at peer_out[h] (peer memory over NVLink, or this
+    // rank's own buffer for h = rank):  peer_out[h] + peer_chunk_off + tile offset + (k & mask) * out_estride.
+    // peer_row_log < 0: plain store to `out`.
+    int peer_row_log;
+    long long peer_chunk_off;
+    float2* peer_out[8];
 };
 
 template <int DIR>
@@ -154,6 +161,20 @@ FFT_HD void tile_body (const TileArgs& a)
             const float2 wm = m == 0 ? bw : cmul_dir<-1> (bw, lds2 (sTw + m * C + ltB));
             v[m] = cmul_dir<DIR> (v[m], wm);
         }
+    }
+    if (a.peer_row_log >= 0)
+    {
+        // the all-to-all of the distributed transform, done by the stores themselves: every row block goes straight
+        // into its owner's receive buffer, so the NVLink transfer overlaps the butterflies of the other tiles
+        const long long toff = a.peer_chunk_off + ghi * a.out_g_hi + glo * a.out_g_lo + ltB * a.out_tstride;
+        const int mask = (1 << a.peer_row_log) - 1;
+#pragma unroll
+        for (int m = 0; m < R; ++m)
+        {
+            const int k = jB + m * T;
+            a.peer_out[k >> a.peer_row_log][toff + (long long) (k & mask) * a.out_estride] = v[m];
+        }
+        return;
     }
     float2* __restrict__ q = out + ltB * a.out_tstride + jB * a.out_estride;
 #pragma unroll

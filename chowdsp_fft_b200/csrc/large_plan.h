@@ -6,7 +6,8 @@
 namespace cfb
 {
 // adjacent transforms per tile = contiguous complex elements on the strided side of a pass: 16 (one full 128-byte
-// line per element row) whenever the CTA stays at <= 512 threads, 8 (64 bytes) for 1024-point passes
+// line per element row) for the strided passes whenever the CTA stays at <= 512 threads, 8 (64 bytes) for
+// 1024-point passes and for the contiguous-row pass
 constexpr int kTileCMax = 16;
 inline int& tile_c_override() { static int v = 0; return v; }       // tuning hooks (0 = policy below)
 inline int& tile_c_jfast_override() { static int v = 0; return v; } // ... for the contiguous-row (last) pass only
@@ -15,7 +16,7 @@ inline int tile_c (int logL, bool jfast = false)
     const int ov = (jfast && tile_c_jfast_override() != 0) ? tile_c_jfast_override() : tile_c_override();
     if (ov != 0)
         return (ov == 16 && logL > 9) ? 8 : ov;
-    return logL <= 9 ? 16 : 8;
+    return (logL <= 9 && ! jfast) ? 16 : 8; // measured: the contiguous-row pass is faster with 8 (profiles/r01_large_tile_width.txt)
 }
 constexpr int kMinTileLog = 6;   // tile transforms are 64 .. 1024 points
 constexpr int kMaxTileLog = 10;
@@ -76,6 +77,7 @@ inline int build_tile_passes (int n, const LargeFactors& f, TilePass (&p)[3], un
         a.args.tw_mult = tw_scale;
         a.args.batch = 1;
         a.args.in_split_log = 31;
+        a.args.peer_row_log = -1;
     }
     if (f.l2 != 0)
     {   // pass B: for every row k1, columns of its [L2][L3] view
@@ -94,6 +96,7 @@ inline int build_tile_passes (int n, const LargeFactors& f, TilePass (&p)[3], un
         b.args.tw_mult = (unsigned) L1 * tw_scale;
         b.args.batch = 1;
         b.args.in_split_log = 31;
+        b.args.peer_row_log = -1;
     }
     {   // pass C: contiguous rows (k1, k2), written transposed to k1 + L1 (k2 + L2 k3)
         TilePass& c = p[np++];
@@ -115,6 +118,7 @@ inline int build_tile_passes (int n, const LargeFactors& f, TilePass (&p)[3], un
         c.args.tw_mult = 0;
         c.args.batch = 1;
         c.args.in_split_log = 31;
+        c.args.peer_row_log = -1;
     }
     return np;
 }
@@ -141,6 +145,7 @@ inline bool build_dist_phase (int n, const LargeFactors& f, int phase, int rank,
     p.C = kTileC;
     p.args.batch = 1;
     p.args.in_split_log = 31;
+    p.args.peer_row_log = -1;
     (void) N;
     if (phase == 0)
     {
@@ -154,6 +159,9 @@ inline bool build_dist_phase (int n, const LargeFactors& f, int phase, int rank,
         p.args.in_estride = p.args.out_estride = cols;
         p.args.tw_mult = 1;
         p.args.tw_c_base = (unsigned) (rank * cols);
+        // peer-store variant (the caller enables it by setting peer_row_log and peer_out): rank h owns rows
+        // [h L1/world, (h+1) L1/world) and receives them as chunk `rank` of its [world][L1/world][cols] buffer
+        p.args.peer_chunk_off = (long long) rank * (L1 / world) * cols;
     }
     else if (phase == 1)
     {

@@ -1,6 +1,9 @@
 """Distributed four-step FFT: ONE complex transform of N = 2^n points (n >= 21) over G GPUs, one process
-per GPU.  The local phases are C-ABI calls (fft_dist_phase); torch.distributed (NCCL over NVLink) carries
-the all-to-all between phase 0 and phase 1.  See include/chowdsp_fft_b200.h for the data contracts.
+per GPU.  The local phases are C-ABI calls (fft_dist_phase).  The exchange between phase 0 and phase 1 is
+either FUSED into phase 0 (exchange="peer", default: the kernel stores every row block straight into its owner's
+buffer through NVLink peer memory, so the transfer overlaps the butterflies; torch.distributed only carries the
+IPC handles at set-up and a one-element all-reduce as the barrier) or an NCCL all_to_all_single
+(exchange="nccl", the baseline).  See include/chowdsp_fft_b200.h for the data contracts.
 
     input  (per rank)  column block  A[n1][c] = x[n1*S1 + rank*S1/G + c],  shape [L1, S1/G] complex
     output (per rank)  transposed-out  out[q][k] = X[(rank*L1/G + k) + L1*q], shape [S1, L1/G] complex
@@ -15,8 +18,10 @@ from . import api
 
 
 class DistributedFFT:
-    def __init__(self, n: int, rank: int, world: int, group=None):
-        self.n, self.rank, self.world, self.group = n, rank, world, group
+    def __init__(self, n: int, rank: int, world: int, group=None, exchange: str = "peer"):
+        if exchange not in ("peer", "nccl"):
+            raise ValueError("exchange must be 'peer' or 'nccl'")
+        self.n, self.rank, self.world, self.group, self.exchange = n, rank, world, group, exchange
         self.N = 1 << n
         self.plan = api.fft_new_setup(self.N, api.FFT_COMPLEX, True)
         l1, l2, l3 = api.fft_large_factors(self.plan)
@@ -26,9 +31,33 @@ class DistributedFFT:
         self.S1 = self.L2 * self.L3
         self.rows, self.cols = self.L1 // world, self.S1 // world
         dev = torch.device("cuda", torch.cuda.current_device())
-        self.send = torch.empty(self.L1 * self.cols * 2, device=dev)       # phase-0 output / all-to-all source
-        self.recv = torch.empty_like(self.send)                             # exchange layout [G][rows][cols]
         self.nat = torch.empty(self.rows * self.S1 * 2, device=dev)         # natural rows [rows][S1]
+        self.step = 0
+        if exchange == "nccl":
+            self.send = torch.empty(self.L1 * self.cols * 2, device=dev)   # phase-0 output / all-to-all source
+            self.recv = torch.empty_like(self.send)                         # exchange layout [G][rows][cols]
+            return
+        # peer exchange: two receive buffers (step parity) so that one barrier per transform is enough; every rank
+        # maps every other rank's buffers through CUDA IPC
+        nbytes = self.L1 * self.cols * 8
+        self.own = [api.fft_dist_alloc(nbytes) for _ in range(2)]
+        self.mapped: list[int] = []
+        if world > 1:
+            handles: list = [None] * world
+            dist.all_gather_object(handles, [api.fft_dist_ipc_export(p) for p in self.own], group=group)
+            self.peers = []
+            for b in range(2):
+                row = []
+                for h in range(world):
+                    if h == rank:
+                        row.append(self.own[b])
+                    else:
+                        row.append(api.fft_dist_ipc_open(handles[h][b]))
+                        self.mapped.append(row[-1])
+                self.peers.append(row)
+            self.token = torch.zeros(1, device=dev)
+        else:
+            self.peers = [[self.own[0]], [self.own[1]]]
 
     @property
     def local_floats(self) -> int:
@@ -41,12 +70,20 @@ class DistributedFFT:
     def forward(self, x_cols: torch.Tensor, out_t: torch.Tensor, direction: int = api.FFT_FORWARD, stream=None):
         """x_cols: [L1, S1/G] complex as float32 pairs (flat ok); out_t: [S1, L1/G] complex (flat ok)."""
         st = stream or torch.cuda.current_stream()
-        api.fft_dist_phase(self.plan, 0, self.rank, self.world, x_cols, self.send, direction, st)
-        if self.world > 1:
-            dist.all_to_all_single(self.recv, self.send, group=self.group)
-            src = self.recv
+        if self.exchange == "peer":
+            b = self.step & 1
+            self.step += 1
+            api.fft_dist_phase0_peer(self.plan, self.rank, self.world, x_cols, self.peers[b], direction, st)
+            if self.world > 1:
+                dist.all_reduce(self.token, group=self.group)  # stream-ordered barrier: every rank's stores have landed
+            src = self.own[b]
         else:
-            src = self.send
+            api.fft_dist_phase(self.plan, 0, self.rank, self.world, x_cols, self.send, direction, st)
+            if self.world > 1:
+                dist.all_to_all_single(self.recv, self.send, group=self.group)
+                src = self.recv
+            else:
+                src = self.send
         api.fft_dist_phase(self.plan, 1, self.rank, self.world, src, self.nat, direction, st)
         api.fft_dist_phase(self.plan, 2, self.rank, self.world, self.nat, out_t, direction, st)
         return out_t
@@ -63,6 +100,15 @@ class DistributedFFT:
         return got.view(G, self.cols, self.rows, 2).permute(1, 0, 2, 3).reshape(-1)
 
     def close(self):
+        if self.exchange == "peer":
+            torch.cuda.synchronize()
+            if self.world > 1:
+                dist.barrier(group=self.group)  # nobody unmaps or frees while a peer may still be storing
+            for p in self.mapped:
+                api.fft_dist_ipc_close(p)
+            for p in self.own:
+                api.fft_dist_free(p)
+            self.mapped, self.own = [], []
         api.fft_destroy_setup(self.plan)
 
 

@@ -80,6 +80,21 @@ int fft_partitioned_convolve_step (void* setup, const float* windows, long long 
    world must be a power of two with L1/world >= 8.  Device pointers, stream-ordered. */
 int fft_dist_phase (void* setup, int phase, int rank, int world, const float* in, float* out, fft_direction_t direction, void* stream);
 
+/* Phase 0 fused with the exchange: same input contract as fft_dist_phase (phase 0), but every output row block is
+   stored straight into its owner's phase-1 input buffer -- peer_recv[h] is rank h's exchange-layout buffer
+   ([world][L1/world][S1/world] complex) mapped into this process (peer memory over NVLink; peer_recv[rank] is
+   this rank's own buffer).  The all-to-all is done by the kernel's stores and overlaps its butterflies; the
+   caller only needs a barrier across ranks before phase 1 reads the buffers.  world <= 8. */
+int fft_dist_phase0_peer (void* setup, int rank, int world, const float* in, float* const* peer_recv, fft_direction_t direction, void* stream);
+
+/* Peer-memory plumbing for fft_dist_phase0_peer, one process per GPU: device blocks that can be exported to the
+   other ranks (64-byte opaque IPC handle, exchanged by the caller, e.g. over torch.distributed) and mapped there. */
+void* fft_dist_alloc (size_t bytes);
+void fft_dist_free (void* block);
+int fft_dist_ipc_export (void* block, void* handle64);
+void* fft_dist_ipc_open (const void* handle64);
+void fft_dist_ipc_close (void* mapped);
+
 /* log2 of the pass lengths of a multi-pass plan (l2 = 0 for two-pass plans); returns FFT_B200_EINVAL for
    single-kernel plans. */
 int fft_large_factors (void* setup, int* l1, int* l2, int* l3);
@@ -93,7 +108,8 @@ const char* fft_b200_last_error (void);
 void fft_b200_clear_error (void);
 
 /* Tuning hook for benchmarks/sweeps (not needed in normal use): key "tile_c" = transforms per tile of the
-   multi-pass kernels (8, 16, or 0 for the built-in policy); "radix32_mask" bit n = use the 32-points-per-thread kernel for complex length 2^n (n in 9, 10, 13, 14);
+   multi-pass kernels (8, 16, or 0 for the built-in policy); "radix32_mask" bit n (complex plans) / bit 16+n (real plans) = use the 32-points-per-thread kernel for
+   complex length 2^n (n in 9, 10, 13, 14), -1 = built-in default;
    "stft_union" = 1 stages the union of a CTA's
    overlapping frames through shared memory (fewer L2 reads, more shared-memory traffic). */
 int fft_b200_set_tuning (const char* key, int value);

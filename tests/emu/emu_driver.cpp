@@ -298,6 +298,42 @@ int emu_dist_phase (int n, int l1, int l2, int l3, int phase, int rank, int worl
     return emu_tile_dispatch<-1> (p);
 }
 
+// phase 0 with the fused exchange: row block h is stored into outs[h] (exchange layout [world][L1/world][cols])
+int emu_dist_phase0_peer (int n, int l1, int l2, int l3, int rank, int world, const float* in, float* const* outs)
+{
+    LargeFactors f;
+    f.l1 = l1; f.l2 = l2; f.l3 = l3;
+    TilePass p;
+    if (! build_dist_phase (n, f, 0, rank, world, p) || world > 8)
+        return -2;
+    const int lobits = big_twiddle_lobits (n);
+    std::vector<float2> lo ((size_t) 1 << lobits), hi ((size_t) 1 << (n - lobits)), tw;
+    fill_big_twiddles (lo.data(), hi.data(), n, lobits);
+    switch (p.logL)
+    {
+        case 6: fill_tw_for<6> (tw); break;
+        case 7: fill_tw_for<7> (tw); break;
+        case 8: fill_tw_for<8> (tw); break;
+        case 9: fill_tw_for<9> (tw); break;
+        case 10: fill_tw_for<10> (tw); break;
+        default: return -3;
+    }
+    int wl = 0;
+    while ((1 << wl) < world)
+        ++wl;
+    p.args.tw = tw.data();
+    p.args.tw_lo = lo.data();
+    p.args.tw_hi = hi.data();
+    p.args.tw_lobits = lobits;
+    p.args.in = reinterpret_cast<const float2*> (in);
+    p.args.out = nullptr;
+    p.args.peer_row_log = l1 - wl;
+    for (int h = 0; h < world; ++h)
+        p.args.peer_out[h] = reinterpret_cast<float2*> (outs[h]);
+    emu::g_log_smem = false;
+    return emu_tile_dispatch<-1> (p);
+}
+
 int emu_convolve (const float* a, const float* b, float* ab, long long a_stride, long long b_stride, long long ab_stride, int nfloats, int batch, int logW, int is_real, float scaling)
 {
     ConvArgs p { a, b, ab, a_stride, b_stride, ab_stride, nfloats, batch, logW, is_real, scaling };

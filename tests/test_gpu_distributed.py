@@ -21,7 +21,7 @@ def _signal(N):
     return torch.rand(N, 2, generator=g) * 2 - 1  # every rank regenerates the same global signal
 
 
-def _run_rank(rank, world, port, n, q):
+def _run_rank(rank, world, port, n, q, exchange="peer"):
     import torch.distributed as dist
 
     from chowdsp_fft_b200.distributed import DistributedFFT, column_block
@@ -32,7 +32,7 @@ def _run_rank(rank, world, port, n, q):
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     N = 1 << n
     x = _signal(N)
-    d = DistributedFFT(n, rank, world)
+    d = DistributedFFT(n, rank, world, exchange=exchange)
     xc = column_block(x.cuda(), d.L1, d.S1, rank, world)
     out_t = torch.empty(d.S1 * d.rows * 2, device="cuda")
     d.forward(xc, out_t)
@@ -63,23 +63,26 @@ def _run_rank(rank, world, port, n, q):
     return e1, e2, e3
 
 
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
 @pytest.mark.parametrize("n", [21, 23])
-def test_dist_phases_world1(n):
+def test_dist_phases_world1(n, exchange):
     tol = 1e-6 * n
-    e1, e2, e3 = _run_rank(0, 1, 0, n, None)
+    e1, e2, e3 = _run_rank(0, 1, 0, n, None, exchange)
     assert e1 < tol and e2 < tol and e3 < tol, (e1, e2, e3)
 
 
-def test_dist_two_gpus():
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_dist_multi_gpu(world, exchange):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs (gpurun --gpus {world})")
     import torch.multiprocessing as mp
 
-    n, world = 22, 2
+    n = 22 if world == 2 else 24
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_run_rank, args=(r, world, port, n, q)) for r in range(world)]
+    procs = [ctx.Process(target=_run_rank, args=(r, world, port, n, q, exchange)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=300) for _ in range(world))

@@ -164,14 +164,16 @@ def test_batched_equals_loop_of_single_calls(cf, oracle_mod):
         cf.fft_destroy_setup(s)
 
 
+@pytest.mark.parametrize("mask", [0x7FFF7FFF, 0])
 @pytest.mark.parametrize("N,is_c", [(512, True), (1024, True), (8192, True), (16384, True), (1024, False), (2048, False), (16384, False), (32768, False)])
-def test_radix32_geometry(cf, oracle_mod, N, is_c):
-    """The 32-points-per-thread kernels (complex lengths 2^9, 2^10, 2^13, 2^14): every kind and layout vs the oracle."""
+def test_radix32_geometry(cf, oracle_mod, N, is_c, mask):
+    """Complex lengths 2^9, 2^10, 2^13, 2^14 exist as 16- and as 32-points-per-thread kernels (the default picks
+    per size and kind): both, every kind and layout, vs the oracle."""
     o = oracle_mod
     nfl = 2 * N if is_c else N
     rng = np.random.default_rng(N)
     x = rng.uniform(-1, 1, (5, nfl)).astype(np.float32)
-    cf.set_tuning("radix32_mask", 0x7FFF)
+    cf.set_tuning("radix32_mask", mask)
     try:
         for ordered in (True, False):
             f = gpu_transform(cf, x, N, is_c, True, False, ordered)
@@ -180,7 +182,7 @@ def test_radix32_geometry(cf, oracle_mod, N, is_c):
             b = gpu_transform(cf, ref, N, is_c, True, True, ordered, inplace=True)
             assert o.rel_l2(b, o.np_transform(ref, N, is_c, 8, True, ordered)) < o.parity_tol(N)
     finally:
-        cf.set_tuning("radix32_mask", 0)
+        cf.set_tuning("radix32_mask", -1)
 
 
 def test_strided_batches_and_stft_gather(cf, oracle_mod):
