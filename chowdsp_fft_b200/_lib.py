@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libchowdsp_fft_b200.so")
+# CHOWDSP_FFT_B200_LIB selects another build of the same library (A/B tuning experiments, tools/ only)
+LIB_PATH = os.environ.get("CHOWDSP_FFT_B200_LIB") or os.path.join(HERE, "lib", "libchowdsp_fft_b200.so")
 CSRC_DIR = os.path.join(HERE, "csrc")
 
 _fp = C.POINTER(C.c_float)

@@ -320,6 +320,13 @@ struct Staging
 thread_local Staging t_staging;
 
 bool g_stft_union = false; // tuning hook "stft_union"
+// tuning hook "pipe_mask": bit (2 kind + logM - 13) = use the persistent TMA-pipelined kernel (pipe_kernels.cuh) for
+// that kind (C2C_FWD, C2C_BWD, R2C, C2R = 0..3) at complex length 2^13 / 2^14, ordered layouts.  Default from the
+// A/B sweeps in profiles/r01_pipe_kernel.txt: every kind at 2^14 (+25..45 %), only C2R at 2^13 (+8 %; the others tie
+// or lose 3 % against fft_kernel, which runs two CTAs per SM there)
+constexpr unsigned kPipeDefault = 0xAAu | (1u << 6);
+unsigned g_pipe_mask = kPipeDefault;
+bool pipe_enabled (int logM, int kind) { return has_pipe (logM) && ((g_pipe_mask >> (2 * kind + logM - 13)) & 1u) != 0; }
 int g_pf_ahead = 0;        // tuning hook "pf_ahead": L2 prefetch distance of the single-kernel transforms, in CTAs
 
 constexpr size_t kZeroCopyBytes = 256 * 1024;     // pinned buffers up to this size are used in place
@@ -478,10 +485,30 @@ int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inne
         return 0;
     }
     Tables t;
-    const int radix = radix_for (p->logM, p->is_complex != 0);
+    // plain, ordered batches of the two largest single-kernel sizes with 16-byte aligned input rows: persistent
+    // TMA-pipelined kernel (32 points per thread)
+    const bool use_pipe = ordered && window == nullptr && pipe_enabled (p->logM, kind_of (p, direction))
+                          && (outer == 1 || inner == 1) && (reinterpret_cast<uintptr_t> (in) & 15) == 0
+                          && ((outer == 1 ? in_inner : in_outer) & 3) == 0;
+    const int radix = use_pipe ? 32 : radix_for (p->logM, p->is_complex != 0);
     const int rc = plan_tables (p, t, radix);
     if (rc != 0)
         return rc;
+    if (use_pipe)
+    {
+        FftArgs pa {};
+        pa.in = in;
+        pa.out = out;
+        pa.in_inner = outer == 1 ? in_inner : in_outer;
+        pa.out_inner = outer == 1 ? out_inner : out_outer;
+        pa.inner = pa.batch = outer * inner;
+        pa.tw = t.tw;
+        pa.rtw = t.rtw;
+        const cudaError_t ep = launch_pipe (p->logM, kind_of (p, direction), pa, stream);
+        if (ep != cudaSuccess)
+            return fail_cuda (ep, "pipelined fft kernel launch");
+        return 0;
+    }
     FftArgs a {};
     a.in = in;
     a.out = out;
@@ -1080,6 +1107,11 @@ CFB_API int fft_b200_set_tuning (const char* key, int value)
     if (key != nullptr && std::strcmp (key, "tile_c_jfast") == 0 && (value == 0 || value == 8 || value == 16))
     {
         tile_c_jfast_override() = value;
+        return 0;
+    }
+    if (key != nullptr && std::strcmp (key, "pipe_mask") == 0)
+    {
+        g_pipe_mask = value == -1 ? kPipeDefault : (unsigned) value;
         return 0;
     }
     if (key != nullptr && std::strcmp (key, "radix32_mask") == 0)

@@ -37,6 +37,16 @@ cudaError_t launch_pconv (int logM, int logW, const PConvArgs& args, cudaStream_
         default: return cudaErrorInvalidValue;
     }
 }
+bool has_pipe (int logM) { return logM == 13 || logM == 14; }
+cudaError_t launch_pipe (int logM, int kind, const FftArgs& args, cudaStream_t stream)
+{
+    switch (logM)
+    {
+        case 13: return launch_pipe_13 (kind, args, stream);
+        case 14: return launch_pipe_14 (kind, args, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
 bool has_radix32 (int logM)
 {
     switch (logM)

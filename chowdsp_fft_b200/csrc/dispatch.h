@@ -21,6 +21,12 @@ bool has_radix32 (int logM);
 // optional window; one CTA gathers the union of its frames once (stft_kernel)
 cudaError_t launch_stft (int logM, int logW, int radix, const FftArgs& args, cudaStream_t stream);
 int transforms_per_cta (int logM, int radix);
+// persistent TMA-pipelined variant (pipe_kernels.cuh) for complex lengths 2^13 / 2^14, ordered layouts, plain batches
+// (args.inner == args.batch) whose input rows are 16-byte aligned
+bool has_pipe (int logM);
+cudaError_t launch_pipe (int logM, int kind, const FftArgs& args, cudaStream_t stream);
+cudaError_t launch_pipe_13 (int kind, const FftArgs& args, cudaStream_t stream);
+cudaError_t launch_pipe_14 (int kind, const FftArgs& args, cudaStream_t stream);
 // number of float2 entries of the stage twiddle table for 2^logM, and the fill routine (fp64 -> fp32)
 int stage_twiddle_len (int logM, int radix);
 void fill_stage_twiddles_rt (int logM, int radix, float2* tw);

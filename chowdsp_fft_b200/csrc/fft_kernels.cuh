@@ -274,6 +274,38 @@ FFT_HD float2 mul_w32_rt (float2 a, int num)
     }
 }
 
+// cos / sin (pi n / 32), n = 0..32, as compile-time constants (forward twiddles W_64^n = c - i s)
+FFT_CX float cos64 (int n)
+{
+    const bool neg = n > 16;
+    if (neg)
+        n = 32 - n;
+    const float c = n == 0 ? 1.f : n == 1 ? 0.995184726672196886f : n == 2 ? 0.980785280403230449f : n == 3 ? 0.956940335732208865f
+                  : n == 4 ? 0.923879532511286756f : n == 5 ? 0.881921264348355030f : n == 6 ? 0.831469612302545237f
+                  : n == 7 ? 0.773010453362736961f : n == 8 ? 0.707106781186547524f : n == 9 ? 0.634393284163645498f
+                  : n == 10 ? 0.555570233019602225f : n == 11 ? 0.471396736825997649f : n == 12 ? 0.382683432365089772f
+                  : n == 13 ? 0.290284677254462368f : n == 14 ? 0.195090322016128268f : n == 15 ? 0.098017140329560602f : 0.f;
+    return neg ? -c : c;
+}
+FFT_CX float sin64 (int n) { return cos64 (n <= 16 ? 16 - n : n - 16); } // n in [0, 32]
+
+// real split / merge twiddle w_k / 2 of bin k = j + m T (T = M / R).  DERIVE = false: one table load per bin (the
+// faster choice wherever the table stays in L1: measured -5 % with DERIVE on B200, the FMA pipe is the scarcer unit,
+// profiles/r01_real_tw_ab.txt).  DERIVE = true: w_k = w_j W_(2R)^m from the thread's own w_j, a compile-time
+// constant after unrolling -- for kernels whose shared-memory carve-out leaves no L1 for a 64 KB table.
+template <int R, bool DERIVE>
+FFT_HD float2 real_tw (float2 wj, const float2* __restrict__ rt_mT, int m)
+{
+    if (m == 0)
+        return wj;
+    if constexpr (! DERIVE)
+        return __ldg (rt_mT);
+    else if constexpr (R == 16)
+        return mul_w32_rt<-1> (wj, m);
+    else
+        return cmul_dir<-1> (wj, make_float2 (cos64 (m), -sin64 (m)));
+}
+
 // ---------------------------------------------------------------------------------------------
 // register butterflies: in place, natural-order output, elements v[0], v[ST], v[2 ST], ...
 // ---------------------------------------------------------------------------------------------
@@ -817,12 +849,12 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
                 xb[m] = ldg_stream (ph);
             }
         }
-        const float2* __restrict__ rt = a.rtw + j;
+        const float2 wj = __ldg (a.rtw + j);
 #pragma unroll
         for (int m = 0; m < R / 2; ++m)
         {
             const float2 xa = v[m], xm = xb[m];
-            const float2 wh = __ldg (rt + m * T);                          // w_k / 2
+            const float2 wh = real_tw<R, false> (wj, a.rtw + j + m * T, m);                         // w_k / 2
             const float2 cm = make_float2 (xm.x, -xm.y);                   // conj X[M-k]
             const float2 e = f2_add (xa, cm), d = f2_sub (xa, cm);
             const float2 wd = cmul_dir<+1> (d, wh);                        // conj(w_k) d / 2
@@ -885,14 +917,14 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
             zb[m] = lds2 (s + ((m == 0 && j == 0) ? G::pad (M / 2) : mirror_slot<G> (j, m)));
         if constexpr (UNORD)
             __syncthreads(); // natural-order image fully consumed before the staging image overwrites it
-        const float2* __restrict__ rt = a.rtw + j;
+        const float2 wj = __ldg (a.rtw + j);
         float2* __restrict__ lo = reinterpret_cast<float2*> (out) + j;
         float2* __restrict__ hi = reinterpret_cast<float2*> (out) + (M - T) - j;
 #pragma unroll
         for (int m = 0; m < R / 2; ++m)
         {
             const float2 za = v[m], zm = zb[m];
-            const float2 wh = __ldg (rt + m * T);                          // w_k / 2
+            const float2 wh = real_tw<R, false> (wj, a.rtw + j + m * T, m);                         // w_k / 2
             const float2 cm = make_float2 (zm.x, -zm.y);                   // conj Z[M-k]
             const float2 e = f2_add (za, cm), d = f2_sub (za, cm);         // 2E, 2D
             const float2 wd = cmul_dir<-1> (d, wh);                        // w_k D

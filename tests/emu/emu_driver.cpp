@@ -5,6 +5,7 @@
 #include "fft_kernels.cuh"
 #include "elementwise_kernels.cuh"
 #include "pconv_kernel.cuh"
+#include "pipe_kernels.cuh"
 #include "large_plan.h"
 
 using namespace cfb;
@@ -141,6 +142,47 @@ int emu_fft (int logM, int kind, int unord, int logW, const float* in, float* ou
         case 14: rc = run_logm<14> (kind, unord ? logW : 0, a); break;
         default: break;
     }
+    if (stats)
+    {
+        stats[0] = emu::g_stats.ops;
+        stats[1] = emu::g_stats.wavefronts;
+        stats[2] = emu::g_stats.ideal;
+        stats[3] = emu::g_stats.worst;
+    }
+    return rc;
+}
+
+// persistent TMA-pipelined transform (pipe_kernels.cuh): `grid` resident CTAs loop over `batch` contiguous transforms
+int emu_pipe (int logM, int kind, const float* in, float* out, int batch, int grid, int log_conflicts, long* stats)
+{
+    auto run = [&] (auto logm_c) -> int
+    {
+        constexpr int LOGM = decltype (logm_c)::value;
+        using P = PipeGeo<LOGM>;
+        using G = typename P::G;
+        std::vector<float2> tw ((size_t) G::TW_LEN + 1), rtw ((size_t) G::M / 2 + 1);
+        fill_stage_twiddles<LOGM, 32> (tw.data());
+        fill_real_twiddles (rtw.data(), G::M);
+        FftArgs a {};
+        a.in = in; a.out = out;
+        a.in_inner = a.out_inner = (kind >= 2 ? 2 : 2) * (long long) G::M;
+        a.inner = batch; a.batch = batch;
+        a.tw = tw.data(); a.rtw = rtw.data();
+        switch (kind)
+        {
+            case 0: emu::launch (pipe_kernel<LOGM, C2C_FWD>, dim3 ((unsigned) grid), dim3 (P::T), (size_t) P::SMEM_BYTES, a); break;
+            case 1: emu::launch (pipe_kernel<LOGM, C2C_BWD>, dim3 ((unsigned) grid), dim3 (P::T), (size_t) P::SMEM_BYTES, a); break;
+            case 2: emu::launch (pipe_kernel<LOGM, R2C>, dim3 ((unsigned) grid), dim3 (P::T), (size_t) P::SMEM_BYTES, a); break;
+            case 3: emu::launch (pipe_kernel<LOGM, C2R>, dim3 ((unsigned) grid), dim3 (P::T), (size_t) P::SMEM_BYTES, a); break;
+            default: return -1;
+        }
+        return 0;
+    };
+    emu::g_log_smem = log_conflicts != 0;
+    emu::g_stats = {};
+    int rc = -1;
+    if (logM == 13) rc = run (std::integral_constant<int, 13> {});
+    if (logM == 14) rc = run (std::integral_constant<int, 14> {});
     if (stats)
     {
         stats[0] = emu::g_stats.ops;

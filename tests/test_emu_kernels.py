@@ -18,6 +18,7 @@ def emu():
     L.emu_fft.argtypes = [C.c_int] * 4 + [fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 4 + [C.c_int, C.POINTER(C.c_long)]
     L.emu_convolve.argtypes = [fp, fp, fp] + [C.c_longlong] * 3 + [C.c_int] * 4 + [C.c_float]
     L.emu_accumulate.argtypes = [fp, fp, fp, C.c_longlong]
+    L.emu_pipe.argtypes = [C.c_int, C.c_int, fp, fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_long)]
     L.emu_stft.argtypes = [C.c_int] * 3 + [fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 4 + [fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_long)]
     return L
 
@@ -96,6 +97,29 @@ def test_emulated_radix32_geometry(emu, oracle_mod, N, is_c):
                     assert s[1] <= 1.10 * s[2] and s[3] <= 200, s
     finally:
         emu.emu_set_radix(16)
+
+
+@pytest.mark.parametrize("N,is_c", [(8192, True), (16384, True), (16384, False), (32768, False)])
+def test_emulated_pipelined_kernel(emu, oracle_mod, N, is_c):
+    """The persistent TMA-pipelined kernel (2^13 / 2^14 complex points): 3 transforms on 2 resident CTAs, so one
+    CTA runs two loop iterations (landing-buffer reuse, barrier phases) and the other one; ordered layouts."""
+    o = oracle_mod
+    nfl = 2 * N if is_c else N
+    logM = int(np.log2(N)) - (0 if is_c else 1)
+    batch, grid = 3, 2
+    rng = np.random.default_rng(N + 77)
+    x = rng.uniform(-1, 1, (batch, nfl)).astype(np.float32)
+    ref = o.np_transform(x, N, is_c, 8, False, True)
+    st = (C.c_long * 4)()
+    f = np.zeros_like(x)
+    assert emu.emu_pipe(logM, 0 if is_c else 2, x.ctypes.data_as(fp), f.ctypes.data_as(fp), batch, grid, 1, st) == 0
+    assert o.rel_l2(f, ref) < 4e-7
+    assert st[1] <= 1.05 * st[2] and st[3] <= 200, list(st)
+    b = np.zeros_like(x)
+    refc = np.ascontiguousarray(ref, np.float32)
+    assert emu.emu_pipe(logM, 1 if is_c else 3, refc.ctypes.data_as(fp), b.ctypes.data_as(fp), batch, grid, 1, st) == 0
+    assert o.rel_l2(b, o.np_transform(ref, N, is_c, 8, True, True)) < 4e-7
+    assert st[1] <= 1.05 * st[2] and st[3] <= 200, list(st)
 
 
 def test_emulated_impulse_and_tone_positions(emu, oracle_mod):

@@ -185,6 +185,46 @@ def test_radix32_geometry(cf, oracle_mod, N, is_c, mask):
         cf.set_tuning("radix32_mask", -1)
 
 
+@pytest.mark.parametrize("mask", [0xFF, 0])
+@pytest.mark.parametrize("N,is_c", [(8192, True), (16384, True), (16384, False), (32768, False)])
+def test_pipelined_kernel(cf, oracle_mod, N, is_c, mask):
+    """Complex lengths 2^13 / 2^14, ordered: the persistent TMA-pipelined kernel (mask 0xFF = every kind) and
+    fft_kernel (mask 0) against the oracle.  The batch exceeds the resident CTA count (so CTAs loop, with a ragged
+    last round), in place and out of place; a row stride that breaks the 16-byte alignment TMA needs must fall
+    back to fft_kernel and still be right."""
+    o = oracle_mod
+    nfl = 2 * N if is_c else N
+    rng = np.random.default_rng(N + 5)
+    batch = 2 * 148 * 2 + 7
+    x = rng.uniform(-1, 1, (batch, nfl)).astype(np.float32)
+    sub = np.r_[0:3, 147:150, 295:299, batch - 3:batch]  # first / second / third round of the persistent loop
+    ref = o.np_transform(x[sub], N, is_c, 8, False, True)
+    cf.set_tuning("pipe_mask", mask)
+    try:
+        f = gpu_transform(cf, x, N, is_c, True, False, True)
+        assert o.rel_l2(f[sub], ref) < o.parity_tol(N)
+        assert np.array_equal(gpu_transform(cf, x, N, is_c, True, False, True, inplace=True), f)
+        b = gpu_transform(cf, f, N, is_c, True, True, True)
+        assert o.rel_l2(b / N, x) < o.parity_tol(N)
+        assert o.rel_l2(b[sub], o.np_transform(f[sub], N, is_c, 8, True, True)) < o.parity_tol(N)
+        # rows 8 bytes off a 16-byte boundary: not a TMA source
+        s = cf.fft_new_setup(N, cf.FFT_COMPLEX if is_c else cf.FFT_REAL, True)
+        try:
+            n0 = cf.launch_count()
+            buf = torch.zeros(4 * (nfl + 2) + 2, device="cuda")
+            xin = buf[2:].as_strided((4, nfl), (nfl + 2, 1))
+            xin.copy_(dev(x[:4]))
+            out = torch.empty(4, nfl, device="cuda")
+            cf.fft_transform_batched(s, xin, out, 4, nfl + 2, nfl, cf.FFT_FORWARD, True)
+            torch.cuda.synchronize()
+            assert cf.launch_count() - n0 == 1
+            assert o.rel_l2(host(out), o.np_transform(x[:4], N, is_c, 8, False, True)) < o.parity_tol(N)
+        finally:
+            cf.fft_destroy_setup(s)
+    finally:
+        cf.set_tuning("pipe_mask", -1)
+
+
 def test_strided_batches_and_stft_gather(cf, oracle_mod):
     o = oracle_mod
     N, hop, channels, frames = 2048, 512, 3, 9

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--json", default="")
     ap.add_argument("--radix32-mask", type=int, default=-1)
     ap.add_argument("--kinds", default="c,r")
+    ap.add_argument("--tune", action="append", default=[], metavar="KEY=VALUE")
     args = ap.parse_args()
     try:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -30,6 +31,10 @@ def main():
     if args.radix32_mask >= 0:
         cf.set_tuning("radix32_mask", args.radix32_mask)
         print("radix32_mask:", args.radix32_mask)
+    for kv in args.tune:
+        k, v = kv.split("=")
+        cf.set_tuning(k, int(v, 0))
+        print("tune:", k, v)
     total_floats = int(args.bytes * 2**30 / 4)
     x = torch.rand(total_floats, device="cuda") * 2 - 1
     y = torch.empty_like(x)
