@@ -559,6 +559,7 @@ WORKLOADS = {
     "c2c1024": lambda: BatchedFFT("c2c1024", 1024, True, 262144, True, "batched C2C N=1024 x 262144 fp32, ordered, forward"),
     "c2c8192": lambda: BatchedFFT("c2c8192", 8192, True, 32768, True, "batched C2C N=8192 x 32768 fp32, ordered, forward"),
     "c2c16384": lambda: BatchedFFT("c2c16384", 16384, True, 16384, True, "batched C2C N=16384 x 16384 fp32, ordered, forward"),
+    "c2c16384_unordered": lambda: BatchedFFT("c2c16384_unordered", 16384, True, 16384, False, "batched C2C N=16384 x 16384 fp32, unordered, forward"),
     "r2c2048": lambda: BatchedFFT("r2c2048", 2048, False, 524288, True, "batched R2C N=2048 x 524288 fp32, ordered, forward"),
     "r2c8192": lambda: BatchedFFT("r2c8192", 8192, False, 131072, False, "batched R2C N=8192 x 131072 fp32, unordered, forward"),
     "single1024": Single1024,

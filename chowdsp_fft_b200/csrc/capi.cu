@@ -320,13 +320,22 @@ struct Staging
 thread_local Staging t_staging;
 
 bool g_stft_union = false; // tuning hook "stft_union"
+// tuning hook "stft_pipe": persistent TMA-fed frame gather (stft_pipe_kernel) where it applies.  Off by default: at
+// hop = N/4 it is 5 % slower on B200 than per-transform loads once the transforms synchronise at warp level (its
+// per-item CTA barrier re-couples the warps; profiles/r01_stft.txt); it moves 2.9x fewer L2 -> SM bytes, so it is
+// kept for parts / hops where that traffic is the bound
+bool g_stft_pipe = false;
 // tuning hook "pipe_mask": bit (2 kind + logM - 13) = use the persistent TMA-pipelined kernel (pipe_kernels.cuh) for
-// that kind (C2C_FWD, C2C_BWD, R2C, C2R = 0..3) at complex length 2^13 / 2^14, ordered layouts.  Default from the
-// A/B sweeps in profiles/r01_pipe_kernel.txt: every kind at 2^14 (+25..45 %), only C2R at 2^13 (+8 %; the others tie
-// or lose 3 % against fft_kernel, which runs two CTAs per SM there)
-constexpr unsigned kPipeDefault = 0xAAu | (1u << 6);
+// that kind (C2C_FWD, C2C_BWD, R2C, C2R = 0..3) at complex length 2^13 / 2^14, ordered layouts; bits 8..15 the same
+// for the 8-lane unordered layout.  Default from the
+// A/B sweeps in profiles/r01_pipe_kernel.txt: everything at 2^14 (+20..50 %); at 2^13, where fft_kernel already runs
+// two CTAs per SM, +2..7 % except ordered R2C (-3..5 %), which stays with fft_kernel
+constexpr unsigned kPipeDefault = 0xFFFFu & ~(1u << 4);
 unsigned g_pipe_mask = kPipeDefault;
-bool pipe_enabled (int logM, int kind) { return has_pipe (logM) && ((g_pipe_mask >> (2 * kind + logM - 13)) & 1u) != 0; }
+bool pipe_enabled (int logM, int kind, int logW)
+{
+    return has_pipe (logM) && (logW == 0 || logW == 3) && ((g_pipe_mask >> ((logW == 0 ? 0 : 8) + 2 * kind + logM - 13)) & 1u) != 0;
+}
 int g_pf_ahead = 0;        // tuning hook "pf_ahead": L2 prefetch distance of the single-kernel transforms, in CTAs
 
 constexpr size_t kZeroCopyBytes = 256 * 1024;     // pinned buffers up to this size are used in place
@@ -487,7 +496,7 @@ int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inne
     Tables t;
     // plain, ordered batches of the two largest single-kernel sizes with 16-byte aligned input rows: persistent
     // TMA-pipelined kernel (32 points per thread)
-    const bool use_pipe = ordered && window == nullptr && pipe_enabled (p->logM, kind_of (p, direction))
+    const bool use_pipe = window == nullptr && pipe_enabled (p->logM, kind_of (p, direction), ordered ? 0 : p->logW)
                           && (outer == 1 || inner == 1) && (reinterpret_cast<uintptr_t> (in) & 15) == 0
                           && ((outer == 1 ? in_inner : in_outer) & 3) == 0;
     const int radix = use_pipe ? 32 : radix_for (p->logM, p->is_complex != 0);
@@ -504,7 +513,7 @@ int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inne
         pa.inner = pa.batch = outer * inner;
         pa.tw = t.tw;
         pa.rtw = t.rtw;
-        const cudaError_t ep = launch_pipe (p->logM, kind_of (p, direction), pa, stream);
+        const cudaError_t ep = launch_pipe (p->logM, kind_of (p, direction), ordered ? 0 : p->logW, pa, stream);
         if (ep != cudaSuccess)
             return fail_cuda (ep, "pipelined fft kernel launch");
         return 0;
@@ -525,6 +534,19 @@ int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inne
     // the union-staging variant is selected (it is slower on B200, see stft_kernel)
     const bool fwd_real = ! p->is_complex && direction == chowdsp::fft::FFT_FORWARD;
     const bool union_ok = in_inner > 0 && in_inner <= p->N;
+    // overlapping (or windowed) frames of 16-byte aligned signals: persistent kernel, the union of a CTA's frames
+    // arrives by TMA while the previous frames are transformed
+    if (g_stft_pipe && fwd_real && union_ok && inner > 1 && (in_inner < p->N || window != nullptr) && (in_inner & 3) == 0 && (in_outer & 3) == 0
+        && (reinterpret_cast<uintptr_t> (in) & 15) == 0)
+    {
+        a.window = window;
+        const cudaError_t es = launch_stft_pipe (p->logM, ordered ? 0 : p->logW, radix, a, stream);
+        if (es == cudaSuccess)
+            return 0;
+        if (es != cudaErrorInvalidConfiguration) // = does not fit in shared memory at this hop: use the kernels below
+            return fail_cuda (es, "persistent stft kernel launch");
+        (void) cudaGetLastError();
+    }
     if (fwd_real && (in_inner & 1) == 0 && (in_outer & 1) == 0
         && (window != nullptr || (g_stft_union && union_ok && in_inner < p->N && inner > 1 && transforms_per_cta (p->logM, radix) > 1)))
     {
@@ -1122,6 +1144,11 @@ CFB_API int fft_b200_set_tuning (const char* key, int value)
     if (key != nullptr && std::strcmp (key, "pf_ahead") == 0 && value >= 0)
     {
         g_pf_ahead = value;
+        return 0;
+    }
+    if (key != nullptr && std::strcmp (key, "stft_pipe") == 0)
+    {
+        g_stft_pipe = value != 0;
         return 0;
     }
     if (key != nullptr && std::strcmp (key, "stft_union") == 0)

@@ -38,12 +38,12 @@ cudaError_t launch_pconv (int logM, int logW, const PConvArgs& args, cudaStream_
     }
 }
 bool has_pipe (int logM) { return logM == 13 || logM == 14; }
-cudaError_t launch_pipe (int logM, int kind, const FftArgs& args, cudaStream_t stream)
+cudaError_t launch_pipe (int logM, int kind, int logW, const FftArgs& args, cudaStream_t stream)
 {
     switch (logM)
     {
-        case 13: return launch_pipe_13 (kind, args, stream);
-        case 14: return launch_pipe_14 (kind, args, stream);
+        case 13: return launch_pipe_13 (kind, logW, args, stream);
+        case 14: return launch_pipe_14 (kind, logW, args, stream);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -64,6 +64,17 @@ cudaError_t launch_stft (int logM, int logW, int radix, const FftArgs& args, cud
     {
 #define X(n) \
     case n: return launch_stft_##n (logW, radix, args, stream);
+        CFB_FOR_SIZES (X)
+#undef X
+        default: return cudaErrorInvalidValue;
+    }
+}
+cudaError_t launch_stft_pipe (int logM, int logW, int radix, const FftArgs& args, cudaStream_t stream)
+{
+    switch (logM)
+    {
+#define X(n) \
+    case n: return launch_stft_pipe_##n (logW, radix, args, stream);
         CFB_FOR_SIZES (X)
 #undef X
         default: return cudaErrorInvalidValue;

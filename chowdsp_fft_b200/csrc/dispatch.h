@@ -20,13 +20,16 @@ bool has_radix32 (int logM);
 // frame-gather R2C (STFT analysis): transform (o, i) reads in + o in_outer + i in_inner with 0 < in_inner <= N,
 // optional window; one CTA gathers the union of its frames once (stft_kernel)
 cudaError_t launch_stft (int logM, int logW, int radix, const FftArgs& args, cudaStream_t stream);
+// persistent TMA-fed variant (stft_pipe_kernel): needs 0 < in_inner <= N, in_inner % 4 == 0, in_outer % 4 == 0 and a
+// 16-byte aligned signal; returns cudaErrorInvalidConfiguration when its buffers do not fit in shared memory
+cudaError_t launch_stft_pipe (int logM, int logW, int radix, const FftArgs& args, cudaStream_t stream);
 int transforms_per_cta (int logM, int radix);
-// persistent TMA-pipelined variant (pipe_kernels.cuh) for complex lengths 2^13 / 2^14, ordered layouts, plain batches
+// persistent TMA-pipelined variant (pipe_kernels.cuh) for complex lengths 2^13 / 2^14, logW 0 or 3, plain batches
 // (args.inner == args.batch) whose input rows are 16-byte aligned
 bool has_pipe (int logM);
-cudaError_t launch_pipe (int logM, int kind, const FftArgs& args, cudaStream_t stream);
-cudaError_t launch_pipe_13 (int kind, const FftArgs& args, cudaStream_t stream);
-cudaError_t launch_pipe_14 (int kind, const FftArgs& args, cudaStream_t stream);
+cudaError_t launch_pipe (int logM, int kind, int logW, const FftArgs& args, cudaStream_t stream);
+cudaError_t launch_pipe_13 (int kind, int logW, const FftArgs& args, cudaStream_t stream);
+cudaError_t launch_pipe_14 (int kind, int logW, const FftArgs& args, cudaStream_t stream);
 // number of float2 entries of the stage twiddle table for 2^logM, and the fill routine (fp64 -> fp32)
 int stage_twiddle_len (int logM, int radix);
 void fill_stage_twiddles_rt (int logM, int radix, float2* tw);
@@ -51,6 +54,7 @@ void count_launch();
     cudaError_t launch_fft_##n (int kind, int logW, int radix, const FftArgs& args, cudaStream_t stream); \
     cudaError_t launch_pconv_##n (int logW, const PConvArgs& args, cudaStream_t stream);           \
     cudaError_t launch_stft_##n (int logW, int radix, FftArgs args, cudaStream_t stream);          \
+    cudaError_t launch_stft_pipe_##n (int logW, int radix, const FftArgs& args, cudaStream_t stream); \
     int transforms_per_cta_##n (int radix);                                                    \
     int has_radix32_##n();                                                                     \
     int stage_twiddle_len_##n (int radix);                                                     \

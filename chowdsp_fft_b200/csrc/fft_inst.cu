@@ -4,6 +4,7 @@
 #error "compile with -DCFB_LOGM=<4..14>"
 #endif
 #include "dispatch.h"
+#include "pipe_kernels.cuh"
 
 // sizes that also get the 32-points-per-thread geometry (one shared-memory exchange fewer than with 16)
 #if CFB_LOGM == 9 || CFB_LOGM == 10 || CFB_LOGM == 13 || CFB_LOGM == 14
@@ -150,6 +151,71 @@ cudaError_t launch_stft_r (int logW, FftArgs a, cudaStream_t stream)
     }
 }
 } // namespace
+
+namespace
+{
+template <int R, int LOGW>
+cudaError_t launch_stft_pipe_one (FftArgs a, cudaStream_t stream)
+{
+    using SP = StftPipeGeo<CFB_LOGM, R, LOGW>;
+    using L = Launch<CFB_LOGM, R>;
+    auto kernel = stft_pipe_kernel<CFB_LOGM, R, LOGW>;
+    a.groups = (a.inner + L::PER_CTA - 1) / L::PER_CTA;
+    a.land_bytes = SP::land_bytes (a.in_inner);
+    const int smem_bytes = SP::smem_bytes (a.in_inner);
+    if (smem_bytes > 227 * 1024)
+        return cudaErrorInvalidConfiguration;
+    if (a.batch <= 0)
+        return cudaSuccess;
+    // resident CTAs for this (device, landing size); the attribute and the occupancy query are cached per thread
+    static thread_local int c_dev = -1, c_smem = -1, c_resident = 0;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice (&dev);
+    if (e != cudaSuccess)
+        return e;
+    if (dev != c_dev || smem_bytes != c_smem)
+    {
+        int sms = 0, per_sm = 0;
+        if ((e = cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)) != cudaSuccess
+            || (e = cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess
+            || (e = cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, kernel, L::THREADS, (size_t) smem_bytes)) != cudaSuccess)
+            return e;
+        if (per_sm < 1)
+            return cudaErrorInvalidConfiguration;
+        c_dev = dev;
+        c_smem = smem_bytes;
+        c_resident = sms * per_sm;
+    }
+    const long long items = (long long) (a.batch / a.inner) * a.groups;
+    const long long resident = c_resident;
+    kernel<<<(unsigned) (items < resident ? items : resident), L::THREADS, smem_bytes, stream>>> (a);
+    count_launch();
+    return cudaGetLastError();
+}
+template <int R>
+cudaError_t launch_stft_pipe_r (int logW, const FftArgs& a, cudaStream_t stream)
+{
+    switch (logW)
+    {
+        case 0: return launch_stft_pipe_one<R, 0> (a, stream);
+        case 2: return launch_stft_pipe_one<R, 2> (a, stream);
+#if CFB_LOGM >= 6
+        case 3: return launch_stft_pipe_one<R, 3> (a, stream);
+#endif
+        default: return cudaErrorInvalidValue;
+    }
+}
+} // namespace
+
+// persistent TMA-fed frame-gather R2C (stft_pipe_kernel); fills in a.groups and a.land_bytes
+cudaError_t CFB_CAT (launch_stft_pipe_, CFB_LOGM) (int logW, int radix, const FftArgs& a, cudaStream_t stream)
+{
+#if CFB_HAS_R32
+    if (radix == 32)
+        return launch_stft_pipe_r<32> (logW, a, stream);
+#endif
+    return radix == 16 ? launch_stft_pipe_r<16> (logW, a, stream) : cudaErrorInvalidValue;
+}
 
 // frame-gather R2C (STFT analysis); fills in a.groups
 cudaError_t CFB_CAT (launch_stft_, CFB_LOGM) (int logW, int radix, FftArgs a, cudaStream_t stream)

@@ -63,6 +63,8 @@ struct FftArgs
     // L2 prefetch distance in CTAs (0 = off): a CTA asks L2 for the input of CTA blockIdx.x + pf_ahead, about one
     // wave of resident CTAs ahead, so that the loads of a later CTA on this SM find their lines in L2
     int pf_ahead;
+    // persistent frame-gather kernel (stft_pipe_kernel): bytes of its landing buffer, ((PER_CTA - 1) hop + N) * 4
+    int land_bytes;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -595,21 +597,60 @@ FFT_HD int mirror_slot (int j, int m)
         return G::pad (G::M - j - m * G::T);
 }
 
-template <class G, int DIR, int STAGE>
+// barrier among the T threads of ONE transform whose shared-memory region is private to it (PRIV): a warp-level
+// barrier when the transform fits in a warp, a named barrier (one id per transform of the CTA) for 64 or 128
+// threads, the CTA barrier otherwise.  The transforms of a CTA then stop marching in lock step through their load /
+// exchange / math phases (ncu on the STFT config: 16 resident warps per SM, barrier + phase-aligned MIO and
+// math-pipe stalls; +5..13 % on B200, profiles/r01_transform_barriers.txt).  PRIV = false is the CTA-wide barrier.
+template <int T, bool PRIV>
+FFT_HD void tsync()
+{
+    constexpr int MODE = ! PRIV ? 0 : T <= 32 ? 1 : T < 256 ? 2 : 0;
+#ifdef CHOWDSP_EMU
+    if (MODE == 1)
+        emu::syncgroup (32);
+    else if (MODE == 2)
+        emu::syncgroup (T);
+    else
+        __syncthreads();
+#elif defined(CFB_NO_WARP_SYNC) // A/B switch (tools/ only)
+    __syncthreads();
+#else
+    if (MODE == 1)
+        __syncwarp();
+    else if (MODE == 2)
+        asm volatile ("bar.sync %0, %1;" ::"r"(1 + (int) threadIdx.x / T), "n"(T) : "memory"); // ids 1 .. 256 / T <= 4
+    else
+        __syncthreads();
+#endif
+}
+
+struct NoHook
+{
+    FFT_HD void operator() () const {}
+};
+// WS: the transform's barriers may be warp-level (see tsync); CTA_FIRST: ... except the first one, which also
+// orders the other transforms' reads of a CTA-wide input image (IN_UNION) before this transform's exchange writes
+template <class G, int DIR, int STAGE, bool WS = false, bool CTA_FIRST = true>
 struct Stages
 {
-    // from_smem: v was gathered from shared memory just before (a barrier is needed before overwriting it)
-    static FFT_HD void run (float2 (&v)[G::R], int j, float2* s, const float2* __restrict__ tw, bool from_smem)
+    // from_smem: v was gathered from shared memory just before (a barrier is needed before overwriting it).
+    // `input_consumed` runs once, right after the first barrier: every thread of the CTA has then taken its
+    // stage-0 input out of shared memory (the persistent kernels start the next input copy there).
+    template <class Hook = NoHook>
+    static FFT_HD void run (float2 (&v)[G::R], int j, float2* s, const float2* __restrict__ tw, bool from_smem, const Hook& input_consumed = Hook())
     {
         stage_compute<G, DIR, STAGE> (v, j, tw);
         if constexpr (STAGE < G::S - 1)
         {
             if (STAGE > 0 || from_smem)
-                __syncthreads(); // every thread has finished reading the previous exchange
+                tsync<G::T, WS && ! (STAGE == 0 && CTA_FIRST)>(); // every thread has finished reading the previous exchange
+            if constexpr (STAGE == 0)
+                input_consumed();
             stage_scatter<G, STAGE> (v, j, s);
-            __syncthreads();
+            tsync<G::T, WS>();
             gather_natural<G, 0, G::R> (v, j, s);
-            Stages<G, DIR, STAGE + 1>::run (v, j, s, tw, true);
+            Stages<G, DIR, STAGE + 1, WS, CTA_FIRST>::run (v, j, s, tw, true);
         }
     }
 };
@@ -754,14 +795,17 @@ FFT_HD void staging_drain (const float* sf, float* __restrict__ out, int j, int 
 //   HALF_OUT   (C2R only): store only the second half of the output samples (overlap-save discard)
 //   IN_UNION   (R2C / C2C_FWD): the stage-0 input is read from the shared-memory image `su` (natural order,
 //              unpadded, float2 units; it may alias `s`) and multiplied by the window `win` when non-null
-template <int LOGM, int R, int KIND, int LOGW, bool IN_STAGED, bool OUT_STAGED, bool HALF_OUT, bool IN_UNION = false>
+//   input_consumed (IN_UNION with more than one stage): hook run after the barrier that follows the stage-0 reads
+template <int LOGM, int R, int KIND, int LOGW, bool IN_STAGED, bool OUT_STAGED, bool HALF_OUT, bool IN_UNION = false, class Hook = NoHook>
 FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, bool active, int j, float2* s, const float2* __restrict__ tw_, const float2* __restrict__ rtw_,
-                      const float2* su = nullptr, const float2* __restrict__ win = nullptr)
+                      const float2* su = nullptr, const float2* __restrict__ win = nullptr, const Hook& input_consumed = Hook())
 {
     using G = Geo<LOGM, R>;
     constexpr int DIR = (KIND == C2C_FWD || KIND == R2C) ? -1 : +1;
     constexpr bool UNORD = LOGW != 0; // 0 = ordered; 2 / 3 = the reference's 4- / 8-lane unordered layout
     constexpr int M = G::M, T = G::T;
+    // transforms that own their shared-memory region synchronise among their own threads only (tsync)
+    constexpr bool WS = ! IN_STAGED && ! OUT_STAGED;
     float* sf = reinterpret_cast<float*> (s); // the same buffer seen as the unordered staging image
     constexpr int logW = LOGW;
     struct { const float2* tw; const float2* rtw; } a { tw_, rtw_ };
@@ -810,7 +854,7 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
         if constexpr (! IN_STAGED)
         {
             staging_fill<G> (sf, in, j, logW, active);
-            __syncthreads();
+            tsync<T, WS>();
         }
 #pragma unroll
         for (int m = 0; m < R; ++m)
@@ -827,7 +871,7 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
             if constexpr (! IN_STAGED)
             {
                 staging_fill<G> (sf, in, j, logW, active);
-                __syncthreads();
+                tsync<T, WS>();
             }
 #pragma unroll
             for (int m = 0; m < R / 2; ++m)
@@ -835,7 +879,7 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
                 v[m] = staged_load (sf, up.real_lo (m), WL);
                 xb[m] = staged_load (sf, (m == 0 && j == 0) ? W_HALF_ROW<LOGW>() : up.real_hi (m), WL);
             }
-            __syncthreads(); // staging image fully consumed before the natural-order image overwrites it
+            tsync<T, WS>(); // staging image fully consumed before the natural-order image overwrites it
         }
         else
         {
@@ -871,13 +915,13 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
             v[m] = zk;
             sts2 (s + slot, zm);
         }
-        __syncthreads();
+        tsync<T, WS>();
         gather_natural<G, R / 2, R> (v, j, s);
         smem_was_read = true;
     }
 
     // ---- the stages -----------------------------------------------------------------------------
-    Stages<G, DIR, 0>::run (v, j, s, a.tw, smem_was_read);
+    Stages<G, DIR, 0, WS, IN_UNION>::run (v, j, s, a.tw, smem_was_read, input_consumed);
     if (G::S > 1)
         smem_was_read = true;
 
@@ -895,11 +939,11 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
     else if constexpr (KIND == C2C_FWD)
     {
         if (smem_was_read)
-            __syncthreads();
+            tsync<T, WS>();
 #pragma unroll
         for (int m = 0; m < R; ++m)
             staged_store (sf, up.cplx (m), WL, v[m]);
-        __syncthreads();
+        tsync<T, WS>();
         if constexpr (! OUT_STAGED)
             staging_drain<G> (sf, out, j, logW, active);
     }
@@ -908,15 +952,15 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
         // Z[k], k = j + m T < M/2, is this thread's register m; Z[M-k] is register R-1-m of thread T-j:
         // only the upper half of the spectrum goes through shared memory.
         if (smem_was_read)
-            __syncthreads();
+            tsync<T, WS && ! (IN_UNION && G::S == 1)>();
         scatter_natural<G, R / 2, R> (v, j, s);
-        __syncthreads();
+        tsync<T, WS>();
         float2 zb[R / 2];
 #pragma unroll
         for (int m = 0; m < R / 2; ++m)
             zb[m] = lds2 (s + ((m == 0 && j == 0) ? G::pad (M / 2) : mirror_slot<G> (j, m)));
         if constexpr (UNORD)
-            __syncthreads(); // natural-order image fully consumed before the staging image overwrites it
+            tsync<T, WS>(); // natural-order image fully consumed before the staging image overwrites it
         const float2 wj = __ldg (a.rtw + j);
         float2* __restrict__ lo = reinterpret_cast<float2*> (out) + j;
         float2* __restrict__ hi = reinterpret_cast<float2*> (out) + (M - T) - j;
@@ -950,7 +994,7 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
         }
         if constexpr (UNORD)
         {
-            __syncthreads();
+            tsync<T, WS>();
             if constexpr (! OUT_STAGED)
                 staging_drain<G> (sf, out, j, logW, active);
         }

@@ -26,11 +26,11 @@ int sm_count()
     return cached_sms;
 }
 
-template <int KIND>
+template <int KIND, int LOGW>
 cudaError_t launch_pipe_one (const FftArgs& a, cudaStream_t stream)
 {
-    using P = PipeGeo<CFB_LOGM>;
-    auto kernel = pipe_kernel<CFB_LOGM, KIND>;
+    using P = PipeGeo<CFB_LOGM, KIND, LOGW>;
+    auto kernel = pipe_kernel<CFB_LOGM, KIND, LOGW>;
     const cudaError_t e = cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM_BYTES);
     if (e != cudaSuccess)
         return e;
@@ -47,15 +47,19 @@ cudaError_t launch_pipe_one (const FftArgs& a, cudaStream_t stream)
 #define CFB_CAT2(a, b) a##b
 #define CFB_CAT(a, b) CFB_CAT2 (a, b)
 
-// ordered kinds only; `a` must describe a plain batch with 16-byte aligned input rows
-cudaError_t CFB_CAT (launch_pipe_, CFB_LOGM) (int kind, const FftArgs& a, cudaStream_t stream)
+// logW: 0 = ordered, 3 = 8-lane unordered layout; `a` must describe a plain batch with 16-byte aligned input rows
+cudaError_t CFB_CAT (launch_pipe_, CFB_LOGM) (int kind, int logW, const FftArgs& a, cudaStream_t stream)
 {
-    switch (kind)
+    switch (kind * 4 + logW)
     {
-        case C2C_FWD: return launch_pipe_one<C2C_FWD> (a, stream);
-        case C2C_BWD: return launch_pipe_one<C2C_BWD> (a, stream);
-        case R2C: return launch_pipe_one<R2C> (a, stream);
-        case C2R: return launch_pipe_one<C2R> (a, stream);
+        case C2C_FWD * 4: return launch_pipe_one<C2C_FWD, 0> (a, stream);
+        case C2C_BWD * 4: return launch_pipe_one<C2C_BWD, 0> (a, stream);
+        case R2C * 4: return launch_pipe_one<R2C, 0> (a, stream);
+        case C2R * 4: return launch_pipe_one<C2R, 0> (a, stream);
+        case C2C_FWD * 4 + 3: return launch_pipe_one<C2C_FWD, 3> (a, stream);
+        case C2C_BWD * 4 + 3: return launch_pipe_one<C2C_BWD, 3> (a, stream);
+        case R2C * 4 + 3: return launch_pipe_one<R2C, 3> (a, stream);
+        case C2R * 4 + 3: return launch_pipe_one<C2R, 3> (a, stream);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -9,13 +9,18 @@
 // current transform is in registers, so HBM reads, butterflies and HBM writes of neighbouring transforms overlap
 // inside one SM.
 //
-// Shared memory (2^14: 218 KB): landing buffer (8 M bytes) + exchange region (4 M bytes + pad) + the last stage's
-// twiddle rows.  The transform is 32 x 32 x r_last.  The stage-0 exchange is an ordinary padded 64-bit exchange that
+// Shared memory (2^14: 217..226 KB, per kind): landing buffer (8 M bytes) + exchange region (4 M bytes) + the
+// last stage's twiddle rows.  The transform is 32 x 32 x r_last.  The stage-0 exchange is an ordinary padded 64-bit exchange that
 // borrows the (already consumed) landing buffer; the TMA for the next transform is issued right after it.  The
 // stage-1 exchange runs while that copy is in flight, so it only has the half-size region: it moves the data in
 // two balanced rounds of 16 registers per thread (round_scatter / round_gather).  [A first version moved real and
 // imaginary parts separately through the half-size region for both exchanges: twice the LDS/STS instructions,
 // MIO-queue bound, 5.0 TB/s at 2^14 -- profiles/r01_pipe_kernel.txt.]
+//
+// Unordered (8-lane) layouts: an unordered INPUT lands as the padded staging image fft_kernel uses (the TMA copies it
+// in 512-byte pieces, one per thread, so that the 32-byte gaps of the bank-spreading pad appear on the fly); an
+// unordered OUTPUT is staged and drained in two halves through the exchange region.  The 4-lane layout stays with
+// fft_kernel.
 //
 // Replaces the same reference pipeline as fft_kernel (simd/chowdsp_fft_impl_avx.cpp:1848-1935); layouts, signs
 // and scaling are identical to it (natural-order complex, pffft-packed real spectra).
@@ -30,46 +35,61 @@ constexpr bool kPipeDeriveRtw = false;
 constexpr bool kPipeDeriveRtw = true;
 #endif
 
-template <int LOGM>
+// geometry and shared-memory layout of pipe_kernel<LOGM, KIND, LOGW> (LOGW = 0 ordered, 3 = 8-lane unordered)
+template <int LOGM, int KIND = C2C_FWD, int LOGW = 0>
 struct PipeGeo
 {
     using G = Geo<LOGM, 32>;
     static constexpr int M = G::M, T = G::T, R = 32;
-    static constexpr int LAND_BYTES = M * 8;                 // one transform, linear (TMA destination)
-    static constexpr int XCH_FLOATS = M + (M >> 5);          // (M/2 + M/64) float2: half-spectrum exchange of the real split step;
-                                                             // the stage-1 rounds use M/2 float2 of it, stage 0 spills M/32 into it
+    static_assert (LOGW == 0 || LOGW == 3, "ordered or 8-lane unordered");
     static_assert (G::S == 3 && G::radix (1) == 32, "written for 32 x 32 x r_last");
+    static_assert (G::T % 32 == 0 && G::R == 32, "the addressing below assumes 32 points per thread");
+    static constexpr bool IN_UNORD = LOGW != 0 && (KIND == C2C_BWD || KIND == C2R);
+    static constexpr bool OUT_UNORD = LOGW != 0 && (KIND == C2C_FWD || KIND == R2C);
+    // landing buffer = TMA destination: one transform, linear; or the padded unordered staging image (one 8-float
+    // gap per 128 floats, upad())
+    static constexpr int LAND_BYTES = IN_UNORD ? (2 * M + (2 * M >> 4)) * 4 : M * 8;
+    static constexpr int CHUNK_FLOATS = 128;                 // unordered input: floats per TMA piece (2 W^2)
+    static constexpr int NCHUNK = 2 * M / CHUNK_FLOATS;      // <= T
+    // exchange region: M/2 float2 (stage-1 rounds, unpadded; half-spectrum exchange of the real split / merge
+    // steps), or half of a padded unordered staging image for unordered outputs; the padded stage-0 exchange
+    // (M + M/32 float2) spans the landing buffer and the start of this region
+    static constexpr int HALF_IMAGE_FLOATS = M + (M >> 4);
+    static constexpr int XCH_BYTES = OUT_UNORD ? HALF_IMAGE_FLOATS * 4 : M * 4;
+    static_assert (LAND_BYTES + XCH_BYTES >= (M + (M >> 5)) * 8, "stage-0 exchange does not fit");
     // last-stage twiddle rows kept in shared memory: q = 1, 2, 3 and 4, 8, .. (the other powers are one register
     // product each, as in the full-radix stages).  Out of L1 they would not fit next to a > 200 KB carve-out, and
     // every L2 round trip stalls one of only four warps per scheduler.
     static constexpr int RL = G::RLAST;
     static constexpr int TW_ROWS = RL <= 4 ? RL - 1 : 3 + (RL / 4 - 1);
-    static constexpr int TW_OFFSET = LAND_BYTES + XCH_FLOATS * 4;
+    static constexpr int TW_OFFSET = LAND_BYTES + XCH_BYTES;
     static constexpr int TW1_OFFSET = TW_OFFSET + TW_ROWS * T * 8; // stage-1 rows w^4 .. w^28, 32 entries each
     static constexpr int BAR_OFFSET = TW1_OFFSET + 7 * 32 * 8;
     static constexpr int SMEM_BYTES = BAR_OFFSET + 16;
-    static constexpr int CTAS_PER_SM = (2 * (SMEM_BYTES + 1024) <= 227 * 1024 && 2 * T <= 512) ? 2 : 1;
+    static constexpr int CTAS_PER_SM = (2 * (SMEM_BYTES + 1024) <= 228 * 1024 && 2 * T <= 512) ? 2 : 1;
     static_assert (SMEM_BYTES <= 227 * 1024, "landing + exchange buffers exceed the shared memory of an SM");
-    static_assert (G::S >= 2 && RL >= 4, "expects a short last stage of radix >= 4");
+    static_assert (RL >= 4, "expects a short last stage of radix >= 4");
     static FFT_CX int tw_row_q (int i) { return i < 3 ? i + 1 : 4 * (i - 2); } // smem row i holds power q
-    static_assert (G::T % 32 == 0 && G::R == 32, "the addressing below assumes 32 points per thread");
 };
 
 // ---------------------------------------------------------------------------------------------
-// mbarrier + bulk-copy helpers (sm_90+ PTX; SASS: SYNCS.*, UBLKCP.S.G)
+// mbarrier + bulk-copy helpers (sm_90+ PTX; SASS: SYNCS.*, UBLKCP.S.G).  One barrier phase = one transform:
+// mbar_expect arms it with the transform's byte count (one thread), bulk_copy starts a piece (any thread), mbar_wait
+// blocks until phase `it` has received all of its bytes.
 // ---------------------------------------------------------------------------------------------
 #ifdef CHOWDSP_EMU
 // the emulator runs every CUDA thread as an OS thread: the "TMA" is a memcpy by the issuing thread followed by a
-// release increment of the barrier word, the wait spins on it
+// release add of the byte count to the barrier word, the wait spins on the running total
 FFT_HD void mbar_init (unsigned long long* bar) { __atomic_store_n (bar, 0ull, __ATOMIC_RELEASE); }
-FFT_HD void bulk_load (void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+FFT_HD void mbar_expect (unsigned long long*, unsigned) {}
+FFT_HD void bulk_copy (void* dst, const void* src, unsigned bytes, unsigned long long* bar)
 {
     std::memcpy (dst, src, bytes);
-    __atomic_fetch_add (bar, 1ull, __ATOMIC_RELEASE);
+    __atomic_fetch_add (bar, (unsigned long long) bytes, __ATOMIC_RELEASE);
 }
-FFT_HD void mbar_wait (unsigned long long* bar, unsigned it)
+FFT_HD void mbar_wait (unsigned long long* bar, unsigned it, unsigned bytes_per_phase)
 {
-    while (__atomic_load_n (bar, __ATOMIC_ACQUIRE) <= (unsigned long long) it)
+    while (__atomic_load_n (bar, __ATOMIC_ACQUIRE) < (unsigned long long) (it + 1) * bytes_per_phase)
         std::this_thread::yield();
 }
 #else
@@ -79,14 +99,16 @@ FFT_HD void mbar_init (unsigned long long* bar)
     asm volatile ("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr (bar)) : "memory");
     asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-// arm the barrier with the byte count, then start the copy; the barrier phase completes when all bytes landed
-FFT_HD void bulk_load (void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+FFT_HD void mbar_expect (unsigned long long* bar, unsigned bytes)
 {
     asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr (bar)), "r"(bytes) : "memory");
+}
+FFT_HD void bulk_copy (void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
     asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                   ::"r"(smem_addr (dst)), "l"(src), "r"(bytes), "r"(smem_addr (bar)) : "memory");
 }
-FFT_HD void mbar_wait (unsigned long long* bar, unsigned it)
+FFT_HD void mbar_wait (unsigned long long* bar, unsigned it, unsigned)
 {
     const unsigned addr = smem_addr (bar), parity = it & 1u;
     unsigned done;
@@ -97,6 +119,126 @@ FFT_HD void mbar_wait (unsigned long long* bar, unsigned it)
     } while (done == 0);
 }
 #endif
+
+// ---------------------------------------------------------------------------------------------
+// Persistent frame-gather (STFT analysis) kernel: R2C of OVERLAPPING windows of one signal, times an optional window,
+// any single-kernel size.  Work item = PER_CTA consecutive frames of one channel (as in stft_kernel); a resident CTA
+// loops over items blockIdx.x, blockIdx.x + gridDim.x, ...  The UNION of an item's frames ((PER_CTA - 1) hop + N floats
+// instead of PER_CTA N) is brought in by one TMA bulk copy into a landing buffer while the previous item is being
+// transformed; every transform takes its stage-0 registers from there.  Against fft_kernel / stft_kernel this
+// hides the load latency (ncu on the STFT config: 28 % of the stall samples sat on the first use of the loaded
+// registers, 16 warps per SM) and cuts the L2 -> SM bytes by the overlap factor without spending LSU instructions
+// on the staging.  Needs 0 < hop <= N, hop and channel stride multiples of 4 floats, 16-byte aligned signal.
+// Shared memory: [landing: a.land_bytes][mbarrier, 16 bytes][PER_CTA exchange buffers].
+// ---------------------------------------------------------------------------------------------
+template <int LOGM, int R, int LOGW>
+struct StftPipeGeo
+{
+    using G = Geo<LOGM, R>;
+    using L = Launch<LOGM, R>;
+    static constexpr int NFL = 2 * G::M;
+    static constexpr int SMEM_F2 = LOGW != 0 ? G::SMEM_F2_UNORD : G::SMEM_F2;
+    static constexpr int XCH_BYTES = L::PER_CTA * SMEM_F2 * 8;
+    static int land_bytes (long long hop) { return (int) (((L::PER_CTA - 1) * hop + NFL) * 4); } // hop % 4 == 0: multiple of 16
+    static int smem_bytes (long long hop) { return land_bytes (hop) + 16 + XCH_BYTES; }
+};
+
+template <int LOGM, int R, int LOGW>
+FFT_HD void stft_pipe_body (const FftArgs& a)
+{
+    using SP = StftPipeGeo<LOGM, R, LOGW>;
+    using G = typename SP::G;
+    constexpr int T = G::T, NFL = SP::NFL, PER_CTA = SP::L::PER_CTA;
+    FFT_DYN_SMEM (char, smem);
+    float2* land = reinterpret_cast<float2*> (smem);
+    unsigned long long* bar = reinterpret_cast<unsigned long long*> (smem + a.land_bytes);
+    float2* xch = reinterpret_cast<float2*> (smem + a.land_bytes + 16);
+
+    const int tid = (int) threadIdx.x;
+    const int j = tid & (T - 1);
+    const int lt = tid / T;
+    const long long items = (long long) (a.batch / a.inner) * a.groups;
+    const long long step = (long long) gridDim.x;
+    const int hop = (int) a.in_inner;
+
+    // item -> (channel, first frame, frames); span = floats of the union of its frames
+    auto fetch = [&] (long long item)
+    {
+        const long long o = item / a.groups;
+        const int f0 = (int) (item - o * a.groups) * PER_CTA;
+        const int nact = a.inner - f0 < PER_CTA ? a.inner - f0 : PER_CTA;
+        const unsigned bytes = (unsigned) ((nact - 1) * hop + NFL) * 4u;
+        mbar_expect (bar, bytes);
+        bulk_copy (land, a.in + o * a.in_outer + (long long) f0 * hop, bytes, bar);
+    };
+    long long item = (long long) blockIdx.x;
+    if (tid == 0)
+    {
+        mbar_init (bar);
+        if (item < items)
+            fetch (item);
+    }
+    __syncthreads();
+#ifdef CHOWDSP_EMU
+    unsigned long long emu_bytes = 0; // the emulated barrier counts bytes: running total expected after each item
+#endif
+    for (unsigned it = 0; item < items; item += step, ++it)
+    {
+        const long long o = item / a.groups;
+        const int f0 = (int) (item - o * a.groups) * PER_CTA;
+        const int nact = a.inner - f0 < PER_CTA ? a.inner - f0 : PER_CTA;
+        const bool active = lt < nact;
+        const int ltc = active ? lt : nact - 1; // idle transforms of a channel's last group redo its last frame, no store
+#ifdef CHOWDSP_EMU
+        emu_bytes += (unsigned long long) ((nact - 1) * hop + NFL) * 4u;
+        while (__atomic_load_n (bar, __ATOMIC_ACQUIRE) < emu_bytes)
+            std::this_thread::yield();
+#else
+        mbar_wait (bar, it, 0);
+#endif
+        float* out = a.out + o * a.out_outer + (long long) (f0 + ltc) * a.out_inner;
+        const auto input_consumed = [&]
+        {
+            if (tid == 0 && item + step < items)
+                fetch (item + step);
+        };
+        fft_core<LOGM, R, R2C, LOGW, false, false, false, true> (nullptr, out, active, j, xch + lt * SP::SMEM_F2, a.tw, a.rtw,
+                                                                 land + ltc * (hop / 2), reinterpret_cast<const float2*> (a.window), input_consumed);
+        if constexpr (G::S == 1)
+        {
+            __syncthreads(); // single-stage transforms have no barrier of their own after the input reads
+            input_consumed();
+        }
+    }
+}
+
+template <int LOGM, int R, int LOGW>
+__global__ void __launch_bounds__ (Launch<LOGM, R>::THREADS, Launch<LOGM, R>::MIN_BLOCKS) stft_pipe_kernel (const FftArgs a)
+{
+    stft_pipe_body<LOGM, R, LOGW> (a);
+}
+
+// start the copy of one transform into the landing buffer (called by every thread of the CTA)
+template <class P>
+FFT_HD void pipe_fetch (char* land, const float* src, int j, unsigned long long* bar)
+{
+    if constexpr (! P::IN_UNORD)
+    {
+        if (j == 0)
+        {
+            mbar_expect (bar, (unsigned) P::LAND_BYTES);
+            bulk_copy (land, src, (unsigned) P::LAND_BYTES, bar);
+        }
+    }
+    else
+    {
+        // piece c of 128 floats goes to float offset 136 c: the staging image's pad appears during the copy
+        if (j == 0)
+            mbar_expect (bar, (unsigned) (2 * P::M * 4));
+        if (j < P::NCHUNK)
+            bulk_copy (land + (size_t) j * (P::CHUNK_FLOATS + 8) * 4, src + (size_t) j * P::CHUNK_FLOATS, (unsigned) P::CHUNK_FLOATS * 4, bar);
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
 // exchange after stage 1 (Ns = 32, radix 32) in TWO balanced rounds through a buffer of M/2 float2: round h moves
@@ -199,26 +341,42 @@ FFT_HD void pipe_last_stage (float2 (&v)[32], int j, const float2* tws)
         RegFft<r, DIR, SUB>::run (&v[u]);
 }
 
+// linear 128-bit drain of one half of the padded unordered staging image (M floats) to global memory
+template <class P>
+FFT_HD void half_drain (const float* sf, float* __restrict__ out, int j)
+{
+#pragma unroll
+    for (int i = 0; i < P::M / (4 * P::T); ++i)
+    {
+        const int q = j + i * P::T;
+        reinterpret_cast<float4*> (out)[q] = lds4 (sf + upad (4 * q, 3));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // the kernel: grid = min (batch, SMs * CTAS_PER_SM), blockDim = T = M / 32, dynamic smem = PipeGeo::SMEM_BYTES.
 // Plain batches only (transform x reads in + x in_inner, writes out + x out_inner); the input rows must be
-// 16-byte aligned (TMA), which the launcher checks.  Ordered layouts (LOGW = 0).
+// 16-byte aligned (TMA), which the launcher checks.
 // ---------------------------------------------------------------------------------------------
-template <int LOGM, int KIND>
+template <int LOGM, int KIND, int LOGW>
 FFT_HD void pipe_body (const FftArgs& a)
 {
-    using P = PipeGeo<LOGM>;
+    using P = PipeGeo<LOGM, KIND, LOGW>;
     using G = typename P::G;
     constexpr int R = 32, T = G::T, M = G::M;
     constexpr int DIR = (KIND == C2C_FWD || KIND == R2C) ? -1 : +1;
+    constexpr int WL = 8;                                    // lanes of the unordered layout
+    constexpr unsigned PHASE_BYTES = P::IN_UNORD ? 2u * M * 4u : (unsigned) P::LAND_BYTES;
     FFT_DYN_SMEM (char, smem);
     float2* land = reinterpret_cast<float2*> (smem);
     float2* xs = reinterpret_cast<float2*> (smem + P::LAND_BYTES);
+    float2* xh = xs - M / 2;                                 // half-spectrum exchange: bin k >= M/2 at xh[k], unit stride
     float2* tws = reinterpret_cast<float2*> (smem + P::TW_OFFSET);
     float2* tw1s = reinterpret_cast<float2*> (smem + P::TW1_OFFSET);
     unsigned long long* bar = reinterpret_cast<unsigned long long*> (smem + P::BAR_OFFSET);
 
     const int j = (int) threadIdx.x;
+    const UPos<G, 3> up (j);
     {   // last-stage twiddle rows: global table row q-1 (T entries each, see Geo) -> shared row i
         const float2* __restrict__ tl = a.tw + G::tw_off (G::S - 1) + j;
 #pragma unroll
@@ -235,22 +393,29 @@ FFT_HD void pipe_body (const FftArgs& a)
     if (j == 0)
         mbar_init (bar);
     __syncthreads();
-    if (j == 0 && x < a.batch)
-        bulk_load (land, a.in + x * a.in_inner, (unsigned) P::LAND_BYTES, bar);
+    if (x < a.batch)
+        pipe_fetch<P> (smem, a.in + x * a.in_inner, j, bar);
 
     for (unsigned it = 0; x < a.batch; x += step, ++it)
     {
         float2 v[R];
-        mbar_wait (bar, it);
+        mbar_wait (bar, it, PHASE_BYTES);
         // ---- prologue: stage-0 registers v[m] = input element j + m T, from the landing buffer ----
-        if constexpr (KIND != C2R)
+        if constexpr (KIND == C2C_FWD || KIND == R2C || (KIND == C2C_BWD && ! P::IN_UNORD))
         {
             const float2* lj = land + j;
 #pragma unroll
             for (int m = 0; m < R; ++m)
                 v[m] = lds2 (lj + m * T);
         }
-        else
+        else if constexpr (KIND == C2C_BWD)
+        {
+            const float* lf = reinterpret_cast<const float*> (land);
+#pragma unroll
+            for (int m = 0; m < R; ++m)
+                v[m] = staged_load (lf, up.cplx (m), WL);
+        }
+        else if constexpr (! P::IN_UNORD)
         {
             // merge step  Z'[k] = (X[k] + X*[M-k]) + i conj(w_k) (X[k] - X*[M-k]),  w_k = e^{-2 pi i k / 2M}: both
             // operands come straight from the landing buffer, so each thread forms all of its own k = j + m T.
@@ -282,6 +447,38 @@ FFT_HD void pipe_body (const FftArgs& a)
                 }
             }
         }
+        else
+        {
+            // unordered half spectrum: the pair (k, M-k), k = j + m T < M/2, comes from the staging image; Z'[k] is
+            // this thread's register m, Z'[M-k] belongs to thread T-j and crosses the exchange region
+            const float* lf = reinterpret_cast<const float*> (land);
+            const float2 two = make_float2 (2.f, 2.f);
+            __syncthreads(); // the previous iteration's last round_gather is done everywhere: xh may be overwritten
+#pragma unroll
+            for (int m = 0; m < R / 2; ++m)
+            {
+                const bool special = (m == 0 && j == 0);
+                const float2 xa = staged_load (lf, up.real_lo (m), WL);
+                const float2 xm = staged_load (lf, special ? W_HALF_ROW<3>() : up.real_hi (m), WL);
+                const float2 wh = real_tw<32, kPipeDeriveRtw> (wj, a.rtw + j + m * T, m);
+                const float2 cm = make_float2 (xm.x, -xm.y);
+                const float2 e = f2_add (xa, cm), d = f2_sub (xa, cm);
+                const float2 wd = cmul_dir<+1> (d, wh);
+                float2 zk = f2_fma (make_float2 (-wd.y, wd.x), two, e);
+                float2 zm = f2_fma (make_float2 (wd.y, wd.x), two, make_float2 (e.x, -e.y));
+                if (special)
+                {
+                    zk = make_float2 (xa.x + xa.y, xa.x - xa.y);   // Z'[0] from (DC, Nyquist)
+                    zm = make_float2 (2.f * xm.x, -2.f * xm.y);    // Z'[M/2] = 2 conj X[M/2]
+                }
+                v[m] = zk;
+                sts2 (special ? xh + M / 2 : xh + (M - m * T) - j, zm);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int m = R / 2; m < R; ++m)
+                v[m] = lds2 (xh + j + m * T);
+        }
         // ---- stage 0, full 64-bit exchange through [landing | exchange] (padded, M + M/32 slots) ----
         stage_compute<G, DIR, 0> (v, j, a.tw);
         __syncthreads(); // the landing buffer has been consumed, and the previous iteration is done with xs
@@ -289,8 +486,8 @@ FFT_HD void pipe_body (const FftArgs& a)
         __syncthreads();
         gather_natural<G, 0, R> (v, j, land);
         __syncthreads(); // landing buffer free again: fetch the next transform while this one finishes
-        if (j == 0 && x + step < a.batch)
-            bulk_load (land, a.in + (x + step) * a.in_inner, (unsigned) P::LAND_BYTES, bar);
+        if (x + step < a.batch)
+            pipe_fetch<P> (smem, a.in + (x + step) * a.in_inner, j, bar);
         // ---- stage 1, two-round exchange through the exchange region alone ----
         pipe_stage1<DIR> (v, w1t, tw1s + (j & 31));
         {
@@ -311,28 +508,47 @@ FFT_HD void pipe_body (const FftArgs& a)
 
         // ---- epilogue ----
         float* out = a.out + x * a.out_inner;
-        if constexpr (KIND != R2C)
+        if constexpr (KIND == C2C_BWD || KIND == C2R || (KIND == C2C_FWD && ! P::OUT_UNORD))
         {
             float2* __restrict__ out2 = reinterpret_cast<float2*> (out) + j;
 #pragma unroll
             for (int m = 0; m < R; ++m)
                 out2[m * T] = v[m];
         }
+        else if constexpr (KIND == C2C_FWD)
+        {
+            // unordered output, staged and drained in two halves of the (padded) image: bin j + m T lies in half
+            // (m mod 4) / 2 (UPos::cplx: block index = j / 8 + (m mod 4) T / 8, M / 64 blocks per half)
+            float* sf = reinterpret_cast<float*> (xs);
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+            {
+                __syncthreads(); // the exchange region (or the previous half) has been read by everyone
+#pragma unroll
+                for (int m = 0; m < R; ++m)
+                    if ((m % 4) / 2 == h)
+                        staged_store (sf, up.cplx (m) - h * P::HALF_IMAGE_FLOATS, WL, v[m]);
+                __syncthreads();
+                half_drain<P> (sf, out + h * M, j);
+            }
+        }
         else
         {
             // split step  X[k] = E - i w_k D,  X[M-k] = conj(E + i w_k D),  E,D = (Z[k] +- Z*[M-k]) / 2.
             // Z[k], k = j + m T < M/2, is register m; Z[M-k] is register R-1-m of thread T-j: the upper half of the
-            // spectrum crosses the exchange region (seen as float2, shifted so that bin M/2 sits at slot 0).
-            float2* xh = xs - G::pad (M / 2);
+            // spectrum crosses the exchange region (unit stride on both sides, no padding needed).
             __syncthreads();
-            scatter_natural<G, R / 2, R> (v, j, xh);
+#pragma unroll
+            for (int m = R / 2; m < R; ++m)
+                sts2 (xh + j + m * T, v[m]);
             __syncthreads();
             float2 zb[R / 2];
 #pragma unroll
             for (int m = 0; m < R / 2; ++m)
-                zb[m] = lds2 (xh + ((m == 0 && j == 0) ? G::pad (M / 2) : mirror_slot<G> (j, m)));
+                zb[m] = lds2 ((m == 0 && j == 0) ? xh + M / 2 : xh + (M - m * T) - j);
             float2* __restrict__ lo = reinterpret_cast<float2*> (out) + j;
             float2* __restrict__ hi = reinterpret_cast<float2*> (out) + (M - T) - j;
+            float2 xlo[P::OUT_UNORD ? R / 2 : 1], xhi[P::OUT_UNORD ? R / 2 : 1];
 #pragma unroll
             for (int m = 0; m < R / 2; ++m)
             {
@@ -349,17 +565,58 @@ FFT_HD void pipe_body (const FftArgs& a)
                     xa = make_float2 (za.x + za.y, za.x - za.y);
                     xm = make_float2 (zm.x, -zm.y);
                 }
-                lo[m * T] = xa;
-                float2* ph = special ? reinterpret_cast<float2*> (out) + M / 2 : hi - m * T + T;
-                *ph = xm;
+                if constexpr (P::OUT_UNORD)
+                {
+                    xlo[m] = xa;
+                    xhi[m] = xm;
+                }
+                else
+                {
+                    lo[m * T] = xa;
+                    float2* ph = special ? reinterpret_cast<float2*> (out) + M / 2 : hi - m * T + T;
+                    *ph = xm;
+                }
+            }
+            if constexpr (P::OUT_UNORD)
+            {
+                // which half of the image a bin falls in depends on the thread for a few bins (the reversed odd rows
+                // wrap at thread 0), so the half is tested on the position itself
+                float* sf = reinterpret_cast<float*> (xs);
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                {
+                    __syncthreads();
+#pragma unroll
+                    for (int m = 0; m < R / 2; ++m)
+                    {
+                        const int plo = up.real_lo (m);
+                        const int phi = (m == 0 && j == 0) ? W_HALF_ROW<3>() : up.real_hi (m);
+                        if ((plo >= P::HALF_IMAGE_FLOATS) == (h == 1))
+                            staged_store (sf, plo - h * P::HALF_IMAGE_FLOATS, WL, xlo[m]);
+                        else
+                        {
+                            smem_skip();
+                            smem_skip();
+                        }
+                        if ((phi >= P::HALF_IMAGE_FLOATS) == (h == 1))
+                            staged_store (sf, phi - h * P::HALF_IMAGE_FLOATS, WL, xhi[m]);
+                        else
+                        {
+                            smem_skip();
+                            smem_skip();
+                        }
+                    }
+                    __syncthreads();
+                    half_drain<P> (sf, out + h * M, j);
+                }
             }
         }
     }
 }
 
-template <int LOGM, int KIND>
-__global__ void __launch_bounds__ (PipeGeo<LOGM>::T, PipeGeo<LOGM>::CTAS_PER_SM) pipe_kernel (const FftArgs a)
+template <int LOGM, int KIND, int LOGW>
+__global__ void __launch_bounds__ (PipeGeo<LOGM>::T, PipeGeo<LOGM, KIND, LOGW>::CTAS_PER_SM) pipe_kernel (const FftArgs a)
 {
-    pipe_body<LOGM, KIND> (a);
+    pipe_body<LOGM, KIND, LOGW> (a);
 }
 } // namespace cfb

@@ -44,10 +44,12 @@ struct ThreadCtx
 {
     dim3 tIdx, bIdx, bDim, gDim;
     std::barrier<>* bar = nullptr;
+    std::barrier<>* group_bar[3] = { nullptr, nullptr, nullptr }; // barriers of this thread's group of 32 / 64 / 128 threads
     char* smem = nullptr;
     std::vector<SmemOp>* log = nullptr; // per-thread smem op sequence (bank-conflict analysis)
 };
 inline thread_local ThreadCtx ctx;
+inline void syncgroup (int n) { ctx.group_bar[n == 32 ? 0 : n == 64 ? 1 : 2]->arrive_and_wait(); } // __syncwarp / named barriers
 
 struct ConflictStats
 {
@@ -118,6 +120,10 @@ void launch (Kernel kernel, dim3 grid, dim3 block, size_t smem_bytes, Args... ar
     {
         std::vector<char> smem (smem_bytes + 64);
         std::barrier<> bar ((std::ptrdiff_t) nthreads);
+        std::vector<std::unique_ptr<std::barrier<>>> group_bars[3];
+        for (int gi = 0; gi < 3; ++gi)
+            for (unsigned w = 0, n = 32u << gi; w < (nthreads + n - 1) / n; ++w)
+                group_bars[gi].emplace_back (new std::barrier<> ((std::ptrdiff_t) std::min (n, nthreads - n * w)));
         std::vector<std::vector<SmemOp>> logs (nthreads);
         std::vector<std::thread> pool;
         pool.reserve (nthreads);
@@ -129,6 +135,8 @@ void launch (Kernel kernel, dim3 grid, dim3 block, size_t smem_bytes, Args... ar
                                    ctx.bDim = block;
                                    ctx.gDim = grid;
                                    ctx.bar = &bar;
+                                   for (int gi = 0; gi < 3; ++gi)
+                                       ctx.group_bar[gi] = group_bars[gi][t / (32u << gi)].get();
                                    ctx.smem = smem.data();
                                    ctx.log = g_log_smem ? &logs[t] : nullptr;
                                    kernel (args...);

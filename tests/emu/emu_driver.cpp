@@ -153,11 +153,11 @@ int emu_fft (int logM, int kind, int unord, int logW, const float* in, float* ou
 }
 
 // persistent TMA-pipelined transform (pipe_kernels.cuh): `grid` resident CTAs loop over `batch` contiguous transforms
-int emu_pipe (int logM, int kind, const float* in, float* out, int batch, int grid, int log_conflicts, long* stats)
+int emu_pipe (int logM, int kind, int unord, const float* in, float* out, int batch, int grid, int log_conflicts, long* stats)
 {
-    auto run = [&] (auto logm_c) -> int
+    auto run = [&] (auto logm_c, auto logw_c) -> int
     {
-        constexpr int LOGM = decltype (logm_c)::value;
+        constexpr int LOGM = decltype (logm_c)::value, LOGW = decltype (logw_c)::value;
         using P = PipeGeo<LOGM>;
         using G = typename P::G;
         std::vector<float2> tw ((size_t) G::TW_LEN + 1), rtw ((size_t) G::M / 2 + 1);
@@ -170,10 +170,10 @@ int emu_pipe (int logM, int kind, const float* in, float* out, int batch, int gr
         a.tw = tw.data(); a.rtw = rtw.data();
         switch (kind)
         {
-            case 0: emu::launch (pipe_kernel<LOGM, C2C_FWD>, dim3 ((unsigned) grid), dim3 (P::T), (size_t) P::SMEM_BYTES, a); break;
-            case 1: emu::launch (pipe_kernel<LOGM, C2C_BWD>, dim3 ((unsigned) grid), dim3 (P::T), (size_t) P::SMEM_BYTES, a); break;
-            case 2: emu::launch (pipe_kernel<LOGM, R2C>, dim3 ((unsigned) grid), dim3 (P::T), (size_t) P::SMEM_BYTES, a); break;
-            case 3: emu::launch (pipe_kernel<LOGM, C2R>, dim3 ((unsigned) grid), dim3 (P::T), (size_t) P::SMEM_BYTES, a); break;
+            case 0: emu::launch (pipe_kernel<LOGM, C2C_FWD, LOGW>, dim3 ((unsigned) grid), dim3 (P::T), (size_t) PipeGeo<LOGM, C2C_FWD, LOGW>::SMEM_BYTES, a); break;
+            case 1: emu::launch (pipe_kernel<LOGM, C2C_BWD, LOGW>, dim3 ((unsigned) grid), dim3 (P::T), (size_t) PipeGeo<LOGM, C2C_BWD, LOGW>::SMEM_BYTES, a); break;
+            case 2: emu::launch (pipe_kernel<LOGM, R2C, LOGW>, dim3 ((unsigned) grid), dim3 (P::T), (size_t) PipeGeo<LOGM, R2C, LOGW>::SMEM_BYTES, a); break;
+            case 3: emu::launch (pipe_kernel<LOGM, C2R, LOGW>, dim3 ((unsigned) grid), dim3 (P::T), (size_t) PipeGeo<LOGM, C2R, LOGW>::SMEM_BYTES, a); break;
             default: return -1;
         }
         return 0;
@@ -181,8 +181,10 @@ int emu_pipe (int logM, int kind, const float* in, float* out, int batch, int gr
     emu::g_log_smem = log_conflicts != 0;
     emu::g_stats = {};
     int rc = -1;
-    if (logM == 13) rc = run (std::integral_constant<int, 13> {});
-    if (logM == 14) rc = run (std::integral_constant<int, 14> {});
+    if (logM == 13 && ! unord) rc = run (std::integral_constant<int, 13> {}, std::integral_constant<int, 0> {});
+    if (logM == 14 && ! unord) rc = run (std::integral_constant<int, 14> {}, std::integral_constant<int, 0> {});
+    if (logM == 13 && unord) rc = run (std::integral_constant<int, 13> {}, std::integral_constant<int, 3> {});
+    if (logM == 14 && unord) rc = run (std::integral_constant<int, 14> {}, std::integral_constant<int, 3> {});
     if (stats)
     {
         stats[0] = emu::g_stats.ops;
@@ -227,6 +229,48 @@ int emu_stft (int logM, int unord, int logW, const float* in, float* out, int ou
     CFB_EMU_STFT (4, 0) CFB_EMU_STFT (4, 2) CFB_EMU_STFT (6, 0) CFB_EMU_STFT (6, 3) CFB_EMU_STFT (8, 0) CFB_EMU_STFT (8, 3)
     CFB_EMU_STFT (10, 0) CFB_EMU_STFT (10, 3) CFB_EMU_STFT (10, 2) CFB_EMU_STFT (12, 0)
 #undef CFB_EMU_STFT
+    if (stats)
+    {
+        stats[0] = emu::g_stats.ops;
+        stats[1] = emu::g_stats.wavefronts;
+        stats[2] = emu::g_stats.ideal;
+        stats[3] = emu::g_stats.worst;
+    }
+    return rc;
+}
+
+// persistent TMA-fed frame gather (stft_pipe_kernel) on `grid` resident CTAs
+int emu_stft_pipe (int logM, int radix, int unord, int logW, const float* in, float* out, int outer, int inner, long long in_outer, long long in_inner, long long out_outer, long long out_inner, const float* window, int grid, int log_conflicts, long* stats)
+{
+    auto run = [&] (auto logm_c, auto r_c, auto logw_c) -> int
+    {
+        constexpr int LOGM = decltype (logm_c)::value, R = decltype (r_c)::value, LOGW = decltype (logw_c)::value;
+        using SP = StftPipeGeo<LOGM, R, LOGW>;
+        using G = Geo<LOGM, R>;
+        using L = Launch<LOGM, R>;
+        std::vector<float2> tw ((size_t) G::TW_LEN + 1), rtw ((size_t) G::M / 2 + 1);
+        fill_stage_twiddles<LOGM, R> (tw.data());
+        fill_real_twiddles (rtw.data(), G::M);
+        FftArgs a {};
+        a.in = in; a.out = out;
+        a.in_inner = in_inner; a.in_outer = in_outer; a.out_inner = out_inner; a.out_outer = out_outer;
+        a.inner = inner; a.batch = outer * inner;
+        a.tw = tw.data(); a.rtw = rtw.data();
+        a.window = window;
+        a.groups = (inner + L::PER_CTA - 1) / L::PER_CTA;
+        a.land_bytes = SP::land_bytes (in_inner);
+        emu::launch (stft_pipe_kernel<LOGM, R, LOGW>, dim3 ((unsigned) grid), dim3 (L::THREADS), (size_t) SP::smem_bytes (in_inner), a);
+        return 0;
+    };
+    using std::integral_constant;
+    emu::g_log_smem = log_conflicts != 0;
+    emu::g_stats = {};
+    int rc = -1;
+    const int lw = unord ? logW : 0;
+#define CFB_EMU_SP(M, RR, W) if (logM == M && radix == RR && lw == W) rc = run (integral_constant<int, M> {}, integral_constant<int, RR> {}, integral_constant<int, W> {});
+    CFB_EMU_SP (4, 16, 0) CFB_EMU_SP (4, 16, 2) CFB_EMU_SP (6, 16, 0) CFB_EMU_SP (6, 16, 3) CFB_EMU_SP (8, 16, 0) CFB_EMU_SP (8, 16, 3)
+    CFB_EMU_SP (10, 16, 0) CFB_EMU_SP (10, 32, 0) CFB_EMU_SP (10, 32, 3) CFB_EMU_SP (12, 16, 0)
+#undef CFB_EMU_SP
     if (stats)
     {
         stats[0] = emu::g_stats.ops;

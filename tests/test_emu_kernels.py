@@ -18,7 +18,8 @@ def emu():
     L.emu_fft.argtypes = [C.c_int] * 4 + [fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 4 + [C.c_int, C.POINTER(C.c_long)]
     L.emu_convolve.argtypes = [fp, fp, fp] + [C.c_longlong] * 3 + [C.c_int] * 4 + [C.c_float]
     L.emu_accumulate.argtypes = [fp, fp, fp, C.c_longlong]
-    L.emu_pipe.argtypes = [C.c_int, C.c_int, fp, fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_long)]
+    L.emu_pipe.argtypes = [C.c_int, C.c_int, C.c_int, fp, fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_long)]
+    L.emu_stft_pipe.argtypes = [C.c_int] * 4 + [fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 4 + [fp, C.c_int, C.c_int, C.POINTER(C.c_long)]
     L.emu_stft.argtypes = [C.c_int] * 3 + [fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 4 + [fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_long)]
     return L
 
@@ -99,26 +100,28 @@ def test_emulated_radix32_geometry(emu, oracle_mod, N, is_c):
         emu.emu_set_radix(16)
 
 
+@pytest.mark.parametrize("ordered", [True, False])
 @pytest.mark.parametrize("N,is_c", [(8192, True), (16384, True), (16384, False), (32768, False)])
-def test_emulated_pipelined_kernel(emu, oracle_mod, N, is_c):
+def test_emulated_pipelined_kernel(emu, oracle_mod, N, is_c, ordered):
     """The persistent TMA-pipelined kernel (2^13 / 2^14 complex points): 3 transforms on 2 resident CTAs, so one
-    CTA runs two loop iterations (landing-buffer reuse, barrier phases) and the other one; ordered layouts."""
+    CTA runs two loop iterations (landing-buffer reuse, barrier phases) and the other one; ordered and 8-lane
+    unordered layouts."""
     o = oracle_mod
     nfl = 2 * N if is_c else N
     logM = int(np.log2(N)) - (0 if is_c else 1)
     batch, grid = 3, 2
     rng = np.random.default_rng(N + 77)
     x = rng.uniform(-1, 1, (batch, nfl)).astype(np.float32)
-    ref = o.np_transform(x, N, is_c, 8, False, True)
+    ref = o.np_transform(x, N, is_c, 8, False, ordered)
     st = (C.c_long * 4)()
     f = np.zeros_like(x)
-    assert emu.emu_pipe(logM, 0 if is_c else 2, x.ctypes.data_as(fp), f.ctypes.data_as(fp), batch, grid, 1, st) == 0
+    assert emu.emu_pipe(logM, 0 if is_c else 2, int(not ordered), x.ctypes.data_as(fp), f.ctypes.data_as(fp), batch, grid, 1, st) == 0
     assert o.rel_l2(f, ref) < 4e-7
     assert st[1] <= 1.05 * st[2] and st[3] <= 200, list(st)
     b = np.zeros_like(x)
     refc = np.ascontiguousarray(ref, np.float32)
-    assert emu.emu_pipe(logM, 1 if is_c else 3, refc.ctypes.data_as(fp), b.ctypes.data_as(fp), batch, grid, 1, st) == 0
-    assert o.rel_l2(b, o.np_transform(ref, N, is_c, 8, True, True)) < 4e-7
+    assert emu.emu_pipe(logM, 1 if is_c else 3, int(not ordered), refc.ctypes.data_as(fp), b.ctypes.data_as(fp), batch, grid, 1, st) == 0
+    assert o.rel_l2(b, o.np_transform(ref, N, is_c, 8, True, ordered)) < 4e-7
     assert st[1] <= 1.05 * st[2] and st[3] <= 200, list(st)
 
 
@@ -263,6 +266,31 @@ def test_emulated_stft_gather(emu, oracle_mod, N, hop, frames, ordered, W, windo
     vec4 = int(hop % 4 == 0 and samples % 4 == 0)
     rc = emu.emu_stft(int(np.log2(N)) - 1, 0 if ordered else 1, {8: 3, 4: 2}[W], sig.ctypes.data_as(fp), out.ctypes.data_as(fp),
                       channels, frames, samples, hop, frames * N, N, win.ctypes.data_as(fp) if windowed else None, vec4, int(union), 1, st)
+    assert rc == 0
+    fr = np.stack([[sig[c, f * hop:f * hop + N] for f in range(frames)] for c in range(channels)])
+    if windowed:
+        fr = fr * win
+    want = o.np_transform(fr.reshape(-1, N).astype(np.float32), N, False, W, False, ordered).reshape(out.shape)
+    assert o.rel_l2(out, want) < min(o.parity_tol(N), 4e-7)
+
+
+@pytest.mark.parametrize("N,radix,hop,frames,ordered,W", [(2048, 32, 512, 19, True, 8), (2048, 32, 512, 9, False, 8), (2048, 16, 2048, 5, True, 8),
+                                                          (512, 16, 96, 19, True, 8), (512, 16, 128, 9, False, 8), (128, 16, 32, 18, False, 8),
+                                                          (32, 16, 8, 21, True, 4), (32, 16, 12, 40, False, 4), (8192, 16, 1024, 3, True, 8)])
+@pytest.mark.parametrize("windowed", [False, True])
+def test_emulated_persistent_stft(emu, oracle_mod, N, radix, hop, frames, ordered, W, windowed):
+    """Persistent TMA-fed frame gather (stft_pipe_kernel): 3 resident CTAs loop over the (channel, frame group) items,
+    ragged last groups included; == a loop of single out-of-place transforms over the overlapping frames."""
+    o = oracle_mod
+    channels = 3
+    samples = ((frames - 1) * hop + N + 7) // 4 * 4
+    rng = np.random.default_rng(N + hop + 1)
+    sig = rng.uniform(-1, 1, (channels, samples)).astype(np.float32)
+    win = (0.5 - 0.5 * np.cos(2 * np.pi * (np.arange(N) + 0.5) / N)).astype(np.float32)
+    out = np.zeros((channels, frames, N), np.float32)
+    st = (C.c_long * 4)()
+    rc = emu.emu_stft_pipe(int(np.log2(N)) - 1, radix, 0 if ordered else 1, {8: 3, 4: 2}[W], sig.ctypes.data_as(fp), out.ctypes.data_as(fp),
+                           channels, frames, samples, hop, frames * N, N, win.ctypes.data_as(fp) if windowed else None, 3, 1, st)
     assert rc == 0
     fr = np.stack([[sig[c, f * hop:f * hop + N] for f in range(frames)] for c in range(channels)])
     if windowed:

@@ -185,10 +185,10 @@ def test_radix32_geometry(cf, oracle_mod, N, is_c, mask):
         cf.set_tuning("radix32_mask", -1)
 
 
-@pytest.mark.parametrize("mask", [0xFF, 0])
+@pytest.mark.parametrize("mask", [0xFFFF, 0])
 @pytest.mark.parametrize("N,is_c", [(8192, True), (16384, True), (16384, False), (32768, False)])
 def test_pipelined_kernel(cf, oracle_mod, N, is_c, mask):
-    """Complex lengths 2^13 / 2^14, ordered: the persistent TMA-pipelined kernel (mask 0xFF = every kind) and
+    """Complex lengths 2^13 / 2^14: the persistent TMA-pipelined kernel (mask 0xFFFF = every kind and layout) and
     fft_kernel (mask 0) against the oracle.  The batch exceeds the resident CTA count (so CTAs loop, with a ragged
     last round), in place and out of place; a row stride that breaks the 16-byte alignment TMA needs must fall
     back to fft_kernel and still be right."""
@@ -198,24 +198,25 @@ def test_pipelined_kernel(cf, oracle_mod, N, is_c, mask):
     batch = 2 * 148 * 2 + 7
     x = rng.uniform(-1, 1, (batch, nfl)).astype(np.float32)
     sub = np.r_[0:3, 147:150, 295:299, batch - 3:batch]  # first / second / third round of the persistent loop
-    ref = o.np_transform(x[sub], N, is_c, 8, False, True)
     cf.set_tuning("pipe_mask", mask)
     try:
-        f = gpu_transform(cf, x, N, is_c, True, False, True)
-        assert o.rel_l2(f[sub], ref) < o.parity_tol(N)
-        assert np.array_equal(gpu_transform(cf, x, N, is_c, True, False, True, inplace=True), f)
-        b = gpu_transform(cf, f, N, is_c, True, True, True)
-        assert o.rel_l2(b / N, x) < o.parity_tol(N)
-        assert o.rel_l2(b[sub], o.np_transform(f[sub], N, is_c, 8, True, True)) < o.parity_tol(N)
+        for ordered in (True, False):
+            ref = o.np_transform(x[sub], N, is_c, 8, False, ordered)
+            f = gpu_transform(cf, x, N, is_c, True, False, ordered)
+            assert o.rel_l2(f[sub], ref) < o.parity_tol(N), ordered
+            assert np.array_equal(gpu_transform(cf, x, N, is_c, True, False, ordered, inplace=True), f)
+            b = gpu_transform(cf, f, N, is_c, True, True, ordered)
+            assert o.rel_l2(b / N, x) < o.parity_tol(N), ordered
+            assert o.rel_l2(b[sub], o.np_transform(f[sub], N, is_c, 8, True, ordered)) < o.parity_tol(N), ordered
+            assert np.array_equal(gpu_transform(cf, f, N, is_c, True, True, ordered, inplace=True), b)
         # rows 8 bytes off a 16-byte boundary: not a TMA source
         s = cf.fft_new_setup(N, cf.FFT_COMPLEX if is_c else cf.FFT_REAL, True)
         try:
             n0 = cf.launch_count()
             buf = torch.zeros(4 * (nfl + 2) + 2, device="cuda")
-            xin = buf[2:].as_strided((4, nfl), (nfl + 2, 1))
-            xin.copy_(dev(x[:4]))
+            buf[2:].as_strided((4, nfl), (nfl + 2, 1)).copy_(dev(x[:4]))
             out = torch.empty(4, nfl, device="cuda")
-            cf.fft_transform_batched(s, xin, out, 4, nfl + 2, nfl, cf.FFT_FORWARD, True)
+            cf.fft_transform_batched(s, buf[2:], out, 4, nfl + 2, nfl, cf.FFT_FORWARD, True)
             torch.cuda.synchronize()
             assert cf.launch_count() - n0 == 1
             assert o.rel_l2(host(out), o.np_transform(x[:4], N, is_c, 8, False, True)) < o.parity_tol(N)
@@ -252,13 +253,18 @@ def test_strided_batches_and_stft_gather(cf, oracle_mod):
 
 
 @pytest.mark.parametrize("N,hop,frames", [(2048, 512, 37), (2048, 2048, 5), (512, 96, 19), (512, 130, 9), (128, 32, 18),
-                                          (32, 6, 41), (8192, 1024, 6), (32768, 4096, 3), (1024, 256, 1)])
-def test_stft_forward_window_and_layouts(cf, oracle_mod, N, hop, frames):
+                                          (32, 6, 41), (32, 8, 41), (8192, 1024, 6), (32768, 4096, 3), (1024, 256, 1)])
+@pytest.mark.parametrize("tail,pipe", [(6, 1), (8, 1), (8, 0)])
+def test_stft_forward_window_and_layouts(cf, oracle_mod, N, hop, frames, tail, pipe):
     """fft_stft_forward == a loop of single transforms over the (windowed) overlapping frames: ordered and
-    unordered, ragged last CTA group, hops that are not multiples of 4 floats (no 128-bit gather)."""
+    unordered, ragged last CTA group, hops that are not multiples of 4 floats (no 128-bit gather).  tail = 8 with
+    pipe = 1 keeps the channels 16-byte aligned, so hops that are multiples of 4 take the persistent TMA-fed kernel
+    (stft_pipe_kernel; N = 32768 does not fit its buffers and must fall back); the other two legs run stft_kernel /
+    fft_kernel."""
     o = oracle_mod
     channels = 3
-    samples = (frames - 1) * hop + N + 6
+    samples = (frames - 1) * hop + N + tail
+    cf.set_tuning("stft_pipe", pipe)
     rng = np.random.default_rng(N + hop)
     sig = rng.uniform(-1, 1, (channels, samples)).astype(np.float32)
     win = (0.5 - 0.5 * np.cos(2 * np.pi * (np.arange(N) + 0.5) / N)).astype(np.float32)
@@ -285,6 +291,7 @@ def test_stft_forward_window_and_layouts(cf, oracle_mod, N, hop, frames):
             assert o.rel_l2(host(out).reshape(-1, N), want) < o.parity_tol(N)
     finally:
         cf.set_tuning("stft_union", 0)
+        cf.set_tuning("stft_pipe", 0)
     cf.fft_destroy_setup(s)
 
 
