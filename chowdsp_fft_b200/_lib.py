@@ -55,6 +55,7 @@ def lib() -> C.CDLL:
         "fft_transform_batched": (i, [vp, vp, vp, i, ll, ll, i, i, vp]),
         "fft_transform_strided": (i, [vp, vp, vp, i, i, ll, ll, ll, ll, i, i, vp]),
         "fft_stft_forward": (i, [vp, vp, vp, i, i, ll, ll, ll, ll, vp, i, vp]),
+        "fft_istft_overlap_add": (i, [vp, vp, vp, i, i, ll, ll, ll, ll, vp, f, i, vp]),
         "fft_convolve_unordered_batched": (i, [vp, vp, vp, vp, i, ll, ll, ll, f, vp]),
         "fft_accumulate_batched": (i, [vp, vp, vp, vp, ll, vp]),
         "fft_partitioned_convolve_step": (i, [vp, vp, ll, vp, ll, vp, ll, vp, ll, i, i, i, f, vp]),
@@ -68,6 +69,7 @@ def lib() -> C.CDLL:
         "fft_large_factors": (i, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "fft_b200_set_tuning": (i, [C.c_char_p, i]),
         "fft_b200_last_error": (C.c_char_p, []),
+        "fft_b200_last_kernel": (C.c_char_p, []),
         "fft_b200_clear_error": (None, []),
         "fft_b200_launch_count": (C.c_ulonglong, []),
         "fft_b200_device_available": (i, []),
@@ -83,7 +85,7 @@ def lib() -> C.CDLL:
 EXPORTED = (
     "fft_bytes_required", "fft_new_setup", "fft_new_setup_preallocated", "fft_destroy_setup",
     "fft_simd_width_bytes", "fft_transform", "fft_transform_unordered", "fft_convolve_unordered",
-    "fft_accumulate", "aligned_malloc", "aligned_free", "fft_transform_batched", "fft_transform_strided", "fft_stft_forward",
-    "fft_convolve_unordered_batched", "fft_accumulate_batched", "fft_partitioned_convolve_step", "fft_dist_phase", "fft_dist_phase0_peer", "fft_dist_alloc", "fft_dist_free", "fft_dist_ipc_export", "fft_dist_ipc_open", "fft_dist_ipc_close", "fft_large_factors", "fft_b200_set_tuning", "fft_b200_last_error", "fft_b200_clear_error",
+    "fft_accumulate", "aligned_malloc", "aligned_free", "fft_transform_batched", "fft_transform_strided", "fft_stft_forward", "fft_istft_overlap_add",
+    "fft_convolve_unordered_batched", "fft_accumulate_batched", "fft_partitioned_convolve_step", "fft_dist_phase", "fft_dist_phase0_peer", "fft_dist_alloc", "fft_dist_free", "fft_dist_ipc_export", "fft_dist_ipc_open", "fft_dist_ipc_close", "fft_large_factors", "fft_b200_set_tuning", "fft_b200_last_error", "fft_b200_last_kernel", "fft_b200_clear_error",
     "fft_b200_launch_count", "fft_b200_device_available",
 )

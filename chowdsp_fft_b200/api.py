@@ -58,6 +58,11 @@ def device_available() -> bool:
     return bool(lib().fft_b200_device_available())
 
 
+def last_kernel() -> str:
+    """Template instance of the transform kernel this thread launched last (diagnostic)."""
+    return lib().fft_b200_last_kernel().decode(errors="replace")
+
+
 def launch_count() -> int:
     return int(lib().fft_b200_launch_count())
 
@@ -150,6 +155,14 @@ def fft_stft_forward(setup: int, signal, spectra, channels: int, frames: int, ch
     _check(lib().fft_stft_forward(setup, _addr(signal), _addr(spectra), channels, frames, channel_stride, hop,
                                   out_channel_stride, out_frame_stride, _addr(window) if window is not None else None,
                                   int(ordered), _stream(stream)))
+
+
+def fft_istft_overlap_add(setup: int, spectra, signal, channels: int, frames: int, spec_channel_stride: int, spec_frame_stride: int,
+                          channel_stride: int, hop: int, window=None, scale: float = 1.0, ordered: bool = True, stream=None) -> None:
+    """Overlap-add synthesis (C2R + optional window + sum at hop distance in one kernel, see chowdsp_fft_b200.h)."""
+    _check(lib().fft_istft_overlap_add(setup, _addr(spectra), _addr(signal), channels, frames, spec_channel_stride, spec_frame_stride,
+                                       channel_stride, hop, _addr(window) if window is not None else None, scale, int(ordered),
+                                       _stream(stream)))
 
 
 def fft_convolve_unordered_batched(setup: int, dft_a, dft_b, dft_ab, batch: int, a_stride: int, b_stride: int,

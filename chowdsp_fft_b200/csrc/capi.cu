@@ -29,6 +29,15 @@ using namespace cfb;
 // errors
 // ------------------------------------------------------------------------------------------------
 thread_local char t_error[512] = "";
+thread_local char t_last_kernel[96] = ""; // name of the transform kernel this thread launched last (fft_b200_last_kernel)
+const char* kKindNames[4] = { "C2C_FWD", "C2C_BWD", "R2C", "C2R" };
+void note_kernel (const char* fmt, ...)
+{
+    va_list ap;
+    va_start (ap, fmt);
+    vsnprintf (t_last_kernel, sizeof (t_last_kernel), fmt, ap);
+    va_end (ap);
+}
 
 int fail (int code, const char* fmt, ...)
 {
@@ -416,6 +425,7 @@ int enqueue_large (Plan* p, const float* in, float* out, int batch, long long in
                 pass[i].args.out = i == np - 1 ? dst : s1;
                 pass[i].args.out_bstride = i == np - 1 ? dst_bs : npts;
                 pass[i].args.batch = nb;
+                note_kernel ("cfb::tile_fft_kernel<%d,%d,%d> x%d passes", pass[i].logL, pass[i].C, dir, np);
                 const cudaError_t le = launch_tile (pass[i].logL, pass[i].C, dir, pass[i].load_j_fast, pass[i].args, stream);
                 if (le != cudaSuccess)
                     return fail_cuda (le, "tile pass launch");
@@ -513,6 +523,7 @@ int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inne
         pa.inner = pa.batch = outer * inner;
         pa.tw = t.tw;
         pa.rtw = t.rtw;
+        note_kernel ("cfb::pipe_kernel<%d,%s,%d>", p->logM, kKindNames[kind_of (p, direction)], ordered ? 0 : p->logW);
         const cudaError_t ep = launch_pipe (p->logM, kind_of (p, direction), ordered ? 0 : p->logW, pa, stream);
         if (ep != cudaSuccess)
             return fail_cuda (ep, "pipelined fft kernel launch");
@@ -542,7 +553,10 @@ int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inne
         a.window = window;
         const cudaError_t es = launch_stft_pipe (p->logM, ordered ? 0 : p->logW, radix, a, stream);
         if (es == cudaSuccess)
+        {
+            note_kernel ("cfb::stft_pipe_kernel<%d,%d,%d>", p->logM, radix, ordered ? 0 : p->logW);
             return 0;
+        }
         if (es != cudaErrorInvalidConfiguration) // = does not fit in shared memory at this hop: use the kernels below
             return fail_cuda (es, "persistent stft kernel launch");
         (void) cudaGetLastError();
@@ -553,6 +567,7 @@ int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inne
         a.window = window;
         a.union_gather = (g_stft_union && union_ok) ? 1 : 0;
         a.vec4 = ((reinterpret_cast<uintptr_t> (in) & 15) == 0 && (in_inner & 3) == 0 && (in_outer & 3) == 0) ? 1 : 0;
+        note_kernel ("cfb::stft_kernel<%d,%d,%d,%s>", p->logM, radix, ordered ? 0 : p->logW, a.union_gather ? "union" : "direct");
         const cudaError_t es = launch_stft (p->logM, ordered ? 0 : p->logW, radix, a, stream);
         if (es != cudaSuccess)
             return fail_cuda (es, "stft kernel launch");
@@ -560,6 +575,7 @@ int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inne
     }
     if (window != nullptr)
         return fail (chowdsp::fft::FFT_B200_EINVAL, "windowed transforms need even hop and channel strides");
+    note_kernel ("cfb::fft_kernel<%d,%d,%s,%d>", p->logM, radix, kKindNames[kind_of (p, direction)], ordered ? 0 : p->logW);
     const cudaError_t e = launch_fft (p->logM, kind_of (p, direction), ordered ? 0 : p->logW, radix, a, stream);
     if (e != cudaSuccess)
         return fail_cuda (e, "fft kernel launch");
@@ -922,6 +938,73 @@ CFB_API int fft_stft_forward (void* setup, const float* signal, float* spectra, 
     return enqueue_transform (p, signal, spectra, channels, frames, channel_stride, hop, out_channel_stride, out_frame_stride, FFT_FORWARD, ordered != 0, static_cast<cudaStream_t> (stream), window);
 }
 
+CFB_API int fft_istft_overlap_add (void* setup, const float* spectra, float* signal, int channels, int frames, long long spec_channel_stride, long long spec_frame_stride, long long channel_stride, long long hop, const float* window, float scale, int ordered, void* stream)
+{
+    Plan* p = as_plan (setup);
+    if (p == nullptr)
+        return FFT_B200_EINVAL;
+    if (p->is_complex || p->logM > 13)
+        return fail (FFT_B200_EINVAL, "fft_istft_overlap_add needs a REAL plan with N <= 16384 (frame buffers + carried tails must fit in shared memory)");
+    if (spectra == nullptr || signal == nullptr || channels < 0 || frames < 0 || hop <= 0 || hop > p->N || (long long) channels * frames > 0x7fffffffLL)
+        return fail (FFT_B200_EINVAL, "fft_istft_overlap_add: bad arguments (0 < hop <= N)");
+    if ((spec_frame_stride & 1) != 0 || (spec_channel_stride & 1) != 0)
+        return fail (FFT_B200_EINVAL, "fft_istft_overlap_add: spectrum strides must be even (8-byte aligned frames)");
+    if (channels == 0 || frames == 0)
+        return 0;
+    if (classify (spectra).kind != Mem::Device || classify (signal).kind != Mem::Device || (window != nullptr && classify (window).kind != Mem::Device))
+        return fail (FFT_B200_EINVAL, "fft_istft_overlap_add needs device pointers");
+    Tables t;
+    const int radix = radix_for (p->logM, false);
+    const int rc = plan_tables (p, t, radix);
+    if (rc != 0)
+        return rc;
+    // segmentation: a CTA per (channel, segment of frames).  More segments fill the last wave of CTAs better but
+    // every segment after a channel's first recomputes a halo of ceil (N / hop) - 1 frames; segments keep at
+    // least 8 groups of frames.  Pick the count with the best (wave occupancy) x (useful fraction of the frames).
+    const int per_cta = transforms_per_cta (p->logM, radix);
+    const int groups = (frames + per_cta - 1) / per_cta;
+    const int halo = (int) ((p->N + hop - 1) / hop) - 1;
+    const long long slots = 148LL * (radix == 32 ? 2 : 4);
+    int nseg = 1, seg_groups = groups;
+    double best = -1.0;
+    for (int cand = 1; cand <= 64 && cand <= (groups + 7) / 8; ++cand)
+    {
+        const int sg = (groups + cand - 1) / cand;
+        const int ns = (groups + sg - 1) / sg;
+        const long long ctas = (long long) channels * ns;
+        const double waves = (double) ((ctas + slots - 1) / slots);
+        const double occupancy = (double) ctas / (waves * (double) slots);
+        const double useful = (double) frames / ((double) frames + (double) (ns - 1) * halo);
+        if (occupancy * useful > best * 1.02) // prefer fewer segments unless clearly better
+        {
+            best = occupancy * useful;
+            nseg = ns;
+            seg_groups = sg;
+        }
+    }
+    FftArgs a {};
+    a.in = spectra;
+    a.out = signal;
+    a.in_inner = spec_frame_stride;
+    a.in_outer = spec_channel_stride;
+    a.out_inner = hop;
+    a.out_outer = channel_stride;
+    a.inner = frames;
+    a.batch = channels * frames;
+    a.tw = t.tw;
+    a.rtw = t.rtw;
+    a.window = window;
+    a.seg_frames = seg_groups * per_cta;
+    a.nseg = nseg;
+    a.scale = scale;
+    a.vec4 = ((hop & 3) == 0 && (channel_stride & 3) == 0 && (reinterpret_cast<uintptr_t> (signal) & 15) == 0) ? 1 : 0;
+    note_kernel ("cfb::istft_kernel<%d,%d,%d>", p->logM, radix, ordered != 0 ? 0 : p->logW);
+    const cudaError_t e = launch_istft (p->logM, ordered != 0 ? 0 : p->logW, radix, a, static_cast<cudaStream_t> (stream));
+    if (e != cudaSuccess)
+        return fail_cuda (e, "istft kernel launch");
+    return 0;
+}
+
 CFB_API int fft_convolve_unordered_batched (void* setup, const float* a, const float* b, float* ab, int batch, long long a_stride, long long b_stride, long long ab_stride, float scaling, void* stream)
 {
     Plan* p = as_plan (setup);
@@ -965,6 +1048,7 @@ CFB_API int fft_partitioned_convolve_step (void* setup, const float* windows, lo
     a.scaling = scaling;
     a.tw = t.tw;
     a.rtw = t.rtw;
+    note_kernel ("cfb::pconv_kernel<%d,%d>", p->logM, p->logW);
     const cudaError_t e = launch_pconv (p->logM, p->logW, a, static_cast<cudaStream_t> (stream));
     return e == cudaSuccess ? 0 : fail_cuda (e, "partitioned convolution kernel launch");
 }
@@ -1160,6 +1244,7 @@ CFB_API int fft_b200_set_tuning (const char* key, int value)
 }
 
 CFB_API const char* fft_b200_last_error (void) { return t_error; }
+CFB_API const char* fft_b200_last_kernel (void) { return t_last_kernel; }
 CFB_API void fft_b200_clear_error (void) { t_error[0] = 0; }
 CFB_API unsigned long long fft_b200_launch_count (void) { return cfb::launch_count(); }
 CFB_API int fft_b200_device_available (void) { return device_available() ? 1 : 0; }

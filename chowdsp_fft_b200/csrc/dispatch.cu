@@ -80,6 +80,17 @@ cudaError_t launch_stft_pipe (int logM, int logW, int radix, const FftArgs& args
         default: return cudaErrorInvalidValue;
     }
 }
+cudaError_t launch_istft (int logM, int logW, int radix, const FftArgs& args, cudaStream_t stream)
+{
+    switch (logM)
+    {
+#define X(n) \
+    case n: return launch_istft_##n (logW, radix, args, stream);
+        CFB_FOR_SIZES (X)
+#undef X
+        default: return cudaErrorInvalidValue;
+    }
+}
 int transforms_per_cta (int logM, int radix)
 {
     switch (logM)

@@ -23,6 +23,10 @@ cudaError_t launch_stft (int logM, int logW, int radix, const FftArgs& args, cud
 // persistent TMA-fed variant (stft_pipe_kernel): needs 0 < in_inner <= N, in_inner % 4 == 0, in_outer % 4 == 0 and a
 // 16-byte aligned signal; returns cudaErrorInvalidConfiguration when its buffers do not fit in shared memory
 cudaError_t launch_stft_pipe (int logM, int logW, int radix, const FftArgs& args, cudaStream_t stream);
+// overlap-add synthesis (istft_kernel): C2R of frames + window + sum at hop distance; args.in_inner / in_outer =
+// spectrum frame / channel strides, args.out_inner = hop (0 < hop <= N), args.out_outer = signal channel stride,
+// args.inner = frames per channel, args.seg_frames (multiple of transforms_per_cta) and args.nseg = segmentation
+cudaError_t launch_istft (int logM, int logW, int radix, const FftArgs& args, cudaStream_t stream);
 int transforms_per_cta (int logM, int radix);
 // persistent TMA-pipelined variant (pipe_kernels.cuh) for complex lengths 2^13 / 2^14, logW 0 or 3, plain batches
 // (args.inner == args.batch) whose input rows are 16-byte aligned
@@ -55,6 +59,7 @@ void count_launch();
     cudaError_t launch_pconv_##n (int logW, const PConvArgs& args, cudaStream_t stream);           \
     cudaError_t launch_stft_##n (int logW, int radix, FftArgs args, cudaStream_t stream);          \
     cudaError_t launch_stft_pipe_##n (int logW, int radix, const FftArgs& args, cudaStream_t stream); \
+    cudaError_t launch_istft_##n (int logW, int radix, const FftArgs& args, cudaStream_t stream);  \
     int transforms_per_cta_##n (int radix);                                                    \
     int has_radix32_##n();                                                                     \
     int stage_twiddle_len_##n (int radix);                                                     \

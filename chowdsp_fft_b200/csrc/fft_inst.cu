@@ -207,6 +207,56 @@ cudaError_t launch_stft_pipe_r (int logW, const FftArgs& a, cudaStream_t stream)
 }
 } // namespace
 
+namespace
+{
+template <int R, int LOGW>
+cudaError_t launch_istft_one (const FftArgs& a, cudaStream_t stream)
+{
+    using G = Geo<CFB_LOGM, R>;
+    using L = Launch<CFB_LOGM, R>;
+    auto kernel = istft_kernel<CFB_LOGM, R, LOGW>;
+    const int tail_n = 2 * G::M - (int) a.out_inner;
+    const int smem_bytes = (LOGW != 0 ? L::SMEM_BYTES_UNORD : L::SMEM_BYTES) + 2 * ((tail_n + 3) & ~3) * 4;
+    if (smem_bytes > 227 * 1024)
+        return cudaErrorInvalidConfiguration;
+    if (smem_bytes > 48 * 1024)
+    {
+        const cudaError_t e = cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e != cudaSuccess)
+            return e;
+    }
+    const long long grid = (long long) (a.batch / a.inner) * a.nseg;
+    if (grid <= 0)
+        return cudaSuccess;
+    kernel<<<(unsigned) grid, L::THREADS, smem_bytes, stream>>> (a);
+    count_launch();
+    return cudaGetLastError();
+}
+template <int R>
+cudaError_t launch_istft_r (int logW, const FftArgs& a, cudaStream_t stream)
+{
+    switch (logW)
+    {
+        case 0: return launch_istft_one<R, 0> (a, stream);
+        case 2: return launch_istft_one<R, 2> (a, stream);
+#if CFB_LOGM >= 6
+        case 3: return launch_istft_one<R, 3> (a, stream);
+#endif
+        default: return cudaErrorInvalidValue;
+    }
+}
+} // namespace
+
+// overlap-add synthesis (istft_kernel); a.seg_frames must be a multiple of transforms_per_cta
+cudaError_t CFB_CAT (launch_istft_, CFB_LOGM) (int logW, int radix, const FftArgs& a, cudaStream_t stream)
+{
+#if CFB_HAS_R32
+    if (radix == 32)
+        return launch_istft_r<32> (logW, a, stream);
+#endif
+    return radix == 16 ? launch_istft_r<16> (logW, a, stream) : cudaErrorInvalidValue;
+}
+
 // persistent TMA-fed frame-gather R2C (stft_pipe_kernel); fills in a.groups and a.land_bytes
 cudaError_t CFB_CAT (launch_stft_pipe_, CFB_LOGM) (int logW, int radix, const FftArgs& a, cudaStream_t stream)
 {

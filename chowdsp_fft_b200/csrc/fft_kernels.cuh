@@ -65,6 +65,10 @@ struct FftArgs
     int pf_ahead;
     // persistent frame-gather kernel (stft_pipe_kernel): bytes of its landing buffer, ((PER_CTA - 1) hop + N) * 4
     int land_bytes;
+    // overlap-add synthesis (istft_kernel): frames per segment (a multiple of the CTA's transforms), segments per
+    // channel, output scale
+    int seg_frames, nseg;
+    float scale;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -796,9 +800,10 @@ FFT_HD void staging_drain (const float* sf, float* __restrict__ out, int j, int 
 //   IN_UNION   (R2C / C2C_FWD): the stage-0 input is read from the shared-memory image `su` (natural order,
 //              unpadded, float2 units; it may alias `s`) and multiplied by the window `win` when non-null
 //   input_consumed (IN_UNION with more than one stage): hook run after the barrier that follows the stage-0 reads
-template <int LOGM, int R, int KIND, int LOGW, bool IN_STAGED, bool OUT_STAGED, bool HALF_OUT, bool IN_UNION = false, class Hook = NoHook>
+//   OUT_REGS   (C2R / C2C_BWD): do not store; hand the result registers (element j + m T in vout[m]) to the caller
+template <int LOGM, int R, int KIND, int LOGW, bool IN_STAGED, bool OUT_STAGED, bool HALF_OUT, bool IN_UNION = false, class Hook = NoHook, bool OUT_REGS = false>
 FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, bool active, int j, float2* s, const float2* __restrict__ tw_, const float2* __restrict__ rtw_,
-                      const float2* su = nullptr, const float2* __restrict__ win = nullptr, const Hook& input_consumed = Hook())
+                      const float2* su = nullptr, const float2* __restrict__ win = nullptr, const Hook& input_consumed = Hook(), float2* vout = nullptr)
 {
     using G = Geo<LOGM, R>;
     constexpr int DIR = (KIND == C2C_FWD || KIND == R2C) ? -1 : +1;
@@ -926,7 +931,14 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
         smem_was_read = true;
 
     // ---- epilogue -------------------------------------------------------------------------------
-    if constexpr (KIND == C2C_BWD || KIND == C2R || (KIND == C2C_FWD && ! UNORD))
+    if constexpr (OUT_REGS)
+    {
+        static_assert (! OUT_REGS || KIND == C2C_BWD || KIND == C2R, "OUT_REGS is for the inverse kinds");
+#pragma unroll
+        for (int m = 0; m < R; ++m)
+            vout[m] = v[m];
+    }
+    else if constexpr (KIND == C2C_BWD || KIND == C2R || (KIND == C2C_FWD && ! UNORD))
     {
         if (active)
         {
@@ -1145,6 +1157,156 @@ template <int LOGM, int R, int LOGW, bool UNION>
 __global__ void __launch_bounds__ (Launch<LOGM, R>::THREADS, Launch<LOGM, R>::MIN_BLOCKS) stft_kernel (const FftArgs a)
 {
     stft_body<LOGM, R, LOGW, UNION> (a);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Overlap-add synthesis (inverse STFT): C2R of the frames of a channel, optional synthesis window, frames summed at
+// hop distance into the output signal -- one kernel, owner-computes, no atomics:
+//   out[c][t] = scale * sum over frames f with 0 <= t - f hop < N of  window[t - f hop] * C2R (spectrum (c, f)) [t - f hop]
+// A CTA owns the frames [fs, fe) of one channel (a "segment") and walks through them PER_CTA at a time: every
+// transform leaves its windowed frame in its own shared-memory region; the CTA then sums the frames over the span
+// they cover plus the tail carried from the previous group, stores the PER_CTA * hop samples that are final and keeps
+// the remaining N - hop as the next tail.  Segments other than a channel's first start ceil (N / hop) - 1 frames early
+// (halo, recomputed, not stored) so that segments never need each other's partial sums.  This is the step the
+// reference leaves to the caller around fft_transform (BACKWARD) + fft_accumulate (chowdsp_fft.h:138,160;
+// test/test.cpp:214-218); fusing it removes the write + re-read of every frame (N / hop times the signal).
+// Grid = channels * nseg.  Needs 0 < hop <= N; the input frames are ordered or unordered spectra.
+// Shared memory: [PER_CTA exchange / frame buffers][2 tails of N - hop floats].
+// ---------------------------------------------------------------------------------------------
+// One overlap-add pass: out sample s = tail[s] + sum over the frames g < nact that cover it of frame_g[s - g hop].
+// Every thread owns the samples s = VEC (tid + k nthreads) .. + VEC, so no two threads touch the same sum; frames
+// are tried in order (nact <= 16 compares per sample group, no division).  Samples below `done` are final and go
+// to global memory (from first_owned on), the others become the next tail (or, at the end of a channel, output).
+template <int VEC>
+FFT_HD void ola_pass (const float* frames, int frame_stride, int nfl, int hop, int nact, int span, int done, int tail_n,
+                      const float* tail_cur, float* tail_new, float* __restrict__ sig, long long first_owned, bool keep_tail, int tid, int nthreads)
+{
+    for (int s = tid * VEC; s < span; s += nthreads * VEC)
+    {
+        float acc[VEC];
+        if (s < tail_n)
+        {
+            if constexpr (VEC == 4)
+            {
+                const float4 t = lds4 (tail_cur + s);
+                acc[0] = t.x; acc[1] = t.y; acc[2] = t.z; acc[3] = t.w;
+            }
+            else
+                acc[0] = lds1 (tail_cur + s);
+        }
+        else
+        {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i)
+                acc[i] = 0.f;
+        }
+#pragma unroll 4
+        for (int g = 0; g < nact; ++g)
+        {
+            const int n = s - g * hop;
+            if ((unsigned) n < (unsigned) nfl)
+            {
+                if constexpr (VEC == 4)
+                {
+                    const float4 x = lds4 (frames + g * frame_stride + n);
+                    acc[0] += x.x; acc[1] += x.y; acc[2] += x.z; acc[3] += x.w;
+                }
+                else
+                    acc[0] += lds1 (frames + g * frame_stride + n);
+            }
+        }
+        if (s < done || ! keep_tail)
+        {
+            if (s >= first_owned)
+            {
+                if constexpr (VEC == 4)
+                    *reinterpret_cast<float4*> (sig + s) = make_float4 (acc[0], acc[1], acc[2], acc[3]);
+                else
+                    sig[s] = acc[0];
+            }
+        }
+        else
+        {
+            if constexpr (VEC == 4)
+                sts4 (tail_new + (s - done), make_float4 (acc[0], acc[1], acc[2], acc[3]));
+            else
+                sts1 (tail_new + (s - done), acc[0]);
+        }
+    }
+}
+
+template <int LOGM, int R, int LOGW>
+FFT_HD void istft_body (const FftArgs& a)
+{
+    using G = Geo<LOGM, R>;
+    constexpr int T = G::T, NFL = 2 * G::M;
+    constexpr int SMEM_F2 = LOGW != 0 ? G::SMEM_F2_UNORD : G::SMEM_F2;
+    FFT_DYN_SMEM (float2, smem);
+
+    const int tid = (int) threadIdx.x, nthreads = (int) blockDim.x;
+    const int j = tid & (T - 1);
+    const int lt = tid / T;
+    const int per_cta = nthreads / T;
+    const int hop = (int) a.out_inner, frames = a.inner;
+    const int tail_n = NFL - hop;                           // samples carried between groups
+    float* tail0 = reinterpret_cast<float*> (smem + per_cta * SMEM_F2);
+    float* tail1 = tail0 + ((tail_n + 3) & ~3);
+    float2* fb = smem + lt * SMEM_F2;                       // this transform's exchange region, then its frame
+
+    const int c = (int) blockIdx.x / a.nseg;
+    const int seg = (int) blockIdx.x - c * a.nseg;
+    const int fs = seg * a.seg_frames;
+    const int fe = fs + a.seg_frames < frames ? fs + a.seg_frames : frames;
+    const int halo = (NFL + hop - 1) / hop - 1;
+    const int f_begin = fs - halo > 0 ? fs - halo : 0;
+    const long long own_start = (long long) fs * hop;       // first sample this CTA stores
+    const bool last_seg = fe == frames;
+    const float* __restrict__ spec = a.in + (long long) c * a.in_outer;
+    float* __restrict__ sig = a.out + (long long) c * a.out_outer;
+    const float2* __restrict__ win2 = reinterpret_cast<const float2*> (a.window);
+
+    for (int i = tid; i < tail_n; i += nthreads)
+        tail0[i] = 0.f;
+    float* tail_cur = tail0;
+    float* tail_new = tail1;
+    for (int f0 = f_begin; f0 < fe; f0 += per_cta)
+    {
+        const int nact = fe - f0 < per_cta ? fe - f0 : per_cta;
+        const int ltc = lt < nact ? lt : nact - 1;          // idle transforms redo the group's last frame; it is never summed
+        float2 v[R];
+        fft_core<LOGM, R, C2R, LOGW, false, false, false, false, NoHook, true> (spec + (long long) (f0 + ltc) * a.in_inner, nullptr, true, j, fb, a.tw, a.rtw,
+                                                                               nullptr, nullptr, NoHook(), v);
+        tsync<T, true>(); // the transform's last exchange has been read: its region becomes the frame buffer
+#pragma unroll
+        for (int m = 0; m < R; ++m)
+        {
+            float2 x = f2_mul (v[m], make_float2 (a.scale, a.scale));
+            if (win2 != nullptr)
+                x = f2_mul (x, __ldg (win2 + j + m * T));
+            sts2 (fb + j + m * T, x);
+        }
+        __syncthreads();
+        // ---- overlap-add over the span of this group; sample index s is relative to the group's first frame ----
+        const int span = (nact - 1) * hop + NFL, done = nact * hop;
+        const long long t0 = (long long) f0 * hop;
+        const bool keep_tail = ! (last_seg && f0 + nact == fe); // at the end of the channel the tail is output too
+        if (a.vec4)
+            ola_pass<4> (reinterpret_cast<const float*> (smem), SMEM_F2 * 2, NFL, hop, nact, span, done, tail_n, tail_cur, tail_new,
+                         sig + t0, own_start - t0, keep_tail, tid, nthreads);
+        else
+            ola_pass<1> (reinterpret_cast<const float*> (smem), SMEM_F2 * 2, NFL, hop, nact, span, done, tail_n, tail_cur, tail_new,
+                         sig + t0, own_start - t0, keep_tail, tid, nthreads);
+        __syncthreads();
+        float* sw = tail_cur;
+        tail_cur = tail_new;
+        tail_new = sw;
+    }
+}
+
+template <int LOGM, int R, int LOGW>
+__global__ void __launch_bounds__ (Launch<LOGM, R>::THREADS, Launch<LOGM, R>::MIN_BLOCKS) istft_kernel (const FftArgs a)
+{
+    istft_body<LOGM, R, LOGW> (a);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -49,6 +49,16 @@ int fft_transform_strided (void* setup, const float* input, float* output, int o
    Device pointers only; hop and channel_stride must be even. */
 int fft_stft_forward (void* setup, const float* signal, float* spectra, int channels, int frames, long long channel_stride, long long hop, long long out_channel_stride, long long out_frame_stride, const float* window, int ordered, void* stream);
 
+/* Overlap-add synthesis (inverse STFT) of `channels` signals from `frames` spectra each: the backward real transform
+   of the spectrum at spectra + c*spec_channel_stride + f*spec_frame_stride (N floats, ordered pffft packing or the
+   plan's unordered layout) is multiplied by scale and by window[0..N) when window is non-NULL, and added into
+   signal + c*channel_stride at offset f*hop.  Every one of the (frames-1)*hop + N output samples of a channel is
+   WRITTEN (the sum of the frames covering it), so the buffer needs no clearing.  Unnormalised like the reference:
+   scale = 1/N undoes fft_stft_forward for a rectangular window at hop = N.  This is the step the reference leaves
+   to its callers around fft_transform (BACKWARD) and fft_accumulate (chowdsp_fft.h:138,160); here it is one kernel,
+   owner-computes (no atomics, bit-reproducible).  0 < hop <= N, even spectrum strides, N <= 16384, device pointers. */
+int fft_istft_overlap_add (void* setup, const float* spectra, float* signal, int channels, int frames, long long spec_channel_stride, long long spec_frame_stride, long long channel_stride, long long hop, const float* window, float scale, int ordered, void* stream);
+
 /* batch x (ab += a*b*scaling) on unordered spectra; a stride of 0 shares that operand across the
    batch (e.g. one impulse response for all channels).  Replaces a loop over reference chowdsp_fft.h:154. */
 int fft_convolve_unordered_batched (void* setup, const float* dft_a, const float* dft_b, float* dft_ab, int batch, long long a_stride, long long b_stride, long long ab_stride, float scaling, void* stream);
@@ -116,6 +126,9 @@ int fft_b200_set_tuning (const char* key, int value);
 
 /* Number of CUDA kernels this library has launched in this process (all threads). */
 unsigned long long fft_b200_launch_count (void);
+/* Name (template instance) of the transform kernel the calling thread launched last, "" if none yet: which of the
+ * kernels in csrc/ a given size / kind / layout / alignment was routed to.  Diagnostic only (bench.py reports it). */
+const char* fft_b200_last_kernel (void);
 
 /* 1 if a CUDA device is usable from this process, else 0. */
 int fft_b200_device_available (void);

@@ -358,3 +358,21 @@ def np_partitioned_convolve(x, h, N: int, P: int, W: int, scaling: float | None 
             acc = np_convolve(fdl[:, (t - p) % P], h[:, p], acc, N, False, W, scaling)
         y[:, t * B:(t + 1) * B] = np_transform(acc, N, False, W, True, False)[:, B:]
     return y, fdl
+
+
+def np_istft_overlap_add(spectra, N: int, hop: int, W: int, ordered: bool, window=None, scale: float = 1.0) -> np.ndarray:
+    """Overlap-add synthesis restated as the caller-side loop the reference leaves to its users: per frame one
+    fft_transform / fft_transform_unordered (BACKWARD) (chowdsp_fft.h:138,145), a window multiply, and a running sum
+    of the overlapping parts at hop distance (fft_accumulate, chowdsp_fft.h:160, is the reference's primitive for
+    that sum; test/test.cpp:214-218).  spectra [channels, frames, N]; returns [channels, (frames-1)*hop + N]
+    float32, sums carried in float64."""
+    spectra = np.asarray(spectra, np.float32)
+    channels, frames, n = spectra.shape
+    assert n == N and 0 < hop <= N
+    fr = np_transform(spectra.reshape(-1, N), N, False, W, True, ordered).astype(np.float64).reshape(channels, frames, N) * scale
+    if window is not None:
+        fr = fr * np.asarray(window, np.float32).astype(np.float64)
+    out = np.zeros((channels, (frames - 1) * hop + N), np.float64)
+    for f in range(frames):
+        out[:, f * hop:f * hop + N] += fr[:, f]
+    return out.astype(np.float32)

@@ -281,6 +281,44 @@ int emu_stft_pipe (int logM, int radix, int unord, int logW, const float* in, fl
     return rc;
 }
 
+// overlap-add synthesis (istft_kernel): `channels` x `frames` spectra -> signals, segments of seg_groups CTA groups
+int emu_istft (int logM, int radix, int unord, int logW, const float* spec, float* sig, int channels, int frames, long long spec_channel_stride, long long spec_frame_stride, long long channel_stride, long long hop, const float* window, float scale, int seg_groups)
+{
+    auto run = [&] (auto logm_c, auto r_c, auto logw_c) -> int
+    {
+        constexpr int LOGM = decltype (logm_c)::value, R = decltype (r_c)::value, LOGW = decltype (logw_c)::value;
+        using G = Geo<LOGM, R>;
+        using L = Launch<LOGM, R>;
+        std::vector<float2> tw ((size_t) G::TW_LEN + 1), rtw ((size_t) G::M / 2 + 1);
+        fill_stage_twiddles<LOGM, R> (tw.data());
+        fill_real_twiddles (rtw.data(), G::M);
+        FftArgs a {};
+        a.in = spec; a.out = sig;
+        a.in_inner = spec_frame_stride; a.in_outer = spec_channel_stride; a.out_inner = hop; a.out_outer = channel_stride;
+        a.inner = frames; a.batch = channels * frames;
+        a.tw = tw.data(); a.rtw = rtw.data();
+        a.window = window;
+        a.scale = scale;
+        a.vec4 = ((hop & 3) == 0 && (channel_stride & 3) == 0 && (reinterpret_cast<uintptr_t> (sig) & 15) == 0) ? 1 : 0;
+        const int groups = (frames + L::PER_CTA - 1) / L::PER_CTA;
+        a.seg_frames = seg_groups * L::PER_CTA;
+        a.nseg = (groups + seg_groups - 1) / seg_groups;
+        const int tail_n = 2 * G::M - (int) hop;
+        const size_t smem_bytes = (size_t) (LOGW != 0 ? L::SMEM_BYTES_UNORD : L::SMEM_BYTES) + 2 * ((tail_n + 3) & ~3) * 4;
+        emu::g_log_smem = false;
+        emu::launch (istft_kernel<LOGM, R, LOGW>, dim3 ((unsigned) (channels * a.nseg)), dim3 (L::THREADS), smem_bytes, a);
+        return 0;
+    };
+    using std::integral_constant;
+    const int lw = unord ? logW : 0;
+    int rc = -1;
+#define CFB_EMU_IS(M, RR, W) if (logM == M && radix == RR && lw == W) rc = run (integral_constant<int, M> {}, integral_constant<int, RR> {}, integral_constant<int, W> {});
+    CFB_EMU_IS (4, 16, 0) CFB_EMU_IS (4, 16, 2) CFB_EMU_IS (6, 16, 0) CFB_EMU_IS (6, 16, 3) CFB_EMU_IS (8, 16, 0) CFB_EMU_IS (8, 16, 3)
+    CFB_EMU_IS (10, 16, 0) CFB_EMU_IS (10, 32, 0) CFB_EMU_IS (10, 32, 3) CFB_EMU_IS (12, 16, 0)
+#undef CFB_EMU_IS
+    return rc;
+}
+
 // fused partitioned-convolution step, real size N = 2^(logM+1)
 int emu_pconv (int logM, int logW, const float* in, long long in_stride, const float* ir, long long ir_ch_stride, float* fdl, long long fdl_ch_stride, float* out, long long out_stride, int channels, int P, int t, float scaling)
 {

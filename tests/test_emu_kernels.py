@@ -20,6 +20,7 @@ def emu():
     L.emu_accumulate.argtypes = [fp, fp, fp, C.c_longlong]
     L.emu_pipe.argtypes = [C.c_int, C.c_int, C.c_int, fp, fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_long)]
     L.emu_stft_pipe.argtypes = [C.c_int] * 4 + [fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 4 + [fp, C.c_int, C.c_int, C.POINTER(C.c_long)]
+    L.emu_istft.argtypes = [C.c_int] * 4 + [fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 4 + [fp, C.c_float, C.c_int]
     L.emu_stft.argtypes = [C.c_int] * 3 + [fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 4 + [fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_long)]
     return L
 
@@ -297,3 +298,28 @@ def test_emulated_persistent_stft(emu, oracle_mod, N, radix, hop, frames, ordere
         fr = fr * win
     want = o.np_transform(fr.reshape(-1, N).astype(np.float32), N, False, W, False, ordered).reshape(out.shape)
     assert o.rel_l2(out, want) < min(o.parity_tol(N), 4e-7)
+
+
+@pytest.mark.parametrize("N,radix,hop,frames,ordered,W,seg_groups", [(2048, 32, 512, 21, True, 8, 1), (2048, 32, 512, 21, False, 8, 2), (2048, 16, 2048, 5, True, 8, 1),
+                                                                     (512, 16, 96, 19, True, 8, 1), (512, 16, 130, 9, False, 8, 4), (128, 16, 32, 70, False, 8, 1),
+                                                                     (32, 16, 8, 45, True, 4, 1), (32, 16, 7, 40, False, 4, 2), (8192, 16, 1024, 5, True, 8, 2)])
+@pytest.mark.parametrize("windowed", [False, True])
+def test_emulated_istft_overlap_add(emu, oracle_mod, N, radix, hop, frames, ordered, W, seg_groups, windowed):
+    """Overlap-add synthesis kernel == C2R of every frame, window, sum at hop distance (oracle.np_istft_overlap_add):
+    segments with recomputed halos (seg_groups CTA groups per segment), ragged last groups, odd hops, every output
+    sample written exactly once (the output buffer starts as NaN)."""
+    o = oracle_mod
+    channels = 2
+    rng = np.random.default_rng(N + hop + 3)
+    x = rng.uniform(-1, 1, (channels * frames, N)).astype(np.float32)
+    spec = np.ascontiguousarray(o.np_transform(x, N, False, W, False, ordered).reshape(channels, frames, N))
+    win = (0.5 - 0.5 * np.cos(2 * np.pi * (np.arange(N) + 0.5) / N)).astype(np.float32)
+    samples = (frames - 1) * hop + N
+    pad = 4 if windowed else 3  # 4 keeps the channels 16-byte aligned: 128-bit overlap-add path when hop % 4 == 0
+    out = np.full((channels, samples + pad), np.nan, np.float32)
+    rc = emu.emu_istft(int(np.log2(N)) - 1, radix, 0 if ordered else 1, {8: 3, 4: 2}[W], spec.ctypes.data_as(fp), out.ctypes.data_as(fp),
+                       channels, frames, frames * N, N, samples + pad, hop, win.ctypes.data_as(fp) if windowed else None, 1.0 / N, seg_groups)
+    assert rc == 0
+    want = o.np_istft_overlap_add(spec, N, hop, W, ordered, win if windowed else None, 1.0 / N)
+    assert np.all(np.isnan(out[:, samples:]))  # nothing written past the end of a channel
+    assert o.rel_l2(out[:, :samples], want) < min(o.parity_tol(N), 4e-7)

@@ -295,6 +295,83 @@ def test_stft_forward_window_and_layouts(cf, oracle_mod, N, hop, frames, tail, p
     cf.fft_destroy_setup(s)
 
 
+@pytest.mark.parametrize("N,hop,frames", [(2048, 512, 37), (2048, 2048, 5), (512, 96, 19), (512, 130, 9), (128, 32, 70),
+                                          (32, 7, 41), (8192, 1024, 6), (16384, 4096, 3), (1024, 256, 1)])
+def test_istft_overlap_add(cf, oracle_mod, N, hop, frames):
+    """fft_istft_overlap_add == backward transform of every frame, window, sum at hop distance (the caller-side loop
+    around the reference API, oracle.np_istft_overlap_add): ordered and unordered spectra, with and without window,
+    ragged groups, odd hops; every output sample written exactly once (buffer starts as NaN, tail stays NaN)."""
+    o = oracle_mod
+    channels = 3
+    rng = np.random.default_rng(N + hop + 9)
+    x = rng.uniform(-1, 1, (channels * frames, N)).astype(np.float32)
+    win = (0.5 - 0.5 * np.cos(2 * np.pi * (np.arange(N) + 0.5) / N)).astype(np.float32)
+    W = o.simd_width(N, False, True)
+    samples = (frames - 1) * hop + N
+    s = cf.fft_new_setup(N, cf.FFT_REAL)
+    dw = dev(win)
+    try:
+        for ordered in (True, False):
+            spec = np.ascontiguousarray(o.np_transform(x, N, False, W, False, ordered).reshape(channels, frames, N))
+            dspec = dev(spec)
+            for w in (None, dw):
+                pad = 5 if w is None else 8  # 8 keeps the channels 16-byte aligned (128-bit overlap-add path)
+                out = torch.full((channels, samples + pad), float("nan"), device="cuda")
+                n0 = cf.launch_count()
+                cf.fft_istft_overlap_add(s, dspec, out, channels, frames, frames * N, N, samples + pad, hop, w, 1.0 / N, ordered)
+                torch.cuda.synchronize()
+                assert cf.launch_count() - n0 == 1
+                got = host(out)
+                assert np.all(np.isnan(got[:, samples:]))
+                want = o.np_istft_overlap_add(spec, N, hop, W, ordered, win if w is not None else None, 1.0 / N)
+                assert o.rel_l2(got[:, :samples], want) < o.parity_tol(N), (ordered, w is not None)
+    finally:
+        cf.fft_destroy_setup(s)
+
+
+def test_istft_rejects_what_does_not_fit(cf):
+    s = cf.fft_new_setup(32768, cf.FFT_REAL)
+    try:
+        buf = torch.zeros(3 * 32768, device="cuda")
+        with pytest.raises(cf.FFTError):
+            cf.fft_istft_overlap_add(s, buf, buf, 1, 2, 0, 32768, 65536, 8192, None, 1.0, True)
+        with pytest.raises(cf.FFTError):
+            cf.fft_istft_overlap_add(s, buf, buf, 1, 2, 0, 32768, 65536, 0, None, 1.0, True)
+    finally:
+        cf.fft_destroy_setup(s)
+
+
+def test_stft_istft_round_trip_at_config3_size(cf, oracle_mod):
+    """Size-independent property at BASELINE configs[2]'s full size per channel (480000 samples, N=2048, hop 512; 64
+    channels here): analysis with a Hann window, synthesis with the same window and scale 1/N, divided by the
+    window-overlap sum, returns the signal (wherever 4 frames overlap).  Few channels, so the synthesis kernel
+    splits every channel into segments with recomputed halos."""
+    N, hop, channels, samples = 2048, 512, 64, 480000
+    frames = (samples - N) // hop + 1
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.rand(channels, samples, device="cuda", generator=gen) * 2 - 1
+    n = torch.arange(N, device="cuda", dtype=torch.float64)
+    win = (0.5 - 0.5 * torch.cos(2 * np.pi * (n + 0.5) / N)).float()
+    s = cf.fft_new_setup(N, cf.FFT_REAL)
+    try:
+        spec = torch.empty(channels, frames, N, device="cuda")
+        cf.fft_stft_forward(s, x, spec, channels, frames, samples, hop, frames * N, N, win, False)
+        y = torch.zeros(channels, samples, device="cuda")
+        cf.fft_istft_overlap_add(s, spec, y, channels, frames, frames * N, N, samples, hop, win, 1.0 / N, False)
+        torch.cuda.synchronize()
+        covered = (frames - 1) * hop + N
+        wsum = torch.zeros(covered, device="cuda", dtype=torch.float64)
+        w2 = (win.double() ** 2)
+        for f in range(frames):
+            wsum[f * hop:f * hop + N] += w2
+        lo, hi = N, covered - N  # fully overlapped region
+        rec = y[:, lo:hi].double() / wsum[lo:hi]
+        err = torch.linalg.norm(rec - x[:, lo:hi].double()) / torch.linalg.norm(x[:, lo:hi].double())
+        assert float(err) < 2 * oracle_mod.parity_tol(N)
+    finally:
+        cf.fft_destroy_setup(s)
+
+
 def test_convolve_and_accumulate(cf, oracle_mod, ref_lib):
     o = oracle_mod
     rng = np.random.default_rng(5)
