@@ -9,7 +9,8 @@ from .api import (FFT_BACKWARD, FFT_COMPLEX, FFT_FORWARD, FFT_REAL, FFTError, al
                   fft_convolve_unordered, fft_convolve_unordered_batched, fft_destroy_setup, fft_dist_alloc, fft_dist_free, fft_dist_ipc_close,
                   fft_dist_ipc_export, fft_dist_ipc_open, fft_dist_phase, fft_dist_phase0_peer,
                   fft_large_factors, fft_new_setup,
-                  fft_new_setup_preallocated, fft_partitioned_convolve_step, fft_simd_width_bytes, fft_stft_forward, fft_istft_overlap_add, fft_transform, fft_transform_batched,
+                  fft_new_setup_preallocated, fft_partitioned_convolve_step, fft_simd_width_bytes, fft_stft_forward, fft_istft_overlap_add, fft_juce_perform_batched, fft_juce_real_forward_batched,
+                  fft_juce_real_inverse_batched, fft_transform, fft_transform_batched,
                   fft_transform_strided, fft_transform_unordered, last_kernel, launch_count, set_tuning)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

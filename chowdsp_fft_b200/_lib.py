@@ -56,6 +56,9 @@ def lib() -> C.CDLL:
         "fft_transform_strided": (i, [vp, vp, vp, i, i, ll, ll, ll, ll, i, i, vp]),
         "fft_stft_forward": (i, [vp, vp, vp, i, i, ll, ll, ll, ll, vp, i, vp]),
         "fft_istft_overlap_add": (i, [vp, vp, vp, i, i, ll, ll, ll, ll, vp, f, i, vp]),
+        "fft_juce_perform_batched": (i, [vp, vp, vp, i, ll, ll, i, vp]),
+        "fft_juce_real_forward_batched": (i, [vp, vp, i, ll, i, vp]),
+        "fft_juce_real_inverse_batched": (i, [vp, vp, i, ll, vp]),
         "fft_convolve_unordered_batched": (i, [vp, vp, vp, vp, i, ll, ll, ll, f, vp]),
         "fft_accumulate_batched": (i, [vp, vp, vp, vp, ll, vp]),
         "fft_partitioned_convolve_step": (i, [vp, vp, ll, vp, ll, vp, ll, vp, ll, i, i, i, f, vp]),
@@ -85,7 +88,7 @@ def lib() -> C.CDLL:
 EXPORTED = (
     "fft_bytes_required", "fft_new_setup", "fft_new_setup_preallocated", "fft_destroy_setup",
     "fft_simd_width_bytes", "fft_transform", "fft_transform_unordered", "fft_convolve_unordered",
-    "fft_accumulate", "aligned_malloc", "aligned_free", "fft_transform_batched", "fft_transform_strided", "fft_stft_forward", "fft_istft_overlap_add",
+    "fft_accumulate", "aligned_malloc", "aligned_free", "fft_transform_batched", "fft_transform_strided", "fft_stft_forward", "fft_istft_overlap_add", "fft_juce_perform_batched", "fft_juce_real_forward_batched", "fft_juce_real_inverse_batched",
     "fft_convolve_unordered_batched", "fft_accumulate_batched", "fft_partitioned_convolve_step", "fft_dist_phase", "fft_dist_phase0_peer", "fft_dist_alloc", "fft_dist_free", "fft_dist_ipc_export", "fft_dist_ipc_open", "fft_dist_ipc_close", "fft_large_factors", "fft_b200_set_tuning", "fft_b200_last_error", "fft_b200_last_kernel", "fft_b200_clear_error",
     "fft_b200_launch_count", "fft_b200_device_available",
 )

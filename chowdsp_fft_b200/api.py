@@ -165,6 +165,21 @@ def fft_istft_overlap_add(setup: int, spectra, signal, channels: int, frames: in
                                        _stream(stream)))
 
 
+def fft_juce_perform_batched(setup: int, input, output, batch: int, in_stride: int, out_stride: int, inverse: bool, stream=None) -> None:
+    """juce::dsp::FFT::perform semantics (chowdsp_fft_juce.cpp:32-46), batched: inverse scaled by 1/N."""
+    _check(lib().fft_juce_perform_batched(setup, _addr(input), _addr(output), batch, in_stride, out_stride, int(inverse), _stream(stream)))
+
+
+def fft_juce_real_forward_batched(setup: int, inout, batch: int, stride: int, ignore_negative_freqs: bool, stream=None) -> None:
+    """performRealOnlyForwardTransform semantics (chowdsp_fft_juce.cpp:48-66), batched, in place."""
+    _check(lib().fft_juce_real_forward_batched(setup, _addr(inout), batch, stride, int(ignore_negative_freqs), _stream(stream)))
+
+
+def fft_juce_real_inverse_batched(setup: int, inout, batch: int, stride: int, stream=None) -> None:
+    """performRealOnlyInverseTransform semantics (chowdsp_fft_juce.cpp:68-84), batched, in place."""
+    _check(lib().fft_juce_real_inverse_batched(setup, _addr(inout), batch, stride, _stream(stream)))
+
+
 def fft_convolve_unordered_batched(setup: int, dft_a, dft_b, dft_ab, batch: int, a_stride: int, b_stride: int,
                                    ab_stride: int, scaling: float, stream=None) -> None:
     _check(lib().fft_convolve_unordered_batched(setup, _addr(dft_a), _addr(dft_b), _addr(dft_ab), batch,

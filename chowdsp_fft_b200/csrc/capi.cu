@@ -118,6 +118,35 @@ int get_tables (int device, int logM, bool real, Tables& out, int radix = 16)
     return 0;
 }
 
+// tables of the generic mixed-radix kernel, per (device, complex length, needs-real-split)
+std::map<uint64_t, Tables> g_mixed_tables;
+int get_mixed_tables (int device, int M, bool real, Tables& out)
+{
+    const uint64_t key = ((uint64_t) device << 40) | ((uint64_t) M << 1) | (real ? 1u : 0u);
+    std::lock_guard<std::mutex> lock (g_tables_mutex);
+    auto it = g_mixed_tables.find (key);
+    if (it != g_mixed_tables.end())
+    {
+        out = it->second;
+        return 0;
+    }
+    Tables t;
+    std::vector<float2> w ((size_t) M);
+    fill_mixed_twiddles (w.data(), M);
+    CFB_CUDA (cudaMalloc (&t.tw, sizeof (float2) * w.size()));
+    CFB_CUDA (cudaMemcpy (t.tw, w.data(), sizeof (float2) * w.size(), cudaMemcpyHostToDevice));
+    if (real)
+    {
+        std::vector<float2> r ((size_t) M / 2 + 1);
+        fill_mixed_real_twiddles (r.data(), M);
+        CFB_CUDA (cudaMalloc (&t.rtw, sizeof (float2) * r.size()));
+        CFB_CUDA (cudaMemcpy (t.rtw, r.data(), sizeof (float2) * r.size(), cudaMemcpyHostToDevice));
+    }
+    g_mixed_tables[key] = t;
+    out = t;
+    return 0;
+}
+
 // two-level tables W_(2^n)^e = lo[e & mask] * hi[e >> lobits] for the multi-pass (large) transforms
 struct BigTables
 {
@@ -166,6 +195,8 @@ struct Plan
     int logW; // unordered layout: 3 = 8-lane, 2 = 4-lane
     int owns_memory;
     int home_device;
+    int mixed;   // N = 2^a 3^b 5^c, not a power of two: generic mixed-radix kernel (mixed_kernels.cuh); logM is unused
+    int M;       // complex points per transform (N, or N/2 for real plans)
     Tables tables[2][kMaxDevices]; // [radix 16 | 32], filled lazily per device (guarded by g_tables_mutex through get_tables)
     bool have[2][kMaxDevices];
 };
@@ -180,9 +211,18 @@ int ilog2i (int v)
 
 // reference size rules: common.hpp:168-177 (+ AVX-then-SSE fallback, chowdsp_fft.cpp:262-273);
 // powers of two only (north star), one CTA-resident transform (<= 2^14 complex points).
+bool is_235 (int N)
+{
+    if (N <= 0)
+        return false;
+    for (int r : { 2, 3, 5 })
+        while (N % r == 0)
+            N /= r;
+    return N == 1;
+}
 int choose_width (int N, bool is_complex, bool use_avx)
 {
-    if (N <= 0 || (N & (N - 1)) != 0)
+    if (! is_235 (N))
         return 0;
     for (int W = use_avx ? 8 : 4; W >= 4; W /= 2)
         if (N % (is_complex ? W * W : 2 * W * W) == 0)
@@ -216,6 +256,8 @@ int plan_tables (Plan* p, Tables& t, int radix = 16)
     CFB_CUDA (cudaGetDevice (&dev));
     if (dev < 0 || dev >= kMaxDevices)
         return fail (chowdsp::fft::FFT_B200_EINVAL, "device index %d out of range", dev);
+    if (p->mixed)
+        return get_mixed_tables (dev, p->M, ! p->is_complex, t);
     if (p->logM > kMaxLogM)
     {
         t = Tables {};
@@ -489,8 +531,37 @@ int enqueue_large (Plan* p, const float* in, float* out, int batch, long long in
 
 int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inner, long long in_outer, long long in_inner, long long out_outer, long long out_inner, int direction, bool ordered, cudaStream_t stream, const float* window = nullptr)
 {
-    if (window != nullptr && (p->logM > kMaxLogM || p->is_complex || direction != chowdsp::fft::FFT_FORWARD))
-        return fail (chowdsp::fft::FFT_B200_EINVAL, "windowed transforms need a REAL single-kernel plan and FFT_FORWARD");
+    if (window != nullptr && (p->mixed || p->logM > kMaxLogM || p->is_complex || direction != chowdsp::fft::FFT_FORWARD))
+        return fail (chowdsp::fft::FFT_B200_EINVAL, "windowed transforms need a REAL single-kernel power-of-two plan and FFT_FORWARD");
+    if (p->mixed)
+    {
+        if ((in_inner & 1) != 0 || (out_inner & 1) != 0 || (in_outer & 1) != 0 || (out_outer & 1) != 0)
+            return fail (chowdsp::fft::FFT_B200_EINVAL, "mixed-radix transforms need even strides (8-byte aligned transforms)");
+        Tables mt;
+        const int mrc = plan_tables (p, mt);
+        if (mrc != 0)
+            return mrc;
+        MixedArgs ma {};
+        ma.M = p->M;
+        ma.nstages = mixed_factor (p->M, ma.radix);
+        ma.wtab = mt.tw;
+        ma.rtab = mt.rtw;
+        ma.kind = kind_of (p, direction);
+        ma.W = ordered ? 0 : (1 << p->logW);
+        note_kernel ("cfb::mixed_kernel M=%d %s W=%d", p->M, kKindNames[ma.kind], ma.W);
+        for (int o = 0; o < outer; ++o) // two-level batches: one launch per outer index
+        {
+            ma.in = in + (long long) o * in_outer;
+            ma.out = out + (long long) o * out_outer;
+            ma.in_stride = in_inner;
+            ma.out_stride = out_inner;
+            ma.batch = inner;
+            const cudaError_t me = launch_mixed (ma, stream);
+            if (me != cudaSuccess)
+                return fail_cuda (me, "mixed-radix kernel launch");
+        }
+        return 0;
+    }
     if (p->logM > kMaxLogM)
     {
         if ((in_inner & 1) != 0 || (out_inner & 1) != 0 || (in_outer & 1) != 0 || (out_outer & 1) != 0)
@@ -746,10 +817,14 @@ CFB_API void* fft_new_setup_preallocated (int N, fft_transform_t transform, void
     }
     const bool is_complex = transform == FFT_COMPLEX;
     const int W = choose_width (N, is_complex, use_avx_if_available);
-    const int logM = W == 0 ? -1 : ilog2i (N) - (is_complex ? 0 : 1);
-    if (W == 0 || logM < kMinLogM || logM > kMaxLargeLog - (is_complex ? 0 : 1))
+    const bool pow2 = N > 0 && (N & (N - 1)) == 0;
+    const int logM = (W == 0 || ! pow2) ? -1 : ilog2i (N) - (is_complex ? 0 : 1);
+    const int M = is_complex ? N : N / 2;
+    const bool size_ok = W != 0 && (pow2 ? (logM >= kMinLogM && logM <= kMaxLargeLog - (is_complex ? 0 : 1)) : M <= kMixedMaxM);
+    if (! size_ok)
     {
-        fail (FFT_B200_EINVAL, "unsupported FFT size N=%d (%s): need a power of two, %s", N, is_complex ? "complex" : "real", is_complex ? "16 <= N <= 2^28" : "32 <= N <= 2^28");
+        fail (FFT_B200_EINVAL, "unsupported FFT size N=%d (%s): need %s, as a power of two up to 2^28 or as 2^a 3^b 5^c up to %d",
+              N, is_complex ? "complex" : "real", is_complex ? "a multiple of 16" : "a multiple of 32", is_complex ? kMixedMaxM : 2 * kMixedMaxM);
         return nullptr;
     }
     if (! device_available())
@@ -762,6 +837,8 @@ CFB_API void* fft_new_setup_preallocated (int N, fft_transform_t transform, void
     p->N = N;
     p->is_complex = is_complex ? 1 : 0;
     p->logM = logM;
+    p->mixed = pow2 ? 0 : 1;
+    p->M = M;
     p->logW = W == 8 ? 3 : 2;
     p->owns_memory = 0;
     p->magic = kMagic;
@@ -943,8 +1020,8 @@ CFB_API int fft_istft_overlap_add (void* setup, const float* spectra, float* sig
     Plan* p = as_plan (setup);
     if (p == nullptr)
         return FFT_B200_EINVAL;
-    if (p->is_complex || p->logM > 13)
-        return fail (FFT_B200_EINVAL, "fft_istft_overlap_add needs a REAL plan with N <= 16384 (frame buffers + carried tails must fit in shared memory)");
+    if (p->is_complex || p->mixed || p->logM > 13)
+        return fail (FFT_B200_EINVAL, "fft_istft_overlap_add needs a REAL power-of-two plan with N <= 16384 (frame buffers + carried tails must fit in shared memory)");
     if (spectra == nullptr || signal == nullptr || channels < 0 || frames < 0 || hop <= 0 || hop > p->N || (long long) channels * frames > 0x7fffffffLL)
         return fail (FFT_B200_EINVAL, "fft_istft_overlap_add: bad arguments (0 < hop <= N)");
     if ((spec_frame_stride & 1) != 0 || (spec_channel_stride & 1) != 0)
@@ -1005,6 +1082,74 @@ CFB_API int fft_istft_overlap_add (void* setup, const float* spectra, float* sig
     return 0;
 }
 
+// ---- JUCE-convention wrappers (reference chowdsp_fft_juce/chowdsp_fft_juce.cpp:32-86), batched ----
+namespace
+{
+int juce_launch (Plan* p, int kind, const float* in, float* out, int batch, long long in_stride, long long out_stride, cudaStream_t stream)
+{
+    if (p->mixed || p->logM > kMaxLogM)
+        return fail (FFT_B200_EINVAL, "the JUCE-convention entry points need a single-kernel power-of-two plan (N <= 16384 complex, 32768 real)");
+    if ((in_stride & 1) != 0 || (out_stride & 1) != 0)
+        return fail (FFT_B200_EINVAL, "the JUCE-convention entry points need even strides");
+    if (batch == 0)
+        return 0;
+    if (classify (in).kind != Mem::Device || classify (out).kind != Mem::Device)
+        return fail (FFT_B200_EINVAL, "the JUCE-convention entry points need device pointers");
+    Tables t;
+    const int radix = radix_for (p->logM, p->is_complex != 0);
+    const int rc = plan_tables (p, t, radix);
+    if (rc != 0)
+        return rc;
+    FftArgs a {};
+    a.in = in;
+    a.out = out;
+    a.in_inner = in_stride;
+    a.out_inner = out_stride;
+    a.inner = a.batch = batch;
+    a.tw = t.tw;
+    a.rtw = t.rtw;
+    note_kernel ("cfb::fft_kernel_juce<%d,%d,%s>", p->logM, radix, kKindNames[kind]);
+    const cudaError_t e = launch_fft_juce (p->logM, kind, radix, a, stream);
+    return e == cudaSuccess ? 0 : fail_cuda (e, "JUCE-convention kernel launch");
+}
+} // namespace
+
+CFB_API int fft_juce_perform_batched (void* setup, const float* input, float* output, int batch, long long in_stride, long long out_stride, int inverse, void* stream)
+{
+    Plan* p = as_plan (setup);
+    if (p == nullptr)
+        return FFT_B200_EINVAL;
+    if (! p->is_complex || input == nullptr || output == nullptr || batch < 0)
+        return fail (FFT_B200_EINVAL, "fft_juce_perform_batched needs a COMPLEX plan and non-null buffers");
+    if (! inverse) // forward: the conventions coincide with fft_transform
+        return transform_any (setup, input, output, batch, in_stride, out_stride, FFT_FORWARD, true, static_cast<cudaStream_t> (stream), false);
+    return juce_launch (p, C2C_BWD, input, output, batch, in_stride, out_stride, static_cast<cudaStream_t> (stream));
+}
+
+CFB_API int fft_juce_real_forward_batched (void* setup, float* inout, int batch, long long stride, int ignore_negative_freqs, void* stream)
+{
+    Plan* p = as_plan (setup);
+    if (p == nullptr)
+        return FFT_B200_EINVAL;
+    if (p->is_complex || inout == nullptr || batch < 0 || (batch > 1 && stride < (ignore_negative_freqs ? p->N + 2 : 2LL * p->N)))
+        return fail (FFT_B200_EINVAL, "fft_juce_real_forward_batched needs a REAL plan and rows of at least %s floats", ignore_negative_freqs ? "N + 2" : "2 N");
+    int rc = juce_launch (p, R2C, inout, inout, batch, stride, stride, static_cast<cudaStream_t> (stream));
+    if (rc != 0 || ignore_negative_freqs || batch == 0)
+        return rc;
+    const cudaError_t e = launch_juce_mirror (inout, stride, p->N / 2, batch, static_cast<cudaStream_t> (stream));
+    return e == cudaSuccess ? 0 : fail_cuda (e, "negative-frequency mirror launch");
+}
+
+CFB_API int fft_juce_real_inverse_batched (void* setup, float* inout, int batch, long long stride, void* stream)
+{
+    Plan* p = as_plan (setup);
+    if (p == nullptr)
+        return FFT_B200_EINVAL;
+    if (p->is_complex || inout == nullptr || batch < 0 || (batch > 1 && stride < p->N + 2))
+        return fail (FFT_B200_EINVAL, "fft_juce_real_inverse_batched needs a REAL plan and rows of at least N + 2 floats");
+    return juce_launch (p, C2R, inout, inout, batch, stride, stride, static_cast<cudaStream_t> (stream));
+}
+
 CFB_API int fft_convolve_unordered_batched (void* setup, const float* a, const float* b, float* ab, int batch, long long a_stride, long long b_stride, long long ab_stride, float scaling, void* stream)
 {
     Plan* p = as_plan (setup);
@@ -1021,8 +1166,8 @@ CFB_API int fft_partitioned_convolve_step (void* setup, const float* windows, lo
         return FFT_B200_EINVAL;
     if (p->is_complex)
         return fail (FFT_B200_EINVAL, "fft_partitioned_convolve_step needs a REAL plan");
-    if (p->logM > kMaxLogM)
-        return fail (FFT_B200_EINVAL, "fft_partitioned_convolve_step: block size N=%d is larger than the single-kernel limit 32768", p->N);
+    if (p->mixed || p->logM > kMaxLogM)
+        return fail (FFT_B200_EINVAL, "fft_partitioned_convolve_step: block size N=%d must be a power of two up to the single-kernel limit 32768", p->N);
     if (windows == nullptr || ir == nullptr || fdl == nullptr || output == nullptr || channels < 0 || partitions < 1 || block_index < 0)
         return fail (FFT_B200_EINVAL, "fft_partitioned_convolve_step: bad arguments");
     if (channels == 0)

@@ -37,6 +37,17 @@ cudaError_t launch_pconv (int logM, int logW, const PConvArgs& args, cudaStream_
         default: return cudaErrorInvalidValue;
     }
 }
+cudaError_t launch_fft_juce (int logM, int kind, int radix, const FftArgs& args, cudaStream_t stream)
+{
+    switch (logM)
+    {
+#define X(n) \
+    case n: return launch_fft_juce_##n (kind, radix, args, stream);
+        CFB_FOR_SIZES (X)
+#undef X
+        default: return cudaErrorInvalidValue;
+    }
+}
 bool has_pipe (int logM) { return logM == 13 || logM == 14; }
 cudaError_t launch_pipe (int logM, int kind, int logW, const FftArgs& args, cudaStream_t stream)
 {
@@ -125,6 +136,29 @@ void fill_stage_twiddles_rt (int logM, int radix, float2* tw)
     }
 }
 
+cudaError_t launch_mixed (const MixedArgs& args, cudaStream_t stream)
+{
+    MixedArgs a = args;
+    if (a.M > kMixedMaxM || a.nstages <= 0)
+        return cudaErrorInvalidValue;
+    int threads = 0;
+    mixed_geometry (a.M, threads, a.tg);
+    const int per_cta = threads / a.tg;
+    const int smem_bytes = 16 * a.M * per_cta;
+    if (smem_bytes > 48 * 1024)
+    {
+        const cudaError_t e = cudaFuncSetAttribute (mixed_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e != cudaSuccess)
+            return e;
+    }
+    if (a.batch <= 0)
+        return cudaSuccess;
+    const long long ctas = ((long long) a.batch + per_cta - 1) / per_cta, cap = 148LL * 16;
+    mixed_kernel<0><<<(unsigned) (ctas < cap ? ctas : cap), threads, smem_bytes, stream>>> (a);
+    count_launch();
+    return cudaGetLastError();
+}
+
 static int elementwise_grid (long long items, int threads)
 {
     // enough CTAs to fill 148 SMs x 8 resident CTAs, grid-stride beyond that
@@ -140,6 +174,16 @@ cudaError_t launch_convolve (const float* a, const float* b, float* ab, long lon
     const ConvArgs p { a, b, ab, a_stride, b_stride, ab_stride, nfloats, batch, logW, is_real ? 1 : 0, scaling };
     const long long items = (long long) (nfloats >> 3) * batch;
     convolve_kernel<<<elementwise_grid (items, 256), 256, 0, stream>>> (p);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_juce_mirror (float* data, long long stride, int M, int batch, cudaStream_t stream)
+{
+    const long long total = (long long) batch * (M - 1);
+    if (total <= 0)
+        return cudaSuccess;
+    juce_mirror_kernel<<<elementwise_grid (total, 256), 256, 0, stream>>> (data, stride, M, total);
     count_launch();
     return cudaGetLastError();
 }

@@ -5,6 +5,7 @@
 #include "fft_kernels.cuh"
 #include "pconv_kernel.cuh"
 #include "large_kernels.cuh"
+#include "mixed_kernels.cuh"
 
 namespace cfb
 {
@@ -17,6 +18,10 @@ constexpr int kMaxLogM = 14; // 16384 complex points: the largest single-kernel 
 // logW: 0 = ordered output/input, 2 / 3 = the reference's 4- / 8-lane unordered layout
 cudaError_t launch_fft (int logM, int kind, int logW, int radix, const FftArgs& args, cudaStream_t stream);
 bool has_radix32 (int logM);
+// the same transform with the conventions of the reference's JUCE adapter (fft_kernel_juce): ordered layouts,
+// kind R2C (Nyquist as bin N/2), C2R and C2C_BWD (scaled by 1/N); and the optional negative-frequency mirror
+cudaError_t launch_fft_juce (int logM, int kind, int radix, const FftArgs& args, cudaStream_t stream);
+cudaError_t launch_juce_mirror (float* data, long long stride, int M, int batch, cudaStream_t stream);
 // frame-gather R2C (STFT analysis): transform (o, i) reads in + o in_outer + i in_inner with 0 < in_inner <= N,
 // optional window; one CTA gathers the union of its frames once (stft_kernel)
 cudaError_t launch_stft (int logM, int logW, int radix, const FftArgs& args, cudaStream_t stream);
@@ -41,6 +46,9 @@ void fill_stage_twiddles_rt (int logM, int radix, float2* tw);
 // fused partitioned-convolution block step for a REAL plan of 2^(logM+1) samples (one CTA per channel)
 cudaError_t launch_pconv (int logM, int logW, const PConvArgs& args, cudaStream_t stream);
 
+// generic mixed-radix transform (N = 2^a 3^b 5^c, not a power of two), one CTA per transform
+cudaError_t launch_mixed (const MixedArgs& args, cudaStream_t stream);
+
 // multi-pass (large transform) kernels, large_inst.cu
 cudaError_t launch_tile (int logL, int C, int dir, bool load_j_fast, const TileArgs& args, cudaStream_t stream);
 cudaError_t launch_real_pass (int dir, const RealPassArgs& args, int batch, cudaStream_t stream);
@@ -56,6 +64,7 @@ void count_launch();
 // per-size entry points, one translation unit each (fft_inst.cu compiled with -DCFB_LOGM=n)
 #define CFB_DECL_INST(n)                                                                       \
     cudaError_t launch_fft_##n (int kind, int logW, int radix, const FftArgs& args, cudaStream_t stream); \
+    cudaError_t launch_fft_juce_##n (int kind, int radix, const FftArgs& args, cudaStream_t stream); \
     cudaError_t launch_pconv_##n (int logW, const PConvArgs& args, cudaStream_t stream);           \
     cudaError_t launch_stft_##n (int logW, int radix, FftArgs args, cudaStream_t stream);          \
     cudaError_t launch_stft_pipe_##n (int logW, int radix, const FftArgs& args, cudaStream_t stream); \

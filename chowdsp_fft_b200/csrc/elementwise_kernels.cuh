@@ -68,4 +68,18 @@ __global__ void __launch_bounds__ (256) accumulate_kernel (const float* a, const
     }
 }
 
+// JUCE convention for real spectra when the caller wants the redundant negative frequencies as well
+// (chowdsp_fft_juce.cpp:58-61): bin M + i = conj (bin M - i), i = 1 .. M-1, rows of 2 M complex bins
+__global__ void __launch_bounds__ (256) juce_mirror_kernel (float* data, long long stride, int M, long long total)
+{
+    for (long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long) gridDim.x * blockDim.x)
+    {
+        const long long row = t / (M - 1);
+        const int i = 1 + (int) (t - row * (M - 1));
+        float2* d = reinterpret_cast<float2*> (data + row * stride);
+        const float2 v = d[M - i];
+        d[M + i] = make_float2 (v.x, -v.y);
+    }
+}
+
 } // namespace cfb

@@ -80,6 +80,49 @@ cudaError_t CFB_CAT (launch_fft_, CFB_LOGM) (int kind, int logW, int radix, cons
 
 namespace
 {
+template <int R, int KIND>
+cudaError_t launch_juce_one (const FftArgs& a, cudaStream_t stream)
+{
+    using L = Launch<CFB_LOGM, R>;
+    auto kernel = fft_kernel_juce<CFB_LOGM, R, KIND>;
+    constexpr int smem_bytes = L::SMEM_BYTES;
+    if (smem_bytes > 48 * 1024)
+    {
+        const cudaError_t e = cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e != cudaSuccess)
+            return e;
+    }
+    if (a.batch <= 0)
+        return cudaSuccess;
+    const unsigned grid = (unsigned) (((long long) a.batch + L::PER_CTA - 1) / L::PER_CTA);
+    kernel<<<grid, L::THREADS, smem_bytes, stream>>> (a);
+    count_launch();
+    return cudaGetLastError();
+}
+template <int R>
+cudaError_t launch_juce_r (int kind, const FftArgs& a, cudaStream_t stream)
+{
+    switch (kind)
+    {
+        case C2C_BWD: return launch_juce_one<R, C2C_BWD> (a, stream);
+        case R2C: return launch_juce_one<R, R2C> (a, stream);
+        case C2R: return launch_juce_one<R, C2R> (a, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+} // namespace
+
+cudaError_t CFB_CAT (launch_fft_juce_, CFB_LOGM) (int kind, int radix, const FftArgs& a, cudaStream_t stream)
+{
+#if CFB_HAS_R32
+    if (radix == 32)
+        return launch_juce_r<32> (kind, a, stream);
+#endif
+    return radix == 16 ? launch_juce_r<16> (kind, a, stream) : cudaErrorInvalidValue;
+}
+
+namespace
+{
 template <int LOGW>
 cudaError_t launch_pconv_one (const PConvArgs& a, cudaStream_t stream)
 {

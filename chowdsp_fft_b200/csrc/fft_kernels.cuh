@@ -801,7 +801,11 @@ FFT_HD void staging_drain (const float* sf, float* __restrict__ out, int j, int 
 //              unpadded, float2 units; it may alias `s`) and multiplied by the window `win` when non-null
 //   input_consumed (IN_UNION with more than one stage): hook run after the barrier that follows the stage-0 reads
 //   OUT_REGS   (C2R / C2C_BWD): do not store; hand the result registers (element j + m T in vout[m]) to the caller
-template <int LOGM, int R, int KIND, int LOGW, bool IN_STAGED, bool OUT_STAGED, bool HALF_OUT, bool IN_UNION = false, class Hook = NoHook, bool OUT_REGS = false>
+//   FMT = 1    (ordered layouts): the conventions of the reference's JUCE adapter (chowdsp_fft_juce/chowdsp_fft_juce.cpp:
+//              32-86) instead of pffft's -- real spectra as N/2 + 1 interleaved complex bins (Nyquist at float 2M, the
+//              imaginary parts of DC and Nyquist zero) rather than Nyquist packed into float 1, and inverse transforms
+//              (C2R, C2C_BWD) scaled by 1/N
+template <int LOGM, int R, int KIND, int LOGW, bool IN_STAGED, bool OUT_STAGED, bool HALF_OUT, bool IN_UNION = false, class Hook = NoHook, bool OUT_REGS = false, int FMT = 0>
 FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, bool active, int j, float2* s, const float2* __restrict__ tw_, const float2* __restrict__ rtw_,
                       const float2* su = nullptr, const float2* __restrict__ win = nullptr, const Hook& input_consumed = Hook(), float2* vout = nullptr)
 {
@@ -897,6 +901,8 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
                 v[m] = ldg_stream (lo + m * T);
                 xb[m] = ldg_stream (ph);
             }
+            if (FMT == 1 && j == 0)
+                v[0].y = ldg_stream (reinterpret_cast<const float2*> (in) + M).x; // Nyquist lives in bin M, not in float 1
         }
         const float2 wj = __ldg (a.rtw + j);
 #pragma unroll
@@ -943,9 +949,10 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
         if (active)
         {
             float2* __restrict__ out2 = reinterpret_cast<float2*> (out) + j;
+            constexpr float inv_n = 1.f / (float) (KIND == C2R ? 2 * M : M);
 #pragma unroll
             for (int m = (HALF_OUT ? R / 2 : 0); m < R; ++m)
-                out2[m * T] = v[m];
+                out2[m * T] = (FMT == 1 && KIND != C2C_FWD) ? f2_mul (v[m], make_float2 (inv_n, inv_n)) : v[m];
         }
     }
     else if constexpr (KIND == C2C_FWD)
@@ -999,6 +1006,11 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
             }
             else if (active)
             {
+                if (FMT == 1 && special)
+                {
+                    reinterpret_cast<float2*> (out)[M] = make_float2 (xa.y, 0.f); // Nyquist as bin M
+                    xa.y = 0.f;
+                }
                 lo[m * T] = xa;
                 float2* ph = special ? reinterpret_cast<float2*> (out) + M / 2 : hi - m * T + T;
                 *ph = xm;
@@ -1017,7 +1029,7 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
 // the batched transform kernel.  blockDim.x = T * (transforms per CTA); dynamic smem = transforms per
 // CTA * SMEM_F2 * 8 bytes.
 // ---------------------------------------------------------------------------------------------
-template <int LOGM, int R, int KIND, int LOGW>
+template <int LOGM, int R, int KIND, int LOGW, int FMT = 0>
 FFT_HD void fft_body (const FftArgs& a)
 {
     using G = Geo<LOGM, R>;
@@ -1056,7 +1068,7 @@ FFT_HD void fft_body (const FftArgs& a)
             prefetch_transform_l2<G> (a.in + (long long) no * a.in_outer + (long long) ni * a.in_inner, j);
         }
     }
-    fft_core<LOGM, R, KIND, LOGW, false, false, false> (in, out, active, j, smem + lt * SMEM_F2, a.tw, a.rtw);
+    fft_core<LOGM, R, KIND, LOGW, false, false, false, false, NoHook, false, FMT> (in, out, active, j, smem + lt * SMEM_F2, a.tw, a.rtw);
 }
 
 // threads per CTA / occupancy targets
@@ -1076,6 +1088,12 @@ template <int LOGM, int R, int KIND, int LOGW>
 __global__ void __launch_bounds__ (Launch<LOGM, R>::THREADS, Launch<LOGM, R>::MIN_BLOCKS) fft_kernel (const FftArgs a)
 {
     fft_body<LOGM, R, KIND, LOGW> (a);
+}
+// the same transform with the JUCE adapter's conventions (fft_core: FMT = 1), ordered layouts, R2C / C2R / C2C_BWD
+template <int LOGM, int R, int KIND>
+__global__ void __launch_bounds__ (Launch<LOGM, R>::THREADS, Launch<LOGM, R>::MIN_BLOCKS) fft_kernel_juce (const FftArgs a)
+{
+    fft_body<LOGM, R, KIND, 0, 1> (a);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -59,6 +59,21 @@ int fft_stft_forward (void* setup, const float* signal, float* spectra, int chan
    owner-computes (no atomics, bit-reproducible).  0 < hop <= N, even spectrum strides, N <= 16384, device pointers. */
 int fft_istft_overlap_add (void* setup, const float* spectra, float* signal, int channels, int frames, long long spec_channel_stride, long long spec_frame_stride, long long channel_stride, long long hop, const float* window, float scale, int ordered, void* stream);
 
+/* The conventions of the reference's JUCE adapter (chowdsp_fft_juce/chowdsp_fft_juce.cpp:32-86), batched and fused
+   into the transform kernels' loads and stores.  Power-of-two plans up to the single-kernel limit, device pointers,
+   even strides.
+     fft_juce_perform_batched       juce::dsp::FFT::perform: complex, interleaved; inverse != 0 scales by 1/N
+     fft_juce_real_forward_batched  performRealOnlyForwardTransform: every row holds 2 N floats (N + 2 suffice when
+                                    ignore_negative_freqs != 0); N real samples in, N/2 + 1 interleaved complex bins
+                                    out (Im of DC and of Nyquist = 0), plus -- unless ignore_negative_freqs -- the
+                                    conjugate mirror in bins N/2+1 .. N-1
+     fft_juce_real_inverse_batched  performRealOnlyInverseTransform: N/2 + 1 interleaved bins in, N real samples out,
+                                    scaled by 1/N
+   In place, like the JUCE interface (row b at inout + b * stride floats). */
+int fft_juce_perform_batched (void* setup_complex, const float* input, float* output, int batch, long long in_stride, long long out_stride, int inverse, void* stream);
+int fft_juce_real_forward_batched (void* setup_real, float* inout, int batch, long long stride, int ignore_negative_freqs, void* stream);
+int fft_juce_real_inverse_batched (void* setup_real, float* inout, int batch, long long stride, void* stream);
+
 /* batch x (ab += a*b*scaling) on unordered spectra; a stride of 0 shares that operand across the
    batch (e.g. one impulse response for all channels).  Replaces a loop over reference chowdsp_fft.h:154. */
 int fft_convolve_unordered_batched (void* setup, const float* dft_a, const float* dft_b, float* dft_ab, int batch, long long a_stride, long long b_stride, long long ab_stride, float scaling, void* stream);

@@ -73,8 +73,14 @@ def aligned_copy(x, align: int = 64) -> np.ndarray:
 # --------------------------------------------------------------------------------------------------
 def simd_width(N: int, is_complex: bool, use_avx: bool = True) -> int:
     """W (floats) the reference picks: 8 = AVX handle, 4 = SSE handle, 0 = unsupported.
-    chowdsp_fft.cpp:258-280 + common.hpp:168-177 (powers of two only here)."""
-    if N <= 0 or N & (N - 1):
+    chowdsp_fft.cpp:258-280 + common.hpp:168-177; N = 2^a 3^b 5^c (common.hpp:51-75 decompose)."""
+    if N <= 0:
+        return 0
+    m = N
+    for r in (2, 3, 5):
+        while m % r == 0:
+            m //= r
+    if m != 1:
         return 0
     for W in ((8, 4) if use_avx else (4,)):
         if N % (W * W if is_complex else 2 * W * W) == 0:
@@ -376,3 +382,44 @@ def np_istft_overlap_add(spectra, N: int, hop: int, W: int, ordered: bool, windo
     for f in range(frames):
         out[:, f * hop:f * hop + N] += fr[:, f]
     return out.astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------------------
+# the JUCE adapter's conventions (chowdsp_fft_juce/chowdsp_fft_juce.cpp), restated on top of np_transform
+# --------------------------------------------------------------------------------------------------
+def np_juce_perform(x, N: int, inverse: bool) -> np.ndarray:
+    """ChowDSP_FFT::perform (chowdsp_fft_juce.cpp:32-46): ordered complex transform, inverse scaled by 1/N."""
+    y = np_transform(x, N, True, 8, inverse, True)
+    return (y.astype(np.float64) / N).astype(np.float32) if inverse else y
+
+
+def np_juce_real_forward(x, N: int, ignore_negative_freqs: bool) -> np.ndarray:
+    """performRealOnlyForwardTransform (chowdsp_fft_juce.cpp:48-66): rows of 2N floats; the first N hold the
+    samples on entry; on return bins 0..N/2 as interleaved complex (Nyquist moved from float 1 to float N, the
+    imaginary parts of DC and Nyquist zero) and, unless ignored, bin N/2+i = conj(bin N/2-i).  Floats the adapter
+    leaves untouched keep their input value."""
+    x = np.array(x, np.float32, copy=True)
+    rows = x.reshape(-1, x.shape[-1])
+    assert rows.shape[1] >= (N + 2 if ignore_negative_freqs else 2 * N)
+    packed = np_transform(rows[:, :N], N, False, 8, False, True)
+    rows[:, :N] = packed
+    rows[:, N] = packed[:, 1]
+    rows[:, N + 1] = 0.0
+    rows[:, 1] = 0.0
+    if not ignore_negative_freqs:
+        c = rows[:, 0:N + 2:2] + 1j * rows[:, 1:N + 2:2]          # bins 0..N/2
+        mirror = np.conj(c[:, N // 2 - 1:0:-1])                   # bins N/2-1 .. 1 -> N/2+1 .. N-1
+        rows[:, N + 2:2 * N:2] = mirror.real
+        rows[:, N + 3:2 * N:2] = mirror.imag
+    return rows.reshape(x.shape)
+
+
+def np_juce_real_inverse(x, N: int) -> np.ndarray:
+    """performRealOnlyInverseTransform (chowdsp_fft_juce.cpp:68-84): bins 0..N/2 interleaved in, N samples out / N."""
+    x = np.array(x, np.float32, copy=True)
+    rows = x.reshape(-1, x.shape[-1])
+    packed = rows[:, :N].copy()
+    packed[:, 1] = rows[:, N]
+    rows[:, 1] = rows[:, N]  # the adapter's own in-place fix-up is visible in the buffer only until the transform overwrites it
+    rows[:, :N] = (np_transform(packed, N, False, 8, True, True).astype(np.float64) / N).astype(np.float32)
+    return rows.reshape(x.shape)

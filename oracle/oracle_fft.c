@@ -29,13 +29,23 @@
 #endif
 
 static int is_pow2 (long n) { return n > 0 && (n & (n - 1)) == 0; }
+/* sizes the reference's decompose() accepts: only the factors 2, 3 and 5 (common.hpp:51-75) */
+static int is_235 (long n)
+{
+    if (n <= 0)
+        return 0;
+    while (n % 2 == 0) n /= 2;
+    while (n % 3 == 0) n /= 3;
+    while (n % 5 == 0) n /= 5;
+    return n == 1;
+}
 
 /* SIMD width (in floats) the reference would pick for this N: 8 (AVX, handle untagged), 4 (SSE) or
  * 0 = unsupported.  Real needs N % (2*W*W) == 0, complex N % (W*W) == 0 (common.hpp:168-177); AVX is
- * tried first when requested (chowdsp_fft.cpp:262-273).  Only powers of two are in scope here. */
+ * tried first when requested (chowdsp_fft.cpp:262-273).  N = 2^a 3^b 5^c (common.hpp:51-75). */
 int oracle_simd_width (int N, int is_complex, int use_avx)
 {
-    if (! is_pow2 (N))
+    if (! is_235 (N))
         return 0;
     const int w_first = use_avx ? 8 : 4;
     for (int W = w_first; W >= 4; W /= 2)
@@ -45,6 +55,47 @@ int oracle_simd_width (int N, int is_complex, int use_avx)
             return W;
     }
     return 0;
+}
+
+static void fft_pow2 (double* re, double* im, long n, int sign);
+
+/* DFT of n complex doubles for any n: the radix-2 FFT below for powers of two, else the O(n^2) definition with an
+ * exact-index twiddle table (the non-power-of-two sizes of the reference's tests are <= 9216). */
+static void dft_any (double* re, double* im, long n, int sign)
+{
+    if (is_pow2 (n))
+    {
+        fft_pow2 (re, im, n, sign);
+        return;
+    }
+    double* c = (double*) malloc (sizeof (double) * (size_t) n);
+    double* s = (double*) malloc (sizeof (double) * (size_t) n);
+    double* xr = (double*) malloc (sizeof (double) * (size_t) n);
+    double* xi = (double*) malloc (sizeof (double) * (size_t) n);
+    for (long t = 0; t < n; ++t)
+    {
+        const double ang = sign * 2.0 * M_PI * (double) t / (double) n;
+        c[t] = cos (ang);
+        s[t] = sin (ang);
+        xr[t] = re[t];
+        xi[t] = im[t];
+    }
+    for (long k = 0; k < n; ++k)
+    {
+        double ar = 0.0, ai = 0.0;
+        long t = 0;
+        for (long m = 0; m < n; ++m)
+        {
+            ar += xr[m] * c[t] - xi[m] * s[t];
+            ai += xr[m] * s[t] + xi[m] * c[t];
+            t += k;
+            if (t >= n)
+                t -= n;
+        }
+        re[k] = ar;
+        im[k] = ai;
+    }
+    free (c); free (s); free (xr); free (xi);
 }
 
 /* In-place iterative radix-2 DIT FFT on n complex doubles; sign = -1 forward, +1 backward; unscaled. */
@@ -122,7 +173,7 @@ void oracle_unordered_map (int N, int is_complex, int W, int* map)
  * in/out: N floats (real) or 2N floats (complex); may alias.  Returns 0, or -1 for an unsupported N/W. */
 int oracle_transform (int N, int is_complex, int W, int backward, int ordered, const float* in, float* out)
 {
-    if (! is_pow2 (N) || (W != 4 && W != 8) || N % (is_complex ? W * W : 2 * W * W) != 0)
+    if (! is_235 (N) || (W != 4 && W != 8) || N % (is_complex ? W * W : 2 * W * W) != 0)
         return -1;
     const long nfloats = is_complex ? 2L * N : N;
     double* re = (double*) malloc (sizeof (double) * (size_t) N);
@@ -142,7 +193,7 @@ int oracle_transform (int N, int is_complex, int W, int backward, int ordered, c
             re[n] = is_complex ? in[2 * n] : in[n];
             im[n] = is_complex ? in[2 * n + 1] : 0.0;
         }
-        fft_pow2 (re, im, N, -1); /* forward kernel e^{-2 pi i k n / N} */
+        dft_any (re, im, N, -1); /* forward kernel e^{-2 pi i k n / N} */
         if (is_complex)
             for (long k = 0; k < N; ++k) { freq[2 * k] = (float) re[k]; freq[2 * k + 1] = (float) im[k]; }
         else
@@ -176,7 +227,7 @@ int oracle_transform (int N, int is_complex, int W, int backward, int ordered, c
                 re[N - k] = freq[2 * k]; im[N - k] = -(double) freq[2 * k + 1]; /* Hermitian extension */
             }
         }
-        fft_pow2 (re, im, N, +1); /* unscaled: BACKWARD(FORWARD(x)) = N x (chowdsp_fft.h:128-129) */
+        dft_any (re, im, N, +1); /* unscaled: BACKWARD(FORWARD(x)) = N x (chowdsp_fft.h:128-129) */
         for (long n = 0; n < N; ++n)
         {
             if (is_complex) { out[2 * n] = (float) re[n]; out[2 * n + 1] = (float) im[n]; }

@@ -6,6 +6,7 @@
 #include "elementwise_kernels.cuh"
 #include "pconv_kernel.cuh"
 #include "pipe_kernels.cuh"
+#include "mixed_kernels.cuh"
 #include "large_plan.h"
 
 using namespace cfb;
@@ -195,6 +196,39 @@ int emu_pipe (int logM, int kind, int unord, const float* in, float* out, int ba
     return rc;
 }
 
+// the transform kernels with the JUCE adapter's conventions (fft_kernel_juce): kind 1 = C2C_BWD, 2 = R2C, 3 = C2R
+int emu_fft_juce (int logM, int radix, int kind, const float* in, float* out, int batch, long long in_stride, long long out_stride)
+{
+    auto run = [&] (auto logm_c, auto r_c) -> int
+    {
+        constexpr int LOGM = decltype (logm_c)::value, R = decltype (r_c)::value;
+        using G = Geo<LOGM, R>;
+        using L = Launch<LOGM, R>;
+        std::vector<float2> tw ((size_t) G::TW_LEN + 1), rtw ((size_t) G::M / 2 + 1);
+        fill_stage_twiddles<LOGM, R> (tw.data());
+        fill_real_twiddles (rtw.data(), G::M);
+        FftArgs a {};
+        a.in = in; a.out = out; a.in_inner = in_stride; a.out_inner = out_stride; a.inner = a.batch = batch;
+        a.tw = tw.data(); a.rtw = rtw.data();
+        const unsigned grid = (unsigned) ((batch + L::PER_CTA - 1) / L::PER_CTA);
+        emu::g_log_smem = false;
+        switch (kind)
+        {
+            case 1: emu::launch (fft_kernel_juce<LOGM, R, C2C_BWD>, dim3 (grid), dim3 (L::THREADS), (size_t) L::SMEM_BYTES, a); break;
+            case 2: emu::launch (fft_kernel_juce<LOGM, R, R2C>, dim3 (grid), dim3 (L::THREADS), (size_t) L::SMEM_BYTES, a); break;
+            case 3: emu::launch (fft_kernel_juce<LOGM, R, C2R>, dim3 (grid), dim3 (L::THREADS), (size_t) L::SMEM_BYTES, a); break;
+            default: return -1;
+        }
+        return 0;
+    };
+    using std::integral_constant;
+    if (logM == 4 && radix == 16) return run (integral_constant<int, 4> {}, integral_constant<int, 16> {});
+    if (logM == 7 && radix == 16) return run (integral_constant<int, 7> {}, integral_constant<int, 16> {});
+    if (logM == 10 && radix == 32) return run (integral_constant<int, 10> {}, integral_constant<int, 32> {});
+    if (logM == 11 && radix == 16) return run (integral_constant<int, 11> {}, integral_constant<int, 16> {});
+    return -1;
+}
+
 // frame-gather R2C (stft_kernel): `outer` channels x `inner` frames, hop = in_inner, optional window
 int emu_stft (int logM, int unord, int logW, const float* in, float* out, int outer, int inner, long long in_outer, long long in_inner, long long out_outer, long long out_inner, const float* window, int vec4, int union_gather, int log_conflicts, long* stats)
 {
@@ -317,6 +351,27 @@ int emu_istft (int logM, int radix, int unord, int logW, const float* spec, floa
     CFB_EMU_IS (10, 16, 0) CFB_EMU_IS (10, 32, 0) CFB_EMU_IS (10, 32, 3) CFB_EMU_IS (12, 16, 0)
 #undef CFB_EMU_IS
     return rc;
+}
+
+// generic mixed-radix transform (mixed_kernels.cuh): M complex points per transform, W = 0 (ordered) / 4 / 8
+int emu_mixed (int M, int kind, int W, const float* in, float* out, int batch, long long in_stride, long long out_stride, int grid)
+{
+    MixedArgs a {};
+    a.in = in; a.out = out; a.in_stride = in_stride; a.out_stride = out_stride; a.batch = batch;
+    a.M = M;
+    a.nstages = mixed_factor (M, a.radix);
+    if (a.nstages == 0 || M > kMixedMaxM)
+        return -1;
+    std::vector<float2> w ((size_t) M), r ((size_t) M / 2 + 1);
+    fill_mixed_twiddles (w.data(), M);
+    fill_mixed_real_twiddles (r.data(), M);
+    a.wtab = w.data(); a.rtab = r.data();
+    a.kind = kind; a.W = W;
+    emu::g_log_smem = false;
+    int threads = 0;
+    mixed_geometry (M, threads, a.tg);
+    emu::launch (mixed_kernel<0>, dim3 ((unsigned) grid), dim3 (threads), (size_t) 16 * M * (threads / a.tg), a);
+    return 0;
 }
 
 // fused partitioned-convolution step, real size N = 2^(logM+1)

@@ -87,7 +87,7 @@ def test_no_device_means_loud_failure_not_a_cpu_path(lib_path):
     with pytest.raises(cf.FFTError, match="no CPU fallback"):
         cf.fft_new_setup(1024, cf.FFT_REAL)
     with pytest.raises(cf.FFTError, match="unsupported FFT size"):
-        cf.fft_new_setup(96, cf.FFT_REAL)  # radix-3/5 sizes are outside the north star
+        cf.fft_new_setup(224, cf.FFT_REAL)  # 2^5 * 7: only the factors 2, 3, 5 are supported (as in the reference)
     assert cf.launch_count() == 0
 
 

@@ -21,6 +21,8 @@ def emu():
     L.emu_pipe.argtypes = [C.c_int, C.c_int, C.c_int, fp, fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_long)]
     L.emu_stft_pipe.argtypes = [C.c_int] * 4 + [fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 4 + [fp, C.c_int, C.c_int, C.POINTER(C.c_long)]
     L.emu_istft.argtypes = [C.c_int] * 4 + [fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 4 + [fp, C.c_float, C.c_int]
+    L.emu_mixed.argtypes = [C.c_int, C.c_int, C.c_int, fp, fp, C.c_int, C.c_longlong, C.c_longlong, C.c_int]
+    L.emu_fft_juce.argtypes = [C.c_int, C.c_int, C.c_int, fp, fp, C.c_int, C.c_longlong, C.c_longlong]
     L.emu_stft.argtypes = [C.c_int] * 3 + [fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 4 + [fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_long)]
     return L
 
@@ -323,3 +325,51 @@ def test_emulated_istft_overlap_add(emu, oracle_mod, N, radix, hop, frames, orde
     want = o.np_istft_overlap_add(spec, N, hop, W, ordered, win if windowed else None, 1.0 / N)
     assert np.all(np.isnan(out[:, samples:]))  # nothing written past the end of a channel
     assert o.rel_l2(out[:, :samples], want) < min(o.parity_tol(N), 4e-7)
+
+
+@pytest.mark.parametrize("N", [96, 192, 384, 480, 640, 768, 9216, 1536, 2000 * 0 + 1920])
+@pytest.mark.parametrize("is_c", [True, False])
+def test_emulated_mixed_radix(emu, oracle_mod, N, is_c):
+    """Generic mixed-radix kernel (radix 4 / 2 / 3 / 5 Stockham passes) on the reference's non-power-of-two test
+    sizes (test/test.cpp:279-285) and two more: every kind, ordered and both unordered layouts, 3 transforms on 2
+    CTAs (so one CTA loops)."""
+    o = oracle_mod
+    nfl = 2 * N if is_c else N
+    M = N if is_c else N // 2
+    rng = np.random.default_rng(N + 11)
+    x = rng.uniform(-1, 1, (3, nfl)).astype(np.float32)
+    widths = sorted({o.simd_width(N, is_c, True), o.simd_width(N, is_c, False)} - {0})
+    assert widths
+    for W in widths:
+        for ordered in (True, False):
+            ref = o.np_transform(x, N, is_c, W, False, ordered)
+            f = np.zeros_like(x)
+            assert emu.emu_mixed(M, 0 if is_c else 2, 0 if ordered else W, x.ctypes.data_as(fp), f.ctypes.data_as(fp), 3, nfl, nfl, 2) == 0
+            assert o.rel_l2(f, ref) < 4e-7, (W, ordered)
+            b = np.zeros_like(x)
+            refc = np.ascontiguousarray(ref, np.float32)
+            assert emu.emu_mixed(M, 1 if is_c else 3, 0 if ordered else W, refc.ctypes.data_as(fp), b.ctypes.data_as(fp), 3, nfl, nfl, 2) == 0
+            assert o.rel_l2(b, o.np_transform(ref, N, is_c, W, True, ordered)) < 4e-7, (W, ordered)
+
+
+@pytest.mark.parametrize("logM,radix", [(4, 16), (7, 16), (10, 32), (11, 16)])
+def test_emulated_juce_conventions(emu, oracle_mod, logM, radix):
+    """fft_kernel_juce: real forward in place with Nyquist as bin N/2, real inverse and complex inverse scaled by 1/N
+    (chowdsp_fft_juce.cpp:32-86 restated in oracle.np_juce_*)."""
+    o = oracle_mod
+    rng = np.random.default_rng(logM)
+    N, batch = 2 << logM, 3
+    stride = 2 * N + 4
+    buf = rng.uniform(-1, 1, (batch, stride)).astype(np.float32)
+    work = buf.copy()
+    assert emu.emu_fft_juce(logM, radix, 2, work.ctypes.data_as(fp), work.ctypes.data_as(fp), batch, stride, stride) == 0
+    want = o.np_juce_real_forward(buf, N, True)
+    assert o.rel_l2(work[:, :N + 2], want[:, :N + 2]) < 4e-7
+    assert np.all(work[:, 1] == 0) and np.all(work[:, N + 1] == 0) and np.array_equal(work[:, N + 2:], buf[:, N + 2:])
+    assert emu.emu_fft_juce(logM, radix, 3, work.ctypes.data_as(fp), work.ctypes.data_as(fp), batch, stride, stride) == 0
+    assert o.rel_l2(work[:, :N], buf[:, :N]) < 4e-7
+    Nc = 1 << logM
+    x = rng.uniform(-1, 1, (batch, 2 * Nc)).astype(np.float32)
+    y = np.zeros_like(x)
+    assert emu.emu_fft_juce(logM, radix, 1, x.ctypes.data_as(fp), y.ctypes.data_as(fp), batch, 2 * Nc, 2 * Nc) == 0
+    assert o.rel_l2(y, o.np_juce_perform(x, Nc, True)) < 4e-7

@@ -462,6 +462,100 @@ def test_reference_test_suite_restated(cf, oracle_mod):
                         cf.fft_destroy_setup(s)
 
 
+@pytest.mark.parametrize("N", [96, 192, 384, 480, 640, 768, 9216, 1920, 24576])
+def test_mixed_radix_sizes(cf, oracle_mod, ref_lib, N):
+    """N = 2^a 3^b 5^c that are not powers of two (the reference's "Other sizes" tests, test/test.cpp:279-285, plus
+    the largest real size of the generic kernel): every kind and layout through the batched entry point vs the
+    oracle and the live reference, in place and out of place; then test_fft_complex / test_fft_real restated
+    (in-place ordered forward, backward, scale; reference margin) through the reference-shaped host-pointer API."""
+    o = oracle_mod
+    rng = np.random.default_rng(N)
+    for is_c in (True, False):
+        if is_c and N > 12288:
+            with pytest.raises(cf.FFTError):
+                cf.fft_new_setup(N, cf.FFT_COMPLEX, True)
+            continue
+        nfl = 2 * N if is_c else N
+        for avx in (True, False):
+            W = o.simd_width(N, is_c, avx)
+            assert W in (4, 8)
+            x = rng.uniform(-1, 1, (5, nfl)).astype(np.float32)
+            tol = o.parity_tol(N)
+            for ordered in (True, False):
+                want_f = o.np_transform(x, N, is_c, W, False, ordered)
+                got_f = gpu_transform(cf, x, N, is_c, avx, False, ordered)
+                assert o.rel_l2(got_f, want_f) < tol, (is_c, W, ordered, "forward")
+                assert np.array_equal(gpu_transform(cf, x, N, is_c, avx, False, ordered, inplace=True), got_f)
+                got_b = gpu_transform(cf, want_f, N, is_c, avx, True, ordered)
+                assert o.rel_l2(got_b, o.np_transform(want_f, N, is_c, W, True, ordered)) < tol, (is_c, W, ordered, "backward")
+                if ref_lib is not None:
+                    ref_f, _ = ref_lib.transform(x, N, is_c, False, ordered, avx)
+                    assert o.rel_l2(got_f, ref_f) < tol, (is_c, W, ordered, "vs live reference")
+            # test/test.cpp:34-62, 92-118 restated
+            s = cf.fft_new_setup(N, cf.FFT_COMPLEX if is_c else cf.FFT_REAL, avx)
+            assert cf.fft_simd_width_bytes(s) == 4 * W
+            sig = o.ref_signal(N, is_c, 100.0)
+            data, work = cf.aligned_array(nfl), cf.aligned_array(nfl)
+            data[:] = sig
+            cf.fft_transform(s, data, data, work, cf.FFT_FORWARD)
+            margin = 2.0e-7 * nfl
+            assert np.max(np.abs(data - o.np_transform(sig, N, is_c, W, False, True))) <= margin
+            cf.fft_transform(s, data, data, work, cf.FFT_BACKWARD)
+            assert np.max(np.abs(data / N - sig)) <= margin
+            cf.aligned_free(data.ctypes.data)
+            cf.aligned_free(work.ctypes.data)
+            cf.fft_destroy_setup(s)
+
+
+@pytest.mark.parametrize("N", [32, 64, 256, 1024, 2048, 4096, 16384, 32768])
+def test_juce_conventions(cf, oracle_mod, N):
+    """The JUCE adapter's conventions (chowdsp_fft_juce.cpp:32-86) fused into the transform kernels: perform (inverse
+    scaled by 1/N), performRealOnlyForwardTransform (Nyquist as bin N/2, optional conjugate mirror),
+    performRealOnlyInverseTransform; batched, in place, rows of 2N floats with a gap between rows."""
+    o = oracle_mod
+    rng = np.random.default_rng(N + 17)
+    batch, tol = 5, o.parity_tol(N)
+    sr = cf.fft_new_setup(N, cf.FFT_REAL)
+    try:
+        stride = 2 * N + 4
+        for ignore in (True, False):
+            buf = rng.uniform(-1, 1, (batch, stride)).astype(np.float32)
+            d = dev(buf)
+            cf.fft_juce_real_forward_batched(sr, d, batch, stride, ignore)
+            torch.cuda.synchronize()
+            got, want = host(d), o.np_juce_real_forward(buf, N, ignore)
+            assert o.rel_l2(got[:, :N + 2], want[:, :N + 2]) < tol
+            assert np.all(got[:, 1] == 0) and np.all(got[:, N + 1] == 0)
+            if ignore:
+                assert np.array_equal(got[:, N + 2:], buf[:, N + 2:])  # nothing else touched
+            else:
+                assert o.rel_l2(got[:, :2 * N], want[:, :2 * N]) < tol
+                assert np.array_equal(got[:, 2 * N:], buf[:, 2 * N:])
+            # and back: inverse of the forward result returns the samples
+            cf.fft_juce_real_inverse_batched(sr, d, batch, stride)
+            torch.cuda.synchronize()
+            back = host(d)
+            assert o.rel_l2(back[:, :N], buf[:, :N]) < tol
+            assert o.rel_l2(back[:, :N], o.np_juce_real_inverse(want, N)[:, :N]) < tol
+    finally:
+        cf.fft_destroy_setup(sr)
+    if N <= 16384:
+        sc = cf.fft_new_setup(N, cf.FFT_COMPLEX)
+        try:
+            x = rng.uniform(-1, 1, (batch, 2 * N)).astype(np.float32)
+            dx, dy = dev(x), torch.empty(batch, 2 * N, device="cuda")
+            cf.fft_juce_perform_batched(sc, dx, dy, batch, 2 * N, 2 * N, False)
+            torch.cuda.synchronize()
+            f = host(dy)
+            assert o.rel_l2(f, o.np_juce_perform(x, N, False)) < tol
+            cf.fft_juce_perform_batched(sc, dy, dy, batch, 2 * N, 2 * N, True)  # in place
+            torch.cuda.synchronize()
+            assert o.rel_l2(host(dy), o.np_juce_perform(f, N, True)) < tol
+            assert o.rel_l2(host(dy), x) < tol
+        finally:
+            cf.fft_destroy_setup(sc)
+
+
 def test_host_pointer_paths(cf, oracle_mod):
     """pageable numpy memory, pinned aligned_malloc memory (zero-copy when small, staged when large)."""
     o = oracle_mod
@@ -499,7 +593,7 @@ def test_host_pointer_paths(cf, oracle_mod):
 
 def test_setup_errors(cf):
     os.environ["CHOWDSP_FFT_B200_QUIET"] = "1"
-    for N, tr in ((8, cf.FFT_COMPLEX), (16, cf.FFT_REAL), (96, cf.FFT_COMPLEX), (100, cf.FFT_REAL), (0, cf.FFT_REAL),
+    for N, tr in ((8, cf.FFT_COMPLEX), (16, cf.FFT_REAL), (112, cf.FFT_COMPLEX), (100, cf.FFT_REAL), (0, cf.FFT_REAL), (3 << 13, cf.FFT_COMPLEX),
                   (-4, cf.FFT_COMPLEX), (1 << 29, cf.FFT_COMPLEX), (1 << 29, cf.FFT_REAL)):
         with pytest.raises(cf.FFTError):
             cf.fft_new_setup(N, tr)

@@ -82,7 +82,9 @@ def test_size_rules(oracle_mod):
     assert o.simd_width(32, False, True) == 4 and o.simd_width(128, False, True) == 8
     assert o.simd_width(16, True, True) == 4 and o.simd_width(64, True, True) == 8
     assert o.simd_width(16, False, True) == 0 and o.simd_width(8, True, False) == 0
-    assert o.simd_width(96, True, True) == 0  # non powers of two are out of scope (north star)
+    # N = 2^a 3^b 5^c (common.hpp:51-75): 96 = 2^5 3 is a multiple of 16 and of 32 but not of 64 / 128
+    assert o.simd_width(96, True, True) == 4 and o.simd_width(96, False, True) == 4 and o.simd_width(384, False, True) == 8
+    assert o.simd_width(112, True, False) == 0 and o.simd_width(7 * 64, True, True) == 0
 
 
 def test_accumulate(oracle_mod):
@@ -101,8 +103,8 @@ def test_against_live_reference(oracle_mod, ref_lib, is_c, avx):
     if ref_lib is None:
         pytest.skip("oracle/_ref/libchowdsp_fft_ref.so not built")
     rng = np.random.default_rng(42)
-    for lg in range(4, 17):
-        N = 1 << lg
+    # powers of two, then the reference's non-power-of-two test sizes (test/test.cpp:279-285) and a few more
+    for N in [1 << lg for lg in range(4, 17)] + [96, 192, 384, 480, 640, 768, 9216, 1536, 1920, 112, 80]:
         W = o.simd_width(N, is_c, avx)
         s = ref_lib.new_setup(N, is_c, avx)
         if W == 0:
