@@ -387,6 +387,13 @@ bool pipe_enabled (int logM, int kind, int logW)
 {
     return has_pipe (logM) && (logW == 0 || logW == 3) && ((g_pipe_mask >> ((logW == 0 ? 0 : 8) + 2 * kind + logM - 13)) & 1u) != 0;
 }
+// tuning hook "wpipe": which batches of the sizes one warp owns (has_wpipe; forward kinds, 16-byte aligned input rows) go
+// through the warp-pipelined kernel (wpipe_kernel): bit 1 = overlapping or windowed frames (STFT analysis), bit 0 = every
+// batch; bits 8.. = warps per CTA (0 = as many as fit an SM).  Default from profiles/r01_wpipe.txt: frames only -- their
+// re-reads are L2 hits, so fft_kernel is bound by the exposed load latency there (STFT config 4.81 -> 5.30 TB/s), while
+// plain batches already run at the HBM roofline with fft_kernel and lose 5..13 % to the landing-buffer round trip
+constexpr int kWPipeDefault = 2;
+int g_wpipe = kWPipeDefault;
 int g_pf_ahead = 0;        // tuning hook "pf_ahead": L2 prefetch distance of the single-kernel transforms, in CTAs
 
 constexpr size_t kZeroCopyBytes = 256 * 1024;     // pinned buffers up to this size are used in place
@@ -580,7 +587,16 @@ int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inne
     const bool use_pipe = window == nullptr && pipe_enabled (p->logM, kind_of (p, direction), ordered ? 0 : p->logW)
                           && (outer == 1 || inner == 1) && (reinterpret_cast<uintptr_t> (in) & 15) == 0
                           && ((outer == 1 ? in_inner : in_outer) & 3) == 0;
-    const int radix = use_pipe ? 32 : radix_for (p->logM, p->is_complex != 0);
+    // sizes owned by one warp (2^10 points at 32 per thread, 2^9 at 16), forward kinds, input rows the TMA unit can
+    // fetch (16-byte aligned): every warp runs its own prefetch pipeline (wpipe_kernel); covers plain batches and
+    // overlapping / windowed frames
+    const int wpipe_radix = p->logM == 10 ? 32 : 16;
+    const long long row_floats = p->is_complex ? 2LL * p->N : p->N;
+    const long long frame_stride = inner > 1 ? in_inner : in_outer;
+    const bool frames = window != nullptr || ((long long) outer * inner > 1 && frame_stride > 0 && frame_stride < row_floats);
+    const bool use_wpipe = ! use_pipe && ((g_wpipe & 1) != 0 || ((g_wpipe & 2) != 0 && frames)) && has_wpipe (p->logM, wpipe_radix) && direction == chowdsp::fft::FFT_FORWARD
+                           && (reinterpret_cast<uintptr_t> (in) & 15) == 0 && (inner == 1 || (in_inner & 3) == 0) && (outer == 1 || (in_outer & 3) == 0);
+    const int radix = use_pipe ? 32 : use_wpipe ? wpipe_radix : radix_for (p->logM, p->is_complex != 0);
     const int rc = plan_tables (p, t, radix);
     if (rc != 0)
         return rc;
@@ -612,6 +628,16 @@ int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inne
     a.tw = t.tw;
     a.rtw = t.rtw;
     a.pf_ahead = g_pf_ahead;
+    if (use_wpipe)
+    {
+        a.window = window;
+        const int kind = kind_of (p, direction);
+        const cudaError_t ew = launch_wpipe (p->logM, kind, ordered ? 0 : p->logW, g_wpipe >> 8, a, stream);
+        if (ew != cudaSuccess)
+            return fail_cuda (ew, "warp-pipelined fft kernel launch");
+        note_kernel ("cfb::wpipe_kernel<%d,%d,%s,%d>", p->logM, radix, kKindNames[kind], ordered ? 0 : p->logW);
+        return 0;
+    }
     // windowed real frames (STFT analysis) go through the frame-gather kernel; plain overlapping frames only when
     // the union-staging variant is selected (it is slower on B200, see stft_kernel)
     const bool fwd_real = ! p->is_complex && direction == chowdsp::fft::FFT_FORWARD;
@@ -1373,6 +1399,11 @@ CFB_API int fft_b200_set_tuning (const char* key, int value)
     if (key != nullptr && std::strcmp (key, "pf_ahead") == 0 && value >= 0)
     {
         g_pf_ahead = value;
+        return 0;
+    }
+    if (key != nullptr && std::strcmp (key, "wpipe") == 0)
+    {
+        g_wpipe = value == -1 ? kWPipeDefault : value;
         return 0;
     }
     if (key != nullptr && std::strcmp (key, "stft_pipe") == 0)

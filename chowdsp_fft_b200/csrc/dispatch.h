@@ -39,6 +39,13 @@ bool has_pipe (int logM);
 cudaError_t launch_pipe (int logM, int kind, int logW, const FftArgs& args, cudaStream_t stream);
 cudaError_t launch_pipe_13 (int kind, int logW, const FftArgs& args, cudaStream_t stream);
 cudaError_t launch_pipe_14 (int kind, int logW, const FftArgs& args, cudaStream_t stream);
+// warp-pipelined variant (wpipe_kernel) for the sizes one warp owns (2^10 points with radix 32, 2^9 with radix 16), kinds R2C /
+// C2C_FWD, every layout, plain or two-level batches whose input rows are all 16-byte aligned; warps per CTA <= 0 = as
+// many as fit one SM
+bool has_wpipe (int logM, int radix);
+cudaError_t launch_wpipe (int logM, int kind, int logW, int warps, const FftArgs& args, cudaStream_t stream);
+cudaError_t launch_wpipe_9 (int kind, int logW, int warps, const FftArgs& args, cudaStream_t stream);
+cudaError_t launch_wpipe_10 (int kind, int logW, int warps, const FftArgs& args, cudaStream_t stream);
 // number of float2 entries of the stage twiddle table for 2^logM, and the fill routine (fp64 -> fp32)
 int stage_twiddle_len (int logM, int radix);
 void fill_stage_twiddles_rt (int logM, int radix, float2* tw);

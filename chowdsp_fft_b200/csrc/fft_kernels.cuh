@@ -798,14 +798,16 @@ FFT_HD void staging_drain (const float* sf, float* __restrict__ out, int j, int 
 //   OUT_STAGED (unordered outputs only): leave the staging image in `s` (synchronised), do not drain it
 //   HALF_OUT   (C2R only): store only the second half of the output samples (overlap-save discard)
 //   IN_UNION   (R2C / C2C_FWD): the stage-0 input is read from the shared-memory image `su` (natural order,
-//              unpadded, float2 units; it may alias `s`) and multiplied by the window `win` when non-null
+//              unpadded, float2 units; it may alias `s`) and multiplied by the window `win` when non-null.
+//              1 = the image is shared by the transforms of the CTA (the first barrier is CTA-wide), 2 = it is
+//              private to this transform (wpipe_kernel's per-warp landing buffer: transform-level barriers only)
 //   input_consumed (IN_UNION with more than one stage): hook run after the barrier that follows the stage-0 reads
 //   OUT_REGS   (C2R / C2C_BWD): do not store; hand the result registers (element j + m T in vout[m]) to the caller
 //   FMT = 1    (ordered layouts): the conventions of the reference's JUCE adapter (chowdsp_fft_juce/chowdsp_fft_juce.cpp:
 //              32-86) instead of pffft's -- real spectra as N/2 + 1 interleaved complex bins (Nyquist at float 2M, the
 //              imaginary parts of DC and Nyquist zero) rather than Nyquist packed into float 1, and inverse transforms
 //              (C2R, C2C_BWD) scaled by 1/N
-template <int LOGM, int R, int KIND, int LOGW, bool IN_STAGED, bool OUT_STAGED, bool HALF_OUT, bool IN_UNION = false, class Hook = NoHook, bool OUT_REGS = false, int FMT = 0>
+template <int LOGM, int R, int KIND, int LOGW, bool IN_STAGED, bool OUT_STAGED, bool HALF_OUT, int IN_UNION = 0, class Hook = NoHook, bool OUT_REGS = false, int FMT = 0>
 FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, bool active, int j, float2* s, const float2* __restrict__ tw_, const float2* __restrict__ rtw_,
                       const float2* su = nullptr, const float2* __restrict__ win = nullptr, const Hook& input_consumed = Hook(), float2* vout = nullptr)
 {
@@ -828,7 +830,7 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
     if constexpr (KIND == C2C_FWD || KIND == R2C || (KIND == C2C_BWD && ! UNORD))
     {
         // interleaved complex (natural order), or real samples read as (x[2n], x[2n+1]) pairs
-        if constexpr (IN_UNION)
+        if constexpr (IN_UNION != 0)
         {
             const float2* sj = su + j;
 #pragma unroll
@@ -932,7 +934,7 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
     }
 
     // ---- the stages -----------------------------------------------------------------------------
-    Stages<G, DIR, 0, WS, IN_UNION>::run (v, j, s, a.tw, smem_was_read, input_consumed);
+    Stages<G, DIR, 0, WS, IN_UNION == 1>::run (v, j, s, a.tw, smem_was_read, input_consumed);
     if (G::S > 1)
         smem_was_read = true;
 
@@ -971,7 +973,7 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
         // Z[k], k = j + m T < M/2, is this thread's register m; Z[M-k] is register R-1-m of thread T-j:
         // only the upper half of the spectrum goes through shared memory.
         if (smem_was_read)
-            tsync<T, WS && ! (IN_UNION && G::S == 1)>();
+            tsync<T, WS && ! (IN_UNION == 1 && G::S == 1)>();
         scatter_natural<G, R / 2, R> (v, j, s);
         tsync<T, WS>();
         float2 zb[R / 2];

@@ -218,6 +218,129 @@ __global__ void __launch_bounds__ (Launch<LOGM, R>::THREADS, Launch<LOGM, R>::MI
     stft_pipe_body<LOGM, R, LOGW> (a);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-pipelined transform (wpipe_kernel) for the sizes one warp owns (T = M / R = 32: 2^10 points at 32 per thread,
+// 2^9 at 16): every warp of a resident CTA is its own software pipeline over transforms of the CTA's share of the batch
+//   * the warp's NEXT input (8 M bytes, contiguous) is fetched by the TMA unit into a landing buffer private to the warp
+//     (cp.async.bulk + the warp's own mbarrier) as soon as the stage-0 registers of the current transform have been
+//     read out of it, i.e. the copy has a whole transform's butterflies, exchanges and stores to complete;
+//   * nothing is CTA-wide: the only barriers are __syncwarp and the warp's mbarrier wait, so the warps of an SM drift
+//     apart and their LSU / FMA / store phases interleave.
+// Against fft_kernel this removes the exposed load latency that bounds the STFT config (ncu: 36 % of the stall samples on
+// the first use of the loaded registers at 16 resident warps per SM, DRAM 60 %): every resident warp keeps 8 M bytes in
+// flight all the time instead of during a third of its life.
+// Plain and two-level (frame gather, optional window) batches, kinds R2C / C2C_FWD, every layout.  Every transform's
+// input must be 16-byte aligned (the launcher checks base, in_inner and in_outer).
+// Shared memory: per warp [landing 8 M bytes][exchange buffer][mbarrier, next-transform slot: 16 bytes]; then the CTA's
+// work counter (16 bytes).
+// ---------------------------------------------------------------------------------------------
+template <int LOGM, int R, int LOGW>
+struct WPipeGeo
+{
+    using G = Geo<LOGM, R>;
+    static_assert (G::T == 32, "wpipe_kernel: one warp per transform");
+    static constexpr int IN_BYTES = 2 * G::M * 4;
+    static constexpr int SMEM_F2 = LOGW != 0 ? G::SMEM_F2_UNORD : G::SMEM_F2;
+    static constexpr int WARP_BYTES = IN_BYTES + SMEM_F2 * 8 + 16;
+    static constexpr int CTA_EXTRA_BYTES = 16; // the work counter
+    static constexpr int MAX_WARPS = (227 * 1024 - CTA_EXTRA_BYTES) / WARP_BYTES < 16 ? (227 * 1024 - CTA_EXTRA_BYTES) / WARP_BYTES : 16;
+    static constexpr int smem_bytes (int warps) { return warps * WARP_BYTES + CTA_EXTRA_BYTES; }
+    static_assert (WARP_BYTES % 16 == 0, "landing buffers must stay 16-byte aligned");
+};
+
+// shared-memory work counter of a CTA (one lane per warp asks for the warp's next transform)
+FFT_HD unsigned smem_take (unsigned* counter)
+{
+#ifdef CHOWDSP_EMU
+    return __atomic_fetch_add (counter, 1u, __ATOMIC_RELAXED);
+#else
+    return atomicAdd (counter, 1u);
+#endif
+}
+
+template <int LOGM, int R, int KIND, int LOGW>
+FFT_HD void wpipe_body (const FftArgs& a)
+{
+    using WP = WPipeGeo<LOGM, R, LOGW>;
+    static_assert (KIND == R2C || KIND == C2C_FWD, "wpipe_kernel: kinds whose input is a contiguous natural-order row");
+    FFT_DYN_SMEM (char, smem);
+    const int tid = (int) threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int wpc = (int) blockDim.x >> 5;
+    char* wbase = smem + (size_t) warp * WP::WARP_BYTES;
+    float2* land = reinterpret_cast<float2*> (wbase);
+    float2* xch = reinterpret_cast<float2*> (wbase + WP::IN_BYTES);
+    unsigned long long* bar = reinterpret_cast<unsigned long long*> (wbase + WP::IN_BYTES + WP::SMEM_F2 * 8);
+    volatile unsigned* wnext = reinterpret_cast<volatile unsigned*> (bar + 1); // the warp's next transform, written by lane 0
+    unsigned* counter = reinterpret_cast<unsigned*> (smem + (size_t) wpc * WP::WARP_BYTES);
+
+    // The CTA owns the contiguous range [first, first + count) of the batch (neighbouring frames of an STFT are then
+    // fetched close together in time: their overlap is an L2 hit); inside the CTA the warps take transforms one at a
+    // time from a shared counter, so a warp that shares its scheduler with more warps than the others just takes fewer.
+    const long long first = (long long) a.batch * (long long) blockIdx.x / (long long) gridDim.x;
+    const unsigned count = (unsigned) ((long long) a.batch * ((long long) blockIdx.x + 1) / (long long) gridDim.x - first);
+    const bool two_level = a.inner < a.batch;
+    auto locate = [&] (unsigned i, long long& xo, long long& xi)
+    {
+        const long long t = first + i;
+        xo = 0;
+        xi = t;
+        if (two_level)
+        {
+            xo = (long long) ((unsigned) t / (unsigned) a.inner);
+            xi = t - xo * a.inner;
+        }
+    };
+    auto fetch = [&] (unsigned i)
+    {
+        long long xo, xi;
+        locate (i, xo, xi);
+        mbar_expect (bar, (unsigned) WP::IN_BYTES);
+        bulk_copy (land, a.in + xo * a.in_outer + xi * a.in_inner, (unsigned) WP::IN_BYTES, bar);
+    };
+    if (tid == 0)
+        *counter = 0u;
+    __syncthreads();
+    if (lane == 0)
+    {
+        mbar_init (bar);
+        const unsigned i = smem_take (counter);
+        *wnext = i;
+        if (i < count)
+            fetch (i);
+    }
+    tsync<32, true>();
+    unsigned cur = *wnext;
+    for (unsigned it = 0; cur < count; ++it)
+    {
+        long long xo, xi;
+        locate (cur, xo, xi);
+        float* out = a.out + xo * a.out_outer + xi * a.out_inner;
+        mbar_wait (bar, it, (unsigned) WP::IN_BYTES);
+        // runs after the warp-level barrier that follows the stage-0 reads: the landing buffer is free again, and every
+        // lane has read *wnext for this trip
+        const auto input_consumed = [&]
+        {
+            if (lane == 0)
+            {
+                const unsigned i = smem_take (counter);
+                *wnext = i;
+                if (i < count)
+                    fetch (i);
+            }
+        };
+        fft_core<LOGM, R, KIND, LOGW, false, false, false, 2> (nullptr, out, true, lane, xch, a.tw, a.rtw, land,
+                                                               reinterpret_cast<const float2*> (a.window), input_consumed);
+        cur = *wnext; // at least one warp-level barrier (the stage-0 exchange) lies between lane 0's write and this read
+    }
+}
+
+template <int LOGM, int R, int KIND, int LOGW>
+__global__ void __launch_bounds__ (WPipeGeo<LOGM, R, LOGW>::MAX_WARPS * 32, 1) wpipe_kernel (const FftArgs a)
+{
+    wpipe_body<LOGM, R, KIND, LOGW> (a);
+}
+
 // start the copy of one transform into the landing buffer (called by every thread of the CTA)
 template <class P>
 FFT_HD void pipe_fetch (char* land, const float* src, int j, unsigned long long* bar)

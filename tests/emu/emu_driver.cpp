@@ -315,6 +315,47 @@ int emu_stft_pipe (int logM, int radix, int unord, int logW, const float* in, fl
     return rc;
 }
 
+// warp-pipelined transform (wpipe_kernel): `grid` resident CTAs of `warps` warps, kind 0 = C2C_FWD, 2 = R2C
+int emu_wpipe (int logM, int radix, int kind, int unord, int logW, const float* in, float* out, int outer, int inner, long long in_outer, long long in_inner, long long out_outer, long long out_inner, const float* window, int grid, int warps, int log_conflicts, long* stats)
+{
+    auto run = [&] (auto logm_c, auto r_c, auto kind_c, auto logw_c) -> int
+    {
+        constexpr int LOGM = decltype (logm_c)::value, R = decltype (r_c)::value, KIND = decltype (kind_c)::value, LOGW = decltype (logw_c)::value;
+        using WP = WPipeGeo<LOGM, R, LOGW>;
+        using G = Geo<LOGM, R>;
+        std::vector<float2> tw ((size_t) G::TW_LEN + 1), rtw ((size_t) G::M / 2 + 1);
+        fill_stage_twiddles<LOGM, R> (tw.data());
+        fill_real_twiddles (rtw.data(), G::M);
+        FftArgs a {};
+        a.in = in; a.out = out;
+        a.in_inner = in_inner; a.in_outer = in_outer; a.out_inner = out_inner; a.out_outer = out_outer;
+        a.inner = inner; a.batch = outer * inner;
+        a.tw = tw.data(); a.rtw = rtw.data();
+        a.window = window;
+        if (warps <= 0 || warps > WP::MAX_WARPS)
+            return -2;
+        emu::launch (wpipe_kernel<LOGM, R, KIND, LOGW>, dim3 ((unsigned) grid), dim3 ((unsigned) warps * 32), (size_t) WP::smem_bytes (warps), a);
+        return 0;
+    };
+    using std::integral_constant;
+    emu::g_log_smem = log_conflicts != 0;
+    emu::g_stats = {};
+    int rc = -1;
+    const int lw = unord ? logW : 0;
+#define CFB_EMU_WP(M, RR, K, W) if (logM == M && radix == RR && kind == K && lw == W) rc = run (integral_constant<int, M> {}, integral_constant<int, RR> {}, integral_constant<int, K> {}, integral_constant<int, W> {});
+    CFB_EMU_WP (10, 32, R2C, 0) CFB_EMU_WP (10, 32, R2C, 3) CFB_EMU_WP (10, 32, R2C, 2) CFB_EMU_WP (10, 32, C2C_FWD, 0) CFB_EMU_WP (10, 32, C2C_FWD, 3)
+    CFB_EMU_WP (9, 16, R2C, 0) CFB_EMU_WP (9, 16, R2C, 3) CFB_EMU_WP (9, 16, C2C_FWD, 0) CFB_EMU_WP (9, 16, C2C_FWD, 2)
+#undef CFB_EMU_WP
+    if (stats)
+    {
+        stats[0] = emu::g_stats.ops;
+        stats[1] = emu::g_stats.wavefronts;
+        stats[2] = emu::g_stats.ideal;
+        stats[3] = emu::g_stats.worst;
+    }
+    return rc;
+}
+
 // overlap-add synthesis (istft_kernel): `channels` x `frames` spectra -> signals, segments of seg_groups CTA groups
 int emu_istft (int logM, int radix, int unord, int logW, const float* spec, float* sig, int channels, int frames, long long spec_channel_stride, long long spec_frame_stride, long long channel_stride, long long hop, const float* window, float scale, int seg_groups)
 {

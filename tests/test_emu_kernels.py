@@ -20,6 +20,7 @@ def emu():
     L.emu_accumulate.argtypes = [fp, fp, fp, C.c_longlong]
     L.emu_pipe.argtypes = [C.c_int, C.c_int, C.c_int, fp, fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_long)]
     L.emu_stft_pipe.argtypes = [C.c_int] * 4 + [fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 4 + [fp, C.c_int, C.c_int, C.POINTER(C.c_long)]
+    L.emu_wpipe.argtypes = [C.c_int] * 5 + [fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 4 + [fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_long)]
     L.emu_istft.argtypes = [C.c_int] * 4 + [fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 4 + [fp, C.c_float, C.c_int]
     L.emu_mixed.argtypes = [C.c_int, C.c_int, C.c_int, fp, fp, C.c_int, C.c_longlong, C.c_longlong, C.c_int]
     L.emu_fft_juce.argtypes = [C.c_int, C.c_int, C.c_int, fp, fp, C.c_int, C.c_longlong, C.c_longlong]
@@ -300,6 +301,39 @@ def test_emulated_persistent_stft(emu, oracle_mod, N, radix, hop, frames, ordere
         fr = fr * win
     want = o.np_transform(fr.reshape(-1, N).astype(np.float32), N, False, W, False, ordered).reshape(out.shape)
     assert o.rel_l2(out, want) < min(o.parity_tol(N), 4e-7)
+
+
+@pytest.mark.parametrize("N,is_c,hop,frames,ordered,W,grid,warps", [(2048, False, 512, 19, True, 8, 2, 3), (2048, False, 512, 9, False, 8, 1, 4), (2048, False, 2048, 7, False, 4, 3, 1),
+                                                                    (1024, False, 100, 23, True, 8, 2, 5), (1024, False, 256, 11, False, 8, 2, 2),
+                                                                    (1024, True, 2048, 11, True, 8, 2, 3), (1024, True, 2048, 5, False, 8, 1, 2), (512, True, 1024, 9, True, 8, 2, 2), (512, True, 1024, 9, False, 4, 1, 13)])
+@pytest.mark.parametrize("windowed", [False, True])
+def test_emulated_warp_pipelined(emu, oracle_mod, N, is_c, hop, frames, ordered, W, grid, warps, windowed):
+    """Warp-pipelined kernel (wpipe_kernel): every warp of `grid` resident CTAs loops over transforms w, w + warps in the
+    grid, ..., its next input arriving by a warp-private bulk copy; plain batches (complex) and overlapping, optionally
+    windowed frames (real), more and fewer transforms than warps; == a loop of single out-of-place transforms.  The
+    shared-memory accesses of the landing-buffer reads must be conflict free."""
+    o = oracle_mod
+    if windowed and is_c:
+        pytest.skip("windows are for real frames")
+    channels = 3
+    nfl = 2 * N if is_c else N
+    samples = ((frames - 1) * hop + nfl + 7) // 4 * 4
+    rng = np.random.default_rng(N + hop + 5)
+    sig = rng.uniform(-1, 1, (channels, samples)).astype(np.float32)
+    win = (0.5 - 0.5 * np.cos(2 * np.pi * (np.arange(N) + 0.5) / N)).astype(np.float32)
+    out = np.zeros((channels, frames, nfl), np.float32)
+    st = (C.c_long * 4)()
+    logM = int(np.log2(N)) - (0 if is_c else 1)
+    rc = emu.emu_wpipe(logM, 32 if logM == 10 else 16, 0 if is_c else 2, 0 if ordered else 1, {8: 3, 4: 2}[W], sig.ctypes.data_as(fp), out.ctypes.data_as(fp),
+                       channels, frames, samples, hop, frames * nfl, nfl, win.ctypes.data_as(fp) if windowed else None, grid, warps, 1, st)
+    assert rc == 0
+    fr = np.stack([[sig[c, f * hop:f * hop + nfl] for f in range(frames)] for c in range(channels)])
+    if windowed:
+        fr = fr * win
+    want = o.np_transform(fr.reshape(-1, nfl).astype(np.float32), N, is_c, W, False, ordered).reshape(out.shape)
+    assert o.rel_l2(out, want) < min(o.parity_tol(N), 4e-7)
+    if ordered:
+        assert st[1] <= 1.1 * st[2], list(st)  # modelled wavefronts vs conflict-free count
 
 
 @pytest.mark.parametrize("N,radix,hop,frames,ordered,W,seg_groups", [(2048, 32, 512, 21, True, 8, 1), (2048, 32, 512, 21, False, 8, 2), (2048, 16, 2048, 5, True, 8, 1),

@@ -295,6 +295,49 @@ def test_stft_forward_window_and_layouts(cf, oracle_mod, N, hop, frames, tail, p
     cf.fft_destroy_setup(s)
 
 
+@pytest.mark.parametrize("N,is_c,hop,frames", [(2048, False, 512, 937), (2048, False, 2048, 50), (1024, False, 100, 333), (1024, True, 2048, 700),
+                                               (512, True, 1024, 5000), (2048, False, 510, 40)])
+@pytest.mark.parametrize("warps", [0, 4, 1])
+def test_warp_pipelined_kernel(cf, oracle_mod, N, is_c, hop, frames, warps):
+    """Tuning hook wpipe: the sizes one warp owns go through wpipe_kernel (per-warp TMA prefetch pipeline) -- plain
+    batches, overlapping frames, windows, ordered and unordered, more transforms than resident warps (several trips of
+    every warp's loop) and fewer; hops the TMA unit cannot fetch (not 16-byte aligned) must fall back to the other
+    kernels.  == a loop of single transforms."""
+    o = oracle_mod
+    channels = 3
+    nfl = 2 * N if is_c else N
+    samples = ((frames - 1) * hop + nfl + 11) // 4 * 4
+    rng = np.random.default_rng(N + hop + frames)
+    sig = rng.uniform(-1, 1, (channels, samples)).astype(np.float32)
+    win = (0.5 - 0.5 * np.cos(2 * np.pi * (np.arange(N) + 0.5) / N)).astype(np.float32)
+    W = o.simd_width(N, is_c, True)
+    s = cf.fft_new_setup(N, cf.FFT_COMPLEX if is_c else cf.FFT_REAL)
+    d, dw = dev(sig), dev(win)
+    fr = np.stack([[sig[c, f * hop:f * hop + nfl] for f in range(frames)] for c in range(channels)]).reshape(-1, nfl)
+    if warps == 0:  # the default policy: overlapping or windowed frames only
+        cf.set_tuning("wpipe", -1)
+        cf.fft_transform_strided(s, d, torch.empty((channels, frames, nfl), device="cuda"), channels, frames, samples, hop, frames * nfl, nfl, cf.FFT_FORWARD, True)
+        assert ("wpipe_kernel" in cf.last_kernel()) == (hop % 4 == 0 and hop < nfl), cf.last_kernel()
+    cf.set_tuning("wpipe", 1 | (warps << 8))
+    try:
+        for ordered in (True, False):
+            for w in ((None,) if is_c else (None, dw)):
+                out = torch.full((channels, frames, nfl), float("nan"), device="cuda")
+                n0 = cf.launch_count()
+                if w is None:
+                    cf.fft_transform_strided(s, d, out, channels, frames, samples, hop, frames * nfl, nfl, cf.FFT_FORWARD, ordered)
+                else:
+                    cf.fft_stft_forward(s, d, out, channels, frames, samples, hop, frames * N, N, w, ordered)
+                torch.cuda.synchronize()
+                assert cf.launch_count() - n0 == 1
+                assert ("wpipe_kernel" in cf.last_kernel()) == (hop % 4 == 0), cf.last_kernel()
+                want = o.np_transform((fr * win if w is not None else fr).astype(np.float32), N, is_c, W, False, ordered)
+                assert o.rel_l2(host(out).reshape(-1, nfl), want) < o.parity_tol(N), (ordered, w is not None)
+    finally:
+        cf.set_tuning("wpipe", -1)
+    cf.fft_destroy_setup(s)
+
+
 @pytest.mark.parametrize("N,hop,frames", [(2048, 512, 37), (2048, 2048, 5), (512, 96, 19), (512, 130, 9), (128, 32, 70),
                                           (32, 7, 41), (8192, 1024, 6), (16384, 4096, 3), (1024, 256, 1)])
 def test_istft_overlap_add(cf, oracle_mod, N, hop, frames):
