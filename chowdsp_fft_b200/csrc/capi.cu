@@ -394,6 +394,23 @@ bool pipe_enabled (int logM, int kind, int logW)
 // plain batches already run at the HBM roofline with fft_kernel and lose 5..13 % to the landing-buffer round trip
 constexpr int kWPipeDefault = 2;
 int g_wpipe = kWPipeDefault;
+// tuning hook "wistft": bit 0 = overlap-add synthesis through the warp-pipelined kernel (wistft_kernel) where it applies;
+// bits 8.. = warps per CTA (0 = the kernel's maximum)
+constexpr int kWIstftDefault = 1;
+int g_wistft = kWIstftDefault;
+int device_sm_count()
+{
+    static thread_local int c_dev = -1, c_sms = 148;
+    int dev = 0;
+    if (cudaGetDevice (&dev) == cudaSuccess && dev != c_dev)
+    {
+        int n = 0;
+        if (cudaDeviceGetAttribute (&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            c_sms = n;
+        c_dev = dev;
+    }
+    return c_sms;
+}
 int g_pf_ahead = 0;        // tuning hook "pf_ahead": L2 prefetch distance of the single-kernel transforms, in CTAs
 
 constexpr size_t kZeroCopyBytes = 256 * 1024;     // pinned buffers up to this size are used in place
@@ -1061,6 +1078,59 @@ CFB_API int fft_istft_overlap_add (void* setup, const float* spectra, float* sig
     const int rc = plan_tables (p, t, radix);
     if (rc != 0)
         return rc;
+    // sizes one warp owns, ordered spectra, hop = N/2, N/4 or N/8: every warp is its own pipeline and the overlap-add
+    // stays in registers (wistft_kernel).  Items = (channel, segment); pick the segment count that minimises
+    // (items per resident warp, rounded up) x (frames per segment + halo).
+    {
+        const int wr = p->logM == 10 ? 32 : 16;
+        const bool hop_ok = hop * 2 == p->N || hop * 4 == p->N || hop * 8 == p->N;
+        if ((g_wistft & 1) != 0 && ordered != 0 && has_wpipe (p->logM, wr) && hop_ok && (spec_frame_stride & 3) == 0 && (spec_channel_stride & 3) == 0
+            && (reinterpret_cast<uintptr_t> (spectra) & 15) == 0 && (channel_stride & 1) == 0 && (reinterpret_cast<uintptr_t> (signal) & 7) == 0)
+        {
+            Tables wt;
+            const int wrc = plan_tables (p, wt, wr);
+            if (wrc != 0)
+                return wrc;
+            const int warps = (g_wistft >> 8) > 0 && (g_wistft >> 8) < wistft_warps (p->logM) ? (g_wistft >> 8) : wistft_warps (p->logM);
+            const long long total_warps = (long long) device_sm_count() * warps;
+            const int halo = (int) (p->N / hop) - 1;
+            int nseg = 1, seg_frames = frames;
+            long long best = -1;
+            for (int cand = 1; cand <= 256 && cand <= (frames + 7) / 8; ++cand)
+            {
+                const int sf = (frames + cand - 1) / cand;
+                const int ns = (frames + sf - 1) / sf;
+                const long long items = (long long) channels * ns;
+                const long long cost = ((items + total_warps - 1) / total_warps) * (sf + (ns > 1 ? halo : 0));
+                if (best < 0 || cost < best)
+                {
+                    best = cost;
+                    nseg = ns;
+                    seg_frames = sf;
+                }
+            }
+            FftArgs wa {};
+            wa.in = spectra;
+            wa.out = signal;
+            wa.in_inner = spec_frame_stride;
+            wa.in_outer = spec_channel_stride;
+            wa.out_inner = hop;
+            wa.out_outer = channel_stride;
+            wa.inner = frames;
+            wa.batch = channels * frames;
+            wa.tw = wt.tw;
+            wa.rtw = wt.rtw;
+            wa.window = window;
+            wa.seg_frames = seg_frames;
+            wa.nseg = nseg;
+            wa.scale = scale;
+            note_kernel ("cfb::wistft_kernel<%d,%d,%d>", p->logM, wr, (int) (hop / 64));
+            const cudaError_t we = launch_wistft (p->logM, (int) (hop / 64), warps, wa, static_cast<cudaStream_t> (stream));
+            if (we != cudaSuccess)
+                return fail_cuda (we, "warp-pipelined istft kernel launch");
+            return 0;
+        }
+    }
     // segmentation: a CTA per (channel, segment of frames).  More segments fill the last wave of CTAs better but
     // every segment after a channel's first recomputes a halo of ceil (N / hop) - 1 frames; segments keep at
     // least 8 groups of frames.  Pick the count with the best (wave occupancy) x (useful fraction of the frames).
@@ -1399,6 +1469,11 @@ CFB_API int fft_b200_set_tuning (const char* key, int value)
     if (key != nullptr && std::strcmp (key, "pf_ahead") == 0 && value >= 0)
     {
         g_pf_ahead = value;
+        return 0;
+    }
+    if (key != nullptr && std::strcmp (key, "wistft") == 0)
+    {
+        g_wistft = value == -1 ? kWIstftDefault : value;
         return 0;
     }
     if (key != nullptr && std::strcmp (key, "wpipe") == 0)

@@ -49,6 +49,16 @@ cudaError_t launch_fft_juce (int logM, int kind, int radix, const FftArgs& args,
     }
 }
 bool has_pipe (int logM) { return logM == 13 || logM == 14; }
+cudaError_t launch_wistft (int logM, int hq, int warps, const FftArgs& args, cudaStream_t stream)
+{
+    switch (logM)
+    {
+        case 9: return launch_wistft_9 (hq, warps, args, stream);
+        case 10: return launch_wistft_10 (hq, warps, args, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+int wistft_warps (int logM) { return logM == 9 ? wistft_warps_9() : logM == 10 ? wistft_warps_10() : 0; }
 bool has_wpipe (int logM, int radix) { return (logM == 10 && radix == 32) || (logM == 9 && radix == 16); }
 cudaError_t launch_wpipe (int logM, int kind, int logW, int warps, const FftArgs& args, cudaStream_t stream)
 {

@@ -46,6 +46,14 @@ bool has_wpipe (int logM, int radix);
 cudaError_t launch_wpipe (int logM, int kind, int logW, int warps, const FftArgs& args, cudaStream_t stream);
 cudaError_t launch_wpipe_9 (int kind, int logW, int warps, const FftArgs& args, cudaStream_t stream);
 cudaError_t launch_wpipe_10 (int kind, int logW, int warps, const FftArgs& args, cudaStream_t stream);
+// warp-pipelined overlap-add synthesis (wistft_kernel) for the same sizes: ordered spectra, hop = N/2, N/4 or N/8
+// (hq = hop / 64), 16-byte aligned frames; wistft_warps = warps per CTA (one CTA per SM)
+cudaError_t launch_wistft (int logM, int hq, int warps, const FftArgs& args, cudaStream_t stream);
+int wistft_warps (int logM);
+cudaError_t launch_wistft_9 (int hq, int warps, const FftArgs& args, cudaStream_t stream);
+cudaError_t launch_wistft_10 (int hq, int warps, const FftArgs& args, cudaStream_t stream);
+int wistft_warps_9();
+int wistft_warps_10();
 // number of float2 entries of the stage twiddle table for 2^logM, and the fill routine (fp64 -> fp32)
 int stage_twiddle_len (int logM, int radix);
 void fill_stage_twiddles_rt (int logM, int radix, float2* tw);

@@ -173,6 +173,20 @@ FFT_HD void smem_skip() // keeps the per-warp op sequences aligned when a lane i
 #endif
 }
 
+// value of `v` held by lane `src` of this thread's group of `width` lanes (width = power of two <= 32; every lane of
+// the warp must call it)
+FFT_HD float2 shfl2 (float2 v, int src, int width)
+{
+#ifdef CHOWDSP_EMU
+    return make_float2 (emu::shfl (v.x, src, width), emu::shfl (v.y, src, width));
+#else
+    return make_float2 (__shfl_sync (0xffffffffu, v.x, src, width), __shfl_sync (0xffffffffu, v.y, src, width));
+#endif
+}
+#ifndef CFB_SHFL_MIRROR
+#define CFB_SHFL_MIRROR 1 // A/B switch (tools/ only): 0 = the real split / merge step always exchanges through shared memory
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // complex arithmetic.  DIR = -1 forward (e^{-i..}), +1 backward.
 // ---------------------------------------------------------------------------------------------
@@ -797,7 +811,7 @@ FFT_HD void staging_drain (const float* sf, float* __restrict__ out, int j, int 
 //   IN_STAGED  (unordered inputs only): the staging image is already in `s` and synchronised
 //   OUT_STAGED (unordered outputs only): leave the staging image in `s` (synchronised), do not drain it
 //   HALF_OUT   (C2R only): store only the second half of the output samples (overlap-save discard)
-//   IN_UNION   (R2C / C2C_FWD): the stage-0 input is read from the shared-memory image `su` (natural order,
+//   IN_UNION   (R2C / C2C_FWD, and C2R from an ordered spectrum with mode 2): the stage-0 input is read from the shared-memory image `su` (natural order,
 //              unpadded, float2 units; it may alias `s`) and multiplied by the window `win` when non-null.
 //              1 = the image is shared by the transforms of the CTA (the first barrier is CTA-wide), 2 = it is
 //              private to this transform (wpipe_kernel's per-warp landing buffer: transform-level barriers only)
@@ -817,6 +831,10 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
     constexpr int M = G::M, T = G::T;
     // transforms that own their shared-memory region synchronise among their own threads only (tsync)
     constexpr bool WS = ! IN_STAGED && ! OUT_STAGED;
+    // real split / merge: transforms owned by (part of) one warp exchange the mirror half of the spectrum by shuffle
+    // (measured, profiles/r01_shfl_mirror.txt: +3..14 % for 16 points per thread and in the warp-pipelined kernels; with
+    // 32 points per thread in fft_kernel the 32 extra shuffles + selects cost 2..5 %, so that geometry keeps shared memory)
+    constexpr bool SHFL_MIRROR = CFB_SHFL_MIRROR != 0 && T <= 32 && (KIND == R2C || KIND == C2R) && (R == 16 || IN_UNION == 2);
     float* sf = reinterpret_cast<float*> (s); // the same buffer seen as the unordered staging image
     constexpr int logW = LOGW;
     struct { const float2* tw; const float2* rtw; } a { tw_, rtw_ };
@@ -890,21 +908,40 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
                 v[m] = staged_load (sf, up.real_lo (m), WL);
                 xb[m] = staged_load (sf, (m == 0 && j == 0) ? W_HALF_ROW<LOGW>() : up.real_hi (m), WL);
             }
-            tsync<T, WS>(); // staging image fully consumed before the natural-order image overwrites it
+            if constexpr (! SHFL_MIRROR)
+                tsync<T, WS>(); // staging image fully consumed before the natural-order image overwrites it
         }
         else
         {
-            const float2* __restrict__ lo = reinterpret_cast<const float2*> (in) + j;
-            const float2* __restrict__ hi = reinterpret_cast<const float2*> (in) + (M - T) - j;
-#pragma unroll
-            for (int m = 0; m < R / 2; ++m)
+            if constexpr (IN_UNION != 0)
             {
-                const float2* ph = (m == 0 && j == 0) ? reinterpret_cast<const float2*> (in) + M / 2 : hi - m * T + T;
-                v[m] = ldg_stream (lo + m * T);
-                xb[m] = ldg_stream (ph);
+                // ordered spectrum already in shared memory (`su`, natural order, unpadded): unit-stride reads both ways
+                static_assert (IN_UNION == 0 || FMT == 0, "landing-buffer input is for the pffft packing");
+                const float2* lo = su + j;
+                const float2* hi = su + (M - T) - j;
+#pragma unroll
+                for (int m = 0; m < R / 2; ++m)
+                {
+                    const float2* ph = (m == 0 && j == 0) ? su + M / 2 : hi - m * T + T;
+                    v[m] = lds2 (lo + m * T);
+                    xb[m] = lds2 (ph);
+                }
+                smem_was_read = true;
             }
-            if (FMT == 1 && j == 0)
-                v[0].y = ldg_stream (reinterpret_cast<const float2*> (in) + M).x; // Nyquist lives in bin M, not in float 1
+            else
+            {
+                const float2* __restrict__ lo = reinterpret_cast<const float2*> (in) + j;
+                const float2* __restrict__ hi = reinterpret_cast<const float2*> (in) + (M - T) - j;
+#pragma unroll
+                for (int m = 0; m < R / 2; ++m)
+                {
+                    const float2* ph = (m == 0 && j == 0) ? reinterpret_cast<const float2*> (in) + M / 2 : hi - m * T + T;
+                    v[m] = ldg_stream (lo + m * T);
+                    xb[m] = ldg_stream (ph);
+                }
+                if (FMT == 1 && j == 0)
+                    v[0].y = ldg_stream (reinterpret_cast<const float2*> (in) + M).x; // Nyquist lives in bin M, not in float 1
+            }
         }
         const float2 wj = __ldg (a.rtw + j);
 #pragma unroll
@@ -926,11 +963,35 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
                 slot = G::pad (M / 2);
             }
             v[m] = zk;
-            sts2 (s + slot, zm);
+            if constexpr (SHFL_MIRROR)
+                xb[m] = zm;
+            else
+                sts2 (s + slot, zm);
         }
-        tsync<T, WS>();
-        gather_natural<G, R / 2, R> (v, j, s);
-        smem_was_read = true;
+        if constexpr (SHFL_MIRROR)
+        {
+            // Z'[M-k] computed by thread T-j is this thread's register R-1-m; thread 0 computed its own registers R-m
+            // (bins M - m T) and, as its first pair, R/2 (bin M/2)
+#pragma unroll
+            for (int m = 0; m < R / 2; ++m)
+                v[R - 1 - m] = shfl2 (xb[m], (T - j) & (T - 1), T);
+            if (j == 0)
+            {
+#pragma unroll
+                for (int m = 1; m < R / 2; ++m)
+                    v[R - m] = xb[m];
+                v[R / 2] = xb[0];
+            }
+            if constexpr (UNORD)
+                smem_was_read = true; // the staging image was read: a barrier must precede the first exchange
+        }
+        else
+        {
+            static_assert (SHFL_MIRROR || IN_UNION == 0, "landing-buffer C2R input needs the shuffle merge (the exchange buffer is not synchronised yet)");
+            tsync<T, WS>();
+            gather_natural<G, R / 2, R> (v, j, s);
+            smem_was_read = true;
+        }
     }
 
     // ---- the stages -----------------------------------------------------------------------------
@@ -972,16 +1033,38 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
     {
         // Z[k], k = j + m T < M/2, is this thread's register m; Z[M-k] is register R-1-m of thread T-j:
         // only the upper half of the spectrum goes through shared memory.
-        if (smem_was_read)
-            tsync<T, WS && ! (IN_UNION == 1 && G::S == 1)>();
-        scatter_natural<G, R / 2, R> (v, j, s);
-        tsync<T, WS>();
         float2 zb[R / 2];
+        if constexpr (SHFL_MIRROR)
+        {
+            // transforms that live inside one warp: the mirror element comes straight from thread T-j's register
+            // R-1-m by shuffle (half the shared-memory wavefronts of the store + load round trip, no barriers);
+            // thread 0's mirrors are its own registers R-m (bins M - m T) and R/2 (bin M/2)
 #pragma unroll
-        for (int m = 0; m < R / 2; ++m)
-            zb[m] = lds2 (s + ((m == 0 && j == 0) ? G::pad (M / 2) : mirror_slot<G> (j, m)));
-        if constexpr (UNORD)
-            tsync<T, WS>(); // natural-order image fully consumed before the staging image overwrites it
+            for (int m = 0; m < R / 2; ++m)
+                zb[m] = shfl2 (v[R - 1 - m], (T - j) & (T - 1), T);
+            if (j == 0)
+            {
+#pragma unroll
+                for (int m = 1; m < R / 2; ++m)
+                    zb[m] = v[R - m];
+                zb[0] = v[R / 2];
+            }
+            if constexpr (UNORD)
+                if (smem_was_read)
+                    tsync<T, WS && ! (IN_UNION == 1 && G::S == 1)>(); // the last exchange has been read: the staging image may overwrite it
+        }
+        else
+        {
+            if (smem_was_read)
+                tsync<T, WS && ! (IN_UNION == 1 && G::S == 1)>();
+            scatter_natural<G, R / 2, R> (v, j, s);
+            tsync<T, WS>();
+#pragma unroll
+            for (int m = 0; m < R / 2; ++m)
+                zb[m] = lds2 (s + ((m == 0 && j == 0) ? G::pad (M / 2) : mirror_slot<G> (j, m)));
+            if constexpr (UNORD)
+                tsync<T, WS>(); // natural-order image fully consumed before the staging image overwrites it
+        }
         const float2 wj = __ldg (a.rtw + j);
         float2* __restrict__ lo = reinterpret_cast<float2*> (out) + j;
         float2* __restrict__ hi = reinterpret_cast<float2*> (out) + (M - T) - j;

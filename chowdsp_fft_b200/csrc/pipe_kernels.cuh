@@ -341,6 +341,161 @@ __global__ void __launch_bounds__ (WPipeGeo<LOGM, R, LOGW>::MAX_WARPS * 32, 1) w
     wpipe_body<LOGM, R, KIND, LOGW> (a);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-pipelined overlap-add synthesis (wistft_kernel): the inverse STFT for the sizes one warp owns, hop = N / 2, N / 4
+// or N / 8.  out[c][t] = scale * sum over frames f of window[t - f hop] * C2R (spectrum (c, f)) [t - f hop], as istft_kernel,
+// but a WARP walks through the frames [fs, fe) of one (channel, segment) item on its own:
+//   * the next frame's spectrum arrives by the warp's own bulk copy while the current one is transformed (as wpipe_kernel);
+//   * thread j's result registers are the samples 2 (j + 32 m) (+1), and hop / 2 = 32 HQ, so the overlap-add never
+//     leaves the thread: the N - hop samples a frame shares with its successors live in R - HQ accumulator REGISTERS
+//     that shift by HQ per frame; the hop samples that are final are stored straight from registers.  No shared-memory
+//     traffic, no barrier and no atomics for the overlap-add; the sums are formed in frame order (bit-reproducible).
+// Segments other than a channel's first start N / hop - 1 frames early (halo, recomputed, not stored).  Items are
+// distributed like wpipe_kernel's transforms (contiguous share per CTA, shared-memory counter inside).
+// Ordered (pffft-packed) spectra, 16-byte aligned frames, 8-byte aligned signals.
+// ---------------------------------------------------------------------------------------------
+template <int LOGM, int R, int HQ>
+FFT_HD void wistft_body (const FftArgs& a)
+{
+    using WP = WPipeGeo<LOGM, R, 0>;
+    static_assert (HQ >= 1 && 2 * HQ <= R, "hop <= N / 2");
+    constexpr int NACC = R - HQ;            // float2 accumulators per thread: the N - hop carried samples
+    constexpr int HOP2 = 32 * HQ;           // hop in float2 units
+    constexpr int HALO = R / HQ - 1;
+    FFT_DYN_SMEM (char, smem);
+    const int tid = (int) threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int wpc = (int) blockDim.x >> 5;
+    char* wbase = smem + (size_t) warp * WP::WARP_BYTES;
+    float2* land = reinterpret_cast<float2*> (wbase);
+    float2* xch = reinterpret_cast<float2*> (wbase + WP::IN_BYTES);
+    unsigned long long* bar = reinterpret_cast<unsigned long long*> (wbase + WP::IN_BYTES + WP::SMEM_F2 * 8);
+    volatile unsigned* wnext = reinterpret_cast<volatile unsigned*> (bar + 1);
+    unsigned* counter = reinterpret_cast<unsigned*> (smem + (size_t) wpc * WP::WARP_BYTES);
+
+    const int frames = a.inner;
+    const long long items = (long long) (a.batch / a.inner) * a.nseg;
+    const long long first = items * (long long) blockIdx.x / (long long) gridDim.x;
+    const unsigned count = (unsigned) (items * ((long long) blockIdx.x + 1) / (long long) gridDim.x - first);
+    const float2* __restrict__ win2 = reinterpret_cast<const float2*> (a.window);
+    const float2 scale2 = make_float2 (a.scale, a.scale);
+
+    auto decode = [&] (unsigned i, int& c, int& fs, int& fe)
+    {
+        const long long t = first + i;
+        c = (int) (t / a.nseg);
+        fs = (int) (t - (long long) c * a.nseg) * a.seg_frames;
+        fe = fs + a.seg_frames < frames ? fs + a.seg_frames : frames;
+    };
+    auto fetch = [&] (int c, int f)
+    {
+        mbar_expect (bar, (unsigned) WP::IN_BYTES);
+        bulk_copy (land, a.in + (long long) c * a.in_outer + (long long) f * a.in_inner, (unsigned) WP::IN_BYTES, bar);
+    };
+    if (tid == 0)
+        *counter = 0u;
+    __syncthreads();
+    if (lane == 0)
+    {
+        mbar_init (bar);
+        const unsigned i = smem_take (counter);
+        *wnext = i;
+        if (i < count)
+        {
+            int c, fs, fe;
+            decode (i, c, fs, fe);
+            fetch (c, fs - HALO > 0 ? fs - HALO : 0);
+        }
+    }
+    tsync<32, true>();
+    unsigned cur = *wnext;
+    if (cur >= count)
+        return;
+    int c, fs, fe;
+    decode (cur, c, fs, fe);
+    int f = fs - HALO > 0 ? fs - HALO : 0;
+    float2 acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i)
+        acc[i] = make_float2 (0.f, 0.f);
+    for (unsigned it = 0;; ++it)
+    {
+        mbar_wait (bar, it, (unsigned) WP::IN_BYTES);
+        const bool last_of_item = f + 1 == fe;
+        const auto input_consumed = [&]
+        {
+            if (lane == 0)
+            {
+                if (! last_of_item)
+                    fetch (c, f + 1);
+                else
+                {
+                    const unsigned i = smem_take (counter);
+                    *wnext = i;
+                    if (i < count)
+                    {
+                        int c2, fs2, fe2;
+                        decode (i, c2, fs2, fe2);
+                        fetch (c2, fs2 - HALO > 0 ? fs2 - HALO : 0);
+                    }
+                }
+            }
+        };
+        float2 v[R];
+        fft_core<LOGM, R, C2R, 0, false, false, false, 2, decltype (input_consumed), true> (nullptr, nullptr, true, lane, xch, a.tw, a.rtw, land, nullptr, input_consumed, v);
+#pragma unroll
+        for (int m = 0; m < R; ++m)
+        {
+            v[m] = f2_mul (v[m], scale2);
+            if (win2 != nullptr)
+                v[m] = f2_mul (v[m], __ldg (win2 + lane + 32 * m));
+        }
+        // overlap-add in registers: slot m of this frame is slot m - HQ of the next one
+        float2* __restrict__ sig2 = reinterpret_cast<float2*> (a.out + (long long) c * a.out_outer) + (long long) f * HOP2 + lane;
+        if (f >= fs)
+        {
+#pragma unroll
+            for (int m = 0; m < HQ; ++m)
+                sig2[32 * m] = f2_add (acc[m], v[m]);
+        }
+#pragma unroll
+        for (int i = 0; i < NACC; ++i)
+            acc[i] = i + HQ < NACC ? f2_add (acc[i + HQ], v[i + HQ]) : v[i + HQ];
+        if (! last_of_item)
+        {
+            ++f;
+            continue;
+        }
+        if (fe == frames) // end of the channel: the carried samples are output too
+        {
+#pragma unroll
+            for (int i = 0; i < NACC; ++i)
+                sig2[HOP2 + 32 * i] = acc[i];
+        }
+        cur = *wnext;
+        if (cur >= count)
+            break;
+        decode (cur, c, fs, fe);
+        f = fs - HALO > 0 ? fs - HALO : 0;
+#pragma unroll
+        for (int i = 0; i < NACC; ++i)
+            acc[i] = make_float2 (0.f, 0.f);
+    }
+}
+
+template <int LOGM, int R>
+struct WIstftGeo
+{
+    // 64 result + up to 56 accumulator registers per thread on top of the transform's temporaries: 12 resident warps
+    // (168 registers per thread) for 32 points per thread, 16 (128) for 16
+    static constexpr int MAX_WARPS = R == 32 ? 12 : 16;
+};
+template <int LOGM, int R, int HQ>
+__global__ void __launch_bounds__ (WIstftGeo<LOGM, R>::MAX_WARPS * 32, 1) wistft_kernel (const FftArgs a)
+{
+    wistft_body<LOGM, R, HQ> (a);
+}
+
 // start the copy of one transform into the landing buffer (called by every thread of the CTA)
 template <class P>
 FFT_HD void pipe_fetch (char* land, const float* src, int j, unsigned long long* bar)

@@ -47,9 +47,21 @@ struct ThreadCtx
     std::barrier<>* group_bar[3] = { nullptr, nullptr, nullptr }; // barriers of this thread's group of 32 / 64 / 128 threads
     char* smem = nullptr;
     std::vector<SmemOp>* log = nullptr; // per-thread smem op sequence (bank-conflict analysis)
+    float* shfl_buf = nullptr;          // 32 floats of this thread's warp (warp shuffles)
+    int lane = 0;
 };
 inline thread_local ThreadCtx ctx;
 inline void syncgroup (int n) { ctx.group_bar[n == 32 ? 0 : n == 64 ? 1 : 2]->arrive_and_wait(); } // __syncwarp / named barriers
+
+// __shfl_sync (full mask) with a sub-group width: publish, barrier, read the source lane's value, barrier
+inline float shfl (float v, int src, int width)
+{
+    ctx.shfl_buf[ctx.lane] = v;
+    syncgroup (32);
+    const float r = ctx.shfl_buf[(ctx.lane & ~(width - 1)) + (src & (width - 1))];
+    syncgroup (32);
+    return r;
+}
 
 struct ConflictStats
 {
@@ -125,6 +137,7 @@ void launch (Kernel kernel, dim3 grid, dim3 block, size_t smem_bytes, Args... ar
             for (unsigned w = 0, n = 32u << gi; w < (nthreads + n - 1) / n; ++w)
                 group_bars[gi].emplace_back (new std::barrier<> ((std::ptrdiff_t) std::min (n, nthreads - n * w)));
         std::vector<std::vector<SmemOp>> logs (nthreads);
+        std::vector<float> shfl_bufs ((nthreads + 31) / 32 * 32);
         std::vector<std::thread> pool;
         pool.reserve (nthreads);
         for (unsigned t = 0; t < nthreads; ++t)
@@ -138,6 +151,8 @@ void launch (Kernel kernel, dim3 grid, dim3 block, size_t smem_bytes, Args... ar
                                    for (int gi = 0; gi < 3; ++gi)
                                        ctx.group_bar[gi] = group_bars[gi][t / (32u << gi)].get();
                                    ctx.smem = smem.data();
+                                   ctx.shfl_buf = shfl_bufs.data() + (t / 32) * 32;
+                                   ctx.lane = (int) (t % 32);
                                    ctx.log = g_log_smem ? &logs[t] : nullptr;
                                    kernel (args...);
                                });

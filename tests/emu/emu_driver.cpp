@@ -356,6 +356,40 @@ int emu_wpipe (int logM, int radix, int kind, int unord, int logW, const float* 
     return rc;
 }
 
+// warp-pipelined overlap-add synthesis (wistft_kernel): hop = 64 hq floats, `grid` CTAs of `warps` warps, segments of seg_frames
+int emu_wistft (int logM, int hq, const float* spec, float* sig, int channels, int frames, long long spec_channel_stride, long long spec_frame_stride, long long channel_stride, const float* window, float scale, int seg_frames, int grid, int warps)
+{
+    auto run = [&] (auto logm_c, auto r_c, auto hq_c) -> int
+    {
+        constexpr int LOGM = decltype (logm_c)::value, R = decltype (r_c)::value, HQ = decltype (hq_c)::value;
+        using WP = WPipeGeo<LOGM, R, 0>;
+        using G = Geo<LOGM, R>;
+        std::vector<float2> tw ((size_t) G::TW_LEN + 1), rtw ((size_t) G::M / 2 + 1);
+        fill_stage_twiddles<LOGM, R> (tw.data());
+        fill_real_twiddles (rtw.data(), G::M);
+        FftArgs a {};
+        a.in = spec; a.out = sig;
+        a.in_inner = spec_frame_stride; a.in_outer = spec_channel_stride; a.out_inner = 64 * HQ; a.out_outer = channel_stride;
+        a.inner = frames; a.batch = channels * frames;
+        a.tw = tw.data(); a.rtw = rtw.data();
+        a.window = window;
+        a.scale = scale;
+        a.seg_frames = seg_frames;
+        a.nseg = (frames + seg_frames - 1) / seg_frames;
+        if (warps <= 0 || warps > WIstftGeo<LOGM, R>::MAX_WARPS)
+            return -2;
+        emu::launch (wistft_kernel<LOGM, R, HQ>, dim3 ((unsigned) grid), dim3 ((unsigned) warps * 32), (size_t) WP::smem_bytes (warps), a);
+        return 0;
+    };
+    using std::integral_constant;
+    emu::g_log_smem = false;
+    int rc = -1;
+#define CFB_EMU_WI(M, RR, H) if (logM == M && hq == H) rc = run (integral_constant<int, M> {}, integral_constant<int, RR> {}, integral_constant<int, H> {});
+    CFB_EMU_WI (10, 32, 16) CFB_EMU_WI (10, 32, 8) CFB_EMU_WI (10, 32, 4) CFB_EMU_WI (9, 16, 8) CFB_EMU_WI (9, 16, 4) CFB_EMU_WI (9, 16, 2)
+#undef CFB_EMU_WI
+    return rc;
+}
+
 // overlap-add synthesis (istft_kernel): `channels` x `frames` spectra -> signals, segments of seg_groups CTA groups
 int emu_istft (int logM, int radix, int unord, int logW, const float* spec, float* sig, int channels, int frames, long long spec_channel_stride, long long spec_frame_stride, long long channel_stride, long long hop, const float* window, float scale, int seg_groups)
 {

@@ -21,6 +21,7 @@ def emu():
     L.emu_pipe.argtypes = [C.c_int, C.c_int, C.c_int, fp, fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_long)]
     L.emu_stft_pipe.argtypes = [C.c_int] * 4 + [fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 4 + [fp, C.c_int, C.c_int, C.POINTER(C.c_long)]
     L.emu_wpipe.argtypes = [C.c_int] * 5 + [fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 4 + [fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_long)]
+    L.emu_wistft.argtypes = [C.c_int, C.c_int, fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 3 + [fp, C.c_float, C.c_int, C.c_int, C.c_int]
     L.emu_istft.argtypes = [C.c_int] * 4 + [fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 4 + [fp, C.c_float, C.c_int]
     L.emu_mixed.argtypes = [C.c_int, C.c_int, C.c_int, fp, fp, C.c_int, C.c_longlong, C.c_longlong, C.c_int]
     L.emu_fft_juce.argtypes = [C.c_int, C.c_int, C.c_int, fp, fp, C.c_int, C.c_longlong, C.c_longlong]
@@ -334,6 +335,29 @@ def test_emulated_warp_pipelined(emu, oracle_mod, N, is_c, hop, frames, ordered,
     assert o.rel_l2(out, want) < min(o.parity_tol(N), 4e-7)
     if ordered:
         assert st[1] <= 1.1 * st[2], list(st)  # modelled wavefronts vs conflict-free count
+
+
+@pytest.mark.parametrize("N,hop,frames,seg_frames,grid,warps", [(2048, 512, 21, 21, 1, 2), (2048, 512, 23, 8, 2, 3), (2048, 1024, 9, 4, 1, 10), (2048, 256, 30, 11, 2, 2),
+                                                                (1024, 256, 19, 19, 1, 1), (1024, 512, 9, 3, 3, 2), (1024, 128, 40, 16, 2, 5)])
+@pytest.mark.parametrize("windowed", [False, True])
+def test_emulated_warp_pipelined_istft(emu, oracle_mod, N, hop, frames, seg_frames, grid, warps, windowed):
+    """Warp-pipelined overlap-add synthesis (wistft_kernel): accumulators in registers shifting by hop per frame, segments
+    with recomputed halos, channel tails, fewer and more items than warps; every output sample written exactly once (the
+    buffer starts as NaN); == oracle.np_istft_overlap_add."""
+    o = oracle_mod
+    channels = 3
+    rng = np.random.default_rng(N + hop + 7)
+    x = rng.uniform(-1, 1, (channels * frames, N)).astype(np.float32)
+    spec = np.ascontiguousarray(o.np_transform(x, N, False, 8, False, True).reshape(channels, frames, N))
+    win = (0.5 - 0.5 * np.cos(2 * np.pi * (np.arange(N) + 0.5) / N)).astype(np.float32)
+    samples = (frames - 1) * hop + N
+    out = np.full((channels, samples + 6), np.nan, np.float32)
+    rc = emu.emu_wistft(int(np.log2(N)) - 1, hop // 64, spec.ctypes.data_as(fp), out.ctypes.data_as(fp), channels, frames, frames * N, N, samples + 6,
+                        win.ctypes.data_as(fp) if windowed else None, 1.0 / N, seg_frames, grid, warps)
+    assert rc == 0
+    want = o.np_istft_overlap_add(spec, N, hop, 8, True, win if windowed else None, 1.0 / N)
+    assert np.all(np.isnan(out[:, samples:]))
+    assert o.rel_l2(out[:, :samples], want) < min(o.parity_tol(N), 4e-7)
 
 
 @pytest.mark.parametrize("N,radix,hop,frames,ordered,W,seg_groups", [(2048, 32, 512, 21, True, 8, 1), (2048, 32, 512, 21, False, 8, 2), (2048, 16, 2048, 5, True, 8, 1),

@@ -372,6 +372,48 @@ def test_istft_overlap_add(cf, oracle_mod, N, hop, frames):
         cf.fft_destroy_setup(s)
 
 
+@pytest.mark.parametrize("N,hop,frames,channels", [(2048, 512, 934, 40), (2048, 1024, 300, 7), (2048, 256, 200, 3), (1024, 256, 1500, 33), (1024, 128, 77, 2), (1024, 512, 9, 1)])
+@pytest.mark.parametrize("warps", [0, 3])
+def test_warp_pipelined_istft(cf, oracle_mod, N, hop, frames, channels, warps):
+    """Overlap-add synthesis through wistft_kernel (sizes one warp owns, hop = N/2, N/4, N/8, ordered spectra): accumulators
+    in registers, segments with recomputed halos chosen by the host for the device's resident warps, several items per
+    warp; == oracle.np_istft_overlap_add, every sample written exactly once, and bit-identical to a second run
+    (owner-computes, no atomics).  Also the STFT -> ISTFT round trip with a Hann window at 75 % overlap."""
+    o = oracle_mod
+    rng = np.random.default_rng(N + hop + frames)
+    x = rng.uniform(-1, 1, (channels * frames, N)).astype(np.float32)
+    win = (0.5 - 0.5 * np.cos(2 * np.pi * (np.arange(N) + 0.5) / N)).astype(np.float32)
+    samples = (frames - 1) * hop + N
+    s = cf.fft_new_setup(N, cf.FFT_REAL)
+    spec = np.ascontiguousarray(o.np_transform(x, N, False, 8, False, True).reshape(channels, frames, N))
+    dspec, dw = dev(spec), dev(win)
+    cf.set_tuning("wistft", 1 | (warps << 8))
+    try:
+        for w in (None, dw):
+            out = torch.full((channels, samples + 6), float("nan"), device="cuda")
+            n0 = cf.launch_count()
+            cf.fft_istft_overlap_add(s, dspec, out, channels, frames, frames * N, N, samples + 6, hop, w, 1.0 / N, True)
+            torch.cuda.synchronize()
+            assert cf.launch_count() - n0 == 1 and "wistft_kernel" in cf.last_kernel(), cf.last_kernel()
+            got = host(out)
+            assert np.all(np.isnan(got[:, samples:]))
+            want = o.np_istft_overlap_add(spec, N, hop, 8, True, win if w is not None else None, 1.0 / N)
+            assert o.rel_l2(got[:, :samples], want) < o.parity_tol(N), w is not None
+            out2 = torch.full_like(out, float("nan"))
+            cf.fft_istft_overlap_add(s, dspec, out2, channels, frames, frames * N, N, samples + 6, hop, w, 1.0 / N, True)
+            torch.cuda.synchronize()
+            assert torch.equal(out[:, :samples], out2[:, :samples])
+        cf.set_tuning("wistft", 0)  # the CTA-per-segment kernel gives the same signal
+        out3 = torch.full((channels, samples + 6), float("nan"), device="cuda")
+        cf.fft_istft_overlap_add(s, dspec, out3, channels, frames, frames * N, N, samples + 6, hop, dw, 1.0 / N, True)
+        torch.cuda.synchronize()
+        assert "istft_kernel" in cf.last_kernel() and "wistft" not in cf.last_kernel()
+        assert o.rel_l2(host(out3)[:, :samples], host(out)[:, :samples]) < 1e-6
+    finally:
+        cf.set_tuning("wistft", -1)
+        cf.fft_destroy_setup(s)
+
+
 def test_istft_rejects_what_does_not_fit(cf):
     s = cf.fft_new_setup(32768, cf.FFT_REAL)
     try:
