@@ -718,11 +718,17 @@ int staged_transform (Plan* p, const float* in, float* out, int batch, long long
         if (rc != 0)
             return rc;
         cudaStream_t st = s.stream[lane];
-        CFB_CUDA (cudaMemcpy2DAsync (s.buf[lane][0], row_bytes, in + (long long) b0 * in_stride, (size_t) (batch > 1 ? in_stride : nfl) * sizeof (float), row_bytes, (size_t) nb, cudaMemcpyHostToDevice, st));
+        if (batch == 1 || in_stride == nfl) // dense rows: one linear copy
+            CFB_CUDA (cudaMemcpyAsync (s.buf[lane][0], in + (long long) b0 * nfl, row_bytes * (size_t) nb, cudaMemcpyHostToDevice, st));
+        else
+            CFB_CUDA (cudaMemcpy2DAsync (s.buf[lane][0], row_bytes, in + (long long) b0 * in_stride, (size_t) in_stride * sizeof (float), row_bytes, (size_t) nb, cudaMemcpyHostToDevice, st));
         rc = enqueue_transform (p, s.buf[lane][0], s.buf[lane][1], 1, nb, 0, nfl, 0, nfl, direction, ordered, st);
         if (rc != 0)
             return rc;
-        CFB_CUDA (cudaMemcpy2DAsync (out + (long long) b0 * out_stride, (size_t) (batch > 1 ? out_stride : nfl) * sizeof (float), s.buf[lane][1], row_bytes, row_bytes, (size_t) nb, cudaMemcpyDeviceToHost, st));
+        if (batch == 1 || out_stride == nfl)
+            CFB_CUDA (cudaMemcpyAsync (out + (long long) b0 * nfl, s.buf[lane][1], row_bytes * (size_t) nb, cudaMemcpyDeviceToHost, st));
+        else
+            CFB_CUDA (cudaMemcpy2DAsync (out + (long long) b0 * out_stride, (size_t) out_stride * sizeof (float), s.buf[lane][1], row_bytes, row_bytes, (size_t) nb, cudaMemcpyDeviceToHost, st));
     }
     for (int l = 0; l < 2; ++l)
         if (t_staging.stream[l] != nullptr)
@@ -1446,6 +1452,11 @@ CFB_API int fft_accumulate_batched (void* setup, const float* a, const float* b,
 
 CFB_API int fft_b200_set_tuning (const char* key, int value)
 {
+    if (key != nullptr && std::strcmp (key, "tile_pipe") == 0 && (value == 0 || value == 1 || value == -1))
+    {
+        tile_pipe_mode() = value == -1 ? 1 : value;
+        return 0;
+    }
     if (key != nullptr && std::strcmp (key, "tile_c") == 0 && (value == 0 || value == 8 || value == 16))
     {
         tile_c_override() = value;

@@ -1,4 +1,6 @@
 // Instantiations and launchers of the multi-pass (large transform) kernels.
+#include <cstdint>
+
 #include "dispatch.h"
 #include "large_plan.h"
 
@@ -21,12 +23,63 @@ cudaError_t launch_tile_one (const TileArgs& a, cudaStream_t stream)
     count_launch();
     return cudaGetLastError();
 }
+// persistent TMA-staged variant; cudaErrorInvalidConfiguration = does not apply (buffers do not fit / unaligned rows)
+template <int LOGL, int C, int DIR, bool JFAST>
+cudaError_t launch_tile_pipe_one (const TileArgs& a, cudaStream_t stream)
+{
+    using TP = TilePipeLaunch<LOGL, C>;
+    if constexpr (! TP::FITS)
+        return cudaErrorInvalidConfiguration;
+    else
+    {
+        const auto even = [] (long long v) { return (v & 1) == 0; };
+        if ((reinterpret_cast<uintptr_t> (a.in) & 15) != 0 || ! even (a.in_bstride) || ! even (a.in_g_hi) || ! even (a.in_g_lo)
+            || (JFAST ? ! even (a.in_tstride) : (! even (a.in_estride) || (a.in_split_log < 31 && ! even (a.in_chunk_stride)))))
+            return cudaErrorInvalidConfiguration;
+        auto kernel = tile_pipe_kernel<LOGL, C, DIR, JFAST>;
+        static thread_local int c_dev = -1, c_resident = 0;
+        int dev = 0;
+        cudaError_t e = cudaGetDevice (&dev);
+        if (e != cudaSuccess)
+            return e;
+        if (dev != c_dev)
+        {
+            int sms = 0, per_sm = 0;
+            if ((e = cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TP::SMEM_BYTES)) != cudaSuccess
+                || (e = cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess
+                || (e = cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, kernel, TP::THREADS, (size_t) TP::SMEM_BYTES)) != cudaSuccess)
+                return e;
+            if (per_sm < 1)
+                return cudaErrorInvalidConfiguration;
+            c_dev = dev;
+            c_resident = sms * per_sm;
+        }
+        const long long tiles = (long long) a.ntiles * a.batch;
+        if (tiles <= 0)
+            return cudaSuccess;
+        kernel<<<(unsigned) (tiles < c_resident ? tiles : c_resident), TP::THREADS, TP::SMEM_BYTES, stream>>> (a);
+        count_launch();
+        return cudaGetLastError();
+    }
+}
+template <int LOGL, int C, int DIR, bool JFAST>
+cudaError_t launch_tile_any (const TileArgs& a, cudaStream_t stream)
+{
+    if (tile_pipe_mode() != 0)
+    {
+        const cudaError_t e = launch_tile_pipe_one<LOGL, C, DIR, JFAST> (a, stream);
+        if (e != cudaErrorInvalidConfiguration)
+            return e;
+        (void) cudaGetLastError();
+    }
+    return launch_tile_one<LOGL, C, DIR, JFAST> (a, stream);
+}
 template <int LOGL, int C>
 cudaError_t launch_tile_lc (int dir, bool jfast, const TileArgs& a, cudaStream_t stream)
 {
     if (dir < 0)
-        return jfast ? launch_tile_one<LOGL, C, -1, true> (a, stream) : launch_tile_one<LOGL, C, -1, false> (a, stream);
-    return jfast ? launch_tile_one<LOGL, C, +1, true> (a, stream) : launch_tile_one<LOGL, C, +1, false> (a, stream);
+        return jfast ? launch_tile_any<LOGL, C, -1, true> (a, stream) : launch_tile_any<LOGL, C, -1, false> (a, stream);
+    return jfast ? launch_tile_any<LOGL, C, +1, true> (a, stream) : launch_tile_any<LOGL, C, +1, false> (a, stream);
 }
 template <int LOGL>
 cudaError_t launch_tile_l (int C, int dir, bool jfast, const TileArgs& a, cudaStream_t stream)

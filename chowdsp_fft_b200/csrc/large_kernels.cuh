@@ -15,6 +15,7 @@
 // twiddle scheme and exchange code are the ones of the single-kernel transform (fft_kernels.cuh).
 #pragma once
 #include "fft_kernels.cuh"
+#include "pipe_kernels.cuh" // mbarrier + bulk-copy helpers
 
 
 namespace cfb
@@ -69,6 +70,47 @@ FFT_HD float2 big_twiddle (const TileArgs& a, unsigned e)
     const float2 lo = __ldg (a.tw_lo + (e & ((1u << a.tw_lobits) - 1u)));
     const float2 hi = __ldg (a.tw_hi + (e >> a.tw_lobits));
     return cmul_dir<-1> (lo, hi); // forward twiddle; the caller conjugates for DIR > 0
+}
+
+// v[m] = X[jB + m T] of transform ltB -> four-step twiddle -> store (or peer store), shared by tile_body and tile_pipe_body
+template <int LOGL, int C, int DIR>
+FFT_HD void tile_epilogue (const TileArgs& a, float2 (&v)[16], int ghi, int glo, int ltB, int jB, unsigned cT, const float2* sTw, float2* __restrict__ out)
+{
+    constexpr int R = 16;
+    using G = Geo<LOGL, R>;
+    constexpr int T = G::T;
+    // v[m] = X[jB + m T] of transform ltB.  Four-step twiddle W_N^(mu k c), k = jB + m T, c = c0 + ltB:
+    //   W^(mu k c) = W^(mu jB c) * W^(mu m T c) = B (own register, one table lookup per thread)
+    //                                            * A[m][ltB] (16 C values per CTA, looked up once, kept in smem)
+    // so a thread makes 2 (+2 for the first 16 C threads) scattered table loads instead of one pair per element.
+    if (a.tw_mult != 0)
+    {
+        const float2 bw = big_twiddle<DIR> (a, (unsigned) jB * cT * a.tw_mult);
+#pragma unroll
+        for (int m = 0; m < R; ++m)
+        {
+            const float2 wm = m == 0 ? bw : cmul_dir<-1> (bw, lds2 (sTw + m * C + ltB));
+            v[m] = cmul_dir<DIR> (v[m], wm);
+        }
+    }
+    if (a.peer_row_log >= 0)
+    {
+        // the all-to-all of the distributed transform, done by the stores themselves: every row block goes straight
+        // into its owner's receive buffer, so the NVLink transfer overlaps the butterflies of the other tiles
+        const long long toff = a.peer_chunk_off + ghi * a.out_g_hi + glo * a.out_g_lo + ltB * a.out_tstride;
+        const int mask = (1 << a.peer_row_log) - 1;
+#pragma unroll
+        for (int m = 0; m < R; ++m)
+        {
+            const int k = jB + m * T;
+            a.peer_out[k >> a.peer_row_log][toff + (long long) (k & mask) * a.out_estride] = v[m];
+        }
+        return;
+    }
+    float2* __restrict__ q = out + ltB * a.out_tstride + jB * a.out_estride;
+#pragma unroll
+    for (int m = 0; m < R; ++m)
+        q[(long long) (m * T) * a.out_estride] = v[m];
 }
 
 // LOAD_J_FAST: the transforms are contiguous rows (pass C), so the LOAD uses the thread map of the batched
@@ -148,38 +190,7 @@ FFT_HD void tile_body (const TileArgs& a)
         Stages<G, DIR, 0>::run (v, jB, sB, a.tw, false);
     }
 
-    // v[m] = X[jB + m T] of transform ltB.  Four-step twiddle W_N^(mu k c), k = jB + m T, c = c0 + ltB:
-    //   W^(mu k c) = W^(mu jB c) * W^(mu m T c) = B (own register, one table lookup per thread)
-    //                                            * A[m][ltB] (16 C values per CTA, looked up once, kept in smem)
-    // so a thread makes 2 (+2 for the first 16 C threads) scattered table loads instead of one pair per element.
-    if (a.tw_mult != 0)
-    {
-        const float2 bw = big_twiddle<DIR> (a, (unsigned) jB * cT * a.tw_mult);
-#pragma unroll
-        for (int m = 0; m < R; ++m)
-        {
-            const float2 wm = m == 0 ? bw : cmul_dir<-1> (bw, lds2 (sTw + m * C + ltB));
-            v[m] = cmul_dir<DIR> (v[m], wm);
-        }
-    }
-    if (a.peer_row_log >= 0)
-    {
-        // the all-to-all of the distributed transform, done by the stores themselves: every row block goes straight
-        // into its owner's receive buffer, so the NVLink transfer overlaps the butterflies of the other tiles
-        const long long toff = a.peer_chunk_off + ghi * a.out_g_hi + glo * a.out_g_lo + ltB * a.out_tstride;
-        const int mask = (1 << a.peer_row_log) - 1;
-#pragma unroll
-        for (int m = 0; m < R; ++m)
-        {
-            const int k = jB + m * T;
-            a.peer_out[k >> a.peer_row_log][toff + (long long) (k & mask) * a.out_estride] = v[m];
-        }
-        return;
-    }
-    float2* __restrict__ q = out + ltB * a.out_tstride + jB * a.out_estride;
-#pragma unroll
-    for (int m = 0; m < R; ++m)
-        q[(long long) (m * T) * a.out_estride] = v[m];
+    tile_epilogue<LOGL, C, DIR> (a, v, ghi, glo, ltB, jB, cT, sTw, out);
 }
 
 template <int LOGL, int C>
@@ -195,6 +206,153 @@ template <int LOGL, int C, int DIR, bool LOAD_J_FAST>
 __global__ void __launch_bounds__ (TileLaunch<LOGL, C>::THREADS, TileLaunch<LOGL, C>::MIN_BLOCKS) tile_fft_kernel (const TileArgs a)
 {
     tile_body<LOGL, C, DIR, LOAD_J_FAST> (a);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent TMA-staged tile kernel: the same tile transform as tile_fft_kernel, but a resident CTA loops over tiles
+// blockIdx.x, blockIdx.x + gridDim.x, ... and the NEXT tile is brought into a landing buffer by the TMA unit while the
+// current one is transformed -- one bulk copy per element row of the tile (C contiguous complex values, 64 or 128
+// bytes) on the strided passes, one per transform (a contiguous row of L values) on the contiguous-row pass, all
+// completing on one mbarrier.  The strided gather therefore costs no LSU instructions and no register scoreboard
+// waits (ncu on tile_fft_kernel: long-scoreboard 5.3 and MIO-throttle 3.7 stalled warps per issue, DRAM 56 %).
+// The landing image is [element][transform] (strided passes) or [transform][element] (contiguous rows), so the
+// stage-0 registers are read from it with unit-stride 64-bit accesses in the thread map that pass uses anyway.
+// Needs 16-byte aligned rows (the launcher checks the base pointer and the strides).
+// Shared memory: [landing L C float2][exchange regions + twiddle rows as tile_fft_kernel][mbarrier, 16 bytes].
+// ---------------------------------------------------------------------------------------------
+template <int LOGL, int C>
+struct TilePipeLaunch
+{
+    using TL = TileLaunch<LOGL, C>;
+    using G = Geo<LOGL, 16>;
+    static constexpr int THREADS = TL::THREADS;
+    // contiguous-row pass: rows of short transforms (T < 16 threads) are pitched L + T so that the transforms a
+    // half-warp reads from land in different banks
+    static constexpr int ROW_PAD = G::T < 16 ? G::T : 0;
+    static constexpr int LAND_BYTES = (G::M + ROW_PAD) * C * 8;
+    static constexpr int SMEM_BYTES = LAND_BYTES + TL::SMEM_BYTES + 16;
+    static constexpr bool FITS = SMEM_BYTES <= 227 * 1024;
+    static constexpr int PER_SM_A = (227 * 1024) / (SMEM_BYTES + 1024);
+    static constexpr int PER_SM_B = 2048 / THREADS; // 64 registers per thread
+    static constexpr int PER_SM = PER_SM_A < PER_SM_B ? (PER_SM_A < 1 ? 1 : PER_SM_A) : PER_SM_B;
+};
+
+template <int LOGL, int C, int DIR, bool LOAD_J_FAST>
+FFT_HD void tile_pipe_body (const TileArgs& a)
+{
+    constexpr int R = 16;
+    using G = Geo<LOGL, R>;
+    using TP = TilePipeLaunch<LOGL, C>;
+    constexpr int T = G::T, L = G::M;
+    constexpr int RS = tile_region_stride (G::SMEM_F2, C);
+    constexpr int NT = T * C;                  // threads per CTA
+    constexpr unsigned TILE_BYTES = (unsigned) (L * C * 8);
+    constexpr int LP = L + TP::ROW_PAD;        // landing row pitch of the contiguous-row pass
+    static_assert (! LOAD_J_FAST || G::S >= 2, "the thread-map switch needs at least one exchange");
+    FFT_DYN_SMEM (char, smem_raw);
+    float2* land = reinterpret_cast<float2*> (smem_raw);
+    float2* smem = reinterpret_cast<float2*> (smem_raw + TP::LAND_BYTES);
+    unsigned long long* bar = reinterpret_cast<unsigned long long*> (smem_raw + TP::LAND_BYTES + TP::TL::SMEM_BYTES);
+    const int tid = (int) threadIdx.x;
+    const int ltB = tid % C, jB = tid / C; // adjacent threads = adjacent transforms
+    const int ltA = tid / T, jA = tid % T; // adjacent threads = adjacent elements
+    float2* sB = smem + ltB * RS;
+    float2* sTw = smem + C * RS;
+    const long long tiles = (long long) a.ntiles * a.batch;
+    const long long step = (long long) gridDim.x;
+
+    // start the copies of tile t (every thread issues its share of the rows; thread 0 arms the barrier)
+    auto fetch = [&] (long long t)
+    {
+        const int bx = (int) (t / a.ntiles);
+        const int g = (int) (t - (long long) bx * a.ntiles);
+        const int ghi = g / a.gdiv, glo = g - ghi * a.gdiv;
+        const float2* __restrict__ in = a.in + bx * a.in_bstride + ghi * a.in_g_hi + glo * a.in_g_lo;
+        if (tid == 0)
+            mbar_expect (bar, TILE_BYTES);
+        if constexpr (LOAD_J_FAST)
+        {
+            if (tid < C) // transform `tid` is a contiguous row of L elements
+                bulk_copy (land + tid * LP, in + tid * a.in_tstride, (unsigned) L * 8u, bar);
+        }
+        else
+        {
+            const int mask = a.in_split_log >= 31 ? -1 : (1 << a.in_split_log) - 1;
+#pragma unroll
+            for (int i = 0; i < L / NT; ++i) // element row idx: C adjacent transforms = C contiguous values
+            {
+                const int idx = tid + i * NT;
+                const long long off = a.in_split_log >= 31 ? (long long) idx * a.in_estride
+                                                           : (long long) (idx >> a.in_split_log) * a.in_chunk_stride + (long long) (idx & mask) * a.in_estride;
+                bulk_copy (land + idx * C, in + off, (unsigned) C * 8u, bar);
+            }
+        }
+    };
+
+    long long t = (long long) blockIdx.x;
+    if (tid == 0)
+        mbar_init (bar);
+    __syncthreads();
+    if (t < tiles)
+        fetch (t);
+    for (unsigned it = 0; t < tiles; t += step, ++it)
+    {
+        const int bx = (int) (t / a.ntiles);
+        const int g = (int) (t - (long long) bx * a.ntiles);
+        const int ghi = g / a.gdiv, glo = g - ghi * a.gdiv;
+        float2* __restrict__ out = a.out + bx * a.out_bstride + ghi * a.out_g_hi + glo * a.out_g_lo;
+        const unsigned cT = a.tw_c_base + (unsigned) (glo * C + ltB);
+        float2 v[R];
+        mbar_wait (bar, it, TILE_BYTES);
+        if constexpr (LOAD_J_FAST)
+        {
+            const float2* p = land + ltA * LP + jA;
+#pragma unroll
+            for (int m = 0; m < R; ++m)
+                v[m] = lds2 (p + m * T);
+        }
+        else
+        {
+            const float2* p = land + tid; // element jB + m T of transform ltB sits at (jB + m T) C + ltB = tid + m T C
+#pragma unroll
+            for (int m = 0; m < R; ++m)
+                v[m] = lds2 (p + m * NT);
+        }
+        __syncthreads(); // the landing buffer is free again; nobody still reads the previous tile's exchange / twiddle rows
+        if (t + step < tiles)
+            fetch (t + step);
+        if (a.tw_mult != 0)
+        {
+            for (int i = tid; i - tid < R * C; i += NT) // i = m C + lt
+            {
+                if (i < R * C)
+                {
+                    const unsigned c = a.tw_c_base + (unsigned) (glo * C + i % C);
+                    sts2 (sTw + i, big_twiddle<DIR> (a, (unsigned) (i / C) * (unsigned) T * c * a.tw_mult));
+                }
+                else
+                    smem_skip();
+            }
+        } // visibility: every pass has at least one exchange barrier before the twiddle step
+        if constexpr (LOAD_J_FAST)
+        {
+            float2* sA = smem + ltA * RS;
+            stage_compute<G, DIR, 0> (v, jA, a.tw);
+            stage_scatter<G, 0> (v, jA, sA);
+            __syncthreads();
+            gather_natural<G, 0, R> (v, jB, sB);
+            Stages<G, DIR, 1>::run (v, jB, sB, a.tw, true);
+        }
+        else
+            Stages<G, DIR, 0>::run (v, jB, sB, a.tw, false);
+        tile_epilogue<LOGL, C, DIR> (a, v, ghi, glo, ltB, jB, cT, sTw, out);
+    }
+}
+
+template <int LOGL, int C, int DIR, bool LOAD_J_FAST>
+__global__ void __launch_bounds__ (TilePipeLaunch<LOGL, C>::THREADS, TilePipeLaunch<LOGL, C>::PER_SM) tile_pipe_kernel (const TileArgs a)
+{
+    tile_pipe_body<LOGL, C, DIR, LOAD_J_FAST> (a);
 }
 
 // ---------------------------------------------------------------------------------------------

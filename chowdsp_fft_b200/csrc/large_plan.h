@@ -11,6 +11,9 @@ namespace cfb
 constexpr int kTileCMax = 16;
 inline int& tile_c_override() { static int v = 0; return v; }       // tuning hooks (0 = policy below)
 inline int& tile_c_jfast_override() { static int v = 0; return v; } // ... for the contiguous-row (last) pass only
+// tuning hook "tile_pipe": 1 = the persistent TMA-staged tile kernel (tile_pipe_kernel) where its buffers fit and the rows are
+// 16-byte aligned, 0 = tile_fft_kernel everywhere
+inline int& tile_pipe_mode() { static int v = 0; return v; }
 inline int tile_c (int logL, bool jfast = false)
 {
     const int ov = (jfast && tile_c_jfast_override() != 0) ? tile_c_jfast_override() : tile_c_override();

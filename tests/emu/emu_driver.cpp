@@ -74,6 +74,17 @@ template <int LOGL, int C, int DIR>
 void emu_tile_launch_c (const TilePass& p)
 {
     using TL = TileLaunch<LOGL, C>;
+    using TP = TilePipeLaunch<LOGL, C>;
+    if constexpr (TP::FITS)
+        if (tile_pipe_mode() != 0) // persistent TMA-staged variant on (at most) 3 resident CTAs
+        {
+            const unsigned tiles = (unsigned) p.args.ntiles * (unsigned) p.args.batch, grid = tiles < 3u ? tiles : 3u;
+            if (p.load_j_fast)
+                emu::launch (tile_pipe_kernel<LOGL, C, DIR, true>, dim3 (grid), dim3 (TP::THREADS), (size_t) TP::SMEM_BYTES, p.args);
+            else
+                emu::launch (tile_pipe_kernel<LOGL, C, DIR, false>, dim3 (grid), dim3 (TP::THREADS), (size_t) TP::SMEM_BYTES, p.args);
+            return;
+        }
     if (p.load_j_fast)
         emu::launch (tile_fft_kernel<LOGL, C, DIR, true>, dim3 ((unsigned) p.args.ntiles), dim3 (TL::THREADS), (size_t) TL::SMEM_BYTES, p.args);
     else
@@ -474,6 +485,7 @@ int emu_pconv (int logM, int logW, const float* in, long long in_stride, const f
 }
 
 void emu_set_tile_c (int c) { tile_c_override() = c; }
+void emu_set_tile_pipe (int v) { tile_pipe_mode() = v; }
 void emu_set_radix (int r) { g_emu_radix = r; }
 
 int emu_large_c2c (int n, int l1, int l2, int l3, int backward, const float* in, float* out, int log_conflicts, long* stats)

@@ -232,12 +232,15 @@ def test_emulated_fused_partitioned_convolution(emu, oracle_mod, ref_lib, N, W):
 
 
 @pytest.mark.parametrize("tile_c", [8, 16])
+@pytest.mark.parametrize("pipe", [0, 1])
 @pytest.mark.parametrize("n,l1,l2,l3", [(12, 6, 0, 6), (13, 6, 0, 7), (15, 7, 0, 8), (18, 6, 6, 6), (15, 9, 0, 6), (15, 6, 0, 9), (16, 10, 0, 6), (16, 6, 0, 10)])
-def test_emulated_multi_pass_transform(emu, n, l1, l2, l3, tile_c):
+def test_emulated_multi_pass_transform(emu, n, l1, l2, l3, tile_c, pipe):
     """Tile kernels + pass planning of the large-transform path (two- and three-pass four-step), with the
-    factorisation forced so that small sizes exercise it; both tile widths; bank-conflict free exchanges."""
+    factorisation forced so that small sizes exercise it; both tile widths; bank-conflict free exchanges; both the
+    one-tile-per-CTA kernel and the persistent TMA-staged one (3 resident CTAs looping over the tiles)."""
     emu.emu_large_c2c.argtypes = [C.c_int] * 5 + [fp, fp, C.c_int, C.POINTER(C.c_long)]
     emu.emu_set_tile_c(tile_c)
+    emu.emu_set_tile_pipe(pipe)
     N = 1 << n
     rng = np.random.default_rng(n)
     x = rng.uniform(-1, 1, 2 * N).astype(np.float32)

@@ -13,6 +13,10 @@ for a in sys.argv[1:]:
     elif a.startswith("--tile-c="):
         cf.set_tuning("tile_c", int(a.split("=")[1]))
         print("tile_c override:", a.split("=")[1])
+for kv in filter(None, os.environ.get("CFB_TUNE", "").split(",")):
+    k, v = kv.split("=")
+    cf.set_tuning(k, int(v))
+    print("tune:", k, v)
 sizes = [int(a) for a in args] or [15, 16, 18, 20, 22, 24, 26, 28]
 st = torch.cuda.current_stream()
 for is_c in (True, False):
