@@ -183,6 +183,17 @@ FFT_HD float2 shfl2 (float2 v, int src, int width)
     return make_float2 (__shfl_sync (0xffffffffu, v.x, src, width), __shfl_sync (0xffffffffu, v.y, src, width));
 #endif
 }
+FFT_HD float shfl1 (float v, int src, int width)
+{
+#ifdef CHOWDSP_EMU
+    return emu::shfl (v, src, width);
+#else
+    return __shfl_sync (0xffffffffu, v, src, width);
+#endif
+}
+#ifndef CFB_UNORD_DIRECT
+#define CFB_UNORD_DIRECT 1 // A/B switch (tools/ only): 0 = unordered complex spectra always go through the shared-memory staging image
+#endif
 #ifndef CFB_SHFL_MIRROR
 #define CFB_SHFL_MIRROR 1 // A/B switch (tools/ only): 0 = the real split / merge step always exchanges through shared memory
 #endif
@@ -831,6 +842,16 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
     constexpr int M = G::M, T = G::T;
     // transforms that own their shared-memory region synchronise among their own threads only (tsync)
     constexpr bool WS = ! IN_STAGED && ! OUT_STAGED;
+    // Unordered COMPLEX spectra without the staging image: neighbouring threads (bins j, j+1) swap one float by shuffle, so
+    // that the even thread holds (re_j, re_j+1) and the odd one (im_j, im_j+1) -- each a contiguous, 8-byte aligned pair
+    // of the unordered layout.  A warp's 64-bit access then covers whole 64-byte [W re | W im] groups: the same
+    // instruction count as the ordered path, no shared-memory round trip, no barriers.
+    using UPD = UPos<G, UNORD ? LOGW : 2>;
+    constexpr bool UDIRECT = CFB_UNORD_DIRECT != 0 && UNORD && UPD::FAST && (KIND == C2C_FWD || KIND == C2C_BWD);
+    constexpr int UW = UPD::W, ULT = UPD::LT;
+    const int u_odd = j & 1;
+    const int u_base = (((j & ~1) >> (UNORD ? LOGW : 2)) * 2 * UW * UW) + ((j & ~1) & (UW - 1)) + (u_odd ? UW : 0); // float offset of this thread's pair
+    constexpr int SW = T < 32 ? T : 32; // shuffle width: transforms never straddle a warp
     // real split / merge: transforms owned by (part of) one warp exchange the mirror half of the spectrum by shuffle
     // (measured, profiles/r01_shfl_mirror.txt: +3..14 % for 16 points per thread and in the warp-pipelined kernels; with
     // 32 points per thread in fft_kernel the 32 extra shuffles + selects cost 2..5 %, so that geometry keeps shared memory)
@@ -876,6 +897,17 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
                 for (int m = 0; m < R; ++m)
                     v[m] = f2_mul (v[m], __ldg (wj + m * T));
             }
+        }
+    }
+    else if constexpr (KIND == C2C_BWD && UDIRECT && ! IN_STAGED)
+    {
+        const float* __restrict__ ib = in + u_base;
+#pragma unroll
+        for (int m = 0; m < R; ++m)
+        {
+            const float2 ld = ldg_stream (reinterpret_cast<const float2*> (ib + (m % ULT) * (T / UW) * 2 * UW * UW + (m / ULT) * 2 * UW));
+            const float recv = shfl1 (u_odd ? ld.x : ld.y, (j ^ 1) & (SW - 1), SW);
+            v[m] = u_odd ? make_float2 (recv, ld.y) : make_float2 (ld.x, recv);
         }
     }
     else if constexpr (KIND == C2C_BWD)
@@ -1016,6 +1048,18 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
 #pragma unroll
             for (int m = (HALF_OUT ? R / 2 : 0); m < R; ++m)
                 out2[m * T] = (FMT == 1 && KIND != C2C_FWD) ? f2_mul (v[m], make_float2 (inv_n, inv_n)) : v[m];
+        }
+    }
+    else if constexpr (KIND == C2C_FWD && UDIRECT && ! OUT_STAGED)
+    {
+        float* __restrict__ ob = out + u_base;
+#pragma unroll
+        for (int m = 0; m < R; ++m)
+        {
+            const float recv = shfl1 (u_odd ? v[m].x : v[m].y, (j ^ 1) & (SW - 1), SW);
+            const float2 o = u_odd ? make_float2 (recv, v[m].y) : make_float2 (v[m].x, recv);
+            if (active)
+                *reinterpret_cast<float2*> (ob + (m % ULT) * (T / UW) * 2 * UW * UW + (m / ULT) * 2 * UW) = o;
         }
     }
     else if constexpr (KIND == C2C_FWD)
