@@ -23,6 +23,7 @@
 #define FFT_DYN_SMEM(type, name) type* name = reinterpret_cast<type*> (emu::ctx.smem)
 #else
 #include <cuda_runtime.h>
+#include <type_traits>
 #define FFT_HD __device__ __forceinline__
 #define FFT_CX __host__ __device__ constexpr
 #define FFT_DYN_SMEM(type, name)                   \
@@ -149,6 +150,14 @@ FFT_HD void prefetch_transform_l2 (const float* p, int j)
 #endif
 }
 
+// orders this thread's earlier generic-proxy shared-memory accesses before later async-proxy (bulk copy) accesses
+FFT_HD void fence_proxy_async()
+{
+#ifndef CHOWDSP_EMU
+    asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
+
 FFT_HD float2 lds2 (const float2* p)
 {
 #ifdef CHOWDSP_EMU
@@ -193,6 +202,9 @@ FFT_HD float shfl1 (float v, int src, int width)
 }
 #ifndef CFB_UNORD_DIRECT
 #define CFB_UNORD_DIRECT 1 // A/B switch (tools/ only): 0 = unordered complex spectra always go through the shared-memory staging image
+#endif
+#ifndef CFB_UNORD_REAL_DIRECT
+#define CFB_UNORD_REAL_DIRECT 0
 #endif
 #ifndef CFB_SHFL_MIRROR
 #define CFB_SHFL_MIRROR 1 // A/B switch (tools/ only): 0 = the real split / merge step always exchanges through shared memory
@@ -666,8 +678,11 @@ struct Stages
     // from_smem: v was gathered from shared memory just before (a barrier is needed before overwriting it).
     // `input_consumed` runs once, right after the first barrier: every thread of the CTA has then taken its
     // stage-0 input out of shared memory (the persistent kernels start the next input copy there).
-    template <class Hook = NoHook>
-    static FFT_HD void run (float2 (&v)[G::R], int j, float2* s, const float2* __restrict__ tw, bool from_smem, const Hook& input_consumed = Hook())
+    // `last_gathered` (when not NoHook) runs after a barrier that follows the gather of the LAST exchange: from then on
+    // the transform does not touch `s` any more unless its epilogue stages an unordered / real-split image there.
+    template <class Hook = NoHook, class Hook2 = NoHook>
+    static FFT_HD void run (float2 (&v)[G::R], int j, float2* s, const float2* __restrict__ tw, bool from_smem, const Hook& input_consumed = Hook(),
+                            const Hook2& last_gathered = Hook2())
     {
         stage_compute<G, DIR, STAGE> (v, j, tw);
         if constexpr (STAGE < G::S - 1)
@@ -679,7 +694,13 @@ struct Stages
             stage_scatter<G, STAGE> (v, j, s);
             tsync<G::T, WS>();
             gather_natural<G, 0, G::R> (v, j, s);
-            Stages<G, DIR, STAGE + 1, WS, CTA_FIRST>::run (v, j, s, tw, true);
+            if constexpr (STAGE == G::S - 2 && ! std::is_same<Hook2, NoHook>::value)
+            {
+                fence_proxy_async(); // this thread's generic-proxy accesses to `s` are ordered before the async-proxy (TMA) writes the hook starts
+                tsync<G::T, WS>();
+                last_gathered();
+            }
+            Stages<G, DIR, STAGE + 1, WS, CTA_FIRST>::run (v, j, s, tw, true, NoHook(), last_gathered);
         }
     }
 };
@@ -733,10 +754,10 @@ FFT_HD void sts4 (float* p, float4 v)
 // i % W, padded position b (2 W^2 + W) + r 2 W + lane.  Odd rows of the real layout are reversed
 // (i -> (Q - i) mod Q), which turns j into -j; the wrap (i == 0) only ever hits thread j == 0 and is
 // patched with a select.  Falls back to the generic index computation when T < W.
-template <class G, int LOGW>
+template <class G, int LOGW, bool PADDED = true> // PADDED = false: float offsets in the unpadded (global-memory) layout
 struct UPos
 {
-    static constexpr int W = 1 << LOGW, PW = 2 * W * W + W, T = G::T, M = G::M, R = G::R;
+    static constexpr int W = 1 << LOGW, PW = 2 * W * W + (PADDED ? W : 0), T = G::T, M = G::M, R = G::R;
     static constexpr int Q = M / W;                       // bins per lane row
     static constexpr int LOGQ = G::LOGM - LOGW;
     static constexpr bool FAST = (T >= W) && (R >= W);
@@ -747,8 +768,8 @@ struct UPos
         ub_pos = (j_ >> LOGW) * PW + (j_ & (W - 1));
         ub_neg = ((-j_) >> LOGW) * PW + ((-j_) & (W - 1));
     }
-    static FFT_HD int generic_complex (int bin) { return upad (unordered_pos_complex<G::LOGM> (bin, LOGW), LOGW); }
-    static FFT_HD int generic_real (int bin) { return upad (unordered_pos_real<G::LOGM> (bin, LOGW), LOGW); }
+    static FFT_HD int generic_complex (int bin) { return PADDED ? upad (unordered_pos_complex<G::LOGM> (bin, LOGW), LOGW) : unordered_pos_complex<G::LOGM> (bin, LOGW); }
+    static FFT_HD int generic_real (int bin) { return PADDED ? upad (unordered_pos_real<G::LOGM> (bin, LOGW), LOGW) : unordered_pos_real<G::LOGM> (bin, LOGW); }
 
     FFT_HD int cplx (int m) const
     {
@@ -827,14 +848,17 @@ FFT_HD void staging_drain (const float* sf, float* __restrict__ out, int j, int 
 //              1 = the image is shared by the transforms of the CTA (the first barrier is CTA-wide), 2 = it is
 //              private to this transform (wpipe_kernel's per-warp landing buffer: transform-level barriers only)
 //   input_consumed (IN_UNION with more than one stage): hook run after the barrier that follows the stage-0 reads
+//   last_gathered (more than one stage): hook run after a barrier that follows the gather of the last exchange -- `s` is
+//              free from then on for ordered outputs (the warp-pipelined kernels start the next input copy INTO it)
 //   OUT_REGS   (C2R / C2C_BWD): do not store; hand the result registers (element j + m T in vout[m]) to the caller
 //   FMT = 1    (ordered layouts): the conventions of the reference's JUCE adapter (chowdsp_fft_juce/chowdsp_fft_juce.cpp:
 //              32-86) instead of pffft's -- real spectra as N/2 + 1 interleaved complex bins (Nyquist at float 2M, the
 //              imaginary parts of DC and Nyquist zero) rather than Nyquist packed into float 1, and inverse transforms
 //              (C2R, C2C_BWD) scaled by 1/N
-template <int LOGM, int R, int KIND, int LOGW, bool IN_STAGED, bool OUT_STAGED, bool HALF_OUT, int IN_UNION = 0, class Hook = NoHook, bool OUT_REGS = false, int FMT = 0>
+template <int LOGM, int R, int KIND, int LOGW, bool IN_STAGED, bool OUT_STAGED, bool HALF_OUT, int IN_UNION = 0, class Hook = NoHook, bool OUT_REGS = false, int FMT = 0, class Hook2 = NoHook>
 FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, bool active, int j, float2* s, const float2* __restrict__ tw_, const float2* __restrict__ rtw_,
-                      const float2* su = nullptr, const float2* __restrict__ win = nullptr, const Hook& input_consumed = Hook(), float2* vout = nullptr)
+                      const float2* su = nullptr, const float2* __restrict__ win = nullptr, const Hook& input_consumed = Hook(), float2* vout = nullptr,
+                      const Hook2& last_gathered = Hook2())
 {
     using G = Geo<LOGM, R>;
     constexpr int DIR = (KIND == C2C_FWD || KIND == R2C) ? -1 : +1;
@@ -852,6 +876,10 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
     const int u_odd = j & 1;
     const int u_base = (((j & ~1) >> (UNORD ? LOGW : 2)) * 2 * UW * UW) + ((j & ~1) & (UW - 1)) + (u_odd ? UW : 0); // float offset of this thread's pair
     constexpr int SW = T < 32 ? T : 32; // shuffle width: transforms never straddle a warp
+    // Unordered REAL spectra without the staging image (A/B switch CFB_UNORD_REAL_DIRECT): 4-byte accesses straight to the
+    // unordered positions; a warp's access still covers whole 32-byte sectors (runs of W lanes)
+    constexpr bool RDIRECT = CFB_UNORD_REAL_DIRECT != 0 && UNORD && ((KIND == R2C && ! OUT_STAGED) || (KIND == C2R && ! IN_STAGED));
+    const UPos<G, UNORD ? LOGW : 2, false> upg (j);
     // real split / merge: transforms owned by (part of) one warp exchange the mirror half of the spectrum by shuffle
     // (measured, profiles/r01_shfl_mirror.txt: +3..14 % for 16 points per thread and in the warp-pipelined kernels; with
     // 32 points per thread in fft_kernel the 32 extra shuffles + selects cost 2..5 %, so that geometry keeps shared memory)
@@ -927,7 +955,17 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
         // This thread owns the pairs (k, M-k), k = j + m T < M/2 (thread 0's first pair is (0, M/2)).
         // Z'[k] is its own stage-0 register m; Z'[M-k] belongs to thread T-j and travels through smem.
         float2 xb[R / 2];
-        if constexpr (UNORD)
+        if constexpr (RDIRECT)
+        {
+#pragma unroll
+            for (int m = 0; m < R / 2; ++m)
+            {
+                const int plo = upg.real_lo (m), phi = (m == 0 && j == 0) ? W_HALF_ROW<LOGW>() : upg.real_hi (m);
+                v[m] = make_float2 (__ldg (in + plo), __ldg (in + plo + WL));
+                xb[m] = make_float2 (__ldg (in + phi), __ldg (in + phi + WL));
+            }
+        }
+        else if constexpr (UNORD)
         {
             if constexpr (! IN_STAGED)
             {
@@ -1014,7 +1052,7 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
                     v[R - m] = xb[m];
                 v[R / 2] = xb[0];
             }
-            if constexpr (UNORD)
+            if constexpr (UNORD && ! RDIRECT)
                 smem_was_read = true; // the staging image was read: a barrier must precede the first exchange
         }
         else
@@ -1027,7 +1065,7 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
     }
 
     // ---- the stages -----------------------------------------------------------------------------
-    Stages<G, DIR, 0, WS, IN_UNION == 1>::run (v, j, s, a.tw, smem_was_read, input_consumed);
+    Stages<G, DIR, 0, WS, IN_UNION == 1>::run (v, j, s, a.tw, smem_was_read, input_consumed, last_gathered);
     if (G::S > 1)
         smem_was_read = true;
 
@@ -1093,7 +1131,7 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
                     zb[m] = v[R - m];
                 zb[0] = v[R / 2];
             }
-            if constexpr (UNORD)
+            if constexpr (UNORD && ! RDIRECT)
                 if (smem_was_read)
                     tsync<T, WS && ! (IN_UNION == 1 && G::S == 1)>(); // the last exchange has been read: the staging image may overwrite it
         }
@@ -1106,7 +1144,7 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
 #pragma unroll
             for (int m = 0; m < R / 2; ++m)
                 zb[m] = lds2 (s + ((m == 0 && j == 0) ? G::pad (M / 2) : mirror_slot<G> (j, m)));
-            if constexpr (UNORD)
+            if constexpr (UNORD && ! RDIRECT)
                 tsync<T, WS>(); // natural-order image fully consumed before the staging image overwrites it
         }
         const float2 wj = __ldg (a.rtw + j);
@@ -1128,7 +1166,18 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
                 xa = make_float2 (za.x + za.y, za.x - za.y); // (DC, Nyquist)
                 xm = make_float2 (zm.x, -zm.y);              // X[M/2] = conj Z[M/2]
             }
-            if constexpr (UNORD)
+            if constexpr (RDIRECT)
+            {
+                if (active)
+                {
+                    const int plo = upg.real_lo (m), phi = special ? W_HALF_ROW<LOGW>() : upg.real_hi (m);
+                    out[plo] = xa.x;
+                    out[plo + WL] = xa.y;
+                    out[phi] = xm.x;
+                    out[phi + WL] = xm.y;
+                }
+            }
+            else if constexpr (UNORD)
             {
                 staged_store (sf, up.real_lo (m), WL, xa);
                 staged_store (sf, special ? W_HALF_ROW<LOGW>() : up.real_hi (m), WL, xm);
@@ -1145,7 +1194,7 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
                 *ph = xm;
             }
         }
-        if constexpr (UNORD)
+        if constexpr (UNORD && ! RDIRECT)
         {
             tsync<T, WS>();
             if constexpr (! OUT_STAGED)

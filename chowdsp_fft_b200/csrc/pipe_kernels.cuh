@@ -234,6 +234,9 @@ __global__ void __launch_bounds__ (Launch<LOGM, R>::THREADS, Launch<LOGM, R>::MI
 // Shared memory: per warp [landing 8 M bytes][exchange buffer][mbarrier, next-transform slot: 16 bytes]; then the CTA's
 // work counter (16 bytes).
 // ---------------------------------------------------------------------------------------------
+#ifndef CFB_WPIPE_ALIAS
+#define CFB_WPIPE_ALIAS 1 // A/B switch (tools/ only)
+#endif
 template <int LOGM, int R, int LOGW>
 struct WPipeGeo
 {
@@ -241,7 +244,14 @@ struct WPipeGeo
     static_assert (G::T == 32, "wpipe_kernel: one warp per transform");
     static constexpr int IN_BYTES = 2 * G::M * 4;
     static constexpr int SMEM_F2 = LOGW != 0 ? G::SMEM_F2_UNORD : G::SMEM_F2;
-    static constexpr int WARP_BYTES = IN_BYTES + SMEM_F2 * 8 + 16;
+    // ALIAS: the landing buffer doubles as the exchange buffer -- the next input copy starts only after the gather of the
+    // last exchange instead of right after the stage-0 reads (a shorter prefetch window), but a warp needs half the shared
+    // memory, so 16 warps (4 per scheduler) are resident instead of 13.  Ordered layouts only (their epilogues do not
+    // stage anything in shared memory).
+    static constexpr bool ALIAS = CFB_WPIPE_ALIAS != 0 && LOGW == 0;
+    static constexpr int XCH_OFFSET = ALIAS ? 0 : IN_BYTES;
+    static constexpr int BAR_OFFSET = XCH_OFFSET + (SMEM_F2 * 8 > IN_BYTES || ! ALIAS ? SMEM_F2 * 8 : IN_BYTES);
+    static constexpr int WARP_BYTES = BAR_OFFSET + 16;
     static constexpr int CTA_EXTRA_BYTES = 16; // the work counter
     static constexpr int MAX_WARPS = (227 * 1024 - CTA_EXTRA_BYTES) / WARP_BYTES < 16 ? (227 * 1024 - CTA_EXTRA_BYTES) / WARP_BYTES : 16;
     static constexpr int smem_bytes (int warps) { return warps * WARP_BYTES + CTA_EXTRA_BYTES; }
@@ -269,10 +279,11 @@ FFT_HD void wpipe_body (const FftArgs& a)
     const int wpc = (int) blockDim.x >> 5;
     char* wbase = smem + (size_t) warp * WP::WARP_BYTES;
     float2* land = reinterpret_cast<float2*> (wbase);
-    float2* xch = reinterpret_cast<float2*> (wbase + WP::IN_BYTES);
-    unsigned long long* bar = reinterpret_cast<unsigned long long*> (wbase + WP::IN_BYTES + WP::SMEM_F2 * 8);
+    float2* xch = reinterpret_cast<float2*> (wbase + WP::XCH_OFFSET);
+    unsigned long long* bar = reinterpret_cast<unsigned long long*> (wbase + WP::BAR_OFFSET);
     volatile unsigned* wnext = reinterpret_cast<volatile unsigned*> (bar + 1); // the warp's next transform, written by lane 0
     unsigned* counter = reinterpret_cast<unsigned*> (smem + (size_t) wpc * WP::WARP_BYTES);
+    constexpr bool ALIAS = WP::ALIAS;
 
     // The CTA owns the contiguous range [first, first + count) of the batch (neighbouring frames of an STFT are then
     // fetched close together in time: their overlap is an L2 hit); inside the CTA the warps take transforms one at a
@@ -319,7 +330,7 @@ FFT_HD void wpipe_body (const FftArgs& a)
         mbar_wait (bar, it, (unsigned) WP::IN_BYTES);
         // runs after the warp-level barrier that follows the stage-0 reads: the landing buffer is free again, and every
         // lane has read *wnext for this trip
-        const auto input_consumed = [&]
+        const auto next_fetch = [&]
         {
             if (lane == 0)
             {
@@ -329,9 +340,16 @@ FFT_HD void wpipe_body (const FftArgs& a)
                     fetch (i);
             }
         };
-        fft_core<LOGM, R, KIND, LOGW, false, false, false, 2> (nullptr, out, true, lane, xch, a.tw, a.rtw, land,
-                                                               reinterpret_cast<const float2*> (a.window), input_consumed);
-        cur = *wnext; // at least one warp-level barrier (the stage-0 exchange) lies between lane 0's write and this read
+        if constexpr (ALIAS)
+        {
+            fft_core<LOGM, R, KIND, LOGW, false, false, false, 2, NoHook, false, 0, decltype (next_fetch)> (nullptr, out, true, lane, xch, a.tw, a.rtw, land,
+                                                                                                      reinterpret_cast<const float2*> (a.window), NoHook(), nullptr, next_fetch);
+            tsync<32, true>(); // lane 0's *wnext is visible to the warp
+        }
+        else
+            fft_core<LOGM, R, KIND, LOGW, false, false, false, 2> (nullptr, out, true, lane, xch, a.tw, a.rtw, land,
+                                                                   reinterpret_cast<const float2*> (a.window), next_fetch);
+        cur = *wnext; // a warp-level barrier lies between lane 0's write and this read
     }
 }
 
@@ -368,8 +386,8 @@ FFT_HD void wistft_body (const FftArgs& a)
     const int wpc = (int) blockDim.x >> 5;
     char* wbase = smem + (size_t) warp * WP::WARP_BYTES;
     float2* land = reinterpret_cast<float2*> (wbase);
-    float2* xch = reinterpret_cast<float2*> (wbase + WP::IN_BYTES);
-    unsigned long long* bar = reinterpret_cast<unsigned long long*> (wbase + WP::IN_BYTES + WP::SMEM_F2 * 8);
+    float2* xch = reinterpret_cast<float2*> (wbase + WP::XCH_OFFSET);
+    unsigned long long* bar = reinterpret_cast<unsigned long long*> (wbase + WP::BAR_OFFSET);
     volatile unsigned* wnext = reinterpret_cast<volatile unsigned*> (bar + 1);
     unsigned* counter = reinterpret_cast<unsigned*> (smem + (size_t) wpc * WP::WARP_BYTES);
 
@@ -442,7 +460,14 @@ FFT_HD void wistft_body (const FftArgs& a)
             }
         };
         float2 v[R];
-        fft_core<LOGM, R, C2R, 0, false, false, false, 2, decltype (input_consumed), true> (nullptr, nullptr, true, lane, xch, a.tw, a.rtw, land, nullptr, input_consumed, v);
+        if constexpr (WP::ALIAS)
+        {
+            fft_core<LOGM, R, C2R, 0, false, false, false, 2, NoHook, true, 0, decltype (input_consumed)> (nullptr, nullptr, true, lane, xch, a.tw, a.rtw, land, nullptr, NoHook(), v,
+                                                                                                     input_consumed);
+            tsync<32, true>(); // lane 0's *wnext is visible to the warp
+        }
+        else
+            fft_core<LOGM, R, C2R, 0, false, false, false, 2, decltype (input_consumed), true> (nullptr, nullptr, true, lane, xch, a.tw, a.rtw, land, nullptr, input_consumed, v);
 #pragma unroll
         for (int m = 0; m < R; ++m)
         {
@@ -489,7 +514,7 @@ struct WIstftGeo
     // 64 result + up to 56 accumulator registers per thread on top of the transform's temporaries: 10 resident warps
     // (168 registers per thread; 12 warps measured 9 % slower: 28 KB of L1 left for window + twiddles) for 32 points per
     // thread, 16 (128) for 16
-    static constexpr int MAX_WARPS = R == 32 ? 10 : 16;
+    static constexpr int MAX_WARPS = R == 32 ? (WPipeGeo<LOGM, R, 0>::ALIAS ? 12 : 10) : 16;
 };
 template <int LOGM, int R, int HQ>
 __global__ void __launch_bounds__ (WIstftGeo<LOGM, R>::MAX_WARPS * 32, 1) wistft_kernel (const FftArgs a)

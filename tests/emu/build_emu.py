@@ -5,16 +5,18 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.abspath(os.path.join(HERE, "..", "..", "chowdsp_fft_b200", "csrc"))
-SO = os.path.join(HERE, "libfft_emu.so")
+# CFB_EMU_DEFINES="-DX=1 -DY=0": build (and load) a variant of the kernel source with A/B switches set
+DEFINES = os.environ.get("CFB_EMU_DEFINES", "").split()
+SO = os.path.join(HERE, "libfft_emu.so" if not DEFINES else "libfft_emu_ab.so")
 
 
 def build(force: bool = False) -> str:
     srcs = [os.path.join(HERE, "emu_driver.cpp"), os.path.join(HERE, "cuda_emu.h"),
             os.path.join(CSRC, "fft_kernels.cuh"), os.path.join(CSRC, "elementwise_kernels.cuh"),
             os.path.join(CSRC, "pconv_kernel.cuh"), os.path.join(CSRC, "pipe_kernels.cuh"), os.path.join(CSRC, "mixed_kernels.cuh"), os.path.join(CSRC, "large_kernels.cuh"), os.path.join(CSRC, "large_plan.h")]
-    if not force and os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(s) for s in srcs):
+    if not force and not DEFINES and os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(s) for s in srcs):
         return SO
-    cmd = ["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", f"-I{HERE}", f"-I{CSRC}", srcs[0], "-o", SO]
+    cmd = ["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", *DEFINES, f"-I{HERE}", f"-I{CSRC}", srcs[0], "-o", SO]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("emu build failed:\n" + r.stderr[-4000:])

@@ -17,6 +17,7 @@
 #include <map>
 #include <memory>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 struct float2 { float x, y; };
