@@ -132,11 +132,16 @@ int fft_accumulate_batched (void* setup, const float* a, const float* b, float* 
 const char* fft_b200_last_error (void);
 void fft_b200_clear_error (void);
 
-/* Tuning hook for benchmarks/sweeps (not needed in normal use): key "tile_c" = transforms per tile of the
-   multi-pass kernels (8, 16, or 0 for the built-in policy); "radix32_mask" bit n (complex plans) / bit 16+n (real plans) = use the 32-points-per-thread kernel for
-   complex length 2^n (n in 9, 10, 13, 14), -1 = built-in default;
-   "stft_union" = 1 stages the union of a CTA's
-   overlapping frames through shared memory (fewer L2 reads, more shared-memory traffic). */
+/* Tuning hook for benchmarks / A-B sweeps (not needed in normal use; value -1 restores a key's built-in default where one exists):
+     "radix32_mask" bit n (complex plans) / bit 16+n (real plans): 32 points per thread for complex length 2^n (n in 9, 10, 13, 14)
+     "pipe_mask"    which kinds / layouts at complex length 2^13, 2^14 use the persistent TMA-pipelined kernel
+     "wpipe"        bit 1: overlapping / windowed frames of the sizes one warp owns use the warp-pipelined kernel (default), bit 0: every
+                    batch of those sizes; bits 8..: warps per CTA (0 = as many as fit)
+     "wistft"       bit 0: overlap-add synthesis through the warp-pipelined kernel where it applies (default); bits 8..: warps per CTA
+     "stft_pipe", "stft_union"  older frame-gather variants (persistent CTA-level TMA union / LDS-STS union staging), off
+     "tile_c", "tile_c_jfast"   transforms per tile of the multi-pass kernels (8, 16, or 0 = built-in policy)
+     "tile_pipe"    1 = persistent TMA-staged tile kernel for the multi-pass transforms (measured slower; default 0)
+     "pf_ahead"     L2 prefetch distance of the single-kernel transforms in CTAs (default 0 = off) */
 int fft_b200_set_tuning (const char* key, int value);
 
 /* Number of CUDA kernels this library has launched in this process (all threads). */
