@@ -1452,6 +1452,11 @@ CFB_API int fft_accumulate_batched (void* setup, const float* a, const float* b,
 
 CFB_API int fft_b200_set_tuning (const char* key, int value)
 {
+    if (key != nullptr && std::strcmp (key, "tile_pf") == 0 && value >= -1)
+    {
+        tile_pf_ahead() = value == -1 ? 0 : value;
+        return 0;
+    }
     if (key != nullptr && std::strcmp (key, "tile_pipe") == 0 && (value == 0 || value == 1 || value == -1))
     {
         tile_pipe_mode() = value == -1 ? 1 : value;

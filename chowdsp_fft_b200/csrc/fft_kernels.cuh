@@ -158,6 +158,15 @@ FFT_HD void fence_proxy_async()
 #endif
 }
 
+FFT_HD void prefetch_l2 (const void* p)
+{
+#ifndef CHOWDSP_EMU
+    asm volatile ("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void) p;
+#endif
+}
+
 FFT_HD float2 lds2 (const float2* p)
 {
 #ifdef CHOWDSP_EMU

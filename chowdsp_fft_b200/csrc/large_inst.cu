@@ -93,8 +93,10 @@ cudaError_t launch_tile_l (int C, int dir, bool jfast, const TileArgs& a, cudaSt
 }
 } // namespace
 
-cudaError_t launch_tile (int logL, int C, int dir, bool load_j_fast, const TileArgs& a, cudaStream_t stream)
+cudaError_t launch_tile (int logL, int C, int dir, bool load_j_fast, const TileArgs& args, cudaStream_t stream)
 {
+    TileArgs a = args;
+    a.pf_ahead = tile_pf_ahead();
     switch (logL)
     {
         case 6: return launch_tile_l<6> (C, dir, load_j_fast, a, stream);

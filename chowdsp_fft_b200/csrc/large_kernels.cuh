@@ -62,6 +62,9 @@ struct TileArgs
     int peer_row_log;
     long long peer_chunk_off;
     float2* peer_out[8];
+    // L2 prefetch distance in tiles (0 = off): CTA b asks L2 for the input rows of tile b + pf_ahead, about one wave of
+    // resident CTAs ahead, so that the strided (DRAM-page-missing) gather of a later CTA finds its lines in L2
+    int pf_ahead;
 };
 
 template <int DIR>
@@ -136,6 +139,31 @@ FFT_HD void tile_body (const TileArgs& a)
 
     const int ltB = tid % C, jB = tid / C; // adjacent threads = adjacent transforms
     const int ltA = tid / T, jA = tid % T; // adjacent threads = adjacent elements
+    if (a.pf_ahead > 0)
+    {
+        const long long tn = (long long) blockIdx.x + a.pf_ahead;
+        if (tn < (long long) a.ntiles * a.batch)
+        {
+            const int bn = (int) (tn / a.ntiles);
+            const int gn = (int) (tn - (long long) bn * a.ntiles);
+            const int ghn = gn / a.gdiv, gln = gn - ghn * a.gdiv;
+            const float2* pn = a.in + bn * a.in_bstride + ghn * a.in_g_hi + gln * a.in_g_lo;
+            if constexpr (LOAD_J_FAST)
+            {
+                // C contiguous rows of L values = L / 16 lines each: line (tid % (L/16)) of row (tid / (L/16))
+                constexpr int LPR = G::M / 16;
+                for (int i = tid; i < C * LPR; i += T * C)
+                    prefetch_l2 (pn + (long long) (i / LPR) * a.in_tstride + (long long) (i % LPR) * 16);
+            }
+            else
+            {
+                const int mask = a.in_split_log >= 31 ? -1 : (1 << a.in_split_log) - 1;
+                for (int idx = tid; idx < G::M; idx += T * C) // one (C * 8)-byte piece per element row
+                    prefetch_l2 (pn + (a.in_split_log >= 31 ? (long long) idx * a.in_estride
+                                                              : (long long) (idx >> a.in_split_log) * a.in_chunk_stride + (long long) (idx & mask) * a.in_estride));
+            }
+        }
+    }
     float2 v[R];
     float2* sB = smem + ltB * RS;
     float2* sTw = smem + C * RS;           // A[m][lt] = W_N^(mu m T c(lt)), see the twiddle step below

@@ -14,6 +14,8 @@ inline int& tile_c_jfast_override() { static int v = 0; return v; } // ... for t
 // tuning hook "tile_pipe": 1 = the persistent TMA-staged tile kernel (tile_pipe_kernel) where its buffers fit and the rows are
 // 16-byte aligned, 0 = tile_fft_kernel everywhere
 inline int& tile_pipe_mode() { static int v = 0; return v; }
+// tuning hook "tile_pf": L2 prefetch distance of the tile passes in tiles (0 = off)
+inline int& tile_pf_ahead() { static int v = 0; return v; }
 inline int tile_c (int logL, bool jfast = false)
 {
     const int ov = (jfast && tile_c_jfast_override() != 0) ? tile_c_jfast_override() : tile_c_override();
