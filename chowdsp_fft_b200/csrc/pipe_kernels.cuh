@@ -819,6 +819,21 @@ FFT_HD void pipe_body (const FftArgs& a)
             for (int m = 0; m < R; ++m)
                 out2[m * T] = v[m];
         }
+        else if constexpr (KIND == C2C_FWD && CFB_UNORD_DIRECT != 0)
+        {
+            // unordered complex output straight from registers (as fft_core's UDIRECT path): threads j, j+1 swap one float, the
+            // even one stores (re_j, re_j+1), the odd one (im_j, im_j+1) -- contiguous 8-byte pairs of the unordered layout
+            constexpr int UW = 8, ULT = R / UW;
+            const int u_odd = j & 1;
+            float* __restrict__ ob = out + (((j & ~1) >> 3) * 2 * UW * UW) + ((j & ~1) & (UW - 1)) + (u_odd ? UW : 0);
+#pragma unroll
+            for (int m = 0; m < R; ++m)
+            {
+                const float recv = shfl1 (u_odd ? v[m].x : v[m].y, (j ^ 1) & 31, 32);
+                const float2 o = u_odd ? make_float2 (recv, v[m].y) : make_float2 (v[m].x, recv);
+                *reinterpret_cast<float2*> (ob + (m % ULT) * (T / UW) * 2 * UW * UW + (m / ULT) * 2 * UW) = o;
+            }
+        }
         else if constexpr (KIND == C2C_FWD)
         {
             // unordered output, staged and drained in two halves of the (padded) image: bin j + m T lies in half
