@@ -5,7 +5,7 @@
 // :1535-1629) and exercises 96, 192, 384, 480, 640, 768 and 9216 in its tests (test/test.cpp:279-285).  They are
 // outside the power-of-two north star, so this is ONE generic kernel, written for coverage of the drop-in API
 // rather than for the roofline: a CTA owns one transform of M complex points (M = N, or N/2 for real plans) in
-// shared memory and runs Stockham autosort passes of radix 4, 2, 3 and 5 between two buffers; the twiddles of
+// shared memory and runs Stockham autosort passes of radix 16, 4, 2, 3 and 5 between two buffers; the twiddles of
 // every pass come from a single table W_M^t (fp64 -> fp32).  Backward transforms use
 // IFFT (x) = conj (FFT (conj x)), so only forward butterflies exist.  Real transforms are the M-point complex
 // transform of the packed pairs plus the same split / merge step as fft_kernel; ordered (pffft packing) and
@@ -18,7 +18,7 @@ namespace cfb
 {
 constexpr int kMixedMaxStages = 16;
 constexpr int kMixedMaxM = 12288;
-constexpr int kMixedMaxThreads = 1024;
+constexpr int kMixedMaxThreads = 512; // 128 registers per thread: the radix-16 pass keeps 16 points + temporaries in registers
 
 struct MixedArgs
 {
@@ -28,7 +28,7 @@ struct MixedArgs
     int batch;
     int M;                           // complex points per transform
     int nstages;
-    int radix[kMixedMaxStages];      // product = M; each 2, 3, 4 or 5
+    int radix[kMixedMaxStages];      // product = M; each 16, 4, 2, 3 or 5
     const float2* wtab;              // W_M^t = exp (-2 pi i t / M), t < M
     const float2* rtab;              // real plans: exp (-2 pi i k / (2 M)), k <= M/2
     int kind;                        // Kind
@@ -36,12 +36,12 @@ struct MixedArgs
     int tg;                          // threads per transform (power of two <= blockDim.x): a CTA runs blockDim.x / tg transforms
 };
 
-// launch geometry: about one thread per radix-4 butterfly, at least a warp and at most 1024 threads per transform;
-// small transforms share a CTA of 256 threads
+// launch geometry: about one thread per radix-16 butterfly (the radix-4 / 3 / 5 passes loop), at least a warp and at most
+// 1024 threads per transform; small transforms share a CTA of 256 threads
 inline void mixed_geometry (int M, int& threads, int& tg)
 {
     tg = 32;
-    while (tg < kMixedMaxThreads && tg * 4 < M)
+    while (tg < kMixedMaxThreads && tg * 16 < M)
         tg *= 2;
     threads = tg < 256 ? 256 : tg;
 }
@@ -110,26 +110,68 @@ FFT_HD void mx_dft5 (float2* u)
     u[3] = csub (p2, q2);
 }
 
-// one Stockham pass of radix RDX: src in natural order of the pass input, dst in autosort order
-template <int RDX>
-FFT_HD void mixed_pass (const float2* src, float2* dst, int M, int Ns, const float2* __restrict__ wtab, int tid, int nthreads)
+// forward DFT of length 16 = 4 x 4 in registers: DFT4 over n1 for every n2 (n = 4 n1 + n2), times W16^(n2 k1), DFT4 over n2;
+// output index k = k1 + 4 k2
+FFT_HD void mx_dft16 (float2* u)
+{
+    constexpr float c1 = 0.923879532511286756f, s1 = 0.382683432365089772f, h = 0.707106781186547524f;
+    float2 t[16];
+#pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2)
+    {
+        float2 c[4] = { u[n2], u[4 + n2], u[8 + n2], u[12 + n2] };
+        mx_dft4 (c);
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1)
+            t[4 * k1 + n2] = c[k1];
+    }
+    // W16^(n2 k1), e = n2 k1 in {1, 2, 3, 4, 6, 9}
+    t[4 * 1 + 1] = mx_mul (t[4 * 1 + 1], make_float2 (c1, -s1));
+    t[4 * 1 + 2] = mx_mul (t[4 * 1 + 2], make_float2 (h, -h));
+    t[4 * 1 + 3] = mx_mul (t[4 * 1 + 3], make_float2 (s1, -c1));
+    t[4 * 2 + 1] = mx_mul (t[4 * 2 + 1], make_float2 (h, -h));
+    t[4 * 2 + 2] = mx_mi (t[4 * 2 + 2]);
+    t[4 * 2 + 3] = mx_mul (t[4 * 2 + 3], make_float2 (-h, -h));
+    t[4 * 3 + 1] = mx_mul (t[4 * 3 + 1], make_float2 (s1, -c1));
+    t[4 * 3 + 2] = mx_mul (t[4 * 3 + 2], make_float2 (-h, -h));
+    t[4 * 3 + 3] = mx_mul (t[4 * 3 + 3], make_float2 (-c1, s1));
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1)
+    {
+        float2 c[4] = { t[4 * k1], t[4 * k1 + 1], t[4 * k1 + 2], t[4 * k1 + 3] };
+        mx_dft4 (c);
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2)
+            u[k1 + 4 * k2] = c[k2];
+    }
+}
+
+// one Stockham pass of radix RDX: src in natural order of the pass input, dst in autosort order.
+//   SRC = 1: src is the transform's input in global memory (first pass of the forward kinds: no staging copy)
+//   DST = 1 / 2: dst is the transform's output in global memory, stored as is / conjugated (last pass of the kinds whose
+//            output is in natural order); `active` = false skips those stores
+template <int RDX, int SRC = 0, int DST = 0>
+FFT_HD void mixed_pass (const float2* src, float2* dst, int M, int Ns, const float2* __restrict__ wtab, int tid, int nthreads, bool active = true)
 {
     const int cols = M / RDX;
     const int tstep = M / (Ns * RDX); // W_(Ns RDX)^(k q) = W_M^(k q tstep)
+    const bool ns_pow2 = (Ns & (Ns - 1)) == 0; // true for every power-of-two pass and the first odd-radix one
     for (int j = tid; j < cols; j += nthreads)
     {
-        const int k = j % Ns;
+        const int k = ns_pow2 ? (j & (Ns - 1)) : j % Ns;
         float2 u[RDX];
 #pragma unroll
         for (int q = 0; q < RDX; ++q)
-            u[q] = lds2 (src + j + q * cols);
+            u[q] = SRC == 1 ? ldg_stream (src + j + q * cols) : lds2 (src + j + q * cols);
         if (Ns > 1)
         {
 #pragma unroll
             for (int q = 1; q < RDX; ++q)
-                u[q] = mx_mul (u[q], __ldg (wtab + (int) (((long long) k * q * tstep) % M)));
+                u[q] = mx_mul (u[q], __ldg (wtab + k * q * tstep)); // k q tstep < Ns RDX tstep = M
         }
-        if (RDX == 2)
+        if (RDX == 16)
+            mx_dft16 (u);
+        else if (RDX == 2)
             mx_dft2 (u);
         else if (RDX == 3)
             mx_dft3 (u);
@@ -138,10 +180,33 @@ FFT_HD void mixed_pass (const float2* src, float2* dst, int M, int Ns, const flo
         else
             mx_dft5 (u);
         const int base = (j - k) * RDX + k;
+        if (DST == 0)
+        {
 #pragma unroll
-        for (int q = 0; q < RDX; ++q)
-            sts2 (dst + base + q * Ns, u[q]);
+            for (int q = 0; q < RDX; ++q)
+                sts2 (dst + base + q * Ns, u[q]);
+        }
+        else if (active)
+        {
+#pragma unroll
+            for (int q = 0; q < RDX; ++q)
+                dst[base + q * Ns] = DST == 2 ? mx_conj (u[q]) : u[q];
+        }
     }
+}
+template <int SRC, int DST>
+FFT_HD void mixed_pass_r (int r, const float2* src, float2* dst, int M, int Ns, const float2* __restrict__ wtab, int tid, int nthreads, bool active = true)
+{
+    if (r == 16)
+        mixed_pass<16, SRC, DST> (src, dst, M, Ns, wtab, tid, nthreads, active);
+    else if (r == 4)
+        mixed_pass<4, SRC, DST> (src, dst, M, Ns, wtab, tid, nthreads, active);
+    else if (r == 2)
+        mixed_pass<2, SRC, DST> (src, dst, M, Ns, wtab, tid, nthreads, active);
+    else if (r == 3)
+        mixed_pass<3, SRC, DST> (src, dst, M, Ns, wtab, tid, nthreads, active);
+    else
+        mixed_pass<5, SRC, DST> (src, dst, M, Ns, wtab, tid, nthreads, active);
 }
 
 FFT_HD void mixed_body (const MixedArgs& a)
@@ -160,8 +225,15 @@ FFT_HD void mixed_body (const MixedArgs& a)
         const long long x = active ? x0 + grp : a.batch - 1;
         const float* __restrict__ in = a.in + x * a.in_stride;
         float* __restrict__ out = a.out + x * a.out_stride;
+        // the first pass of the forward kinds reads global memory itself; the last pass of the kinds whose output is in
+        // natural order (ordered complex spectra, time-domain signals) writes it itself (two or more passes)
+        const bool src_global = (a.kind == C2C_FWD || a.kind == R2C) && a.nstages >= 2;
+        const int dst_global = a.nstages < 2 ? 0 : (a.kind == C2C_FWD && W == 0) ? 1 : backward ? 2 : 0;
         // ---- load: A[n] = stage-0 input (conjugated for the backward kinds) ----
-        if (a.kind == C2C_FWD || a.kind == R2C)
+        if (src_global)
+        {
+        }
+        else if (a.kind == C2C_FWD || a.kind == R2C)
         {
             for (int n = tid; n < M; n += nthreads)
                 A[n] = reinterpret_cast<const float2*> (in)[n];
@@ -215,7 +287,8 @@ FFT_HD void mixed_body (const MixedArgs& a)
                 A[k] = mx_conj (z);
             }
         }
-        __syncthreads();
+        if (! src_global)
+            __syncthreads();
         // ---- Stockham passes ----
         float2* src = A;
         float2* dst = B;
@@ -223,14 +296,14 @@ FFT_HD void mixed_body (const MixedArgs& a)
         for (int s = 0; s < a.nstages; ++s)
         {
             const int r = a.radix[s];
-            if (r == 4)
-                mixed_pass<4> (src, dst, M, Ns, a.wtab, tid, nthreads);
-            else if (r == 2)
-                mixed_pass<2> (src, dst, M, Ns, a.wtab, tid, nthreads);
-            else if (r == 3)
-                mixed_pass<3> (src, dst, M, Ns, a.wtab, tid, nthreads);
+            if (s == 0 && src_global)
+                mixed_pass_r<1, 0> (r, reinterpret_cast<const float2*> (in), dst, M, Ns, a.wtab, tid, nthreads);
+            else if (s == a.nstages - 1 && dst_global == 1)
+                mixed_pass_r<0, 1> (r, src, reinterpret_cast<float2*> (out), M, Ns, a.wtab, tid, nthreads, active);
+            else if (s == a.nstages - 1 && dst_global == 2)
+                mixed_pass_r<0, 2> (r, src, reinterpret_cast<float2*> (out), M, Ns, a.wtab, tid, nthreads, active);
             else
-                mixed_pass<5> (src, dst, M, Ns, a.wtab, tid, nthreads);
+                mixed_pass_r<0, 0> (r, src, dst, M, Ns, a.wtab, tid, nthreads);
             Ns *= r;
             __syncthreads();
             float2* t = src;
@@ -238,7 +311,7 @@ FFT_HD void mixed_body (const MixedArgs& a)
             dst = t;
         }
         // ---- store (src holds the spectrum in natural order) ----
-        if (! active)
+        if (! active || dst_global != 0)
         {
         }
         else if (a.kind == C2C_FWD)
@@ -309,7 +382,7 @@ FFT_HD void mixed_body (const MixedArgs& a)
 
 // (a template only so that the kernel can live in this header, which several translation units include)
 template <int UNUSED = 0>
-__global__ void __launch_bounds__ (kMixedMaxThreads) mixed_kernel (const MixedArgs a)
+__global__ void __launch_bounds__ (kMixedMaxThreads, 2) mixed_kernel (const MixedArgs a)
 {
     mixed_body (a);
 }
@@ -321,6 +394,14 @@ __global__ void __launch_bounds__ (kMixedMaxThreads) mixed_kernel (const MixedAr
 inline int mixed_factor (int M, int* radix)
 {
     int n = 0;
+    // two radix-4 steps in registers: half the shared-memory round trips (not for tiny transforms, whose radix-16 pass would
+    // keep a handful of threads busy)
+    const bool use16 = M >= 256;
+    while (use16 && M % 16 == 0 && n < kMixedMaxStages)
+    {
+        radix[n++] = 16;
+        M /= 16;
+    }
     while (M % 4 == 0 && n < kMixedMaxStages)
     {
         radix[n++] = 4;
