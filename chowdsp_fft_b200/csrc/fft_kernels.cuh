@@ -216,7 +216,7 @@ FFT_HD float shfl1 (float v, int src, int width)
 #define CFB_UNORD_REAL_DIRECT 0
 #endif
 #ifndef CFB_SHFL_MIRROR
-#define CFB_SHFL_MIRROR 1 // A/B switch (tools/ only): 0 = the real split / merge step always exchanges through shared memory
+#define CFB_SHFL_MIRROR 1 // A/B switch (tools/ only): 0 = the real split / merge step of fft_kernel exchanges through shared memory
 #endif
 
 // ---------------------------------------------------------------------------------------------
@@ -892,7 +892,7 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
     // real split / merge: transforms owned by (part of) one warp exchange the mirror half of the spectrum by shuffle
     // (measured, profiles/r01_shfl_mirror.txt: +3..14 % for 16 points per thread and in the warp-pipelined kernels; with
     // 32 points per thread in fft_kernel the 32 extra shuffles + selects cost 2..5 %, so that geometry keeps shared memory)
-    constexpr bool SHFL_MIRROR = CFB_SHFL_MIRROR != 0 && T <= 32 && (KIND == R2C || KIND == C2R) && (R == 16 || IN_UNION == 2);
+    constexpr bool SHFL_MIRROR = T <= 32 && (KIND == R2C || KIND == C2R) && ((CFB_SHFL_MIRROR != 0 && R == 16) || IN_UNION == 2);
     float* sf = reinterpret_cast<float*> (s); // the same buffer seen as the unordered staging image
     constexpr int logW = LOGW;
     struct { const float2* tw; const float2* rtw; } a { tw_, rtw_ };

@@ -434,3 +434,21 @@ def test_emulated_juce_conventions(emu, oracle_mod, logM, radix):
     y = np.zeros_like(x)
     assert emu.emu_fft_juce(logM, radix, 1, x.ctypes.data_as(fp), y.ctypes.data_as(fp), batch, 2 * Nc, 2 * Nc) == 0
     assert o.rel_l2(y, o.np_juce_perform(x, Nc, True)) < 4e-7
+
+
+def test_ab_switches_still_compile_and_agree():
+    """The A/B switches kept in the kernel source (CFB_WPIPE_ALIAS, CFB_UNORD_DIRECT, CFB_SHFL_MIRROR, CFB_UNORD_REAL_DIRECT)
+    select the alternative code paths measured in profiles/; build the emulator with every switch flipped (a second .so,
+    tests/emu/build_emu.py) and rerun the transform, warp-pipelined and pipelined-kernel checks against the oracle in a
+    subprocess, so that the alternatives stay correct while they are kept."""
+    import os
+    import subprocess
+    import sys
+
+    if os.environ.get("CFB_EMU_DEFINES"):
+        pytest.skip("already running inside the flipped build")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CFB_EMU_DEFINES="-DCFB_WPIPE_ALIAS=0 -DCFB_UNORD_DIRECT=0 -DCFB_SHFL_MIRROR=0 -DCFB_UNORD_REAL_DIRECT=1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_emu_kernels.py", "-x", "-q", "-p", "no:cacheprovider",
+                        "-k", "match_oracle or warp_pipelined or pipelined"], cwd=root, env=env, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
