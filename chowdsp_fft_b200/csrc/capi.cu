@@ -15,9 +15,24 @@
 #include <unordered_map>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h> // header-only; a no-op unless a profiler injects its NVTX library
+
 #include "../../include/chowdsp_fft_b200.h"
 #include "dispatch.h"
 #include "large_plan.h"
+
+// tracing: every computing entry point of the C ABI is an NVTX range (visible in Nsight Systems / Compute timelines)
+namespace
+{
+struct TraceRange
+{
+    explicit TraceRange (const char* name) { nvtxRangePushA (name); }
+    ~TraceRange() { nvtxRangePop(); }
+    TraceRange (const TraceRange&) = delete;
+    TraceRange& operator= (const TraceRange&) = delete;
+};
+} // namespace
+#define CFB_TRACE(name) const TraceRange cfb_trace_range_ (name)
 
 #define CFB_API __attribute__ ((visibility ("default")))
 
@@ -907,6 +922,7 @@ CFB_API void* fft_new_setup_preallocated (int N, fft_transform_t transform, void
 
 CFB_API void* fft_new_setup (int N, fft_transform_t transform, bool use_avx_if_available)
 {
+    CFB_TRACE ("fft_new_setup");
     void* block = std::malloc (sizeof (Plan) + 64);
     if (block == nullptr)
         return nullptr;
@@ -947,6 +963,7 @@ CFB_API int fft_simd_width_bytes (void* setup)
 
 CFB_API void fft_transform (void* setup, const float* input, float* output, float*, fft_direction_t direction)
 {
+    CFB_TRACE ("fft_transform");
     const Plan* p = static_cast<const Plan*> (setup);
     const long long nfl = (p != nullptr && p->magic == kMagic) ? (p->is_complex ? 2LL * p->N : p->N) : 0;
     (void) transform_any (setup, input, output, 1, nfl, nfl, direction, true, cudaStreamPerThread, true);
@@ -954,6 +971,7 @@ CFB_API void fft_transform (void* setup, const float* input, float* output, floa
 
 CFB_API void fft_transform_unordered (void* setup, const float* input, float* output, float*, fft_direction_t direction)
 {
+    CFB_TRACE ("fft_transform_unordered");
     const Plan* p = static_cast<const Plan*> (setup);
     const long long nfl = (p != nullptr && p->magic == kMagic) ? (p->is_complex ? 2LL * p->N : p->N) : 0;
     (void) transform_any (setup, input, output, 1, nfl, nfl, direction, false, cudaStreamPerThread, true);
@@ -961,6 +979,7 @@ CFB_API void fft_transform_unordered (void* setup, const float* input, float* ou
 
 CFB_API void fft_convolve_unordered (void* setup, const float* a, const float* b, float* ab, float scaling)
 {
+    CFB_TRACE ("fft_convolve_unordered");
     Plan* p = as_plan (setup);
     if (p == nullptr)
         return;
@@ -970,6 +989,7 @@ CFB_API void fft_convolve_unordered (void* setup, const float* a, const float* b
 
 CFB_API void fft_accumulate (void* setup, const float* a, const float* b, float* ab, int N)
 {
+    CFB_TRACE ("fft_accumulate");
     Plan* p = as_plan (setup);
     if (p == nullptr)
         return;
@@ -1031,11 +1051,13 @@ CFB_API void aligned_free (void* p)
 // ---- extensions (chowdsp_fft_b200.h) -----------------------------------------------------------
 CFB_API int fft_transform_batched (void* setup, const float* input, float* output, int batch, long long in_stride, long long out_stride, fft_direction_t direction, int ordered, void* stream)
 {
+    CFB_TRACE ("fft_transform_batched");
     return transform_any (setup, input, output, batch, in_stride, out_stride, direction, ordered != 0, static_cast<cudaStream_t> (stream), false);
 }
 
 CFB_API int fft_transform_strided (void* setup, const float* input, float* output, int outer, int inner, long long in_outer, long long in_inner, long long out_outer, long long out_inner, fft_direction_t direction, int ordered, void* stream)
 {
+    CFB_TRACE ("fft_transform_strided");
     Plan* p = as_plan (setup);
     if (p == nullptr)
         return FFT_B200_EINVAL;
@@ -1050,6 +1072,7 @@ CFB_API int fft_transform_strided (void* setup, const float* input, float* outpu
 
 CFB_API int fft_stft_forward (void* setup, const float* signal, float* spectra, int channels, int frames, long long channel_stride, long long hop, long long out_channel_stride, long long out_frame_stride, const float* window, int ordered, void* stream)
 {
+    CFB_TRACE ("fft_stft_forward");
     Plan* p = as_plan (setup);
     if (p == nullptr)
         return FFT_B200_EINVAL;
@@ -1066,6 +1089,7 @@ CFB_API int fft_stft_forward (void* setup, const float* signal, float* spectra, 
 
 CFB_API int fft_istft_overlap_add (void* setup, const float* spectra, float* signal, int channels, int frames, long long spec_channel_stride, long long spec_frame_stride, long long channel_stride, long long hop, const float* window, float scale, int ordered, void* stream)
 {
+    CFB_TRACE ("fft_istft_overlap_add");
     Plan* p = as_plan (setup);
     if (p == nullptr)
         return FFT_B200_EINVAL;
@@ -1218,6 +1242,7 @@ int juce_launch (Plan* p, int kind, const float* in, float* out, int batch, long
 
 CFB_API int fft_juce_perform_batched (void* setup, const float* input, float* output, int batch, long long in_stride, long long out_stride, int inverse, void* stream)
 {
+    CFB_TRACE ("fft_juce_perform_batched");
     Plan* p = as_plan (setup);
     if (p == nullptr)
         return FFT_B200_EINVAL;
@@ -1230,6 +1255,7 @@ CFB_API int fft_juce_perform_batched (void* setup, const float* input, float* ou
 
 CFB_API int fft_juce_real_forward_batched (void* setup, float* inout, int batch, long long stride, int ignore_negative_freqs, void* stream)
 {
+    CFB_TRACE ("fft_juce_real_forward_batched");
     Plan* p = as_plan (setup);
     if (p == nullptr)
         return FFT_B200_EINVAL;
@@ -1244,6 +1270,7 @@ CFB_API int fft_juce_real_forward_batched (void* setup, float* inout, int batch,
 
 CFB_API int fft_juce_real_inverse_batched (void* setup, float* inout, int batch, long long stride, void* stream)
 {
+    CFB_TRACE ("fft_juce_real_inverse_batched");
     Plan* p = as_plan (setup);
     if (p == nullptr)
         return FFT_B200_EINVAL;
@@ -1254,6 +1281,7 @@ CFB_API int fft_juce_real_inverse_batched (void* setup, float* inout, int batch,
 
 CFB_API int fft_convolve_unordered_batched (void* setup, const float* a, const float* b, float* ab, int batch, long long a_stride, long long b_stride, long long ab_stride, float scaling, void* stream)
 {
+    CFB_TRACE ("fft_convolve_unordered_batched");
     Plan* p = as_plan (setup);
     if (p == nullptr)
         return FFT_B200_EINVAL;
@@ -1263,6 +1291,7 @@ CFB_API int fft_convolve_unordered_batched (void* setup, const float* a, const f
 
 CFB_API int fft_partitioned_convolve_step (void* setup, const float* windows, long long window_stride, const float* ir, long long ir_channel_stride, float* fdl, long long fdl_channel_stride, float* output, long long output_stride, int channels, int partitions, int block_index, float scaling, void* stream)
 {
+    CFB_TRACE ("fft_partitioned_convolve_step");
     Plan* p = as_plan (setup);
     if (p == nullptr)
         return FFT_B200_EINVAL;
@@ -1319,6 +1348,7 @@ CFB_API int fft_large_factors (void* setup, int* l1, int* l2, int* l3)
 
 CFB_API int fft_dist_phase (void* setup, int phase, int rank, int world, const float* in, float* out, fft_direction_t direction, void* stream)
 {
+    CFB_TRACE ("fft_dist_phase");
     Plan* p = as_plan (setup);
     if (p == nullptr)
         return FFT_B200_EINVAL;
@@ -1352,6 +1382,7 @@ CFB_API int fft_dist_phase (void* setup, int phase, int rank, int world, const f
 
 CFB_API int fft_dist_phase0_peer (void* setup, int rank, int world, const float* in, float* const* peer_recv, fft_direction_t direction, void* stream)
 {
+    CFB_TRACE ("fft_dist_phase0_peer");
     Plan* p = as_plan (setup);
     if (p == nullptr)
         return FFT_B200_EINVAL;
@@ -1442,6 +1473,7 @@ CFB_API void fft_dist_ipc_close (void* p)
 
 CFB_API int fft_accumulate_batched (void* setup, const float* a, const float* b, float* ab, long long n, void* stream)
 {
+    CFB_TRACE ("fft_accumulate_batched");
     Plan* p = as_plan (setup);
     if (p == nullptr)
         return FFT_B200_EINVAL;
