@@ -613,6 +613,22 @@ int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inne
         }
         return 0;
     }
+    {
+        // the kernels move complex pairs (8 bytes) on the ordered side and 16-byte vectors on the unordered side: reject
+        // transforms that do not start on such a boundary instead of faulting on the device (the reference asks for buffers
+        // aligned to fft_simd_width_bytes, chowdsp_fft.h:131-136)
+        const bool fwd = direction == chowdsp::fft::FFT_FORWARD;
+        const unsigned a_in = (! ordered && ! fwd) ? 16u : 8u, a_out = (! ordered && fwd) ? 16u : 8u;
+        const auto bad = [] (const void* ptr, long long s_inner, long long s_outer, int n_inner, int n_outer, unsigned align)
+        {
+            const long long m = (long long) (align / 4u) - 1;
+            return (reinterpret_cast<uintptr_t> (ptr) & (align - 1u)) != 0 || (n_inner > 1 && (s_inner & m) != 0) || (n_outer > 1 && (s_outer & m) != 0);
+        };
+        if (bad (in, in_inner, in_outer, inner, outer, a_in) || bad (out, out_inner, out_outer, inner, outer, a_out))
+            return fail (chowdsp::fft::FFT_B200_EINVAL, "every transform must start on an 8-byte boundary (16-byte for unordered spectra): check the base pointers and strides");
+        if (window != nullptr && (reinterpret_cast<uintptr_t> (window) & 7u) != 0)
+            return fail (chowdsp::fft::FFT_B200_EINVAL, "the window must be 8-byte aligned");
+    }
     Tables t;
     // plain, ordered batches of the two largest single-kernel sizes with 16-byte aligned input rows: persistent
     // TMA-pipelined kernel (32 points per thread)

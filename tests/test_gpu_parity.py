@@ -684,6 +684,20 @@ def test_setup_errors(cf):
             cf.fft_new_setup(N, tr)
     with pytest.raises(cf.FFTError):
         cf.fft_transform_batched(12345678, None, None, 1, 1, 1, 0, True)
+    # transforms that do not start on an 8-byte (unordered: 16-byte) boundary are rejected on the host, not faulted on the device
+    s = cf.fft_new_setup(64, cf.FFT_REAL)
+    try:
+        buf = torch.zeros(2048, device="cuda")
+        with pytest.raises(cf.FFTError):
+            cf.fft_transform_batched(s, buf[1:], buf[1024:], 1, 64, 64, cf.FFT_FORWARD, True)   # input 4 bytes off
+        with pytest.raises(cf.FFTError):
+            cf.fft_transform_batched(s, buf, buf[1024:], 2, 65, 64, cf.FFT_FORWARD, True)       # odd input stride
+        with pytest.raises(cf.FFTError):
+            cf.fft_transform_batched(s, buf, buf[1026:], 2, 64, 66, cf.FFT_FORWARD, False)      # unordered output rows 8 bytes off
+        cf.fft_transform_batched(s, buf[2:], buf[1024:], 2, 66, 68, cf.FFT_FORWARD, False)      # 8 / 16-byte aligned rows are fine
+        torch.cuda.synchronize()
+    finally:
+        cf.fft_destroy_setup(s)
 
 
 # --------------------------------------------------------------------------------------------------
