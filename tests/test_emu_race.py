@@ -40,3 +40,28 @@ def test_kernel_source_has_no_shared_memory_races(tmp_path):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     reports = "".join(open(f).read() for f in glob.glob(log + "*"))
     assert "ThreadSanitizer: data race" not in reports, reports[:6000]
+
+
+@pytest.mark.timeout(3000)
+def test_kernel_source_memcheck():
+    """The same idea with AddressSanitizer (out-of-bounds shared-memory / global accesses of the kernel source; the
+    emulator's shared memory and the numpy buffers are heap blocks with red zones).  Takes about four minutes for the whole
+    emulator suite, so it only runs on request: CFB_RUN_ASAN=1 pytest tests/test_emu_race.py (clean as of this round)."""
+    if os.environ.get("CFB_RUN_ASAN") != "1" or os.environ.get("CFB_EMU_DEFINES"):
+        pytest.skip("set CFB_RUN_ASAN=1 to run the AddressSanitizer pass")
+    try:
+        asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    except OSError:
+        pytest.skip("gcc not available")
+    if not (os.path.isabs(asan) and os.path.exists(asan)):
+        pytest.skip("libasan not available")
+    log = os.path.join(ROOT, "tests", "emu", "asan_log")
+    for f in glob.glob(log + "*"):
+        os.remove(f)
+    env = dict(os.environ, CFB_EMU_DEFINES="-fsanitize=address -fsanitize-recover=address -g", LD_PRELOAD=asan,
+               ASAN_OPTIONS=f"detect_leaks=0:halt_on_error=0:exitcode=0:log_path={log}")
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_emu_kernels.py", "-q", "-p", "no:cacheprovider", "-k", "not ab_switches"],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=2900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    reports = "".join(open(f).read() for f in glob.glob(log + "*"))
+    assert "ERROR: AddressSanitizer" not in reports, reports[:6000]
