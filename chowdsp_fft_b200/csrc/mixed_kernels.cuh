@@ -147,8 +147,7 @@ FFT_HD void mx_dft16 (float2* u)
 }
 
 // one Stockham pass of radix RDX: src in natural order of the pass input, dst in autosort order.
-//   SRC = 1 / 2: src is the transform's input in global memory, read as is / conjugated (first pass of the forward kinds and of
-//            the ordered complex inverse: no staging copy)
+//   SRC = 1: src is the transform's input in global memory (first pass of the forward kinds: no staging copy)
 //   DST = 1 / 2: dst is the transform's output in global memory, stored as is / conjugated (last pass of the kinds whose
 //            output is in natural order); `active` = false skips those stores
 template <int RDX, int SRC = 0, int DST = 0>
@@ -163,7 +162,7 @@ FFT_HD void mixed_pass (const float2* src, float2* dst, int M, int Ns, const flo
         float2 u[RDX];
 #pragma unroll
         for (int q = 0; q < RDX; ++q)
-            u[q] = SRC == 1 ? ldg_stream (src + j + q * cols) : SRC == 2 ? mx_conj (ldg_stream (src + j + q * cols)) : lds2 (src + j + q * cols);
+            u[q] = SRC == 1 ? ldg_stream (src + j + q * cols) : lds2 (src + j + q * cols);
         if (Ns > 1)
         {
 #pragma unroll
@@ -228,10 +227,10 @@ FFT_HD void mixed_body (const MixedArgs& a)
         float* __restrict__ out = a.out + x * a.out_stride;
         // the first pass of the forward kinds reads global memory itself; the last pass of the kinds whose output is in
         // natural order (ordered complex spectra, time-domain signals) writes it itself (two or more passes)
-        const int src_global = a.nstages < 2 ? 0 : (a.kind == C2C_FWD || a.kind == R2C) ? 1 : (a.kind == C2C_BWD && W == 0) ? 2 : 0;
+        const bool src_global = (a.kind == C2C_FWD || a.kind == R2C) && a.nstages >= 2;
         const int dst_global = a.nstages < 2 ? 0 : (a.kind == C2C_FWD && W == 0) ? 1 : backward ? 2 : 0;
         // ---- load: A[n] = stage-0 input (conjugated for the backward kinds) ----
-        if (src_global != 0)
+        if (src_global)
         {
         }
         else if (a.kind == C2C_FWD || a.kind == R2C)
@@ -288,7 +287,7 @@ FFT_HD void mixed_body (const MixedArgs& a)
                 A[k] = mx_conj (z);
             }
         }
-        if (src_global == 0)
+        if (! src_global)
             __syncthreads();
         // ---- Stockham passes ----
         float2* src = A;
@@ -297,10 +296,8 @@ FFT_HD void mixed_body (const MixedArgs& a)
         for (int s = 0; s < a.nstages; ++s)
         {
             const int r = a.radix[s];
-            if (s == 0 && src_global == 1)
+            if (s == 0 && src_global)
                 mixed_pass_r<1, 0> (r, reinterpret_cast<const float2*> (in), dst, M, Ns, a.wtab, tid, nthreads);
-            else if (s == 0 && src_global == 2)
-                mixed_pass_r<2, 0> (r, reinterpret_cast<const float2*> (in), dst, M, Ns, a.wtab, tid, nthreads);
             else if (s == a.nstages - 1 && dst_global == 1)
                 mixed_pass_r<0, 1> (r, src, reinterpret_cast<float2*> (out), M, Ns, a.wtab, tid, nthreads, active);
             else if (s == a.nstages - 1 && dst_global == 2)
