@@ -279,18 +279,42 @@ int plan_tables (Plan* p, Tables& t, int radix = 16)
         return 0; // multi-pass plan: tables are fetched per pass (enqueue_large)
     }
     const int ri = radix == 32 ? 1 : 0;
-    if (! p->have[ri][dev])
     {
-        Tables nt;
-        const int rc = get_tables (dev, p->logM, ! p->is_complex, nt, radix);
-        if (rc != 0)
-            return rc;
+        // the plan may be shared across threads (chowdsp_fft.h:87-91): its per-device cache is read and written under the mutex
         std::lock_guard<std::mutex> lock (g_tables_mutex);
-        p->tables[ri][dev] = nt;
-        p->have[ri][dev] = true;
+        if (p->have[ri][dev])
+        {
+            t = p->tables[ri][dev];
+            return 0;
+        }
     }
-    t = p->tables[ri][dev];
+    Tables nt;
+    const int rc = get_tables (dev, p->logM, ! p->is_complex, nt, radix);
+    if (rc != 0)
+        return rc;
+    std::lock_guard<std::mutex> lock (g_tables_mutex);
+    p->tables[ri][dev] = nt;
+    p->have[ri][dev] = true;
+    t = nt;
     return 0;
+}
+
+// Setup-time table upload for the current device: every table a later transform call on this plan can ask for, so that
+// device-pointer calls only enqueue work on the caller's stream -- no cudaMalloc / blocking cudaMemcpy under the tables
+// mutex on the first transform, nothing that would invalidate a stream capture.  Other devices are still
+// filled lazily on first use there.
+int preload_large (Plan* p); // multi-pass plans: big twiddle tables + the per-pass stage tables (defined with enqueue_large)
+int preload_tables (Plan* p)
+{
+    Tables t;
+    if (p->mixed)
+        return plan_tables (p, t);
+    if (p->logM > kMaxLogM)
+        return preload_large (p);
+    int rc = plan_tables (p, t, 16);
+    if (rc == 0 && has_radix32 (p->logM))
+        rc = plan_tables (p, t, 32); // default radix-32 geometries, the TMA-pipelined kernels (2^13 / 2^14) and wpipe at 2^10
+    return rc;
 }
 
 size_t reference_bytes (int N, bool is_complex) // sse:67-72 / avx:73-78: 2*Ncvec*W*4 + sizeof(FFT_Setup)
@@ -381,7 +405,34 @@ struct Staging
             stream[l] = nullptr;
         }
     }
-    ~Staging() { /* process teardown: the driver reclaims; avoid CUDA calls during static destruction */ }
+    // Runs when the owning thread exits (thread_local).  A worker thread that used the host-memory path gives its two
+    // streams and up to six staging buffers back here -- short-lived audio worker threads would otherwise grow device
+    // memory without bound.  On the main thread this runs at exit() before any static destructor / atexit
+    // handler, i.e. while the runtime is still loaded; if the runtime is already unloading the calls fail with
+    // cudaErrorCudartUnloading, which is ignored.
+    ~Staging()
+    {
+        if (device < 0)
+            return;
+        int cur = -1;
+        if (cudaGetDevice (&cur) != cudaSuccess)
+        {
+            (void) cudaGetLastError();
+            return;
+        }
+        if (cur != device && cudaSetDevice (device) != cudaSuccess)
+        {
+            (void) cudaGetLastError();
+            return;
+        }
+        for (int l = 0; l < 2; ++l)
+            if (stream[l] != nullptr)
+                (void) cudaStreamSynchronize (stream[l]);
+        release();
+        if (cur != device)
+            (void) cudaSetDevice (cur);
+        (void) cudaGetLastError();
+    }
 };
 thread_local Staging t_staging;
 
@@ -440,8 +491,102 @@ int kind_of (const Plan* p, int direction)
     return direction == chowdsp::fft::FFT_FORWARD ? R2C : C2R;
 }
 
-// `batch` transforms larger than a CTA: 2 or 3 tile passes (+ a split/merge or reorder pass) through
-// stream-ordered scratch.  The reference uses the caller's `work` buffer for the same purpose
+
+// Alignment guard shared by every entry point: the kernels move 8-byte complex pairs on ordered data,
+// windows and signals and 16-byte vectors on unordered spectra, delay lines and IR partitions.  A misaligned base or
+// an odd stride would become cudaErrorMisalignedAddress on the device -- a sticky error that poisons the whole CUDA
+// context of the host process -- so it is rejected here with FFT_B200_EINVAL instead.  Strides in floats; a stride only
+// matters when more than one row is addressed through it.
+bool misaligned (const void* ptr, unsigned align_bytes, long long s0 = 0, long long n0 = 1, long long s1 = 0, long long n1 = 1)
+{
+    const long long m = (long long) (align_bytes / 4u) - 1;
+    return (reinterpret_cast<uintptr_t> (ptr) & (uintptr_t) (align_bytes - 1u)) != 0 || (n0 > 1 && (s0 & m) != 0) || (n1 > 1 && (s1 & m) != 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-pass (large) transforms
+// ------------------------------------------------------------------------------------------------
+// tuning hooks "l2_chunk_mb" (MiB of intermediate per chunk of the L2-chunked schedules, 0 = classic whole-array passes),
+// "l2_lanes" (helper streams / ring slots, 1..4) and "l2_policy" (1 = evict_last / evict_first hints on ring / stream accesses)
+constexpr int kL2ChunkMbDefault = 16, kL2LanesDefault = 2, kL2PolicyDefault = 1;
+int g_l2_chunk_mb = kL2ChunkMbDefault, g_l2_lanes = kL2LanesDefault, g_l2_policy = kL2PolicyDefault;
+constexpr int kMaxLanes = 4;
+
+// helper streams of the chunked schedules: chunks alternate over them so that pass B of one chunk overlaps pass C of the
+// previous one; joined back into the caller's stream with events (also legal inside a stream capture)
+struct ForkJoin
+{
+    cudaStream_t lane[kMaxLanes] = { nullptr, nullptr, nullptr, nullptr };
+    cudaEvent_t fork = nullptr, join[kMaxLanes] = { nullptr, nullptr, nullptr, nullptr };
+    int device = -1;
+    int ensure()
+    {
+        int dev = 0;
+        CFB_CUDA (cudaGetDevice (&dev));
+        if (device == dev)
+            return 0;
+        release();
+        for (int i = 0; i < kMaxLanes; ++i)
+        {
+            CFB_CUDA (cudaStreamCreateWithFlags (&lane[i], cudaStreamNonBlocking));
+            CFB_CUDA (cudaEventCreateWithFlags (&join[i], cudaEventDisableTiming));
+        }
+        CFB_CUDA (cudaEventCreateWithFlags (&fork, cudaEventDisableTiming));
+        device = dev;
+        return 0;
+    }
+    void release()
+    {
+        for (int i = 0; i < kMaxLanes; ++i)
+        {
+            if (lane[i] != nullptr)
+                (void) cudaStreamDestroy (lane[i]);
+            if (join[i] != nullptr)
+                (void) cudaEventDestroy (join[i]);
+            lane[i] = nullptr;
+            join[i] = nullptr;
+        }
+        if (fork != nullptr)
+            (void) cudaEventDestroy (fork);
+        fork = nullptr;
+        device = -1;
+    }
+    ~ForkJoin()
+    {
+        if (device >= 0)
+        {
+            release();
+            (void) cudaGetLastError();
+        }
+    }
+};
+thread_local ForkJoin t_forkjoin;
+
+struct LargeTables
+{
+    BigTables bt;
+    Tables pass[3];
+};
+int large_tables (Plan* p, int dev, const LargeFactors& f, LargeTables& lt)
+{
+    int rc = get_big_tables (dev, p->is_complex ? p->logM : p->logM + 1, lt.bt);
+    const int logs[3] = { f.l1, f.l2, f.l3 };
+    for (int i = 0; i < 3 && rc == 0; ++i)
+        if (logs[i] != 0)
+            rc = get_tables (dev, logs[i], false, lt.pass[i]);
+    return rc;
+}
+int preload_large (Plan* p)
+{
+    int dev = 0;
+    CFB_CUDA (cudaGetDevice (&dev));
+    LargeTables lt;
+    return large_tables (p, dev, choose_factors (p->logM), lt);
+}
+
+// `batch` transforms larger than a CTA: 2 or 3 tile passes (+ a split / merge pass for real plans) through stream-ordered
+// scratch, L2-chunked where that saves HBM sweeps (large_plan.h: build_large_schedule).  Unordered complex layouts are
+// folded into the first / last pass.  The reference uses the caller's `work` buffer for the same purpose
 // (simd/chowdsp_fft_impl_avx.cpp:1861-1863); here `work` may stay NULL.  Strides in floats.
 int enqueue_large (Plan* p, const float* in, float* out, int batch, long long in_stride, long long out_stride, int direction, bool ordered, cudaStream_t stream)
 {
@@ -451,23 +596,11 @@ int enqueue_large (Plan* p, const float* in, float* out, int batch, long long in
     const bool fwd = direction == chowdsp::fft::FFT_FORWARD;
     const int dir = fwd ? -1 : +1;
     const LargeFactors f = choose_factors (n);
-    TilePass pass[3];
-    const int np = build_tile_passes (n, f, pass, p->is_complex ? 1u : 2u);
-    BigTables bt;
-    int rc = get_big_tables (dev, p->is_complex ? n : n + 1, bt);
+    const int np = f.passes();
+    LargeTables lt;
+    int rc = large_tables (p, dev, f, lt);
     if (rc != 0)
         return rc;
-    for (int i = 0; i < np; ++i)
-    {
-        Tables st;
-        rc = get_tables (dev, pass[i].logL, false, st);
-        if (rc != 0)
-            return rc;
-        pass[i].args.tw = st.tw;
-        pass[i].args.tw_lo = bt.lo;
-        pass[i].args.tw_hi = bt.hi;
-        pass[i].args.tw_lobits = bt.lobits;
-    }
     {   // keep freed scratch cached in the stream-ordered pool instead of returning it to the OS at every sync
         static thread_local int pool_ready_for = -1;
         if (pool_ready_for != dev)
@@ -484,87 +617,200 @@ int enqueue_large (Plan* p, const float* in, float* out, int batch, long long in
     }
     const long long npts = 1LL << n;              // float2 per transform
     const size_t bytes = sizeof (float2) << n;
-    // scratch is allocated per chunk of the batch (<= 512 MiB per buffer)
-    int chunk = (int) ((512ull << 20) / bytes);
-    chunk = chunk < 1 ? 1 : (chunk > batch ? batch : chunk);
-    const bool need_s2 = fwd && (! p->is_complex || ! ordered);
-    float2 *s1 = nullptr, *s2 = nullptr;
-    CFB_CUDA (cudaMallocAsync (&s1, bytes * (size_t) chunk, stream));
+    const bool real = ! p->is_complex;
+    // Chunked schedule?  Two-pass plans: only when the batch does not fit in L2 anyway (a single 2^15..2^20-point transform is
+    // L2-resident between its passes as it is).  Three-pass plans: always.
+    long long chunk_elems = (long long) g_l2_chunk_mb * (1 << 20) / 8;
+    if (np == 2 && (long long) batch * npts <= 2 * chunk_elems)
+        chunk_elems = 0;
+    const int lanes = g_l2_lanes < 1 ? 1 : (g_l2_lanes > kMaxLanes ? kMaxLanes : g_l2_lanes);
+    // full-size scratch is allocated per super-chunk of the batch (<= 512 MiB per buffer)
+    int super = (int) ((512ull << 20) / bytes);
+    super = super < 1 ? 1 : (super > batch ? batch : super);
+    const long long ring_lane = ring_elems_needed (n, f, super, chunk_elems);
+    // real two-pass chunked plans keep the split / merge step inside the chunk: a second sub-slot per lane holds z
+    const bool real_in_chunk = real && np == 2 && chunk_elems > 0;
+    const bool need_s1 = chunk_elems == 0 || np == 3;
+    const bool need_s2 = real && ! real_in_chunk && fwd; // z of a forward real transform, before the split pass (backward: merged into s1)
+    float2 *s1 = nullptr, *s2 = nullptr, *ring = nullptr;
+    if (need_s1)
+        CFB_CUDA (cudaMallocAsync (&s1, bytes * (size_t) super, stream));
     if (need_s2)
-        CFB_CUDA (cudaMallocAsync (&s2, bytes * (size_t) chunk, stream));
+        CFB_CUDA (cudaMallocAsync (&s2, bytes * (size_t) super, stream));
+    if (chunk_elems > 0)
+        CFB_CUDA (cudaMallocAsync (&ring, sizeof (float2) * (size_t) ring_lane * (size_t) lanes * (real_in_chunk ? 2u : 1u), stream));
+    ForkJoin& fj = t_forkjoin;
+    if (chunk_elems > 0 && (rc = fj.ensure()) != 0)
+        return rc;
+
+    RealPassArgs ra {};
+    ra.logM = n;
+    ra.logW = ordered ? 0 : p->logW;
+    ra.tw_lobits = lt.bt.lobits;
+    ra.tw_mult = 1;
+    ra.tw_lo = lt.bt.lo;
+    ra.tw_hi = lt.bt.hi;
     cudaError_t e = cudaSuccess;
-    for (int b0 = 0; b0 < batch && rc == 0 && e == cudaSuccess; b0 += chunk)
+    std::vector<LargeLaunch> sched;
+    int launches_total = 0;
+    for (int b0 = 0; b0 < batch && rc == 0 && e == cudaSuccess; b0 += super)
     {
-        const int nb = batch - b0 < chunk ? batch - b0 : chunk;
+        const int nb = batch - b0 < super ? batch - b0 : super;
         const float* cin = in + (long long) b0 * in_stride;
         float* cout = out + (long long) b0 * out_stride;
-        // src / dst strides in float2; the scratch is dense
-        auto run_passes = [&] (const float2* src, long long src_bs, float2* dst, long long dst_bs) -> int
+        LargeBuffers bufs {};
+        bufs.s1 = s1;
+        bufs.ring = ring;
+        bufs.ring_lane_elems = ring_lane;
+        bool forked = false;
+        bool lane_used[kMaxLanes] = { false, false, false, false };
+        auto stream_of = [&] (int lane) -> cudaStream_t
         {
-            for (int i = 0; i < np; ++i)
+            if (lane < 0)
+                return stream;
+            if (! forked)
             {
-                pass[i].args.in = i == 0 ? src : s1;
-                pass[i].args.in_bstride = i == 0 ? src_bs : npts;
-                pass[i].args.out = i == np - 1 ? dst : s1;
-                pass[i].args.out_bstride = i == np - 1 ? dst_bs : npts;
-                pass[i].args.batch = nb;
-                note_kernel ("cfb::tile_fft_kernel<%d,%d,%d> x%d passes", pass[i].logL, pass[i].C, dir, np);
-                const cudaError_t le = launch_tile (pass[i].logL, pass[i].C, dir, pass[i].load_j_fast, pass[i].args, stream);
-                if (le != cudaSuccess)
-                    return fail_cuda (le, "tile pass launch");
+                e = cudaEventRecord (fj.fork, stream);
+                forked = true;
             }
-            return 0;
-        };
-        RealPassArgs ra {};
-        ra.logM = n;
-        ra.logW = ordered ? 0 : p->logW;
-        ra.tw_lobits = bt.lobits;
-        ra.tw_mult = 1;
-        ra.tw_lo = bt.lo;
-        ra.tw_hi = bt.hi;
-        if (p->is_complex)
-        {
-            if (fwd && ordered)
-                rc = run_passes (reinterpret_cast<const float2*> (cin), in_stride / 2, reinterpret_cast<float2*> (cout), out_stride / 2);
-            else if (fwd)
+            if (! lane_used[lane])
             {
-                rc = run_passes (reinterpret_cast<const float2*> (cin), in_stride / 2, s2, npts);
-                if (rc == 0)
-                    e = launch_complex_reorder (reinterpret_cast<const float*> (s2), cout, 2 * npts, out_stride, nb, n, p->logW, true, stream);
-            }
-            else if (ordered)
-                rc = run_passes (reinterpret_cast<const float2*> (cin), in_stride / 2, reinterpret_cast<float2*> (cout), out_stride / 2);
-            else
-            {
-                e = launch_complex_reorder (cin, reinterpret_cast<float*> (s1), in_stride, 2 * npts, nb, n, p->logW, false, stream);
                 if (e == cudaSuccess)
-                    rc = run_passes (s1, npts, reinterpret_cast<float2*> (cout), out_stride / 2);
+                    e = cudaStreamWaitEvent (fj.lane[lane], fj.fork, 0);
+                lane_used[lane] = true;
             }
-        }
-        else if (fwd)
+            return fj.lane[lane];
+        };
+        auto join = [&]
         {
-            rc = run_passes (reinterpret_cast<const float2*> (cin), in_stride / 2, s2, npts);
-            ra.in = reinterpret_cast<const float*> (s2);
-            ra.in_bstride = 2 * npts;
-            ra.out = cout;
-            ra.out_bstride = out_stride;
-            if (rc == 0)
-                e = launch_real_pass (-1, ra, nb, stream);
+            for (int l = 0; l < kMaxLanes; ++l)
+                if (lane_used[l])
+                {
+                    if (e == cudaSuccess)
+                        e = cudaEventRecord (fj.join[l], fj.lane[l]);
+                    if (e == cudaSuccess)
+                        e = cudaStreamWaitEvent (stream, fj.join[l], 0);
+                }
+        };
+        if (real_in_chunk)
+        {
+            // per chunk of k transforms on lane l:  forward  A: src -> ring, C: ring -> z, split: z -> out
+            //                                        backward merge: in -> z, A: z -> ring, C: ring -> out
+            const long long k = ring_lane / npts;
+            int lane = 0;
+            for (long long c0 = 0; c0 < nb && e == cudaSuccess; c0 += k, lane = (lane + 1) % lanes)
+            {
+                const int nc = (int) (nb - c0 < k ? nb - c0 : k);
+                float2* slot = ring + (long long) lane * 2 * ring_lane;
+                float2* zbuf = slot + ring_lane;
+                cudaStream_t st = stream_of (lane);
+                LargeBuffers cb {};
+                cb.src = fwd ? reinterpret_cast<const float2*> (cin + c0 * in_stride) : zbuf;
+                cb.src_bs = fwd ? in_stride / 2 : npts;
+                cb.dst = fwd ? zbuf : reinterpret_cast<float2*> (cout + c0 * out_stride);
+                cb.dst_bs = fwd ? npts : out_stride / 2;
+                cb.s1 = slot;
+                build_large_schedule (n, f, nc, cb, 2u, false, false, 0, 0, 1, false, sched);
+                const int keep = g_l2_policy ? POLICY_KEEP : POLICY_NORMAL, strm = g_l2_policy ? POLICY_STREAM : POLICY_NORMAL;
+                sched[0].pass.args.in_policy = fwd ? strm : keep;
+                sched[0].pass.args.out_policy = keep;
+                sched[1].pass.args.in_policy = keep;
+                sched[1].pass.args.out_policy = fwd ? keep : strm;
+                if (! fwd)
+                {
+                    ra.in = cin + c0 * in_stride;
+                    ra.in_bstride = in_stride;
+                    ra.out = reinterpret_cast<float*> (zbuf);
+                    ra.out_bstride = 2 * npts;
+                    if (e == cudaSuccess)
+                        e = launch_real_pass (+1, ra, nc, st);
+                    ++launches_total;
+                }
+                for (auto& l : sched)
+                {
+                    TileArgs& ta = l.pass.args;
+                    ta.tw = lt.pass[l.pass.which].tw;
+                    ta.tw_lo = lt.bt.lo;
+                    ta.tw_hi = lt.bt.hi;
+                    ta.tw_lobits = lt.bt.lobits;
+                    if (e == cudaSuccess)
+                        e = launch_tile (l.pass.logL, l.pass.C, dir, l.pass.load_j_fast, l.pass.uio, ta, st);
+                    ++launches_total;
+                }
+                if (fwd)
+                {
+                    ra.in = reinterpret_cast<const float*> (zbuf);
+                    ra.in_bstride = 2 * npts;
+                    ra.out = cout + c0 * out_stride;
+                    ra.out_bstride = out_stride;
+                    if (e == cudaSuccess)
+                        e = launch_real_pass (-1, ra, nc, st);
+                    ++launches_total;
+                }
+            }
+            join();
+            continue;
         }
-        else
+        // complex passes:  src -> dst of this super-chunk
+        if (real && ! fwd)
         {
             ra.in = cin;
             ra.in_bstride = in_stride;
             ra.out = reinterpret_cast<float*> (s1);
             ra.out_bstride = 2 * npts;
             e = launch_real_pass (+1, ra, nb, stream);
+            ++launches_total;
+            bufs.src = s1; // pass A then runs in place on s1 (every tile reads all of its elements before it writes them)
+            bufs.src_bs = npts;
+        }
+        else
+        {
+            bufs.src = reinterpret_cast<const float2*> (cin);
+            bufs.src_bs = in_stride / 2;
+        }
+        if (real && fwd)
+        {
+            bufs.dst = s2;
+            bufs.dst_bs = npts;
+        }
+        else
+        {
+            bufs.dst = reinterpret_cast<float2*> (cout);
+            bufs.dst_bs = out_stride / 2;
+        }
+        const bool uio_in = ! real && ! ordered && ! fwd, uio_out = ! real && ! ordered && fwd;
+        build_large_schedule (n, f, nb, bufs, real ? 2u : 1u, uio_in, uio_out, p->logW, chunk_elems, lanes, g_l2_policy != 0, sched);
+        for (auto& l : sched)
+        {
+            TileArgs& ta = l.pass.args;
+            ta.tw = lt.pass[l.pass.which].tw;
+            ta.tw_lo = lt.bt.lo;
+            ta.tw_hi = lt.bt.hi;
+            ta.tw_lobits = lt.bt.lobits;
+            cudaStream_t st = stream_of (l.lane);
             if (e == cudaSuccess)
-                rc = run_passes (s1, npts, reinterpret_cast<float2*> (cout), out_stride / 2);
+                e = launch_tile (l.pass.logL, l.pass.C, dir, l.pass.load_j_fast, l.pass.uio, ta, st);
+            ++launches_total;
+        }
+        join();
+        if (real && fwd && e == cudaSuccess)
+        {
+            ra.in = reinterpret_cast<const float*> (s2);
+            ra.in_bstride = 2 * npts;
+            ra.out = cout;
+            ra.out_bstride = out_stride;
+            e = launch_real_pass (-1, ra, nb, stream);
+            ++launches_total;
         }
     }
-    CFB_CUDA (cudaFreeAsync (s1, stream));
+    note_kernel ("cfb::tile_fft_kernel<%d|%d|%d,dir %d> %d passes, %s, %d launches", f.l1, f.l2, f.l3, dir, np,
+                 chunk_elems > 0 ? (np == 2 ? "L2-chunked (A,C per chunk)" : "L2-chunked (A global; B,C per chunk)") : "whole-array passes", launches_total);
+    if (s1 != nullptr)
+        CFB_CUDA (cudaFreeAsync (s1, stream));
     if (s2 != nullptr)
         CFB_CUDA (cudaFreeAsync (s2, stream));
+    if (ring != nullptr)
+        CFB_CUDA (cudaFreeAsync (ring, stream));
     if (e != cudaSuccess)
         return fail_cuda (e, "large transform pass launch");
     return rc;
@@ -576,8 +822,8 @@ int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inne
         return fail (chowdsp::fft::FFT_B200_EINVAL, "windowed transforms need a REAL single-kernel power-of-two plan and FFT_FORWARD");
     if (p->mixed)
     {
-        if ((in_inner & 1) != 0 || (out_inner & 1) != 0 || (in_outer & 1) != 0 || (out_outer & 1) != 0)
-            return fail (chowdsp::fft::FFT_B200_EINVAL, "mixed-radix transforms need even strides (8-byte aligned transforms)");
+        if (misaligned (in, 8, in_inner, inner, in_outer, outer) || misaligned (out, 8, out_inner, inner, out_outer, outer))
+            return fail (chowdsp::fft::FFT_B200_EINVAL, "mixed-radix transforms need 8-byte aligned buffers and even strides");
         Tables mt;
         const int mrc = plan_tables (p, mt);
         if (mrc != 0)
@@ -605,8 +851,8 @@ int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inne
     }
     if (p->logM > kMaxLogM)
     {
-        if ((in_inner & 1) != 0 || (out_inner & 1) != 0 || (in_outer & 1) != 0 || (out_outer & 1) != 0)
-            return fail (chowdsp::fft::FFT_B200_EINVAL, "large transforms need even strides (8-byte aligned transforms)");
+        if (misaligned (in, 8, in_inner, inner, in_outer, outer) || misaligned (out, 8, out_inner, inner, out_outer, outer))
+            return fail (chowdsp::fft::FFT_B200_EINVAL, "large transforms need 8-byte aligned buffers and even strides");
         for (int o = 0; o < outer; ++o)
         {
             const int rc = enqueue_large (p, in + o * in_outer, out + o * out_outer, inner, in_inner, out_inner, direction, ordered, stream);
@@ -621,12 +867,7 @@ int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inne
         // aligned to fft_simd_width_bytes, chowdsp_fft.h:131-136)
         const bool fwd = direction == chowdsp::fft::FFT_FORWARD;
         const unsigned a_in = (! ordered && ! fwd) ? 16u : 8u, a_out = (! ordered && fwd) ? 16u : 8u;
-        const auto bad = [] (const void* ptr, long long s_inner, long long s_outer, int n_inner, int n_outer, unsigned align)
-        {
-            const long long m = (long long) (align / 4u) - 1;
-            return (reinterpret_cast<uintptr_t> (ptr) & (align - 1u)) != 0 || (n_inner > 1 && (s_inner & m) != 0) || (n_outer > 1 && (s_outer & m) != 0);
-        };
-        if (bad (in, in_inner, in_outer, inner, outer, a_in) || bad (out, out_inner, out_outer, inner, outer, a_out))
+        if (misaligned (in, a_in, in_inner, inner, in_outer, outer) || misaligned (out, a_out, out_inner, inner, out_outer, outer))
             return fail (chowdsp::fft::FFT_B200_EINVAL, "every transform must start on an 8-byte boundary (16-byte for unordered spectra): check the base pointers and strides");
         if (window != nullptr && (reinterpret_cast<uintptr_t> (window) & 7u) != 0)
             return fail (chowdsp::fft::FFT_B200_EINVAL, "the window must be 8-byte aligned");
@@ -817,6 +1058,9 @@ int elementwise_any (Plan* p, bool convolve, const float* a, const float* b, flo
         return fail (chowdsp::fft::FFT_B200_EINVAL, "null buffer or negative batch");
     if (batch == 0 || nfl == 0)
         return 0;
+    // both kernels move float4 vectors (4 re | 4 im lanes): operands start on 16-byte boundaries, strides are multiples of 4
+    if (misaligned (a, 16, a_stride, batch) || misaligned (b, 16, b_stride, batch) || misaligned (ab, 16, ab_stride, batch))
+        return fail (chowdsp::fft::FFT_B200_EINVAL, "%s: operands must be 16-byte aligned with strides that are multiples of 4 floats", convolve ? "convolve" : "accumulate");
     const PtrInfo ia = classify (a), ib = classify (b), iab = classify (ab);
     const bool all_dev = ia.kind == Mem::Device && ib.kind == Mem::Device && iab.kind == Mem::Device;
     const bool any_dev = ia.kind == Mem::Device || ib.kind == Mem::Device || iab.kind == Mem::Device;
@@ -930,8 +1174,7 @@ CFB_API void* fft_new_setup_preallocated (int N, fft_transform_t transform, void
         fail (FFT_B200_ECUDA, "cudaGetDevice failed");
         return nullptr;
     }
-    Tables t;
-    if (plan_tables (p, t) != 0)
+    if (preload_tables (p) != 0)
     {
         p->magic = 0;
         return nullptr;
@@ -1116,8 +1359,12 @@ CFB_API int fft_istft_overlap_add (void* setup, const float* spectra, float* sig
         return fail (FFT_B200_EINVAL, "fft_istft_overlap_add needs a REAL power-of-two plan with N <= 16384 (frame buffers + carried tails must fit in shared memory)");
     if (spectra == nullptr || signal == nullptr || channels < 0 || frames < 0 || hop <= 0 || hop > p->N || (long long) channels * frames > 0x7fffffffLL)
         return fail (FFT_B200_EINVAL, "fft_istft_overlap_add: bad arguments (0 < hop <= N)");
-    if ((spec_frame_stride & 1) != 0 || (spec_channel_stride & 1) != 0)
-        return fail (FFT_B200_EINVAL, "fft_istft_overlap_add: spectrum strides must be even (8-byte aligned frames)");
+    if (misaligned (spectra, ordered != 0 ? 8 : 16, spec_frame_stride, frames, spec_channel_stride, channels))
+        return fail (FFT_B200_EINVAL, "fft_istft_overlap_add: every spectrum frame must start on an 8-byte boundary (16-byte for unordered spectra): check the base pointer and strides");
+    if (window != nullptr && misaligned (window, 8))
+        return fail (FFT_B200_EINVAL, "fft_istft_overlap_add: the window must be 8-byte aligned");
+    if (misaligned (signal, 4))
+        return fail (FFT_B200_EINVAL, "fft_istft_overlap_add: the signal must be 4-byte aligned");
     if (channels == 0 || frames == 0)
         return 0;
     if (classify (spectra).kind != Mem::Device || classify (signal).kind != Mem::Device || (window != nullptr && classify (window).kind != Mem::Device))
@@ -1234,8 +1481,8 @@ int juce_launch (Plan* p, int kind, const float* in, float* out, int batch, long
 {
     if (p->mixed || p->logM > kMaxLogM)
         return fail (FFT_B200_EINVAL, "the JUCE-convention entry points need a single-kernel power-of-two plan (N <= 16384 complex, 32768 real)");
-    if ((in_stride & 1) != 0 || (out_stride & 1) != 0)
-        return fail (FFT_B200_EINVAL, "the JUCE-convention entry points need even strides");
+    if (misaligned (in, 8, in_stride, batch) || misaligned (out, 8, out_stride, batch))
+        return fail (FFT_B200_EINVAL, "the JUCE-convention entry points need 8-byte aligned buffers and even strides");
     if (batch == 0)
         return 0;
     if (classify (in).kind != Mem::Device || classify (out).kind != Mem::Device)
@@ -1322,6 +1569,10 @@ CFB_API int fft_partitioned_convolve_step (void* setup, const float* windows, lo
         return fail (FFT_B200_EINVAL, "fft_partitioned_convolve_step: bad arguments");
     if (channels == 0)
         return 0;
+    // windows / output move float2 pairs; the delay line and the IR partitions (N floats each, N % 32 == 0) move float4 vectors
+    if (misaligned (windows, 8, window_stride, channels) || misaligned (output, 8, output_stride, channels)
+        || misaligned (ir, 16, ir_channel_stride, channels) || misaligned (fdl, 16, fdl_channel_stride, channels))
+        return fail (FFT_B200_EINVAL, "fft_partitioned_convolve_step: windows / output must be 8-byte aligned with even strides, ir / fdl 16-byte aligned with strides that are multiples of 4 floats");
     if (classify (windows).kind != Mem::Device || classify (ir).kind != Mem::Device || classify (fdl).kind != Mem::Device || classify (output).kind != Mem::Device)
         return fail (FFT_B200_EINVAL, "fft_partitioned_convolve_step needs device pointers");
     Tables t;
@@ -1395,7 +1646,7 @@ CFB_API int fft_dist_phase (void* setup, int phase, int rank, int world, const f
     tp.args.tw_lobits = bt.lobits;
     tp.args.in = reinterpret_cast<const float2*> (in);
     tp.args.out = reinterpret_cast<float2*> (out);
-    const cudaError_t e = launch_tile (tp.logL, tp.C, direction == FFT_FORWARD ? -1 : +1, tp.load_j_fast, tp.args, static_cast<cudaStream_t> (stream));
+    const cudaError_t e = launch_tile (tp.logL, tp.C, direction == FFT_FORWARD ? -1 : +1, tp.load_j_fast, 0, tp.args, static_cast<cudaStream_t> (stream));
     return e == cudaSuccess ? 0 : fail_cuda (e, "distributed phase launch");
 }
 
@@ -1439,7 +1690,7 @@ CFB_API int fft_dist_phase0_peer (void* setup, int rank, int world, const float*
             return fail (FFT_B200_EINVAL, "fft_dist_phase0_peer: null receive buffer for rank %d", h);
         tp.args.peer_out[h] = reinterpret_cast<float2*> (peer_recv[h]);
     }
-    const cudaError_t e = launch_tile (tp.logL, tp.C, direction == FFT_FORWARD ? -1 : +1, tp.load_j_fast, tp.args, static_cast<cudaStream_t> (stream));
+    const cudaError_t e = launch_tile (tp.logL, tp.C, direction == FFT_FORWARD ? -1 : +1, tp.load_j_fast, 0, tp.args, static_cast<cudaStream_t> (stream));
     return e == cudaSuccess ? 0 : fail_cuda (e, "distributed phase 0 (peer stores) launch");
 }
 
@@ -1503,24 +1754,29 @@ CFB_API int fft_accumulate_batched (void* setup, const float* a, const float* b,
 
 CFB_API int fft_b200_set_tuning (const char* key, int value)
 {
-    if (key != nullptr && std::strcmp (key, "tile_pf") == 0 && value >= -1)
+    if (key != nullptr && std::strcmp (key, "l2_chunk_mb") == 0 && value >= -1 && value <= 256)
     {
-        tile_pf_ahead() = value == -1 ? 0 : value;
+        g_l2_chunk_mb = value == -1 ? kL2ChunkMbDefault : value;
         return 0;
     }
-    if (key != nullptr && std::strcmp (key, "tile_pipe") == 0 && (value == 0 || value == 1 || value == -1))
+    if (key != nullptr && std::strcmp (key, "l2_lanes") == 0 && (value == -1 || (value >= 1 && value <= kMaxLanes)))
     {
-        tile_pipe_mode() = value == -1 ? 1 : value;
+        g_l2_lanes = value == -1 ? kL2LanesDefault : value;
         return 0;
     }
-    if (key != nullptr && std::strcmp (key, "tile_c") == 0 && (value == 0 || value == 8 || value == 16))
+    if (key != nullptr && std::strcmp (key, "l2_policy") == 0 && value >= -1 && value <= 1)
     {
-        tile_c_override() = value;
+        g_l2_policy = value == -1 ? kL2PolicyDefault : value;
         return 0;
     }
-    if (key != nullptr && std::strcmp (key, "tile_c_jfast") == 0 && (value == 0 || value == 8 || value == 16))
+    if (key != nullptr && std::strcmp (key, "tile_c") == 0 && (value == -1 || value == 0 || value == 8 || value == 16))
     {
-        tile_c_jfast_override() = value;
+        tile_c_override() = value == -1 ? 0 : value;
+        return 0;
+    }
+    if (key != nullptr && std::strcmp (key, "tile_c_jfast") == 0 && (value == -1 || value == 0 || value == 8 || value == 16))
+    {
+        tile_c_jfast_override() = value == -1 ? 0 : value;
         return 0;
     }
     if (key != nullptr && std::strcmp (key, "pipe_mask") == 0)
@@ -1533,9 +1789,9 @@ CFB_API int fft_b200_set_tuning (const char* key, int value)
         g_radix32_mask = value == -1 ? kRadix32Default : (unsigned) value;
         return 0;
     }
-    if (key != nullptr && std::strcmp (key, "pf_ahead") == 0 && value >= 0)
+    if (key != nullptr && std::strcmp (key, "pf_ahead") == 0 && value >= -1)
     {
-        g_pf_ahead = value;
+        g_pf_ahead = value == -1 ? 0 : value;
         return 0;
     }
     if (key != nullptr && std::strcmp (key, "wistft") == 0)

@@ -65,9 +65,8 @@ cudaError_t launch_pconv (int logM, int logW, const PConvArgs& args, cudaStream_
 cudaError_t launch_mixed (const MixedArgs& args, cudaStream_t stream);
 
 // multi-pass (large transform) kernels, large_inst.cu
-cudaError_t launch_tile (int logL, int C, int dir, bool load_j_fast, const TileArgs& args, cudaStream_t stream);
+cudaError_t launch_tile (int logL, int C, int dir, bool load_j_fast, int uio, const TileArgs& args, cudaStream_t stream);
 cudaError_t launch_real_pass (int dir, const RealPassArgs& args, int batch, cudaStream_t stream);
-cudaError_t launch_complex_reorder (const float* in, float* out, long long in_bstride, long long out_bstride, int batch, int logN, int logW, bool to_unordered, cudaStream_t stream);
 
 cudaError_t launch_convolve (const float* a, const float* b, float* ab, long long a_stride, long long b_stride, long long ab_stride, int nfloats, int batch, int logW, bool is_real, float scaling, cudaStream_t stream);
 cudaError_t launch_accumulate (const float* a, const float* b, float* ab, long long n, cudaStream_t stream);

@@ -15,7 +15,6 @@
 // twiddle scheme and exchange code are the ones of the single-kernel transform (fft_kernels.cuh).
 #pragma once
 #include "fft_kernels.cuh"
-#include "pipe_kernels.cuh" // mbarrier + bulk-copy helpers
 
 
 namespace cfb
@@ -31,16 +30,64 @@ FFT_CX int tile_region_stride (int smem_f2, int C)
     return rs;
 }
 
+// L2 cache policy of one side of a pass (TileArgs::in_policy / out_policy).  The chunked plans (large_plan.h) keep the
+// intermediate of two consecutive passes in a small ring that is meant to stay L2-resident: ring accesses ask for
+// evict_last, the HBM-facing streams of the same kernels for evict_first, so that streaming data does not push the ring out.
+enum TilePolicy : int
+{
+    POLICY_NORMAL = 0,
+    POLICY_STREAM = 1, // evict_first
+    POLICY_KEEP = 2    // evict_last
+};
+FFT_HD unsigned long long make_l2_policy (int which)
+{
+#ifdef CHOWDSP_EMU
+    return (unsigned long long) which;
+#else
+    unsigned long long p;
+    if (which == POLICY_STREAM)
+        asm volatile ("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    else if (which == POLICY_KEEP)
+        asm volatile ("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    else
+        asm volatile ("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+#endif
+}
+FFT_HD float2 ldg_hint (const float2* p, unsigned long long policy)
+{
+#ifdef CHOWDSP_EMU
+    (void) policy;
+    return *p;
+#else
+    float2 r;
+    asm volatile ("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(r.x), "=f"(r.y) : "l"(p), "l"(policy));
+    return r;
+#endif
+}
+FFT_HD void stg_hint (float2* p, float2 v, unsigned long long policy)
+{
+#ifdef CHOWDSP_EMU
+    (void) policy;
+    *p = v;
+#else
+    asm volatile ("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(policy) : "memory");
+#endif
+}
+
 struct TileArgs
 {
+    // in / out = base of transform 0's buffer (or of a ring slot); this launch's tile 0 starts in_bin0 / out_bin0
+    // complex elements into it (chunked launches cover a sub-range of a pass's tiles)
     const float2* in;
     float2* out;
-    // tile g = blockIdx.x:  base = (g / gdiv) * g_hi + (g % gdiv) * g_lo ;  element idx of transform lt sits at
+    long long in_bin0, out_bin0;
+    // tile g = blockIdx.x:  base = bin0 + (g / gdiv) * g_hi + (g % gdiv) * g_lo ;  element idx of transform lt sits at
     // base + lt * tstride + idx * estride   (all in float2 units)
     long long in_g_hi, in_g_lo, in_tstride, in_estride;
     long long out_g_hi, out_g_lo, out_tstride, out_estride;
     int gdiv;
-    int ntiles;          // tiles of ONE transform
+    int ntiles;          // tiles of ONE transform in this launch
     int batch;           // transforms in this launch: grid = batch * ntiles
     long long in_bstride, out_bstride; // float2 between consecutive transforms of the batch
     // optional two-level element stride on the input side (distributed exchange layout): element idx sits at
@@ -62,9 +109,12 @@ struct TileArgs
     int peer_row_log;
     long long peer_chunk_off;
     float2* peer_out[8];
-    // L2 prefetch distance in tiles (0 = off): CTA b asks L2 for the input rows of tile b + pf_ahead, about one wave of
-    // resident CTAs ahead, so that the strided (DRAM-page-missing) gather of a later CTA finds its lines in L2
-    int pf_ahead;
+    // Unordered complex layouts (the reference's pffft_zreorder permutation, simd/chowdsp_fft_impl_avx.cpp:1816-1838) folded
+    // into the addressing of the FIRST pass's loads (UIO = 1, inverse transforms) / the LAST pass's stores (UIO = 2,
+    // forward transforms): the element offset computed above is the natural BIN index of a 2^logN-point transform and
+    // the access goes to that bin's slot of the W = 2^unord_logW lane layout.  No separate reorder sweep.
+    int logN, unord_logW;
+    int in_policy, out_policy; // TilePolicy
 };
 
 template <int DIR>
@@ -75,9 +125,22 @@ FFT_HD float2 big_twiddle (const TileArgs& a, unsigned e)
     return cmul_dir<-1> (lo, hi); // forward twiddle; the caller conjugates for DIR > 0
 }
 
-// v[m] = X[jB + m T] of transform ltB -> four-step twiddle -> store (or peer store), shared by tile_body and tile_pipe_body
-template <int LOGL, int C, int DIR>
-FFT_HD void tile_epilogue (const TileArgs& a, float2 (&v)[16], int ghi, int glo, int ltB, int jB, unsigned cT, const float2* sTw, float2* __restrict__ out)
+// float offset, inside an unordered complex spectrum of 2^logN bins, of the 8-byte pair a thread accesses for bin `bin`:
+// the even bin of a pair owns (re, re') at the pair's slot, the odd one (im, im') W floats later (SURVEY.md §8a-L:
+// vector 2k holds W real parts, vector 2k+1 the W imaginary parts of bins r (N/W) + b W + lane, k = b W + r)
+FFT_HD long long unord_pair_offset (long long bin, int logN, int logW)
+{
+    const int logL = logN - logW;
+    const long long r = bin >> logL, rem = bin & ((1LL << logL) - 1);
+    const long long blk = rem >> logW, lane = rem & ((1 << logW) - 2);
+    return ((((blk << logW) + r) * 2) << logW) + lane + ((bin & 1) << logW);
+}
+
+// v[m] = X[jB + m T] of transform ltB -> four-step twiddle -> store (or peer store)
+// obase = the transform's output buffer, tbin = bin0 + tile offset (element offset of the tile's first transform)
+// (natural-order outputs pass obase = buffer + tile offset and tbin = 0: one live 64-bit value instead of two)
+template <int LOGL, int C, int DIR, int UIO>
+FFT_HD void tile_epilogue (const TileArgs& a, float2 (&v)[16], long long tbin, int ltB, int jB, unsigned cT, const float2* sTw, float2* __restrict__ obase)
 {
     constexpr int R = 16;
     using G = Geo<LOGL, R>;
@@ -100,7 +163,7 @@ FFT_HD void tile_epilogue (const TileArgs& a, float2 (&v)[16], int ghi, int glo,
     {
         // the all-to-all of the distributed transform, done by the stores themselves: every row block goes straight
         // into its owner's receive buffer, so the NVLink transfer overlaps the butterflies of the other tiles
-        const long long toff = a.peer_chunk_off + ghi * a.out_g_hi + glo * a.out_g_lo + ltB * a.out_tstride;
+        const long long toff = a.peer_chunk_off + tbin + ltB * a.out_tstride;
         const int mask = (1 << a.peer_row_log) - 1;
 #pragma unroll
         for (int m = 0; m < R; ++m)
@@ -110,16 +173,35 @@ FFT_HD void tile_epilogue (const TileArgs& a, float2 (&v)[16], int ghi, int glo,
         }
         return;
     }
-    float2* __restrict__ q = out + ltB * a.out_tstride + jB * a.out_estride;
+    const unsigned long long pol = make_l2_policy (a.out_policy);
+    if constexpr (UIO == 2)
+    {
+        // unordered output: lanes (bins) 2i and 2i+1 are adjacent threads; they swap one float so that the even one holds
+        // (re, re') and the odd one (im, im') -- contiguous 8-byte pairs of the unordered layout (as fft_core's UDIRECT)
+        float* __restrict__ fb = reinterpret_cast<float*> (obase);
+        const long long bin0 = tbin + ltB * a.out_tstride + jB * a.out_estride;
+        const int odd = ltB & 1;
+#pragma unroll
+        for (int m = 0; m < R; ++m)
+        {
+            const float recv = shfl1 (odd ? v[m].x : v[m].y, ((int) threadIdx.x ^ 1) & 31, 32);
+            const float2 o = odd ? make_float2 (recv, v[m].y) : make_float2 (v[m].x, recv);
+            stg_hint (reinterpret_cast<float2*> (fb + unord_pair_offset (bin0 + (long long) (m * T) * a.out_estride, a.logN, a.unord_logW)), o, pol);
+        }
+        return;
+    }
+    float2* __restrict__ q = obase + tbin + ltB * a.out_tstride + jB * a.out_estride;
 #pragma unroll
     for (int m = 0; m < R; ++m)
-        q[(long long) (m * T) * a.out_estride] = v[m];
+        stg_hint (q + (long long) (m * T) * a.out_estride, v[m], pol);
 }
 
 // LOAD_J_FAST: the transforms are contiguous rows (pass C), so the LOAD uses the thread map of the batched
 // kernel (consecutive threads = consecutive elements of one row) and the map switches to "consecutive
 // threads = adjacent transforms" at the first exchange, which is what makes the transposed store coalesced.
-template <int LOGL, int C, int DIR, bool LOAD_J_FAST>
+// UIO: 0 = natural-order interleaved complex on both sides, 1 = unordered input (first pass of an inverse transform;
+// strided passes only), 2 = unordered output (last pass of a forward transform)
+template <int LOGL, int C, int DIR, bool LOAD_J_FAST, int UIO = 0>
 FFT_HD void tile_body (const TileArgs& a)
 {
     constexpr int R = 16;
@@ -127,6 +209,7 @@ FFT_HD void tile_body (const TileArgs& a)
     constexpr int T = G::T;
     constexpr int RS = tile_region_stride (G::SMEM_F2, C);
     static_assert (! LOAD_J_FAST || G::S >= 2, "the thread-map switch needs at least one exchange");
+    static_assert (UIO != 1 || ! LOAD_J_FAST, "unordered inputs enter through a strided (first) pass");
     FFT_DYN_SMEM (float2, smem);
     const int tid = (int) threadIdx.x;
     const int bx = (int) blockIdx.x / a.ntiles;
@@ -134,36 +217,17 @@ FFT_HD void tile_body (const TileArgs& a)
     if (bx >= a.batch)
         return;
     const int ghi = g / a.gdiv, glo = g - ghi * a.gdiv;
-    const float2* __restrict__ in = a.in + bx * a.in_bstride + ghi * a.in_g_hi + glo * a.in_g_lo;
-    float2* __restrict__ out = a.out + bx * a.out_bstride + ghi * a.out_g_hi + glo * a.out_g_lo;
+    const float2* __restrict__ ibase = a.in + bx * a.in_bstride;
+    const long long in_tbin = a.in_bin0 + ghi * a.in_g_hi + glo * a.in_g_lo;
+    const long long out_tbin_full = a.out_bin0 + ghi * a.out_g_hi + glo * a.out_g_lo;
+    const float2* __restrict__ in = ibase + in_tbin;
+    // unordered outputs address by bin; the others by pointer
+    const long long out_tbin = (UIO == 2 || a.peer_row_log >= 0) ? out_tbin_full : 0;
+    float2* __restrict__ obase = a.out + bx * a.out_bstride + ((UIO == 2 || a.peer_row_log >= 0) ? 0 : out_tbin_full);
 
     const int ltB = tid % C, jB = tid / C; // adjacent threads = adjacent transforms
     const int ltA = tid / T, jA = tid % T; // adjacent threads = adjacent elements
-    if (a.pf_ahead > 0)
-    {
-        const long long tn = (long long) blockIdx.x + a.pf_ahead;
-        if (tn < (long long) a.ntiles * a.batch)
-        {
-            const int bn = (int) (tn / a.ntiles);
-            const int gn = (int) (tn - (long long) bn * a.ntiles);
-            const int ghn = gn / a.gdiv, gln = gn - ghn * a.gdiv;
-            const float2* pn = a.in + bn * a.in_bstride + ghn * a.in_g_hi + gln * a.in_g_lo;
-            if constexpr (LOAD_J_FAST)
-            {
-                // C contiguous rows of L values = L / 16 lines each: line (tid % (L/16)) of row (tid / (L/16))
-                constexpr int LPR = G::M / 16;
-                for (int i = tid; i < C * LPR; i += T * C)
-                    prefetch_l2 (pn + (long long) (i / LPR) * a.in_tstride + (long long) (i % LPR) * 16);
-            }
-            else
-            {
-                const int mask = a.in_split_log >= 31 ? -1 : (1 << a.in_split_log) - 1;
-                for (int idx = tid; idx < G::M; idx += T * C) // one (C * 8)-byte piece per element row
-                    prefetch_l2 (pn + (a.in_split_log >= 31 ? (long long) idx * a.in_estride
-                                                              : (long long) (idx >> a.in_split_log) * a.in_chunk_stride + (long long) (idx & mask) * a.in_estride));
-            }
-        }
-    }
+    const unsigned long long ipol = make_l2_policy (a.in_policy);
     float2 v[R];
     float2* sB = smem + ltB * RS;
     float2* sTw = smem + C * RS;           // A[m][lt] = W_N^(mu m T c(lt)), see the twiddle step below
@@ -187,7 +251,7 @@ FFT_HD void tile_body (const TileArgs& a)
         const float2* __restrict__ p = in + ltA * a.in_tstride + jA * a.in_estride;
 #pragma unroll
         for (int m = 0; m < R; ++m)
-            v[m] = ldg_stream (p + (long long) (m * T) * a.in_estride);
+            v[m] = ldg_hint (p + (long long) (m * T) * a.in_estride, ipol);
         float2* sA = smem + ltA * RS;
         stage_compute<G, DIR, 0> (v, jA, a.tw);
         stage_scatter<G, 0> (v, jA, sA);
@@ -197,28 +261,45 @@ FFT_HD void tile_body (const TileArgs& a)
     }
     else
     {
-        const float2* __restrict__ p = in + ltB * a.in_tstride;
-        if (a.in_split_log >= 31)
+        if constexpr (UIO == 1)
         {
-            p += jB * a.in_estride;
-#pragma unroll
-            for (int m = 0; m < R; ++m)
-                v[m] = ldg_stream (p + (long long) (m * T) * a.in_estride);
-        }
-        else
-        {
-            const int mask = (1 << a.in_split_log) - 1;
+            // unordered input: the even bin of a pair loads (re, re'), the odd one (im, im'); one shuffle each way
+            const float* __restrict__ fb = reinterpret_cast<const float*> (ibase);
+            const long long bin0 = in_tbin + ltB * a.in_tstride + jB * a.in_estride;
+            const int odd = ltB & 1;
 #pragma unroll
             for (int m = 0; m < R; ++m)
             {
-                const int idx = jB + m * T;
-                v[m] = ldg_stream (p + (long long) (idx >> a.in_split_log) * a.in_chunk_stride + (long long) (idx & mask) * a.in_estride);
+                const float2 ld = ldg_hint (reinterpret_cast<const float2*> (fb + unord_pair_offset (bin0 + (long long) (m * T) * a.in_estride, a.logN, a.unord_logW)), ipol);
+                const float recv = shfl1 (odd ? ld.x : ld.y, (tid ^ 1) & 31, 32);
+                v[m] = odd ? make_float2 (recv, ld.y) : make_float2 (ld.x, recv);
+            }
+        }
+        else
+        {
+            const float2* __restrict__ p = in + ltB * a.in_tstride;
+            if (a.in_split_log >= 31)
+            {
+                p += jB * a.in_estride;
+#pragma unroll
+                for (int m = 0; m < R; ++m)
+                    v[m] = ldg_hint (p + (long long) (m * T) * a.in_estride, ipol);
+            }
+            else
+            {
+                const int mask = (1 << a.in_split_log) - 1;
+#pragma unroll
+                for (int m = 0; m < R; ++m)
+                {
+                    const int idx = jB + m * T;
+                    v[m] = ldg_hint (p + (long long) (idx >> a.in_split_log) * a.in_chunk_stride + (long long) (idx & mask) * a.in_estride, ipol);
+                }
             }
         }
         Stages<G, DIR, 0>::run (v, jB, sB, a.tw, false);
     }
 
-    tile_epilogue<LOGL, C, DIR> (a, v, ghi, glo, ltB, jB, cT, sTw, out);
+    tile_epilogue<LOGL, C, DIR, UIO> (a, v, out_tbin, ltB, jB, cT, sTw, obase);
 }
 
 template <int LOGL, int C>
@@ -230,157 +311,10 @@ struct TileLaunch
     static constexpr int MIN_BLOCKS = THREADS <= 256 ? 4 : (THREADS <= 512 ? 2 : 1);
 };
 
-template <int LOGL, int C, int DIR, bool LOAD_J_FAST>
+template <int LOGL, int C, int DIR, bool LOAD_J_FAST, int UIO>
 __global__ void __launch_bounds__ (TileLaunch<LOGL, C>::THREADS, TileLaunch<LOGL, C>::MIN_BLOCKS) tile_fft_kernel (const TileArgs a)
 {
-    tile_body<LOGL, C, DIR, LOAD_J_FAST> (a);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Persistent TMA-staged tile kernel: the same tile transform as tile_fft_kernel, but a resident CTA loops over tiles
-// blockIdx.x, blockIdx.x + gridDim.x, ... and the NEXT tile is brought into a landing buffer by the TMA unit while the
-// current one is transformed -- one bulk copy per element row of the tile (C contiguous complex values, 64 or 128
-// bytes) on the strided passes, one per transform (a contiguous row of L values) on the contiguous-row pass, all
-// completing on one mbarrier.  The strided gather therefore costs no LSU instructions and no register scoreboard
-// waits (ncu on tile_fft_kernel: long-scoreboard 5.3 and MIO-throttle 3.7 stalled warps per issue, DRAM 56 %).
-// The landing image is [element][transform] (strided passes) or [transform][element] (contiguous rows), so the
-// stage-0 registers are read from it with unit-stride 64-bit accesses in the thread map that pass uses anyway.
-// Needs 16-byte aligned rows (the launcher checks the base pointer and the strides).
-// Shared memory: [landing L C float2][exchange regions + twiddle rows as tile_fft_kernel][mbarrier, 16 bytes].
-// ---------------------------------------------------------------------------------------------
-template <int LOGL, int C>
-struct TilePipeLaunch
-{
-    using TL = TileLaunch<LOGL, C>;
-    using G = Geo<LOGL, 16>;
-    static constexpr int THREADS = TL::THREADS;
-    // contiguous-row pass: rows of short transforms (T < 16 threads) are pitched L + T so that the transforms a
-    // half-warp reads from land in different banks
-    static constexpr int ROW_PAD = G::T < 16 ? G::T : 0;
-    static constexpr int LAND_BYTES = (G::M + ROW_PAD) * C * 8;
-    static constexpr int SMEM_BYTES = LAND_BYTES + TL::SMEM_BYTES + 16;
-    static constexpr bool FITS = SMEM_BYTES <= 227 * 1024;
-    static constexpr int PER_SM_A = (227 * 1024) / (SMEM_BYTES + 1024);
-    static constexpr int PER_SM_B = 2048 / THREADS; // 64 registers per thread
-    static constexpr int PER_SM = PER_SM_A < PER_SM_B ? (PER_SM_A < 1 ? 1 : PER_SM_A) : PER_SM_B;
-};
-
-template <int LOGL, int C, int DIR, bool LOAD_J_FAST>
-FFT_HD void tile_pipe_body (const TileArgs& a)
-{
-    constexpr int R = 16;
-    using G = Geo<LOGL, R>;
-    using TP = TilePipeLaunch<LOGL, C>;
-    constexpr int T = G::T, L = G::M;
-    constexpr int RS = tile_region_stride (G::SMEM_F2, C);
-    constexpr int NT = T * C;                  // threads per CTA
-    constexpr unsigned TILE_BYTES = (unsigned) (L * C * 8);
-    constexpr int LP = L + TP::ROW_PAD;        // landing row pitch of the contiguous-row pass
-    static_assert (! LOAD_J_FAST || G::S >= 2, "the thread-map switch needs at least one exchange");
-    FFT_DYN_SMEM (char, smem_raw);
-    float2* land = reinterpret_cast<float2*> (smem_raw);
-    float2* smem = reinterpret_cast<float2*> (smem_raw + TP::LAND_BYTES);
-    unsigned long long* bar = reinterpret_cast<unsigned long long*> (smem_raw + TP::LAND_BYTES + TP::TL::SMEM_BYTES);
-    const int tid = (int) threadIdx.x;
-    const int ltB = tid % C, jB = tid / C; // adjacent threads = adjacent transforms
-    const int ltA = tid / T, jA = tid % T; // adjacent threads = adjacent elements
-    float2* sB = smem + ltB * RS;
-    float2* sTw = smem + C * RS;
-    const long long tiles = (long long) a.ntiles * a.batch;
-    const long long step = (long long) gridDim.x;
-
-    // start the copies of tile t (every thread issues its share of the rows; thread 0 arms the barrier)
-    auto fetch = [&] (long long t)
-    {
-        const int bx = (int) (t / a.ntiles);
-        const int g = (int) (t - (long long) bx * a.ntiles);
-        const int ghi = g / a.gdiv, glo = g - ghi * a.gdiv;
-        const float2* __restrict__ in = a.in + bx * a.in_bstride + ghi * a.in_g_hi + glo * a.in_g_lo;
-        if (tid == 0)
-            mbar_expect (bar, TILE_BYTES);
-        if constexpr (LOAD_J_FAST)
-        {
-            if (tid < C) // transform `tid` is a contiguous row of L elements
-                bulk_copy (land + tid * LP, in + tid * a.in_tstride, (unsigned) L * 8u, bar);
-        }
-        else
-        {
-            const int mask = a.in_split_log >= 31 ? -1 : (1 << a.in_split_log) - 1;
-#pragma unroll
-            for (int i = 0; i < L / NT; ++i) // element row idx: C adjacent transforms = C contiguous values
-            {
-                const int idx = tid + i * NT;
-                const long long off = a.in_split_log >= 31 ? (long long) idx * a.in_estride
-                                                           : (long long) (idx >> a.in_split_log) * a.in_chunk_stride + (long long) (idx & mask) * a.in_estride;
-                bulk_copy (land + idx * C, in + off, (unsigned) C * 8u, bar);
-            }
-        }
-    };
-
-    long long t = (long long) blockIdx.x;
-    if (tid == 0)
-        mbar_init (bar);
-    __syncthreads();
-    if (t < tiles)
-        fetch (t);
-    for (unsigned it = 0; t < tiles; t += step, ++it)
-    {
-        const int bx = (int) (t / a.ntiles);
-        const int g = (int) (t - (long long) bx * a.ntiles);
-        const int ghi = g / a.gdiv, glo = g - ghi * a.gdiv;
-        float2* __restrict__ out = a.out + bx * a.out_bstride + ghi * a.out_g_hi + glo * a.out_g_lo;
-        const unsigned cT = a.tw_c_base + (unsigned) (glo * C + ltB);
-        float2 v[R];
-        mbar_wait (bar, it, TILE_BYTES);
-        if constexpr (LOAD_J_FAST)
-        {
-            const float2* p = land + ltA * LP + jA;
-#pragma unroll
-            for (int m = 0; m < R; ++m)
-                v[m] = lds2 (p + m * T);
-        }
-        else
-        {
-            const float2* p = land + tid; // element jB + m T of transform ltB sits at (jB + m T) C + ltB = tid + m T C
-#pragma unroll
-            for (int m = 0; m < R; ++m)
-                v[m] = lds2 (p + m * NT);
-        }
-        __syncthreads(); // the landing buffer is free again; nobody still reads the previous tile's exchange / twiddle rows
-        if (t + step < tiles)
-            fetch (t + step);
-        if (a.tw_mult != 0)
-        {
-            for (int i = tid; i - tid < R * C; i += NT) // i = m C + lt
-            {
-                if (i < R * C)
-                {
-                    const unsigned c = a.tw_c_base + (unsigned) (glo * C + i % C);
-                    sts2 (sTw + i, big_twiddle<DIR> (a, (unsigned) (i / C) * (unsigned) T * c * a.tw_mult));
-                }
-                else
-                    smem_skip();
-            }
-        } // visibility: every pass has at least one exchange barrier before the twiddle step
-        if constexpr (LOAD_J_FAST)
-        {
-            float2* sA = smem + ltA * RS;
-            stage_compute<G, DIR, 0> (v, jA, a.tw);
-            stage_scatter<G, 0> (v, jA, sA);
-            __syncthreads();
-            gather_natural<G, 0, R> (v, jB, sB);
-            Stages<G, DIR, 1>::run (v, jB, sB, a.tw, true);
-        }
-        else
-            Stages<G, DIR, 0>::run (v, jB, sB, a.tw, false);
-        tile_epilogue<LOGL, C, DIR> (a, v, ghi, glo, ltB, jB, cT, sTw, out);
-    }
-}
-
-template <int LOGL, int C, int DIR, bool LOAD_J_FAST>
-__global__ void __launch_bounds__ (TilePipeLaunch<LOGL, C>::THREADS, TilePipeLaunch<LOGL, C>::PER_SM) tile_pipe_kernel (const TileArgs a)
-{
-    tile_pipe_body<LOGL, C, DIR, LOAD_J_FAST> (a);
+    tile_body<LOGL, C, DIR, LOAD_J_FAST, UIO> (a);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -478,32 +412,6 @@ __global__ void __launch_bounds__ (256) real_pass_kernel (const RealPassArgs a)
         z[k] = make_float2 (ee.x - wd.y, ee.y + wd.x);
         z[M - k] = make_float2 (ee.x + wd.y, wd.x - ee.y);
     }
-}
-
-// Complex ordered <-> unordered permutation for large N (the single-kernel sizes fuse it; here it is one
-// streaming pass: 64-byte chunk of 8 (or 32-byte chunk of 4) bins per thread group).
-//   TO_UNORDERED : in = interleaved natural order, out = unordered layout ; else the inverse.
-template <bool TO_UNORDERED>
-__global__ void __launch_bounds__ (256) complex_reorder_kernel (const float* in, float* out, long long in_bstride, long long out_bstride, int logN, int logW)
-{
-    in += (long long) blockIdx.y * in_bstride;
-    out += (long long) blockIdx.y * out_bstride;
-    const long long bin = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-    if (bin >= (1LL << logN))
-        return;
-    const int logL = logN - logW;
-    const int r = (int) (bin >> logL);
-    const int rem = (int) (bin & ((1LL << logL) - 1));
-    const int b = rem >> logW, lane = rem & ((1 << logW) - 1);
-    const long long pos = ((((long long) (b << logW) + r) * 2) << logW) + lane;
-    if (TO_UNORDERED)
-    {
-        const float2 v = reinterpret_cast<const float2*> (in)[bin];
-        out[pos] = v.x;
-        out[pos + (1 << logW)] = v.y;
-    }
-    else
-        reinterpret_cast<float2*> (out)[bin] = make_float2 (in[pos], in[pos + (1 << logW)]);
 }
 
 // host: two-level table for W_N^e, e < N = 2^logN:  lo[e & mask] = W_N^(e & mask), hi[e >> lobits] = W_N^((e >> lobits) << lobits)

@@ -1,6 +1,8 @@
 // Host-side description of a multi-pass (four-step) transform: factorisation and per-pass tile
 // arguments.  Pure arithmetic, shared by the library (capi.cu) and the CPU emulator tests.
 #pragma once
+#include <vector>
+
 #include "large_kernels.cuh"
 
 namespace cfb
@@ -11,11 +13,6 @@ namespace cfb
 constexpr int kTileCMax = 16;
 inline int& tile_c_override() { static int v = 0; return v; }       // tuning hooks (0 = policy below)
 inline int& tile_c_jfast_override() { static int v = 0; return v; } // ... for the contiguous-row (last) pass only
-// tuning hook "tile_pipe": 1 = the persistent TMA-staged tile kernel (tile_pipe_kernel) where its buffers fit and the rows are
-// 16-byte aligned, 0 = tile_fft_kernel everywhere
-inline int& tile_pipe_mode() { static int v = 0; return v; }
-// tuning hook "tile_pf": L2 prefetch distance of the tile passes in tiles (0 = off)
-inline int& tile_pf_ahead() { static int v = 0; return v; }
 inline int tile_c (int logL, bool jfast = false)
 {
     const int ov = (jfast && tile_c_jfast_override() != 0) ? tile_c_jfast_override() : tile_c_override();
@@ -56,6 +53,8 @@ struct TilePass
     int C;             // transforms per tile (8 or 16)
     int logL;          // transform length of this pass
     bool load_j_fast;  // contiguous-row pass (the last one)
+    int uio;           // 0 natural order, 1 unordered input (first pass, inverse), 2 unordered output (last pass, forward)
+    int which;         // 0 = pass A (length L1), 1 = pass B (L2), 2 = pass C (L3)
     TileArgs args;     // in / out / twiddle pointers are filled in by the caller
 };
 
@@ -83,11 +82,13 @@ inline int build_tile_passes (int n, const LargeFactors& f, TilePass (&p)[3], un
         a.args.batch = 1;
         a.args.in_split_log = 31;
         a.args.peer_row_log = -1;
+        a.args.logN = n;
     }
     if (f.l2 != 0)
     {   // pass B: for every row k1, columns of its [L2][L3] view
         TilePass& b = p[np++];
         b = {};
+        b.which = 1;
         b.logL = f.l2;
         b.C = tile_c (f.l2);
         const int kTileC = b.C;
@@ -102,10 +103,12 @@ inline int build_tile_passes (int n, const LargeFactors& f, TilePass (&p)[3], un
         b.args.batch = 1;
         b.args.in_split_log = 31;
         b.args.peer_row_log = -1;
+        b.args.logN = n;
     }
     {   // pass C: contiguous rows (k1, k2), written transposed to k1 + L1 (k2 + L2 k3)
         TilePass& c = p[np++];
         c = {};
+        c.which = 2;
         c.logL = f.l3;
         c.C = tile_c (f.l3, true);
         const int kTileC = c.C;
@@ -124,6 +127,7 @@ inline int build_tile_passes (int n, const LargeFactors& f, TilePass (&p)[3], un
         c.args.batch = 1;
         c.args.in_split_log = 31;
         c.args.peer_row_log = -1;
+        c.args.logN = n;
     }
     return np;
 }
@@ -205,6 +209,167 @@ inline bool build_dist_phase (int n, const LargeFactors& f, int phase, int rank,
         p.args.tw_mult = 0;
     }
     return true;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// L2-chunked schedules.  B200 has 126 MB of L2: instead of running every pass over the whole array (each pass = one
+// HBM read + one HBM write of the array), consecutive passes are run back to back on CHUNKS whose intermediate lives in
+// a small ring buffer that stays L2-resident:
+//   two-pass plans   (2^15 .. 2^20 points, batched): chunk = a few whole transforms;  A: src -> ring, C: ring -> dst
+//                     => one HBM read + one HBM write per transform instead of two of each
+//   three-pass plans (2^21 .. 2^28 points): pass A over the whole array (src -> s1), then chunks of k1-rows:
+//                     B: s1 rows -> ring, C: ring -> dst   => two HBM reads + two writes instead of three of each
+// (a chunk of k1-rows is the smallest unit on which B and C compose: pass C needs every column group of its C adjacent
+// rows finished).  Chunks alternate over `lanes` helper streams, each with its own ring slot, so that the B of one chunk
+// overlaps the C of the previous one and launch tails are filled; ring accesses carry an evict_last L2 policy, the
+// HBM-facing streams evict_first.  The reference does all of this through one work buffer in cache-sized FFTPACK passes
+// (/root/reference/simd/chowdsp_fft_impl_avx.cpp:430-490, :1848-1935); here "cache-sized" means L2-sized.
+// ---------------------------------------------------------------------------------------------
+struct LargeLaunch
+{
+    TilePass pass;
+    int lane; // helper stream / ring slot index; -1 = the caller's stream, before the fork
+};
+
+struct LargeBuffers
+{
+    const float2* src;
+    float2* dst;
+    long long src_bs, dst_bs; // float2 between transforms of the batch (src / dst)
+    float2* s1;               // full-size scratch, batch * 2^n float2 (classic schedule and pass A of chunked three-pass plans)
+    float2* ring;             // lanes * ring_lane_elems float2 (chunked schedules), else nullptr
+    long long ring_lane_elems;
+};
+
+// rows of pass B / C per chunk (three-pass plans): a multiple of the last pass's tile width, at most L1
+inline long long chunk_rows (int n, const LargeFactors& f, int c_last, long long chunk_elems)
+{
+    const long long L1 = 1LL << f.l1, row = 1LL << (n - f.l1);
+    long long rows = chunk_elems / row;
+    rows -= rows % c_last;
+    if (rows < c_last)
+        rows = c_last;
+    return rows > L1 ? L1 : rows;
+}
+// elements one ring slot needs for chunk size `chunk_elems` (0 = classic schedule, no ring)
+inline long long ring_elems_needed (int n, const LargeFactors& f, int batch, long long chunk_elems)
+{
+    if (chunk_elems <= 0)
+        return 0;
+    const long long N = 1LL << n;
+    if (f.l2 == 0)
+    {
+        long long k = chunk_elems / N;
+        k = k < 1 ? 1 : (k > batch ? batch : k);
+        return k * N;
+    }
+    return chunk_rows (n, f, tile_c (f.l3, true), chunk_elems) * (N >> f.l1);
+}
+
+// uio_in / uio_out: the transform reads / writes the unordered complex layout (logW lanes) -- folded into the first / last pass
+inline void build_large_schedule (int n, const LargeFactors& f, int batch, const LargeBuffers& bufs, unsigned tw_scale, bool uio_in, bool uio_out, int logW,
+                                  long long chunk_elems, int lanes, bool policies, std::vector<LargeLaunch>& out)
+{
+    TilePass p[3];
+    const int np = build_tile_passes (n, f, p, tw_scale);
+    const long long N = 1LL << n;
+    if (uio_in)
+    {
+        p[0].uio = 1;
+        p[0].args.unord_logW = logW;
+    }
+    if (uio_out)
+    {
+        p[np - 1].uio = 2;
+        p[np - 1].args.unord_logW = logW;
+    }
+    out.clear();
+    if (chunk_elems <= 0 || bufs.ring == nullptr)
+    {
+        // classic: every pass over the whole batch, src -> s1 -> ... -> dst
+        for (int i = 0; i < np; ++i)
+        {
+            LargeLaunch l { p[i], -1 };
+            l.pass.args.in = i == 0 ? bufs.src : bufs.s1;
+            l.pass.args.in_bstride = i == 0 ? bufs.src_bs : N;
+            l.pass.args.out = i == np - 1 ? bufs.dst : bufs.s1;
+            l.pass.args.out_bstride = i == np - 1 ? bufs.dst_bs : N;
+            l.pass.args.batch = batch;
+            out.push_back (l);
+        }
+        return;
+    }
+    const int keep = policies ? POLICY_KEEP : POLICY_NORMAL, strm = policies ? POLICY_STREAM : POLICY_NORMAL;
+    if (np == 2)
+    {
+        const long long k = bufs.ring_lane_elems / N; // transforms per chunk
+        int lane = k >= batch ? -1 : 0;               // a single chunk stays on the caller's stream
+        for (long long b0 = 0; b0 < batch; b0 += k, lane = lane < 0 ? -1 : (lane + 1) % lanes)
+        {
+            const int nb = (int) (batch - b0 < k ? batch - b0 : k);
+            float2* slot = bufs.ring + (long long) (lane < 0 ? 0 : lane) * bufs.ring_lane_elems;
+            LargeLaunch a { p[0], lane }, c { p[1], lane };
+            a.pass.args.in = bufs.src + b0 * bufs.src_bs;
+            a.pass.args.in_bstride = bufs.src_bs;
+            a.pass.args.out = slot;
+            a.pass.args.out_bstride = N;
+            a.pass.args.batch = nb;
+            a.pass.args.in_policy = strm;
+            a.pass.args.out_policy = keep;
+            c.pass.args.in = slot;
+            c.pass.args.in_bstride = N;
+            c.pass.args.out = bufs.dst + b0 * bufs.dst_bs;
+            c.pass.args.out_bstride = bufs.dst_bs;
+            c.pass.args.batch = nb;
+            c.pass.args.in_policy = keep;
+            c.pass.args.out_policy = strm;
+            out.push_back (a);
+            out.push_back (c);
+        }
+        return;
+    }
+    // three passes: A over everything on the caller's stream, then (B, C) per chunk of k1-rows
+    {
+        LargeLaunch a { p[0], -1 };
+        a.pass.args.in = bufs.src;
+        a.pass.args.in_bstride = bufs.src_bs;
+        a.pass.args.out = bufs.s1;
+        a.pass.args.out_bstride = N;
+        a.pass.args.batch = batch;
+        out.push_back (a);
+    }
+    const long long L1 = 1LL << f.l1, L2 = 1LL << f.l2, S1 = N >> f.l1;
+    const long long rows = bufs.ring_lane_elems / S1;
+    int lane = (batch == 1 && rows >= L1) ? -1 : 0;
+    for (int b = 0; b < batch; ++b)
+        for (long long r0 = 0; r0 < L1; r0 += rows, lane = lane < 0 ? -1 : (lane + 1) % lanes)
+        {
+            const long long nr = L1 - r0 < rows ? L1 - r0 : rows;
+            float2* slot = bufs.ring + (long long) (lane < 0 ? 0 : lane) * bufs.ring_lane_elems;
+            LargeLaunch bb { p[1], lane }, cc { p[2], lane };
+            // B on rows [r0, r0 + nr): tile g -> (row g / gdiv, column group g % gdiv); the ring slot starts at row r0
+            bb.pass.args.in = bufs.s1 + (long long) b * N;
+            bb.pass.args.in_bin0 = r0 * S1;
+            bb.pass.args.out = slot;
+            bb.pass.args.out_bin0 = 0;
+            bb.pass.args.ntiles = (int) (nr * bb.pass.args.gdiv);
+            bb.pass.args.batch = 1;
+            bb.pass.args.in_policy = strm;
+            bb.pass.args.out_policy = keep;
+            // C on the same rows: tile g -> (k2 = g / gdiv', k1 group g % gdiv'), gdiv' = nr / C
+            cc.pass.args.in = slot;
+            cc.pass.args.in_bin0 = 0;
+            cc.pass.args.out = bufs.dst + (long long) b * bufs.dst_bs;
+            cc.pass.args.out_bin0 = r0;
+            cc.pass.args.gdiv = (int) (nr / cc.pass.C);
+            cc.pass.args.ntiles = (int) (cc.pass.args.gdiv * L2);
+            cc.pass.args.batch = 1;
+            cc.pass.args.in_policy = keep;
+            cc.pass.args.out_policy = strm;
+            out.push_back (bb);
+            out.push_back (cc);
+        }
 }
 
 inline int big_twiddle_lobits (int n) { return n < 28 ? (n + 1) / 2 : 14; }

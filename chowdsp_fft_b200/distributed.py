@@ -70,6 +70,13 @@ class DistributedFFT:
     def forward(self, x_cols: torch.Tensor, out_t: torch.Tensor, direction: int = api.FFT_FORWARD, stream=None):
         """x_cols: [L1, S1/G] complex as float32 pairs (flat ok); out_t: [S1, L1/G] complex (flat ok)."""
         st = stream or torch.cuda.current_stream()
+        # the collectives below order themselves against torch's CURRENT stream, so the phase kernels must run on it too:
+        # make `st` current for the whole body (a caller-supplied stream other than the current one would otherwise let
+        # phase 1 read buffers that peers are still writing)
+        with torch.cuda.stream(st):
+            return self._forward_on(st, x_cols, out_t, direction)
+
+    def _forward_on(self, st, x_cols: torch.Tensor, out_t: torch.Tensor, direction: int):
         if self.exchange == "peer":
             b = self.step & 1
             self.step += 1

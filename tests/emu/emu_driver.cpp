@@ -74,21 +74,21 @@ template <int LOGL, int C, int DIR>
 void emu_tile_launch_c (const TilePass& p)
 {
     using TL = TileLaunch<LOGL, C>;
-    using TP = TilePipeLaunch<LOGL, C>;
-    if constexpr (TP::FITS)
-        if (tile_pipe_mode() != 0) // persistent TMA-staged variant on (at most) 3 resident CTAs
-        {
-            const unsigned tiles = (unsigned) p.args.ntiles * (unsigned) p.args.batch, grid = tiles < 3u ? tiles : 3u;
-            if (p.load_j_fast)
-                emu::launch (tile_pipe_kernel<LOGL, C, DIR, true>, dim3 (grid), dim3 (TP::THREADS), (size_t) TP::SMEM_BYTES, p.args);
-            else
-                emu::launch (tile_pipe_kernel<LOGL, C, DIR, false>, dim3 (grid), dim3 (TP::THREADS), (size_t) TP::SMEM_BYTES, p.args);
-            return;
-        }
-    if (p.load_j_fast)
-        emu::launch (tile_fft_kernel<LOGL, C, DIR, true>, dim3 ((unsigned) p.args.ntiles), dim3 (TL::THREADS), (size_t) TL::SMEM_BYTES, p.args);
+    const dim3 grid ((unsigned) p.args.ntiles * (unsigned) p.args.batch), block (TL::THREADS);
+    if (p.uio == 1)
+    {
+        if constexpr (DIR > 0)
+            emu::launch (tile_fft_kernel<LOGL, C, +1, false, 1>, grid, block, (size_t) TL::SMEM_BYTES, p.args);
+    }
+    else if (p.uio == 2)
+    {
+        if constexpr (DIR < 0)
+            emu::launch (tile_fft_kernel<LOGL, C, -1, true, 2>, grid, block, (size_t) TL::SMEM_BYTES, p.args);
+    }
+    else if (p.load_j_fast)
+        emu::launch (tile_fft_kernel<LOGL, C, DIR, true, 0>, grid, block, (size_t) TL::SMEM_BYTES, p.args);
     else
-        emu::launch (tile_fft_kernel<LOGL, C, DIR, false>, dim3 ((unsigned) p.args.ntiles), dim3 (TL::THREADS), (size_t) TL::SMEM_BYTES, p.args);
+        emu::launch (tile_fft_kernel<LOGL, C, DIR, false, 0>, grid, block, (size_t) TL::SMEM_BYTES, p.args);
 }
 template <int LOGL, int DIR>
 void emu_tile_launch (const TilePass& p)
@@ -485,28 +485,30 @@ int emu_pconv (int logM, int logW, const float* in, long long in_stride, const f
 }
 
 void emu_set_tile_c (int c) { tile_c_override() = c; }
-void emu_set_tile_pipe (int v) { tile_pipe_mode() = v; }
 void emu_set_radix (int r) { g_emu_radix = r; }
 
-int emu_large_c2c (int n, int l1, int l2, int l3, int backward, const float* in, float* out, int log_conflicts, long* stats)
+// batch transforms of 2^n complex points through build_large_schedule: classic whole-array passes (chunk_elems = 0) or the
+// L2-chunked schedule (the lanes run one after the other here: this checks the chunk addressing, not the overlap);
+// unordered = the W = 2^logW lane layout on the spectrum side (output of forward, input of backward transforms)
+int emu_large_c2c (int n, int l1, int l2, int l3, int backward, int batch, int unordered_logW, long long chunk_elems, int lanes, const float* in, float* out, int log_conflicts, long* stats)
 {
     LargeFactors f;
     f.l1 = l1; f.l2 = l2; f.l3 = l3;
     if (l1 + l2 + l3 != n)
         return -2;
-    TilePass p[3];
-    const int np = build_tile_passes (n, f, p);
     const int lobits = big_twiddle_lobits (n);
     std::vector<float2> lo ((size_t) 1 << lobits), hi ((size_t) 1 << (n - lobits));
     fill_big_twiddles (lo.data(), hi.data(), n, lobits);
-    std::vector<float2> tmp ((size_t) 1 << n);
+    const long long N = 1LL << n;
+    std::vector<float2> s1 ((size_t) (N * batch));
+    const long long ring_lane = ring_elems_needed (n, f, batch, chunk_elems);
+    std::vector<float2> ring ((size_t) (ring_lane * lanes) + 1);
     std::vector<float2> tw[3];
-    emu::g_log_smem = log_conflicts != 0;
-    emu::g_stats = {};
-    for (int i = 0; i < np; ++i)
-    {
-        switch (p[i].logL)
+    const int logs[3] = { l1, l2, l3 };
+    for (int i = 0; i < 3; ++i)
+        switch (logs[i])
         {
+            case 0: break;
             case 6: fill_tw_for<6> (tw[i]); break;
             case 7: fill_tw_for<7> (tw[i]); break;
             case 8: fill_tw_for<8> (tw[i]); break;
@@ -514,13 +516,24 @@ int emu_large_c2c (int n, int l1, int l2, int l3, int backward, const float* in,
             case 10: fill_tw_for<10> (tw[i]); break;
             default: return -3;
         }
-        p[i].args.tw = tw[i].data();
-        p[i].args.tw_lo = lo.data();
-        p[i].args.tw_hi = hi.data();
-        p[i].args.tw_lobits = lobits;
-        p[i].args.in = i == 0 ? reinterpret_cast<const float2*> (in) : tmp.data();
-        p[i].args.out = i == np - 1 ? reinterpret_cast<float2*> (out) : tmp.data();
-        const int rc = backward ? emu_tile_dispatch<+1> (p[i]) : emu_tile_dispatch<-1> (p[i]);
+    emu::g_log_smem = log_conflicts != 0;
+    emu::g_stats = {};
+    LargeBuffers bufs {};
+    bufs.src = reinterpret_cast<const float2*> (in);
+    bufs.dst = reinterpret_cast<float2*> (out);
+    bufs.src_bs = bufs.dst_bs = N;
+    bufs.s1 = s1.data();
+    bufs.ring = chunk_elems > 0 ? ring.data() : nullptr;
+    bufs.ring_lane_elems = ring_lane;
+    std::vector<LargeLaunch> sched;
+    build_large_schedule (n, f, batch, bufs, 1u, unordered_logW != 0 && backward, unordered_logW != 0 && ! backward, unordered_logW, chunk_elems, lanes, true, sched);
+    for (auto& l : sched)
+    {
+        l.pass.args.tw = tw[l.pass.which].data();
+        l.pass.args.tw_lo = lo.data();
+        l.pass.args.tw_hi = hi.data();
+        l.pass.args.tw_lobits = lobits;
+        const int rc = backward ? emu_tile_dispatch<+1> (l.pass) : emu_tile_dispatch<-1> (l.pass);
         if (rc != 0)
             return rc;
     }
@@ -530,6 +543,7 @@ int emu_large_c2c (int n, int l1, int l2, int l3, int backward, const float* in,
         stats[1] = emu::g_stats.wavefronts;
         stats[2] = emu::g_stats.ideal;
         stats[3] = emu::g_stats.worst;
+        stats[4] = (long) sched.size();
     }
     return 0;
 }

@@ -231,29 +231,69 @@ def test_emulated_fused_partitioned_convolution(emu, oracle_mod, ref_lib, N, W):
         assert o.rel_l2(y, ref_y) < 2e-6
 
 
+def _emu_large(emu, n, l1, l2, l3, backward, x, batch=1, logw=0, chunk_elems=0, lanes=1, log_conflicts=0):
+    emu.emu_large_c2c.argtypes = [C.c_int] * 7 + [C.c_longlong, C.c_int, fp, fp, C.c_int, C.POINTER(C.c_long)]
+    out = np.zeros_like(x)
+    st = (C.c_long * 5)()
+    rc = emu.emu_large_c2c(n, l1, l2, l3, backward, batch, logw, chunk_elems, lanes, x.ctypes.data_as(fp), out.ctypes.data_as(fp), log_conflicts, st)
+    assert rc == 0
+    return out, list(st)
+
+
 @pytest.mark.parametrize("tile_c", [8, 16])
-@pytest.mark.parametrize("pipe", [0, 1])
 @pytest.mark.parametrize("n,l1,l2,l3", [(12, 6, 0, 6), (13, 6, 0, 7), (15, 7, 0, 8), (18, 6, 6, 6), (15, 9, 0, 6), (15, 6, 0, 9), (16, 10, 0, 6), (16, 6, 0, 10)])
-def test_emulated_multi_pass_transform(emu, n, l1, l2, l3, tile_c, pipe):
+def test_emulated_multi_pass_transform(emu, n, l1, l2, l3, tile_c):
     """Tile kernels + pass planning of the large-transform path (two- and three-pass four-step), with the
-    factorisation forced so that small sizes exercise it; both tile widths; bank-conflict free exchanges; both the
-    one-tile-per-CTA kernel and the persistent TMA-staged one (3 resident CTAs looping over the tiles)."""
-    emu.emu_large_c2c.argtypes = [C.c_int] * 5 + [fp, fp, C.c_int, C.POINTER(C.c_long)]
+    factorisation forced so that small sizes exercise it; both tile widths; bank-conflict free exchanges."""
     emu.emu_set_tile_c(tile_c)
-    emu.emu_set_tile_pipe(pipe)
     N = 1 << n
     rng = np.random.default_rng(n)
     x = rng.uniform(-1, 1, 2 * N).astype(np.float32)
     z = x[0::2].astype(np.float64) + 1j * x[1::2]
     for backward in ((0, 1) if n <= 13 else (0,)):
-        out = np.zeros_like(x)
-        st = (C.c_long * 4)()
-        assert emu.emu_large_c2c(n, l1, l2, l3, backward, x.ctypes.data_as(fp), out.ctypes.data_as(fp), int(n <= 16), st) == 0
+        out, st = _emu_large(emu, n, l1, l2, l3, backward, x, log_conflicts=int(n <= 16))
         ref = np.fft.ifft(z) * N if backward else np.fft.fft(z)
         got = out[0::2] + 1j * out[1::2]
         assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 4e-7
         if n <= 16:
             assert st[1] <= 1.15 * st[2] and st[3] <= 150, list(st)  # (nearly) conflict free
+    emu.emu_set_tile_c(0)
+
+
+@pytest.mark.parametrize("n,l1,l2,l3,batch,chunk_elems,lanes", [
+    (12, 6, 0, 6, 5, 2 << 12, 2),      # two-pass plan, chunks of 2 transforms (ragged last chunk), 2 ring slots
+    (13, 6, 0, 7, 3, 1 << 13, 3),      # one transform per chunk, 3 ring slots
+    (18, 6, 6, 6, 1, 16 << 12, 2),     # three-pass plan: A global, (B, C) on chunks of 16 k1-rows
+    (18, 6, 6, 6, 2, 24 << 12, 3),     # batch of 2, 24-row chunks (64 rows: ragged last chunk), 3 slots
+    (18, 6, 6, 6, 1, 1 << 20, 2),      # one chunk covers everything: stays on the caller's stream
+])
+@pytest.mark.parametrize("logw", [0, 3, 2])
+def test_emulated_l2_chunked_schedule(emu, oracle_mod, n, l1, l2, l3, batch, chunk_elems, lanes, logw):
+    """The L2-chunked schedules (large_plan.h: build_large_schedule) compute the same transforms as the classic
+    whole-array passes: chunk / ring-slot addressing of every launch, forward and backward, natural order and the
+    unordered layouts folded into the last pass's stores / the first pass's loads (bit-exact permutation of the
+    ordered result, positions from the oracle's closed form)."""
+    o = oracle_mod
+    N = 1 << n
+    rng = np.random.default_rng(n + batch)
+    x = rng.uniform(-1, 1, (batch, 2 * N)).astype(np.float32)
+    z = x[:, 0::2].astype(np.float64) + 1j * x[:, 1::2]
+    W = 1 << logw
+    perm = o.np_unordered_map(N, True, W) if logw else None  # perm[unordered float slot] = ordered float slot
+    # forward
+    classic, st0 = _emu_large(emu, n, l1, l2, l3, 0, x.reshape(-1), batch)
+    got, st1 = _emu_large(emu, n, l1, l2, l3, 0, x.reshape(-1), batch, logw, chunk_elems, lanes)
+    classic, got = classic.reshape(batch, 2 * N), got.reshape(batch, 2 * N)
+    ref = np.fft.fft(z)
+    assert np.linalg.norm((classic[:, 0::2] + 1j * classic[:, 1::2]) - ref) / np.linalg.norm(ref) < 4e-7
+    want = classic[:, perm] if logw else classic
+    assert np.array_equal(got, want)
+    assert st1[4] >= st0[4]
+    # backward (unordered INPUT)
+    xin = x[:, perm] if logw else x
+    classic_b, _ = _emu_large(emu, n, l1, l2, l3, 1, x.reshape(-1), batch)
+    got_b, _ = _emu_large(emu, n, l1, l2, l3, 1, np.ascontiguousarray(xin).reshape(-1), batch, logw, chunk_elems, lanes)
+    assert np.array_equal(got_b, classic_b)
 
 
 @pytest.mark.parametrize("N,hop,frames,ordered,W", [(2048, 512, 7, True, 8), (2048, 512, 4, False, 8), (2048, 2048, 5, True, 8),
