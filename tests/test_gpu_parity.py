@@ -908,3 +908,144 @@ def test_config5_single_gpu_point(cf, oracle_mod):
     cf.fft_transform_batched(s, y, z, 1, 2 * N, 2 * N, cf.FFT_BACKWARD, True)
     assert float((z / N - x).double().norm() / x.double().norm()) < o.parity_tol(N)
     cf.fft_destroy_setup(s)
+
+
+def _tuned(cf, **kv):
+    for k, v in kv.items():
+        cf.set_tuning(k, v)
+
+
+@pytest.mark.parametrize("lanes,policy", [(1, 1), (3, 1), (2, 0)])
+def test_l2_chunked_schedules_equal_whole_array_passes(cf, oracle_mod, lanes, policy):
+    """The L2-chunked schedules (csrc/large_plan.h: build_large_schedule) run the SAME tile kernels on
+    chunks whose intermediate stays in a ring buffer: results must be bit-identical to the classic whole-array passes
+    (tuning l2_chunk_mb = 0), which in turn match the oracle.  Small chunk sizes force many chunks, ragged last chunks and
+    ring-slot reuse at sizes the oracle finishes quickly.  Complex ordered / unordered (folded into the first / last
+    pass), real forward / backward (split / merge step inside the chunk for two-pass plans)."""
+    o = oracle_mod
+    rng = np.random.default_rng(5)
+    try:
+        for lg, is_c, batch, mb in [(16, True, 7, 1), (15, True, 9, 1), (17, False, 6, 1), (22, True, 1, 2), (22, True, 2, 4), (22, False, 2, 2), (21, True, 3, 1)]:
+            N = 1 << lg
+            nfl = 2 * N if is_c else N
+            x = rng.uniform(-1, 1, (batch, nfl)).astype(np.float32)
+            for ordered in (True, False):
+                _tuned(cf, l2_chunk_mb=0)
+                classic_f = gpu_transform(cf, x, N, is_c, True, False, ordered)
+                want_f = o.np_transform(x[:1], N, is_c, 8, False, ordered)
+                assert o.rel_l2(classic_f[:1], want_f) < o.parity_tol(N)
+                classic_b = gpu_transform(cf, classic_f, N, is_c, True, True, ordered)
+                _tuned(cf, l2_chunk_mb=mb, l2_lanes=lanes, l2_policy=policy)
+                got_f = gpu_transform(cf, x, N, is_c, True, False, ordered)
+                assert "L2-chunked" in cf.last_kernel(), cf.last_kernel()
+                assert np.array_equal(got_f, classic_f), (lg, is_c, batch, ordered, "forward")
+                got_b = gpu_transform(cf, classic_f, N, is_c, True, True, ordered)
+                assert np.array_equal(got_b, classic_b), (lg, is_c, batch, ordered, "backward")
+                assert o.rel_l2(got_b / N, x) < o.parity_tol(N)
+    finally:
+        _tuned(cf, l2_chunk_mb=-1, l2_lanes=-1, l2_policy=-1)
+
+
+def sampled_dft(torch, x2, ks):
+    """float64 DFT bins X[k], k in ks, of the complex signal x2 ([N, 2] float32 on the device); phases from exact int64
+    arithmetic, chunked so that the temporaries stay small."""
+    N = x2.shape[0]
+    out = []
+    step = 1 << 24
+    for k in ks:
+        re = im = 0.0
+        for n0 in range(0, N, step):
+            n = torch.arange(n0, min(N, n0 + step), device=x2.device, dtype=torch.int64)
+            ang = ((n * int(k)) % N).double() * (-2.0 * np.pi / N)
+            c, s = torch.cos(ang), torch.sin(ang)
+            xr, xi = x2[n0:n0 + step, 0].double(), x2[n0:n0 + step, 1].double()
+            re += float((xr * c - xi * s).sum())
+            im += float((xr * s + xi * c).sum())
+        out.append(complex(re, im))
+    return np.array(out)
+
+
+def test_config5_full_size_single_gpu(cf, oracle_mod):
+    """BASELINE configs[4] at its STATED size on one GPU: C2C N = 2^28 (2 GiB in, 2 GiB out).  The oracle cannot hold this in
+    seconds, so parity is pinned by size-independent properties plus sampled bins: 48 bins (spread over every k1 / k2 / k3
+    digit of the three-pass plan, first and last bins included) against a float64 DFT with exact integer phases, Parseval,
+    forward -> backward round trip, and unordered output == the closed-form permutation of the ordered output."""
+    o = oracle_mod
+    free, _ = torch.cuda.mem_get_info()
+    if free < 14 * (1 << 30):
+        pytest.skip("needs 14 GiB of free device memory")
+    lg = 28
+    N = 1 << lg
+    s = cf.fft_new_setup(N, cf.FFT_COMPLEX)
+    g = torch.Generator(device="cuda").manual_seed(42)
+    x = torch.rand(2 * N, device="cuda", generator=g) * 2 - 1
+    y = torch.empty_like(x)
+    cf.fft_transform_batched(s, x, y, 1, 2 * N, 2 * N, cf.FFT_FORWARD, True)
+    torch.cuda.synchronize()
+    rng = np.random.default_rng(28)
+    ks = sorted(set([0, 1, N - 1, N // 2, (1 << 9) - 1, 1 << 9, (1 << 18) + 5] + [int(k) for k in rng.integers(0, N, 41)]))
+    want = sampled_dft(torch, x.view(-1, 2), ks)
+    yk = host(y.view(-1, 2)[torch.tensor(ks, device="cuda")])
+    got = yk[:, 0].astype(np.float64) + 1j * yk[:, 1]
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < o.parity_tol(N)
+    ex, ey = float((x.double() ** 2).sum()), float((y.double() ** 2).sum())
+    assert abs(ey - N * ex) / (N * ex) < 1e-6
+    z = torch.empty_like(x)
+    cf.fft_transform_batched(s, y, z, 1, 2 * N, 2 * N, cf.FFT_BACKWARD, True)
+    assert float((z / N - x).double().norm() / x.double().norm()) < o.parity_tol(N)
+    # unordered output: slot u holds ordered slot map[u]; checked on a slice of the closed form (2^20 slots) to stay in seconds
+    cf.fft_transform_batched(s, x, z, 1, 2 * N, 2 * N, cf.FFT_FORWARD, False)
+    torch.cuda.synchronize()
+    W = 8
+    u = torch.from_numpy(rng.integers(0, 2 * N, 1 << 20)).cuda()
+    vec, lane = u // W, u % W           # unordered vector index, lane
+    kk, is_im = vec // 2, vec % 2
+    b, r = kk // W, kk % W
+    bins = r * (N // W) + b * W + lane  # SURVEY.md §8a-L, complex
+    assert torch.equal(z[u], y[2 * bins + is_im])
+    cf.fft_destroy_setup(s)
+
+
+def test_misaligned_operands_are_rejected_not_faulted(cf):
+    """every entry point validates base-pointer and stride alignment on the host (FFT_B200_EINVAL) instead of
+    letting a vector access fault on the device (cudaErrorMisalignedAddress is sticky and would poison the context)."""
+    N = 1024
+    s = cf.fft_new_setup(N, cf.FFT_REAL)
+    buf = torch.zeros(8 * N + 64, device="cuda")
+    a, b, ab = buf[0:N], buf[N:2 * N], buf[2 * N:3 * N]
+    cf.fft_convolve_unordered_batched(s, a, b, ab, 1, N, N, N, 1.0)  # aligned: fine
+    for bad in (buf[1:N + 1], buf[2:N + 2]):
+        with pytest.raises(cf.FFTError):
+            cf.fft_convolve_unordered_batched(s, bad, b, ab, 1, N, N, N, 1.0)
+        with pytest.raises(cf.FFTError):
+            cf.fft_convolve_unordered_batched(s, a, b, bad, 1, N, N, N, 1.0)
+        with pytest.raises(cf.FFTError):
+            cf.fft_accumulate_batched(s, a, bad, ab, N)
+    with pytest.raises(cf.FFTError):  # odd stride between spectra
+        cf.fft_convolve_unordered_batched(s, a, b, ab, 2, N + 2, N, N, 1.0)
+    with pytest.raises(cf.FFTError):  # window not 8-byte aligned
+        cf.fft_istft_overlap_add(s, buf[0:4 * N], buf[4 * N:8 * N], 1, 4, 4 * N, N, 4 * N, N // 2, buf[1:N + 1], 1.0, True)
+    with pytest.raises(cf.FFTError):  # unordered spectra need 16-byte frames
+        cf.fft_istft_overlap_add(s, buf[2:4 * N + 2], buf[4 * N:8 * N], 1, 4, 4 * N, N, 4 * N, N // 2, None, 1.0, False)
+    with pytest.raises(cf.FFTError):
+        cf.fft_juce_real_inverse_batched(s, buf[1:2 * N + 3], 1, N + 2)
+    # partitioned convolution: fdl / ir 16-byte aligned, windows / output 8-byte aligned
+    P = 2
+    win, ir, fdl, out = buf[0:N], torch.zeros(P * N + 8, device="cuda"), torch.zeros(P * N + 8, device="cuda"), torch.zeros(N, device="cuda")
+    cf.fft_partitioned_convolve_step(s, win, N, ir[:P * N], 0, fdl[:P * N], P * N, out, N // 2, 1, P, 0, 1.0)
+    with pytest.raises(cf.FFTError):
+        cf.fft_partitioned_convolve_step(s, win, N, ir[2:P * N + 2], 0, fdl[:P * N], P * N, out, N // 2, 1, P, 0, 1.0)
+    with pytest.raises(cf.FFTError):
+        cf.fft_partitioned_convolve_step(s, win, N, ir[:P * N], 0, fdl[1:P * N + 1], P * N, out, N // 2, 1, P, 0, 1.0)
+    with pytest.raises(cf.FFTError):
+        cf.fft_partitioned_convolve_step(s, buf[1:N + 1], N, ir[:P * N], 0, fdl[:P * N], P * N, out, N // 2, 1, P, 0, 1.0)
+    cf.fft_destroy_setup(s)
+    # multi-pass and mixed-radix plans: 8-byte aligned bases
+    for n in (1 << 16, 96):
+        s = cf.fft_new_setup(n, cf.FFT_COMPLEX)
+        big = torch.zeros(4 * n + 8, device="cuda")
+        with pytest.raises(cf.FFTError):
+            cf.fft_transform_batched(s, big[1:2 * n + 1], big[2 * n + 2:4 * n + 2], 1, 2 * n, 2 * n, cf.FFT_FORWARD, True)
+        cf.fft_destroy_setup(s)
+    torch.cuda.synchronize()  # the context is still healthy
+    assert float(buf.sum()) == 0.0

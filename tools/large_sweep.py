@@ -19,7 +19,7 @@ for kv in filter(None, os.environ.get("CFB_TUNE", "").split(",")):
     print("tune:", k, v)
 sizes = [int(a) for a in args] or [15, 16, 18, 20, 22, 24, 26, 28]
 st = torch.cuda.current_stream()
-for is_c in (True, False):
+for is_c in ((True,) if "--complex-only" in sys.argv else (True, False)):
     for lg in sizes:
         N = 1 << lg
         nfl = 2 * N if is_c else N

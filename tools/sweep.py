@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--json", default="")
     ap.add_argument("--radix32-mask", type=int, default=-1)
     ap.add_argument("--kinds", default="c,r")
+    ap.add_argument("--layouts", default="ordered,w8,w4", help="ordered, w8 (8-lane unordered, AVX handle), w4 (4-lane unordered, SSE handle)")
     ap.add_argument("--tune", action="append", default=[], metavar="KEY=VALUE")
     args = ap.parse_args()
     try:
@@ -41,16 +42,27 @@ def main():
     stream = torch.cuda.current_stream()
     rows = []
     sizes = [int(s) for s in args.sizes.split(",")] if args.sizes else [1 << l for l in range(5, 16)]
+    layouts = args.layouts.split(",")
     for is_c in [k == "c" for k in args.kinds.split(",")]:
         for N in sizes:
             nfl = 2 * N if is_c else N
-            try:
-                s = cf.fft_new_setup(N, cf.FFT_COMPLEX if is_c else cf.FFT_REAL, True)
-            except cf.FFTError:
+            plans = {}
+            for avx in (True, False):
+                try:
+                    plans[avx] = cf.fft_new_setup(N, cf.FFT_COMPLEX if is_c else cf.FFT_REAL, avx)
+                except cf.FFTError:
+                    pass
+            if True not in plans:
                 continue
+            w8 = cf.fft_simd_width_bytes(plans[True]) == 32
             batch = total_floats // nfl
             for direction in (cf.FFT_FORWARD, cf.FFT_BACKWARD):
-                for ordered in (True, False):
+                for layout in layouts:
+                    if layout == "w8" and not w8:
+                        continue
+                    s = plans[False] if layout == "w4" else plans[True]
+                    ordered = layout == "ordered"
+
                     def step():
                         cf.fft_transform_batched(s, x, y, batch, nfl, nfl, direction, ordered, stream)
                     for _ in range(3):
@@ -66,11 +78,12 @@ def main():
                     gbs = batch * nfl * 8 / (ms * 1e-3) / 1e9
                     gfl = batch * (5.0 if is_c else 2.5) * N * math.log2(N) / (ms * 1e-3) / 1e9
                     row = dict(kind=("C2C" if is_c else ("R2C" if direction == 0 else "C2R")), N=N,
-                               dir="fwd" if direction == 0 else "bwd", layout="ordered" if ordered else "unordered",
-                               batch=batch, ms=ms, gbs=gbs, frac=gbs / peak, gflops=gfl)
+                               dir="fwd" if direction == 0 else "bwd", layout=layout,
+                               batch=batch, ms=ms, gbs=gbs, frac=gbs / peak, frac_nominal=gbs / 8000.0, gflops=gfl, kernel=cf.last_kernel())
                     rows.append(row)
-                    print(f"{row['kind']:4s} N={N:6d} {row['dir']} {row['layout']:9s} batch={batch:8d} {ms:8.4f} ms {gbs:8.1f} GB/s  frac={gbs/peak:5.3f}  {gfl/1e3:6.2f} TFLOP/s", flush=True)
-            cf.fft_destroy_setup(s)
+                    print(f"{row['kind']:4s} N={N:7d} {row['dir']} {row['layout']:7s} batch={batch:8d} {ms:8.4f} ms {gbs:8.1f} GB/s  frac={gbs/peak:5.3f} of measured, {gbs/8000.0:5.3f} of 8 TB/s  {gfl/1e3:6.2f} TFLOP/s  {row['kernel']}", flush=True)
+            for s in plans.values():
+                cf.fft_destroy_setup(s)
     if args.json:
         json.dump({"peak_gbs": peak, "rows": rows}, open(args.json, "w"), indent=1)
 
