@@ -70,6 +70,15 @@ def lib() -> C.CDLL:
         "fft_dist_ipc_open": (vp, [vp]),
         "fft_dist_ipc_close": (None, [vp]),
         "fft_large_factors": (i, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "fft_dist_create": (i, [vp, i, i, C.POINTER(vp)]),
+        "fft_dist_blob_bytes": (C.c_size_t, []),
+        "fft_dist_export": (i, [vp, vp]),
+        "fft_dist_connect": (i, [vp, vp]),
+        "fft_dist_transform": (i, [vp, vp, vp, i, i, i, vp]),
+        "fft_dist_natural_buffer": (vp, [vp]),
+        "fft_dist_status": (i, [vp]),
+        "fft_dist_phase_ms": (i, [vp, _fp]),
+        "fft_dist_destroy": (i, [vp]),
         "fft_b200_set_tuning": (i, [C.c_char_p, i]),
         "fft_b200_last_error": (C.c_char_p, []),
         "fft_b200_last_kernel": (C.c_char_p, []),
@@ -89,6 +98,6 @@ EXPORTED = (
     "fft_bytes_required", "fft_new_setup", "fft_new_setup_preallocated", "fft_destroy_setup",
     "fft_simd_width_bytes", "fft_transform", "fft_transform_unordered", "fft_convolve_unordered",
     "fft_accumulate", "aligned_malloc", "aligned_free", "fft_transform_batched", "fft_transform_strided", "fft_stft_forward", "fft_istft_overlap_add", "fft_juce_perform_batched", "fft_juce_real_forward_batched", "fft_juce_real_inverse_batched",
-    "fft_convolve_unordered_batched", "fft_accumulate_batched", "fft_partitioned_convolve_step", "fft_dist_phase", "fft_dist_phase0_peer", "fft_dist_alloc", "fft_dist_free", "fft_dist_ipc_export", "fft_dist_ipc_open", "fft_dist_ipc_close", "fft_large_factors", "fft_b200_set_tuning", "fft_b200_last_error", "fft_b200_last_kernel", "fft_b200_clear_error",
+    "fft_convolve_unordered_batched", "fft_accumulate_batched", "fft_partitioned_convolve_step", "fft_dist_phase", "fft_dist_phase0_peer", "fft_dist_alloc", "fft_dist_free", "fft_dist_ipc_export", "fft_dist_ipc_open", "fft_dist_ipc_close", "fft_dist_create", "fft_dist_blob_bytes", "fft_dist_export", "fft_dist_connect", "fft_dist_transform", "fft_dist_natural_buffer", "fft_dist_status", "fft_dist_phase_ms", "fft_dist_destroy", "fft_large_factors", "fft_b200_set_tuning", "fft_b200_last_error", "fft_b200_last_kernel", "fft_b200_clear_error",
     "fft_b200_launch_count", "fft_b200_device_available",
 )

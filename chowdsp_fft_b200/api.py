@@ -248,3 +248,46 @@ def fft_dist_ipc_open(handle: bytes) -> int:
 
 def fft_dist_ipc_close(p: int) -> None:
     lib().fft_dist_ipc_close(p)
+
+
+# ---- the distributed transform as one call per rank (chowdsp_fft_b200.h: fft_dist_create ... fft_dist_destroy) ----
+def fft_dist_create(setup: int, rank: int, world: int) -> int:
+    ctx = C.c_void_p()
+    _check(lib().fft_dist_create(setup, rank, world, C.byref(ctx)))
+    return ctx.value
+
+
+def fft_dist_blob_bytes() -> int:
+    return int(lib().fft_dist_blob_bytes())
+
+
+def fft_dist_export(ctx: int) -> bytes:
+    buf = C.create_string_buffer(fft_dist_blob_bytes())
+    _check(lib().fft_dist_export(ctx, buf))
+    return buf.raw
+
+
+def fft_dist_connect(ctx: int, blobs: bytes | None) -> None:
+    _check(lib().fft_dist_connect(ctx, C.create_string_buffer(blobs, len(blobs)) if blobs else None))
+
+
+def fft_dist_transform(ctx: int, input, output, direction: int = FFT_FORWARD, natural_order: bool = False, timed: bool = False, stream=None) -> None:
+    _check(lib().fft_dist_transform(ctx, _addr(input), _addr(output), direction, int(natural_order), int(timed), _stream(stream)))
+
+
+def fft_dist_natural_buffer(ctx: int) -> int:
+    return lib().fft_dist_natural_buffer(ctx)
+
+
+def fft_dist_status(ctx: int) -> None:
+    _check(lib().fft_dist_status(ctx))
+
+
+def fft_dist_phase_ms(ctx: int) -> list[float]:
+    ms = (C.c_float * 4)()
+    _check(lib().fft_dist_phase_ms(ctx, ms))
+    return [float(v) for v in ms]
+
+
+def fft_dist_destroy(ctx: int) -> None:
+    lib().fft_dist_destroy(ctx)

@@ -480,6 +480,12 @@ int device_sm_count()
     return c_sms;
 }
 int g_pf_ahead = 0;        // tuning hook "pf_ahead": L2 prefetch distance of the single-kernel transforms, in CTAs
+// tuning hook "cluster": 1 = complex transforms of 2^15 .. 2^17 points run in ONE pass on a thread-block cluster
+// (cluster_kernels.cuh) where the batch layout allows, 0 = always the multi-pass tile path; "cluster_min_batch": batches
+// smaller than this stay with the tile path (a cluster kernel runs one transform per cluster: a single transform would
+// occupy 4 .. 16 of the 148 SMs)
+constexpr int kClusterDefault = 1, kClusterMinBatchDefault = 8;
+int g_cluster = kClusterDefault, g_cluster_min_batch = kClusterMinBatchDefault;
 
 constexpr size_t kZeroCopyBytes = 256 * 1024;     // pinned buffers up to this size are used in place
 constexpr size_t kChunkBytes = 32ull * 1024 * 1024; // host staging granularity per lane
@@ -508,7 +514,7 @@ bool misaligned (const void* ptr, unsigned align_bytes, long long s0 = 0, long l
 // ------------------------------------------------------------------------------------------------
 // tuning hooks "l2_chunk_mb" (MiB of intermediate per chunk of the L2-chunked schedules, 0 = classic whole-array passes),
 // "l2_lanes" (helper streams / ring slots, 1..4) and "l2_policy" (1 = evict_last / evict_first hints on ring / stream accesses)
-constexpr int kL2ChunkMbDefault = 16, kL2LanesDefault = 2, kL2PolicyDefault = 1;
+constexpr int kL2ChunkMbDefault = 16, kL2LanesDefault = 3, kL2PolicyDefault = 1;
 int g_l2_chunk_mb = kL2ChunkMbDefault, g_l2_lanes = kL2LanesDefault, g_l2_policy = kL2PolicyDefault;
 constexpr int kMaxLanes = 4;
 
@@ -562,6 +568,49 @@ struct ForkJoin
 };
 thread_local ForkJoin t_forkjoin;
 
+
+// fork / join bookkeeping of one schedule run: lane -1 is the caller's stream; the first use of a helper lane makes it
+// wait for everything enqueued on the caller's stream so far, join() makes the caller's stream wait for every used lane
+struct LaneSet
+{
+    ForkJoin& fj;
+    cudaStream_t main;
+    bool forked = false;
+    bool used[kMaxLanes] = { false, false, false, false };
+    LaneSet (ForkJoin& f, cudaStream_t s) : fj (f), main (s) {}
+    cudaStream_t stream_of (int lane, cudaError_t& e)
+    {
+        if (lane < 0)
+            return main;
+        if (! forked)
+        {
+            if (e == cudaSuccess)
+                e = cudaEventRecord (fj.fork, main);
+            forked = true;
+        }
+        if (! used[lane])
+        {
+            if (e == cudaSuccess)
+                e = cudaStreamWaitEvent (fj.lane[lane], fj.fork, 0);
+            used[lane] = true;
+        }
+        return fj.lane[lane];
+    }
+    void join (cudaError_t& e)
+    {
+        for (int l = 0; l < kMaxLanes; ++l)
+            if (used[l])
+            {
+                if (e == cudaSuccess)
+                    e = cudaEventRecord (fj.join[l], fj.lane[l]);
+                if (e == cudaSuccess)
+                    e = cudaStreamWaitEvent (main, fj.join[l], 0);
+                used[l] = false;
+            }
+        forked = false;
+    }
+};
+
 struct LargeTables
 {
     BigTables bt;
@@ -581,7 +630,13 @@ int preload_large (Plan* p)
     int dev = 0;
     CFB_CUDA (cudaGetDevice (&dev));
     LargeTables lt;
-    return large_tables (p, dev, choose_factors (p->logM), lt);
+    int rc = large_tables (p, dev, choose_factors (p->logM), lt);
+    if (rc == 0 && p->is_complex && has_cluster (p->logM))
+    {
+        Tables st; // the cluster kernel's local 512-point stage table
+        rc = get_tables (dev, 9, false, st, 32);
+    }
+    return rc;
 }
 
 // `batch` transforms larger than a CTA: 2 or 3 tile passes (+ a split / merge pass for real plans) through stream-ordered
@@ -620,8 +675,13 @@ int enqueue_large (Plan* p, const float* in, float* out, int batch, long long in
     const bool real = ! p->is_complex;
     // Chunked schedule?  Two-pass plans: only when the batch does not fit in L2 anyway (a single 2^15..2^20-point transform is
     // L2-resident between its passes as it is).  Three-pass plans: always.
-    long long chunk_elems = (long long) g_l2_chunk_mb * (1 << 20) / 8;
+    // Measured on B200 (profiles/r02_l2_chunked.txt): +4..8 % up to 2^24 points with 16 MiB chunks on 3 lanes, nothing at
+    // 2^26 and -6 % at 2^28 (the chunk unit of 8 k1-rows is 32 MiB there, beyond what L2 keeps for all SMs: 32..40 MB),
+    // so the largest transforms keep whole-array passes unless the hook says otherwise (l2_chunk_mb < 0: force chunking)
+    long long chunk_elems = (long long) (g_l2_chunk_mb < 0 ? -g_l2_chunk_mb : g_l2_chunk_mb) * (1 << 20) / 8;
     if (np == 2 && (long long) batch * npts <= 2 * chunk_elems)
+        chunk_elems = 0;
+    if (n > 24 && g_l2_chunk_mb > 0)
         chunk_elems = 0;
     const int lanes = g_l2_lanes < 1 ? 1 : (g_l2_lanes > kMaxLanes ? kMaxLanes : g_l2_lanes);
     // full-size scratch is allocated per super-chunk of the batch (<= 512 MiB per buffer)
@@ -662,36 +722,9 @@ int enqueue_large (Plan* p, const float* in, float* out, int batch, long long in
         bufs.s1 = s1;
         bufs.ring = ring;
         bufs.ring_lane_elems = ring_lane;
-        bool forked = false;
-        bool lane_used[kMaxLanes] = { false, false, false, false };
-        auto stream_of = [&] (int lane) -> cudaStream_t
-        {
-            if (lane < 0)
-                return stream;
-            if (! forked)
-            {
-                e = cudaEventRecord (fj.fork, stream);
-                forked = true;
-            }
-            if (! lane_used[lane])
-            {
-                if (e == cudaSuccess)
-                    e = cudaStreamWaitEvent (fj.lane[lane], fj.fork, 0);
-                lane_used[lane] = true;
-            }
-            return fj.lane[lane];
-        };
-        auto join = [&]
-        {
-            for (int l = 0; l < kMaxLanes; ++l)
-                if (lane_used[l])
-                {
-                    if (e == cudaSuccess)
-                        e = cudaEventRecord (fj.join[l], fj.lane[l]);
-                    if (e == cudaSuccess)
-                        e = cudaStreamWaitEvent (stream, fj.join[l], 0);
-                }
-        };
+        LaneSet ls (fj, stream);
+        auto stream_of = [&] (int lane) -> cudaStream_t { return ls.stream_of (lane, e); };
+        auto join = [&] { ls.join (e); };
         if (real_in_chunk)
         {
             // per chunk of k transforms on lane l:  forward  A: src -> ring, C: ring -> z, split: z -> out
@@ -853,6 +886,41 @@ int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inne
     {
         if (misaligned (in, 8, in_inner, inner, in_outer, outer) || misaligned (out, 8, out_inner, inner, out_outer, outer))
             return fail (chowdsp::fft::FFT_B200_EINVAL, "large transforms need 8-byte aligned buffers and even strides");
+        // complex 2^15 .. 2^17 points, plain batches with TMA-loadable rows: ONE pass on a thread-block cluster
+        // (cluster_kernels.cuh) instead of two tile passes; unordered inputs (inverse) stay with the tile path
+        const bool fwd = direction == chowdsp::fft::FFT_FORWARD;
+        const long long bstride_in = outer == 1 ? in_inner : in_outer, bstride_out = outer == 1 ? out_inner : out_outer;
+        if (g_cluster != 0 && p->is_complex && has_cluster (p->logM) && (outer == 1 || inner == 1) && (ordered || (fwd && p->logW == 3))
+            && ! misaligned (in, 16, bstride_in, (long long) outer * inner) && (long long) outer * inner >= g_cluster_min_batch)
+        {
+            int dev = 0;
+            CFB_CUDA (cudaGetDevice (&dev));
+            Tables st;
+            BigTables bt;
+            int rc = get_tables (dev, 9, false, st, 32);
+            if (rc == 0)
+                rc = get_big_tables (dev, p->logM, bt);
+            if (rc != 0)
+                return rc;
+            ClusterArgs ca {};
+            ca.out = out;
+            ca.out_stride = bstride_out;
+            ca.batch = outer * inner;
+            ca.logW = ordered ? 0 : p->logW;
+            ca.tw = st.tw;
+            ca.tw_lo = bt.lo;
+            ca.tw_hi = bt.hi;
+            ca.tw_lobits = bt.lobits;
+            const cudaError_t ce = launch_cluster_fft (p->logM, fwd ? -1 : +1, ca.logW, in, bstride_in, ca, stream);
+            if (ce == cudaSuccess)
+            {
+                note_kernel ("cfb::cluster_fft_kernel<%d,%d,%d> (cluster of %d CTAs, one pass)", p->logM - 13, fwd ? -1 : 1, ca.logW, 1 << (p->logM - 13));
+                return 0;
+            }
+            if (ce != cudaErrorInvalidConfiguration && ce != cudaErrorNotSupported)
+                return fail_cuda (ce, "cluster fft kernel launch");
+            (void) cudaGetLastError();
+        }
         for (int o = 0; o < outer; ++o)
         {
             const int rc = enqueue_large (p, in + o * in_outer, out + o * out_outer, inner, in_inner, out_inner, direction, ordered, stream);
@@ -1694,6 +1762,332 @@ CFB_API int fft_dist_phase0_peer (void* setup, int rank, int world, const float*
     return e == cudaSuccess ? 0 : fail_cuda (e, "distributed phase 0 (peer stores) launch");
 }
 
+// ---- distributed transform as ONE call per rank (the reference's contract is one fft_transform call,
+// /root/reference/chowdsp_fft.cpp:318-356; here every rank makes one fft_dist_transform call) ------------------------
+namespace
+{
+constexpr uint64_t kDistMagic = 0x4346424449535431ull; // "CFBDIST1"
+constexpr int kDistBlobHandles = 4;                    // recv[0], recv[1], natural, flags
+struct DistCtx
+{
+    uint64_t magic;
+    Plan* plan;
+    int rank, world, device;
+    LargeFactors f;
+    long long L1, S1, rows, cols;
+    size_t local_bytes;                 // this rank's share of the transform: N / world complex values
+    float2* recv[2] = { nullptr, nullptr };
+    float2* nat = nullptr;
+    unsigned long long* flags = nullptr; // [2][8] step counters + status word behind them
+    int* status = nullptr;
+    float2* peer_recv[2][8];
+    float2* peer_nat[8];
+    unsigned long long* peer_flags[8];
+    std::vector<void*> mapped;
+    bool connected = false;
+    unsigned long long step = 0;
+    float phase_ms[4] = { 0.f, 0.f, 0.f, 0.f };
+    cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+};
+DistCtx* as_dist (void* ctx)
+{
+    auto* d = static_cast<DistCtx*> (ctx);
+    if (d == nullptr || d->magic != kDistMagic)
+    {
+        fail (chowdsp::fft::FFT_B200_EINVAL, "invalid distributed context %p", ctx);
+        return nullptr;
+    }
+    return d;
+}
+} // namespace
+
+CFB_API int fft_dist_create (void* setup, int rank, int world, void** ctx_out)
+{
+    CFB_TRACE ("fft_dist_create");
+    Plan* p = as_plan (setup);
+    if (p == nullptr || ctx_out == nullptr)
+        return FFT_B200_EINVAL;
+    *ctx_out = nullptr;
+    if (! p->is_complex || p->logM <= kMaxLogM)
+        return fail (FFT_B200_EINVAL, "fft_dist_create needs a complex multi-pass plan");
+    if (world < 1 || world > 8 || rank < 0 || rank >= world)
+        return fail (FFT_B200_EINVAL, "fft_dist_create: 0 <= rank < world <= 8");
+    const LargeFactors f = choose_factors (p->logM);
+    TilePass probe;
+    if (! build_dist_phase (p->logM, f, 0, rank, world, probe) || f.l3 < ilog2i (world))
+        return fail (FFT_B200_EINVAL, "fft_dist_create: N=2^%d cannot be split over %d ranks (needs a three-pass plan, power-of-two world, L1/world >= 16)", p->logM, world);
+    auto* d = new (std::nothrow) DistCtx();
+    if (d == nullptr)
+        return fail (FFT_B200_ECUDA, "out of host memory");
+    d->magic = kDistMagic;
+    d->plan = p;
+    d->rank = rank;
+    d->world = world;
+    d->f = f;
+    d->L1 = 1LL << f.l1;
+    d->S1 = 1LL << (f.l2 + f.l3);
+    d->rows = d->L1 / world;
+    d->cols = d->S1 / world;
+    d->local_bytes = sizeof (float2) * (size_t) (d->L1 * d->cols);
+    cudaError_t e = cudaGetDevice (&d->device);
+    for (int b = 0; b < 2 && e == cudaSuccess; ++b)
+        e = cudaMalloc (&d->recv[b], d->local_bytes);
+    if (e == cudaSuccess)
+        e = cudaMalloc (&d->nat, d->local_bytes);
+    if (e == cudaSuccess)
+        e = cudaMalloc (&d->flags, 256);
+    if (e == cudaSuccess)
+        e = cudaMemset (d->flags, 0, 256);
+    for (int i = 0; i < 5 && e == cudaSuccess; ++i)
+        e = cudaEventCreate (&d->ev[i]);
+    if (e != cudaSuccess)
+    {
+        fail_cuda (e, "fft_dist_create");
+        for (auto* q : { (void*) d->recv[0], (void*) d->recv[1], (void*) d->nat, (void*) d->flags })
+            if (q != nullptr)
+                (void) cudaFree (q);
+        delete d;
+        return FFT_B200_ECUDA;
+    }
+    d->status = reinterpret_cast<int*> (d->flags + 16);
+    for (int h = 0; h < 8; ++h)
+    {
+        d->peer_recv[0][h] = d->peer_recv[1][h] = d->peer_nat[h] = nullptr;
+        d->peer_flags[h] = nullptr;
+    }
+    d->peer_recv[0][rank] = d->recv[0];
+    d->peer_recv[1][rank] = d->recv[1];
+    d->peer_nat[rank] = d->nat;
+    d->peer_flags[rank] = d->flags;
+    d->connected = world == 1;
+    if (preload_large (p) != 0)
+    {
+        fft_dist_destroy (d);
+        return FFT_B200_ECUDA;
+    }
+    *ctx_out = d;
+    return 0;
+}
+
+CFB_API size_t fft_dist_blob_bytes (void) { return 64 * kDistBlobHandles; }
+
+CFB_API int fft_dist_export (void* ctx, void* blob)
+{
+    DistCtx* d = as_dist (ctx);
+    if (d == nullptr || blob == nullptr)
+        return FFT_B200_EINVAL;
+    void* blocks[kDistBlobHandles] = { d->recv[0], d->recv[1], d->nat, d->flags };
+    for (int i = 0; i < kDistBlobHandles; ++i)
+    {
+        cudaIpcMemHandle_t h;
+        CFB_CUDA (cudaIpcGetMemHandle (&h, blocks[i]));
+        std::memcpy (static_cast<char*> (blob) + 64 * i, &h, 64);
+    }
+    return 0;
+}
+
+CFB_API int fft_dist_connect (void* ctx, const void* blobs)
+{
+    CFB_TRACE ("fft_dist_connect");
+    DistCtx* d = as_dist (ctx);
+    if (d == nullptr || (blobs == nullptr && d->world > 1))
+        return FFT_B200_EINVAL;
+    if (d->connected)
+        return 0;
+    for (int h = 0; h < d->world; ++h)
+    {
+        if (h == d->rank)
+            continue;
+        void* mapped[kDistBlobHandles];
+        for (int i = 0; i < kDistBlobHandles; ++i)
+        {
+            cudaIpcMemHandle_t hd;
+            std::memcpy (&hd, static_cast<const char*> (blobs) + (size_t) h * fft_dist_blob_bytes() + 64 * i, 64);
+            mapped[i] = nullptr;
+            CFB_CUDA (cudaIpcOpenMemHandle (&mapped[i], hd, cudaIpcMemLazyEnablePeerAccess));
+            d->mapped.push_back (mapped[i]);
+        }
+        d->peer_recv[0][h] = static_cast<float2*> (mapped[0]);
+        d->peer_recv[1][h] = static_cast<float2*> (mapped[1]);
+        d->peer_nat[h] = static_cast<float2*> (mapped[2]);
+        d->peer_flags[h] = static_cast<unsigned long long*> (mapped[3]);
+    }
+    d->connected = true;
+    return 0;
+}
+
+CFB_API float* fft_dist_natural_buffer (void* ctx)
+{
+    DistCtx* d = as_dist (ctx);
+    return d == nullptr ? nullptr : reinterpret_cast<float*> (d->nat);
+}
+
+CFB_API int fft_dist_status (void* ctx)
+{
+    DistCtx* d = as_dist (ctx);
+    if (d == nullptr)
+        return FFT_B200_EINVAL;
+    int st = 0;
+    CFB_CUDA (cudaMemcpy (&st, d->status, sizeof (int), cudaMemcpyDeviceToHost));
+    return st == 0 ? 0 : fail (FFT_B200_ECUDA, "distributed transform: a peer did not reach the exchange barrier in time");
+}
+
+CFB_API int fft_dist_phase_ms (void* ctx, float* ms4)
+{
+    DistCtx* d = as_dist (ctx);
+    if (d == nullptr || ms4 == nullptr)
+        return FFT_B200_EINVAL;
+    for (int i = 0; i < 4; ++i)
+        ms4[i] = d->phase_ms[i];
+    return 0;
+}
+
+CFB_API int fft_dist_transform (void* ctx, const float* input, float* output, fft_direction_t direction, int natural_order, int timed, void* stream_)
+{
+    CFB_TRACE ("fft_dist_transform");
+    DistCtx* d = as_dist (ctx);
+    if (d == nullptr)
+        return FFT_B200_EINVAL;
+    if (! d->connected)
+        return fail (FFT_B200_EINVAL, "fft_dist_transform: call fft_dist_connect first");
+    if (input == nullptr || (output == nullptr && ! natural_order))
+        return fail (FFT_B200_EINVAL, "fft_dist_transform: null buffer");
+    if (misaligned (input, 8) || (output != nullptr && misaligned (output, 8)))
+        return fail (FFT_B200_EINVAL, "fft_dist_transform: buffers must be 8-byte aligned");
+    if (classify (input).kind != Mem::Device || (output != nullptr && classify (output).kind != Mem::Device))
+        return fail (FFT_B200_EINVAL, "fft_dist_transform needs device pointers");
+    cudaStream_t stream = static_cast<cudaStream_t> (stream_);
+    Plan* p = d->plan;
+    const int n = p->logM, dir = direction == FFT_FORWARD ? -1 : +1, world = d->world;
+    LargeTables lt;
+    int rc = large_tables (p, d->device, d->f, lt);
+    if (rc != 0)
+        return rc;
+    const unsigned long long step = ++d->step;
+    const int b = (int) (step & 1);
+    cudaError_t e = cudaSuccess;
+    auto mark = [&] (int i)
+    {
+        if (timed && e == cudaSuccess)
+            e = cudaEventRecord (d->ev[i], stream);
+    };
+    auto barrier = [&] (int which)
+    {
+        if (world == 1)
+            return;
+        DistBarrierArgs ba {};
+        for (int h = 0; h < world; ++h)
+            ba.peer_flags[h] = d->peer_flags[h];
+        ba.own_flags = d->flags;
+        ba.status = d->status;
+        ba.rank = d->rank;
+        ba.world = world;
+        ba.which = which;
+        ba.step = step;
+        ba.timeout_ns = 20ull * 1000 * 1000 * 1000;
+        if (e == cudaSuccess)
+            e = launch_dist_barrier (ba, stream);
+    };
+    mark (0);
+    {   // phase 0: column FFTs + twiddle, every output row block stored straight into its owner's receive buffer
+        TilePass tp;
+        build_dist_phase (n, d->f, 0, d->rank, world, tp);
+        int wl = 0;
+        while ((1 << wl) < world)
+            ++wl;
+        tp.args.tw = lt.pass[0].tw;
+        tp.args.tw_lo = lt.bt.lo;
+        tp.args.tw_hi = lt.bt.hi;
+        tp.args.tw_lobits = lt.bt.lobits;
+        tp.args.in = reinterpret_cast<const float2*> (input);
+        tp.args.out = nullptr;
+        tp.args.peer_row_log = d->f.l1 - wl;
+        for (int h = 0; h < world; ++h)
+            tp.args.peer_out[h] = d->peer_recv[b][h];
+        e = launch_tile (tp.logL, tp.C, dir, tp.load_j_fast, 0, tp.args, stream);
+    }
+    mark (1);
+    barrier (0);
+    mark (2);
+    // phases 1 + 2 on this rank's rows, L2-chunked
+    long long chunk_elems = (long long) (g_l2_chunk_mb < 0 ? -g_l2_chunk_mb : g_l2_chunk_mb) * (1 << 20) / 8;
+    const int lanes = g_l2_lanes < 1 ? 1 : (g_l2_lanes > kMaxLanes ? kMaxLanes : g_l2_lanes);
+    const int c_last = tile_c (d->f.l3, true);
+    long long nrc = chunk_elems / d->S1;
+    nrc -= nrc % c_last;
+    if (chunk_elems > 0 && nrc < c_last)
+        nrc = c_last;
+    const long long ring_lane = chunk_elems > 0 ? (nrc > d->rows ? d->rows : nrc) * d->S1 : 0;
+    float2 *s1 = nullptr, *ring = nullptr;
+    if (chunk_elems <= 0)
+        CFB_CUDA (cudaMallocAsync (&s1, d->local_bytes, stream));
+    else
+        CFB_CUDA (cudaMallocAsync (&ring, sizeof (float2) * (size_t) ring_lane * (size_t) lanes, stream));
+    ForkJoin& fj = t_forkjoin;
+    if ((rc = fj.ensure()) != 0)
+        return rc;
+    std::vector<LargeLaunch> sched;
+    float2* dst = natural_order ? nullptr : reinterpret_cast<float2*> (output);
+    if (! build_dist_schedule (n, d->f, d->rank, world, d->recv[b], dst, d->peer_nat, natural_order != 0, s1, ring, ring_lane, chunk_elems, lanes, g_l2_policy != 0, sched))
+        return fail (FFT_B200_EINVAL, "fft_dist_transform: cannot schedule N=2^%d over %d ranks", n, world);
+    LaneSet ls (fj, stream);
+    for (auto& l : sched)
+    {
+        TileArgs& ta = l.pass.args;
+        ta.tw = lt.pass[l.pass.which].tw;
+        ta.tw_lo = lt.bt.lo;
+        ta.tw_hi = lt.bt.hi;
+        ta.tw_lobits = lt.bt.lobits;
+        cudaStream_t st = ls.stream_of (l.lane, e);
+        if (e == cudaSuccess)
+            e = launch_tile (l.pass.logL, l.pass.C, dir, l.pass.load_j_fast, 0, ta, st);
+    }
+    ls.join (e);
+    mark (3);
+    if (natural_order)
+    {
+        barrier (1); // every rank's pass-C stores into this rank's natural block have landed
+        if (output != nullptr && reinterpret_cast<float2*> (output) != d->nat && e == cudaSuccess)
+            e = cudaMemcpyAsync (output, d->nat, d->local_bytes, cudaMemcpyDeviceToDevice, stream);
+    }
+    mark (4);
+    if (s1 != nullptr)
+        CFB_CUDA (cudaFreeAsync (s1, stream));
+    if (ring != nullptr)
+        CFB_CUDA (cudaFreeAsync (ring, stream));
+    note_kernel ("cfb::tile_fft_kernel<%d|%d|%d,dir %d> distributed over %d ranks: phase 0 with peer stores, in-stream flag barrier, %s (B,C)%s",
+                 d->f.l1, d->f.l2, d->f.l3, dir, world, chunk_elems > 0 ? "L2-chunked" : "whole-array", natural_order ? ", natural order by peer stores" : "");
+    if (e != cudaSuccess)
+        return fail_cuda (e, "distributed transform launch");
+    if (timed)
+    {
+        CFB_CUDA (cudaEventSynchronize (d->ev[4]));
+        for (int i = 0; i < 4; ++i)
+            CFB_CUDA (cudaEventElapsedTime (&d->phase_ms[i], d->ev[i], d->ev[i + 1]));
+    }
+    return 0;
+}
+
+CFB_API int fft_dist_destroy (void* ctx)
+{
+    DistCtx* d = as_dist (ctx);
+    if (d == nullptr)
+        return FFT_B200_EINVAL;
+    (void) cudaDeviceSynchronize();
+    for (void* m : d->mapped)
+        (void) cudaIpcCloseMemHandle (m);
+    for (auto* q : { (void*) d->recv[0], (void*) d->recv[1], (void*) d->nat, (void*) d->flags })
+        if (q != nullptr)
+            (void) cudaFree (q);
+    for (auto& ev : d->ev)
+        if (ev != nullptr)
+            (void) cudaEventDestroy (ev);
+    d->magic = 0;
+    delete d;
+    (void) cudaGetLastError();
+    return 0;
+}
+
 // Peer-memory plumbing for the fused exchange: plain cudaMalloc blocks (IPC handles need whole allocations)
 CFB_API void* fft_dist_alloc (size_t bytes)
 {
@@ -1754,9 +2148,19 @@ CFB_API int fft_accumulate_batched (void* setup, const float* a, const float* b,
 
 CFB_API int fft_b200_set_tuning (const char* key, int value)
 {
-    if (key != nullptr && std::strcmp (key, "l2_chunk_mb") == 0 && value >= -1 && value <= 256)
+    if (key != nullptr && std::strcmp (key, "cluster") == 0 && value >= -1 && value <= 1)
     {
-        g_l2_chunk_mb = value == -1 ? kL2ChunkMbDefault : value;
+        g_cluster = value == -1 ? kClusterDefault : value;
+        return 0;
+    }
+    if (key != nullptr && std::strcmp (key, "cluster_min_batch") == 0 && value >= -1)
+    {
+        g_cluster_min_batch = value == -1 ? kClusterMinBatchDefault : value;
+        return 0;
+    }
+    if (key != nullptr && std::strcmp (key, "l2_chunk_mb") == 0 && value >= -256 && value <= 256)
+    {
+        g_l2_chunk_mb = value == -1 ? kL2ChunkMbDefault : value; // -1 = default; other negative values: |value| MiB, also beyond 2^24 points
         return 0;
     }
     if (key != nullptr && std::strcmp (key, "l2_lanes") == 0 && (value == -1 || (value >= 1 && value <= kMaxLanes)))

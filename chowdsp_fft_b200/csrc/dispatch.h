@@ -6,6 +6,7 @@
 #include "pconv_kernel.cuh"
 #include "large_kernels.cuh"
 #include "mixed_kernels.cuh"
+#include "cluster_kernels.cuh"
 
 namespace cfb
 {
@@ -64,9 +65,16 @@ cudaError_t launch_pconv (int logM, int logW, const PConvArgs& args, cudaStream_
 // generic mixed-radix transform (N = 2^a 3^b 5^c, not a power of two), one CTA per transform
 cudaError_t launch_mixed (const MixedArgs& args, cudaStream_t stream);
 
+// one-pass cluster transform (cluster_kernels.cuh) for complex lengths 2^15 .. 2^17: plain batches, 16-byte aligned input rows
+// with in_stride % 4 == 0; dir < 0 forward (logW 0 or 3 = 8-lane unordered output), dir > 0 backward (logW 0).
+// cudaErrorInvalidConfiguration / cudaErrorNotSupported = does not apply (fall back to the multi-pass path)
+bool has_cluster (int logN);
+cudaError_t launch_cluster_fft (int logN, int dir, int logW, const float* in, long long in_stride, const ClusterArgs& args, cudaStream_t stream);
+
 // multi-pass (large transform) kernels, large_inst.cu
 cudaError_t launch_tile (int logL, int C, int dir, bool load_j_fast, int uio, const TileArgs& args, cudaStream_t stream);
 cudaError_t launch_real_pass (int dir, const RealPassArgs& args, int batch, cudaStream_t stream);
+cudaError_t launch_dist_barrier (const DistBarrierArgs& args, cudaStream_t stream);
 
 cudaError_t launch_convolve (const float* a, const float* b, float* ab, long long a_stride, long long b_stride, long long ab_stride, int nfloats, int batch, int logW, bool is_real, float scaling, cudaStream_t stream);
 cudaError_t launch_accumulate (const float* a, const float* b, float* ab, long long n, cudaStream_t stream);

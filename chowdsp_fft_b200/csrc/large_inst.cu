@@ -61,6 +61,13 @@ cudaError_t launch_tile (int logL, int C, int dir, bool load_j_fast, int uio, co
     }
 }
 
+cudaError_t launch_dist_barrier (const DistBarrierArgs& a, cudaStream_t stream)
+{
+    dist_barrier_kernel<0><<<1, 32, 0, stream>>> (a);
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t launch_real_pass (int dir, const RealPassArgs& a, int batch, cudaStream_t stream)
 {
     const long long pairs = 1LL << (a.logM - 1);

@@ -414,6 +414,53 @@ __global__ void __launch_bounds__ (256) real_pass_kernel (const RealPassArgs a)
     }
 }
 
+
+#ifndef CHOWDSP_EMU
+// ---------------------------------------------------------------------------------------------
+// Cross-rank barrier of the distributed transform, in the stream, without a host round trip or a collective library:
+// every rank owns a flag row flags[which][world] in peer-mapped memory.  One CTA per rank; lane g publishes this rank's
+// step counter into rank g's row (release at system scope, after a system fence that orders the phase kernel's peer
+// stores -- complete at kernel boundary -- before it) and then waits until rank g's counter has arrived in its own row.
+// A rank that never arrives would hang the GPU, so the wait gives up after `timeout_ns` and raises *status instead.
+// ---------------------------------------------------------------------------------------------
+struct DistBarrierArgs
+{
+    unsigned long long* peer_flags[8]; // rank g's flag block (2 rows of 8 counters), mapped into this process
+    unsigned long long* own_flags;
+    int* status;                       // set to 1 on timeout
+    int rank, world, which;
+    unsigned long long step;
+    unsigned long long timeout_ns;
+};
+template <int UNUSED = 0> // a template only so that every translation unit including this header may hold a copy
+__global__ void __launch_bounds__ (32) dist_barrier_kernel (const DistBarrierArgs a)
+{
+    const int g = (int) threadIdx.x;
+    if (g >= a.world)
+        return;
+    __threadfence_system();
+    unsigned long long* dst = a.peer_flags[g] + a.which * 8 + a.rank;
+    asm volatile ("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(a.step) : "memory");
+    const unsigned long long* src = a.own_flags + a.which * 8 + g;
+    unsigned long long t0, now, seen;
+    asm volatile ("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;)
+    {
+        asm volatile ("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(src) : "memory");
+        if (seen >= a.step)
+            break;
+        asm volatile ("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t0 > a.timeout_ns)
+        {
+            *a.status = 1;
+            break;
+        }
+        __nanosleep (200);
+    }
+    __threadfence_system();
+}
+#endif
+
 // host: two-level table for W_N^e, e < N = 2^logN:  lo[e & mask] = W_N^(e & mask), hi[e >> lobits] = W_N^((e >> lobits) << lobits)
 inline void fill_big_twiddles (float2* lo, float2* hi, int logN, int lobits)
 {

@@ -372,5 +372,76 @@ inline void build_large_schedule (int n, const LargeFactors& f, int batch, const
         }
 }
 
+// Phases 1 + 2 of the distributed transform on this rank's rows, L2-chunked like the single-GPU three-pass plan (a chunk =
+// nr of the rank's L1/world k1-rows: B: exchange layout -> ring, C: ring -> result), or whole-array through `s1`
+// (chunk_elems = 0).  natural = false: transposed-out into `dst` ([S1][L1/world]).  natural = true: the second
+// all-to-all is fused into pass C's stores -- bin k1 + L1 q belongs to rank q / (S1/world) = k3 >> (l3 - log2 world), whose
+// natural-order block is mapped at peer_nat[h]; it lands at offset k1 + L1 (q mod S1/world) there.
+inline bool build_dist_schedule (int n, const LargeFactors& f, int rank, int world, const float2* recv, float2* dst, float2* const* peer_nat, bool natural,
+                                 float2* s1, float2* ring, long long ring_lane_elems, long long chunk_elems, int lanes, bool policies, std::vector<LargeLaunch>& out)
+{
+    TilePass p1, p2;
+    if (! build_dist_phase (n, f, 1, rank, world, p1) || ! build_dist_phase (n, f, 2, rank, world, p2))
+        return false;
+    p1.which = 1;
+    p2.which = 2;
+    const long long L1 = 1LL << f.l1, L2 = 1LL << f.l2, S1 = 1LL << (f.l2 + f.l3), rows = L1 / world;
+    int wl = 0;
+    while ((1 << wl) < world)
+        ++wl;
+    if (natural)
+    {
+        if (world > 8 || f.l3 < wl)
+            return false;
+        p2.args.out_g_hi = L1;
+        p2.args.out_g_lo = p2.C;
+        p2.args.out_tstride = 1;
+        p2.args.out_estride = L1 * L2;
+        p2.args.peer_row_log = f.l3 - wl;
+        p2.args.peer_chunk_off = (long long) rank * rows;
+        for (int h = 0; h < world; ++h)
+            p2.args.peer_out[h] = peer_nat[h];
+    }
+    out.clear();
+    p1.args.in = recv;
+    p2.args.out = dst;
+    if (chunk_elems <= 0 || ring == nullptr)
+    {
+        p1.args.out = s1;
+        p2.args.in = s1;
+        out.push_back ({ p1, -1 });
+        out.push_back ({ p2, -1 });
+        return true;
+    }
+    const int keep = policies ? POLICY_KEEP : POLICY_NORMAL, strm = policies ? POLICY_STREAM : POLICY_NORMAL;
+    long long nrc = ring_lane_elems / S1;
+    nrc -= nrc % p2.C;
+    if (nrc < p2.C)
+        return false;
+    int lane = nrc >= rows ? -1 : 0;
+    for (long long r0 = 0; r0 < rows; r0 += nrc, lane = lane < 0 ? -1 : (lane + 1) % lanes)
+    {
+        const long long nr = rows - r0 < nrc ? rows - r0 : nrc;
+        float2* slot = ring + (long long) (lane < 0 ? 0 : lane) * ring_lane_elems;
+        LargeLaunch bb { p1, lane }, cc { p2, lane };
+        bb.pass.args.in_bin0 = r0 * p1.args.in_g_hi; // row r0 inside every chunk of the exchange layout
+        bb.pass.args.out = slot;
+        bb.pass.args.out_bin0 = 0;
+        bb.pass.args.ntiles = (int) (nr * bb.pass.args.gdiv);
+        bb.pass.args.in_policy = strm;
+        bb.pass.args.out_policy = keep;
+        cc.pass.args.in = slot;
+        cc.pass.args.in_bin0 = 0;
+        cc.pass.args.out_bin0 = r0;
+        cc.pass.args.gdiv = (int) (nr / cc.pass.C);
+        cc.pass.args.ntiles = (int) (cc.pass.args.gdiv * L2);
+        cc.pass.args.in_policy = keep;
+        cc.pass.args.out_policy = strm;
+        out.push_back (bb);
+        out.push_back (cc);
+    }
+    return true;
+}
+
 inline int big_twiddle_lobits (int n) { return n < 28 ? (n + 1) / 2 : 14; }
 } // namespace cfb

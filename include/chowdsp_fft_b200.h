@@ -120,6 +120,36 @@ int fft_dist_ipc_export (void* block, void* handle64);
 void* fft_dist_ipc_open (const void* handle64);
 void fft_dist_ipc_close (void* mapped);
 
+/* The distributed transform as ONE call per rank (one process per GPU): the reference's contract is a single
+   fft_transform call (chowdsp_fft.cpp:318-356), so the exchange orchestration lives behind the C ABI and needs no
+   collective library -- the all-to-all is done by the phase-0 kernel's peer stores over NVLink, the barrier across ranks
+   is a flag exchange in peer memory executed in the caller's stream, and phases 1 + 2 run L2-chunked.
+     fft_dist_create     allocates this rank's two exchange buffers, its natural-order block and its barrier flags
+     fft_dist_export     writes fft_dist_blob_bytes() opaque bytes (CUDA IPC handles) that the caller ships to every
+                         other rank over any transport (MPI, torch.distributed, files ...) -- like a communicator id
+     fft_dist_connect    takes all ranks' blobs, rank-major (blob of rank r at offset r * fft_dist_blob_bytes()), and maps
+                         the peers' buffers; world == 1 needs no blobs
+     fft_dist_transform  input : this rank's column block  A[n1][c] = x[n1*S1 + rank*S1/world + c]  ([L1][S1/world] complex)
+                         natural_order = 0: output = transposed-out [S1][L1/world], out[q][k] = X[(rank*L1/world + k) + L1*q]
+                         natural_order = 1: the second all-to-all is fused into the last pass's peer stores; this rank's
+                                            contiguous block X[rank*N/world, (rank+1)*N/world) lands in
+                                            fft_dist_natural_buffer() and is copied to `output` unless output is that
+                                            buffer or NULL
+                         timed != 0: records events around the phases and blocks until done; fft_dist_phase_ms then
+                                     returns { phase 0 incl. peer stores, barrier wait, phases 1+2, natural barrier + copy }
+                         Collective: every rank must call it the same number of times.  A peer that never arrives makes
+                         the in-stream barrier give up after 20 s and raises fft_dist_status() instead of hanging the GPU.
+   world <= 8, power of two, L1/world >= 16.  Device pointers, stream-ordered. */
+int fft_dist_create (void* setup, int rank, int world, void** ctx_out);
+size_t fft_dist_blob_bytes (void);
+int fft_dist_export (void* ctx, void* blob);
+int fft_dist_connect (void* ctx, const void* blobs);
+int fft_dist_transform (void* ctx, const float* input, float* output, fft_direction_t direction, int natural_order, int timed, void* stream);
+float* fft_dist_natural_buffer (void* ctx);
+int fft_dist_status (void* ctx);
+int fft_dist_phase_ms (void* ctx, float* ms4);
+int fft_dist_destroy (void* ctx);
+
 /* log2 of the pass lengths of a multi-pass plan (l2 = 0 for two-pass plans); returns FFT_B200_EINVAL for
    single-kernel plans. */
 int fft_large_factors (void* setup, int* l1, int* l2, int* l3);
@@ -140,7 +170,12 @@ void fft_b200_clear_error (void);
      "wistft"       bit 0: overlap-add synthesis through the warp-pipelined kernel where it applies (default); bits 8..: warps per CTA
      "stft_pipe", "stft_union"  older frame-gather variants (persistent CTA-level TMA union / LDS-STS union staging), off
      "tile_c", "tile_c_jfast"   transforms per tile of the multi-pass kernels (8, 16, or 0 = built-in policy)
-     "tile_pipe"    1 = persistent TMA-staged tile kernel for the multi-pass transforms (measured slower; default 0)
+     "cluster"      1 = complex transforms of 2^15 .. 2^17 points run in one pass on a thread-block cluster (default), 0 = tile passes;
+                    "cluster_min_batch": smaller batches stay with the tile passes (default 8)
+     "l2_chunk_mb"  MiB of intermediate per chunk of the L2-chunked multi-pass schedules (default 16, applied up to 2^24 points;
+                    0 = whole-array passes everywhere; -m (m >= 2) = m MiB chunks at every size)
+     "l2_lanes"     helper streams / ring slots the chunks alternate over (1..4, default 3)
+     "l2_policy"    1 = evict_last / evict_first L2 hints on ring / streaming accesses of the chunked schedules (default)
      "pf_ahead"     L2 prefetch distance of the single-kernel transforms in CTAs (default 0 = off) */
 int fft_b200_set_tuning (const char* key, int value);
 

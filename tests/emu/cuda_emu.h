@@ -50,6 +50,11 @@ struct ThreadCtx
     std::vector<SmemOp>* log = nullptr; // per-thread smem op sequence (bank-conflict analysis)
     float* shfl_buf = nullptr;          // 32 floats of this thread's warp (warp shuffles)
     int lane = 0;
+    // thread-block clusters (launch_cluster): rank of this CTA, index / count of clusters, every CTA's shared-memory
+    // block (distributed shared memory) and the cluster-wide barrier
+    int cluster_rank = 0, cluster_id = 0, cluster_count = 1;
+    char* cluster_smem[16] = {};
+    std::barrier<>* cluster_bar = nullptr;
 };
 inline thread_local ThreadCtx ctx;
 inline void syncgroup (int n) { ctx.group_bar[n == 32 ? 0 : n == 64 ? 1 : 2]->arrive_and_wait(); } // __syncwarp / named barriers
@@ -161,6 +166,61 @@ void launch (Kernel kernel, dim3 grid, dim3 block, size_t smem_bytes, Args... ar
             th.join();
         if (g_log_smem)
             analyse_block (logs);
+    }
+}
+
+// Cluster launch: the `cluster` CTAs of one cluster run CONCURRENTLY (they exchange data through each other's shared
+// memory and meet at cluster barriers); clusters run one after the other.  grid.x = clusters * cluster.
+template <typename Kernel, typename... Args>
+void launch_cluster (Kernel kernel, dim3 grid, unsigned cluster, dim3 block, size_t smem_bytes, Args... args)
+{
+    const unsigned nthreads = block.x * block.y * block.z;
+    const unsigned nclusters = grid.x / cluster;
+    for (unsigned cid = 0; cid < nclusters; ++cid)
+    {
+        std::vector<std::vector<char>> smem (cluster, std::vector<char> (smem_bytes + 64));
+        std::vector<std::unique_ptr<std::barrier<>>> bars;
+        std::barrier<> cluster_bar ((std::ptrdiff_t) (nthreads * cluster));
+        std::vector<std::vector<std::unique_ptr<std::barrier<>>>> group_bars (cluster * 3);
+        std::vector<std::vector<std::vector<SmemOp>>> logs (cluster, std::vector<std::vector<SmemOp>> (nthreads));
+        std::vector<std::vector<float>> shfl_bufs (cluster, std::vector<float> ((nthreads + 31) / 32 * 32));
+        for (unsigned r = 0; r < cluster; ++r)
+        {
+            bars.emplace_back (new std::barrier<> ((std::ptrdiff_t) nthreads));
+            for (int gi = 0; gi < 3; ++gi)
+                for (unsigned w = 0, n = 32u << gi; w < (nthreads + n - 1) / n; ++w)
+                    group_bars[r * 3 + gi].emplace_back (new std::barrier<> ((std::ptrdiff_t) std::min (n, nthreads - n * w)));
+        }
+        std::vector<std::thread> pool;
+        pool.reserve ((size_t) nthreads * cluster);
+        for (unsigned r = 0; r < cluster; ++r)
+            for (unsigned t = 0; t < nthreads; ++t)
+                pool.emplace_back ([&, r, t]
+                                   {
+                                       ctx.tIdx = dim3 (t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+                                       ctx.bIdx = dim3 (cid * cluster + r, 0, 0);
+                                       ctx.bDim = block;
+                                       ctx.gDim = grid;
+                                       ctx.bar = bars[r].get();
+                                       for (int gi = 0; gi < 3; ++gi)
+                                           ctx.group_bar[gi] = group_bars[r * 3 + gi][t / (32u << gi)].get();
+                                       ctx.smem = smem[r].data();
+                                       ctx.shfl_buf = shfl_bufs[r].data() + (t / 32) * 32;
+                                       ctx.lane = (int) (t % 32);
+                                       ctx.log = g_log_smem ? &logs[r][t] : nullptr;
+                                       ctx.cluster_rank = (int) r;
+                                       ctx.cluster_id = (int) cid;
+                                       ctx.cluster_count = (int) nclusters;
+                                       for (unsigned q = 0; q < cluster; ++q)
+                                           ctx.cluster_smem[q] = smem[q].data();
+                                       ctx.cluster_bar = &cluster_bar;
+                                       kernel (args...);
+                                   });
+        for (auto& th : pool)
+            th.join();
+        if (g_log_smem)
+            for (unsigned r = 0; r < cluster; ++r)
+                analyse_block (logs[r]);
     }
 }
 } // namespace emu

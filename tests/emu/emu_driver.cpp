@@ -6,6 +6,7 @@
 #include "elementwise_kernels.cuh"
 #include "pconv_kernel.cuh"
 #include "pipe_kernels.cuh"
+#include "cluster_kernels.cuh"
 #include "mixed_kernels.cuh"
 #include "large_plan.h"
 
@@ -612,6 +613,111 @@ int emu_dist_phase0_peer (int n, int l1, int l2, int l3, int rank, int world, co
         p.args.peer_out[h] = reinterpret_cast<float2*> (outs[h]);
     emu::g_log_smem = false;
     return emu_tile_dispatch<-1> (p);
+}
+
+// phases 1 + 2 of one rank through build_dist_schedule (fft_dist_transform's schedule): recv = this rank's exchange-layout
+// buffer; natural = 0: out = transposed-out buffer of this rank; natural = 1: outs[h] = rank h's natural-order block (the
+// second all-to-all done by pass C's stores).  chunk_elems = 0: whole-array passes.
+int emu_dist_schedule (int n, int l1, int l2, int l3, int rank, int world, int natural, long long chunk_elems, int lanes, const float* recv, float* out, float* const* outs)
+{
+    LargeFactors f;
+    f.l1 = l1; f.l2 = l2; f.l3 = l3;
+    const long long S1 = 1LL << (l2 + l3), rows = (1LL << l1) / world;
+    const int lobits = big_twiddle_lobits (n);
+    std::vector<float2> lo ((size_t) 1 << lobits), hi ((size_t) 1 << (n - lobits));
+    fill_big_twiddles (lo.data(), hi.data(), n, lobits);
+    std::vector<float2> tw[3];
+    const int logs[3] = { l1, l2, l3 };
+    for (int i = 1; i < 3; ++i)
+        switch (logs[i])
+        {
+            case 6: fill_tw_for<6> (tw[i]); break;
+            case 7: fill_tw_for<7> (tw[i]); break;
+            case 8: fill_tw_for<8> (tw[i]); break;
+            case 9: fill_tw_for<9> (tw[i]); break;
+            case 10: fill_tw_for<10> (tw[i]); break;
+            default: return -3;
+        }
+    const int c_last = tile_c (l3, true);
+    long long nrc = chunk_elems / S1;
+    nrc -= nrc % c_last;
+    if (chunk_elems > 0 && nrc < c_last)
+        nrc = c_last;
+    const long long ring_lane = chunk_elems > 0 ? (nrc > rows ? rows : nrc) * S1 : 0;
+    std::vector<float2> s1 ((size_t) (rows * S1)), ring ((size_t) (ring_lane * lanes) + 1);
+    float2* peer_nat[8] = {};
+    for (int h = 0; h < world && natural; ++h)
+        peer_nat[h] = reinterpret_cast<float2*> (outs[h]);
+    std::vector<LargeLaunch> sched;
+    if (! build_dist_schedule (n, f, rank, world, reinterpret_cast<const float2*> (recv), natural ? nullptr : reinterpret_cast<float2*> (out), peer_nat, natural != 0,
+                               s1.data(), chunk_elems > 0 ? ring.data() : nullptr, ring_lane, chunk_elems, lanes, true, sched))
+        return -2;
+    emu::g_log_smem = false;
+    for (auto& l : sched)
+    {
+        l.pass.args.tw = tw[l.pass.which].data();
+        l.pass.args.tw_lo = lo.data();
+        l.pass.args.tw_hi = hi.data();
+        l.pass.args.tw_lobits = lobits;
+        const int rc = emu_tile_dispatch<-1> (l.pass);
+        if (rc != 0)
+            return rc;
+    }
+    return (int) sched.size();
+}
+
+// one-pass cluster transform (cluster_kernels.cuh): `nclusters` resident clusters of 2^logG CTAs loop over `batch` contiguous
+// transforms of 2^(13 + logG) complex points; unord = 1: 8-lane unordered output (forward only)
+int emu_cluster_fft (int logG, int backward, int unord, const float* in, float* out, int batch, int nclusters, int log_conflicts, long* stats)
+{
+    auto run = [&] (auto logg_c) -> int
+    {
+        constexpr int LOGG = decltype (logg_c)::value;
+        using CG = ClusterGeo<LOGG>;
+        constexpr int LOGN = CG::LOGN;
+        const long long N = 1LL << LOGN;
+        std::vector<float2> tw ((size_t) CG::GL::TW_LEN + 1);
+        fill_stage_twiddles<9, 32> (tw.data());
+        const int lobits = big_twiddle_lobits (LOGN);
+        std::vector<float2> lo ((size_t) 1 << lobits), hi ((size_t) 1 << (LOGN - lobits));
+        fill_big_twiddles (lo.data(), hi.data(), LOGN, lobits);
+        TensorMap4 tm {};
+        tm.base = reinterpret_cast<const char*> (in);
+        tm.dim[0] = 32; tm.dim[1] = CG::G; tm.dim[2] = CG::LC; tm.dim[3] = (unsigned long long) batch;
+        tm.stride[0] = 128; tm.stride[1] = 128ull * CG::G; tm.stride[2] = (unsigned long long) N * 8;
+        tm.box[0] = 32; tm.box[1] = 1; tm.box[2] = CG::TMA_ROWS; tm.box[3] = 1;
+        ClusterArgs a {};
+        a.out = out;
+        a.out_stride = 2 * N;
+        a.batch = batch;
+        a.logW = unord ? 3 : 0;
+        a.tw = tw.data();
+        a.tw_lo = lo.data();
+        a.tw_hi = hi.data();
+        a.tw_lobits = lobits;
+        const dim3 grid ((unsigned) (nclusters * CG::G)), block (CG::THREADS);
+        if (backward)
+            emu::launch_cluster (cluster_fft_kernel<LOGG, +1, 0>, grid, CG::G, block, (size_t) CG::SMEM_BYTES, tm, a);
+        else if (unord)
+            emu::launch_cluster (cluster_fft_kernel<LOGG, -1, 3>, grid, CG::G, block, (size_t) CG::SMEM_BYTES, tm, a);
+        else
+            emu::launch_cluster (cluster_fft_kernel<LOGG, -1, 0>, grid, CG::G, block, (size_t) CG::SMEM_BYTES, tm, a);
+        return 0;
+    };
+    emu::g_log_smem = log_conflicts != 0;
+    emu::g_stats = {};
+    int rc = -1;
+    if (logG == 1) rc = run (std::integral_constant<int, 1> {});
+    if (logG == 2) rc = run (std::integral_constant<int, 2> {});
+    if (logG == 3) rc = run (std::integral_constant<int, 3> {});
+    if (stats)
+    {
+        stats[0] = emu::g_stats.ops;
+        stats[1] = emu::g_stats.wavefronts;
+        stats[2] = emu::g_stats.ideal;
+        stats[3] = emu::g_stats.worst;
+    }
+    return rc;
 }
 
 int emu_convolve (const float* a, const float* b, float* ab, long long a_stride, long long b_stride, long long ab_stride, int nfloats, int batch, int logW, int is_real, float scaling)

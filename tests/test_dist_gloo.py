@@ -26,6 +26,7 @@ def _emu():
     L = C.CDLL(build())
     L.emu_dist_phase.argtypes = [C.c_int] * 7 + [fp, fp]
     L.emu_dist_phase0_peer.argtypes = [C.c_int] * 6 + [fp, C.POINTER(fp)]
+    L.emu_dist_schedule.argtypes = [C.c_int] * 7 + [C.c_longlong, C.c_int, fp, fp, C.POINTER(fp)]
     return L
 
 
@@ -123,3 +124,40 @@ def test_peer_store_phase0_equals_all_to_all(world):
     for h in range(world):
         for rank in range(world):
             assert np.array_equal(bufs[h][rank], sends[rank][h]), (h, rank)
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+@pytest.mark.parametrize("chunk_rows", [0, 8, 24])
+def test_dist_schedule_chunked_and_natural_order(world, chunk_rows):
+    """fft_dist_transform's schedule for phases 1 + 2 (large_plan.h: build_dist_schedule), kernel source emulated:
+    whole-array or L2-chunked (ragged last chunk), transposed-out == the plain phases; natural order with the second
+    all-to-all fused into pass C's stores == the contiguous blocks of the spectrum on every rank."""
+    L = _emu()
+    L1, S1, rows, cols = _geometry(world)
+    N = 1 << N_LOG
+    x = _signal()
+    X = np.fft.fft(x[:, 0].astype(np.float64) + 1j * x[:, 1])
+    # exchange-layout buffers of every rank, produced by the (already tested) peer-store phase 0
+    bufs = [np.zeros((world, rows * cols * 2), np.float32) for _ in range(world)]
+    ptrs = (fp * world)(*[b.ctypes.data_as(fp) for b in bufs])
+    for rank in range(world):
+        blk = _column_block(x, rank, world).reshape(-1)
+        assert L.emu_dist_phase0_peer(N_LOG, *FACTORS, rank, world, blk.ctypes.data_as(fp), ptrs) == 0
+    chunk_elems = chunk_rows * S1
+    nats = [np.full(2 * N // world, np.nan, np.float32) for _ in range(world)]
+    nat_ptrs = (fp * world)(*[b.ctypes.data_as(fp) for b in nats])
+    for rank in range(world):
+        recv = bufs[rank].reshape(-1)
+        plain = _phase(L, 2, rank, world, _phase(L, 1, rank, world, recv, rows * S1 * 2), S1 * rows * 2)
+        out_t = np.full(S1 * rows * 2, np.nan, np.float32)
+        nl = L.emu_dist_schedule(N_LOG, *FACTORS, rank, world, 0, chunk_elems, 2, recv.ctypes.data_as(fp), out_t.ctypes.data_as(fp), nat_ptrs)
+        assert nl >= 2
+        if chunk_rows and chunk_rows < rows:
+            assert nl == 2 * -(-rows // chunk_rows)
+        assert np.array_equal(out_t, plain)
+        assert L.emu_dist_schedule(N_LOG, *FACTORS, rank, world, 1, chunk_elems, 3, recv.ctypes.data_as(fp), None, nat_ptrs) >= 2
+    for rank in range(world):
+        got = nats[rank].reshape(-1, 2)
+        got = got[:, 0].astype(np.float64) + 1j * got[:, 1]
+        want = X[rank * N // world:(rank + 1) * N // world]
+        assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-6 * N_LOG

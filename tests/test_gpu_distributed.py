@@ -38,6 +38,13 @@ def _run_rank(rank, world, port, n, q, exchange="peer"):
     d.forward(xc, out_t)
     nat = d.natural(out_t)
     torch.cuda.synchronize()
+    if exchange == "peer":
+        # natural order with the second all-to-all fused into the last pass's peer stores == the NCCL redistribution, bit for bit
+        nat2 = torch.empty_like(nat)
+        d.forward(xc, nat2, natural=True, timed=True)
+        torch.cuda.synchronize()
+        assert torch.equal(nat2, nat)
+        assert len(d.phase_ms()) == 4 and all(t >= 0 for t in d.phase_ms())
     X = np.fft.fft(x[:, 0].double().numpy() + 1j * x[:, 1].double().numpy())
     want_t = X.reshape(d.S1, d.L1)[:, rank * d.rows:(rank + 1) * d.rows]
     got_t = out_t.view(d.S1, d.rows, 2).cpu().numpy()
@@ -91,3 +98,90 @@ def test_dist_multi_gpu(world, exchange):
         assert p.exitcode == 0
     for r in res:
         assert max(r[1:]) < 1e-6 * n, r
+
+
+def _hash_signal(idx):
+    """Counter-based synthetic signal keyed by the global FLOAT index (every rank / layout regenerates the same values):
+    64-bit LCG step, top bits -> U(-1, 1).  idx: int64 tensor."""
+    h = idx * 6364136223846793005 + 1442695040888963407
+    h = (h ^ (h >> 29)) * 2862933555777941757 + 3037000493
+    return ((h >> 40) & 0xFFFFFF).double() / float(1 << 23) - 1.0
+
+
+def _sampled_bins(N, ks, device):
+    """float64 DFT bins of the hash signal, exact integer phases, chunked"""
+    out = []
+    step = 1 << 23
+    for k in ks:
+        re = im = 0.0
+        for n0 in range(0, N, step):
+            n = torch.arange(n0, n0 + step, device=device, dtype=torch.int64)
+            ang = ((n * int(k)) % N).double() * (-2.0 * np.pi / N)
+            c, s_ = torch.cos(ang), torch.sin(ang)
+            xr, xi = _hash_signal(2 * n), _hash_signal(2 * n + 1)
+            re += float((xr * c - xi * s_).sum())
+            im += float((xr * s_ + xi * c).sum())
+        out.append(complex(re, im))
+    return np.array(out)
+
+
+def _run_rank_full_size(rank, world, port, q):
+    """BASELINE configs[4] at its stated size: N = 2^28 over `world` GPUs; sampled bins of this rank's block against a
+    float64 DFT, for the transposed-out and the natural-order contract."""
+    import torch.distributed as dist
+
+    from chowdsp_fft_b200.distributed import DistributedFFT
+
+    torch.cuda.set_device(rank)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    n = 28
+    N = 1 << n
+    d = DistributedFFT(n, rank, world, exchange="peer")
+    n1 = torch.arange(d.L1, device="cuda", dtype=torch.int64)[:, None]
+    c = torch.arange(d.cols, device="cuda", dtype=torch.int64)[None, :]
+    g = n1 * d.S1 + rank * d.cols + c                               # global complex index of every element of the column block
+    xc = torch.stack([_hash_signal(2 * g).float(), _hash_signal(2 * g + 1).float()], dim=-1).contiguous()
+    del g
+    out_t = torch.empty(d.S1 * d.rows * 2, device="cuda")
+    d.forward(xc, out_t)
+    nat = torch.empty(2 * (N // world), device="cuda")
+    d.forward(xc, nat, natural=True)
+    torch.cuda.synchronize()
+    rng = np.random.default_rng(100 + rank)
+    # transposed-out: out[q][k] = X[(rank*rows + k) + L1*q]
+    qs, ks = rng.integers(0, d.S1, 6), rng.integers(0, d.rows, 6)
+    bins = [int(rank * d.rows + k + d.L1 * qq) for qq, k in zip(qs, ks)]
+    want = _sampled_bins(N, bins, "cuda")
+    got = out_t.view(d.S1, d.rows, 2)[torch.tensor(qs, device="cuda"), torch.tensor(ks, device="cuda")].cpu().numpy()
+    got = got[:, 0].astype(np.float64) + 1j * got[:, 1]
+    e1 = float(np.linalg.norm(got - want) / np.linalg.norm(want))
+    # natural order: block[i] = X[rank*N/world + i]
+    idx = rng.integers(0, N // world, 6)
+    want = _sampled_bins(N, [int(rank * (N // world) + i) for i in idx], "cuda")
+    got = nat.view(-1, 2)[torch.tensor(idx, device="cuda")].cpu().numpy()
+    got = got[:, 0].astype(np.float64) + 1j * got[:, 1]
+    e2 = float(np.linalg.norm(got - want) / np.linalg.norm(want))
+    d.close()
+    dist.destroy_process_group()
+    q.put((rank, e1, e2, 0.0))
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_config5_full_size_distributed(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs (gpurun --gpus {world})")
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_run_rank_full_size, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in res:
+        assert max(r[1:]) < 1e-6 * 28, r

@@ -925,6 +925,7 @@ def test_l2_chunked_schedules_equal_whole_array_passes(cf, oracle_mod, lanes, po
     o = oracle_mod
     rng = np.random.default_rng(5)
     try:
+        cf.set_tuning("cluster", 0)  # this test is about the tile passes
         for lg, is_c, batch, mb in [(16, True, 7, 1), (15, True, 9, 1), (17, False, 6, 1), (22, True, 1, 2), (22, True, 2, 4), (22, False, 2, 2), (21, True, 3, 1)]:
             N = 1 << lg
             nfl = 2 * N if is_c else N
@@ -943,7 +944,7 @@ def test_l2_chunked_schedules_equal_whole_array_passes(cf, oracle_mod, lanes, po
                 assert np.array_equal(got_b, classic_b), (lg, is_c, batch, ordered, "backward")
                 assert o.rel_l2(got_b / N, x) < o.parity_tol(N)
     finally:
-        _tuned(cf, l2_chunk_mb=-1, l2_lanes=-1, l2_policy=-1)
+        _tuned(cf, l2_chunk_mb=-1, l2_lanes=-1, l2_policy=-1, cluster=-1)
 
 
 def sampled_dft(torch, x2, ks):
@@ -1049,3 +1050,45 @@ def test_misaligned_operands_are_rejected_not_faulted(cf):
         cf.fft_destroy_setup(s)
     torch.cuda.synchronize()  # the context is still healthy
     assert float(buf.sum()) == 0.0
+
+
+@pytest.mark.parametrize("lg", [15, 16, 17])
+def test_cluster_one_pass_transform(cf, oracle_mod, ref_lib, lg):
+    """Complex transforms of 2^15 .. 2^17 points in ONE pass on a thread-block cluster (csrc/cluster_kernels.cuh: tensor-map
+    TMA loads, radix-G butterfly across the CTAs through distributed shared memory): forward / backward, natural order and
+    the 8-lane unordered output, in place, batches smaller / larger than the resident cluster count and not a multiple of
+    it -- against the oracle, the live reference, and bit-exact against nothing else: the tile path is a different
+    algorithm, so the two are compared within tolerance."""
+    o = oracle_mod
+    N = 1 << lg
+    tol = o.parity_tol(N)
+    rng = np.random.default_rng(lg)
+    try:
+        cf.set_tuning("cluster_min_batch", 1)
+        for batch in (1, 9, 83):
+            x = rng.uniform(-1, 1, (batch, 2 * N)).astype(np.float32)
+            want_f = o.np_transform(x[:3], N, True, 8, False, True)
+            cf.set_tuning("cluster", 1)
+            got_f = gpu_transform(cf, x, N, True, True, False, True)
+            if "cluster_fft_kernel" not in cf.last_kernel():
+                pytest.skip("clusters of %d CTAs cannot be co-scheduled on this device: %s" % (1 << (lg - 13), cf.last_kernel()))
+            assert o.rel_l2(got_f[:3], want_f) < tol, (lg, batch, "forward")
+            cf.set_tuning("cluster", 0)
+            tile_f = gpu_transform(cf, x, N, True, True, False, True)
+            assert "tile_fft_kernel" in cf.last_kernel()
+            assert o.rel_l2(got_f, tile_f) < tol
+            cf.set_tuning("cluster", 1)
+            got_u = gpu_transform(cf, x, N, True, True, False, False)
+            assert "cluster_fft_kernel" in cf.last_kernel()
+            perm = o.np_unordered_map(N, True, 8)
+            assert np.array_equal(got_u, got_f[:, perm])          # unordered == the closed-form permutation of ordered, bit for bit
+            assert np.array_equal(gpu_transform(cf, x, N, True, True, False, True, inplace=True), got_f)
+            got_b = gpu_transform(cf, got_f, N, True, True, True, True)
+            assert "cluster_fft_kernel" in cf.last_kernel()
+            assert o.rel_l2(got_b / N, x) < tol, (lg, batch, "round trip")
+            if ref_lib is not None and lg <= 16 and batch == 1:
+                ref_f, _ = ref_lib.transform(x[:1], N, True, False, True, True)
+                assert o.rel_l2(got_f[:1], ref_f) < tol
+    finally:
+        cf.set_tuning("cluster", -1)
+        cf.set_tuning("cluster_min_batch", -1)
