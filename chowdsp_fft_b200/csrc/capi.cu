@@ -12,6 +12,8 @@
 #include <map>
 #include <mutex>
 #include <new>
+#include <atomic>
+#include <chrono>
 #include <unordered_map>
 #include <vector>
 
@@ -338,7 +340,19 @@ struct PtrInfo
     const void* dev; // pointer a kernel may dereference (Device / Pinned)
 };
 
-PtrInfo classify (const void* p)
+// aligned_malloc blocks are known without asking the driver: base -> (size, pinned, device alias).  Looked up first by
+// classify(); a generation counter (bumped by aligned_free) invalidates the per-thread cache of the last ranges seen.
+struct HostBlock
+{
+    size_t bytes;
+    bool pinned;
+    void* dev; // device alias of a pinned block (cudaHostGetDevicePointer), else nullptr
+};
+std::mutex g_alloc_mutex;
+std::map<uintptr_t, HostBlock> g_allocs;
+std::atomic<unsigned long long> g_alloc_generation { 1 };
+
+PtrInfo classify_slow (const void* p)
 {
     cudaPointerAttributes a {};
     if (cudaPointerGetAttributes (&a, p) != cudaSuccess)
@@ -353,6 +367,44 @@ PtrInfo classify (const void* p)
         case cudaMemoryTypeHost: return { a.devicePointer ? Mem::Pinned : Mem::Pageable, a.devicePointer };
         default: return { Mem::Pageable, nullptr };
     }
+}
+
+// Pointer classification is on the latency path of every drop-in call (two cudaPointerGetAttributes round trips cost more
+// than the launch itself for a 1024-point transform): blocks handed out by aligned_malloc -- what the
+// reference's callers use (test/test.c:19-22, bench/bench.cpp) -- are answered from a thread-local cache of their ranges.
+PtrInfo classify (const void* p)
+{
+    struct Cached
+    {
+        uintptr_t lo = 1, hi = 0;
+        HostBlock blk {};
+        unsigned long long generation = 0;
+    };
+    static thread_local Cached cache[4];
+    static thread_local unsigned next = 0;
+    const uintptr_t u = reinterpret_cast<uintptr_t> (p);
+    const unsigned long long gen = g_alloc_generation.load (std::memory_order_acquire);
+    for (const Cached& c : cache)
+        if (c.generation == gen && u >= c.lo && u < c.hi)
+            return c.blk.pinned ? PtrInfo { Mem::Pinned, static_cast<char*> (c.blk.dev) + (u - c.lo) } : PtrInfo { Mem::Pageable, nullptr };
+    {
+        std::lock_guard<std::mutex> lock (g_alloc_mutex);
+        auto it = g_allocs.upper_bound (u);
+        if (it != g_allocs.begin())
+        {
+            --it;
+            if (u < it->first + it->second.bytes)
+            {
+                Cached& c = cache[next++ & 3u];
+                c.lo = it->first;
+                c.hi = it->first + it->second.bytes;
+                c.blk = it->second;
+                c.generation = gen;
+                return c.blk.pinned ? PtrInfo { Mem::Pinned, static_cast<char*> (c.blk.dev) + (u - c.lo) } : PtrInfo { Mem::Pageable, nullptr };
+            }
+        }
+    }
+    return classify_slow (p);
 }
 
 // per-thread staging: two lanes so H2D of chunk c+1, the kernel of chunk c and D2H of chunk c-1 overlap
@@ -1039,6 +1091,102 @@ int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inne
     return 0;
 }
 
+// Completion of everything enqueued on `stream` so far.  Small drop-in calls (the reference's single-transform loop,
+// bench/bench.cpp:92-97) are latency-bound by the blocking synchronise itself, so for them the stream writes a sequence number
+// into a word of mapped pinned memory right behind the kernel (cuStreamWriteValue32, a stream memory operation: no extra
+// kernel launch) and the host thread spins on that word; anything larger, or a platform without stream memory operations,
+// takes cudaStreamSynchronize.  If the word does not arrive within the spin budget the blocking path reports the outcome.
+using WriteValue32Fn = int (*) (void* stream, unsigned long long dptr, unsigned value, unsigned flags);
+WriteValue32Fn write_value32()
+{
+    static WriteValue32Fn fn = []() -> WriteValue32Fn
+    {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint ("cuStreamWriteValue32", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+        {
+            (void) cudaGetLastError();
+            return nullptr;
+        }
+        return reinterpret_cast<WriteValue32Fn> (p);
+    }();
+    return fn;
+}
+struct SpinFlag
+{
+    volatile unsigned* host = nullptr;
+    unsigned long long dev = 0;
+    unsigned seq = 0;
+    int device = -1;
+    bool broken = false;
+    bool ensure()
+    {
+        int dv = 0;
+        if (broken || cudaGetDevice (&dv) != cudaSuccess)
+            return false;
+        if (host != nullptr && dv == device)
+            return true;
+        release();
+        void *h = nullptr, *d = nullptr;
+        if (cudaHostAlloc (&h, 64, cudaHostAllocMapped) != cudaSuccess || cudaHostGetDevicePointer (&d, h, 0) != cudaSuccess)
+        {
+            (void) cudaGetLastError();
+            if (h != nullptr)
+                (void) cudaFreeHost (h);
+            broken = true;
+            return false;
+        }
+        host = static_cast<volatile unsigned*> (h);
+        *host = 0;
+        dev = reinterpret_cast<unsigned long long> (d);
+        device = dv;
+        return true;
+    }
+    void release()
+    {
+        if (host != nullptr)
+            (void) cudaFreeHost (const_cast<unsigned*> (host));
+        host = nullptr;
+    }
+    ~SpinFlag()
+    {
+        release();
+        (void) cudaGetLastError();
+    }
+};
+thread_local SpinFlag t_spin;
+bool g_spin_sync = true; // tuning hook "spin_sync"
+
+int wait_stream (cudaStream_t stream, bool small_work)
+{
+    const WriteValue32Fn wv = (small_work && g_spin_sync) ? write_value32() : nullptr;
+    if (wv != nullptr && t_spin.ensure())
+    {
+        const unsigned seq = ++t_spin.seq;
+        if (wv (stream, t_spin.dev, seq, 0) == 0)
+        {
+            const auto t0 = std::chrono::steady_clock::now();
+            for (unsigned i = 1;; ++i)
+            {
+                if (*t_spin.host == seq)
+                {
+                    std::atomic_thread_fence (std::memory_order_acquire);
+                    return 0;
+                }
+#if defined(__x86_64__) || defined(__i386__)
+                __builtin_ia32_pause();
+#endif
+                if ((i & 255u) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds (500))
+                    break; // not a small piece of work after all (or a fault): let the blocking synchronise report it
+            }
+        }
+        else
+            t_spin.broken = true; // stream memory operations are not available here: stay on the blocking path
+    }
+    CFB_CUDA (cudaStreamSynchronize (stream));
+    return 0;
+}
+
 // Host-resident batch: chunked H2D -> kernel -> D2H on two alternating lanes.
 int staged_transform (Plan* p, const float* in, float* out, int batch, long long in_stride, long long out_stride, int direction, bool ordered)
 {
@@ -1079,6 +1227,75 @@ int staged_transform (Plan* p, const float* in, float* out, int batch, long long
     return 0;
 }
 
+// Host-resident two-level batches (STFT analysis, fft_transform_strided): transform (o, i) reads in + o in_outer + i in_inner.
+// Per outer index (channel) the UNIQUE input span ((inner - 1) in_inner + nfl floats) is uploaded once -- not one copy per
+// overlapping frame -- in chunks of channels on two alternating lanes (H2D || kernel || D2H); the device-side output is dense.
+// `window` (optional) is a device pointer already.
+int staged_two_level (Plan* p, const float* in, float* out, int outer, int inner, long long in_outer, long long in_inner, long long out_outer, long long out_inner,
+                      int direction, bool ordered, const float* window_dev)
+{
+    const long long nfl = p->is_complex ? 2LL * p->N : p->N;
+    if (in_inner < 0 || out_inner < nfl || (outer > 1 && out_outer < (long long) (inner - 1) * out_inner + nfl))
+        return fail (chowdsp::fft::FFT_B200_EINVAL, "host-memory frame batches need in_inner >= 0 and non-overlapping output rows");
+    const long long span_in = (long long) (inner - 1) * in_inner + nfl;  // floats per outer index
+    const long long span_in_al = (span_in + 3) & ~3LL;                   // device rows stay 16-byte aligned
+    if (outer > 1 && in_outer < span_in && in_outer != 0)
+        return fail (chowdsp::fft::FFT_B200_EINVAL, "host-memory frame batches need channel strides >= the channel's span");
+    const size_t row_out_bytes = (size_t) inner * (size_t) nfl * sizeof (float);
+    int per_chunk = (int) (kChunkBytes / (row_out_bytes > (size_t) span_in_al * 4 ? row_out_bytes : (size_t) span_in_al * 4));
+    per_chunk = per_chunk < 1 ? 1 : (per_chunk > outer ? outer : per_chunk);
+    int lane = 0;
+    for (int o0 = 0; o0 < outer; o0 += per_chunk, lane ^= 1)
+    {
+        const int no = outer - o0 < per_chunk ? outer - o0 : per_chunk;
+        Staging& s = t_staging;
+        int rc = s.ensure (lane, 0, (size_t) span_in_al * 4 * (size_t) no);
+        if (rc == 0)
+            rc = s.ensure (lane, 1, row_out_bytes * (size_t) no);
+        if (rc != 0)
+            return rc;
+        cudaStream_t st = s.stream[lane];
+        CFB_CUDA (cudaMemcpy2DAsync (s.buf[lane][0], (size_t) span_in_al * 4, in + (long long) o0 * in_outer, (size_t) (in_outer != 0 ? in_outer : span_in) * 4, (size_t) span_in * 4,
+                                     (size_t) (in_outer != 0 ? no : 1), cudaMemcpyHostToDevice, st));
+        rc = enqueue_transform (p, s.buf[lane][0], s.buf[lane][1], no, inner, in_outer != 0 ? span_in_al : 0, in_inner, (long long) inner * nfl, nfl, direction, ordered, st, window_dev);
+        if (rc != 0)
+            return rc;
+        if (out_inner == nfl && (no == 1 || out_outer == (long long) inner * nfl))
+            CFB_CUDA (cudaMemcpyAsync (out + (long long) o0 * out_outer, s.buf[lane][1], row_out_bytes * (size_t) no, cudaMemcpyDeviceToHost, st));
+        else if (out_inner == nfl)
+            CFB_CUDA (cudaMemcpy2DAsync (out + (long long) o0 * out_outer, (size_t) out_outer * 4, s.buf[lane][1], row_out_bytes, row_out_bytes, (size_t) no, cudaMemcpyDeviceToHost, st));
+        else
+            for (int o = 0; o < no; ++o)
+                CFB_CUDA (cudaMemcpy2DAsync (out + (long long) (o0 + o) * out_outer, (size_t) out_inner * 4, s.buf[lane][1] + (size_t) o * (size_t) inner * (size_t) nfl, (size_t) nfl * 4,
+                                             (size_t) nfl * 4, (size_t) inner, cudaMemcpyDeviceToHost, st));
+    }
+    for (int l = 0; l < 2; ++l)
+        if (t_staging.stream[l] != nullptr)
+            CFB_CUDA (cudaStreamSynchronize (t_staging.stream[l]));
+    return 0;
+}
+
+// a window given as a host pointer is uploaded once (blocking, N floats) into the calling thread's window slot
+int window_to_device (const float* window, int n, const float*& dev_out)
+{
+    dev_out = nullptr;
+    if (window == nullptr)
+        return 0;
+    const PtrInfo wi = classify (window);
+    if (wi.kind == Mem::Device)
+    {
+        dev_out = static_cast<const float*> (wi.dev);
+        return 0;
+    }
+    Staging& s = t_staging;
+    const int rc = s.ensure (0, 2, (size_t) n * sizeof (float));
+    if (rc != 0)
+        return rc;
+    CFB_CUDA (cudaMemcpy (s.buf[0][2], window, (size_t) n * sizeof (float), cudaMemcpyHostToDevice));
+    dev_out = s.buf[0][2];
+    return 0;
+}
+
 // shared front end of fft_transform / fft_transform_unordered / fft_transform_batched
 int transform_any (void* setup, const float* in, float* out, int batch, long long in_stride, long long out_stride, int direction, bool ordered, cudaStream_t stream, bool force_sync)
 {
@@ -1100,7 +1317,7 @@ int transform_any (void* setup, const float* in, float* out, int batch, long lon
         if (rc != 0)
             return rc;
         if (force_sync)
-            CFB_CUDA (cudaStreamSynchronize (stream));
+            return wait_stream (stream, (long long) batch * nfl <= 65536);
         return 0;
     }
     // host memory
@@ -1113,8 +1330,7 @@ int transform_any (void* setup, const float* in, float* out, int batch, long lon
         const int rc = enqueue_transform (p, static_cast<const float*> (pi.dev), static_cast<float*> (const_cast<void*> (po.dev)), 1, batch, 0, in_stride, 0, out_stride, direction, ordered, st);
         if (rc != 0)
             return rc;
-        CFB_CUDA (cudaStreamSynchronize (st));
-        return 0;
+        return wait_stream (st, true);
     }
     return staged_transform (p, in, out, batch, in_stride, out_stride, direction, ordered);
 }
@@ -1147,7 +1363,7 @@ int elementwise_any (Plan* p, bool convolve, const float* a, const float* b, flo
         if (rc != 0)
             return rc;
         if (force_sync)
-            CFB_CUDA (cudaStreamSynchronize (stream));
+            return wait_stream (stream, (long long) batch * nfl <= 65536);
         return 0;
     }
     const size_t bytes_a = (size_t) ((batch - 1) * a_stride + nfl) * sizeof (float);
@@ -1160,8 +1376,7 @@ int elementwise_any (Plan* p, bool convolve, const float* a, const float* b, flo
         const int rc = run (static_cast<const float*> (ia.dev), static_cast<const float*> (ib.dev), static_cast<float*> (const_cast<void*> (iab.dev)), a_stride, b_stride, ab_stride, st);
         if (rc != 0)
             return rc;
-        CFB_CUDA (cudaStreamSynchronize (st));
-        return 0;
+        return wait_stream (st, true);
     }
     // staged: whole operands through lane 0 (aliasing between host operands is preserved by copying
     // each one separately and writing only ab back)
@@ -1185,9 +1400,6 @@ int elementwise_any (Plan* p, bool convolve, const float* a, const float* b, flo
     return 0;
 }
 
-// registry of aligned_malloc blocks: pinned (cudaHostAlloc) vs plain (posix_memalign)
-std::mutex g_alloc_mutex;
-std::unordered_map<void*, bool> g_allocs; // ptr -> is_pinned
 } // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -1334,21 +1546,24 @@ CFB_API void fft_accumulate (void* setup, const float* a, const float* b, float*
 CFB_API void* aligned_malloc (size_t nb_bytes)
 {
     void* p = nullptr;
-    bool pinned = false;
+    HostBlock blk { nb_bytes > 0 ? nb_bytes : 1, false, nullptr };
     if (device_available())
     {
-        if (cudaHostAlloc (&p, nb_bytes > 0 ? nb_bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped) == cudaSuccess)
-            pinned = true;
+        if (cudaHostAlloc (&p, blk.bytes, cudaHostAllocPortable | cudaHostAllocMapped) == cudaSuccess
+            && cudaHostGetDevicePointer (&blk.dev, p, 0) == cudaSuccess)
+            blk.pinned = true;
         else
         {
             (void) cudaGetLastError();
+            if (p != nullptr)
+                (void) cudaFreeHost (p);
             p = nullptr;
         }
     }
-    if (p == nullptr && posix_memalign (&p, 64, nb_bytes > 0 ? nb_bytes : 1) != 0)
+    if (p == nullptr && posix_memalign (&p, 64, blk.bytes) != 0)
         return nullptr;
     std::lock_guard<std::mutex> lock (g_alloc_mutex);
-    g_allocs[p] = pinned;
+    g_allocs[reinterpret_cast<uintptr_t> (p)] = blk;
     return p;
 }
 
@@ -1359,12 +1574,13 @@ CFB_API void aligned_free (void* p)
     bool pinned = false, known = false;
     {
         std::lock_guard<std::mutex> lock (g_alloc_mutex);
-        auto it = g_allocs.find (p);
+        auto it = g_allocs.find (reinterpret_cast<uintptr_t> (p));
         if (it != g_allocs.end())
         {
-            pinned = it->second;
+            pinned = it->second.pinned;
             known = true;
             g_allocs.erase (it);
+            g_alloc_generation.fetch_add (1, std::memory_order_acq_rel); // per-thread range caches forget the block
         }
     }
     if (! known)
@@ -1395,8 +1611,11 @@ CFB_API int fft_transform_strided (void* setup, const float* input, float* outpu
         return fail (FFT_B200_EINVAL, "fft_transform_strided: bad arguments");
     if (outer == 0 || inner == 0)
         return 0;
-    if (classify (input).kind != Mem::Device || classify (output).kind != Mem::Device)
-        return fail (FFT_B200_EINVAL, "fft_transform_strided needs device pointers");
+    const PtrInfo pi = classify (input), po = classify (output);
+    if ((pi.kind == Mem::Device) != (po.kind == Mem::Device))
+        return fail (FFT_B200_EINVAL, "fft_transform_strided: input and output must both be device memory or both be host memory");
+    if (pi.kind != Mem::Device) // host buffers: synchronous, the unique input span of every outer index is uploaded once
+        return staged_two_level (p, input, output, outer, inner, in_outer, in_inner, out_outer, out_inner, direction, ordered != 0, nullptr);
     return enqueue_transform (p, input, output, outer, inner, in_outer, in_inner, out_outer, out_inner, direction, ordered != 0, static_cast<cudaStream_t> (stream));
 }
 
@@ -1412,31 +1631,27 @@ CFB_API int fft_stft_forward (void* setup, const float* signal, float* spectra, 
         return fail (FFT_B200_EINVAL, "fft_stft_forward: bad arguments");
     if (channels == 0 || frames == 0)
         return 0;
-    if (classify (signal).kind != Mem::Device || classify (spectra).kind != Mem::Device || (window != nullptr && classify (window).kind != Mem::Device))
-        return fail (FFT_B200_EINVAL, "fft_stft_forward needs device pointers");
+    const PtrInfo si = classify (signal), so = classify (spectra);
+    if ((si.kind == Mem::Device) != (so.kind == Mem::Device))
+        return fail (FFT_B200_EINVAL, "fft_stft_forward: signal and spectra must both be device memory or both be host memory");
+    if (si.kind != Mem::Device)
+    {
+        // host audio (the reference API is host-pointer only, chowdsp_fft.h:138): synchronous; every channel's samples cross
+        // PCIe once, the frame overlap is re-read on the device
+        const float* wdev = nullptr;
+        const int rc = window_to_device (window, p->N, wdev);
+        return rc != 0 ? rc : staged_two_level (p, signal, spectra, channels, frames, channel_stride, hop, out_channel_stride, out_frame_stride, FFT_FORWARD, ordered != 0, wdev);
+    }
+    if (window != nullptr && classify (window).kind != Mem::Device)
+        return fail (FFT_B200_EINVAL, "fft_stft_forward: a device signal needs a device window");
     return enqueue_transform (p, signal, spectra, channels, frames, channel_stride, hop, out_channel_stride, out_frame_stride, FFT_FORWARD, ordered != 0, static_cast<cudaStream_t> (stream), window);
 }
 
-CFB_API int fft_istft_overlap_add (void* setup, const float* spectra, float* signal, int channels, int frames, long long spec_channel_stride, long long spec_frame_stride, long long channel_stride, long long hop, const float* window, float scale, int ordered, void* stream)
+namespace
 {
-    CFB_TRACE ("fft_istft_overlap_add");
-    Plan* p = as_plan (setup);
-    if (p == nullptr)
-        return FFT_B200_EINVAL;
-    if (p->is_complex || p->mixed || p->logM > 13)
-        return fail (FFT_B200_EINVAL, "fft_istft_overlap_add needs a REAL power-of-two plan with N <= 16384 (frame buffers + carried tails must fit in shared memory)");
-    if (spectra == nullptr || signal == nullptr || channels < 0 || frames < 0 || hop <= 0 || hop > p->N || (long long) channels * frames > 0x7fffffffLL)
-        return fail (FFT_B200_EINVAL, "fft_istft_overlap_add: bad arguments (0 < hop <= N)");
-    if (misaligned (spectra, ordered != 0 ? 8 : 16, spec_frame_stride, frames, spec_channel_stride, channels))
-        return fail (FFT_B200_EINVAL, "fft_istft_overlap_add: every spectrum frame must start on an 8-byte boundary (16-byte for unordered spectra): check the base pointer and strides");
-    if (window != nullptr && misaligned (window, 8))
-        return fail (FFT_B200_EINVAL, "fft_istft_overlap_add: the window must be 8-byte aligned");
-    if (misaligned (signal, 4))
-        return fail (FFT_B200_EINVAL, "fft_istft_overlap_add: the signal must be 4-byte aligned");
-    if (channels == 0 || frames == 0)
-        return 0;
-    if (classify (spectra).kind != Mem::Device || classify (signal).kind != Mem::Device || (window != nullptr && classify (window).kind != Mem::Device))
-        return fail (FFT_B200_EINVAL, "fft_istft_overlap_add needs device pointers");
+// overlap-add synthesis on device buffers (arguments validated by the caller)
+int istft_enqueue (Plan* p, const float* spectra, float* signal, int channels, int frames, long long spec_channel_stride, long long spec_frame_stride, long long channel_stride, long long hop, const float* window, float scale, int ordered, cudaStream_t stream)
+{
     Tables t;
     const int radix = radix_for (p->logM, false);
     const int rc = plan_tables (p, t, radix);
@@ -1489,7 +1704,7 @@ CFB_API int fft_istft_overlap_add (void* setup, const float* spectra, float* sig
             wa.nseg = nseg;
             wa.scale = scale;
             note_kernel ("cfb::wistft_kernel<%d,%d,%d>", p->logM, wr, (int) (hop / 64));
-            const cudaError_t we = launch_wistft (p->logM, (int) (hop / 64), warps, wa, static_cast<cudaStream_t> (stream));
+            const cudaError_t we = launch_wistft (p->logM, (int) (hop / 64), warps, wa, stream);
             if (we != cudaSuccess)
                 return fail_cuda (we, "warp-pipelined istft kernel launch");
             return 0;
@@ -1536,10 +1751,75 @@ CFB_API int fft_istft_overlap_add (void* setup, const float* spectra, float* sig
     a.scale = scale;
     a.vec4 = ((hop & 3) == 0 && (channel_stride & 3) == 0 && (reinterpret_cast<uintptr_t> (signal) & 15) == 0) ? 1 : 0;
     note_kernel ("cfb::istft_kernel<%d,%d,%d>", p->logM, radix, ordered != 0 ? 0 : p->logW);
-    const cudaError_t e = launch_istft (p->logM, ordered != 0 ? 0 : p->logW, radix, a, static_cast<cudaStream_t> (stream));
+    const cudaError_t e = launch_istft (p->logM, ordered != 0 ? 0 : p->logW, radix, a, stream);
     if (e != cudaSuccess)
         return fail_cuda (e, "istft kernel launch");
     return 0;
+}
+} // namespace
+
+CFB_API int fft_istft_overlap_add (void* setup, const float* spectra, float* signal, int channels, int frames, long long spec_channel_stride, long long spec_frame_stride, long long channel_stride, long long hop, const float* window, float scale, int ordered, void* stream)
+{
+    CFB_TRACE ("fft_istft_overlap_add");
+    Plan* p = as_plan (setup);
+    if (p == nullptr)
+        return FFT_B200_EINVAL;
+    if (p->is_complex || p->mixed || p->logM > 13)
+        return fail (FFT_B200_EINVAL, "fft_istft_overlap_add needs a REAL power-of-two plan with N <= 16384 (frame buffers + carried tails must fit in shared memory)");
+    if (spectra == nullptr || signal == nullptr || channels < 0 || frames < 0 || hop <= 0 || hop > p->N || (long long) channels * frames > 0x7fffffffLL)
+        return fail (FFT_B200_EINVAL, "fft_istft_overlap_add: bad arguments (0 < hop <= N)");
+    if (misaligned (spectra, ordered != 0 ? 8 : 16, spec_frame_stride, frames, spec_channel_stride, channels))
+        return fail (FFT_B200_EINVAL, "fft_istft_overlap_add: every spectrum frame must start on an 8-byte boundary (16-byte for unordered spectra): check the base pointer and strides");
+    if (window != nullptr && misaligned (window, 8))
+        return fail (FFT_B200_EINVAL, "fft_istft_overlap_add: the window must be 8-byte aligned");
+    if (misaligned (signal, 4))
+        return fail (FFT_B200_EINVAL, "fft_istft_overlap_add: the signal must be 4-byte aligned");
+    if (channels == 0 || frames == 0)
+        return 0;
+    const PtrInfo si = classify (spectra), so = classify (signal);
+    if ((si.kind == Mem::Device) != (so.kind == Mem::Device))
+        return fail (FFT_B200_EINVAL, "fft_istft_overlap_add: spectra and signal must both be device memory or both be host memory");
+    if (si.kind != Mem::Device)
+    {
+        // host buffers: synchronous; chunks of channels on two alternating lanes (H2D spectra || kernel || D2H signal)
+        const float* wdev = nullptr;
+        int rc = window_to_device (window, p->N, wdev);
+        if (rc != 0)
+            return rc;
+        if (spec_frame_stride < p->N || (channels > 1 && spec_channel_stride < (long long) (frames - 1) * spec_frame_stride + p->N))
+            return fail (FFT_B200_EINVAL, "fft_istft_overlap_add: host spectra need non-overlapping frames");
+        const long long samples = (long long) (frames - 1) * hop + p->N, samples_al = (samples + 3) & ~3LL;
+        const size_t spec_bytes = (size_t) frames * (size_t) p->N * sizeof (float);
+        int per_chunk = (int) (kChunkBytes / spec_bytes);
+        per_chunk = per_chunk < 1 ? 1 : (per_chunk > channels ? channels : per_chunk);
+        int lane = 0;
+        for (int c0 = 0; c0 < channels; c0 += per_chunk, lane ^= 1)
+        {
+            const int nc = channels - c0 < per_chunk ? channels - c0 : per_chunk;
+            Staging& sg = t_staging;
+            rc = sg.ensure (lane, 0, spec_bytes * (size_t) nc);
+            if (rc == 0)
+                rc = sg.ensure (lane, 1, (size_t) samples_al * 4 * (size_t) nc);
+            if (rc != 0)
+                return rc;
+            cudaStream_t st = sg.stream[lane];
+            for (int c = 0; c < nc; ++c) // frames packed densely on the device
+                CFB_CUDA (cudaMemcpy2DAsync (sg.buf[lane][0] + (size_t) c * (size_t) frames * (size_t) p->N, (size_t) p->N * 4, spectra + (long long) (c0 + c) * spec_channel_stride,
+                                             (size_t) spec_frame_stride * 4, (size_t) p->N * 4, (size_t) frames, cudaMemcpyHostToDevice, st));
+            rc = istft_enqueue (p, sg.buf[lane][0], sg.buf[lane][1], nc, frames, (long long) frames * p->N, p->N, samples_al, hop, wdev, scale, ordered, st);
+            if (rc != 0)
+                return rc;
+            CFB_CUDA (cudaMemcpy2DAsync (signal + (long long) c0 * channel_stride, (size_t) (nc > 1 ? channel_stride : samples) * 4, sg.buf[lane][1], (size_t) samples_al * 4, (size_t) samples * 4,
+                                         (size_t) nc, cudaMemcpyDeviceToHost, st));
+        }
+        for (int l = 0; l < 2; ++l)
+            if (t_staging.stream[l] != nullptr)
+                CFB_CUDA (cudaStreamSynchronize (t_staging.stream[l]));
+        return 0;
+    }
+    if (window != nullptr && classify (window).kind != Mem::Device)
+        return fail (FFT_B200_EINVAL, "fft_istft_overlap_add: device spectra need a device window");
+    return istft_enqueue (p, spectra, signal, channels, frames, spec_channel_stride, spec_frame_stride, channel_stride, hop, window, scale, ordered, static_cast<cudaStream_t> (stream));
 }
 
 // ---- JUCE-convention wrappers (reference chowdsp_fft_juce/chowdsp_fft_juce.cpp:32-86), batched ----
@@ -2148,6 +2428,11 @@ CFB_API int fft_accumulate_batched (void* setup, const float* a, const float* b,
 
 CFB_API int fft_b200_set_tuning (const char* key, int value)
 {
+    if (key != nullptr && std::strcmp (key, "spin_sync") == 0 && value >= -1 && value <= 1)
+    {
+        g_spin_sync = value != 0;
+        return 0;
+    }
     if (key != nullptr && std::strcmp (key, "cluster") == 0 && value >= -1 && value <= 1)
     {
         g_cluster = value == -1 ? kClusterDefault : value;

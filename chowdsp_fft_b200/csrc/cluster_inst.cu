@@ -47,6 +47,24 @@ cudaError_t make_input_map (const float* in, long long in_stride, int batch, Ten
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+// 3-D view of the natural-order output: [batch][N / 512 rows][1024 floats]; one CTA's part of a spectrum is the box
+// { 2 RUN floats, 16 G rows } at column 2 RUN g: bins RUN g + r + 512 (kb + G ka)
+template <int LOGG>
+cudaError_t make_output_map (float* out, long long out_stride, int batch, TensorMap4& map)
+{
+    using CG = ClusterGeo<LOGG>;
+    const EncodeTiledFn enc = encode_tiled();
+    if (enc == nullptr)
+        return cudaErrorNotSupported;
+    const cuuint64_t dims[3] = { 1024, (cuuint64_t) (16 * CG::G), (cuuint64_t) batch };
+    const cuuint64_t strides[2] = { 4096, (cuuint64_t) out_stride * 4ull };
+    const cuuint32_t box[3] = { (cuuint32_t) (2 * CG::RUN), (cuuint32_t) (16 * CG::G), 1 };
+    const cuuint32_t estr[3] = { 1, 1, 1 };
+    const CUresult r = enc (reinterpret_cast<CUtensorMap*> (&map), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, out, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 template <int LOGG, int DIR, int LOGW>
 cudaError_t launch_cluster_one (const float* in, long long in_stride, const ClusterArgs& a, cudaStream_t stream)
 {
@@ -85,12 +103,16 @@ cudaError_t launch_cluster_one (const float* in, long long in_stride, const Clus
     }
     if (a.batch <= 0)
         return cudaSuccess;
-    TensorMap4 tm;
+    TensorMap4 tm, om;
     if ((e = make_input_map<LOGG> (in, in_stride, a.batch, tm)) != cudaSuccess)
+        return e;
+    if (LOGW != 0)
+        om = tm; // unused by the kernel
+    else if ((e = make_output_map<LOGG> (a.out, a.out_stride, a.batch, om)) != cudaSuccess)
         return e;
     const int clusters = a.batch < c_clusters ? a.batch : c_clusters;
     cfg.gridDim = dim3 ((unsigned) (clusters * CG::G));
-    e = cudaLaunchKernelEx (&cfg, kernel, tm, a);
+    e = cudaLaunchKernelEx (&cfg, kernel, tm, om, a);
     count_launch();
     return e != cudaSuccess ? e : cudaGetLastError();
 }

@@ -38,7 +38,9 @@ int fft_transform_batched (void* setup, const float* input, float* output, int b
 
 /* Two-level batch: transform (o, i), o < outer, i < inner, reads input + o*in_outer + i*in_inner and
    writes output + o*out_outer + i*out_inner.  Input windows may overlap (STFT frame gather:
-   in_inner = hop, in_outer = channel stride); outputs must not.  Device pointers only. */
+   in_inner = hop, in_outer = channel stride); outputs must not.  Device pointers: stream-ordered.  Host pointers (both
+   buffers; the reference API is host-pointer only): synchronous, the UNIQUE input span of every outer index crosses PCIe
+   once, in chunks overlapped with the kernels and the downloads (needs in_inner >= 0 and in_outer >= that span). */
 int fft_transform_strided (void* setup, const float* input, float* output, int outer, int inner, long long in_outer, long long in_inner, long long out_outer, long long out_inner, fft_direction_t direction, int ordered, void* stream);
 
 /* Short-time Fourier analysis of `channels` real signals: frame f of channel c is the N samples at
@@ -46,7 +48,8 @@ int fft_transform_strided (void* setup, const float* input, float* output, int o
    is non-NULL (NULL = rectangular, which is what a loop over reference chowdsp_fft.h:138 computes), and its
    forward real transform is written to spectra + c*out_channel_stride + f*out_frame_stride (N floats,
    ordered pffft packing or the unordered layout).  One kernel, the window multiply is fused into the load.
-   Device pointers only; hop and channel_stride must be even. */
+   hop and channel_stride must be even.  Device pointers: stream-ordered.  Host pointers (signal and spectra; the window
+   may live on either side): synchronous, every channel's samples are uploaded once -- not once per overlapping frame. */
 int fft_stft_forward (void* setup, const float* signal, float* spectra, int channels, int frames, long long channel_stride, long long hop, long long out_channel_stride, long long out_frame_stride, const float* window, int ordered, void* stream);
 
 /* Overlap-add synthesis (inverse STFT) of `channels` signals from `frames` spectra each: the backward real transform
@@ -56,7 +59,8 @@ int fft_stft_forward (void* setup, const float* signal, float* spectra, int chan
    WRITTEN (the sum of the frames covering it), so the buffer needs no clearing.  Unnormalised like the reference:
    scale = 1/N undoes fft_stft_forward for a rectangular window at hop = N.  This is the step the reference leaves
    to its callers around fft_transform (BACKWARD) and fft_accumulate (chowdsp_fft.h:138,160); here it is one kernel,
-   owner-computes (no atomics, bit-reproducible).  0 < hop <= N, even spectrum strides, N <= 16384, device pointers. */
+   owner-computes (no atomics, bit-reproducible).  0 < hop <= N, even spectrum strides, N <= 16384.  Device pointers:
+   stream-ordered.  Host pointers (spectra and signal): synchronous, staged in chunks of channels. */
 int fft_istft_overlap_add (void* setup, const float* spectra, float* signal, int channels, int frames, long long spec_channel_stride, long long spec_frame_stride, long long channel_stride, long long hop, const float* window, float scale, int ordered, void* stream);
 
 /* The conventions of the reference's JUCE adapter (chowdsp_fft_juce/chowdsp_fft_juce.cpp:32-86), batched and fused
@@ -170,6 +174,8 @@ void fft_b200_clear_error (void);
      "wistft"       bit 0: overlap-add synthesis through the warp-pipelined kernel where it applies (default); bits 8..: warps per CTA
      "stft_pipe", "stft_union"  older frame-gather variants (persistent CTA-level TMA union / LDS-STS union staging), off
      "tile_c", "tile_c_jfast"   transforms per tile of the multi-pass kernels (8, 16, or 0 = built-in policy)
+     "spin_sync"    1 = small synchronous drop-in calls wait on a stream-written word in mapped memory instead of
+                    cudaStreamSynchronize (default), 0 = always the blocking synchronise
      "cluster"      1 = complex transforms of 2^15 .. 2^17 points run in one pass on a thread-block cluster (default), 0 = tile passes;
                     "cluster_min_batch": smaller batches stay with the tile passes (default 8)
      "l2_chunk_mb"  MiB of intermediate per chunk of the L2-chunked multi-pass schedules (default 16, applied up to 2^24 points;

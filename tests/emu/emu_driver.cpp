@@ -695,13 +695,18 @@ int emu_cluster_fft (int logG, int backward, int unord, const float* in, float* 
         a.tw_lo = lo.data();
         a.tw_hi = hi.data();
         a.tw_lobits = lobits;
+        TensorMap4 om {};
+        om.base = reinterpret_cast<const char*> (out);
+        om.dim[0] = 1024; om.dim[1] = 16 * CG::G; om.dim[2] = (unsigned long long) batch;
+        om.stride[0] = 4096; om.stride[1] = (unsigned long long) N * 8;
+        om.box[0] = 2 * CG::RUN; om.box[1] = 16 * CG::G; om.box[2] = 1;
         const dim3 grid ((unsigned) (nclusters * CG::G)), block (CG::THREADS);
         if (backward)
-            emu::launch_cluster (cluster_fft_kernel<LOGG, +1, 0>, grid, CG::G, block, (size_t) CG::SMEM_BYTES, tm, a);
+            emu::launch_cluster (cluster_fft_kernel<LOGG, +1, 0>, grid, CG::G, block, (size_t) CG::SMEM_BYTES, tm, om, a);
         else if (unord)
-            emu::launch_cluster (cluster_fft_kernel<LOGG, -1, 3>, grid, CG::G, block, (size_t) CG::SMEM_BYTES, tm, a);
+            emu::launch_cluster (cluster_fft_kernel<LOGG, -1, 3>, grid, CG::G, block, (size_t) CG::SMEM_BYTES, tm, om, a);
         else
-            emu::launch_cluster (cluster_fft_kernel<LOGG, -1, 0>, grid, CG::G, block, (size_t) CG::SMEM_BYTES, tm, a);
+            emu::launch_cluster (cluster_fft_kernel<LOGG, -1, 0>, grid, CG::G, block, (size_t) CG::SMEM_BYTES, tm, om, a);
         return 0;
     };
     emu::g_log_smem = log_conflicts != 0;

@@ -1092,3 +1092,45 @@ def test_cluster_one_pass_transform(cf, oracle_mod, ref_lib, lg):
     finally:
         cf.set_tuning("cluster", -1)
         cf.set_tuning("cluster_min_batch", -1)
+
+
+def test_host_pointer_stft_istft_and_strided(cf, oracle_mod):
+    """the extended entry points accept HOST buffers like the reference API does (chowdsp_fft.h:138):
+    fft_stft_forward / fft_transform_strided upload every channel's unique samples once (not once per overlapping frame),
+    fft_istft_overlap_add stages spectra in and the signal out.  Results are bit-identical to the device-pointer calls."""
+    o = oracle_mod
+    N, hop, frames, ch = 2048, 512, 61, 37
+    samples = (frames - 1) * hop + N
+    rng = np.random.default_rng(3)
+    sig = rng.uniform(-1, 1, (ch, samples + 6)).astype(np.float32)  # channel stride > span
+    win = (0.5 - 0.5 * np.cos(2 * np.pi * (np.arange(N) + 0.5) / N)).astype(np.float32)
+    s = cf.fft_new_setup(N, cf.FFT_REAL)
+    dsig, dwin = dev(sig), dev(win)
+    for ordered in (True, False):
+        for w_host, w_dev in ((None, None), (win, dwin)):
+            dspec = torch.empty(ch, frames, N, device="cuda")
+            cf.fft_stft_forward(s, dsig, dspec, ch, frames, sig.shape[1], hop, frames * N, N, w_dev, ordered)
+            torch.cuda.synchronize()
+            hspec = np.full((ch, frames, N), np.nan, np.float32)
+            cf.fft_stft_forward(s, sig, hspec, ch, frames, sig.shape[1], hop, frames * N, N, w_host, ordered)
+            assert np.array_equal(hspec, host(dspec)), (ordered, w_host is not None)
+            fr = np.stack([sig[5, f * hop:f * hop + N] * (win if w_host is not None else 1.0) for f in range(frames)]).astype(np.float32)
+            assert o.rel_l2(hspec[5], o.np_transform(fr, N, False, 8, False, ordered)) < o.parity_tol(N)
+            # synthesis from host spectra
+            dout = torch.empty(ch, samples, device="cuda")
+            cf.fft_istft_overlap_add(s, dspec, dout, ch, frames, frames * N, N, samples, hop, w_dev, 1.0 / N, ordered)
+            torch.cuda.synchronize()
+            hout = np.full((ch, samples + 2), np.nan, np.float32)
+            cf.fft_istft_overlap_add(s, hspec, hout, ch, frames, frames * N, N, samples + 2, hop, w_host, 1.0 / N, ordered)
+            assert np.array_equal(hout[:, :samples], host(dout))
+            assert np.isnan(hout[:, samples:]).all()  # nothing beyond a channel's span is touched
+    # plain two-level strided batch from host memory, no window
+    hspec = np.full((ch, frames, N), np.nan, np.float32)
+    cf.fft_transform_strided(s, sig, hspec, ch, frames, sig.shape[1], hop, frames * N, N, cf.FFT_FORWARD, True)
+    dspec = torch.empty(ch, frames, N, device="cuda")
+    cf.fft_transform_strided(s, dsig, dspec, ch, frames, sig.shape[1], hop, frames * N, N, cf.FFT_FORWARD, True)
+    torch.cuda.synchronize()
+    assert np.array_equal(hspec, host(dspec))
+    with pytest.raises(cf.FFTError):  # mixing host and device buffers is rejected
+        cf.fft_stft_forward(s, sig, dspec, ch, frames, sig.shape[1], hop, frames * N, N, None, True)
+    cf.fft_destroy_setup(s)
