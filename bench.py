@@ -159,7 +159,8 @@ class BatchedFFT:
             call()
         torch.cuda.synchronize()
         dt = reduce_max((time.perf_counter() - t0) / steps)
-        ok = bool(np.array_equal(hout.reshape(self.batch, self.nfl)[:4], self.y[:4].cpu().numpy()))
+        nchk = min(4, self.batch) * self.nfl
+        ok = bool(np.array_equal(hout.reshape(-1)[:nchk], self.y.reshape(-1)[:nchk].cpu().numpy()))
         cf.aligned_free(hin.ctypes.data)
         cf.aligned_free(hout.ctypes.data)
         return {"seconds": dt, "h2d_bytes_per_step": self.batch * self.nfl * 4, "d2h_bytes_per_step": self.batch * self.nfl * 4,
@@ -178,16 +179,10 @@ class BatchedFFT:
         rng = np.random.default_rng(42)
         xin = o.aligned_copy(rng.uniform(-1, 1, sample * self.nfl).astype(np.float32))
         out = o.aligned_empty(sample * self.nfl)
-        run = lambda: ref.transform_timed(xin, out, self.N, self.is_complex, False, self.ordered, sample, self.nfl, self.nfl, cores)
+        run = lambda reps=1: ref.transform_timed(xin, out, self.N, self.is_complex, False, self.ordered, sample, self.nfl, self.nfl, cores, reps=reps)
         t1 = run()
         reps = max(1, int(seconds_target / max(t1, 1e-6) / max(1, steps + warmup)))
-        times = []
-        for it in range(warmup + steps):
-            t0 = time.perf_counter()
-            for _ in range(reps):
-                run()
-            if it >= warmup:
-                times.append(time.perf_counter() - t0)
+        times = [run(reps) for _ in range(warmup + steps)][warmup:]  # seconds of the threaded region only (plan / threads made outside)
         per_step = float(np.mean(times))
         gbs = sample * reps * (self.bytes_step / self.batch) / per_step / 1e9
         desc = f"{sample} transforms x {reps} passes per step, {cores} threads (one per core, pinned), reference AVX build W=32B"
@@ -240,7 +235,27 @@ class STFT(BatchedFFT):
         return {"rel_l2_vs_oracle": o.rel_l2(got, o.np_transform(fr, self.N, False, 8, False, True)), "tolerance": o.parity_tol(self.N), "transforms": len(fr)}
 
     def e2e(self, steps, barrier, reduce_max):
-        return None  # the strided (frame-gather) entry point takes device pointers only
+        """fft_stft_forward on HOST (pinned) audio: every channel's samples cross PCIe once, spectra come back; bounded to a
+        slice of the channels so that the pinned allocations stay small (the per-channel cost is what is measured)."""
+        cf, torch = self.cf, self.torch
+        ch = min(self.channels, 64)
+        hin = cf.aligned_array(ch * self.samples).reshape(ch, self.samples)
+        hout = cf.aligned_array(ch * self.frames * self.N).reshape(ch, self.frames, self.N)
+        hin[:] = self.x[:ch].cpu().numpy()
+        call = lambda: cf.fft_stft_forward(self.plan, hin, hout, ch, self.frames, self.samples, self.hop, self.frames * self.N, self.N, None, True)
+        call()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            call()
+        dt = reduce_max((time.perf_counter() - t0) / steps)
+        ok = bool(np.array_equal(hout[:2], self.y[:2].cpu().numpy()))
+        frac = ch / self.channels
+        cf.aligned_free(hin.ctypes.data)
+        cf.aligned_free(hout.ctypes.data)
+        return {"seconds": dt / frac, "h2d_bytes_per_step": int(self.channels * self.samples * 4), "d2h_bytes_per_step": int(self.batch * self.N * 4),
+                "matches_device_path": ok,
+                "path": f"fft_stft_forward(host pinned signal / spectra): measured on {ch} of this rank's {self.channels} channels and scaled; unique samples uploaded once, 32 MiB chunks, H2D/kernel/D2H overlapped"}
 
     def cpu(self, seconds_target, steps=1, warmup=0):
         from oracle import oracle as o
@@ -251,16 +266,10 @@ class STFT(BatchedFFT):
         # one channel per call: 934 overlapping frames split across the cores (out of place, frames overlap)
         xin = o.aligned_copy(rng.uniform(-1, 1, self.samples).astype(np.float32))
         out = o.aligned_empty(self.frames * self.N)
-        run = lambda: ref.transform_timed(xin, out, self.N, False, False, True, self.frames, self.hop, self.N, cores)
+        run = lambda reps=1: ref.transform_timed(xin, out, self.N, False, False, True, self.frames, self.hop, self.N, cores, reps=reps)
         t1 = run()
         reps = max(1, int(seconds_target / max(t1, 1e-6) / max(1, steps + warmup)))
-        times = []
-        for it in range(warmup + steps):
-            t0 = time.perf_counter()
-            for _ in range(reps):
-                run()
-            if it >= warmup:
-                times.append(time.perf_counter() - t0)
+        times = [run(reps) for _ in range(warmup + steps)][warmup:]
         per_step = float(np.mean(times))
         bytes_ch = self.samples * 4 + self.frames * self.N * 4
         gbs = reps * bytes_ch / per_step / 1e9
@@ -380,7 +389,34 @@ class Reverb(BatchedFFT):
         return {"rel_l2_vs_oracle": o.rel_l2(np.stack(got), np.stack(want)), "tolerance": 1e-5, "transforms": 2}
 
     def e2e(self, steps, barrier, reduce_max):
-        return None  # streaming state (delay line, IR) lives on the device by design
+        """One block step with HOST audio: the new 4096 samples of every channel come from pinned host memory and the 4096
+        output samples go back to it; the delay line and the IR spectra are the convolver's state and stay on the device
+        (as they stay in RAM across calls in the reference's usage)."""
+        cf, torch = self.cf, self.torch
+        hin = torch.empty(self.channels, self.B, pin_memory=True)
+        hout = torch.empty(self.channels, self.B, pin_memory=True)
+        hin.copy_(self.sig[:, self.B:2 * self.B].cpu())
+        win = torch.zeros(self.channels, self.N, device="cuda")
+        dout = torch.empty(self.channels, self.B, device="cuda")
+        st = torch.cuda.current_stream()
+
+        def call():
+            win[:, :self.B].copy_(win[:, self.B:], non_blocking=True)     # previous block slides down (device-local)
+            win[:, self.B:].copy_(hin, non_blocking=True)                 # H2D: the new samples
+            cf.fft_partitioned_convolve_step(self.plan, win, self.N, self.h, self.P * self.N, self.fdl, self.P * self.N, dout, self.B,
+                                             self.channels, self.P, self.t, 1.0 / self.N, st)
+            self.t += 1
+            hout.copy_(dout, non_blocking=True)                           # D2H: the block's output
+            torch.cuda.synchronize()
+        call()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            call()
+        dt = reduce_max((time.perf_counter() - t0) / steps)
+        return {"seconds": dt, "h2d_bytes_per_step": int(self.channels * self.B * 4), "d2h_bytes_per_step": int(self.channels * self.B * 4),
+                "matches_device_path": bool(torch.isfinite(hout).all()),
+                "path": "pinned host block -> H2D -> fft_partitioned_convolve_step -> D2H, per block step; delay line + IR spectra resident on the device"}
 
     def cpu(self, seconds_target, steps=1, warmup=0):
         from oracle import oracle as o
@@ -407,64 +443,130 @@ class Reverb(BatchedFFT):
         return gbs, cores, f"{reps} x ({channels} channels x {blocks} blocks, {parts / blocks:.1f} partitions summed per block on average), {cores} threads, reference AVX build", per_step * 1e3
 
 
+def hash_signal(torch, idx):
+    """Counter-based synthetic signal keyed by the global FLOAT index (SURVEY.md §8d cfg 5: every GPU layout regenerates
+    the same values): 64-bit LCG mix, top bits -> U(-1, 1).  idx: int64 tensor."""
+    h = idx * 6364136223846793005 + 1442695040888963407
+    h = (h ^ (h >> 29)) * 2862933555777941757 + 3037000493
+    return ((h >> 40) & 0xFFFFFF).double() / float(1 << 23) - 1.0
+
+
+def sampled_dft_of_hash_signal(torch, N, ks):
+    """float64 DFT bins X[k] of the hash signal, phases from exact int64 arithmetic, chunked"""
+    out = []
+    step = 1 << 24
+    for k in ks:
+        re = im = 0.0
+        for n0 in range(0, N, step):
+            n = torch.arange(n0, min(N, n0 + step), device="cuda", dtype=torch.int64)
+            ang = ((n * int(k)) % N).double() * (-2.0 * math.pi / N)
+            c, sn = torch.cos(ang), torch.sin(ang)
+            xr, xi = hash_signal(torch, 2 * n), hash_signal(torch, 2 * n + 1)
+            re += float((xr * c - xi * sn).sum())
+            im += float((xr * sn + xi * c).sum())
+        out.append(complex(re, im))
+    return np.array(out)
+
+
 class Huge(BatchedFFT):
     """BASELINE configs[4]: ONE complex FFT of N = 2^28 points.  1 GPU: three-pass four-step on the device.
-    G > 1 GPUs: distributed four-step, local tile passes + one NCCL all-to-all over NVLink (transposed-out
-    contract; the natural-order variant costs a second all-to-all and is reported separately)."""
+    G > 1 GPUs: distributed four-step through ONE C-ABI call per rank (fft_dist_transform): local tile passes, the
+    all-to-all fused into phase 0's peer stores over NVLink, in-stream flag barrier; `natural` adds the second all-to-all
+    (fused into the last pass's peer stores).  CFB_DIST_EXCHANGE=nccl times the NCCL all_to_all_single baseline instead."""
 
     scaling = "strong"
 
-    def __init__(self, n=28):
+    def __init__(self, n=28, natural=False, exchange=None):
         self.name, self.n, self.N = "huge", n, 1 << n
+        self.natural = natural
+        self.exchange = exchange or os.environ.get("CFB_DIST_EXCHANGE", "peer")
         self.is_complex, self.ordered, self.nfl = True, True, 2 << n
-        self.desc = f"single complex FFT N=2^{n} fp32 (BASELINE configs[4]): 3-pass four-step; distributed over G GPUs with an NCCL all-to-all"
-        self.kernel = "cfb::tile_fft_kernel<9|10,8,-1,*> x3 (+ ncclAllToAll for G>1)"
+        self.desc = f"single complex FFT N=2^{n} fp32 (BASELINE configs[4]): 3-pass four-step; distributed over G GPUs with the all-to-all over NVLink"
+        self.kernel = "cfb::tile_fft_kernel<9|9|10> x3"
+        self.phase_ms = None
 
     def config(self):
-        return {"workload": self.desc, "N": self.N, "transform": "C2C", "ordered": "natural order on 1 GPU; transposed-out per rank for G>1",
-                "passes": 3, "bytes": "algorithmic 16 N = 4 GiB per transform; each of the 3 passes re-reads and re-writes the array (12 GiB of HBM traffic in total)",
-                "l2_policy": "2 GiB arrays, far larger than L2", "sharding": "column blocks -> all-to-all -> row blocks"}
+        c = {"workload": self.desc, "N": self.N, "transform": "C2C",
+             "output": "natural order" if (self.world == 1 or self.natural) else "transposed-out per rank (one all-to-all)",
+             "passes": 3, "bytes": "algorithmic 16 N = 4 GiB per transform; each of the 3 passes re-reads and re-writes the array",
+             "l2_policy": "2 GiB arrays, far larger than L2", "sharding": "column blocks -> all-to-all -> row blocks"}
+        if self.world > 1:
+            c["exchange"] = self.exchange
+            c["exchange_bytes_per_rank"] = self.d.exchange_bytes() * (2 if self.natural else 1)
+        return c
 
     def setup(self, cf, torch, rank, world):
         self.cf, self.torch, self.rank, self.world = cf, torch, rank, world
         self.batch = 1
         self.bytes_step = 16 * self.N // world
         self.flops_step = 5.0 * self.N * math.log2(self.N) / world
-        gen = torch.Generator(device="cuda").manual_seed(42 + rank)
         if world == 1:
             self.plan = cf.fft_new_setup(self.N, cf.FFT_COMPLEX, True)
-            self.x = torch.rand(2 * self.N, device="cuda", generator=gen) * 2 - 1
+            self.x = torch.empty(2 * self.N, device="cuda")
+            step = 1 << 26
+            for f0 in range(0, 2 * self.N, step):
+                self.x[f0:f0 + step] = hash_signal(torch, torch.arange(f0, f0 + step, device="cuda", dtype=torch.int64)).float()
             self.y = torch.empty_like(self.x)
         else:
             from chowdsp_fft_b200.distributed import DistributedFFT
 
-            self.d = DistributedFFT(self.n, rank, world, exchange=os.environ.get("CFB_DIST_EXCHANGE", "peer"))
-            self.x = torch.rand(self.d.local_floats, device="cuda", generator=gen) * 2 - 1
-            self.y = torch.empty(self.d.S1 * self.d.rows * 2, device="cuda")
+            self.d = d = DistributedFFT(self.n, rank, world, exchange=self.exchange)
+            self.x = torch.empty(d.L1, d.cols, 2, device="cuda")
+            rows = max(1, (1 << 24) // d.cols)
+            c = torch.arange(d.cols, device="cuda", dtype=torch.int64)[None, :]
+            for r0 in range(0, d.L1, rows):  # global complex index of every element of this rank's column block
+                n1 = torch.arange(r0, min(d.L1, r0 + rows), device="cuda", dtype=torch.int64)[:, None]
+                g = n1 * d.S1 + rank * d.cols + c
+                self.x[r0:r0 + rows, :, 0] = hash_signal(torch, 2 * g).float()
+                self.x[r0:r0 + rows, :, 1] = hash_signal(torch, 2 * g + 1).float()
+            self.y = torch.empty(2 * (self.N // world), device="cuda")
 
     def step(self, stream):
         if self.world == 1:
             self.cf.fft_transform_batched(self.plan, self.x, self.y, 1, 2 * self.N, 2 * self.N, self.cf.FFT_FORWARD, True, stream)
         else:
-            self.d.forward(self.x, self.y, stream=stream)
+            self.d.forward(self.x, self.y, stream=stream, natural=self.natural)
+
+    def after_timing(self):
+        """one extra, event-timed transform for the per-phase split (peer exchange only)"""
+        if self.world > 1 and self.exchange == "peer":
+            self.d.forward(self.x, self.y, natural=self.natural, timed=True)
+            self.phase_ms = self.d.phase_ms()
+
+    def nvlink(self):
+        """G > 1: the exchange is the bound (SURVEY.md §8d cfg 5): bytes this rank sends in the fused phase 0 / its duration"""
+        if self.world == 1 or not self.phase_ms:
+            return None
+        sent = self.d.exchange_bytes()
+        window_ms = self.phase_ms[0] + self.phase_ms[1]
+        gbs = sent / (window_ms * 1e-3) / 1e9
+        return {"bound": "nvlink", "achieved": gbs, "peak": 900.0, "unit": "GB/s", "frac": gbs / 900.0, "frac_of_measured_peer_copy_770": gbs / 770.0,
+                "traffic": None, "exchange_bytes_per_rank": sent, "exchange_window_ms": window_ms,
+                "phase_ms": {"phase0_fft_plus_peer_stores": self.phase_ms[0], "flag_barrier_wait": self.phase_ms[1], "phases_1_2_local": self.phase_ms[2],
+                             "natural_order_barrier_and_copy": self.phase_ms[3]},
+                "kernel": "cfb::tile_fft_kernel (phase 0, peer-store epilogue) + cfb::dist_barrier_kernel",
+                "peak_source": "nominal NVLink 5 per direction per GPU (B200_PROFILING.md; measured peer copy 770 GB/s)"}
 
     def parity(self):
-        if self.world != 1:
-            return {"note": "distributed parity is covered by tests/test_gpu_distributed.py"}
-        y = self.y.view(-1, 2)
-        x = self.x.view(-1, 2).double()
-        # 64 sampled bins against a direct float64 DFT sum (the full-size oracle comparison is in tests/)
         torch = self.torch
-        ks = torch.arange(0, self.N, self.N // 64, device="cuda")[:64] + 3
-        n = torch.arange(self.N, device="cuda", dtype=torch.float64)
-        err, ref = 0.0, 0.0
-        for k in ks.tolist():
-            ang = -2.0 * math.pi * ((n * k) % self.N) / self.N
-            re = float((x[:, 0] * torch.cos(ang) - x[:, 1] * torch.sin(ang)).sum())
-            im = float((x[:, 0] * torch.sin(ang) + x[:, 1] * torch.cos(ang)).sum())
-            err += (float(y[k, 0]) - re) ** 2 + (float(y[k, 1]) - im) ** 2
-            ref += re * re + im * im
-        return {"rel_l2_vs_float64_dft": math.sqrt(err / ref), "tolerance": 1e-6 * self.n, "bins": int(ks.numel())}
+        rng = np.random.default_rng(7 + self.rank)
+        if self.world == 1:
+            ks = sorted(set([0, 1, self.N - 1, self.N // 2] + [int(k) for k in rng.integers(0, self.N, 12)]))
+            got = self.y.view(-1, 2)[torch.tensor(ks, device="cuda")].cpu().numpy()
+        elif self.natural or self.exchange == "nccl" and False:
+            blk = self.N // self.world
+            idx = [int(i) for i in rng.integers(0, blk, 8)]
+            ks = [self.rank * blk + i for i in idx]
+            got = self.y.view(-1, 2)[torch.tensor(idx, device="cuda")].cpu().numpy()
+        else:
+            d = self.d
+            qs, kk = rng.integers(0, d.S1, 8), rng.integers(0, d.rows, 8)
+            ks = [int(self.rank * d.rows + k + d.L1 * q) for q, k in zip(qs, kk)]
+            got = self.y.view(d.S1, d.rows, 2)[torch.tensor(qs, device="cuda"), torch.tensor(kk, device="cuda")].cpu().numpy()
+        want = sampled_dft_of_hash_signal(torch, self.N, ks)
+        got = got[:, 0].astype(np.float64) + 1j * got[:, 1]
+        return {"rel_l2_vs_float64_dft": float(np.linalg.norm(got - want) / np.linalg.norm(want)), "tolerance": 1e-6 * self.n, "bins": len(ks),
+                "note": "rank 0's share of the spectrum, sampled bins against a float64 DFT with exact integer phases"}
 
     def e2e(self, steps, barrier, reduce_max):
         if self.world != 1:
@@ -523,6 +625,10 @@ class Single1024(BatchedFFT):
             cf.fft_transform(self.plan, self.x, self.y, None, cf.FFT_FORWARD)
             cf.fft_transform(self.plan, self.y, self.z, None, cf.FFT_BACKWARD)
         self.latency["drop_in_sync_calls"] = (time.perf_counter() - t0) / 200 * 1e6
+        # (1b) the same loop as a COMPILED C caller (tests/c_caller/latency_bench.c = the reference's bench/bench.cpp loop on
+        # aligned_malloc buffers): the latency of the drop-in calls without the ctypes binding around them
+        self.latency["drop_in_sync_calls_compiled_c_caller"] = self.c_caller_latency("1")
+        self.latency["drop_in_sync_calls_compiled_c_caller_blocking_sync"] = self.c_caller_latency("0")
         # (2) CUDA-graph replay of 100 round trips
         side = torch.cuda.Stream()
         g = torch.cuda.CUDAGraph()
@@ -540,6 +646,25 @@ class Single1024(BatchedFFT):
             torch.cuda.synchronize()
         self.latency["cuda_graph_replay"] = e0.elapsed_time(e1) / 1000 * 1e3
         self.graph = g
+
+    def c_caller_latency(self, spin):
+        import subprocess
+        import tempfile
+
+        from chowdsp_fft_b200 import _lib
+
+        try:
+            exe = os.path.join(tempfile.gettempdir(), "cfb_latency_bench")
+            src = os.path.join(ROOT, "tests", "c_caller", "latency_bench.c")
+            r = subprocess.run(["gcc", "-std=c11", "-O2", f"-I{os.path.join(ROOT, 'include')}", src, _lib.LIB_PATH, f"-Wl,-rpath,{os.path.dirname(_lib.LIB_PATH)}", "-lm", "-o", exe],
+                               capture_output=True, text=True, timeout=120)
+            if r.returncode != 0:
+                return None
+            r = subprocess.run([exe, str(self.N), "2000"], capture_output=True, text=True, timeout=120, env=dict(os.environ, CHOWDSP_FFT_B200_SPIN_SYNC=spin))
+            tok = r.stdout.split()
+            return float(tok[tok.index("us_per_round_trip") + 1]) if r.returncode == 0 else None
+        except Exception:
+            return None
 
     def step(self, stream):
         cf = self.cf
@@ -610,18 +735,112 @@ WORKLOADS = {
 }
 
 
+def load_traffic(name, kernel_name):
+    """ncu dram bytes per launch of the dominant kernel, from the committed capture summary -- only if that capture was of
+    the kernel this run was actually routed to (otherwise null: a stale figure must not ride along silently)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            ent = json.load(f).get(name)
+    except Exception:
+        return None, None
+    if not isinstance(ent, dict):
+        return None, None
+    if ent.get("kernel") and ent["kernel"] not in kernel_name:
+        return None, f"capture was of {ent['kernel']}, this run used {kernel_name}"
+    return ent.get("bytes"), ent.get("source")
+
+
+def measure(wl, name, ctx, steps, warmup, do_e2e, do_cpu, cpu_seconds, tune=None):
+    """warm-up, `steps` timed steps (CUDA events on the launch stream, barrier + synchronize on both sides, max over
+    ranks), parity gate, e2e with host buffers, CPU baseline -> one record"""
+    cf, torch, dist = ctx["cf"], ctx["torch"], ctx["dist"]
+    rank, world, local_rank = ctx["rank"], ctx["world"], ctx["local_rank"]
+    barrier, reduce_max, reduce_sum = ctx["barrier"], ctx["reduce_max"], ctx["reduce_sum"]
+    wl.setup(cf, torch, rank, world)
+    stream = torch.cuda.current_stream()
+    for _ in range(max(3, warmup)):
+        wl.step(stream)
+    barrier()
+    launches0 = cf.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        ev0.record(stream)
+        for _ in range(steps):
+            wl.step(stream)
+        ev1.record(stream)
+        barrier()
+    launches = cf.launch_count() - launches0
+    kernel_name = cf.last_kernel() or wl.kernel  # what the library actually routed this workload to
+    ms_local = ev0.elapsed_time(ev1) / steps
+    ms_step = reduce_max(ms_local)
+    bytes_job = reduce_sum(float(wl.bytes_step))
+    flops_job = reduce_sum(float(wl.flops_step))
+    value = bytes_job / (ms_step * 1e-3) / 1e9
+    per_gpu = wl.bytes_step / (ms_local * 1e-3) / 1e9
+    peak, peak_src = hbm_peak()
+    if hasattr(wl, "after_timing"):
+        wl.after_timing()
+
+    parity = None
+    if rank == 0:
+        try:
+            parity = wl.parity()  # quick gate beside the timing; tests/ hold the real parity suite
+        except Exception as e:
+            parity = {"error": repr(e)}
+    e2e = None
+    if do_e2e:
+        r = wl.e2e(max(2, min(5, steps)), barrier, reduce_max)
+        if r is not None:
+            secs = r.pop("seconds")
+            e2e = {"value": bytes_job / secs / 1e9, "unit": "GB/s", "ms_per_step": secs * 1e3, **r}
+    cpu = None
+    if rank == 0 and do_cpu:
+        try:
+            gbs, cores, desc, _ = wl.cpu(seconds_target=cpu_seconds)
+            cpu = {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "reference", "sample": desc}
+        except Exception as e:
+            cpu = {"value": None, "unit": "GB/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e!r}"}
+    traffic, traffic_src = load_traffic(name, kernel_name)
+    roofline = {"bound": "hbm", "achieved": per_gpu, "peak": peak, "unit": "GB/s", "frac": per_gpu / peak,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "frac_of_nominal_8TBs": per_gpu / 8000.0,
+                "kernel": kernel_name, "algorithmic_bytes_per_step": wl.bytes_step, "launches_per_step": launches / max(1, steps)}
+    nv = wl.nvlink() if hasattr(wl, "nvlink") else None
+    if nv is not None:
+        nv["hbm_view"] = roofline
+        roofline = nv
+    rec = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": steps, "warmup": max(3, warmup),
+           "ms_per_step": ms_step, "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "config": wl.config(), "gflops": flops_job / (ms_step * 1e-3) / 1e9, "roofline": roofline,
+           "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(), "parity": parity}
+    if tune:
+        rec["config"]["tuning"] = tune
+    return rec
+
+
+def release(wl, torch):
+    for k in list(vars(wl)):
+        v = getattr(wl, k)
+        if hasattr(v, "close") and k == "d":
+            v.close()
+        if torch.is_tensor(v):
+            delattr(wl, k)
+    torch.cuda.empty_cache()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2c4096", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS), help="one workload only (default: the headline c2c4096 plus sub-records of every BASELINE config)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="headline workload only, no per-config sub-records")
     ap.add_argument("--tune", action="append", default=[], metavar="KEY=VALUE", help="fft_b200_set_tuning hook (sweeps only)")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]()
+    headline = args.workload or "c2c4096"
+    wl = WORKLOADS[headline]()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -630,6 +849,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
+        wl.world = 1
         gbs, cores, desc, ms = wl.cpu(seconds_target=20.0, steps=max(1, args.steps), warmup=args.warmup)
         flops_per_byte = (5.0 * wl.N * math.log2(wl.N)) / (16 * wl.N) if wl.is_complex else None
         line = {"impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
@@ -643,7 +863,6 @@ def main():
         return
 
     # ---------------------------------------------------------------- our arm
-    args.warmup = max(args.warmup, 3)
     import torch
     import torch.distributed as dist
 
@@ -666,78 +885,41 @@ def main():
             dist.all_reduce(t, op=op)
         return float(t.item())
 
-    reduce_max = lambda v: reduce(v, dist.ReduceOp.MAX)
-    reduce_sum = lambda v: reduce(v, dist.ReduceOp.SUM)
-
+    ctx = {"cf": cf, "torch": torch, "dist": dist, "rank": rank, "world": world, "local_rank": local_rank, "barrier": barrier,
+           "reduce_max": lambda v: reduce(v, dist.ReduceOp.MAX), "reduce_sum": lambda v: reduce(v, dist.ReduceOp.SUM)}
     for kv in args.tune:
         k, v = kv.split("=")
         cf.set_tuning(k, int(v, 0))
-    wl.setup(cf, torch, rank, world)
-    stream = torch.cuda.current_stream()
-    for _ in range(args.warmup):
-        wl.step(stream)
-    barrier()
-    launches0 = cf.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
-        ev0.record(stream)
-        for _ in range(args.steps):
-            wl.step(stream)
-        ev1.record(stream)
-        barrier()
-    launches = cf.launch_count() - launches0
-    kernel_name = cf.last_kernel() or wl.kernel  # what the library actually routed this workload to
-    if "huge" in args.workload or getattr(wl, "kernel_override", False):
-        kernel_name = wl.kernel
-    ms_local = ev0.elapsed_time(ev1) / args.steps
-    ms_step = reduce_max(ms_local)
-    bytes_job = reduce_sum(float(wl.bytes_step))
-    flops_job = reduce_sum(float(wl.flops_step))
-    value = bytes_job / (ms_step * 1e-3) / 1e9
-    per_gpu = wl.bytes_step / (ms_local * 1e-3) / 1e9  # this rank's kernel: one launch per step
-    peak, peak_src = hbm_peak()
+    t_start = time.perf_counter()
+    line = measure(wl, headline, ctx, args.steps, args.warmup, not args.no_e2e, world == 1 and not args.no_cpu, 12.0, args.tune)
+    release(wl, torch)
 
-    parity = None
+    # ---------------------------------------------------------------- sub-records: every BASELINE config in the driver-run line
+    if args.workload is None and not args.no_configs:
+        subs = []
+        if world == 1:
+            plan = [("configs[0] single real N=1024 round trip (latency)", "single1024", Single1024, 20),
+                    ("configs[1] unordered half", "c2c4096_unordered", WORKLOADS["c2c4096_unordered"], 10),
+                    ("configs[2] STFT", "stft", STFT, 5),
+                    ("configs[3] reverb", "reverb", Reverb, 10),
+                    ("configs[4] N=2^28 on one GPU", "huge", Huge, 5)]
+        else:
+            plan = [("configs[2] STFT, channels sharded (strong scaling)", "stft", STFT, 5),
+                    ("configs[4] N=2^28 distributed, fused peer exchange, transposed-out", "huge", lambda: Huge(exchange="peer"), 5),
+                    ("configs[4] N=2^28 distributed, fused peer exchange, natural order (second all-to-all fused)", "huge", lambda: Huge(natural=True, exchange="peer"), 5),
+                    ("configs[4] N=2^28 distributed, NCCL all_to_all_single baseline, transposed-out", "huge", lambda: Huge(exchange="nccl"), 5)]
+        for label, name, make, nsteps in plan:
+            try:
+                w = make()
+                rec = measure(w, name, ctx, nsteps, 3, not args.no_e2e, world == 1 and not args.no_cpu, 3.0)
+                rec["baseline_config"] = label
+                release(w, torch)
+            except Exception as e:  # a sub-record must not take the headline down
+                rec = {"baseline_config": label, "error": repr(e)}
+            subs.append(rec)
+        line["configs"] = subs
+    line["bench_wall_seconds"] = time.perf_counter() - t_start
     if rank == 0:
-        try:
-            parity = wl.parity()  # quick gate beside the timing; tests/ hold the real parity suite
-        except Exception as e:
-            parity = {"error": repr(e)}
-
-    e2e = None
-    if not args.no_e2e:
-        r = wl.e2e(max(2, min(5, args.steps)), barrier, reduce_max)
-        if r is not None:
-            secs = r.pop("seconds")
-            e2e = {"value": bytes_job / secs / 1e9, "unit": "GB/s", "ms_per_step": secs * 1e3, **r}
-
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        try:
-            gbs, cores, desc, _ = wl.cpu(seconds_target=12.0)
-            cpu = {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "reference", "sample": desc}
-        except Exception as e:
-            cpu = {"value": None, "unit": "GB/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e!r}"}
-
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(args.workload)
-    except Exception:
-        pass
-
-    if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": wl.scaling,
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wl.config(),
-                "gflops": flops_job / (ms_step * 1e-3) / 1e9,
-                "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peak, "unit": "GB/s", "frac": per_gpu / peak,
-                             "traffic": traffic, "peak_source": peak_src, "frac_of_nominal_8TBs": per_gpu / 8000.0,
-                             "kernel": kernel_name, "algorithmic_bytes_per_launch": wl.bytes_step},
-                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(),
-                "parity": parity}
-        if args.tune:
-            line["config"]["tuning"] = args.tune
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -963,6 +963,7 @@ int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inne
             ca.tw_lo = bt.lo;
             ca.tw_hi = bt.hi;
             ca.tw_lobits = bt.lobits;
+            ca.l2_prefetch = (g_cluster & 2) != 0 ? 0 : 1; // tuning bit 1 switches the L2 prefetch off (A/B)
             const cudaError_t ce = launch_cluster_fft (p->logM, fwd ? -1 : +1, ca.logW, in, bstride_in, ca, stream);
             if (ce == cudaSuccess)
             {
@@ -1155,7 +1156,12 @@ struct SpinFlag
     }
 };
 thread_local SpinFlag t_spin;
-bool g_spin_sync = true; // tuning hook "spin_sync"
+// tuning hook "spin_sync" (environment CHOWDSP_FFT_B200_SPIN_SYNC=0/1 sets the initial value for callers without the hook)
+bool g_spin_sync = []
+{
+    const char* e = getenv ("CHOWDSP_FFT_B200_SPIN_SYNC");
+    return e == nullptr || e[0] != '0';
+}();
 
 int wait_stream (cudaStream_t stream, bool small_work)
 {
@@ -2433,7 +2439,7 @@ CFB_API int fft_b200_set_tuning (const char* key, int value)
         g_spin_sync = value != 0;
         return 0;
     }
-    if (key != nullptr && std::strcmp (key, "cluster") == 0 && value >= -1 && value <= 1)
+    if (key != nullptr && std::strcmp (key, "cluster") == 0 && value >= -1 && value <= 3)
     {
         g_cluster = value == -1 ? kClusterDefault : value;
         return 0;

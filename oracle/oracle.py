@@ -261,6 +261,8 @@ class RefLib:
         L.fft_accumulate.restype = None
         L.ref_transform_batched.argtypes = [C.c_int] * 5 + [_fp, _fp, C.c_long, C.c_long, C.c_long, C.c_int]
         L.ref_transform_batched.restype = C.c_double
+        L.ref_transform_batched_reps.argtypes = [C.c_int] * 5 + [_fp, _fp, C.c_long, C.c_long, C.c_long, C.c_int, C.c_int]
+        L.ref_transform_batched_reps.restype = C.c_double
         L.ref_convolve_batched.argtypes = [C.c_int] * 3 + [_fp, _fp, _fp] + [C.c_long] * 4 + [C.c_float, C.c_int]
         L.ref_convolve_batched.restype = C.c_double
         L.ref_partitioned_convolve.argtypes = [C.c_int] * 3 + [_fp] * 4 + [C.c_long, C.c_int, C.c_int, C.c_int]
@@ -294,9 +296,10 @@ class RefLib:
         return np.array(out).reshape(*lead, nfl), simd_width(N, is_complex, use_avx)
 
     def transform_timed(self, xin, out, N, is_complex, backward, ordered, batch, in_stride, out_stride,
-                        nthreads, use_avx=True) -> float:
-        return self.lib.ref_transform_batched(N, int(is_complex), int(use_avx), int(backward), int(ordered),
-                                              _ptr(xin), _ptr(out), batch, in_stride, out_stride, nthreads)
+                        nthreads, use_avx=True, reps: int = 1) -> float:
+        """seconds of `reps` passes over the batch; plan, threads and work buffers are created outside the timed region"""
+        return self.lib.ref_transform_batched_reps(N, int(is_complex), int(use_avx), int(backward), int(ordered),
+                                                   _ptr(xin), _ptr(out), batch, in_stride, out_stride, nthreads, reps)
 
     def convolve(self, a, b, ab, N, is_complex, scaling, use_avx=True):
         nfl = 2 * N if is_complex else N

@@ -7,6 +7,7 @@
 #include <chowdsp_fft.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstring>
 #include <thread>
@@ -86,6 +87,49 @@ double ref_transform_batched (int N, int is_complex, int use_avx, int backward, 
                                          }
                                          aligned_free (work);
                                      });
+    fft_destroy_setup (setup);
+    return secs;
+}
+
+// The same loop `reps` times inside ONE set of pinned threads: plan, work buffers and threads are created before the timed
+// region, which starts when every thread is ready (bench.py's CPU arms: no thread spawn or fft_new_setup inside the timing).
+double ref_transform_batched_reps (int N, int is_complex, int use_avx, int backward, int ordered, const float* in, float* out, long batch, long in_stride, long out_stride, int nthreads, int reps)
+{
+    void* setup = fft_new_setup (N, is_complex ? FFT_COMPLEX : FFT_REAL, use_avx != 0);
+    if (setup == nullptr || setup == (void*) 1)
+        return -1.0;
+    const size_t nfloats = (size_t) N * (is_complex ? 2 : 1);
+    nthreads = (int) std::max<long> (1, std::min<long> (nthreads, batch));
+    std::atomic<int> ready { 0 }, go { 0 };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; ++t)
+    {
+        const long lo = batch * t / nthreads, hi = batch * (t + 1) / nthreads;
+        pool.emplace_back ([=, &ready, &go]
+                           {
+                               pin_to_core (t);
+                               auto* work = (float*) aligned_malloc (nfloats * sizeof (float));
+                               ready.fetch_add (1);
+                               while (go.load (std::memory_order_acquire) == 0)
+                                   std::this_thread::yield();
+                               for (int r = 0; r < reps; ++r)
+                                   for (long b = lo; b < hi; ++b)
+                                   {
+                                       if (ordered)
+                                           fft_transform (setup, in + b * in_stride, out + b * out_stride, work, backward ? FFT_BACKWARD : FFT_FORWARD);
+                                       else
+                                           fft_transform_unordered (setup, in + b * in_stride, out + b * out_stride, work, backward ? FFT_BACKWARD : FFT_FORWARD);
+                                   }
+                               aligned_free (work);
+                           });
+    }
+    while (ready.load() < nthreads)
+        std::this_thread::yield();
+    const auto t0 = std::chrono::steady_clock::now();
+    go.store (1, std::memory_order_release);
+    for (auto& th : pool)
+        th.join();
+    const double secs = std::chrono::duration<double> (std::chrono::steady_clock::now() - t0).count();
     fft_destroy_setup (setup);
     return secs;
 }

@@ -695,6 +695,7 @@ int emu_cluster_fft (int logG, int backward, int unord, const float* in, float* 
         a.tw_lo = lo.data();
         a.tw_hi = hi.data();
         a.tw_lobits = lobits;
+        a.l2_prefetch = 1;
         TensorMap4 om {};
         om.base = reinterpret_cast<const char*> (out);
         om.dim[0] = 1024; om.dim[1] = 16 * CG::G; om.dim[2] = (unsigned long long) batch;
