@@ -536,7 +536,10 @@ int g_pf_ahead = 0;        // tuning hook "pf_ahead": L2 prefetch distance of th
 // (cluster_kernels.cuh) where the batch layout allows, 0 = always the multi-pass tile path; "cluster_min_batch": batches
 // smaller than this stay with the tile path (a cluster kernel runs one transform per cluster: a single transform would
 // occupy 4 .. 16 of the 148 SMs)
-constexpr int kClusterDefault = 1, kClusterMinBatchDefault = 8;
+// Default OFF: measured on B200 (profiles/r02_cluster_kernel.txt) the one-pass cluster kernel reaches 2.9 / 2.6 / 2.3 TB/s at
+// 2^15 / 2^16 / 2^17 points against 3.0 / 3.3 / 3.2 TB/s of the two tile passes -- its transform-long critical path (input
+// barrier, cluster barrier, exchange barrier, store) is exposed with only two CTAs per SM to overlap it.
+constexpr int kClusterDefault = 0, kClusterMinBatchDefault = 8;
 int g_cluster = kClusterDefault, g_cluster_min_batch = kClusterMinBatchDefault;
 
 constexpr size_t kZeroCopyBytes = 256 * 1024;     // pinned buffers up to this size are used in place
@@ -1157,10 +1160,13 @@ struct SpinFlag
 };
 thread_local SpinFlag t_spin;
 // tuning hook "spin_sync" (environment CHOWDSP_FFT_B200_SPIN_SYNC=0/1 sets the initial value for callers without the hook)
+// Default OFF: measured with the compiled caller (tests/c_caller/latency_bench.c, profiles/r02_latency.txt) the stream-written
+// word costs 16.5 us per call against 15.1 us for the blocking synchronise -- the stream memory operation is submitted as its
+// own command and adds more than the spin saves.
 bool g_spin_sync = []
 {
     const char* e = getenv ("CHOWDSP_FFT_B200_SPIN_SYNC");
-    return e == nullptr || e[0] != '0';
+    return e != nullptr && e[0] == '1';
 }();
 
 int wait_stream (cudaStream_t stream, bool small_work)
@@ -2436,7 +2442,7 @@ CFB_API int fft_b200_set_tuning (const char* key, int value)
 {
     if (key != nullptr && std::strcmp (key, "spin_sync") == 0 && value >= -1 && value <= 1)
     {
-        g_spin_sync = value != 0;
+        g_spin_sync = value == 1;
         return 0;
     }
     if (key != nullptr && std::strcmp (key, "cluster") == 0 && value >= -1 && value <= 3)

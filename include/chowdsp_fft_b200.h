@@ -175,9 +175,10 @@ void fft_b200_clear_error (void);
      "stft_pipe", "stft_union"  older frame-gather variants (persistent CTA-level TMA union / LDS-STS union staging), off
      "tile_c", "tile_c_jfast"   transforms per tile of the multi-pass kernels (8, 16, or 0 = built-in policy)
      "spin_sync"    1 = small synchronous drop-in calls wait on a stream-written word in mapped memory instead of
-                    cudaStreamSynchronize (default), 0 = always the blocking synchronise
-     "cluster"      1 = complex transforms of 2^15 .. 2^17 points run in one pass on a thread-block cluster (default), 0 = tile passes;
-                    "cluster_min_batch": smaller batches stay with the tile passes (default 8)
+                    cudaStreamSynchronize; default 0 (measured 1.4 us slower per call on B200)
+     "cluster"      1 = complex transforms of 2^15 .. 2^17 points run in one pass on a thread-block cluster (csrc/cluster_kernels.cuh),
+                    0 = two tile passes (default: the cluster kernel measured 5..30 % slower); bit 1 (value 3) = without the
+                    tensor-map L2 prefetch; "cluster_min_batch": smaller batches stay with the tile passes (default 8)
      "l2_chunk_mb"  MiB of intermediate per chunk of the L2-chunked multi-pass schedules (default 16, applied up to 2^24 points;
                     0 = whole-array passes everywhere; -m (m >= 2) = m MiB chunks at every size)
      "l2_lanes"     helper streams / ring slots the chunks alternate over (1..4, default 3)
