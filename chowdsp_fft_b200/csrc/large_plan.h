@@ -13,6 +13,8 @@ namespace cfb
 constexpr int kTileCMax = 16;
 inline int& tile_c_override() { static int v = 0; return v; }       // tuning hooks (0 = policy below)
 inline int& tile_c_jfast_override() { static int v = 0; return v; } // ... for the contiguous-row (last) pass only
+// tuning hook "tile_r": 1 = 32 complex points per thread in the 512- / 1024-point tile passes (two Stockham stages instead of three)
+inline int& tile_radix32() { static int v = 0; return v; }
 inline int tile_c (int logL, bool jfast = false)
 {
     const int ov = (jfast && tile_c_jfast_override() != 0) ? tile_c_jfast_override() : tile_c_override();

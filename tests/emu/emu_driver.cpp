@@ -71,25 +71,36 @@ namespace
 {
 // multi-pass complex transform of 2^n points through the tile kernels (factors forced by the caller so that
 // small sizes can exercise the two- and three-pass plans); in/out interleaved complex, natural order
-template <int LOGL, int C, int DIR>
-void emu_tile_launch_c (const TilePass& p)
+template <int LOGL, int C, int DIR, int R>
+void emu_tile_launch_cr (const TilePass& p)
 {
-    using TL = TileLaunch<LOGL, C>;
+    using TL = TileLaunch<LOGL, C, R>;
     const dim3 grid ((unsigned) p.args.ntiles * (unsigned) p.args.batch), block (TL::THREADS);
     if (p.uio == 1)
     {
         if constexpr (DIR > 0)
-            emu::launch (tile_fft_kernel<LOGL, C, +1, false, 1>, grid, block, (size_t) TL::SMEM_BYTES, p.args);
+            emu::launch (tile_fft_kernel<LOGL, C, +1, false, 1, R>, grid, block, (size_t) TL::SMEM_BYTES, p.args);
     }
     else if (p.uio == 2)
     {
         if constexpr (DIR < 0)
-            emu::launch (tile_fft_kernel<LOGL, C, -1, true, 2>, grid, block, (size_t) TL::SMEM_BYTES, p.args);
+            emu::launch (tile_fft_kernel<LOGL, C, -1, true, 2, R>, grid, block, (size_t) TL::SMEM_BYTES, p.args);
     }
     else if (p.load_j_fast)
-        emu::launch (tile_fft_kernel<LOGL, C, DIR, true, 0>, grid, block, (size_t) TL::SMEM_BYTES, p.args);
+        emu::launch (tile_fft_kernel<LOGL, C, DIR, true, 0, R>, grid, block, (size_t) TL::SMEM_BYTES, p.args);
     else
-        emu::launch (tile_fft_kernel<LOGL, C, DIR, false, 0>, grid, block, (size_t) TL::SMEM_BYTES, p.args);
+        emu::launch (tile_fft_kernel<LOGL, C, DIR, false, 0, R>, grid, block, (size_t) TL::SMEM_BYTES, p.args);
+}
+template <int LOGL, int C, int DIR>
+void emu_tile_launch_c (const TilePass& p)
+{
+    if constexpr (LOGL >= 9 && (C == 8 || LOGL == 9))
+        if (tile_radix32() != 0)
+        {
+            emu_tile_launch_cr<LOGL, C, DIR, 32> (p);
+            return;
+        }
+    emu_tile_launch_cr<LOGL, C, DIR, 16> (p);
 }
 template <int LOGL, int DIR>
 void emu_tile_launch (const TilePass& p)
@@ -118,6 +129,13 @@ int emu_tile_dispatch (const TilePass& p)
 template <int LOGL>
 void fill_tw_for (std::vector<float2>& tw)
 {
+    if constexpr (LOGL >= 9)
+        if (tile_radix32() != 0) // must match emu_tile_launch_c
+        {
+            tw.assign ((size_t) Geo<LOGL, 32>::TW_LEN + 1, float2 { 0, 0 });
+            fill_stage_twiddles<LOGL, 32> (tw.data());
+            return;
+        }
     tw.assign ((size_t) Geo<LOGL, 16>::TW_LEN + 1, float2 { 0, 0 });
     fill_stage_twiddles<LOGL, 16> (tw.data());
 }
@@ -486,6 +504,7 @@ int emu_pconv (int logM, int logW, const float* in, long long in_stride, const f
 }
 
 void emu_set_tile_c (int c) { tile_c_override() = c; }
+void emu_set_tile_r (int r) { tile_radix32() = r; }
 void emu_set_radix (int r) { g_emu_radix = r; }
 
 // batch transforms of 2^n complex points through build_large_schedule: classic whole-array passes (chunk_elems = 0) or the

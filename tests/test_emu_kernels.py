@@ -240,12 +240,16 @@ def _emu_large(emu, n, l1, l2, l3, backward, x, batch=1, logw=0, chunk_elems=0, 
     return out, list(st)
 
 
-@pytest.mark.parametrize("tile_c", [8, 16])
+@pytest.mark.parametrize("tile_c,tile_r", [(8, 0), (16, 0), (8, 1), (16, 1)])
 @pytest.mark.parametrize("n,l1,l2,l3", [(12, 6, 0, 6), (13, 6, 0, 7), (15, 7, 0, 8), (18, 6, 6, 6), (15, 9, 0, 6), (15, 6, 0, 9), (16, 10, 0, 6), (16, 6, 0, 10)])
-def test_emulated_multi_pass_transform(emu, n, l1, l2, l3, tile_c):
+def test_emulated_multi_pass_transform(emu, n, l1, l2, l3, tile_c, tile_r):
     """Tile kernels + pass planning of the large-transform path (two- and three-pass four-step), with the
-    factorisation forced so that small sizes exercise it; both tile widths; bank-conflict free exchanges."""
+    factorisation forced so that small sizes exercise it; both tile widths; 16 and 32 points per thread (tile_r: the
+    512- / 1024-point passes in two Stockham stages); bank-conflict free exchanges."""
+    if tile_r and max(l1, l2, l3) < 9:
+        pytest.skip("no 512- / 1024-point pass in this plan")
     emu.emu_set_tile_c(tile_c)
+    emu.emu_set_tile_r(tile_r)
     N = 1 << n
     rng = np.random.default_rng(n)
     x = rng.uniform(-1, 1, 2 * N).astype(np.float32)
@@ -258,6 +262,7 @@ def test_emulated_multi_pass_transform(emu, n, l1, l2, l3, tile_c):
         if n <= 16:
             assert st[1] <= 1.15 * st[2] and st[3] <= 150, list(st)  # (nearly) conflict free
     emu.emu_set_tile_c(0)
+    emu.emu_set_tile_r(0)
 
 
 @pytest.mark.parametrize("n,l1,l2,l3,batch,chunk_elems,lanes", [

@@ -1134,3 +1134,26 @@ def test_host_pointer_stft_istft_and_strided(cf, oracle_mod):
     with pytest.raises(cf.FFTError):  # mixing host and device buffers is rejected
         cf.fft_stft_forward(s, sig, dspec, ch, frames, sig.shape[1], hop, frames * N, N, None, True)
     cf.fft_destroy_setup(s)
+
+
+def test_tile_passes_with_32_points_per_thread(cf, oracle_mod):
+    """tuning hook tile_r = 1: the 512- / 1024-point tile passes of the multi-pass path with 32 complex points per thread (two
+    Stockham stages, one shared-memory exchange fewer).  Same transforms within tolerance, every layout and direction."""
+    o = oracle_mod
+    rng = np.random.default_rng(32)
+    try:
+        cf.set_tuning("tile_r", 1)
+        cf.set_tuning("cluster", 0)
+        for lg, is_c in [(19, True), (20, True), (22, True), (21, False), (27, True)]:
+            N = 1 << lg
+            nfl = 2 * N if is_c else N
+            x = rng.uniform(-1, 1, (2 if lg < 27 else 1, nfl)).astype(np.float32)
+            for ordered in (True, False):
+                got_f = gpu_transform(cf, x, N, is_c, True, False, ordered)
+                if lg <= 22:
+                    assert o.rel_l2(got_f[:1], o.np_transform(x[:1], N, is_c, 8, False, ordered)) < o.parity_tol(N), (lg, is_c, ordered)
+                got_b = gpu_transform(cf, got_f, N, is_c, True, True, ordered)
+                assert o.rel_l2(got_b / N, x) < o.parity_tol(N), (lg, is_c, ordered, "round trip")
+    finally:
+        cf.set_tuning("tile_r", -1)
+        cf.set_tuning("cluster", -1)
