@@ -533,8 +533,15 @@ class Huge(BatchedFFT):
     def after_timing(self):
         """one extra, event-timed transform for the per-phase split (peer exchange only); it also fills self.y for the parity gate"""
         if self.world > 1 and self.exchange == "peer":
+            import torch.distributed as dist
+
+            torch = self.torch
+            torch.cuda.synchronize()
+            dist.barrier()  # every rank starts its phase 0 together: the exchange is timed under the full all-to-all load
             self.d.forward(self.x, self.y, natural=self.natural, timed=True)
-            self.phase_ms = self.d.phase_ms()
+            t = torch.tensor(self.d.phase_ms(), device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)  # slowest rank per phase
+            self.phase_ms = [float(v) for v in t.tolist()]
 
     def nvlink(self):
         """G > 1: the exchange is the bound (SURVEY.md §8d cfg 5): bytes this rank sends in the fused phase 0 / its duration"""
@@ -908,9 +915,9 @@ def main():
                     ("configs[4] N=2^28 on one GPU", "huge", Huge, 5)]
         else:
             plan = [("configs[2] STFT, channels sharded (strong scaling)", "stft", STFT, 5),
-                    ("configs[4] N=2^28 distributed, fused peer exchange, transposed-out", "huge", lambda: Huge(exchange="peer"), 5),
-                    ("configs[4] N=2^28 distributed, fused peer exchange, natural order (second all-to-all fused)", "huge", lambda: Huge(natural=True, exchange="peer"), 5),
-                    ("configs[4] N=2^28 distributed, NCCL all_to_all_single baseline, transposed-out", "huge", lambda: Huge(exchange="nccl"), 5)]
+                    ("configs[4] N=2^28 distributed, fused peer exchange, transposed-out", "huge", lambda: Huge(exchange="peer"), 10),
+                    ("configs[4] N=2^28 distributed, fused peer exchange, natural order (second all-to-all fused)", "huge", lambda: Huge(natural=True, exchange="peer"), 10),
+                    ("configs[4] N=2^28 distributed, NCCL all_to_all_single baseline, transposed-out", "huge", lambda: Huge(exchange="nccl"), 10)]
         for label, name, make, nsteps in plan:
             try:
                 w = make()

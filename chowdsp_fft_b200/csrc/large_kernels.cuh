@@ -15,6 +15,7 @@
 // twiddle scheme and exchange code are the ones of the single-kernel transform (fft_kernels.cuh).
 #pragma once
 #include "fft_kernels.cuh"
+#include "tma.cuh"
 
 
 namespace cfb
@@ -317,6 +318,193 @@ __global__ void __launch_bounds__ (TileLaunch<LOGL, C, R>::THREADS, TileLaunch<L
 {
     tile_body<LOGL, C, DIR, LOAD_J_FAST, UIO, R> (a);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Persistent tile kernel with tensor-map TMA on both sides (round 2).  ncu on tile_fft_kernel (profiles/r02_tile_passes.txt):
+// DRAM 56..59 %, issue slots 40 %, L1 60 % -- nothing saturated; the top stall is the long scoreboard of the strided gather
+// (4.5..4.9 warps per issue): two 512-thread CTAs per SM that load -> compute -> store in near lock step do not keep enough
+// bytes in flight.  Here ONE resident CTA per SM loops over tiles; a tile arrives in a landing slot by ONE
+// cp.async.bulk.tensor copy per 256 rows (a box of C contiguous values x rows -- the per-row bulk copies of round 1's
+// tile_pipe_kernel were TMA-issue bound), the NEXT tile's copy is issued before the current tile is touched (two slots),
+// and the result leaves the same way: staged as the tile's output image in the slot it came from, written by one
+// tensor-map store per 256 rows.  No LSU instruction touches global memory; 128 KB of loads stay in flight per SM.
+// Same butterflies, exchange layout and four-step twiddle as tile_fft_kernel; natural-order data on both sides, no peer
+// stores, no split input rows (those cases keep tile_fft_kernel).
+// Shared memory: [slot 0][slot 1][exchange regions + twiddle rows as tile_fft_kernel][2 mbarriers].
+// ---------------------------------------------------------------------------------------------
+struct TileTmaCoords
+{
+    // coordinates of tile (ghi, glo) of batch element bx, per tensor-map dimension: c = base + ghi * per_hi + glo * per_lo
+    // (+ bx in the batch dimension, + the row / chunk index the kernel iterates over in `iter_dim`)
+    int per_hi[5], per_lo[5];
+    int batch_dim, iter_dim;
+    int iters, iter_step; // copies per tile and the coordinate step between them (rows per box)
+};
+
+template <int LOGL, int C, int R = 16>
+struct TileTmaLaunch
+{
+    using TL = TileLaunch<LOGL, C, R>;
+    using G = Geo<LOGL, R>;
+    static constexpr int THREADS = TL::THREADS;
+    static constexpr int SLOT_BYTES = G::M * C * 8;
+    static constexpr int XCH_OFFSET = 2 * SLOT_BYTES;
+    static constexpr int BAR_OFFSET = XCH_OFFSET + TL::SMEM_BYTES;
+    static constexpr int SMEM_BYTES = BAR_OFFSET + 16;
+    static constexpr bool FITS = SMEM_BYTES <= 227 * 1024 && THREADS <= 1024;
+    static constexpr int ROWS_PER_BOX = G::M < 256 ? G::M : 256; // strided side: element rows per tensor copy
+};
+
+template <int LOGL, int C, int DIR, bool LOAD_J_FAST, int R>
+FFT_HD void tile_tma_body (const TensorMap5* imap, const TensorMap5* omap, const TileArgs& a, const TileTmaCoords& ic, const TileTmaCoords& oc)
+{
+    using G = Geo<LOGL, R>;
+    using TT = TileTmaLaunch<LOGL, C, R>;
+    constexpr int T = G::T, L = G::M;
+    constexpr int RS = tile_region_stride (G::SMEM_F2, C);
+    constexpr int NT = T * C;
+    constexpr unsigned TILE_BYTES = (unsigned) TT::SLOT_BYTES;
+    static_assert (! LOAD_J_FAST || G::S >= 2, "the thread-map switch needs at least one exchange");
+    FFT_DYN_SMEM (char, smem_raw);
+    float2* slot[2] = { reinterpret_cast<float2*> (smem_raw), reinterpret_cast<float2*> (smem_raw + TT::SLOT_BYTES) };
+    float2* smem = reinterpret_cast<float2*> (smem_raw + TT::XCH_OFFSET);
+    unsigned long long* bar = reinterpret_cast<unsigned long long*> (smem_raw + TT::BAR_OFFSET);
+    const int tid = (int) threadIdx.x;
+    const int ltB = tid % C, jB = tid / C; // adjacent threads = adjacent transforms
+    const int ltA = tid / T, jA = tid % T; // adjacent threads = adjacent elements
+    float2* sB = smem + ltB * RS;
+    float2* sTw = smem + C * RS;
+    const long long tiles = (long long) a.ntiles * a.batch;
+    const long long step = (long long) gridDim.x;
+
+    auto coords = [&] (const TileTmaCoords& k, long long t, int it, int (&c)[5])
+    {
+        const int bx = (int) (t / a.ntiles);
+        const int g = (int) (t - (long long) bx * a.ntiles);
+        const int ghi = g / a.gdiv, glo = g - ghi * a.gdiv;
+#pragma unroll
+        for (int d = 0; d < 5; ++d)
+            c[d] = ghi * k.per_hi[d] + glo * k.per_lo[d];
+        c[k.batch_dim] += bx;
+        c[k.iter_dim] += it * k.iter_step;
+    };
+    auto fetch = [&] (long long t, int s)
+    {
+        mbar_expect (bar + s, TILE_BYTES);
+        for (int it = 0; it < ic.iters; ++it)
+        {
+            int c[5];
+            coords (ic, t, it, c);
+            tma_load_5d (reinterpret_cast<char*> (slot[s]) + (size_t) it * (TILE_BYTES / (unsigned) ic.iters), imap, c[0], c[1], c[2], c[3], c[4], bar + s);
+        }
+    };
+
+    long long t = (long long) blockIdx.x;
+    if (tid == 0)
+    {
+        mbar_init (bar);
+        mbar_init (bar + 1);
+    }
+    __syncthreads();
+    if (tid == 0 && t < tiles)
+        fetch (t, 0);
+    for (unsigned it = 0; t < tiles; t += step, ++it)
+    {
+        const int s = (int) (it & 1u);
+        if (tid == 0)
+        {
+            tma_store_wait_read(); // the previous tile's store has read slot s ^ 1: it may receive the next tile
+            if (t + step < tiles)
+                fetch (t + step, s ^ 1);
+        }
+        const int bx = (int) (t / a.ntiles);
+        const int g = (int) (t - (long long) bx * a.ntiles);
+        const int glo = g % a.gdiv;
+        const unsigned cT = a.tw_c_base + (unsigned) (glo * C + ltB);
+        if (a.tw_mult != 0)
+        {
+            for (int i = tid; i - tid < R * C; i += NT) // i = m C + lt
+            {
+                if (i < R * C)
+                {
+                    const unsigned c = a.tw_c_base + (unsigned) (glo * C + i % C);
+                    sts2 (sTw + i, big_twiddle<DIR> (a, (unsigned) (i / C) * (unsigned) T * c * a.tw_mult));
+                }
+                else
+                    smem_skip();
+            }
+        } // visibility: every pass has at least one exchange barrier before the twiddle step
+        float2 v[R];
+        mbar_wait (bar + s, it >> 1, TILE_BYTES);
+        if constexpr (LOAD_J_FAST)
+        {
+            const float2* p = slot[s] + ltA * L + jA; // landing image [transform][element]
+#pragma unroll
+            for (int m = 0; m < R; ++m)
+                v[m] = lds2 (p + m * T);
+            float2* sA = smem + ltA * RS;
+            stage_compute<G, DIR, 0> (v, jA, a.tw);
+            stage_scatter<G, 0> (v, jA, sA);
+            __syncthreads();
+            gather_natural<G, 0, R> (v, jB, sB);
+            Stages<G, DIR, 1>::run (v, jB, sB, a.tw, true);
+        }
+        else
+        {
+            const float2* p = slot[s] + tid; // landing image [element][transform]: (jB + m T) C + ltB = tid + m T C
+#pragma unroll
+            for (int m = 0; m < R; ++m)
+                v[m] = lds2 (p + m * NT);
+            Stages<G, DIR, 0>::run (v, jB, sB, a.tw, false);
+        }
+        if (a.tw_mult != 0)
+        {
+            const float2 bw = big_twiddle<DIR> (a, (unsigned) jB * cT * a.tw_mult);
+#pragma unroll
+            for (int m = 0; m < R; ++m)
+            {
+                const float2 wm = m == 0 ? bw : cmul_dir<-1> (bw, lds2 (sTw + m * C + ltB));
+                v[m] = cmul_dir<DIR> (v[m], wm);
+            }
+        }
+        // output image [element k = jB + m T][transform ltB] in the slot the tile came from (every thread's reads of the
+        // slot are behind at least one CTA barrier of the stages above)
+        {
+            float2* q = slot[s] + tid;
+#pragma unroll
+            for (int m = 0; m < R; ++m)
+                sts2 (q + m * NT, v[m]);
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0)
+        {
+            for (int io = 0; io < oc.iters; ++io)
+            {
+                int c[5];
+                coords (oc, t, io, c);
+                tma_store_5d (reinterpret_cast<const char*> (slot[s]) + (size_t) io * (TILE_BYTES / (unsigned) oc.iters), omap, c[0], c[1], c[2], c[3], c[4]);
+            }
+            tma_store_commit();
+        }
+    }
+    if (tid == 0)
+        tma_store_wait_all();
+}
+
+#ifndef CHOWDSP_EMU
+template <int LOGL, int C, int DIR, bool LOAD_J_FAST, int R = 16>
+__global__ void __launch_bounds__ (TileTmaLaunch<LOGL, C, R>::THREADS, 1) tile_tma_kernel (CFB_TMAP5_PARAM imap, CFB_TMAP5_PARAM omap, const TileArgs a, const TileTmaCoords ic, const TileTmaCoords oc)
+{
+    tile_tma_body<LOGL, C, DIR, LOAD_J_FAST, R> (&imap, &omap, a, ic, oc);
+}
+#else
+template <int LOGL, int C, int DIR, bool LOAD_J_FAST, int R = 16>
+void tile_tma_kernel (CFB_TMAP5_PARAM imap, CFB_TMAP5_PARAM omap, const TileArgs a, const TileTmaCoords ic, const TileTmaCoords oc)
+{
+    tile_tma_body<LOGL, C, DIR, LOAD_J_FAST, R> (&imap, &omap, a, ic, oc);
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Real transforms of 2M samples on top of an M-point complex transform (M too large for one CTA):

@@ -1,6 +1,7 @@
 // Host-side description of a multi-pass (four-step) transform: factorisation and per-pass tile
 // arguments.  Pure arithmetic, shared by the library (capi.cu) and the CPU emulator tests.
 #pragma once
+#include <cstdint>
 #include <vector>
 
 #include "large_kernels.cuh"
@@ -13,6 +14,9 @@ namespace cfb
 constexpr int kTileCMax = 16;
 inline int& tile_c_override() { static int v = 0; return v; }       // tuning hooks (0 = policy below)
 inline int& tile_c_jfast_override() { static int v = 0; return v; } // ... for the contiguous-row (last) pass only
+// tuning hook "tile_tma": 1 = the persistent tensor-map TMA tile kernel (tile_tma_kernel) where a pass can be expressed as
+// tensor maps, 0 = tile_fft_kernel everywhere
+inline int& tile_tma_mode() { static int v = 0; return v; }
 // tuning hook "tile_r": 1 = 32 complex points per thread in the 512- / 1024-point tile passes (two Stockham stages instead of three)
 inline int& tile_radix32() { static int v = 0; return v; }
 inline int tile_c (int logL, bool jfast = false)
@@ -442,6 +446,102 @@ inline bool build_dist_schedule (int n, const LargeFactors& f, int rank, int wor
         out.push_back (bb);
         out.push_back (cc);
     }
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tensor-map view of one tile pass (tile_tma_kernel): dims / strides / box of the 5-D maps of its input and output
+// side and the per-tile coordinate rule, from the pass's TileArgs.  Pure arithmetic (shared with the emulator tests).
+// Returns false when the pass cannot be expressed (split input rows, peer stores, unordered layouts, unaligned strides).
+// ---------------------------------------------------------------------------------------------
+struct TileTmaSide
+{
+    const float2* base;
+    unsigned long long dims[5], strides[4];
+    unsigned box[5];
+    TileTmaCoords coords;
+};
+inline bool build_tile_tma (const TilePass& p, TileTmaSide& in, TileTmaSide& out)
+{
+    const TileArgs& a = p.args;
+    if (p.uio != 0 || a.peer_row_log >= 0 || a.in_split_log < 31)
+        return false;
+    const int C = p.C, L = 1 << p.logL;
+    const int rows_per_box = L < 256 ? L : 256;
+    const long long nhi = a.ntiles / a.gdiv;
+    auto even = [] (long long v) { return (v & 1) == 0; };
+    if (! even (a.in_bstride) || ! even (a.out_bstride) || ! even (a.in_bin0) || ! even (a.out_bin0) || ! even (a.in_g_hi) || ! even (a.out_g_hi)
+        || (reinterpret_cast<uintptr_t> (a.in) & 15) != 0 || (reinterpret_cast<uintptr_t> (a.out) & 15) != 0)
+        return false;
+    auto strided_side = [&] (TileTmaSide& s, const float2* base, long long bin0, long long g_hi, long long estride, long long bstride)
+    {
+        s = {};
+        s.base = base + bin0;
+        s.dims[0] = (unsigned long long) a.gdiv * C * 2;
+        s.dims[1] = (unsigned long long) L;
+        s.dims[2] = (unsigned long long) nhi;
+        s.dims[3] = (unsigned long long) a.batch;
+        s.dims[4] = 1;
+        s.strides[0] = (unsigned long long) estride * 8;
+        s.strides[1] = (unsigned long long) (nhi > 1 ? g_hi : estride * L) * 8;
+        s.strides[2] = (unsigned long long) (a.batch > 1 ? bstride : (nhi > 1 ? g_hi * nhi : estride * L)) * 8;
+        s.strides[3] = s.strides[2] * (unsigned long long) (a.batch > 1 ? a.batch : 1);
+        s.box[0] = (unsigned) (2 * C); s.box[1] = (unsigned) rows_per_box; s.box[2] = s.box[3] = s.box[4] = 1;
+        s.coords.per_lo[0] = 2 * C;
+        s.coords.per_hi[2] = 1;
+        s.coords.batch_dim = 3;
+        s.coords.iter_dim = 1;
+        s.coords.iters = L / rows_per_box;
+        s.coords.iter_step = rows_per_box;
+    };
+    if (! p.load_j_fast)
+    {
+        if (a.in_tstride != 1 || a.out_tstride != 1 || a.in_g_lo != C || a.out_g_lo != C || ! even (a.in_estride) || ! even (a.out_estride))
+            return false;
+        strided_side (in, a.in, a.in_bin0, a.in_g_hi, a.in_estride, a.in_bstride);
+        strided_side (out, a.out, a.out_bin0, a.out_g_hi, a.out_estride, a.out_bstride);
+        return true;
+    }
+    // contiguous-row pass: input [k1][k2][n3] (tile = C adjacent k1 at one k2), output transposed k1 + L1 (k2 + L2 k3)
+    if (a.in_estride != 1 || a.out_tstride != 1 || a.out_g_lo != C || a.in_g_lo != (long long) C * a.in_tstride || ! even (a.in_tstride) || ! even (a.out_estride))
+        return false;
+    const int chunk = 2 * L < 256 ? 2 * L : 256;
+    in = {};
+    in.base = a.in + a.in_bin0;
+    in.dims[0] = (unsigned long long) chunk;
+    in.dims[1] = (unsigned long long) (2 * L / chunk);
+    in.dims[2] = (unsigned long long) nhi;
+    in.dims[3] = (unsigned long long) a.gdiv * C;
+    in.dims[4] = (unsigned long long) a.batch;
+    in.strides[0] = (unsigned long long) chunk * 4;
+    in.strides[1] = (unsigned long long) (nhi > 1 ? a.in_g_hi : L) * 8;
+    in.strides[2] = (unsigned long long) a.in_tstride * 8;
+    in.strides[3] = (unsigned long long) (a.batch > 1 ? a.in_bstride : a.in_tstride * a.gdiv * C) * 8;
+    in.box[0] = (unsigned) chunk; in.box[1] = (unsigned) (2 * L / chunk); in.box[2] = 1; in.box[3] = (unsigned) C; in.box[4] = 1;
+    in.coords.per_hi[2] = 1;
+    in.coords.per_lo[3] = C;
+    in.coords.batch_dim = 4;
+    in.coords.iter_dim = 0;
+    in.coords.iters = 1;
+    in.coords.iter_step = 0;
+    out = {};
+    out.base = a.out + a.out_bin0;
+    out.dims[0] = (unsigned long long) a.gdiv * C * 2;
+    out.dims[1] = (unsigned long long) nhi;
+    out.dims[2] = (unsigned long long) L;
+    out.dims[3] = (unsigned long long) a.batch;
+    out.dims[4] = 1;
+    out.strides[0] = (unsigned long long) (nhi > 1 ? a.out_g_hi : a.gdiv * C) * 8;
+    out.strides[1] = (unsigned long long) a.out_estride * 8;
+    out.strides[2] = (unsigned long long) (a.batch > 1 ? a.out_bstride : a.out_estride * L) * 8;
+    out.strides[3] = out.strides[2] * (unsigned long long) (a.batch > 1 ? a.batch : 1);
+    out.box[0] = (unsigned) (2 * C); out.box[1] = 1; out.box[2] = (unsigned) rows_per_box; out.box[3] = out.box[4] = 1;
+    out.coords.per_lo[0] = 2 * C;
+    out.coords.per_hi[1] = 1;
+    out.coords.batch_dim = 3;
+    out.coords.iter_dim = 2;
+    out.coords.iters = L / rows_per_box;
+    out.coords.iter_step = rows_per_box;
     return true;
 }
 
