@@ -572,6 +572,7 @@ bool misaligned (const void* ptr, unsigned align_bytes, long long s0 = 0, long l
 constexpr int kL2ChunkMbDefault = 16, kL2LanesDefault = 3, kL2PolicyDefault = 1;
 int g_l2_chunk_mb = kL2ChunkMbDefault, g_l2_lanes = kL2LanesDefault, g_l2_policy = kL2PolicyDefault;
 constexpr int kMaxLanes = 4;
+constexpr int kTileTmaDefault = 0; // tuning hook "tile_tma" (large_plan.h: tile_tma_mode)
 
 // helper streams of the chunked schedules: chunks alternate over them so that pass B of one chunk overlaps pass C of the
 // previous one; joined back into the caller's stream with events (also legal inside a stream capture)
@@ -827,7 +828,7 @@ int enqueue_large (Plan* p, const float* in, float* out, int batch, long long in
                     ta.tw_hi = lt.bt.hi;
                     ta.tw_lobits = lt.bt.lobits;
                     if (e == cudaSuccess)
-                        e = launch_tile (l.pass.logL, l.pass.C, dir, l.pass.load_j_fast, l.pass.uio, ta, st);
+                        e = launch_tile_pass (dir, l.pass, st);
                     ++launches_total;
                 }
                 if (fwd)
@@ -882,7 +883,7 @@ int enqueue_large (Plan* p, const float* in, float* out, int batch, long long in
             ta.tw_lobits = lt.bt.lobits;
             cudaStream_t st = stream_of (l.lane);
             if (e == cudaSuccess)
-                e = launch_tile (l.pass.logL, l.pass.C, dir, l.pass.load_j_fast, l.pass.uio, ta, st);
+                e = launch_tile_pass (dir, l.pass, st);
             ++launches_total;
         }
         join();
@@ -2352,7 +2353,7 @@ CFB_API int fft_dist_transform (void* ctx, const float* input, float* output, ff
         ta.tw_lobits = lt.bt.lobits;
         cudaStream_t st = ls.stream_of (l.lane, e);
         if (e == cudaSuccess)
-            e = launch_tile (l.pass.logL, l.pass.C, dir, l.pass.load_j_fast, 0, ta, st);
+            e = launch_tile_pass (dir, l.pass, st);
     }
     ls.join (e);
     mark (3);
@@ -2484,6 +2485,11 @@ CFB_API int fft_b200_set_tuning (const char* key, int value)
     if (key != nullptr && std::strcmp (key, "l2_policy") == 0 && value >= -1 && value <= 1)
     {
         g_l2_policy = value == -1 ? kL2PolicyDefault : value;
+        return 0;
+    }
+    if (key != nullptr && std::strcmp (key, "tile_tma") == 0 && value >= -1 && value <= 1)
+    {
+        tile_tma_mode() = value == -1 ? kTileTmaDefault : value;
         return 0;
     }
     if (key != nullptr && std::strcmp (key, "tile_r") == 0 && value >= -1 && value <= 1)

@@ -73,6 +73,9 @@ cudaError_t launch_cluster_fft (int logN, int dir, int logW, const float* in, lo
 
 // multi-pass (large transform) kernels, large_inst.cu
 cudaError_t launch_tile (int logL, int C, int dir, bool load_j_fast, int uio, const TileArgs& args, cudaStream_t stream);
+struct TilePass; // large_plan.h
+// one tile pass through the persistent tensor-map TMA kernel where it applies (tuning hook tile_tma), else tile_fft_kernel
+cudaError_t launch_tile_pass (int dir, const TilePass& pass, cudaStream_t stream);
 cudaError_t launch_real_pass (int dir, const RealPassArgs& args, int batch, cudaStream_t stream);
 cudaError_t launch_dist_barrier (const DistBarrierArgs& args, cudaStream_t stream);
 

@@ -3,6 +3,7 @@
 
 #include "dispatch.h"
 #include "large_plan.h"
+#include "tma_host.h"
 
 namespace cfb
 {
@@ -69,6 +70,98 @@ cudaError_t launch_tile (int logL, int C, int dir, bool load_j_fast, int uio, co
         case 10: return launch_tile_l<10> (C, dir, load_j_fast, uio, a, stream);
         default: return cudaErrorInvalidValue;
     }
+}
+
+// ---- persistent tensor-map TMA tile kernel (tile_tma_kernel): cudaErrorInvalidConfiguration / NotSupported = does not apply ----
+namespace
+{
+int sm_count_cached()
+{
+    static thread_local int c_dev = -1, c_sms = 148;
+    int dev = 0;
+    if (cudaGetDevice (&dev) == cudaSuccess && dev != c_dev)
+    {
+        int n = 0;
+        if (cudaDeviceGetAttribute (&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            c_sms = n;
+        c_dev = dev;
+    }
+    return c_sms;
+}
+template <int LOGL, int C, int DIR, bool JFAST>
+cudaError_t launch_tile_tma_one (const TilePass& p, cudaStream_t stream)
+{
+    using TT = TileTmaLaunch<LOGL, C, 16>;
+    if constexpr (! TT::FITS)
+        return cudaErrorInvalidConfiguration;
+    else
+    {
+        TileTmaSide in, out;
+        if (! build_tile_tma (p, in, out))
+            return cudaErrorInvalidConfiguration;
+        TensorMap5 im, om;
+        cudaError_t e = tma_make_map5 (in.base, in.dims, in.strides, in.box, im);
+        if (e == cudaSuccess)
+            e = tma_make_map5 (out.base, out.dims, out.strides, out.box, om);
+        if (e != cudaSuccess)
+            return e == cudaErrorInvalidValue ? cudaErrorInvalidConfiguration : e; // a shape the encoder rejects: use tile_fft_kernel
+        auto kernel = tile_tma_kernel<LOGL, C, DIR, JFAST, 16>;
+        static thread_local int attr_dev = -1, resident = 0;
+        int dev = 0;
+        if ((e = cudaGetDevice (&dev)) != cudaSuccess)
+            return e;
+        if (dev != attr_dev)
+        {
+            int per_sm = 0;
+            if ((e = cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TT::SMEM_BYTES)) != cudaSuccess
+                || (e = cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, kernel, TT::THREADS, (size_t) TT::SMEM_BYTES)) != cudaSuccess)
+                return e;
+            if (per_sm < 1)
+                return cudaErrorInvalidConfiguration;
+            attr_dev = dev;
+            resident = sm_count_cached() * per_sm;
+        }
+        const long long tiles = (long long) p.args.ntiles * p.args.batch;
+        if (tiles <= 0)
+            return cudaSuccess;
+        kernel<<<(unsigned) (tiles < resident ? tiles : resident), TT::THREADS, TT::SMEM_BYTES, stream>>> (im, om, p.args, in.coords, out.coords);
+        count_launch();
+        return cudaGetLastError();
+    }
+}
+template <int LOGL, int C>
+cudaError_t launch_tile_tma_lc (int dir, const TilePass& p, cudaStream_t stream)
+{
+    if (dir < 0)
+        return p.load_j_fast ? launch_tile_tma_one<LOGL, C, -1, true> (p, stream) : launch_tile_tma_one<LOGL, C, -1, false> (p, stream);
+    return p.load_j_fast ? launch_tile_tma_one<LOGL, C, +1, true> (p, stream) : launch_tile_tma_one<LOGL, C, +1, false> (p, stream);
+}
+} // namespace
+
+cudaError_t launch_tile_tma (int dir, const TilePass& p, cudaStream_t stream)
+{
+    switch (p.logL * 100 + p.C)
+    {
+        case 808: return launch_tile_tma_lc<8, 8> (dir, p, stream);
+        case 816: return launch_tile_tma_lc<8, 16> (dir, p, stream);
+        case 908: return launch_tile_tma_lc<9, 8> (dir, p, stream);
+        case 916: return launch_tile_tma_lc<9, 16> (dir, p, stream);
+        case 1008: return launch_tile_tma_lc<10, 8> (dir, p, stream);
+        default: return cudaErrorInvalidConfiguration;
+    }
+}
+
+// one tile pass: the TMA kernel where the tuning hook allows and the pass can be expressed, else tile_fft_kernel
+cudaError_t launch_tile_pass (int dir, const TilePass& p, cudaStream_t stream)
+{
+    if (tile_tma_mode() != 0 && tile_radix32() == 0)
+    {
+        const cudaError_t e = launch_tile_tma (dir, p, stream);
+        if (e != cudaErrorInvalidConfiguration && e != cudaErrorNotSupported)
+            return e;
+        (void) cudaGetLastError();
+    }
+    return launch_tile (p.logL, p.C, dir, p.load_j_fast, p.uio, p.args, stream);
 }
 
 cudaError_t launch_dist_barrier (const DistBarrierArgs& a, cudaStream_t stream)

@@ -91,9 +91,45 @@ void emu_tile_launch_cr (const TilePass& p)
     else
         emu::launch (tile_fft_kernel<LOGL, C, DIR, false, 0, R>, grid, block, (size_t) TL::SMEM_BYTES, p.args);
 }
+// persistent tensor-map TMA tile kernel on (at most) 3 resident CTAs; false = the pass cannot be expressed as tensor maps
+template <int LOGL, int C, int DIR>
+bool emu_tile_launch_tma (const TilePass& p)
+{
+    using TT = TileTmaLaunch<LOGL, C, 16>;
+    if constexpr (! TT::FITS || LOGL < 8)
+        return false;
+    else
+    {
+        TileTmaSide in, out;
+        if (! build_tile_tma (p, in, out))
+            return false;
+        auto to_map = [] (const TileTmaSide& s)
+        {
+            TensorMap5 m {};
+            m.base = reinterpret_cast<const char*> (s.base);
+            for (int i = 0; i < 5; ++i)
+            {
+                m.dim[i] = s.dims[i];
+                m.box[i] = s.box[i];
+            }
+            for (int i = 0; i < 4; ++i)
+                m.stride[i] = s.strides[i];
+            return m;
+        };
+        const TensorMap5 im = to_map (in), om = to_map (out);
+        const unsigned tiles = (unsigned) p.args.ntiles * (unsigned) p.args.batch, grid = tiles < 3u ? tiles : 3u;
+        if (p.load_j_fast)
+            emu::launch (tile_tma_kernel<LOGL, C, DIR, true, 16>, dim3 (grid), dim3 (TT::THREADS), (size_t) TT::SMEM_BYTES, im, om, p.args, in.coords, out.coords);
+        else
+            emu::launch (tile_tma_kernel<LOGL, C, DIR, false, 16>, dim3 (grid), dim3 (TT::THREADS), (size_t) TT::SMEM_BYTES, im, om, p.args, in.coords, out.coords);
+        return true;
+    }
+}
 template <int LOGL, int C, int DIR>
 void emu_tile_launch_c (const TilePass& p)
 {
+    if (tile_tma_mode() != 0 && tile_radix32() == 0 && emu_tile_launch_tma<LOGL, C, DIR> (p))
+        return;
     if constexpr (LOGL >= 9 && (C == 8 || LOGL == 9))
         if (tile_radix32() != 0)
         {
@@ -505,6 +541,7 @@ int emu_pconv (int logM, int logW, const float* in, long long in_stride, const f
 
 void emu_set_tile_c (int c) { tile_c_override() = c; }
 void emu_set_tile_r (int r) { tile_radix32() = r; }
+void emu_set_tile_tma (int v) { tile_tma_mode() = v; }
 void emu_set_radix (int r) { g_emu_radix = r; }
 
 // batch transforms of 2^n complex points through build_large_schedule: classic whole-array passes (chunk_elems = 0) or the

@@ -265,6 +265,37 @@ def test_emulated_multi_pass_transform(emu, n, l1, l2, l3, tile_c, tile_r):
     emu.emu_set_tile_r(0)
 
 
+@pytest.mark.parametrize("tile_c", [8, 16])
+@pytest.mark.parametrize("n,l1,l2,l3,batch,chunk_elems,lanes", [(16, 8, 0, 8, 3, 0, 1), (17, 9, 0, 8, 2, 0, 1), (18, 8, 0, 10, 1, 0, 1), (18, 9, 0, 9, 2, 1 << 18, 2),
+                                                                (22, 8, 6, 8, 1, 8 << 14, 2)])
+def test_emulated_tma_tile_kernel(emu, n, l1, l2, l3, batch, chunk_elems, lanes, tile_c):
+    """tile_tma_kernel (persistent CTAs, tensor-map TMA loads and stores, two landing slots) == tile_fft_kernel bit for bit:
+    strided passes, the contiguous-row pass with its transposed store, batches, chunked launches (sub-ranges of a pass's
+    tiles through ring slots) -- the emulated tensor copies follow the same dims / strides / box / coordinates the host
+    encodes into the CUtensorMap (large_plan.h: build_tile_tma)."""
+    if n >= 22 and tile_c == 16:
+        pytest.skip("one tile width is enough at this size")
+    N = 1 << n
+    rng = np.random.default_rng(n)
+    x = rng.uniform(-1, 1, (batch, 2 * N)).astype(np.float32)
+    emu.emu_set_tile_c(tile_c)
+    try:
+        for backward in (0, 1):
+            emu.emu_set_tile_tma(0)
+            want, _ = _emu_large(emu, n, l1, l2, l3, backward, x.reshape(-1), batch, 0, chunk_elems, lanes)
+            emu.emu_set_tile_tma(1)
+            got, _ = _emu_large(emu, n, l1, l2, l3, backward, x.reshape(-1), batch, 0, chunk_elems, lanes)
+            assert np.array_equal(got, want), (n, backward)
+            if n <= 18 and not backward:
+                z = x[:, 0::2].astype(np.float64) + 1j * x[:, 1::2]
+                ref = np.fft.fft(z, axis=-1)
+                g = got.reshape(batch, 2 * N)
+                assert np.linalg.norm((g[:, 0::2] + 1j * g[:, 1::2]) - ref) / np.linalg.norm(ref) < 4e-7
+    finally:
+        emu.emu_set_tile_tma(0)
+        emu.emu_set_tile_c(0)
+
+
 @pytest.mark.parametrize("n,l1,l2,l3,batch,chunk_elems,lanes", [
     (12, 6, 0, 6, 5, 2 << 12, 2),      # two-pass plan, chunks of 2 transforms (ragged last chunk), 2 ring slots
     (13, 6, 0, 7, 3, 1 << 13, 3),      # one transform per chunk, 3 ring slots

@@ -1157,3 +1157,36 @@ def test_tile_passes_with_32_points_per_thread(cf, oracle_mod):
     finally:
         cf.set_tuning("tile_r", -1)
         cf.set_tuning("cluster", -1)
+
+
+def test_tma_tile_kernel_equals_tile_fft_kernel(cf, oracle_mod):
+    """tuning hook tile_tma = 1: the multi-pass path through the persistent tensor-map TMA tile kernel (cp.async.bulk.tensor
+    loads into two landing slots, tensor-map stores of the output image): bit-identical to tile_fft_kernel (same butterflies
+    and twiddles, only the data movement differs) for two- and three-pass plans, batches, chunked schedules, both
+    directions, real transforms; and within tolerance of the oracle."""
+    o = oracle_mod
+    rng = np.random.default_rng(77)
+    try:
+        cf.set_tuning("cluster", 0)
+        for lg, is_c, batch, mb in [(16, True, 5, 16), (17, True, 3, 16), (18, True, 9, 1), (20, True, 2, 16), (19, False, 3, 16), (24, True, 1, 16), (24, True, 2, 4), (25, False, 1, 16), (27, True, 1, 16)]:
+            N = 1 << lg
+            nfl = 2 * N if is_c else N
+            x = rng.uniform(-1, 1, (batch, nfl)).astype(np.float32)
+            cf.set_tuning("l2_chunk_mb", mb)
+            cf.set_tuning("tile_tma", 0)
+            want_f = gpu_transform(cf, x, N, is_c, True, False, True)
+            want_b = gpu_transform(cf, want_f, N, is_c, True, True, True)
+            cf.set_tuning("tile_tma", 1)
+            got_f = gpu_transform(cf, x, N, is_c, True, False, True)
+            got_b = gpu_transform(cf, want_f, N, is_c, True, True, True)
+            assert np.array_equal(got_f, want_f), (lg, is_c, batch, "forward")
+            assert np.array_equal(got_b, want_b), (lg, is_c, batch, "backward")
+            if lg <= 20:
+                assert o.rel_l2(got_f[:1], o.np_transform(x[:1], N, is_c, 8, False, True)) < o.parity_tol(N)
+            # unordered layouts: only the first / last pass differs (it keeps tile_fft_kernel), the others take the TMA kernel
+            got_u = gpu_transform(cf, x, N, is_c, True, False, False)
+            cf.set_tuning("tile_tma", 0)
+            assert np.array_equal(got_u, gpu_transform(cf, x, N, is_c, True, False, False))
+    finally:
+        for k in ("tile_tma", "l2_chunk_mb", "cluster"):
+            cf.set_tuning(k, -1)
