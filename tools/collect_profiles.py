@@ -14,7 +14,7 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 def main():
     tag, prefix = sys.argv[1], sys.argv[2]
     src, dst = os.path.join(ROOT, "gpurun_out", tag), os.path.join(ROOT, "profiles")
-    for f in sorted(glob.glob(os.path.join(src, "bench_*.json")) + glob.glob(os.path.join(src, "sweep_*.txt"))
+    for f in sorted(glob.glob(os.path.join(src, "bench_*.json")) + glob.glob(os.path.join(src, "sweep_*.txt")) + glob.glob(os.path.join(src, "sweep_*.json")) + glob.glob(os.path.join(src, "pytest_gpu.txt"))
                     + glob.glob(os.path.join(src, "launches_*.csv")) + glob.glob(os.path.join(src, "pcie_ceiling.txt"))):
         shutil.copy(f, os.path.join(dst, f"{prefix}_{os.path.basename(f)}"))
     traffic_path = os.path.join(dst, "traffic.json")
@@ -25,9 +25,12 @@ def main():
         open(os.path.join(dst, f"{prefix}_ncu_{name}.txt"), "w").write(out)
         rd = [float(l.split("=")[1].split()[0]) * (1e9 if "Gbyte" in l else 1e6 if "Mbyte" in l else 1.0) for l in out.splitlines() if "dram__bytes_read.sum" in l]
         wr = [float(l.split("=")[1].split()[0]) * (1e9 if "Gbyte" in l else 1e6 if "Mbyte" in l else 1.0) for l in out.splitlines() if "dram__bytes_write.sum" in l]
-        if rd and wr:
-            traffic[name] = int(rd[0] + wr[0])
-    traffic["_source"] = f"dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, ncu --set full captures of tools/gpu_refresh.sh ({prefix}_ncu_*.txt)"
+        kern = [l.split(": ", 1)[1].split("(")[0].replace("void ", "").strip() for l in out.splitlines() if l.startswith("== ")]
+        if rd and wr and kern:
+            # bench.py matches `kernel` as a substring of fft_b200_last_kernel(): keep the template name up to the first two arguments
+            k = kern[0].replace("(int)", "").replace(" ", "")
+            k = k.split(",")[0] if "<" in k else k
+            traffic[name] = {"bytes": int(rd[0] + wr[0]), "kernel": k.replace("cfb::", ""), "source": f"profiles/{prefix}_ncu_{name}.txt"}
     json.dump(traffic, open(traffic_path, "w"), indent=1)
     print("profiles updated:", prefix)
 
