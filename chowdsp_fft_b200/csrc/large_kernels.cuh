@@ -178,15 +178,23 @@ FFT_HD void tile_epilogue (const TileArgs& a, float2 (&v)[R], long long tbin, in
     {
         // unordered output: lanes (bins) 2i and 2i+1 are adjacent threads; they swap one float so that the even one holds
         // (re, re') and the odd one (im, im') -- contiguous 8-byte pairs of the unordered layout (as fft_core's UDIRECT)
+        // The element index k = jB + m T is the MOST significant digit of the bin (bin = tile offset + k * estride, estride =
+        // 2^(logN - LOGL)), and m is its top log2(R) bits: the lane row r of the unordered layout is the top logW bits of m, the
+        // rest of m stays in the in-row index -- so every store address is (one per-thread base) + (two small multiples of m).
         float* __restrict__ fb = reinterpret_cast<float*> (obase);
         const long long bin0 = tbin + ltB * a.out_tstride + jB * a.out_estride;
         const int odd = ltB & 1;
+        constexpr int LOGR = ilog2 (R);
+        const int sh = LOGR - a.unord_logW;
+        const long long step_lo = 1LL << (a.logN - LOGR + a.unord_logW + 1); // floats per unit of (m mod 2^sh)
+        const int step_r = 2 << a.unord_logW;                                 // floats per lane row
+        float* __restrict__ pb = fb + unord_pair_offset (bin0, a.logN, a.unord_logW);
 #pragma unroll
         for (int m = 0; m < R; ++m)
         {
             const float recv = shfl1 (odd ? v[m].x : v[m].y, ((int) threadIdx.x ^ 1) & 31, 32);
             const float2 o = odd ? make_float2 (recv, v[m].y) : make_float2 (v[m].x, recv);
-            stg_hint (reinterpret_cast<float2*> (fb + unord_pair_offset (bin0 + (long long) (m * T) * a.out_estride, a.logN, a.unord_logW)), o, pol);
+            stg_hint (reinterpret_cast<float2*> (pb + (long long) (m & ((1 << sh) - 1)) * step_lo + (m >> sh) * step_r), o, pol);
         }
         return;
     }
@@ -268,10 +276,16 @@ FFT_HD void tile_body (const TileArgs& a)
             const float* __restrict__ fb = reinterpret_cast<const float*> (ibase);
             const long long bin0 = in_tbin + ltB * a.in_tstride + jB * a.in_estride;
             const int odd = ltB & 1;
+            // as in the unordered stores of tile_epilogue: the element index is the top digit of the bin, m its top bits
+            constexpr int LOGR = ilog2 (R);
+            const int sh = LOGR - a.unord_logW;
+            const long long step_lo = 1LL << (a.logN - LOGR + a.unord_logW + 1);
+            const int step_r = 2 << a.unord_logW;
+            const float* __restrict__ pb = fb + unord_pair_offset (bin0, a.logN, a.unord_logW);
 #pragma unroll
             for (int m = 0; m < R; ++m)
             {
-                const float2 ld = ldg_hint (reinterpret_cast<const float2*> (fb + unord_pair_offset (bin0 + (long long) (m * T) * a.in_estride, a.logN, a.unord_logW)), ipol);
+                const float2 ld = ldg_hint (reinterpret_cast<const float2*> (pb + (long long) (m & ((1 << sh) - 1)) * step_lo + (m >> sh) * step_r), ipol);
                 const float recv = shfl1 (odd ? ld.x : ld.y, (tid ^ 1) & 31, 32);
                 v[m] = odd ? make_float2 (recv, ld.y) : make_float2 (ld.x, recv);
             }
