@@ -542,7 +542,9 @@ int g_pf_ahead = 0;        // tuning hook "pf_ahead": L2 prefetch distance of th
 constexpr int kClusterDefault = 0, kClusterMinBatchDefault = 8;
 int g_cluster = kClusterDefault, g_cluster_min_batch = kClusterMinBatchDefault;
 
-constexpr size_t kZeroCopyBytes = 256 * 1024;     // pinned buffers up to this size are used in place
+constexpr size_t kZeroCopyBytesDefault = 256 * 1024; // pinned buffers up to this size are used in place (tuning hook zero_copy_kb)
+size_t g_zero_copy_bytes = kZeroCopyBytesDefault;
+#define kZeroCopyBytes g_zero_copy_bytes
 constexpr size_t kChunkBytes = 32ull * 1024 * 1024; // host staging granularity per lane
 
 int kind_of (const Plan* p, int direction)
@@ -2460,6 +2462,11 @@ CFB_API int fft_b200_set_tuning (const char* key, int value)
     if (key != nullptr && std::strcmp (key, "spin_sync") == 0 && value >= -1 && value <= 1)
     {
         g_spin_sync = value == 1;
+        return 0;
+    }
+    if (key != nullptr && std::strcmp (key, "zero_copy_kb") == 0 && value >= -1)
+    {
+        g_zero_copy_bytes = value == -1 ? kZeroCopyBytesDefault : (size_t) value * 1024;
         return 0;
     }
     if (key != nullptr && std::strcmp (key, "cluster") == 0 && value >= -1 && value <= 3)

@@ -6,12 +6,63 @@ import json
 import math
 import os
 import sys
+import threading
+import time
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 import chowdsp_fft_b200 as cf  # noqa: E402
+
+
+class GpuState:
+    """SM clock / board power / throttle reasons sampled through NVML while a cell is timed (every cell of the sweep is
+    judged against the HBM roofline, so a cell measured under a power cap or on a hot board has to say so)."""
+
+    def __init__(self, index=0):
+        self.clk, self.pw, self.reasons = [], [], set()
+        self._stop = threading.Event()
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.n = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.n = None
+
+    def _run(self):
+        n = self.n
+        names = {n.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap", n.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 n.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal", n.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal"}
+        while not self._stop.is_set():
+            try:
+                self.clk.append(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                self.pw.append(n.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.reasons |= {v for k, v in names.items() if r & k}
+            except Exception:
+                pass
+            self._stop.wait(0.005)
+
+    def __enter__(self):
+        self.t = None
+        if self.n is not None:
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.t is not None:
+            self.t.join()
+
+    def summary(self):
+        if not self.clk:
+            return dict(sm_mhz=None, power_w=None, reasons=[])
+        c, p = sorted(self.clk), sorted(self.pw)
+        return dict(sm_mhz=c[len(c) // 2], power_w=p[len(p) // 2] if p else None, reasons=sorted(self.reasons))
 
 
 def main():
@@ -24,6 +75,8 @@ def main():
     ap.add_argument("--kinds", default="c,r")
     ap.add_argument("--layouts", default="ordered,w8,w4", help="ordered, w8 (8-lane unordered, AVX handle), w4 (4-lane unordered, SSE handle)")
     ap.add_argument("--tune", action="append", default=[], metavar="KEY=VALUE")
+    ap.add_argument("--pause", type=float, default=0.0, help="idle seconds before each cell (lets a power-capped board recover)")
+    ap.add_argument("--repeats", type=int, default=1, help="timed groups of --steps launches per cell; the best group is reported")
     args = ap.parse_args()
     try:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -65,23 +118,30 @@ def main():
 
                     def step():
                         cf.fft_transform_batched(s, x, y, batch, nfl, nfl, direction, ordered, stream)
+                    if args.pause > 0:
+                        torch.cuda.synchronize()
+                        time.sleep(args.pause)
                     for _ in range(3):
                         step()
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    torch.cuda.synchronize()
-                    e0.record(stream)
-                    for _ in range(args.steps):
-                        step()
-                    e1.record(stream)
-                    torch.cuda.synchronize()
-                    ms = e0.elapsed_time(e1) / args.steps
+                    ms = float("inf")
+                    with GpuState() as gs:
+                        for _ in range(max(1, args.repeats)):
+                            torch.cuda.synchronize()
+                            e0.record(stream)
+                            for _ in range(args.steps):
+                                step()
+                            e1.record(stream)
+                            torch.cuda.synchronize()
+                            ms = min(ms, e0.elapsed_time(e1) / args.steps)
+                    st = gs.summary()
                     gbs = batch * nfl * 8 / (ms * 1e-3) / 1e9
                     gfl = batch * (5.0 if is_c else 2.5) * N * math.log2(N) / (ms * 1e-3) / 1e9
                     row = dict(kind=("C2C" if is_c else ("R2C" if direction == 0 else "C2R")), N=N,
                                dir="fwd" if direction == 0 else "bwd", layout=layout,
-                               batch=batch, ms=ms, gbs=gbs, frac=gbs / peak, frac_nominal=gbs / 8000.0, gflops=gfl, kernel=cf.last_kernel())
+                               batch=batch, ms=ms, gbs=gbs, frac=gbs / peak, frac_nominal=gbs / 8000.0, gflops=gfl, kernel=cf.last_kernel(), **st)
                     rows.append(row)
-                    print(f"{row['kind']:4s} N={N:7d} {row['dir']} {row['layout']:7s} batch={batch:8d} {ms:8.4f} ms {gbs:8.1f} GB/s  frac={gbs/peak:5.3f} of measured, {gbs/8000.0:5.3f} of 8 TB/s  {gfl/1e3:6.2f} TFLOP/s  {row['kernel']}", flush=True)
+                    print(f"{row['kind']:4s} N={N:7d} {row['dir']} {row['layout']:7s} batch={batch:8d} {ms:8.4f} ms {gbs:8.1f} GB/s  frac={gbs/peak:5.3f} of measured, {gbs/8000.0:5.3f} of 8 TB/s  {gfl/1e3:6.2f} TFLOP/s  {st['sm_mhz']} MHz {st['power_w'] and round(st['power_w'])} W {','.join(st['reasons']) or '-'}  {row['kernel']}", flush=True)
             for s in plans.values():
                 cf.fft_destroy_setup(s)
     if args.json:
