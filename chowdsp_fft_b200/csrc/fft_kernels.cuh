@@ -215,6 +215,9 @@ FFT_HD float shfl1 (float v, int src, int width)
 #ifndef CFB_UNORD_REAL_DIRECT
 #define CFB_UNORD_REAL_DIRECT 0
 #endif
+#ifndef CFB_REAL_TW_DERIVE
+#define CFB_REAL_TW_DERIVE 2 // real split / merge twiddles of fft_core: 0 = one table load per bin, 1 = derived in registers, 2 = measured policy (RTW_DERIVE)
+#endif
 #ifndef CFB_SHFL_MIRROR
 #define CFB_SHFL_MIRROR 1 // A/B switch (tools/ only): 0 = the real split / merge step of fft_kernel exchanges through shared memory
 #endif
@@ -893,6 +896,12 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
     // (measured, profiles/r01_shfl_mirror.txt: +3..14 % for 16 points per thread and in the warp-pipelined kernels; with
     // 32 points per thread in fft_kernel the 32 extra shuffles + selects cost 2..5 %, so that geometry keeps shared memory)
     constexpr bool SHFL_MIRROR = T <= 32 && (KIND == R2C || KIND == C2R) && ((CFB_SHFL_MIRROR != 0 && R == 16) || IN_UNION == 2);
+    // Real split / merge twiddles: derived in registers (w_k = w_j W_2R^m, one table load per thread) or one table load per bin.
+    // Burst-mode A/B on B200 (profiles/r02_retune.txt; the round-1 table in profiles/r01_real_tw_ab.txt was taken under the power
+    // cap, where the variant with more FMA work loses): the table loads double the global-load sectors of the real kernels
+    // (l1tex 77..87 % busy), deriving wins +2..12 % for ordered spectra at every size and for unordered ones up to 2^11 complex
+    // points, and loses 1.5 % for unordered 2^12 and 6 % in the warp-pipelined kernel (landing-buffer input), which keep the table.
+    constexpr bool RTW_DERIVE = CFB_REAL_TW_DERIVE == 1 || (CFB_REAL_TW_DERIVE == 2 && IN_UNION == 0 && (! UNORD || LOGM <= 11));
     float* sf = reinterpret_cast<float*> (s); // the same buffer seen as the unordered staging image
     constexpr int logW = LOGW;
     struct { const float2* tw; const float2* rtw; } a { tw_, rtw_ };
@@ -1027,7 +1036,7 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
         for (int m = 0; m < R / 2; ++m)
         {
             const float2 xa = v[m], xm = xb[m];
-            const float2 wh = real_tw<R, false> (wj, a.rtw + j + m * T, m);                         // w_k / 2
+            const float2 wh = real_tw<R, RTW_DERIVE> (wj, a.rtw + j + m * T, m);                         // w_k / 2
             const float2 cm = make_float2 (xm.x, -xm.y);                   // conj X[M-k]
             const float2 e = f2_add (xa, cm), d = f2_sub (xa, cm);
             const float2 wd = cmul_dir<+1> (d, wh);                        // conj(w_k) d / 2
@@ -1163,7 +1172,7 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
         for (int m = 0; m < R / 2; ++m)
         {
             const float2 za = v[m], zm = zb[m];
-            const float2 wh = real_tw<R, false> (wj, a.rtw + j + m * T, m);                         // w_k / 2
+            const float2 wh = real_tw<R, RTW_DERIVE> (wj, a.rtw + j + m * T, m);                         // w_k / 2
             const float2 cm = make_float2 (zm.x, -zm.y);                   // conj Z[M-k]
             const float2 e = f2_add (za, cm), d = f2_sub (za, cm);         // 2E, 2D
             const float2 wd = cmul_dir<-1> (d, wh);                        // w_k D
