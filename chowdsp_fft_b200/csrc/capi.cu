@@ -574,6 +574,8 @@ bool misaligned (const void* ptr, unsigned align_bytes, long long s0 = 0, long l
 constexpr int kL2ChunkMbDefault = 16, kL2LanesDefault = 3, kL2PolicyDefault = 1;
 int g_l2_chunk_mb = kL2ChunkMbDefault, g_l2_lanes = kL2LanesDefault, g_l2_policy = kL2PolicyDefault;
 constexpr int kMaxLanes = 4;
+int g_mixq = 1; // tuning hook "mixq"
+constexpr int kTilePfDefault = 0;  // tuning hook "tile_pf" (large_plan.h: tile_pf_distance)
 constexpr int kTileTmaDefault = 0; // tuning hook "tile_tma" (large_plan.h: tile_tma_mode)
 
 // helper streams of the chunked schedules: chunks alternate over them so that pass B of one chunk overlaps pass C of the
@@ -924,6 +926,46 @@ int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inne
         const int mrc = plan_tables (p, mt);
         if (mrc != 0)
             return mrc;
+        // M = Q 2^p with Q in {3, 5, 9, 15}: the odd factor as one register butterfly around the power-of-two stages
+        // (mixq_kernels.cuh); other odd parts keep the generic kernel (tuning hook "mixq" = 0: always the generic kernel)
+        int mq_logP = 0, mq_Q = 0;
+        if (g_mixq != 0 && mixq_applies (p->M, mq_logP, mq_Q))
+        {
+            int dev = 0;
+            CFB_CUDA (cudaGetDevice (&dev));
+            Tables pt;
+            const int prc = get_tables (dev, mq_logP, false, pt, 16);
+            if (prc != 0)
+                return prc;
+            MixQArgs qa {};
+            qa.tw = pt.tw;
+            qa.wtab = mt.tw;
+            qa.rtab = mt.rtw;
+            qa.kind = kind_of (p, direction);
+            qa.W = ordered ? 0 : (1 << p->logW);
+            bool ok = true;
+            for (int o = 0; o < outer && ok; ++o)
+            {
+                qa.in = in + (long long) o * in_outer;
+                qa.out = out + (long long) o * out_outer;
+                qa.in_stride = in_inner;
+                qa.out_stride = out_inner;
+                qa.batch = inner;
+                const cudaError_t qe = launch_mixq (mq_logP, mq_Q, qa, stream);
+                if (qe == cudaErrorInvalidConfiguration && o == 0)
+                {
+                    (void) cudaGetLastError();
+                    ok = false; // no such instance: generic kernel below
+                }
+                else if (qe != cudaSuccess)
+                    return fail_cuda (qe, "mixed-radix (Q x 2^p) kernel launch");
+            }
+            if (ok)
+            {
+                note_kernel ("cfb::mixq_kernel<%d,%d> M=%d %s W=%d", mq_logP, mq_Q, p->M, kKindNames[qa.kind], qa.W);
+                return 0;
+            }
+        }
         MixedArgs ma {};
         ma.M = p->M;
         ma.nstages = mixed_factor (p->M, ma.radix);
@@ -2462,6 +2504,16 @@ CFB_API int fft_b200_set_tuning (const char* key, int value)
     if (key != nullptr && std::strcmp (key, "spin_sync") == 0 && value >= -1 && value <= 1)
     {
         g_spin_sync = value == 1;
+        return 0;
+    }
+    if (key != nullptr && std::strcmp (key, "mixq") == 0 && value >= -1 && value <= 1)
+    {
+        g_mixq = value == -1 ? 1 : value;
+        return 0;
+    }
+    if (key != nullptr && std::strcmp (key, "tile_pf") == 0 && value >= -1)
+    {
+        tile_pf_distance() = value == -1 ? kTilePfDefault : value;
         return 0;
     }
     if (key != nullptr && std::strcmp (key, "zero_copy_kb") == 0 && value >= -1)

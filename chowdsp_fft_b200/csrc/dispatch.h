@@ -6,6 +6,7 @@
 #include "pconv_kernel.cuh"
 #include "large_kernels.cuh"
 #include "mixed_kernels.cuh"
+#include "mixq_kernels.cuh"
 #include "cluster_kernels.cuh"
 
 namespace cfb
@@ -64,6 +65,8 @@ cudaError_t launch_pconv (int logM, int logW, const PConvArgs& args, cudaStream_
 
 // generic mixed-radix transform (N = 2^a 3^b 5^c, not a power of two), one CTA per transform
 cudaError_t launch_mixed (const MixedArgs& args, cudaStream_t stream);
+// Q x 2^logP transforms (mixq_kernels.cuh); cudaErrorInvalidConfiguration = no such instance
+cudaError_t launch_mixq (int logP, int Q, const MixQArgs& args, cudaStream_t stream);
 
 // one-pass cluster transform (cluster_kernels.cuh) for complex lengths 2^15 .. 2^17: plain batches, 16-byte aligned input rows
 // with in_stride % 4 == 0; dir < 0 forward (logW 0 or 3 = 8-lane unordered output), dir > 0 backward (logW 0).

@@ -901,7 +901,9 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
     // cap, where the variant with more FMA work loses): the table loads double the global-load sectors of the real kernels
     // (l1tex 77..87 % busy), deriving wins +2..12 % for ordered spectra at every size and for unordered ones up to 2^11 complex
     // points, and loses 1.5 % for unordered 2^12 and 6 % in the warp-pipelined kernel (landing-buffer input), which keep the table.
-    constexpr bool RTW_DERIVE = CFB_REAL_TW_DERIVE == 1 || (CFB_REAL_TW_DERIVE == 2 && IN_UNION == 0 && (! UNORD || LOGM <= 11));
+    // Not below 2^11 complex points (gains of 0..3 % there): those sizes also run in the warp-pipelined kernels, and the host- and
+    // device-pointer paths of the STFT entry points, which may pick different kernels, promise bit-identical results.
+    constexpr bool RTW_DERIVE = CFB_REAL_TW_DERIVE == 1 || (CFB_REAL_TW_DERIVE == 2 && IN_UNION == 0 && LOGM >= 11 && (! UNORD || LOGM <= 11));
     float* sf = reinterpret_cast<float*> (s); // the same buffer seen as the unordered staging image
     constexpr int logW = LOGW;
     struct { const float2* tw; const float2* rtw; } a { tw_, rtw_ };

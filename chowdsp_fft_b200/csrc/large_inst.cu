@@ -151,12 +151,64 @@ cudaError_t launch_tile_tma (int dir, const TilePass& p, cudaStream_t stream)
     }
 }
 
+// ---- tile_fft_kernel with the tensor-map L2 prefetch (tile_fft_pf_kernel); cudaErrorInvalidConfiguration = does not apply ----
+namespace
+{
+template <int LOGL, int C, int DIR, bool JFAST>
+cudaError_t launch_tile_pf_one (const TilePass& p, int distance, cudaStream_t stream)
+{
+    using TL = TileLaunch<LOGL, C, 16>;
+    TileTmaSide in, out;
+    if (! build_tile_tma (p, in, out))
+        return cudaErrorInvalidConfiguration;
+    TensorMap5 im;
+    cudaError_t e = tma_make_map5 (in.base, in.dims, in.strides, in.box, im);
+    if (e != cudaSuccess)
+        return e == cudaErrorInvalidValue ? cudaErrorInvalidConfiguration : e;
+    auto kernel = tile_fft_pf_kernel<LOGL, C, DIR, JFAST, 16>;
+    if (TL::SMEM_BYTES > 48 * 1024)
+        if ((e = cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TL::SMEM_BYTES)) != cudaSuccess)
+            return e;
+    kernel<<<(unsigned) p.args.ntiles * (unsigned) p.args.batch, TL::THREADS, TL::SMEM_BYTES, stream>>> (im, p.args, in.coords, distance);
+    count_launch();
+    return cudaGetLastError();
+}
+template <int LOGL, int C>
+cudaError_t launch_tile_pf_lc (int dir, const TilePass& p, int distance, cudaStream_t stream)
+{
+    if (dir < 0)
+        return p.load_j_fast ? launch_tile_pf_one<LOGL, C, -1, true> (p, distance, stream) : launch_tile_pf_one<LOGL, C, -1, false> (p, distance, stream);
+    return p.load_j_fast ? launch_tile_pf_one<LOGL, C, +1, true> (p, distance, stream) : launch_tile_pf_one<LOGL, C, +1, false> (p, distance, stream);
+}
+cudaError_t launch_tile_pf (int dir, const TilePass& p, int distance, cudaStream_t stream)
+{
+    switch (p.logL * 100 + p.C)
+    {
+        case 708: return launch_tile_pf_lc<7, 8> (dir, p, distance, stream);
+        case 716: return launch_tile_pf_lc<7, 16> (dir, p, distance, stream);
+        case 808: return launch_tile_pf_lc<8, 8> (dir, p, distance, stream);
+        case 816: return launch_tile_pf_lc<8, 16> (dir, p, distance, stream);
+        case 908: return launch_tile_pf_lc<9, 8> (dir, p, distance, stream);
+        case 916: return launch_tile_pf_lc<9, 16> (dir, p, distance, stream);
+        case 1008: return launch_tile_pf_lc<10, 8> (dir, p, distance, stream);
+        default: return cudaErrorInvalidConfiguration;
+    }
+}
+} // namespace
+
 // one tile pass: the TMA kernel where the tuning hook allows and the pass can be expressed, else tile_fft_kernel
 cudaError_t launch_tile_pass (int dir, const TilePass& p, cudaStream_t stream)
 {
     if (tile_tma_mode() != 0 && tile_radix32() == 0)
     {
         const cudaError_t e = launch_tile_tma (dir, p, stream);
+        if (e != cudaErrorInvalidConfiguration && e != cudaErrorNotSupported)
+            return e;
+        (void) cudaGetLastError();
+    }
+    if (tile_pf_distance() > 0 && tile_radix32() == 0)
+    {
+        const cudaError_t e = launch_tile_pf (dir, p, tile_pf_distance(), stream);
         if (e != cudaErrorInvalidConfiguration && e != cudaErrorNotSupported)
             return e;
         (void) cudaGetLastError();

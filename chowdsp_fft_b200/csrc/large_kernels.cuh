@@ -521,6 +521,48 @@ void tile_tma_kernel (CFB_TMAP5_PARAM imap, CFB_TMAP5_PARAM omap, const TileArgs
 #endif
 
 // ---------------------------------------------------------------------------------------------
+// tile_fft_kernel + tensor-map L2 prefetch (tuning hook "tile_pf" = distance in tiles).  ncu on tile_fft_kernel: two resident
+// CTAs per SM keep at most 128 KB of loads in flight per SM and only while they wait (about a quarter of a CTA's life), and the
+// strided gather's latency is 3-4 us -- by Little's law that is the 2.3 TB/s of reads the passes reach, while a copy kernel with
+// the same access pattern and twice the resident threads reaches 2.9.  Here thread 0 of CTA b asks L2 for the input tile of CTA
+// b + distance with ONE cp.async.bulk.prefetch.tensor per 256 element rows (no registers, no shared memory, no LSU slot), so
+// that the tile is an L2 hit when its CTA starts.  Natural-order passes whose input side a tensor map can describe
+// (large_plan.h: build_tile_tma); the others run tile_fft_kernel.
+// ---------------------------------------------------------------------------------------------
+template <int LOGL, int C, int DIR, bool LOAD_J_FAST, int R>
+FFT_HD void tile_pf_body (const TensorMap5* imap, const TileArgs& a, const TileTmaCoords& ic, int distance)
+{
+    if (threadIdx.x == 0)
+    {
+        const long long t = (long long) blockIdx.x + distance;
+        if (t < (long long) a.ntiles * a.batch)
+        {
+            const int bx = (int) (t / a.ntiles);
+            const int g = (int) (t - (long long) bx * a.ntiles);
+            const int ghi = g / a.gdiv, glo = g - ghi * a.gdiv;
+            for (int it = 0; it < ic.iters; ++it)
+            {
+                int c[5];
+#pragma unroll
+                for (int d = 0; d < 5; ++d)
+                    c[d] = ghi * ic.per_hi[d] + glo * ic.per_lo[d];
+                c[ic.batch_dim] += bx;
+                c[ic.iter_dim] += it * ic.iter_step;
+                tma_prefetch_5d (imap, c[0], c[1], c[2], c[3], c[4]);
+            }
+        }
+    }
+    tile_body<LOGL, C, DIR, LOAD_J_FAST, 0, R> (a);
+}
+#ifndef CHOWDSP_EMU
+template <int LOGL, int C, int DIR, bool LOAD_J_FAST, int R = 16>
+__global__ void __launch_bounds__ (TileLaunch<LOGL, C, R>::THREADS, TileLaunch<LOGL, C, R>::MIN_BLOCKS) tile_fft_pf_kernel (CFB_TMAP5_PARAM imap, const TileArgs a, const TileTmaCoords ic, const int distance)
+{
+    tile_pf_body<LOGL, C, DIR, LOAD_J_FAST, R> (&imap, a, ic, distance);
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------
 // Real transforms of 2M samples on top of an M-point complex transform (M too large for one CTA):
 // the split (forward) / merge (backward) step as its own streaming pass.  One thread per pair (k, M-k).
 //   forward : z = M-point FFT of the packed samples (ordered, natural) -> X in the pffft packing or the

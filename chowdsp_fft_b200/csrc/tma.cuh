@@ -54,6 +54,16 @@ FFT_HD void tma_load_5d (void* dst, const TensorMap5* map, int c0, int c1, int c
 #endif
 }
 
+// ask L2 for the box at coordinates (c0 .. c4) ahead of time: no shared-memory destination, no completion (SASS UTMAPF)
+FFT_HD void tma_prefetch_5d (const TensorMap5* map, int c0, int c1, int c2, int c3, int c4)
+{
+#ifdef CHOWDSP_EMU
+    (void) map; (void) c0; (void) c1; (void) c2; (void) c3; (void) c4;
+#else
+    asm volatile ("cp.async.bulk.prefetch.tensor.5d.L2.global [%0, {%1, %2, %3, %4, %5}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+#endif
+}
+
 // src (dense box image) -> box at coordinates (c0 .. c4); joins the calling thread's current bulk group
 FFT_HD void tma_store_5d (const void* src, const TensorMap5* map, int c0, int c1, int c2, int c3, int c4)
 {

@@ -13,7 +13,7 @@ SO = os.path.join(HERE, "libfft_emu.so" if not DEFINES else "libfft_emu_ab.so")
 def build(force: bool = False) -> str:
     srcs = [os.path.join(HERE, "emu_driver.cpp"), os.path.join(HERE, "cuda_emu.h"),
             os.path.join(CSRC, "fft_kernels.cuh"), os.path.join(CSRC, "elementwise_kernels.cuh"),
-            os.path.join(CSRC, "pconv_kernel.cuh"), os.path.join(CSRC, "pipe_kernels.cuh"), os.path.join(CSRC, "mixed_kernels.cuh"), os.path.join(CSRC, "large_kernels.cuh"), os.path.join(CSRC, "large_plan.h"), os.path.join(CSRC, "cluster_kernels.cuh")]
+            os.path.join(CSRC, "pconv_kernel.cuh"), os.path.join(CSRC, "pipe_kernels.cuh"), os.path.join(CSRC, "mixed_kernels.cuh"), os.path.join(CSRC, "mixq_kernels.cuh"), os.path.join(CSRC, "tma.cuh"), os.path.join(CSRC, "large_kernels.cuh"), os.path.join(CSRC, "large_plan.h"), os.path.join(CSRC, "cluster_kernels.cuh")]
     if not force and not DEFINES and os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(s) for s in srcs):
         return SO
     cmd = ["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", *DEFINES, f"-I{HERE}", f"-I{CSRC}", srcs[0], "-o", SO]

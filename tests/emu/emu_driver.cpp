@@ -8,6 +8,7 @@
 #include "pipe_kernels.cuh"
 #include "cluster_kernels.cuh"
 #include "mixed_kernels.cuh"
+#include "mixq_kernels.cuh"
 #include "large_plan.h"
 
 using namespace cfb;
@@ -513,6 +514,65 @@ int emu_mixed (int M, int kind, int W, const float* in, float* out, int batch, l
     mixed_geometry (M, threads, a.tg);
     emu::launch (mixed_kernel<0>, dim3 ((unsigned) grid), dim3 (threads), (size_t) 16 * M * (threads / a.tg), a);
     return 0;
+}
+
+} // extern "C" (the templates below need C++ linkage)
+// Q x 2^p mixed-radix transform (mixq_kernels.cuh); -1: no such instance
+namespace
+{
+template <int LOGP, int Q>
+int emu_mixq_one (MixQArgs a, int M)
+{
+    using X = MixQGeo<LOGP, Q>;
+    if constexpr (X::M > kMixedMaxM || X::THREADS > 1024)
+        return -1;
+    else
+    {
+        std::vector<float2> tw ((size_t) X::G::TW_LEN + 1), w ((size_t) M), r ((size_t) M / 2 + 1);
+        fill_stage_twiddles<LOGP, 16> (tw.data());
+        fill_mixed_twiddles (w.data(), M);
+        fill_mixed_real_twiddles (r.data(), M);
+        a.tw = tw.data(); a.wtab = w.data(); a.rtab = r.data();
+        emu::g_log_smem = false;
+        emu::launch (mixq_kernel<LOGP, Q>, dim3 ((unsigned) ((a.batch + X::SLOTS - 1) / X::SLOTS)), dim3 (X::THREADS), (size_t) X::SMEM_BYTES, a);
+        return 0;
+    }
+}
+template <int LOGP>
+int emu_mixq_p (int Q, const MixQArgs& a, int M)
+{
+    switch (Q)
+    {
+        case 3: return emu_mixq_one<LOGP, 3> (a, M);
+        case 5: return emu_mixq_one<LOGP, 5> (a, M);
+        case 9: return emu_mixq_one<LOGP, 9> (a, M);
+        case 15: return emu_mixq_one<LOGP, 15> (a, M);
+    }
+    return -1;
+}
+} // namespace
+extern "C"
+{
+int emu_mixq (int M, int kind, int W, const float* in, float* out, int batch, long long in_stride, long long out_stride)
+{
+    int logP = 0, Q = 0;
+    if (! mixq_applies (M, logP, Q))
+        return -1;
+    MixQArgs a {};
+    a.in = in; a.out = out; a.in_stride = in_stride; a.out_stride = out_stride; a.batch = batch; a.kind = kind; a.W = W;
+    switch (logP)
+    {
+        case 4: return emu_mixq_p<4> (Q, a, M);
+        case 5: return emu_mixq_p<5> (Q, a, M);
+        case 6: return emu_mixq_p<6> (Q, a, M);
+        case 7: return emu_mixq_p<7> (Q, a, M);
+        case 8: return emu_mixq_p<8> (Q, a, M);
+        case 9: return emu_mixq_p<9> (Q, a, M);
+        case 10: return emu_mixq_p<10> (Q, a, M);
+        case 11: return emu_mixq_p<11> (Q, a, M);
+        case 12: return emu_mixq_p<12> (Q, a, M);
+    }
+    return -1;
 }
 
 // fused partitioned-convolution step, real size N = 2^(logM+1)

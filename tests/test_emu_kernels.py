@@ -25,6 +25,7 @@ def emu():
     L.emu_wistft.argtypes = [C.c_int, C.c_int, fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 3 + [fp, C.c_float, C.c_int, C.c_int, C.c_int]
     L.emu_istft.argtypes = [C.c_int] * 4 + [fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 4 + [fp, C.c_float, C.c_int]
     L.emu_mixed.argtypes = [C.c_int, C.c_int, C.c_int, fp, fp, C.c_int, C.c_longlong, C.c_longlong, C.c_int]
+    L.emu_mixq.argtypes = [C.c_int, C.c_int, C.c_int, fp, fp, C.c_int, C.c_longlong, C.c_longlong]
     L.emu_fft_juce.argtypes = [C.c_int, C.c_int, C.c_int, fp, fp, C.c_int, C.c_longlong, C.c_longlong]
     L.emu_stft.argtypes = [C.c_int] * 3 + [fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 4 + [fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_long)]
     return L
@@ -492,6 +493,32 @@ def test_emulated_mixed_radix(emu, oracle_mod, N, is_c):
             b = np.zeros_like(x)
             refc = np.ascontiguousarray(ref, np.float32)
             assert emu.emu_mixed(M, 1 if is_c else 3, 0 if ordered else W, refc.ctypes.data_as(fp), b.ctypes.data_as(fp), 3, nfl, nfl, 2) == 0
+            assert o.rel_l2(b, o.np_transform(ref, N, is_c, W, True, ordered)) < 4e-7, (W, ordered)
+
+
+@pytest.mark.parametrize("N", [96, 192, 384, 480, 640, 768, 9216, 160, 288, 1920, 2560])
+@pytest.mark.parametrize("is_c", [True, False])
+def test_emulated_mixq(emu, oracle_mod, N, is_c):
+    """Q x 2^p kernel (mixq_kernels.cuh: power-of-two stages of fft_kernel + one radix-3 / 5 / 9 / 15 register butterfly) on the
+    reference's non-power-of-two test sizes (test/test.cpp:279-285) and a few more, so that every odd factor and the one-stage
+    (P = 16) geometry are covered: every kind, ordered and both unordered layouts, batches that do not fill the last CTA."""
+    o = oracle_mod
+    nfl = 2 * N if is_c else N
+    M = N if is_c else N // 2
+    rng = np.random.default_rng(N + 17)
+    batch = 3 if M >= 256 else 7
+    x = rng.uniform(-1, 1, (batch, nfl)).astype(np.float32)
+    widths = sorted({o.simd_width(N, is_c, True), o.simd_width(N, is_c, False)} - {0})
+    assert widths
+    for W in widths:
+        for ordered in (True, False):
+            ref = o.np_transform(x, N, is_c, W, False, ordered)
+            f = np.zeros_like(x)
+            assert emu.emu_mixq(M, 0 if is_c else 2, 0 if ordered else W, x.ctypes.data_as(fp), f.ctypes.data_as(fp), batch, nfl, nfl) == 0
+            assert o.rel_l2(f, ref) < 4e-7, (W, ordered)
+            b = np.zeros_like(x)
+            refc = np.ascontiguousarray(ref, np.float32)
+            assert emu.emu_mixq(M, 1 if is_c else 3, 0 if ordered else W, refc.ctypes.data_as(fp), b.ctypes.data_as(fp), batch, nfl, nfl) == 0
             assert o.rel_l2(b, o.np_transform(ref, N, is_c, W, True, ordered)) < 4e-7, (W, ordered)
 
 
