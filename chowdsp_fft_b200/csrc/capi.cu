@@ -499,7 +499,7 @@ bool g_stft_pipe = false;
 // for the 8-lane unordered layout.  Default from the
 // A/B sweeps in profiles/r01_pipe_kernel.txt: everything at 2^14 (+20..50 %); at 2^13, where fft_kernel already runs
 // two CTAs per SM, +2..7 % except ordered R2C (-3..5 %), which stays with fft_kernel
-constexpr unsigned kPipeDefault = 0xFFFFu & ~(1u << 4);
+constexpr unsigned kPipeDefault = 0xFFFFu & ~(1u << 4) & ~(1u << 6); // ordered R2C / C2R at 2^13 stay with fft_kernel<13,32> (C2R since the derived split twiddles: 5.60 vs 5.34 TB/s, profiles/r02_retune.txt)
 unsigned g_pipe_mask = kPipeDefault;
 bool pipe_enabled (int logM, int kind, int logW)
 {

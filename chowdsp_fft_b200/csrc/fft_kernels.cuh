@@ -136,6 +136,23 @@ FFT_HD float4 ldg_stream (const float4* p)
 #endif
 }
 
+// input loads of fft_core: streaming (no L1 allocation) when the T threads of a transform cover whole 32-byte sectors with
+// every load instruction; transforms owned by one or two threads (16 / 32 complex points) touch every sector with two or four
+// different instructions, so there the first touch allocates the line in L1 and the others hit (no_allocate would fetch the
+// sector from L2 each time: ncu l1tex sectors 2-4x the algorithmic figure)
+template <int T>
+FFT_HD float2 ldg_in (const float2* p)
+{
+#if defined(CHOWDSP_EMU) || defined(CFB_NO_CACHED_SMALL_LOADS)
+    return ldg_stream (p);
+#else
+    if constexpr (T <= 2)
+        return __ldg (p);
+    else
+        return ldg_stream (p);
+#endif
+}
+
 // ask L2 for the 128-byte lines of one transform's input (M complex = M/16 lines, R/16 per thread)
 template <class G>
 FFT_HD void prefetch_transform_l2 (const float* p, int j)
@@ -937,7 +954,7 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
             const float2* __restrict__ in2 = reinterpret_cast<const float2*> (in) + j;
 #pragma unroll
             for (int m = 0; m < R; ++m)
-                v[m] = ldg_stream (in2 + m * T);
+                v[m] = ldg_in<T> (in2 + m * T);
             if (win != nullptr) // constant-folded away in the plain batched kernel
             {
                 const float2* __restrict__ wj = win + j;
@@ -1026,8 +1043,8 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
                 for (int m = 0; m < R / 2; ++m)
                 {
                     const float2* ph = (m == 0 && j == 0) ? reinterpret_cast<const float2*> (in) + M / 2 : hi - m * T + T;
-                    v[m] = ldg_stream (lo + m * T);
-                    xb[m] = ldg_stream (ph);
+                    v[m] = ldg_in<T> (lo + m * T);
+                    xb[m] = ldg_in<T> (ph);
                 }
                 if (FMT == 1 && j == 0)
                     v[0].y = ldg_stream (reinterpret_cast<const float2*> (in) + M).x; // Nyquist lives in bin M, not in float 1

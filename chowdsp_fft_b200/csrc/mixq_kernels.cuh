@@ -142,44 +142,60 @@ FFT_HD void mixq_body (const MixQArgs& a)
     const bool staged_in = kind == C2R || (kind == C2C_BWD && W != 0);
 
     // ---- input sequence z (conjugated for the backward kinds): straight from global memory, or staged in the regions ----
+    // (M = 16 NT: every thread owns 16 elements n = lt + i NT, or the 8 bin pairs (k, M - k), k = lt + i NT < M / 2; the loops are
+    // unrolled so that all global loads of a thread are in flight together)
     if (staged_in)
     {
         if (kind == C2C_BWD)
         {
-            for (int n = lt; n < M; n += NT)
+            float2 t[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
             {
-                const int p = mixed_upos_complex (n, M, W);
-                sts2 (base + X::flat (n), make_float2 (in[p], -in[p + W]));
+                const int p = mixed_upos_complex (lt + i * NT, M, W);
+                t[i] = make_float2 (__ldg (in + p), -__ldg (in + p + W));
             }
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                sts2 (base + X::flat (lt + i * NT), t[i]);
         }
-        else // C2R merge: Z'[k] = (X[k] + X*[M-k]) + i conj(w_k) (X[k] - X*[M-k]), stored conjugated (mixed_kernels.cuh);
-        {    // one thread per pair: Z'[M-k] = conj ((X[k] + X*[M-k]) - i conj(w_k) (X[k] - X*[M-k]))
-            for (int k = lt; k <= M / 2; k += NT)
+        else // C2R merge: Z'[k] = (X[k] + X*[M-k]) + i conj(w_k) (X[k] - X*[M-k]), Z'[M-k] = conj ((X[k] + X*[M-k]) - i conj(w_k) (X[k] - X*[M-k])),
+        {    // stored conjugated; bin 0 carries (DC, Nyquist) and is paired with bin M / 2 (Z'[M/2] = 2 conj X[M/2])
+            float2 xa[8], xm[8], w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
             {
-                const int km = k == 0 ? 0 : M - k;
-                float2 xa, xm;
+                const int k = lt + i * NT;
+                const int km = k == 0 ? M / 2 : M - k;
                 if (W == 0)
                 {
-                    xa = reinterpret_cast<const float2*> (in)[k];
-                    xm = reinterpret_cast<const float2*> (in)[km];
+                    xa[i] = __ldg (reinterpret_cast<const float2*> (in) + k);
+                    xm[i] = __ldg (reinterpret_cast<const float2*> (in) + km);
                 }
                 else
                 {
                     const int pa = mixed_upos_real (k, M, W), pm = mixed_upos_real (km, M, W);
-                    xa = make_float2 (in[pa], in[pa + W]);
-                    xm = make_float2 (in[pm], in[pm + W]);
+                    xa[i] = make_float2 (__ldg (in + pa), __ldg (in + pa + W));
+                    xm[i] = make_float2 (__ldg (in + pm), __ldg (in + pm + W));
                 }
+                w[i] = __ldg (a.rtab + k);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+            {
+                const int k = lt + i * NT;
                 if (k == 0)
-                    sts2 (base, make_float2 (xa.x + xa.y, xa.y - xa.x)); // conj Z'[0]; slot 0 carries (DC, Nyquist)
+                {
+                    sts2 (base, make_float2 (xa[i].x + xa[i].y, xa[i].y - xa[i].x)); // conj Z'[0]
+                    sts2 (base + X::flat (M / 2), make_float2 (2.f * xm[i].x, 2.f * xm[i].y));
+                }
                 else
                 {
-                    const float2 w = __ldg (a.rtab + k);
-                    const float2 cm = mx_conj (xm);
-                    const float2 e = cadd (xa, cm), d = csub (xa, cm);
-                    const float2 wd = mx_mul (d, mx_conj (w));
-                    sts2 (base + X::flat (k), make_float2 (e.x - wd.y, -e.y - wd.x));  // conj (e + i wd)
-                    if (km != k)
-                        sts2 (base + X::flat (km), make_float2 (e.x + wd.y, e.y - wd.x)); // conj Z'[M-k] = e - i wd
+                    const float2 cm = mx_conj (xm[i]);
+                    const float2 e = cadd (xa[i], cm), d = csub (xa[i], cm);
+                    const float2 wd = mx_mul (d, mx_conj (w[i]));
+                    sts2 (base + X::flat (k), make_float2 (e.x - wd.y, -e.y - wd.x));    // conj (e + i wd)
+                    sts2 (base + X::flat (M - k), make_float2 (e.x + wd.y, e.y - wd.x)); // conj Z'[M-k] = e - i wd
                 }
             }
         }
@@ -254,59 +270,58 @@ FFT_HD void mixq_body (const MixQArgs& a)
     __syncthreads();
 
     // ---- spectrum in the regions (natural order): unordered complex store / real split ----
+    if (! active)
+        return;
     if (kind == C2C_FWD)
     {
-        if (active)
-            for (int n = lt; n < M; n += NT)
-            {
-                const float2 val = lds2 (base + X::flat (n));
-                const int p = mixed_upos_complex (n, M, W);
-                out[p] = val.x;
-                out[p + W] = val.y;
-            }
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+        {
+            const int n = lt + i * NT;
+            const float2 val = lds2 (base + X::flat (n));
+            const int p = mixed_upos_complex (n, M, W);
+            out[p] = val.x;
+            out[p + W] = val.y;
+        }
     }
-    else // R2C: X[k] = E - i w_k D, X[M-k] = conj (E + i w_k D), E, D = (Z[k] +- Z*[M-k]) / 2
+    else // R2C: X[k] = E - i w_k D, X[M-k] = conj (E + i w_k D), E, D = (Z[k] +- Z*[M-k]) / 2; bin 0 = (DC, Nyquist), paired with bin M / 2
     {
-        if (active)
-            for (int k = lt; k <= M / 2; k += NT)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+        {
+            const int k = lt + i * NT;
+            const int km = k == 0 ? M / 2 : M - k;
+            const float2 za = lds2 (base + X::flat (k)), zm = lds2 (base + X::flat (km));
+            float2 xa, xm;
+            if (k == 0)
             {
-                const float2 za = lds2 (base + X::flat (k)), zm = lds2 (base + X::flat (k == 0 ? 0 : M - k));
-                float2 xa, xm;
-                if (k == 0)
-                {
-                    xa = make_float2 (za.x + za.y, za.x - za.y); // (DC, Nyquist)
-                    xm = xa;
-                }
-                else
-                {
-                    const float2 w = __ldg (a.rtab + k);
-                    const float2 cm = mx_conj (zm);
-                    const float2 e = make_float2 (0.5f * (za.x + cm.x), 0.5f * (za.y + cm.y));
-                    const float2 d = make_float2 (0.5f * (za.x - cm.x), 0.5f * (za.y - cm.y));
-                    const float2 wd = mx_mul (d, w);
-                    xa = make_float2 (e.x + wd.y, e.y - wd.x);
-                    xm = make_float2 (e.x - wd.y, -e.y - wd.x);
-                }
-                const int km = M - k;
-                if (W == 0)
-                {
-                    out2[k] = xa;
-                    if (k != 0 && km != k)
-                        out2[km] = xm;
-                }
-                else
-                {
-                    const int pa = mixed_upos_real (k, M, W);
-                    out[pa] = xa.x;
-                    out[pa + W] = xa.y;
-                    if (k != 0 && km != k)
-                    {
-                        const int pm = mixed_upos_real (km, M, W);
-                        out[pm] = xm.x;
-                        out[pm + W] = xm.y;
-                    }
-                }
+                xa = make_float2 (za.x + za.y, za.x - za.y); // (DC, Nyquist)
+                xm = mx_conj (zm);                           // X[M/2] = conj Z[M/2]
             }
+            else
+            {
+                const float2 w = __ldg (a.rtab + k);
+                const float2 cm = mx_conj (zm);
+                const float2 e = make_float2 (0.5f * (za.x + cm.x), 0.5f * (za.y + cm.y));
+                const float2 d = make_float2 (0.5f * (za.x - cm.x), 0.5f * (za.y - cm.y));
+                const float2 wd = mx_mul (d, w);
+                xa = make_float2 (e.x + wd.y, e.y - wd.x);
+                xm = make_float2 (e.x - wd.y, -e.y - wd.x);
+            }
+            if (W == 0)
+            {
+                out2[k] = xa;
+                out2[km] = xm;
+            }
+            else
+            {
+                const int pa = mixed_upos_real (k, M, W), pm = mixed_upos_real (km, M, W);
+                out[pa] = xa.x;
+                out[pa + W] = xa.y;
+                out[pm] = xm.x;
+                out[pm + W] = xm.y;
+            }
+        }
     }
 }
 
