@@ -310,7 +310,17 @@ int preload_tables (Plan* p)
 {
     Tables t;
     if (p->mixed)
-        return plan_tables (p, t);
+    {
+        const int rc = plan_tables (p, t);
+        int logP = 0, Q = 0;
+        if (rc == 0 && mixq_applies (p->M, logP, Q)) // stage twiddles of the power-of-two sub-transforms (mixq_kernels.cuh)
+        {
+            int dev = 0;
+            CFB_CUDA (cudaGetDevice (&dev));
+            return get_tables (dev, logP, false, t, 16);
+        }
+        return rc;
+    }
     if (p->logM > kMaxLogM)
         return preload_large (p);
     int rc = plan_tables (p, t, 16);

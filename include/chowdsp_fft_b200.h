@@ -183,6 +183,8 @@ void fft_b200_clear_error (void);
                     0 = whole-array passes everywhere; -m (m >= 2) = m MiB chunks at every size)
      "l2_lanes"     helper streams / ring slots the chunks alternate over (1..4, default 3)
      "l2_policy"    1 = evict_last / evict_first L2 hints on ring / streaming accesses of the chunked schedules (default)
+     "tile_pf"      tensor-map L2 prefetch distance of the multi-pass tile kernels in tiles (default 0 = off: measured 3..10 % slower)
+     "mixq"         1 = sizes Q 2^p with Q in {3, 5, 9, 15} run in mixq_kernel (default), 0 = always the generic mixed-radix kernel
      "zero_copy_kb" pinned (device-mapped) host buffers up to this many KiB are transformed in place over PCIe by the kernel's own
                     loads / stores instead of being staged through device memory (default 256)
      "pf_ahead"     L2 prefetch distance of the single-kernel transforms in CTAs (default 0 = off) */
