@@ -2521,6 +2521,11 @@ CFB_API int fft_b200_set_tuning (const char* key, int value)
         g_mixq = value == -1 ? 1 : value;
         return 0;
     }
+    if (key != nullptr && std::strcmp (key, "tile_stream") == 0 && value >= -1 && value <= 3)
+    {
+        tile_stream_mode() = value == -1 ? 0 : value;
+        return 0;
+    }
     if (key != nullptr && std::strcmp (key, "tile_pf") == 0 && value >= -1)
     {
         tile_pf_distance() = value == -1 ? kTilePfDefault : value;

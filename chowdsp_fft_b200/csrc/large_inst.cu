@@ -197,8 +197,13 @@ cudaError_t launch_tile_pf (int dir, const TilePass& p, int distance, cudaStream
 } // namespace
 
 // one tile pass: the TMA kernel where the tuning hook allows and the pass can be expressed, else tile_fft_kernel
-cudaError_t launch_tile_pass (int dir, const TilePass& p, cudaStream_t stream)
+cudaError_t launch_tile_pass (int dir, const TilePass& p_in, cudaStream_t stream)
 {
+    TilePass p = p_in;
+    if ((tile_stream_mode() & 1) != 0 && p.args.in_policy == POLICY_NORMAL)
+        p.args.in_policy = POLICY_STREAM;
+    if ((tile_stream_mode() & 2) != 0 && p.args.out_policy == POLICY_NORMAL)
+        p.args.out_policy = POLICY_STREAM;
     if (tile_tma_mode() != 0 && tile_radix32() == 0)
     {
         const cudaError_t e = launch_tile_tma (dir, p, stream);

@@ -19,6 +19,7 @@ inline int& tile_c_jfast_override() { static int v = 0; return v; } // ... for t
 inline int& tile_tma_mode() { static int v = 0; return v; }
 // tuning hook "tile_r": 1 = 32 complex points per thread in the 512- / 1024-point tile passes (two Stockham stages instead of three)
 inline int& tile_radix32() { static int v = 0; return v; }
+inline int& tile_stream_mode() { static int v = 0; return v; } // tuning hook "tile_stream": bit 0 / 1 = evict-first loads / stores in passes that carry no policy
 inline int& tile_pf_distance() { static int v = 0; return v; } // tuning hook "tile_pf": tensor-map L2 prefetch distance of the tile passes in tiles (0 = off)
 inline int tile_c (int logL, bool jfast = false)
 {

@@ -662,6 +662,21 @@ FFT_HD void half_drain (const float* sf, float* __restrict__ out, int j)
 // Plain batches only (transform x reads in + x in_inner, writes out + x out_inner); the input rows must be
 // 16-byte aligned (TMA), which the launcher checks.
 // ---------------------------------------------------------------------------------------------
+// result stores of the ordered epilogue: streaming (st.global.cs, evict-first) at 2^14 points, plain at 2^13 -- burst-mode A/B on
+// B200 (profiles/r02_retune.txt): +1.5 % at 2^14 (one resident CTA per SM), -3.5 % at 2^13 (two)
+template <int LOGM>
+FFT_HD void pipe_stg (float2* p, float2 v)
+{
+#if ! defined(CHOWDSP_EMU) && ! defined(CFB_PIPE_NO_STCS)
+    if constexpr (LOGM >= 14)
+        __stcs (p, v);
+    else
+        *p = v;
+#else
+    *p = v;
+#endif
+}
+
 template <int LOGM, int KIND, int LOGW>
 FFT_HD void pipe_body (const FftArgs& a)
 {
@@ -817,7 +832,7 @@ FFT_HD void pipe_body (const FftArgs& a)
             float2* __restrict__ out2 = reinterpret_cast<float2*> (out) + j;
 #pragma unroll
             for (int m = 0; m < R; ++m)
-                out2[m * T] = v[m];
+                pipe_stg<LOGM> (out2 + m * T, v[m]);
         }
         else if constexpr (KIND == C2C_FWD && CFB_UNORD_DIRECT != 0)
         {
