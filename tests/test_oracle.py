@@ -145,3 +145,26 @@ def test_reference_partitioned_convolution_is_a_linear_convolution(oracle_mod, r
     for c in range(channels):
         want = np.convolve(x[c].astype(np.float64), ir[c].astype(np.float64))[:blocks * B]
         assert o.rel_l2(y[c], want) < 1e-5
+
+
+def test_reference_real_transforms_with_factor_25_are_wrong(oracle_mod):
+    """A finding, pinned so that nobody 'fixes' parity in the wrong direction: the reference's REAL transforms are wrong (not even
+    self-inverse) when the length contains 5^2 -- N = 800, 1600, 2400 ... -- in both its SSE and its AVX build, while complex transforms
+    of those lengths and real ones with a single factor 5 (160, 320, 480, 640: the only ones its tests reach, test/test.cpp:279-285)
+    are right.  The restated oracle and the CUDA path follow the DFT for these sizes."""
+    o = oracle_mod
+    ref = o.load_ref()
+    if ref is None:
+        pytest.skip("reference build not available")
+    rng = np.random.default_rng(25)
+    for N, broken in [(160, False), (480, False), (800, True), (2400, True), (864, False)]:
+        x = rng.uniform(-1, 1, (1, N)).astype(np.float32)
+        want = o.np_transform(x, N, False, 4, False, True)
+        for avx in (True, False):
+            f, _ = ref.transform(x, N, False, False, True, avx)
+            b, _ = ref.transform(f, N, False, True, True, avx)
+            assert (o.rel_l2(f, want) > 0.5) == broken, (N, avx)
+            assert (o.rel_l2(b / N, x) > 0.5) == broken, (N, avx, "round trip")
+        xc = rng.uniform(-1, 1, (1, 2 * N)).astype(np.float32)
+        fc, _ = ref.transform(xc, N, True, False, True, True)
+        assert o.rel_l2(fc, o.np_transform(xc, N, True, o.simd_width(N, True, True), False, True)) < 1e-6

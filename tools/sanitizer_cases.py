@@ -2,7 +2,7 @@
 """One small case per kernel family, meant to run UNDER compute-sanitizer (memcheck / racecheck / synccheck):
     compute-sanitizer --tool racecheck python tools/sanitizer_cases.py
 fft_kernel (ordered / unordered, real / complex), pipe_kernel (2^13, 2^14), wpipe_kernel + wistft_kernel (STFT / ISTFT),
-istft_kernel, stft_kernel, pconv_kernel, mixed_kernel, tile_fft_kernel (classic + L2-chunked, unordered folded in),
+istft_kernel, stft_kernel, pconv_kernel, mixq_kernel, mixed_kernel, tile_fft_kernel (+ the L2-prefetch variant) (classic + L2-chunked, unordered folded in),
 real_pass_kernel, convolve / accumulate, the distributed phase kernels with the peer-store epilogue (world = 1).
 Results are checked loosely (finite, right norm): parity proper lives in tests/.  GPU only."""
 import os
@@ -43,9 +43,15 @@ roundtrip(256, True, 5, False, avx=False)
 for N, is_c in [(8192, True), (16384, True), (32768, False)]:   # pipe_kernel
     for ordered in (True, False):
         roundtrip(N, is_c, 3, ordered)
-for N in (96, 480):                                              # mixed radix
+for N in (96, 480):                                              # mixed radix: mixq_kernel (odd part 3 / 15)
     roundtrip(N, True, 3, True)
     roundtrip(N * 4, False, 3, False)
+for N in (400, 864):                                             # ... and the generic mixed_kernel (odd part 25 / 27)
+    roundtrip(N, True, 3, True)
+    roundtrip(N * 2, False, 3, False)
+cf.set_tuning("tile_pf", 4)                                      # tile_fft_pf_kernel (tensor-map L2 prefetch)
+roundtrip(1 << 16, True, 5, True)
+cf.set_tuning("tile_pf", -1)
 # multi-pass: classic and L2-chunked (tiny chunks), unordered folded in; real split / merge
 for mb in (0, 1):
     cf.set_tuning("l2_chunk_mb", mb)
