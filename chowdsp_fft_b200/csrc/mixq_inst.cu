@@ -14,7 +14,8 @@ cudaError_t launch_mixq_one (const MixQArgs& a, cudaStream_t stream)
         return cudaErrorInvalidConfiguration;
     else
     {
-        auto kernel = mixq_kernel<LOGP, Q>;
+        const bool fast = (a.kind == C2C_FWD || a.kind == C2C_BWD) && a.W == 0;
+        auto kernel = fast ? mixq_kernel<LOGP, Q, 0> : mixq_kernel<LOGP, Q, 1>;
         if (X::SMEM_BYTES > 48 * 1024)
         {
             const cudaError_t e = cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, X::SMEM_BYTES);

@@ -534,7 +534,8 @@ int emu_mixq_one (MixQArgs a, int M)
         fill_mixed_real_twiddles (r.data(), M);
         a.tw = tw.data(); a.wtab = w.data(); a.rtab = r.data();
         emu::g_log_smem = false;
-        emu::launch (mixq_kernel<LOGP, Q>, dim3 ((unsigned) ((a.batch + X::SLOTS - 1) / X::SLOTS)), dim3 (X::THREADS), (size_t) X::SMEM_BYTES, a);
+        const bool fast = (a.kind == C2C_FWD || a.kind == C2C_BWD) && a.W == 0;
+        emu::launch (fast ? mixq_kernel<LOGP, Q, 0> : mixq_kernel<LOGP, Q, 1>, dim3 ((unsigned) ((a.batch + X::SLOTS - 1) / X::SLOTS)), dim3 (X::THREADS), (size_t) X::SMEM_BYTES, a);
         return 0;
     }
 }
