@@ -1148,7 +1148,16 @@ int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inne
     }
     if (window != nullptr)
         return fail (chowdsp::fft::FFT_B200_EINVAL, "windowed transforms need even hop and channel strides");
-    note_kernel ("cfb::fft_kernel<%d,%d,%s,%d>", p->logM, radix, kKindNames[kind_of (p, direction)], ordered ? 0 : p->logW);
+    {
+        // mirrors small_applies() in fft_inst.cu: dense batches of 16- / 32-point transforms
+        const int kd = kind_of (p, direction);
+        const long long row = 2LL << p->logM;
+        const uintptr_t al = ordered ? 7 : 15;
+        const bool small = p->logM <= 5 && radix == 16 && fft_small_mode() != 0 && a.inner >= a.batch
+                           && a.in_inner == row && a.out_inner == row && (reinterpret_cast<uintptr_t> (a.in) & al) == 0 && (reinterpret_cast<uintptr_t> (a.out) & al) == 0;
+        (void) kd;
+        note_kernel (small ? "cfb::fft_small_kernel<%d,%d,%s,%d>" : "cfb::fft_kernel<%d,%d,%s,%d>", p->logM, radix, kKindNames[kd], ordered ? 0 : p->logW);
+    }
     const cudaError_t e = launch_fft (p->logM, kind_of (p, direction), ordered ? 0 : p->logW, radix, a, stream);
     if (e != cudaSuccess)
         return fail_cuda (e, "fft kernel launch");
@@ -2514,6 +2523,11 @@ CFB_API int fft_b200_set_tuning (const char* key, int value)
     if (key != nullptr && std::strcmp (key, "spin_sync") == 0 && value >= -1 && value <= 1)
     {
         g_spin_sync = value == 1;
+        return 0;
+    }
+    if (key != nullptr && std::strcmp (key, "small") == 0 && value >= -1 && value <= 1)
+    {
+        fft_small_mode() = value == -1 ? 1 : value;
         return 0;
     }
     if (key != nullptr && std::strcmp (key, "mixq") == 0 && value >= -1 && value <= 1)

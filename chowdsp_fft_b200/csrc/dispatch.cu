@@ -156,6 +156,12 @@ void fill_stage_twiddles_rt (int logM, int radix, float2* tw)
     }
 }
 
+int& fft_small_mode()
+{
+    static int v = 1;
+    return v;
+}
+
 cudaError_t launch_mixed (const MixedArgs& args, cudaStream_t stream)
 {
     MixedArgs a = args;

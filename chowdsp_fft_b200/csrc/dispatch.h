@@ -88,6 +88,8 @@ cudaError_t launch_accumulate (const float* a, const float* b, float* ab, long l
 // every kernel launch made by this library bumps this counter (bench.py reports it as gpu_launches)
 unsigned long long launch_count();
 void count_launch();
+// tuning hook "small": 1 = dense batches of 16 .. 64-point transforms go through the staged kernel (fft_small_kernel), 0 = fft_kernel
+int& fft_small_mode();
 
 // per-size entry points, one translation unit each (fft_inst.cu compiled with -DCFB_LOGM=n)
 #define CFB_DECL_INST(n)                                                                       \

@@ -3,6 +3,8 @@
 #ifndef CFB_LOGM
 #error "compile with -DCFB_LOGM=<4..14>"
 #endif
+#include <cstdint>
+
 #include "dispatch.h"
 #include "pipe_kernels.cuh"
 
@@ -17,9 +19,49 @@ namespace cfb
 {
 namespace
 {
+#if CFB_LOGM <= 5
+// dense batch of tiny transforms through the staged kernel (fft_small_kernel)?  Rows of 2 M floats on both sides, 8-byte aligned
+// bases (16 for the unordered layouts, whose image is drained with 128-bit stores into the shared-memory row anyway)
+template <int KIND, int LOGW>
+bool small_applies (const FftArgs& a)
+{
+    using SL = SmallLaunch<CFB_LOGM, KIND, LOGW>;
+    constexpr long long ROW = 2LL << CFB_LOGM;
+    constexpr uintptr_t AL = LOGW != 0 ? 15 : 7;
+    return SL::APPLIES && fft_small_mode() != 0 && a.inner >= a.batch && a.in_inner == ROW && a.out_inner == ROW && a.window == nullptr
+           && (reinterpret_cast<uintptr_t> (a.in) & AL) == 0 && (reinterpret_cast<uintptr_t> (a.out) & AL) == 0;
+}
+template <int KIND, int LOGW>
+cudaError_t launch_small (const FftArgs& a, cudaStream_t stream)
+{
+    using SL = SmallLaunch<CFB_LOGM, KIND, LOGW>;
+    using L = Launch<CFB_LOGM, 16>;
+    if constexpr (! SL::APPLIES)
+        return cudaErrorInvalidConfiguration;
+    else
+    {
+        auto kernel = fft_small_kernel<CFB_LOGM, KIND, LOGW>;
+        const cudaError_t e = cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::SMEM_BYTES);
+        if (e != cudaSuccess)
+            return e;
+        if (a.batch <= 0)
+            return cudaSuccess;
+        const unsigned grid = (unsigned) (((long long) a.batch + L::PER_CTA - 1) / L::PER_CTA);
+        kernel<<<grid, L::THREADS, SL::SMEM_BYTES, stream>>> (a);
+        count_launch();
+        return cudaGetLastError();
+    }
+}
+#endif
+
 template <int R, int KIND, int LOGW>
 cudaError_t launch_one (const FftArgs& a, cudaStream_t stream)
 {
+#if CFB_LOGM <= 5
+    if constexpr (R == 16)
+        if (small_applies<KIND, LOGW> (a))
+            return launch_small<KIND, LOGW> (a, stream);
+#endif
     using L = Launch<CFB_LOGM, R>;
     auto kernel = fft_kernel<CFB_LOGM, R, KIND, LOGW>;
     constexpr int smem_bytes = LOGW != 0 ? L::SMEM_BYTES_UNORD : L::SMEM_BYTES;

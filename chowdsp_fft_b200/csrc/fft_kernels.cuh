@@ -1304,6 +1304,110 @@ __global__ void __launch_bounds__ (Launch<LOGM, R>::THREADS, Launch<LOGM, R>::MI
 {
     fft_body<LOGM, R, KIND, LOGW> (a);
 }
+// ---------------------------------------------------------------------------------------------
+// Dense batches of TINY transforms (16 .. 64 complex points: one, two or four threads per transform).  In fft_kernel a load
+// instruction of such a transform covers 8 .. 32 bytes of every 128-byte line it touches, so a warp's access spreads over 8 .. 32
+// lines: sector-efficient at best, but four to sixteen times the L1 tag work and, for one or two threads per transform, partial-
+// sector stores (ncu: l1tex-bound at 1.8 .. 5.3 TB/s).  Here the CTA's transforms, which are contiguous in a dense batch, are copied
+// with fully coalesced 64-bit accesses into padded shared-memory rows (the pad spreads a warp's transforms over the banks), every
+// transform runs fft_core on its row (input = private shared-memory image, output = the same row through a generic pointer) and the
+// rows go back with coalesced stores (unordered inputs are copied straight into the transforms' staging images instead).  Batch
+// stride = transform length on both sides, 16 / 32 complex points; everything else keeps fft_kernel.
+// ---------------------------------------------------------------------------------------------
+template <int LOGM, int KIND, int LOGW>
+struct SmallLaunch
+{
+    using G = Geo<LOGM, 16>;
+    using L = Launch<LOGM, 16>;
+    // float2 slots between rows: a half-warp's rows start 8 / 4 / 2 banks apart for 4 / 2 / 1 threads per transform (one thread per
+    // transform with an unordered output keeps rows 16-byte aligned for the 128-bit drain and accepts two-way conflicts)
+    static constexpr int PAD = G::T >= 4 ? 4 : G::T == 2 ? 2 : (LOGW != 0 ? 2 : 1);
+    static constexpr int PITCH = G::M + PAD;
+    static constexpr int XCH_F2 = LOGW != 0 ? G::SMEM_F2_UNORD : G::SMEM_F2;
+    static constexpr int SMEM_BYTES = L::PER_CTA * (PITCH + XCH_F2) * 8;
+    // unordered INPUTS (inverse kinds) are copied straight into the padded staging image fft_core expects (IN_STAGED)
+    static constexpr bool IN_IMAGE = LOGW != 0 && (KIND == C2C_BWD || KIND == C2R);
+    // one or two threads per transform: 3.1-3.3x / 1.5-1.6x over fft_kernel on B200; with four (64 points) it is a tie for ordered
+    // data and 13-17 % slower for unordered outputs (profiles/r02_small_kernel.txt), so those stay with fft_kernel
+    static constexpr bool APPLIES = G::T <= 2;
+};
+template <int LOGM, int KIND, int LOGW>
+FFT_HD void small_body (const FftArgs& a)
+{
+    using SL = SmallLaunch<LOGM, KIND, LOGW>;
+    using G = typename SL::G;
+    constexpr int T = G::T, M = G::M, PER_CTA = SL::L::PER_CTA, THREADS = SL::L::THREADS, PITCH = SL::PITCH;
+    constexpr int ITERS = PER_CTA * M / THREADS; // = 16
+    FFT_DYN_SMEM (float2, smem);
+    float2* rows = smem;
+    float2* xch = smem + PER_CTA * PITCH;
+    const int tid = (int) threadIdx.x;
+    const long long x0 = (long long) blockIdx.x * PER_CTA;
+    const long long left = (long long) a.batch - x0;
+    const int total = (int) (left < PER_CTA ? left : PER_CTA) * M; // complex elements of this CTA's transforms
+    const float2* __restrict__ in2 = reinterpret_cast<const float2*> (a.in) + x0 * M;
+    float2* __restrict__ out2 = reinterpret_cast<float2*> (a.out) + x0 * M;
+    float2 t[ITERS];
+    const int j = tid & (T - 1), lt = tid / T;
+    float2* row = rows + lt * PITCH;
+    if constexpr (SL::IN_IMAGE)
+    {
+        // unordered input: 128-bit coalesced copy of the CTA's spectra into every transform's staging image (the layout staging_fill builds)
+        const float4* __restrict__ in4 = reinterpret_cast<const float4*> (a.in) + x0 * (M / 2);
+        float4 t4[ITERS / 2];
+#pragma unroll
+        for (int i = 0; i < ITERS / 2; ++i)
+        {
+            const int e = tid + i * THREADS;
+            t4[i] = e < total / 2 ? ldg_stream (in4 + e) : make_float4 (0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < ITERS / 2; ++i)
+        {
+            const int e = tid + i * THREADS;
+            sts4 (reinterpret_cast<float*> (xch + (e >> (LOGM - 1)) * SL::XCH_F2) + upad (4 * (e & (M / 2 - 1)), LOGW), t4[i]);
+        }
+        __syncthreads();
+        fft_core<LOGM, 16, KIND, LOGW, true, false, false, 0> (nullptr, reinterpret_cast<float*> (row), true, j, xch + lt * SL::XCH_F2, a.tw, a.rtw);
+    }
+    else
+    {
+#pragma unroll
+        for (int i = 0; i < ITERS; ++i)
+        {
+            const int e = tid + i * THREADS;
+            t[i] = e < total ? ldg_stream (in2 + e) : make_float2 (0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < ITERS; ++i)
+        {
+            const int e = tid + i * THREADS;
+            sts2 (rows + (e >> LOGM) * PITCH + (e & (M - 1)), t[i]);
+        }
+        __syncthreads();
+        fft_core<LOGM, 16, KIND, LOGW, false, false, false, 2> (nullptr, reinterpret_cast<float*> (row), true, j, xch + lt * SL::XCH_F2, a.tw, a.rtw, row);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i)
+    {
+        const int e = tid + i * THREADS;
+        t[i] = lds2 (rows + (e >> LOGM) * PITCH + (e & (M - 1)));
+    }
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i)
+    {
+        const int e = tid + i * THREADS;
+        if (e < total)
+            out2[e] = t[i];
+    }
+}
+template <int LOGM, int KIND, int LOGW>
+__global__ void __launch_bounds__ (Launch<LOGM, 16>::THREADS, 3) fft_small_kernel (const FftArgs a)
+{
+    small_body<LOGM, KIND, LOGW> (a);
+}
+
 // the same transform with the JUCE adapter's conventions (fft_core: FMT = 1), ordered layouts, R2C / C2R / C2C_BWD
 template <int LOGM, int R, int KIND>
 __global__ void __launch_bounds__ (Launch<LOGM, R>::THREADS, Launch<LOGM, R>::MIN_BLOCKS) fft_kernel_juce (const FftArgs a)

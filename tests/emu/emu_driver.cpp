@@ -220,6 +220,75 @@ int emu_fft (int logM, int kind, int unord, int logW, const float* in, float* ou
     return rc;
 }
 
+} // extern "C"
+// staged kernel for dense batches of tiny transforms (fft_small_kernel); -1: kind / layout / size not served by it
+namespace
+{
+template <int LOGM, int KIND, int LOGW>
+int emu_small_one (FftArgs a)
+{
+    using SL = SmallLaunch<LOGM, KIND, LOGW>;
+    if constexpr (! SL::APPLIES)
+        return -1;
+    else
+    {
+        using G = typename SL::G;
+        std::vector<float2> tw ((size_t) G::TW_LEN + 1), rtw ((size_t) G::M / 2 + 1);
+        fill_stage_twiddles<LOGM, 16> (tw.data());
+        fill_real_twiddles (rtw.data(), G::M);
+        a.tw = tw.data();
+        a.rtw = rtw.data();
+        const unsigned grid = (unsigned) ((a.batch + SL::L::PER_CTA - 1) / SL::L::PER_CTA);
+        emu::launch (fft_small_kernel<LOGM, KIND, LOGW>, dim3 (grid), dim3 (SL::L::THREADS), (size_t) SL::SMEM_BYTES, a);
+        return 0;
+    }
+}
+template <int LOGM>
+int emu_small_logm (int kind, int logW, const FftArgs& a)
+{
+    switch (kind * 4 + logW)
+    {
+        case 0: return emu_small_one<LOGM, C2C_FWD, 0> (a);
+        case 2: return emu_small_one<LOGM, C2C_FWD, 2> (a);
+        case 4: return emu_small_one<LOGM, C2C_BWD, 0> (a);
+        case 6: return emu_small_one<LOGM, C2C_BWD, 2> (a);
+        case 8: return emu_small_one<LOGM, R2C, 0> (a);
+        case 10: return emu_small_one<LOGM, R2C, 2> (a);
+        case 12: return emu_small_one<LOGM, C2R, 0> (a);
+        case 14: return emu_small_one<LOGM, C2R, 2> (a);
+    }
+    return -1;
+}
+} // namespace
+extern "C"
+{
+int emu_small (int logM, int kind, int logW, const float* in, float* out, int batch, int log_conflicts, long* stats)
+{
+    FftArgs a {};
+    a.in = in;
+    a.out = out;
+    a.in_inner = a.out_inner = 2LL << logM;
+    a.inner = batch;
+    a.batch = batch;
+    emu::g_log_smem = log_conflicts != 0;
+    emu::g_stats = {};
+    int rc = -1;
+    switch (logM)
+    {
+        case 4: rc = emu_small_logm<4> (kind, logW, a); break;
+        case 5: rc = emu_small_logm<5> (kind, logW, a); break;
+        default: break;
+    }
+    if (stats)
+    {
+        stats[0] = emu::g_stats.ops;
+        stats[1] = emu::g_stats.wavefronts;
+        stats[2] = emu::g_stats.ideal;
+        stats[3] = emu::g_stats.worst;
+    }
+    return rc;
+}
+
 // persistent TMA-pipelined transform (pipe_kernels.cuh): `grid` resident CTAs loop over `batch` contiguous transforms
 int emu_pipe (int logM, int kind, int unord, const float* in, float* out, int batch, int grid, int log_conflicts, long* stats)
 {

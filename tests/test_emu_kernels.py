@@ -26,6 +26,7 @@ def emu():
     L.emu_istft.argtypes = [C.c_int] * 4 + [fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 4 + [fp, C.c_float, C.c_int]
     L.emu_mixed.argtypes = [C.c_int, C.c_int, C.c_int, fp, fp, C.c_int, C.c_longlong, C.c_longlong, C.c_int]
     L.emu_mixq.argtypes = [C.c_int, C.c_int, C.c_int, fp, fp, C.c_int, C.c_longlong, C.c_longlong]
+    L.emu_small.argtypes = [C.c_int, C.c_int, C.c_int, fp, fp, C.c_int, C.c_int, C.POINTER(C.c_long)]
     L.emu_fft_juce.argtypes = [C.c_int, C.c_int, C.c_int, fp, fp, C.c_int, C.c_longlong, C.c_longlong]
     L.emu_stft.argtypes = [C.c_int] * 3 + [fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 4 + [fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_long)]
     return L
@@ -494,6 +495,37 @@ def test_emulated_mixed_radix(emu, oracle_mod, N, is_c):
             refc = np.ascontiguousarray(ref, np.float32)
             assert emu.emu_mixed(M, 1 if is_c else 3, 0 if ordered else W, refc.ctypes.data_as(fp), b.ctypes.data_as(fp), 3, nfl, nfl, 2) == 0
             assert o.rel_l2(b, o.np_transform(ref, N, is_c, W, True, ordered)) < 4e-7, (W, ordered)
+
+
+@pytest.mark.parametrize("logM", [4, 5])
+def test_emulated_small_kernel(emu, oracle_mod, logM):
+    """fft_small_kernel: dense batches of 16- / 32-point transforms staged through padded shared-memory rows (coalesced copies
+    in and out, fft_core on the row; unordered inputs copied straight into the staging images).  Every kind / layout against the
+    oracle, a ragged last CTA (batch not a multiple of the CTA's transforms) and in place; the staging copies and the row accesses
+    of the ordered kinds are bank-conflict free."""
+    o = oracle_mod
+    M = 1 << logM
+    rng = np.random.default_rng(logM)
+    batch = 3 * (256 // (M // 16)) // 2 + 5  # one and a half CTAs
+    stats = (C.c_long * 4)()
+    for is_c in (True, False):
+        N = M if is_c else 2 * M
+        nfl = 2 * N if is_c else N
+        x = rng.uniform(-1, 1, (batch, nfl)).astype(np.float32)
+        W = o.simd_width(N, is_c, False)
+        assert W == 4
+        for ordered in (True, False):
+            ref = np.ascontiguousarray(o.np_transform(x, N, is_c, W, False, ordered), np.float32)
+            f = np.full_like(x, np.nan)
+            assert emu.emu_small(logM, 0 if is_c else 2, 0 if ordered else 2, x.ctypes.data_as(fp), f.ctypes.data_as(fp), batch, 1, stats) == 0
+            assert o.rel_l2(f, ref) < 4e-7, (is_c, ordered)
+            assert stats[1] <= (1.05 if ordered else 2.0) * stats[2], ("shared-memory wavefronts", is_c, ordered, list(stats))
+            g = x.copy()  # in place
+            assert emu.emu_small(logM, 0 if is_c else 2, 0 if ordered else 2, g.ctypes.data_as(fp), g.ctypes.data_as(fp), batch, 0, None) == 0
+            assert np.array_equal(g, f)
+            b = np.full_like(x, np.nan)  # inverse from the ordered / unordered spectrum
+            assert emu.emu_small(logM, 1 if is_c else 3, 0 if ordered else 2, ref.ctypes.data_as(fp), b.ctypes.data_as(fp), batch, 0, None) == 0
+            assert o.rel_l2(b / N, x) < 4e-7, (is_c, ordered, "round trip")
 
 
 @pytest.mark.parametrize("N", [96, 192, 384, 480, 640, 768, 9216, 160, 288, 1920, 2560])

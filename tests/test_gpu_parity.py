@@ -635,6 +635,55 @@ def test_mixed_radix_kernel_routing(cf, oracle_mod, ref_lib, N, hook):
         cf.set_tuning("mixq", -1)
 
 
+def test_small_transform_kernel_routing(cf, oracle_mod):
+    """Dense batches of 16- / 32-point complex transforms (C2C N = 16, 32; real N = 32, 64) run in fft_small_kernel (coalesced staging
+    through shared-memory rows); strided batches, misaligned bases and the tuning hook small = 0 fall back to fft_kernel.  Same results
+    either way (bit-identical: the same fft_core code), ragged batches, in place, every kind and layout."""
+    o = oracle_mod
+    rng = np.random.default_rng(16)
+    for N, is_c in [(16, True), (32, True), (32, False), (64, False)]:
+        nfl = 2 * N if is_c else N
+        W = o.simd_width(N, is_c, False)
+        s = cf.fft_new_setup(N, cf.FFT_COMPLEX if is_c else cf.FFT_REAL, False)
+        try:
+            batch = 1000  # not a multiple of the CTA's 128 / 256 transforms
+            x = rng.uniform(-1, 1, (batch, nfl)).astype(np.float32)
+            for ordered in (True, False):
+                for backward in (False, True):
+                    src = x if not backward else np.ascontiguousarray(o.np_transform(x, N, is_c, W, False, ordered), np.float32)
+                    want = o.np_transform(src, N, is_c, W, backward, ordered)
+                    d_in, d_out = dev(src), torch.full((batch, nfl), float("nan"), device="cuda")
+                    direction = cf.FFT_BACKWARD if backward else cf.FFT_FORWARD
+                    cf.fft_transform_batched(s, d_in, d_out, batch, nfl, nfl, direction, ordered)
+                    torch.cuda.synchronize()
+                    assert "fft_small_kernel" in cf.last_kernel(), cf.last_kernel()
+                    got = host(d_out)
+                    assert o.rel_l2(got, want) < o.parity_tol(N), (N, is_c, ordered, backward)
+                    # strided batch (gap between rows): fft_kernel, bit-identical
+                    gap = nfl + 8
+                    d_in2 = torch.zeros((batch, gap), device="cuda")
+                    d_in2[:, :nfl] = d_in
+                    d_out2 = torch.full((batch, gap), float("nan"), device="cuda")
+                    cf.fft_transform_batched(s, d_in2, d_out2, batch, gap, gap, direction, ordered)
+                    torch.cuda.synchronize()
+                    assert "fft_small_kernel" not in cf.last_kernel()
+                    assert np.array_equal(host(d_out2)[:, :nfl], got)
+                    assert bool(torch.isnan(d_out2[:, nfl:]).all())
+                    # in place
+                    d_io = d_in.clone()
+                    cf.fft_transform_batched(s, d_io, d_io, batch, nfl, nfl, direction, ordered)
+                    torch.cuda.synchronize()
+                    assert np.array_equal(host(d_io), got)
+            cf.set_tuning("small", 0)
+            d_out = torch.empty((batch, nfl), device="cuda")
+            cf.fft_transform_batched(s, dev(x), d_out, batch, nfl, nfl, cf.FFT_FORWARD, True)
+            torch.cuda.synchronize()
+            assert "fft_small_kernel" not in cf.last_kernel()
+        finally:
+            cf.set_tuning("small", -1)
+            cf.fft_destroy_setup(s)
+
+
 @pytest.mark.parametrize("N", [32, 64, 256, 1024, 2048, 4096, 16384, 32768])
 def test_juce_conventions(cf, oracle_mod, N):
     """The JUCE adapter's conventions (chowdsp_fft_juce.cpp:32-86) fused into the transform kernels: perform (inverse

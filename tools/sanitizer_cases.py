@@ -36,6 +36,9 @@ def roundtrip(N, is_c, batch, ordered, avx=True):
     print(f"ok round trip N={N} {'C2C' if is_c else 'R2C'} {'ordered' if ordered else 'unordered'} avx={avx}: {k1} | {cf.last_kernel()}", flush=True)
 
 
+for N, is_c in [(16, True), (32, True), (32, False), (64, False)]:  # fft_small_kernel (dense batches of tiny transforms)
+    for ordered in (True, False):
+        roundtrip(N, is_c, 300, ordered, avx=False)
 for N, is_c in [(64, True), (1024, True), (4096, True), (2048, False), (8192, False)]:
     for ordered in (True, False):
         roundtrip(N, is_c, 3, ordered)
