@@ -168,9 +168,9 @@ namespace
 template <int LOGW>
 cudaError_t launch_pconv_one (const PConvArgs& a, cudaStream_t stream)
 {
-    using G = Geo<CFB_LOGM, 16>;
+    using PL = PConvLaunch<CFB_LOGM>;
     auto kernel = pconv_kernel<CFB_LOGM, LOGW>;
-    constexpr int smem_bytes = G::SMEM_F2_UNORD * 8;
+    constexpr int smem_bytes = PL::SMEM_BYTES;
     if (smem_bytes > 48 * 1024)
     {
         const cudaError_t e = cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
@@ -179,7 +179,7 @@ cudaError_t launch_pconv_one (const PConvArgs& a, cudaStream_t stream)
     }
     if (a.channels <= 0)
         return cudaSuccess;
-    kernel<<<(unsigned) a.channels, G::T, smem_bytes, stream>>> (a);
+    kernel<<<(unsigned) ((a.channels + PL::PER_CTA - 1) / PL::PER_CTA), PL::THREADS, smem_bytes, stream>>> (a);
     count_launch();
     return cudaGetLastError();
 }

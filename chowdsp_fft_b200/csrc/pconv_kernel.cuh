@@ -44,6 +44,17 @@ FFT_HD void cmac4 (float4& ar, float4& ai, const float4& xr, const float4& xi, c
     ar.w = fmaf (xr.w, hr.w, ar.w); ar.w = fmaf (-xi.w, hi.w, ar.w); ai.w = fmaf (xr.w, hi.w, ai.w); ai.w = fmaf (xi.w, hr.w, ai.w);
 }
 
+template <int LOGM>
+struct PConvLaunch
+{
+    using G = Geo<LOGM, 16>;
+    // channels per CTA: 256 threads' worth for blocks up to N = 512 (measured on B200, tools/pconv_sweep.py: 2.7x at N = 128, 1.6x at 256, +7 % at 512;
+    // from N = 1024 on one channel per CTA is 1..3 % faster and stays)
+    static constexpr int PER_CTA = G::T > 16 ? 1 : 256 / G::T;
+    static constexpr int THREADS = PER_CTA * G::T;
+    static constexpr int SMEM_BYTES = PER_CTA * G::SMEM_F2_UNORD * 8;
+};
+
 template <int LOGM, int LOGW>
 FFT_HD void pconv_body (const PConvArgs& a)
 {
@@ -51,12 +62,16 @@ FFT_HD void pconv_body (const PConvArgs& a)
     using G = Geo<LOGM, R>;
     constexpr int M = G::M, T = G::T, N = 2 * M, W = 1 << LOGW;
     constexpr int PAIRS = R / 4; // (4 re | 4 im) lane groups per thread: N / 8 per spectrum = 4 T
-    FFT_DYN_SMEM (float2, smem);
+    // small blocks: a CTA of 256 threads takes 256 / T channels (one channel per CTA left 4 .. 128-thread CTAs for N <= 4096);
+    // channels past the end redo the last one and skip every global store (the barriers inside fft_core are CTA-wide)
+    constexpr int PER_CTA = PConvLaunch<LOGM>::PER_CTA;
+    FFT_DYN_SMEM (float2, smem_all);
+    const int lt = PER_CTA == 1 ? 0 : (int) threadIdx.x / T, j = (int) threadIdx.x - lt * T;
+    float2* smem = smem_all + lt * G::SMEM_F2_UNORD;
     float* sf = reinterpret_cast<float*> (smem);
-    const int j = (int) threadIdx.x;
-    const int c = (int) blockIdx.x;
-    if (c >= a.channels)
-        return;
+    const long long c0 = (long long) blockIdx.x * PER_CTA + lt;
+    const bool active = PER_CTA == 1 || c0 < a.channels;
+    const int c = active ? (int) c0 : a.channels - 1;
 
     // 1. forward transform of the window; the unordered spectrum stays in shared memory (staging image)
     fft_core<LOGM, R, R2C, LOGW, false, true, false> (a.in + (long long) c * a.in_stride, nullptr, true, j, smem, a.tw, a.rtw);
@@ -72,8 +87,11 @@ FFT_HD void pconv_body (const PConvArgs& a)
         off[i] = (pr / (W / 4)) * 2 * W + (pr % (W / 4)) * 4;
         xr[i] = lds4 (sf + upad (off[i], LOGW));
         xi[i] = lds4 (sf + upad (off[i] + W, LOGW));
-        *reinterpret_cast<float4*> (slot + off[i]) = xr[i];     // delay-line write (linear across the CTA)
-        *reinterpret_cast<float4*> (slot + off[i] + W) = xi[i];
+        if (active)
+        {
+            *reinterpret_cast<float4*> (slot + off[i]) = xr[i];     // delay-line write (linear across the channel's threads)
+            *reinterpret_cast<float4*> (slot + off[i] + W) = xi[i];
+        }
         ar[i] = make_float4 (0.f, 0.f, 0.f, 0.f);
         ai[i] = make_float4 (0.f, 0.f, 0.f, 0.f);
     }
@@ -130,11 +148,11 @@ FFT_HD void pconv_body (const PConvArgs& a)
 
     // 5. inverse transform; only the last N/2 samples are valid in overlap-save and only they are stored
     float* outc = a.out + (long long) c * a.out_stride - M; // sample n >= M lands at out[n - M]
-    fft_core<LOGM, R, C2R, LOGW, true, false, true> (nullptr, outc, true, j, smem, a.tw, a.rtw);
+    fft_core<LOGM, R, C2R, LOGW, true, false, true> (nullptr, outc, active, j, smem, a.tw, a.rtw);
 }
 
 template <int LOGM, int LOGW>
-__global__ void __launch_bounds__ (Geo<LOGM, 16>::T, (Geo<LOGM, 16>::T <= 256 ? 2 : 1)) pconv_kernel (const PConvArgs a)
+__global__ void __launch_bounds__ (PConvLaunch<LOGM>::THREADS, (PConvLaunch<LOGM>::THREADS <= 256 ? 2 : 1)) pconv_kernel (const PConvArgs a)
 {
     pconv_body<LOGM, LOGW> (a);
 }

@@ -657,7 +657,8 @@ int emu_pconv (int logM, int logW, const float* in, long long in_stride, const f
         fill_real_twiddles (rtw.data(), G::M);
         PConvArgs a { in, in_stride, ir, ir_ch_stride, fdl, fdl_ch_stride, out, out_stride, channels, P, t, scaling, tw.data(), rtw.data() };
         emu::g_log_smem = false;
-        emu::launch (pconv_kernel<LOGM, LOGW>, dim3 ((unsigned) channels), dim3 (G::T), (size_t) G::SMEM_F2_UNORD * 8, a);
+        using PL = PConvLaunch<LOGM>;
+        emu::launch (pconv_kernel<LOGM, LOGW>, dim3 ((unsigned) ((channels + PL::PER_CTA - 1) / PL::PER_CTA)), dim3 (PL::THREADS), (size_t) PL::SMEM_BYTES, a);
         return 0;
     };
     using std::integral_constant;

@@ -202,7 +202,7 @@ def test_emulated_fused_partitioned_convolution(emu, oracle_mod, ref_lib, N, W):
     o = oracle_mod
     emu.emu_pconv.argtypes = [C.c_int, C.c_int, fp, C.c_longlong, fp, C.c_longlong, fp, C.c_longlong, fp, C.c_longlong,
                               C.c_int, C.c_int, C.c_int, C.c_float]
-    P, channels, blocks = 3, 2, 5
+    P, channels, blocks = 3, (2 if N >= 2048 else 37), 5  # 37 channels: more than one CTA of 32 / 256 channels at the small sizes, ragged
     B = N // 2
     rng = np.random.default_rng(N + W)
     x = rng.uniform(-1, 1, (channels, blocks * B)).astype(np.float32)
