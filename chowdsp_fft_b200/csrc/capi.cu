@@ -585,6 +585,7 @@ constexpr int kL2ChunkMbDefault = 16, kL2LanesDefault = 3, kL2PolicyDefault = 1;
 int g_l2_chunk_mb = kL2ChunkMbDefault, g_l2_lanes = kL2LanesDefault, g_l2_policy = kL2PolicyDefault;
 constexpr int kMaxLanes = 4;
 int g_mixq = 1; // tuning hook "mixq"
+int g_ristft = 1; // tuning hook "ristft": overlap-add synthesis through ristft_kernel where it applies
 constexpr int kTilePfDefault = 0;  // tuning hook "tile_pf" (large_plan.h: tile_pf_distance)
 constexpr int kTileTmaDefault = 0; // tuning hook "tile_tma" (large_plan.h: tile_tma_mode)
 
@@ -1791,6 +1792,64 @@ int istft_enqueue (Plan* p, const float* spectra, float* signal, int channels, i
             return 0;
         }
     }
+    // N = 128 .. 8192, hop = N/2, N/4 or N/8, any layout: the overlap-add stays in the registers of the transform's own
+    // thread group (ristft_kernel).  Items = (channel, segment); segment count as above, for the resident transform slots.
+    {
+        const bool hop_ok = hop * 2 == p->N || hop * 4 == p->N || hop * 8 == p->N;
+        const uintptr_t spec_al = ordered != 0 ? 7 : 15;
+        if (g_ristft != 0 && p->logM >= 6 && p->logM <= 12 && hop_ok && (spec_frame_stride & (ordered != 0 ? 1 : 3)) == 0 && (spec_channel_stride & (ordered != 0 ? 1 : 3)) == 0
+            && (reinterpret_cast<uintptr_t> (spectra) & spec_al) == 0 && (channel_stride & 1) == 0 && (reinterpret_cast<uintptr_t> (signal) & 7) == 0
+            && (window == nullptr || (reinterpret_cast<uintptr_t> (window) & 7) == 0))
+        {
+            Tables rt;
+            const int rrc = plan_tables (p, rt, 16);
+            if (rrc != 0)
+                return rrc;
+            const int per_cta16 = transforms_per_cta (p->logM, 16);
+            const long long slots = (long long) device_sm_count() * 2 * per_cta16; // two resident CTAs per SM (128 registers)
+            const int halo = (int) (p->N / hop) - 1;
+            int nseg = 1, seg_frames = frames;
+            long long best = -1;
+            for (int cand = 1; cand <= 256 && cand <= (frames + 7) / 8; ++cand)
+            {
+                const int sf = (frames + cand - 1) / cand;
+                const int ns = (frames + sf - 1) / sf;
+                const long long items = (long long) channels * ns;
+                const long long cost = ((items + slots - 1) / slots) * (sf + (ns > 1 ? halo : 0));
+                if (best < 0 || cost < best)
+                {
+                    best = cost;
+                    nseg = ns;
+                    seg_frames = sf;
+                }
+            }
+            FftArgs ra {};
+            ra.in = spectra;
+            ra.out = signal;
+            ra.in_inner = spec_frame_stride;
+            ra.in_outer = spec_channel_stride;
+            ra.out_inner = hop;
+            ra.out_outer = channel_stride;
+            ra.inner = frames;
+            ra.batch = channels * frames;
+            ra.tw = rt.tw;
+            ra.rtw = rt.rtw;
+            ra.window = window;
+            ra.seg_frames = seg_frames;
+            ra.nseg = nseg;
+            ra.scale = scale;
+            const int hq = (int) (hop * 16 / p->N); // hop / (2 T), T = N / 32: 8, 4 or 2
+            const cudaError_t re = launch_ristft (p->logM, hq, ordered != 0 ? 0 : p->logW, ra, stream);
+            if (re == cudaSuccess)
+            {
+                note_kernel ("cfb::ristft_kernel<%d,%d,%d>", p->logM, hq, ordered != 0 ? 0 : p->logW);
+                return 0;
+            }
+            if (re != cudaErrorInvalidConfiguration)
+                return fail_cuda (re, "register overlap-add istft kernel launch");
+            (void) cudaGetLastError();
+        }
+    }
     // segmentation: a CTA per (channel, segment of frames).  More segments fill the last wave of CTAs better but
     // every segment after a channel's first recomputes a halo of ceil (N / hop) - 1 frames; segments keep at
     // least 8 groups of frames.  Pick the count with the best (wave occupancy) x (useful fraction of the frames).
@@ -2523,6 +2582,11 @@ CFB_API int fft_b200_set_tuning (const char* key, int value)
     if (key != nullptr && std::strcmp (key, "spin_sync") == 0 && value >= -1 && value <= 1)
     {
         g_spin_sync = value == 1;
+        return 0;
+    }
+    if (key != nullptr && std::strcmp (key, "ristft") == 0 && value >= -1 && value <= 1)
+    {
+        g_ristft = value == -1 ? 1 : value;
         return 0;
     }
     if (key != nullptr && std::strcmp (key, "small") == 0 && value >= -1 && value <= 1)

@@ -111,6 +111,17 @@ cudaError_t launch_stft_pipe (int logM, int logW, int radix, const FftArgs& args
         default: return cudaErrorInvalidValue;
     }
 }
+cudaError_t launch_ristft (int logM, int hq, int logW, const FftArgs& args, cudaStream_t stream)
+{
+    switch (logM)
+    {
+#define X(n) \
+    case n: return launch_ristft_##n (hq, logW, args, stream);
+        CFB_FOR_SIZES (X)
+#undef X
+        default: return cudaErrorInvalidConfiguration;
+    }
+}
 cudaError_t launch_istft (int logM, int logW, int radix, const FftArgs& args, cudaStream_t stream)
 {
     switch (logM)

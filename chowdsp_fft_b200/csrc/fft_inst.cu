@@ -332,6 +332,58 @@ cudaError_t launch_istft_r (int logW, const FftArgs& a, cudaStream_t stream)
 }
 } // namespace
 
+// overlap-add synthesis with register accumulators (ristft_kernel): hq = hop / (2 T) in {2, 4, 8}; cudaErrorInvalidConfiguration = no such instance
+#if CFB_LOGM >= 6 && CFB_LOGM <= 12
+namespace
+{
+template <int HQ, int LOGW>
+cudaError_t launch_ristft_one (const FftArgs& a, cudaStream_t stream)
+{
+    using L = Launch<CFB_LOGM, 16>;
+    auto kernel = ristft_kernel<CFB_LOGM, HQ, LOGW>;
+    constexpr int smem_bytes = LOGW != 0 ? L::SMEM_BYTES_UNORD : L::SMEM_BYTES;
+    if (smem_bytes > 48 * 1024)
+    {
+        const cudaError_t e = cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e != cudaSuccess)
+            return e;
+    }
+    const long long items = (long long) (a.batch / a.inner) * a.nseg;
+    if (items <= 0)
+        return cudaSuccess;
+    kernel<<<(unsigned) ((items + L::PER_CTA - 1) / L::PER_CTA), L::THREADS, smem_bytes, stream>>> (a);
+    count_launch();
+    return cudaGetLastError();
+}
+template <int HQ>
+cudaError_t launch_ristft_h (int logW, const FftArgs& a, cudaStream_t stream)
+{
+    switch (logW)
+    {
+        case 0: return launch_ristft_one<HQ, 0> (a, stream);
+        case 2: return launch_ristft_one<HQ, 2> (a, stream);
+        case 3: return launch_ristft_one<HQ, 3> (a, stream);
+        default: return cudaErrorInvalidConfiguration;
+    }
+}
+} // namespace
+#endif
+cudaError_t CFB_CAT (launch_ristft_, CFB_LOGM) (int hq, int logW, const FftArgs& a, cudaStream_t stream)
+{
+#if CFB_LOGM >= 6 && CFB_LOGM <= 12
+    switch (hq)
+    {
+        case 2: return launch_ristft_h<2> (logW, a, stream);
+        case 4: return launch_ristft_h<4> (logW, a, stream);
+        case 8: return launch_ristft_h<8> (logW, a, stream);
+        default: return cudaErrorInvalidConfiguration;
+    }
+#else
+    (void) hq; (void) logW; (void) a; (void) stream;
+    return cudaErrorInvalidConfiguration;
+#endif
+}
+
 // overlap-add synthesis (istft_kernel); a.seg_frames must be a multiple of transforms_per_cta
 cudaError_t CFB_CAT (launch_istft_, CFB_LOGM) (int logW, int radix, const FftArgs& a, cudaStream_t stream)
 {

@@ -1640,6 +1640,97 @@ FFT_HD void istft_body (const FftArgs& a)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Overlap-add synthesis with the sums in REGISTERS (ristft_kernel): hop = N / 2, N / 4 or N / 8, transforms of 32 .. 256 threads
+// (N = 1024 .. 8192), ordered or unordered spectra.  Thread j's result registers are the sample pairs j + m T, and hop / 2 = T HQ
+// pairs, so slot m of a frame is slot m - HQ of the next one: the N - hop samples a frame shares with its successors stay in
+// R - HQ accumulator registers of the same thread that shift by HQ per frame, the hop samples that are final leave straight from
+// registers -- the scheme of the warp-pipelined wistft_kernel, for any transform whose threads are whole warps.  A transform's
+// thread group walks through the frames of one (channel, segment) item; no shared-memory frame buffers, no carried tails, no CTA
+// barrier (istft_kernel rewrites a tail of N - hop samples in shared memory for every group of 1 .. 8 frames: 1.7 .. 2.9 TB/s at
+// these sizes, tools/stft_sweep.py).  Segments other than a channel's first recompute a halo of N / hop - 1 frames.
+// a.in_inner / in_outer: floats between frames / channels of the spectra; a.out_inner = hop; a.out_outer: floats between channels
+// of the signal; a.nseg, a.seg_frames: segments per channel and frames per segment; a.scale; a.window (N floats or nullptr).
+// ---------------------------------------------------------------------------------------------
+template <int LOGM, int HQ, int LOGW>
+FFT_HD void ristft_body (const FftArgs& a)
+{
+    constexpr int R = 16;
+    using G = Geo<LOGM, R>;
+    constexpr int T = G::T;
+    static_assert (HQ >= 1 && 2 * HQ <= R && R % HQ == 0, "hop = N/2, N/4 or N/8");
+    // transforms smaller than a warp share their warp-level barriers with their neighbours: every item then runs the same number of
+    // iterations (seg_frames + HALO; frames outside its range are computed on a clamped index and neither summed nor stored)
+    constexpr bool UNIFORM = T < 32;
+    constexpr int NACC = R - HQ, HOP2 = T * HQ, HALO = R / HQ - 1;
+    constexpr int SMEM_F2 = LOGW != 0 ? G::SMEM_F2_UNORD : G::SMEM_F2;
+    FFT_DYN_SMEM (float2, smem);
+    const int tid = (int) threadIdx.x;
+    const int j = tid & (T - 1), lt = tid / T, per_cta = (int) blockDim.x / T;
+    float2* fb = smem + lt * SMEM_F2;
+    const int frames = a.inner;
+    const long long items = (long long) (a.batch / a.inner) * a.nseg;
+    long long item = (long long) blockIdx.x * per_cta + lt;
+    const bool item_ok = item < items;
+    if (! item_ok)
+    {
+        if constexpr (! UNIFORM)
+            return; // every barrier below is private to the transform's own warps
+        item = items - 1;
+    }
+    const int c = (int) (item / a.nseg);
+    const int fs = (int) (item - (long long) c * a.nseg) * a.seg_frames;
+    const int fe = fs + a.seg_frames < frames ? fs + a.seg_frames : frames;
+    const float* __restrict__ spec = a.in + (long long) c * a.in_outer;
+    float2* __restrict__ sig2 = reinterpret_cast<float2*> (a.out + (long long) c * a.out_outer) + j;
+    const float2* __restrict__ win2 = reinterpret_cast<const float2*> (a.window);
+    const float2 scale2 = make_float2 (a.scale, a.scale);
+    float2 acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i)
+        acc[i] = make_float2 (0.f, 0.f);
+    const int f_first = UNIFORM ? fs - HALO : (fs - HALO > 0 ? fs - HALO : 0);
+    const int f_last = UNIFORM ? fs + a.seg_frames : fe;
+    for (int ff = f_first; ff < f_last; ++ff)
+    {
+        const bool valid = ! UNIFORM || (item_ok && ff >= 0 && ff < fe);
+        const int f = valid ? ff : (fe - 1);
+        float2 v[R];
+        fft_core<LOGM, R, C2R, LOGW, false, false, false, 0, NoHook, true> (spec + (long long) f * a.in_inner, nullptr, true, j, fb, a.tw, a.rtw, nullptr, nullptr, NoHook(), v);
+        tsync<T, true>(); // the last exchange has been read by every thread of the transform: the next frame may write the region
+        if (! valid)
+            continue;
+#pragma unroll
+        for (int m = 0; m < R; ++m)
+        {
+            v[m] = f2_mul (v[m], scale2);
+            if (win2 != nullptr)
+                v[m] = f2_mul (v[m], __ldg (win2 + j + m * T));
+        }
+        float2* __restrict__ o = sig2 + (long long) f * HOP2;
+        if (f >= fs)
+        {
+#pragma unroll
+            for (int m = 0; m < HQ; ++m)
+                o[m * T] = f2_add (acc[m], v[m]);
+        }
+#pragma unroll
+        for (int i = 0; i < NACC; ++i)
+            acc[i] = i + HQ < NACC ? f2_add (acc[i + HQ], v[i + HQ]) : v[i + HQ];
+        if (f + 1 == fe && fe == frames) // end of the channel: the carried samples are output too
+        {
+#pragma unroll
+            for (int i = 0; i < NACC; ++i)
+                o[HOP2 + T * i] = acc[i];
+        }
+    }
+}
+template <int LOGM, int HQ, int LOGW>
+__global__ void __launch_bounds__ (Launch<LOGM, 16>::THREADS, 2) ristft_kernel (const FftArgs a)
+{
+    ristft_body<LOGM, HQ, LOGW> (a);
+}
+
 template <int LOGM, int R, int LOGW>
 __global__ void __launch_bounds__ (Launch<LOGM, R>::THREADS, Launch<LOGM, R>::MIN_BLOCKS) istft_kernel (const FftArgs a)
 {

@@ -184,6 +184,8 @@ void fft_b200_clear_error (void);
      "l2_lanes"     helper streams / ring slots the chunks alternate over (1..4, default 3)
      "l2_policy"    1 = evict_last / evict_first L2 hints on ring / streaming accesses of the chunked schedules (default)
      "tile_pf"      tensor-map L2 prefetch distance of the multi-pass tile kernels in tiles (default 0 = off: measured 3..10 % slower)
+     "ristft"       1 = overlap-add synthesis with hop = N/2, N/4, N/8 at N = 1024 .. 8192 keeps its sums in registers (ristft_kernel; default),
+                    0 = istft_kernel (shared-memory frame buffers and carried tails)
      "small"        1 = dense batches of 16- / 32-point complex transforms run in the staged fft_small_kernel (default), 0 = fft_kernel
      "mixq"         1 = sizes Q 2^p with Q in {3, 5, 9, 15} run in mixq_kernel (default), 0 = always the generic mixed-radix kernel
      "zero_copy_kb" pinned (device-mapped) host buffers up to this many KiB are transformed in place over PCIe by the kernel's own

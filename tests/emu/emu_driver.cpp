@@ -527,6 +527,44 @@ int emu_wistft (int logM, int hq, const float* spec, float* sig, int channels, i
 }
 
 // overlap-add synthesis (istft_kernel): `channels` x `frames` spectra -> signals, segments of seg_groups CTA groups
+// overlap-add synthesis with register accumulators (ristft_kernel); -1: no such instance
+int emu_ristft (int logM, int hq, int logW, const float* spec, float* sig, int channels, int frames, long long spec_channel_stride, long long spec_frame_stride, long long channel_stride, const float* window, float scale, int nseg)
+{
+    auto run = [&] (auto logm_c, auto hq_c, auto logw_c) -> int
+    {
+        constexpr int LOGM = decltype (logm_c)::value, HQ = decltype (hq_c)::value, LOGW = decltype (logw_c)::value;
+        using G = Geo<LOGM, 16>;
+        using L = Launch<LOGM, 16>;
+        std::vector<float2> tw ((size_t) G::TW_LEN + 1), rtw ((size_t) G::M / 2 + 1);
+        fill_stage_twiddles<LOGM, 16> (tw.data());
+        fill_real_twiddles (rtw.data(), G::M);
+        FftArgs a {};
+        a.in = spec; a.out = sig;
+        a.in_inner = spec_frame_stride; a.in_outer = spec_channel_stride; a.out_inner = 2 * G::T * HQ; a.out_outer = channel_stride;
+        a.inner = frames; a.batch = channels * frames;
+        a.tw = tw.data(); a.rtw = rtw.data();
+        a.window = window;
+        a.scale = scale;
+        a.seg_frames = (frames + nseg - 1) / nseg;
+        a.nseg = (frames + a.seg_frames - 1) / a.seg_frames;
+        const long long items = (long long) channels * a.nseg;
+        emu::g_log_smem = false;
+        emu::launch (ristft_kernel<LOGM, HQ, LOGW>, dim3 ((unsigned) ((items + L::PER_CTA - 1) / L::PER_CTA)), dim3 (L::THREADS),
+                     (size_t) (LOGW != 0 ? L::SMEM_BYTES_UNORD : L::SMEM_BYTES), a);
+        return 0;
+    };
+    using std::integral_constant;
+    int rc = -1;
+#define CFB_EMU_RIS(M, H, W) if (logM == M && hq == H && logW == W) rc = run (integral_constant<int, M> {}, integral_constant<int, H> {}, integral_constant<int, W> {});
+    CFB_EMU_RIS (6, 4, 3) CFB_EMU_RIS (6, 2, 0) CFB_EMU_RIS (7, 4, 0) CFB_EMU_RIS (8, 8, 2) CFB_EMU_RIS (8, 4, 3)
+    CFB_EMU_RIS (9, 4, 0) CFB_EMU_RIS (9, 8, 3) CFB_EMU_RIS (9, 2, 2)
+    CFB_EMU_RIS (10, 4, 3) CFB_EMU_RIS (10, 2, 0)
+    CFB_EMU_RIS (11, 4, 0) CFB_EMU_RIS (11, 8, 3)
+    CFB_EMU_RIS (12, 4, 0)
+#undef CFB_EMU_RIS
+    return rc;
+}
+
 int emu_istft (int logM, int radix, int unord, int logW, const float* spec, float* sig, int channels, int frames, long long spec_channel_stride, long long spec_frame_stride, long long channel_stride, long long hop, const float* window, float scale, int seg_groups)
 {
     auto run = [&] (auto logm_c, auto r_c, auto logw_c) -> int

@@ -24,6 +24,7 @@ def emu():
     L.emu_wpipe.argtypes = [C.c_int] * 5 + [fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 4 + [fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_long)]
     L.emu_wistft.argtypes = [C.c_int, C.c_int, fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 3 + [fp, C.c_float, C.c_int, C.c_int, C.c_int]
     L.emu_istft.argtypes = [C.c_int] * 4 + [fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 4 + [fp, C.c_float, C.c_int]
+    L.emu_ristft.argtypes = [C.c_int] * 3 + [fp, fp, C.c_int, C.c_int] + [C.c_longlong] * 3 + [fp, C.c_float, C.c_int]
     L.emu_mixed.argtypes = [C.c_int, C.c_int, C.c_int, fp, fp, C.c_int, C.c_longlong, C.c_longlong, C.c_int]
     L.emu_mixq.argtypes = [C.c_int, C.c_int, C.c_int, fp, fp, C.c_int, C.c_longlong, C.c_longlong]
     L.emu_small.argtypes = [C.c_int, C.c_int, C.c_int, fp, fp, C.c_int, C.c_int, C.POINTER(C.c_long)]
@@ -469,6 +470,32 @@ def test_emulated_istft_overlap_add(emu, oracle_mod, N, radix, hop, frames, orde
     assert rc == 0
     want = o.np_istft_overlap_add(spec, N, hop, W, ordered, win if windowed else None, 1.0 / N)
     assert np.all(np.isnan(out[:, samples:]))  # nothing written past the end of a channel
+    assert o.rel_l2(out[:, :samples], want) < min(o.parity_tol(N), 4e-7)
+
+
+@pytest.mark.parametrize("N,hq,W,ordered,frames,nseg", [(128, 4, 8, False, 23, 2), (128, 2, 8, True, 41, 3), (256, 4, 8, True, 30, 4), (512, 8, 4, False, 9, 1), (512, 4, 8, False, 26, 3),
+                                                        (1024, 4, 8, True, 19, 1), (1024, 8, 8, False, 7, 1), (1024, 2, 4, False, 37, 3), (2048, 4, 8, False, 21, 2),
+                                                        (2048, 2, 8, True, 33, 2), (4096, 4, 8, True, 11, 1), (4096, 8, 8, False, 9, 2), (8192, 4, 8, True, 9, 2)])
+@pytest.mark.parametrize("windowed", [False, True])
+def test_emulated_register_overlap_add(emu, oracle_mod, N, hq, W, ordered, frames, nseg, windowed):
+    """ristft_kernel: overlap-add synthesis with the sums in the registers of the transform's own thread group (hop = N/2, N/4, N/8;
+    32 .. 256 threads per transform; ordered and unordered spectra) == oracle.np_istft_overlap_add.  Segments with recomputed halos,
+    odd channel counts (transform groups that leave a CTA early), every output sample written exactly once (the buffer starts as NaN)."""
+    o = oracle_mod
+    channels = 3 if N >= 1024 else 21  # small transforms: several items per warp, ragged last CTA
+    hop = hq * N // 16  # hq = hop / (2 T), T = N / 32
+    rng = np.random.default_rng(N + hq)
+    x = rng.uniform(-1, 1, (channels * frames, N)).astype(np.float32)
+    spec = np.ascontiguousarray(o.np_transform(x, N, False, W, False, ordered).reshape(channels, frames, N))
+    win = (0.5 - 0.5 * np.cos(2 * np.pi * (np.arange(N) + 0.5) / N)).astype(np.float32)
+    samples = (frames - 1) * hop + N
+    out = np.full((channels, samples + 2), np.nan, np.float32)
+    rc = emu.emu_ristft(int(np.log2(N)) - 1, hq, 0 if ordered else {8: 3, 4: 2}[W], spec.ctypes.data_as(fp), out.ctypes.data_as(fp), channels, frames,
+                        frames * N, N, samples + 2, win.ctypes.data_as(fp) if windowed else None, 1.0 / N, nseg)
+    assert rc == 0
+    want = o.np_istft_overlap_add(spec, N, hop, W, ordered, win if windowed else None, 1.0 / N)
+    assert np.all(np.isnan(out[:, samples:]))
+    assert not np.any(np.isnan(out[:, :samples]))
     assert o.rel_l2(out[:, :samples], want) < min(o.parity_tol(N), 4e-7)
 
 

@@ -414,6 +414,54 @@ def test_warp_pipelined_istft(cf, oracle_mod, N, hop, frames, channels, warps):
         cf.fft_destroy_setup(s)
 
 
+@pytest.mark.parametrize("N,hop,frames,channels", [(128, 32, 900, 41), (256, 128, 300, 7), (512, 64, 210, 5), (2048, 512, 120, 9), (4096, 1024, 70, 6), (8192, 1024, 33, 3), (8192, 4096, 9, 2)])
+def test_register_overlap_add_istft(cf, oracle_mod, N, hop, frames, channels):
+    """Overlap-add synthesis through ristft_kernel (hop = N/2, N/4, N/8; N = 128 .. 8192; sums in the registers of the transform's own
+    threads; unordered spectra at every size, ordered ones where no warp-pipelined kernel exists): == oracle.np_istft_overlap_add, every
+    sample written exactly once, bit-identical between runs, and the same signal as istft_kernel (tuning hook ristft = 0)."""
+    o = oracle_mod
+    rng = np.random.default_rng(N + hop + frames)
+    x = rng.uniform(-1, 1, (channels * frames, N)).astype(np.float32)
+    win = (0.5 - 0.5 * np.cos(2 * np.pi * (np.arange(N) + 0.5) / N)).astype(np.float32)
+    samples = (frames - 1) * hop + N
+    W = o.simd_width(N, False, True)
+    s = cf.fft_new_setup(N, cf.FFT_REAL)
+    dw = dev(win)
+    try:
+        for ordered in (True, False):
+            spec = np.ascontiguousarray(o.np_transform(x, N, False, W, False, ordered).reshape(channels, frames, N))
+            dspec = dev(spec)
+            for w in (None, dw):
+                out = torch.full((channels, samples + 6), float("nan"), device="cuda")
+                n0 = cf.launch_count()
+                cf.fft_istft_overlap_add(s, dspec, out, channels, frames, frames * N, N, samples + 6, hop, w, 1.0 / N, ordered)
+                torch.cuda.synchronize()
+                assert cf.launch_count() - n0 == 1
+                if not (ordered and N in (1024, 2048)):
+                    assert "ristft_kernel" in cf.last_kernel(), cf.last_kernel()
+                got = host(out)
+                assert np.all(np.isnan(got[:, samples:])) and not np.any(np.isnan(got[:, :samples]))
+                want = o.np_istft_overlap_add(spec, N, hop, W, ordered, win if w is not None else None, 1.0 / N)
+                assert o.rel_l2(got[:, :samples], want) < o.parity_tol(N), (ordered, w is not None)
+                out2 = torch.full_like(out, float("nan"))
+                cf.fft_istft_overlap_add(s, dspec, out2, channels, frames, frames * N, N, samples + 6, hop, w, 1.0 / N, ordered)
+                torch.cuda.synchronize()
+                assert torch.equal(out[:, :samples], out2[:, :samples])
+            cf.set_tuning("ristft", 0)
+            cf.set_tuning("wistft", 0)
+            out3 = torch.full((channels, samples + 6), float("nan"), device="cuda")
+            cf.fft_istft_overlap_add(s, dspec, out3, channels, frames, frames * N, N, samples + 6, hop, dw, 1.0 / N, ordered)
+            torch.cuda.synchronize()
+            assert "cfb::istft_kernel" in cf.last_kernel(), cf.last_kernel()
+            assert o.rel_l2(host(out3)[:, :samples], host(out)[:, :samples]) < 1e-6
+            cf.set_tuning("ristft", -1)
+            cf.set_tuning("wistft", -1)
+    finally:
+        cf.set_tuning("ristft", -1)
+        cf.set_tuning("wistft", -1)
+        cf.fft_destroy_setup(s)
+
+
 def test_istft_rejects_what_does_not_fit(cf):
     s = cf.fft_new_setup(32768, cf.FFT_REAL)
     try:

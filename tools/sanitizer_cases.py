@@ -66,7 +66,8 @@ cf.set_tuning("l2_chunk_mb", -1)
 cf.set_tuning("l2_lanes", -1)
 
 # STFT / ISTFT: wpipe_kernel + wistft_kernel (N = 2048, hop 512), stft_kernel / istft_kernel (other hops / sizes)
-for N, hop, frames, ch in [(2048, 512, 23, 3), (1024, 256, 17, 2), (512, 96, 11, 2), (4096, 1024, 9, 2)]:
+# (N = 512 hop 128 and N = 4096 hop 1024 synthesise through ristft_kernel, N = 512 hop 96 through istft_kernel)
+for N, hop, frames, ch in [(2048, 512, 23, 3), (1024, 256, 17, 2), (512, 96, 11, 2), (512, 128, 29, 5), (4096, 1024, 9, 2)]:
     s = cf.fft_new_setup(N, cf.FFT_REAL)
     samples = (frames - 1) * hop + N
     sig = rnd(ch * samples)
