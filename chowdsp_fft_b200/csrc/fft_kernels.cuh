@@ -1695,6 +1695,11 @@ FFT_HD void ristft_body (const FftArgs& a)
     {
         const bool valid = ! UNIFORM || (item_ok && ff >= 0 && ff < fe);
         const int f = valid ? ff : (fe - 1);
+#ifndef CFB_RISTFT_NO_PREFETCH
+        // the frames of an item are transformed strictly one after the other: ask L2 for the next one now (one line per thread)
+        if (ff + 1 < fe && ff + 1 >= 0)
+            prefetch_transform_l2<G> (spec + (long long) (ff + 1) * a.in_inner, j);
+#endif
         float2 v[R];
         fft_core<LOGM, R, C2R, LOGW, false, false, false, 0, NoHook, true> (spec + (long long) f * a.in_inner, nullptr, true, j, fb, a.tw, a.rtw, nullptr, nullptr, NoHook(), v);
         tsync<T, true>(); // the last exchange has been read by every thread of the transform: the next frame may write the region
