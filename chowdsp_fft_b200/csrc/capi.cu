@@ -521,7 +521,9 @@ bool pipe_enabled (int logM, int kind, int logW)
 // latency-bound too: 5.6-5.9 -> 6.3 TB/s); bits 8.. = warps per CTA (0 = as many as fit an SM).  Default from
 // profiles/r01_wpipe.txt: frames (and that one plain case) only -- their
 // re-reads are L2 hits, so fft_kernel is bound by the exposed load latency there (STFT config 4.81 -> 5.30 TB/s), while
-// plain batches already run at the HBM roofline with fft_kernel and lose 5..13 % to the landing-buffer round trip
+// plain batches already run at the HBM roofline with fft_kernel and lose 5..13 % to the landing-buffer round trip.  Bit 3: frames of the
+// 2^9-point size too -- off since the burst-mode re-measurement of round 2 (profiles/r02_stft_sizes.txt: N = 1024 frames 4.12 / 4.45 TB/s with /
+// without a window through wpipe_kernel<9,16>, 4.44 / 4.95 through stft_kernel / fft_kernel, at 64 .. 1024 channels)
 constexpr int kWPipeDefault = 2 | 4;
 int g_wpipe = kWPipeDefault;
 // tuning hook "wistft": bit 0 = overlap-add synthesis through the warp-pipelined kernel (wistft_kernel) where it applies;
@@ -1071,7 +1073,7 @@ int enqueue_transform (Plan* p, const float* in, float* out, int outer, int inne
     const long long frame_stride = inner > 1 ? in_inner : in_outer;
     const bool frames = window != nullptr || ((long long) outer * inner > 1 && frame_stride > 0 && frame_stride < row_floats);
     const bool unord_real_2048 = ! ordered && ! p->is_complex && p->logM == 10 && (long long) outer * inner >= 4096; // throughput batches only
-    const bool use_wpipe = ! use_pipe && ((g_wpipe & 1) != 0 || ((g_wpipe & 2) != 0 && frames) || ((g_wpipe & 4) != 0 && unord_real_2048)) && has_wpipe (p->logM, wpipe_radix) && direction == chowdsp::fft::FFT_FORWARD
+    const bool use_wpipe = ! use_pipe && ((g_wpipe & 1) != 0 || ((g_wpipe & 2) != 0 && frames && (p->logM == 10 || (g_wpipe & 8) != 0)) || ((g_wpipe & 4) != 0 && unord_real_2048)) && has_wpipe (p->logM, wpipe_radix) && direction == chowdsp::fft::FFT_FORWARD
                            && (reinterpret_cast<uintptr_t> (in) & 15) == 0 && (inner == 1 || (in_inner & 3) == 0) && (outer == 1 || (in_outer & 3) == 0);
     const int radix = use_pipe ? 32 : use_wpipe ? wpipe_radix : radix_for (p->logM, p->is_complex != 0);
     const int rc = plan_tables (p, t, radix);

@@ -169,8 +169,8 @@ void fft_b200_clear_error (void);
 /* Tuning hook for benchmarks / A-B sweeps (not needed in normal use; value -1 restores a key's built-in default where one exists):
      "radix32_mask" bit n (complex plans) / bit 16+n (real plans): 32 points per thread for complex length 2^n (n in 9, 10, 13, 14)
      "pipe_mask"    which kinds / layouts at complex length 2^13, 2^14 use the persistent TMA-pipelined kernel
-     "wpipe"        bit 1: overlapping / windowed frames of the sizes one warp owns use the warp-pipelined kernel (default), bit 0: every
-                    batch of those sizes; bits 8..: warps per CTA (0 = as many as fit)
+     "wpipe"        bit 1: overlapping / windowed frames of N = 2048 real transforms use the warp-pipelined kernel (default), bit 3: those of
+                    N = 1024 too (measured 8..11 % slower), bit 0: every batch of those sizes; bits 8..: warps per CTA (0 = as many as fit)
      "wistft"       bit 0: overlap-add synthesis through the warp-pipelined kernel where it applies (default); bits 8..: warps per CTA
      "stft_pipe", "stft_union"  older frame-gather variants (persistent CTA-level TMA union / LDS-STS union staging), off
      "tile_c", "tile_c_jfast"   transforms per tile of the multi-pass kernels (8, 16, or 0 = built-in policy)

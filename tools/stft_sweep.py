@@ -39,12 +39,12 @@ def timed(f):
 sizes = [int(a) for a in sys.argv[1:]] or [128, 256, 512, 1024, 2048, 4096, 8192]
 for N in sizes:
     hop = N // 4
-    channels = 256
+    channels = int(os.environ.get("STFT_CHANNELS", "256"))
     frames = max(8, (1 << 28) // (channels * N))  # about 1 GiB of spectra
     samples = (frames - 1) * hop + N
     s = cf.fft_new_setup(N, cf.FFT_REAL)
     sig = torch.rand(channels * samples, device="cuda") * 2 - 1
-    win = torch.hann_window(N, periodic=True, device="cuda").contiguous()
+    win = None if os.environ.get("STFT_NOWIN") else torch.hann_window(N, periodic=True, device="cuda").contiguous()
     spec = torch.empty(channels * frames * N, device="cuda")
     out = torch.empty(channels * samples, device="cuda")
     nbytes = 4 * (channels * samples + channels * frames * N)
