@@ -526,8 +526,8 @@ bool pipe_enabled (int logM, int kind, int logW)
 // without a window through wpipe_kernel<9,16>, 4.44 / 4.95 through stft_kernel / fft_kernel, at 64 .. 1024 channels)
 constexpr int kWPipeDefault = 2 | 4;
 int g_wpipe = kWPipeDefault;
-// tuning hook "wistft": bit 0 = overlap-add synthesis through the warp-pipelined kernel (wistft_kernel) where it applies;
-// bits 8.. = warps per CTA (0 = the kernel's maximum)
+// tuning hook "wistft": bit 0 = overlap-add synthesis through the warp-pipelined kernel (wistft_kernel) where it applies (N = 2048; bit 1: N = 1024
+// too); bits 8.. = warps per CTA (0 = the kernel's maximum)
 constexpr int kWIstftDefault = 1;
 int g_wistft = kWIstftDefault;
 int device_sm_count()
@@ -1747,7 +1747,8 @@ int istft_enqueue (Plan* p, const float* spectra, float* signal, int channels, i
     {
         const int wr = p->logM == 10 ? 32 : 16;
         const bool hop_ok = hop * 2 == p->N || hop * 4 == p->N || hop * 8 == p->N;
-        if ((g_wistft & 1) != 0 && ordered != 0 && has_wpipe (p->logM, wr) && hop_ok && (spec_frame_stride & 3) == 0 && (spec_channel_stride & 3) == 0
+        // (the 2^9-point size only with bit 1 of the hook: ristft_kernel measured 3..6 % faster there, profiles/r02_stft_sizes.txt)
+        if ((g_wistft & 1) != 0 && (p->logM == 10 || (g_wistft & 2) != 0) && ordered != 0 && has_wpipe (p->logM, wr) && hop_ok && (spec_frame_stride & 3) == 0 && (spec_channel_stride & 3) == 0
             && (reinterpret_cast<uintptr_t> (spectra) & 15) == 0 && (channel_stride & 1) == 0 && (reinterpret_cast<uintptr_t> (signal) & 7) == 0)
         {
             Tables wt;

@@ -171,7 +171,8 @@ void fft_b200_clear_error (void);
      "pipe_mask"    which kinds / layouts at complex length 2^13, 2^14 use the persistent TMA-pipelined kernel
      "wpipe"        bit 1: overlapping / windowed frames of N = 2048 real transforms use the warp-pipelined kernel (default), bit 3: those of
                     N = 1024 too (measured 8..11 % slower), bit 0: every batch of those sizes; bits 8..: warps per CTA (0 = as many as fit)
-     "wistft"       bit 0: overlap-add synthesis through the warp-pipelined kernel where it applies (default); bits 8..: warps per CTA
+     "wistft"       bit 0: overlap-add synthesis of ordered N = 2048 frames through the warp-pipelined kernel (default), bit 1: N = 1024 too;
+                    bits 8..: warps per CTA
      "stft_pipe", "stft_union"  older frame-gather variants (persistent CTA-level TMA union / LDS-STS union staging), off
      "tile_c", "tile_c_jfast"   transforms per tile of the multi-pass kernels (8, 16, or 0 = built-in policy)
      "spin_sync"    1 = small synchronous drop-in calls wait on a stream-written word in mapped memory instead of

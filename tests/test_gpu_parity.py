@@ -387,7 +387,7 @@ def test_warp_pipelined_istft(cf, oracle_mod, N, hop, frames, channels, warps):
     s = cf.fft_new_setup(N, cf.FFT_REAL)
     spec = np.ascontiguousarray(o.np_transform(x, N, False, 8, False, True).reshape(channels, frames, N))
     dspec, dw = dev(spec), dev(win)
-    cf.set_tuning("wistft", 1 | (warps << 8))
+    cf.set_tuning("wistft", 3 | (warps << 8))  # bit 1: the 2^9-point size too (it goes to ristft_kernel by default)
     try:
         for w in (None, dw):
             out = torch.full((channels, samples + 6), float("nan"), device="cuda")
@@ -437,7 +437,7 @@ def test_register_overlap_add_istft(cf, oracle_mod, N, hop, frames, channels):
                 cf.fft_istft_overlap_add(s, dspec, out, channels, frames, frames * N, N, samples + 6, hop, w, 1.0 / N, ordered)
                 torch.cuda.synchronize()
                 assert cf.launch_count() - n0 == 1
-                if not (ordered and N in (1024, 2048)):
+                if not (ordered and N == 2048):
                     assert "ristft_kernel" in cf.last_kernel(), cf.last_kernel()
                 got = host(out)
                 assert np.all(np.isnan(got[:, samples:])) and not np.any(np.isnan(got[:, :samples]))
