@@ -1,5 +1,5 @@
 #!/bin/bash
-# Regenerates the round's evidence in ONE gpurun call (about 12 minutes on one B200):
+# Regenerates the round's evidence in ONE gpurun call (about 14 minutes on one B200):
 #   gpurun --timeout 1800 -- bash tools/gpu_refresh.sh <tag>      then      python tools/collect_profiles.py <tag> r02
 # GPU parity suite, smoke, the default bench line (every BASELINE config as a sub-record, e2e + cpu_baseline), the reference arm, the
 # size sweeps, the ncu launch list of the default command and one ncu --set full capture per dominant kernel.
@@ -20,6 +20,8 @@ done
 echo "== sweep sizes"; timeout 1500 python tools/sweep.py --bytes 2 --steps 20 --pause 1.0 --repeats 3 --json $OUT/sweep_sizes.json 2>&1 | grep -E "C2C|R2C|C2R" | tee $OUT/sweep_sizes.txt
 echo "== sweep sustained (back to back, no pause)"; timeout 600 python tools/sweep.py --bytes 2 --steps 20 --sizes 1024,2048,4096,8192,16384 --layouts ordered,w8 2>&1 | grep -E "C2C|R2C|C2R" | tee $OUT/sweep_sustained.txt
 echo "== sweep mixed"; timeout 900 python tools/sweep.py --sizes 96,160,192,288,384,480,640,768,1920,2560,9216,12288 --bytes 2 --pause 0.5 --repeats 2 --layouts ordered,w8 2>&1 | grep -E "C2C|R2C|C2R" | tee $OUT/sweep_mixed_radix.txt
+echo "== sweep stft / istft / mac over frame sizes"; timeout 600 python tools/stft_sweep.py 2>&1 | grep "N=" | tee $OUT/sweep_stft.txt
+echo "== sweep partitioned convolution over block sizes"; timeout 600 python tools/pconv_sweep.py 16 2>&1 | grep pconv | tee $OUT/sweep_pconv.txt
 echo "== sweep large"; timeout 600 python tools/large_sweep.py 15 16 17 18 20 22 24 26 28 2>&1 | tee $OUT/sweep_large.txt
 echo "== pcie"; timeout 300 python tools/pcie_probe.py 2>&1 | tee $OUT/pcie_ceiling.txt
 echo "== ncu launch list (default command, headline only)"
