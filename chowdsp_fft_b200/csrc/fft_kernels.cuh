@@ -1730,8 +1730,11 @@ FFT_HD void ristft_body (const FftArgs& a)
         }
     }
 }
+#ifndef CFB_RISTFT_MINB
+#define CFB_RISTFT_MINB 2 // A/B switch (tools/ only): resident CTAs per SM the register budget of ristft_kernel is sized for
+#endif
 template <int LOGM, int HQ, int LOGW>
-__global__ void __launch_bounds__ (Launch<LOGM, 16>::THREADS, 2) ristft_kernel (const FftArgs a)
+__global__ void __launch_bounds__ (Launch<LOGM, 16>::THREADS, CFB_RISTFT_MINB) ristft_kernel (const FftArgs a)
 {
     ristft_body<LOGM, HQ, LOGW> (a);
 }
