@@ -34,7 +34,10 @@ def test_kernel_source_has_no_shared_memory_races(tmp_path):
     log = str(tmp_path / "tsan")
     env = dict(os.environ, CFB_EMU_DEFINES="-fsanitize=thread -g", LD_PRELOAD=tsan,
                TSAN_OPTIONS=f"halt_on_error=0 report_signal_unsafe=0 history_size=2 exitcode=0 log_path={log}")
-    sel = "warp_pipelined or pipelined or persistent_stft or (match_oracle and 1024)"
+    # round 2: plus a slice of the new kernels (staged small-transform kernel, register overlap-add synthesis, Q x 2^p mixed radix, multi-channel
+    # partitioned convolution); the full set of their emulator tests was run under ThreadSanitizer once and is clean (38 tests, 2 minutes)
+    sel = ("warp_pipelined or pipelined or persistent_stft or (match_oracle and 1024) or small_kernel or (register_overlap and 512) "
+           "or (mixq and 96) or (partitioned and 32)")
     r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_emu_kernels.py", "-x", "-q", "-p", "no:cacheprovider", "-k", sel],
                        cwd=ROOT, env=env, capture_output=True, text=True, timeout=1400)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
