@@ -136,17 +136,20 @@ FFT_HD float4 ldg_stream (const float4* p)
 #endif
 }
 
-// input loads of fft_core: streaming (no L1 allocation) when the T threads of a transform cover whole 32-byte sectors with
-// every load instruction; transforms owned by one or two threads (16 / 32 complex points) touch every sector with two or four
-// different instructions, so there the first touch allocates the line in L1 and the others hit (no_allocate would fetch the
-// sector from L2 each time: ncu l1tex sectors 2-4x the algorithmic figure)
+// input loads of fft_core: streaming (no L1 allocation) when the T threads of a transform cover a whole 128-byte line with every load
+// instruction (T >= 16); with fewer threads per transform every line is touched by 2 .. 16 different instructions of the warp, so there
+// the first touch allocates the line in L1 and the others hit instead of going to L2 again (one or two threads per transform even
+// split 32-byte sectors: ncu l1tex sectors 2-4x the algorithmic figure with no_allocate)
 template <int T>
 FFT_HD float2 ldg_in (const float2* p)
 {
 #if defined(CHOWDSP_EMU) || defined(CFB_NO_CACHED_SMALL_LOADS)
     return ldg_stream (p);
 #else
-    if constexpr (T <= 2)
+#ifndef CFB_CACHED_LOADS_MAX_T
+#define CFB_CACHED_LOADS_MAX_T 8 // burst-mode A/B on B200 (profiles/r02_retune.txt): up to 8 threads per transform +1..13 %, nothing beyond
+#endif
+    if constexpr (T <= CFB_CACHED_LOADS_MAX_T)
         return __ldg (p);
     else
         return ldg_stream (p);
