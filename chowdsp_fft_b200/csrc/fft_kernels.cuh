@@ -156,6 +156,19 @@ FFT_HD float2 ldg_in (const float2* p)
 #endif
 }
 
+template <int T>
+FFT_HD float4 ldg_in (const float4* p)
+{
+#if defined(CHOWDSP_EMU) || defined(CFB_NO_CACHED_SMALL_LOADS)
+    return ldg_stream (p);
+#else
+    if constexpr (T <= CFB_CACHED_LOADS_MAX_T)
+        return __ldg (p);
+    else
+        return ldg_stream (p);
+#endif
+}
+
 // ask L2 for the 128-byte lines of one transform's input (M complex = M/16 lines, R/16 per thread)
 template <class G>
 FFT_HD void prefetch_transform_l2 (const float* p, int j)
@@ -853,7 +866,7 @@ FFT_HD void staging_fill (float* sf, const float* __restrict__ in, int j, int lo
     for (int i = 0; i < G::R / 2; ++i)
     {
         const int q = j + i * G::T;
-        const float4 val = ldg_stream (reinterpret_cast<const float4*> (in) + q);
+        const float4 val = ldg_in<2 * G::T> (reinterpret_cast<const float4*> (in) + q); // 16 bytes per thread: whole lines from 8 threads on
         sts4 (sf + upad (4 * q, logW), val);
     }
 }
@@ -973,7 +986,7 @@ FFT_HD void fft_core (const float* __restrict__ in, float* __restrict__ out, boo
 #pragma unroll
         for (int m = 0; m < R; ++m)
         {
-            const float2 ld = ldg_stream (reinterpret_cast<const float2*> (ib + (m % ULT) * (T / UW) * 2 * UW * UW + (m / ULT) * 2 * UW));
+            const float2 ld = ldg_in<T> (reinterpret_cast<const float2*> (ib + (m % ULT) * (T / UW) * 2 * UW * UW + (m / ULT) * 2 * UW));
             const float recv = shfl1 (u_odd ? ld.x : ld.y, (j ^ 1) & (SW - 1), SW);
             v[m] = u_odd ? make_float2 (recv, ld.y) : make_float2 (ld.x, recv);
         }
